@@ -1,0 +1,27 @@
+"""Named parity cases shared by the golden generator, the oracle tests and the GPU parity tests."""
+
+FULL = dict(image_size=160, image_patch_size=16, frames=120, frame_patch_size=12)   # configs/gaviko.yaml:14-17
+SMALL = dict(image_size=64, image_patch_size=16, frames=48, frame_patch_size=12)    # 4x4x4 = 64 tokens
+
+GAVIKO_CASES = {
+    # name: (ctor kwargs, batch)
+    'gaviko_t16_full': (dict(FULL, num_classes=5, channels=1, freeze_vit=True, pool='cls', backbone='vit-t16',
+                             num_prompts=32, prompt_latent_dim=20, local_dim=20, local_k=[6, 6, 6], DHW=[10, 10, 10],
+                             dropout=0.0, emb_dropout=0.0, attn_drop=0.0, proj_drop=0.0, share_factor=1, fp16=False), 2),
+    'gaviko_t16_small': (dict(SMALL, num_classes=5, channels=1, freeze_vit=True, pool='cls', backbone='vit-t16',
+                              num_prompts=8, prompt_latent_dim=20, local_dim=20, local_k=[3, 2, 2], DHW=[4, 4, 4],
+                              dropout=0.0, emb_dropout=0.0, attn_drop=0.0, proj_drop=0.0, share_factor=2, fp16=False), 3),
+}
+
+VARIANT_CASES = {
+    # name: (method, ctor kwargs, batch)
+    'linear_t16_small': ('linear', dict(SMALL, num_classes=5, channels=1, pool='cls', backbone='vit-t16', dropout=0.0, emb_dropout=0.0), 2),
+    'bitfit_t16_small': ('bitfit', dict(SMALL, num_classes=5, channels=1, pool='cls', backbone='vit-t16', dropout=0.0, emb_dropout=0.0), 2),
+    'adaptformer_t16_small': ('adaptformer', dict(SMALL, num_classes=5, channels=1, pool='cls', backbone='vit-t16', dropout=0.0, emb_dropout=0.0, freeze_vit=True), 2),
+    'melo_t16_small': ('melo', dict(SMALL, num_classes=5, channels=1, pool='cls', backbone='vit-t16', dropout=0.0, emb_dropout=0.0, r=4, alpha=8), 2),
+    'ssf_t16_small': ('ssf', dict(SMALL, num_classes=5, channels=1, pool='cls', backbone='vit-t16', dropout=0.0, emb_dropout=0.0, freeze_vit=True), 2),
+    'shallow_vpt_t16_small': ('shallow_vpt', dict(SMALL, num_classes=5, channels=1, pool='cls', backbone='vit-t16', dropout=0.0, emb_dropout=0.0,
+                                                  freeze_vit=True, prompt_dropout=0.0, prompt_dim=16, num_prompts=4, deep_prompt=False), 2),
+    'deep_vpt_t16_small': ('deep_vpt', dict(SMALL, num_classes=5, channels=1, pool='cls', backbone='vit-t16', dropout=0.0, emb_dropout=0.0,
+                                            freeze_vit=True, prompt_dropout=0.0, prompt_dim=6, num_prompts=4, deep_prompt=True), 2),
+}

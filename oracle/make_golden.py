@@ -1,0 +1,114 @@
+"""Generate tests/golden/*.npz by running the UNMODIFIED reference in this container (CPU, fp32).
+
+    python -m oracle.make_golden
+
+Weights come from ``oracle.golden_fill`` (name/shape-deterministic), inputs from ``golden_volume`` /
+``golden_labels``; the files hold only outputs: logits, focal + CE loss, and every trainable gradient
+under both losses.  TEST INFRASTRUCTURE ONLY.
+"""
+import os
+import tempfile
+
+import numpy as np
+import torch
+
+from . import refload
+from .cases import GAVIKO_CASES, VARIANT_CASES
+from .golden_fill import golden_fill, golden_labels, golden_volume
+
+OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'tests', 'golden')
+
+
+def build_variant(ref, method, kw):
+    if method in ('linear', 'bitfit'):
+        m = ref.VisionTransformer(**kw)
+        for k, v in m.named_parameters():                   # train.py:114-137
+            if method == 'linear':
+                v.requires_grad = 'head' in k
+            else:
+                v.requires_grad = ('bias' in k) or ('head' in k)
+        return m
+    if method == 'adaptformer':
+        return ref.AdaptFormer(**kw)
+    if method == 'ssf':
+        return ref.ScalingShiftingFeatures(**kw)
+    if method == 'melo':
+        return ref.MeLO(vit=ref.VisionTransformer(**kw), **kw)   # train.py:145-147
+    if method in ('deep_vpt', 'shallow_vpt'):
+        return ref.PromptedVisionTransformer(**kw)
+    raise ValueError(method)
+
+
+def run_case(ref, model, kw, batch, name):
+    golden_fill(model, seed=0)
+    model.eval()
+    img = golden_volume(batch, kw['frames'], kw['image_size'], kw['image_size'], channels=kw['channels'])
+    y = golden_labels(batch, kw['num_classes'])
+    out = {}
+    names = [n for n, p in model.named_parameters() if p.requires_grad]
+    out['trainable_names'] = np.array(names)
+    out['all_names'] = np.array([n for n, _ in model.named_parameters()])
+    out['all_shapes'] = np.array([str(tuple(p.shape)) for _, p in model.named_parameters()])
+    out['state_dict_keys'] = np.array(list(model.state_dict().keys()))
+    for loss_name, crit in (('focal', ref.FocalLoss(gamma=1.2)), ('ce', torch.nn.CrossEntropyLoss())):
+        model.zero_grad(set_to_none=True)
+        logits = model(img)
+        loss = crit(logits, y)
+        loss.backward()
+        out['logits'] = logits.detach().numpy()
+        out[f'loss_{loss_name}'] = loss.detach().numpy()
+        for n, p in model.named_parameters():
+            if p.requires_grad:
+                assert p.grad is not None, (name, n)
+                out[f'grad_{loss_name}/{n}'] = p.grad.detach().numpy().copy()
+    np.savez_compressed(os.path.join(OUT, name + '.npz'), **out)
+    print(name, 'logits', out['logits'][0], 'focal', float(out['loss_focal']), 'ce', float(out['loss_ce']), 'trainable', len(names))
+
+
+def focal_known_answers(ref):
+    g = torch.Generator().manual_seed(5)
+    cases = {}
+    for i, (b, c, scale, shift) in enumerate([(7, 5, 1.0, 0.0), (4, 5, 0.3, 0.5), (6, 3, 4.0, 0.0), (5, 5, 0.2, 0.4)]):
+        z = (torch.randn(b, c, generator=g) * scale + shift).requires_grad_(True)
+        y = torch.randint(0, c, (b,), generator=g)
+        if i == 2:
+            y[1] = -100                                   # ignore_index path, focal_loss.py:101-108
+        loss = ref.FocalLoss(gamma=1.2)(z, y)
+        loss.backward()
+        cases[f'z{i}'] = z.detach().numpy()
+        cases[f'y{i}'] = y.numpy()
+        cases[f'loss{i}'] = loss.detach().numpy()
+        cases[f'dz{i}'] = z.grad.numpy()
+    np.savez_compressed(os.path.join(OUT, 'focal_known_answers.npz'), **cases)
+
+
+def window_masks(ref):
+    out = {}
+    for i, (dhw, k) in enumerate([((10, 10, 10), (6, 6, 6)), ((10, 10, 10), (3, 6, 6)), ((4, 4, 4), (3, 2, 2)), ((5, 4, 3), (5, 4, 2))]):
+        m = ref.gaviko.LocalSelfAttention(32, local_k=k, DHW=dhw).mask[0]
+        out[f'dhw{i}'] = np.array(dhw)
+        out[f'k{i}'] = np.array(k)
+        out[f'allow{i}'] = np.packbits((m == 0).numpy())
+    np.savez_compressed(os.path.join(OUT, 'window_masks.npz'), **out)
+
+
+def main():
+    torch.manual_seed(0)
+    torch.set_num_threads(os.cpu_count())
+    os.makedirs(OUT, exist_ok=True)
+    ref = refload.load()
+    cwd = os.getcwd()
+    os.chdir(tempfile.mkdtemp())       # vpt.py:54 appends deep_prompt.txt to the cwd
+    try:
+        focal_known_answers(ref)
+        window_masks(ref)
+        for name, (kw, batch) in GAVIKO_CASES.items():
+            run_case(ref, ref.Gaviko(**kw), kw, batch, name)
+        for name, (method, kw, batch) in VARIANT_CASES.items():
+            run_case(ref, build_variant(ref, method, kw), kw, batch, name)
+    finally:
+        os.chdir(cwd)
+
+
+if __name__ == '__main__':
+    main()

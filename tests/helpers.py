@@ -1,0 +1,72 @@
+"""Shared test helpers (golden loading, error metrics)."""
+import ast
+import os
+
+import numpy as np
+import torch
+
+from oracle.golden_fill import golden_fill
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
+
+
+def load_golden(name):
+    return np.load(os.path.join(GOLDEN, name + '.npz'), allow_pickle=False)
+
+
+def sd_from_golden(g, requires_grad=True):
+    """Rebuild the golden weights from parameter names/shapes alone (oracle/golden_fill.py)."""
+    sd = {}
+    for n, s in zip(g['all_names'].tolist(), g['all_shapes'].tolist()):
+        sd[n] = torch.zeros(ast.literal_eval(s), dtype=torch.float32)
+    golden_fill(sd, seed=0)
+    if requires_grad:
+        tn = set(g['trainable_names'].tolist())
+        for n in sd:
+            if n in tn:
+                sd[n].requires_grad_(True)
+    return sd
+
+
+def rel_l2(a, b):
+    a = torch.as_tensor(a, dtype=torch.float64).flatten()
+    b = torch.as_tensor(b, dtype=torch.float64).flatten()
+    den = b.norm().item()
+    return (a - b).norm().item() / (den if den > 0 else 1.0)
+
+
+def grad_parity(got, g, loss_name, tol_global, tol_tensor, floor=1e-4):
+    """Compare a {name: grad} dict against golden gradients.
+
+    Per tensor: rel-L2 <= tol_tensor, except tensors whose reference norm is below ``floor`` x the global
+    gradient norm, which are cancellation-dominated (the reference itself only reproduces them to ~4e-4 in
+    fp32 under a different summation order) and are held to an absolute bound
+    ||diff|| <= tol_tensor * floor * ||all grads|| instead.  Globally: rel-L2 over the concatenation <= tol_global.
+    Returns (global_rel, worst_tensor_rel, worst_name).
+    """
+    names = g['trainable_names'].tolist()
+    num = den = 0.0
+    for n in names:
+        r = g[f'grad_{loss_name}/{n}'].astype(np.float64)
+        den += float((r ** 2).sum())
+    gnorm = den ** 0.5
+    worst, worst_name = 0.0, None
+    for n in names:
+        r = g[f'grad_{loss_name}/{n}'].astype(np.float64)
+        assert n in got and got[n] is not None, f'missing gradient for {n}'
+        a = torch.as_tensor(got[n]).detach().double().cpu().numpy()
+        assert a.shape == r.shape, (n, a.shape, r.shape)
+        assert np.isfinite(a).all(), f'non-finite gradient in {n}'
+        d = float(np.linalg.norm(a - r))
+        num += d * d
+        rn = float(np.linalg.norm(r))
+        if rn <= floor * gnorm:
+            assert d <= tol_tensor * floor * gnorm + 1e-30, (loss_name, n, d, rn, gnorm)
+        else:
+            rel = d / rn
+            if rel > worst:
+                worst, worst_name = rel, n
+            assert rel <= tol_tensor, (loss_name, n, rel)
+    glob = (num ** 0.5) / (gnorm if gnorm > 0 else 1.0)
+    assert glob <= tol_global, (loss_name, 'global', glob)
+    return glob, worst, worst_name

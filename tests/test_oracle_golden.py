@@ -1,0 +1,76 @@
+"""CPU: the oracle restatement reproduces the live reference's outputs (tests/golden, oracle/make_golden.py)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import gaviko_oracle as O
+from oracle.cases import GAVIKO_CASES, VARIANT_CASES
+from oracle.golden_fill import golden_labels, golden_volume
+
+from helpers import grad_parity, load_golden, rel_l2, sd_from_golden
+
+TOL = 2e-5   # fp32 noise floor of the reference itself is <=6.5e-6 per tensor
+
+
+def _check(g, sd, logits_fn, kw, batch):
+    img = golden_volume(batch, kw['frames'], kw['image_size'], kw['image_size'], channels=kw['channels'])
+    y = golden_labels(batch, kw['num_classes'])
+    for loss_name, fn in (('focal', O.focal_loss), ('ce', O.cross_entropy)):
+        for t in sd.values():
+            t.grad = None
+        logits = logits_fn(sd, img)
+        loss = fn(logits, y)
+        loss.backward()
+        assert rel_l2(logits.detach(), g['logits']) < TOL
+        assert abs(loss.item() - float(g[f'loss_{loss_name}'])) < 1e-5
+        grad_parity({n: sd[n].grad for n in g['trainable_names'].tolist()}, g, loss_name, tol_global=2e-5, tol_tensor=1e-3)
+
+
+@pytest.mark.parametrize('name', list(GAVIKO_CASES))
+def test_gaviko_oracle_matches_reference(name):
+    kw, batch = GAVIKO_CASES[name]
+    g = load_golden(name)
+    sd = sd_from_golden(g)
+    fn = lambda sd, img: O.gaviko_forward(sd, img, backbone=kw['backbone'], num_prompts=kw['num_prompts'],
+                                          frame_patch_size=kw['frame_patch_size'], image_patch_size=kw['image_patch_size'],
+                                          local_k=kw['local_k'], DHW=kw['DHW'], share_factor=kw['share_factor'])
+    _check(g, sd, fn, kw, batch)
+
+
+@pytest.mark.parametrize('name', list(VARIANT_CASES))
+def test_variant_oracle_matches_reference(name):
+    method, kw, batch = VARIANT_CASES[name]
+    g = load_golden(name)
+    sd = sd_from_golden(g)
+    common = dict(backbone=kw['backbone'], frame_patch_size=kw['frame_patch_size'], image_patch_size=kw['image_patch_size'], pool=kw['pool'])
+    if method in ('linear', 'bitfit'):
+        fn = lambda sd, img: O.vit_forward(sd, img, **common)
+    elif method == 'adaptformer':
+        fn = lambda sd, img: O.adaptformer_forward(sd, img, **common)
+    elif method == 'melo':
+        fn = lambda sd, img: O.melo_forward(sd, img, r=kw['r'], alpha=kw['alpha'], **common)
+    elif method == 'ssf':
+        fn = lambda sd, img: O.ssf_forward(sd, img, **common)
+    else:
+        fn = lambda sd, img: O.vpt_forward(sd, img, deep_prompt=kw['deep_prompt'], **common)
+    _check(g, sd, fn, kw, batch)
+
+
+def test_focal_known_answers():
+    g = load_golden('focal_known_answers')
+    for i in range(4):
+        z = torch.tensor(g[f'z{i}'], requires_grad=True)
+        y = torch.tensor(g[f'y{i}'])
+        loss = O.focal_loss(z, y)
+        loss.backward()
+        assert loss.item() == pytest.approx(float(g[f'loss{i}']), rel=1e-6)
+        np.testing.assert_allclose(z.grad.numpy(), g[f'dz{i}'], rtol=1e-5, atol=1e-8)
+
+
+def test_window_mask_formula():
+    g = load_golden('window_masks')
+    for i in range(4):
+        allow = O.window_allow(tuple(g[f'dhw{i}']), tuple(g[f'k{i}']))
+        assert np.array_equal(np.packbits(allow.numpy()), g[f'allow{i}'])
+    a = O.window_allow((10, 10, 10), (6, 6, 6))
+    assert int(a.sum()) == 132651 and int(a.sum(1).min()) == 27 and int(a.sum(1).max()) == 216
