@@ -1,0 +1,98 @@
+// gvk_api.cu — C-ABI entry points (include/gvk.h) and host-side plumbing shared by the kernels.
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+
+#include "gvk_common.cuh"
+
+namespace gvk {
+
+static thread_local char g_err[512] = "";
+static std::atomic<uint64_t> g_launches{0};
+
+void set_last_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+void note_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+
+int cuda_status(cudaError_t e, const char* what) {
+  if (e == cudaSuccess) return GVK_OK;
+  set_last_error("%s: %s", what, cudaGetErrorString(e));
+  return GVK_ERR_CUDA;
+}
+
+int sm_count() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+  }
+  return n;
+}
+
+// cuTensorMapEncodeTiled resolved through the runtime so that the library has no link-time libcuda dependency
+// (it must load, and export its symbols, on a machine without a GPU driver).
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess && qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  });
+  return fn;
+}
+
+static int encode_bf16(CUtensorMap* out, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes, const cuuint32_t* box) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) {
+    set_last_error("cuTensorMapEncodeTiled is unavailable (no CUDA driver?)");
+    return GVK_ERR_NO_DEVICE;
+  }
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, const_cast<void*>(base), dims, strides_bytes, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_last_error("cuTensorMapEncodeTiled failed (CUresult %d): rank %d dims [%llu,%llu,%llu] box [%u,%u,%u]", (int)r, rank, (unsigned long long)dims[0],
+                   (unsigned long long)dims[1], (unsigned long long)(rank > 2 ? dims[2] : 0), box[0], box[1], rank > 2 ? box[2] : 0);
+    return GVK_ERR_CUDA;
+  }
+  return GVK_OK;
+}
+
+int make_tma_2d_bf16(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld_elems, uint32_t box_rows, uint32_t box_cols) {
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {ld_elems * 2};
+  cuuint32_t box[2] = {box_cols, box_rows};
+  return encode_bf16(out, base, 2, dims, strides, box);
+}
+
+int make_tma_3d_bf16(CUtensorMap* out, const void* base, uint64_t d2, uint64_t rows, uint64_t cols, uint64_t ld_row_elems, uint64_t ld_d2_elems,
+                     uint32_t box_rows, uint32_t box_cols) {
+  cuuint64_t dims[3] = {cols, rows, d2};
+  cuuint64_t strides[2] = {ld_row_elems * 2, ld_d2_elems * 2};
+  cuuint32_t box[3] = {box_cols, box_rows, 1};
+  return encode_bf16(out, base, 3, dims, strides, box);
+}
+
+int gemm_dispatch(const gvk_gemm_params* p, cudaStream_t stream);
+
+}  // namespace gvk
+
+extern "C" {
+
+const char* gvk_last_error(void) { return gvk::g_err; }
+int gvk_version(void) { return 100; }
+uint64_t gvk_launch_count(void) { return gvk::g_launches.load(); }
+
+int gvk_gemm(const gvk_gemm_params* p, gvk_stream_t stream) { return gvk::gemm_dispatch(p, reinterpret_cast<cudaStream_t>(stream)); }
+
+}  // extern "C"

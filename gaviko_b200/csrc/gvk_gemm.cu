@@ -1,0 +1,349 @@
+// gvk_gemm.cu — dense TN GEMM with fused epilogue (see include/gvk.h: gvk_gemm).
+//
+//  * bf16 path: persistent, warp-specialised tcgen05 kernel.  TMA (SWIZZLE_128B) feeds a 4..6-stage smem ring, one elected
+//    thread issues tcgen05.mma (UMMA 128 x BN x 16, fp32 accumulators in TMEM, double-buffered so the epilogue of tile i
+//    overlaps the main loop of tile i+1), eight epilogue warps drain TMEM with tcgen05.ld, transpose through a private
+//    smem patch so that every global access of the fused epilogue is row-contiguous.
+//  * fp32 path: exact FFMA kernel with the same epilogue (the "fp32 mode" used for 1e-4 parity).
+//
+// Replaces the nn.Linear / Conv3d-as-GEMM calls of the reference (model/vision_transformer.py:31-35,53-58,
+// model/gaviko.py:383-385) and their dgrad counterparts in autograd.
+#include <algorithm>
+
+#include "gvk_common.cuh"
+
+namespace gvk {
+
+struct EpiArgs {
+  const float* bias;
+  const float* ssf_scale;
+  const float* ssf_shift;
+  int act;
+  void* aux;
+  int aux_dtype;
+  int ld_aux;
+  const float* pos;
+  int rows_per_batch;
+  int out_batch_rows;
+  int out_row_offset;
+  const float* res1;
+  int ld_res1;
+  const float* res2;
+  int ld_res2;
+  void* out;
+  int out_dtype;
+  int ld_out;
+  float* out2;
+  int ld_out2;
+  int N;
+};
+
+// Per-column constants of the epilogue, loaded once per (lane, column).
+struct EpiCol {
+  float bias, sc, sh;
+};
+__device__ __forceinline__ EpiCol epi_col(const EpiArgs& e, int n, bool valid) {
+  EpiCol c;
+  c.bias = (e.bias && valid) ? e.bias[n] : 0.f;
+  c.sc = (e.ssf_scale && valid) ? e.ssf_scale[n] : 1.f;
+  c.sh = (e.ssf_shift && valid) ? e.ssf_shift[n] : 0.f;
+  return c;
+}
+__device__ __forceinline__ void epi_elem(const EpiArgs& e, int m, int n, float v, const EpiCol& c) {
+  v += c.bias;
+  if (e.ssf_scale) v = v * c.sc + c.sh;
+  if (e.act == GVK_ACT_GELU) {
+    if (e.aux) st_dyn(e.aux, (size_t)m * e.ld_aux + n, e.aux_dtype, v);
+    v = gelu_erf(v);
+  } else if (e.act == GVK_ACT_GELU_BWD) {
+    v *= gelu_erf_grad(ld_dyn(e.aux, (size_t)m * e.ld_aux + n, e.aux_dtype));
+  }
+  int orow = m;
+  if (e.rows_per_batch > 0) {
+    const int b = m / e.rows_per_batch;
+    const int r = m - b * e.rows_per_batch;
+    if (e.pos) v += e.pos[(size_t)r * e.N + n];
+    orow = b * e.out_batch_rows + e.out_row_offset + r;
+  }
+  if (e.res1) v += e.res1[(size_t)m * e.ld_res1 + n];
+  if (e.res2) v += e.res2[(size_t)m * e.ld_res2 + n];
+  st_dyn(e.out, (size_t)orow * e.ld_out + n, e.out_dtype, v);
+  if (e.out2) e.out2[(size_t)m * e.ld_out2 + n] = v;
+}
+
+// =================================================================================================
+// tcgen05 kernel
+// =================================================================================================
+constexpr int kBM = 128;
+constexpr int kBK = 64;
+constexpr int kEpiWarps = 8;
+constexpr int kGemmThreads = 128 + kEpiWarps * 32;
+constexpr int kEpiPatch = 32 * 33;  // floats per epilogue warp
+
+template <int BN, int STAGES>
+struct GemmSmem {
+  static constexpr int kABytes = kBM * kBK * 2;
+  static constexpr int kBBytes = BN * kBK * 2;
+  static constexpr int kRing = STAGES * (kABytes + kBBytes);
+  static constexpr int kEpi = kEpiWarps * kEpiPatch * 4;
+  static constexpr int kBars = (2 * STAGES + 4) * 8 + 16;
+  static constexpr int kTotal = kRing + kEpi + kBars + 1024;  // +1024: manual alignment slack
+};
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_bf16_sm100_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, EpiArgs e, int M, int N, int K) {
+  using L = GemmSmem<BN, STAGES>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + STAGES * L::kABytes;
+  float* epi_patch = reinterpret_cast<float*>(smem + L::kRing);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::kRing + L::kEpi);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tfull_bar = empty_bar + STAGES;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  constexpr uint32_t kTmemCols = 2 * BN;  // 256 or 512: power of two
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tma_a);
+    tma_prefetch_desc(&tma_b);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tfull_bar[s], 1);
+      mbar_init(&tempty_bar[s], kEpiWarps);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_slot, kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int num_m = (M + kBM - 1) / kBM;
+  const int num_n = (N + BN - 1) / BN;
+  const int num_tiles = num_m * num_n;
+  const int num_kb = K / kBK;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===== TMA producer =====
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+        const int m_blk = t / num_n, n_blk = t % num_n;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          mbar_arrive_expect_tx(&full_bar[stage], L::kABytes + L::kBBytes);
+          tma_load_2d(sA + stage * L::kABytes, &tma_a, &full_bar[stage], kb * kBK, m_blk * kBM);
+          tma_load_2d(sB + stage * L::kBBytes, &tma_b, &full_bar[stage], kb * kBK, n_blk * BN);
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ===== MMA issuer =====
+      constexpr uint32_t idesc = make_idesc_bf16(kBM, BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int lt = 0;
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++lt) {
+        const int as = lt & 1;
+        const uint32_t aphase = (lt >> 1) & 1;
+        mbar_wait(&tempty_bar[as], aphase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + as * BN;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(sA + stage * L::kABytes);
+          const uint32_t b_addr = smem_u32(sB + stage * L::kBBytes);
+#pragma unroll
+          for (int k = 0; k < kBK / 16; ++k) {
+            const uint64_t adesc = make_sw128_desc(a_addr + k * 32, 16, 1024);
+            const uint64_t bdesc = make_sw128_desc(b_addr + k * 32, 16, 1024);
+            umma_bf16(d_tmem, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);  // frees the smem slot once the MMAs above have read it
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        umma_commit(&tfull_bar[as]);  // accumulator complete -> epilogue
+      }
+    }
+  } else if (warp >= 4) {
+    // ===== epilogue: TMEM -> regs -> private smem transpose -> fused elementwise -> global =====
+    const int ew = warp - 4;
+    const int q = warp & 3;   // TMEM lane group this warp may access
+    const int h = ew >> 2;    // column half
+    float* patch = epi_patch + ew * kEpiPatch;
+    int lt = 0;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++lt) {
+      const int m_blk = t / num_n, n_blk = t % num_n;
+      const int as = lt & 1;
+      const uint32_t aphase = (lt >> 1) & 1;
+      mbar_wait(&tfull_bar[as], aphase);
+      tc_fence_after();
+      const int row0 = m_blk * kBM + q * 32;
+#pragma unroll 1
+      for (int c = 0; c < BN / 64; ++c) {
+        const int colt = h * (BN / 2) + c * 32;
+        const int col0 = n_blk * BN + colt;
+        if (col0 < N && row0 < M) {  // warp-uniform
+          float v[32];
+          tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN + colt, v);
+          tc_wait_ld();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) patch[lane * 33 + j] = v[j];
+          __syncwarp();
+          const int n = col0 + lane;
+          const bool nvalid = n < N;
+          const EpiCol ec = epi_col(e, n, nvalid);
+          const int rmax = min(32, M - row0);
+          if (nvalid) {
+#pragma unroll 4
+            for (int r = 0; r < rmax; ++r) epi_elem(e, row0 + r, n, patch[r * 33 + lane], ec);
+          }
+          __syncwarp();
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[as]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem_base, kTmemCols);
+}
+
+// =================================================================================================
+// exact fp32 FFMA kernel (64x64x16 tiles, 4x4 micro-tiles)
+// =================================================================================================
+__global__ void __launch_bounds__(256) gemm_f32_kernel(const float* __restrict__ A, const float* __restrict__ B, int lda, int ldb, EpiArgs e,
+                                                         int M, int N, int K) {
+  __shared__ float sA[16][64 + 4];
+  __shared__ float sB[16][64 + 4];
+  const int tid = threadIdx.x;
+  const int tx = tid & 15, ty = tid >> 4;
+  const int m0 = blockIdx.y * 64, n0 = blockIdx.x * 64;
+  const int lr = tid >> 2;         // 0..63 row inside tile
+  const int lk = (tid & 3) * 4;    // 0,4,8,12
+  float acc[4][4] = {};
+  for (int k0 = 0; k0 < K; k0 += 16) {
+    float4 av = make_float4(0.f, 0.f, 0.f, 0.f), bv = av;
+    if (m0 + lr < M && k0 + lk < K) av = *reinterpret_cast<const float4*>(A + (size_t)(m0 + lr) * lda + k0 + lk);
+    if (n0 + lr < N && k0 + lk < K) bv = *reinterpret_cast<const float4*>(B + (size_t)(n0 + lr) * ldb + k0 + lk);
+    sA[lk + 0][lr] = av.x; sA[lk + 1][lr] = av.y; sA[lk + 2][lr] = av.z; sA[lk + 3][lr] = av.w;
+    sB[lk + 0][lr] = bv.x; sB[lk + 1][lr] = bv.y; sB[lk + 2][lr] = bv.z; sB[lk + 3][lr] = bv.w;
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      float a[4], b[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) a[i] = sA[k][ty * 4 + i];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) b[j] = sB[k][tx + 16 * j];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int n = n0 + tx + 16 * j;
+    if (n >= N) continue;
+    const EpiCol ec = epi_col(e, n, true);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int m = m0 + ty * 4 + i;
+      if (m < M) epi_elem(e, m, n, acc[i][j], ec);
+    }
+  }
+}
+
+// =================================================================================================
+// host
+// =================================================================================================
+static EpiArgs to_epi(const gvk_gemm_params* p) {
+  EpiArgs e;
+  e.bias = p->bias; e.ssf_scale = p->ssf_scale; e.ssf_shift = p->ssf_shift; e.act = p->act;
+  e.aux = p->aux; e.aux_dtype = p->aux_dtype; e.ld_aux = p->ld_aux;
+  e.pos = p->pos; e.rows_per_batch = p->rows_per_batch; e.out_batch_rows = p->out_batch_rows; e.out_row_offset = p->out_row_offset;
+  e.res1 = p->res1; e.ld_res1 = p->ld_res1; e.res2 = p->res2; e.ld_res2 = p->ld_res2;
+  e.out = p->out; e.out_dtype = p->out_dtype; e.ld_out = p->ld_out; e.out2 = p->out2; e.ld_out2 = p->ld_out2;
+  e.N = p->N;
+  return e;
+}
+
+template <int BN, int STAGES>
+static int launch_bf16(const gvk_gemm_params* p, const EpiArgs& e, cudaStream_t stream) {
+  using L = GemmSmem<BN, STAGES>;
+  static bool configured = false;
+  auto kern = gemm_bf16_sm100_kernel<BN, STAGES>;
+  if (!configured) {
+    int st = cuda_status(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal), "gemm smem attribute");
+    if (st != GVK_OK) return st;
+    configured = true;
+  }
+  CUtensorMap ta, tb;
+  int st = make_tma_2d_bf16(&ta, p->a, p->M, p->K, p->lda, kBM, kBK);
+  if (st != GVK_OK) return st;
+  st = make_tma_2d_bf16(&tb, p->b, p->N, p->K, p->ldb, BN, kBK);
+  if (st != GVK_OK) return st;
+  const int tiles = ((p->M + kBM - 1) / kBM) * ((p->N + BN - 1) / BN);
+  const int grid = std::min(tiles, sm_count());
+  kern<<<grid, kGemmThreads, L::kTotal, stream>>>(ta, tb, e, p->M, p->N, p->K);
+  GVK_CHECK_LAUNCH("gemm_bf16_sm100");
+  return GVK_OK;
+}
+
+int gemm_dispatch(const gvk_gemm_params* p, cudaStream_t stream) {
+  GVK_CHECK_ARG(p && p->a && p->b && p->out, "gvk_gemm: null operand");
+  GVK_CHECK_ARG(p->M > 0 && p->N > 0 && p->K > 0, "gvk_gemm: non-positive shape M=%d N=%d K=%d", p->M, p->N, p->K);
+  GVK_CHECK_ARG(p->act != GVK_ACT_GELU_BWD || p->aux, "gvk_gemm: GELU_BWD needs aux");
+  GVK_CHECK_ARG(p->rows_per_batch >= 0, "gvk_gemm: rows_per_batch < 0");
+  const EpiArgs e = to_epi(p);
+  if (p->ab_dtype == GVK_BF16) {
+    GVK_CHECK_ARG(p->K % kBK == 0, "gvk_gemm(bf16): K=%d must be a multiple of %d", p->K, kBK);
+    GVK_CHECK_ARG(p->lda % 8 == 0 && p->ldb % 8 == 0, "gvk_gemm(bf16): lda/ldb must be multiples of 8");
+    GVK_CHECK_ARG((reinterpret_cast<uintptr_t>(p->a) & 15) == 0 && (reinterpret_cast<uintptr_t>(p->b) & 15) == 0,
+                  "gvk_gemm(bf16): operands must be 16-byte aligned");
+    if (p->N % 256 == 0) return launch_bf16<256, 4>(p, e, stream);
+    return launch_bf16<128, 6>(p, e, stream);
+  }
+  if (p->ab_dtype == GVK_F32) {
+    GVK_CHECK_ARG(p->K % 4 == 0 && p->lda % 4 == 0 && p->ldb % 4 == 0, "gvk_gemm(f32): K, lda, ldb must be multiples of 4");
+    dim3 grid((p->N + 63) / 64, (p->M + 63) / 64);
+    gemm_f32_kernel<<<grid, 256, 0, stream>>>(reinterpret_cast<const float*>(p->a), reinterpret_cast<const float*>(p->b), p->lda, p->ldb, e,
+                                              p->M, p->N, p->K);
+    GVK_CHECK_LAUNCH("gemm_f32");
+    return GVK_OK;
+  }
+  set_last_error("gvk_gemm: unsupported ab_dtype %d", p->ab_dtype);
+  return GVK_ERR_UNSUPPORTED;
+}
+
+}  // namespace gvk

@@ -1,0 +1,91 @@
+"""GPU: gvk_gemm (tcgen05 bf16 path and exact fp32 path) against torch matmul, through the C ABI."""
+import pytest
+import torch
+
+from gaviko_b200 import ops
+
+pytestmark = pytest.mark.gpu
+
+
+def _ref(a, b, bias=None, act=None, res1=None, res2=None, pre=None):
+    v = a.double() @ b.double().t()
+    if bias is not None:
+        v = v + bias.double()
+    if act == 'gelu':
+        v = torch.nn.functional.gelu(v)
+    if act == 'gelu_bwd':
+        x = pre.double()
+        cdf = 0.5 * (1 + torch.erf(x / 2 ** 0.5))
+        pdf = torch.exp(-0.5 * x * x) / (2 * torch.pi) ** 0.5
+        v = v * (cdf + x * pdf)
+    if res1 is not None:
+        v = v + res1.double()
+    if res2 is not None:
+        v = v + res2.double()
+    return v
+
+
+SHAPES = [(128, 256, 64), (300, 768, 768), (2066, 2304, 768), (1033, 192, 192), (2000, 576, 192), (515, 768, 3072), (97, 3072, 768), (4132, 1024, 4096)]
+
+
+@pytest.mark.parametrize('M,N,K', SHAPES)
+@pytest.mark.parametrize('dt', [torch.bfloat16, torch.float32])
+def test_gemm_plain(M, N, K, dt):
+    torch.manual_seed(M + N + K)
+    a = torch.randn(M, K, device='cuda').to(dt)
+    b = (torch.randn(N, K, device='cuda') / K ** 0.5).to(dt)
+    out = ops.gemm(a, b, out_dtype=torch.float32)
+    ref = _ref(a, b)
+    err = (out.double() - ref).abs().max().item()
+    tol = 2e-3 if dt == torch.bfloat16 else 2e-5   # bf16 products are exact in fp32; error is accumulation order only
+    assert err < tol * max(1.0, ref.abs().max().item()), (err, ref.abs().max().item())
+
+
+@pytest.mark.parametrize('dt', [torch.bfloat16, torch.float32])
+def test_gemm_epilogues(dt):
+    torch.manual_seed(0)
+    M, N, K = 1033 * 2, 768, 192
+    a = torch.randn(M, K, device='cuda').to(dt)
+    b = (torch.randn(N, K, device='cuda') / K ** 0.5).to(dt)
+    bias = torch.randn(N, device='cuda')
+    res1 = torch.randn(M, N, device='cuda')
+    res2 = torch.randn(M, N, device='cuda')
+    # bias + gelu with saved pre-activation, bf16 output
+    aux = torch.empty(M, N, device='cuda', dtype=torch.float32)
+    out = ops.gemm(a, b, bias=bias, act=ops.ACT_GELU, aux=aux, out_dtype=torch.bfloat16)
+    assert (aux.double() - _ref(a, b, bias)).abs().max().item() < 1e-3
+    assert (out.double() - _ref(a, b, bias, 'gelu')).abs().max().item() < 3e-2      # bf16 output rounding
+    out = ops.gemm(a, b, bias=bias, act=ops.ACT_GELU, out_dtype=torch.float32)
+    assert (out.double() - _ref(a, b, bias, 'gelu')).abs().max().item() < 1e-3
+    # gelu backward epilogue + two residuals, fp32 output
+    out = ops.gemm(a, b, act=ops.ACT_GELU_BWD, aux=aux, res1=res1, res2=res2, out_dtype=torch.float32)
+    assert (out.double() - _ref(a, b, None, 'gelu_bwd', res1, res2, pre=aux)).abs().max().item() < 1e-3
+    # in-place residual update (out aliases res1), as the residual stream does
+    r = res1.clone()
+    ops.gemm(a, b, bias=bias, res1=r, out=r)
+    assert (r.double() - _ref(a, b, bias, None, res1)).abs().max().item() < 1e-3
+
+
+@pytest.mark.parametrize('dt', [torch.bfloat16, torch.float32])
+def test_gemm_patch_embed_epilogue(dt):
+    """Row remap + positional add + dual store: the a1+a2 fusion (model/gaviko.py:532-548)."""
+    torch.manual_seed(1)
+    B, Np, P, K, N = 3, 64, 8, 3072, 192
+    T = P + 1 + Np
+    a = torch.rand(B * Np, K, device='cuda').to(dt)
+    b = (torch.randn(N, K, device='cuda') / K ** 0.5).to(dt)
+    bias = torch.randn(N, device='cuda')
+    pos = torch.randn(Np, N, device='cuda')
+    g = torch.zeros(B * T, N, device='cuda')
+    loc = torch.empty(B * Np, N, device='cuda')
+    ops.gemm(a, b, bias=bias, pos=pos, rows_per_batch=Np, out_batch_rows=T, out_row_offset=P + 1, out=g, out2=loc)
+    ref = (_ref(a, b, bias).view(B, Np, N) + pos.double()).float()
+    assert (loc.view(B, Np, N) - ref).abs().max().item() < 1e-3
+    assert (g.view(B, T, N)[:, P + 1:] - ref).abs().max().item() < 1e-3
+    assert g.view(B, T, N)[:, :P + 1].abs().max().item() == 0
+
+
+def test_gemm_rejects_cpu_tensors():
+    from gaviko_b200._lib import GvkError
+    with pytest.raises(GvkError):
+        ops.gemm(torch.zeros(4, 64), torch.zeros(4, 64))
