@@ -1,21 +1,60 @@
-"""ctypes binding of libgvk_sm100a.so (include/gvk.h).  There is no CPU fallback: if the library is missing, or a
-tensor is not on a CUDA device, the call raises."""
+"""ctypes binding of libgvk_sm100a.so.  Struct layouts are parsed from include/gvk.h (the single source of truth for the
+C ABI) so the Python mirror cannot drift.  There is no CPU fallback: if the library is missing, or a tensor is not on a
+CUDA device, the call raises GvkError."""
 import ctypes as C
 import os
+import re
 
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, 'libgvk_sm100a.so')
+HEADER_PATH = os.path.join(os.path.dirname(_HERE), 'include', 'gvk.h')
 
 GVK_F32, GVK_BF16 = 0, 1
 ACT_NONE, ACT_GELU, ACT_GELU_BWD = 0, 1, 2
-
-_lib = None
+ROWACT_NONE, ROWACT_QUICKGELU, ROWACT_RELU = 0, 1, 2
+LOSS_FOCAL, LOSS_CE = 0, 1
 
 
 class GvkError(RuntimeError):
     pass
+
+
+_SCALARS = {'int': C.c_int, 'float': C.c_float, 'uint64_t': C.c_uint64, 'size_t': C.c_size_t, 'long long': C.c_longlong,
+            'int64_t': C.c_int64, 'uint32_t': C.c_uint32, 'double': C.c_double}
+
+
+def _parse_header(path):
+    """typedef struct { ... } name;  ->  ctypes.Structure subclasses (nested structs by value supported)."""
+    src = open(path).read()
+    src = re.sub(r'/\*.*?\*/', '', src, flags=re.S)
+    src = re.sub(r'//[^\n]*', '', src)
+    structs = {}
+    for body, name in re.findall(r'typedef\s+struct\s*\{(.*?)\}\s*(\w+)\s*;', src, flags=re.S):
+        fields = []
+        for decl in body.split(';'):
+            decl = ' '.join(decl.split())
+            if not decl:
+                continue
+            if '*' in decl:
+                base, names = decl.rsplit('*', 1)
+                assert ',' not in names, f'one pointer per declaration please: {decl}'
+                fields.append((names.strip(), C.c_void_p))
+                continue
+            m = re.match(r'(?:const\s+)?((?:unsigned\s+)?(?:long long|\w+))\s+(.*)', decl)
+            ctype_name, names = m.group(1), m.group(2)
+            ctype = _SCALARS.get(ctype_name) or structs.get(ctype_name)
+            assert ctype is not None, f'unknown type in gvk.h: {decl}'
+            for n in names.split(','):
+                fields.append((n.strip(), ctype))
+        structs[name] = type(name, (C.Structure,), {'_fields_': fields})
+    funcs = re.findall(r'\bint\s+(gvk_\w+)\s*\(', src)
+    return structs, sorted(set(funcs))
+
+
+STRUCTS, FUNCTIONS = _parse_header(HEADER_PATH)
+_lib = None
 
 
 def lib():
@@ -47,26 +86,27 @@ def dtype_tag(t: torch.dtype) -> int:
     raise GvkError(f'unsupported dtype {t}')
 
 
-def ptr(t):
-    """Device pointer of an optional tensor (None -> NULL); refuses CPU tensors (no CPU fallback)."""
+def ptr(t, dtype=None):
+    """Device address of an optional tensor (None -> NULL).  Refuses CPU tensors: there is no CPU fallback."""
     if t is None:
         return None
     if not t.is_cuda:
         raise GvkError('gaviko_b200 kernels need CUDA tensors (there is no CPU fallback)')
-    return C.c_void_p(t.data_ptr())
+    if dtype is not None and t.dtype != dtype:
+        raise GvkError(f'expected {dtype}, got {t.dtype}')
+    return t.data_ptr()
+
+
+def fptr(t):
+    """fp32, contiguous device tensor (or None)."""
+    if t is not None and not t.is_contiguous():
+        raise GvkError('expected a contiguous tensor')
+    return ptr(t, torch.float32)
 
 
 def stream():
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
-class GemmParams(C.Structure):
-    _fields_ = [
-        ('a', C.c_void_p), ('b', C.c_void_p), ('ab_dtype', C.c_int), ('M', C.c_int), ('N', C.c_int), ('K', C.c_int),
-        ('lda', C.c_int), ('ldb', C.c_int),
-        ('bias', C.c_void_p), ('ssf_scale', C.c_void_p), ('ssf_shift', C.c_void_p), ('act', C.c_int),
-        ('aux', C.c_void_p), ('aux_dtype', C.c_int), ('ld_aux', C.c_int),
-        ('pos', C.c_void_p), ('rows_per_batch', C.c_int), ('out_batch_rows', C.c_int), ('out_row_offset', C.c_int),
-        ('res1', C.c_void_p), ('ld_res1', C.c_int), ('res2', C.c_void_p), ('ld_res2', C.c_int),
-        ('out', C.c_void_p), ('out_dtype', C.c_int), ('ld_out', C.c_int), ('out2', C.c_void_p), ('ld_out2', C.c_int),
-    ]
+def call(name, *args):
+    check(getattr(lib(), name)(*args), name)

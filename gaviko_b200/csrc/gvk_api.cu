@@ -83,8 +83,6 @@ int make_tma_3d_bf16(CUtensorMap* out, const void* base, uint64_t d2, uint64_t r
   return encode_bf16(out, base, 3, dims, strides, box);
 }
 
-int gemm_dispatch(const gvk_gemm_params* p, cudaStream_t stream);
-
 }  // namespace gvk
 
 extern "C" {
@@ -92,7 +90,53 @@ extern "C" {
 const char* gvk_last_error(void) { return gvk::g_err; }
 int gvk_version(void) { return 100; }
 uint64_t gvk_launch_count(void) { return gvk::g_launches.load(); }
+long long gvk_struct_size(const char* name) {
+#define GVK_SZ(T) \
+  if (strcmp(name, #T) == 0) return (long long)sizeof(T);
+  GVK_SZ(gvk_gemm_params) GVK_SZ(gvk_layernorm_fwd_params) GVK_SZ(gvk_rowproj_down_params) GVK_SZ(gvk_rowproj_up_params)
+  GVK_SZ(gvk_skinny_wgrad_params) GVK_SZ(gvk_layernorm_bwd_params) GVK_SZ(gvk_attn_fwd_params) GVK_SZ(gvk_attn_bwd_params)
+  GVK_SZ(gvk_fusion_weights) GVK_SZ(gvk_fusion_grads) GVK_SZ(gvk_fusion_saved) GVK_SZ(gvk_fusion_fwd_params)
+  GVK_SZ(gvk_fusion_bwd_params) GVK_SZ(gvk_head_fwd_params) GVK_SZ(gvk_head_bwd_params)
+#undef GVK_SZ
+  return -1;
+}
 
-int gvk_gemm(const gvk_gemm_params* p, gvk_stream_t stream) { return gvk::gemm_dispatch(p, reinterpret_cast<cudaStream_t>(stream)); }
+#define S(stream) reinterpret_cast<cudaStream_t>(stream)
+int gvk_gemm(const gvk_gemm_params* p, gvk_stream_t stream) { return gvk::gemm_dispatch(p, S(stream)); }
+int gvk_layernorm_fwd(const gvk_layernorm_fwd_params* p, gvk_stream_t stream) { return gvk::layernorm_fwd(p, S(stream)); }
+int gvk_layernorm_bwd(const gvk_layernorm_bwd_params* p, gvk_stream_t stream) { return gvk::layernorm_bwd(p, S(stream)); }
+int gvk_rowproj_down(const gvk_rowproj_down_params* p, gvk_stream_t stream) { return gvk::rowproj_down(p, S(stream)); }
+int gvk_rowproj_up(const gvk_rowproj_up_params* p, gvk_stream_t stream) { return gvk::rowproj_up(p, S(stream)); }
+int gvk_skinny_wgrad(const gvk_skinny_wgrad_params* p, gvk_stream_t stream) { return gvk::skinny_wgrad(p, S(stream)); }
+int gvk_small_wgrad(const float* a, int lda, int ra, const float* b, int ldb, int rb, int M, float* dw, gvk_stream_t stream) {
+  return gvk::small_wgrad(a, lda, ra, b, ldb, rb, M, dw, S(stream));
+}
+int gvk_attn_simt_fwd(const gvk_attn_fwd_params* p, gvk_stream_t stream) { return gvk::attn_simt_fwd(p, S(stream)); }
+int gvk_attn_simt_bwd(const gvk_attn_bwd_params* p, gvk_stream_t stream) { return gvk::attn_simt_bwd(p, S(stream)); }
+int gvk_patch_gather(const float* img, int B, int C, int D, int H, int W, int fp, int ps, void* patches, int out_dtype, gvk_stream_t stream) {
+  return gvk::patch_gather(img, B, C, D, H, W, fp, ps, patches, out_dtype, S(stream));
+}
+int gvk_fill_rows(const float* a, const float* b, int R, int dim, float* out, int ld_out, int out_batch_rows, int out_row_offset, int B, gvk_stream_t stream) {
+  return gvk::fill_rows(a, b, R, dim, out, ld_out, out_batch_rows, out_row_offset, B, S(stream));
+}
+int gvk_batch_rowsum(const float* x, int ldx, int batch_rows, int row_offset, int R, int dim, int B, float* out, int accumulate, gvk_stream_t stream) {
+  return gvk::batch_rowsum(x, ldx, batch_rows, row_offset, R, dim, B, out, accumulate, S(stream));
+}
+int gvk_prompt_fusion_fwd(const gvk_fusion_fwd_params* p, gvk_stream_t stream) { return gvk::prompt_fusion_fwd(p, S(stream)); }
+int gvk_prompt_fusion_bwd(const gvk_fusion_bwd_params* p, gvk_stream_t stream) { return gvk::prompt_fusion_bwd(p, S(stream)); }
+int gvk_quickgelu_bwd(const float* dy, const float* pre, float* y, size_t n, gvk_stream_t stream) { return gvk::quickgelu_bwd(dy, pre, y, n, S(stream)); }
+int gvk_head_fwd(const gvk_head_fwd_params* p, gvk_stream_t stream) { return gvk::head_fwd(p, S(stream)); }
+int gvk_head_bwd(const gvk_head_bwd_params* p, gvk_stream_t stream) { return gvk::head_bwd(p, S(stream)); }
+int gvk_loss_fwd_bwd(const float* logits, const long long* target, int B, int C, int kind, float gamma, float eps, long long ignore_index, float* loss, float* dlogits,
+                     gvk_stream_t stream) {
+  return gvk::loss_fwd_bwd(logits, target, B, C, kind, gamma, eps, ignore_index, loss, dlogits, S(stream));
+}
+int gvk_small_matmul(const float* a, int lda, int ra, const float* w, int rb, int M, float* out, int ldo, gvk_stream_t stream) {
+  return gvk::small_matmul(a, lda, ra, w, rb, M, out, ldo, S(stream));
+}
+int gvk_colsum(const float* x, int ldx, int M, int dim, float* out, gvk_stream_t stream) { return gvk::colsum(x, ldx, M, dim, out, S(stream)); }
+int gvk_cast_f32_bf16(const float* x, int ldx, void* y, int ldy, int M, int dim, gvk_stream_t stream) {
+  return gvk::cast_f32_bf16(x, ldx, y, ldy, M, dim, S(stream));
+}
 
 }  // extern "C"

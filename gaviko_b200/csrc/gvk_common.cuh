@@ -39,6 +39,30 @@ int make_tma_2d_bf16(CUtensorMap* out, const void* base, uint64_t rows, uint64_t
 int make_tma_3d_bf16(CUtensorMap* out, const void* base, uint64_t d2, uint64_t rows, uint64_t cols,
                      uint64_t ld_row_elems, uint64_t ld_d2_elems, uint32_t box_rows, uint32_t box_cols);
 
+// op dispatchers (one per extern "C" entry point; defined next to their kernels)
+int gemm_dispatch(const gvk_gemm_params* p, cudaStream_t stream);
+int layernorm_fwd(const gvk_layernorm_fwd_params* p, cudaStream_t stream);
+int layernorm_bwd(const gvk_layernorm_bwd_params* p, cudaStream_t stream);
+int rowproj_down(const gvk_rowproj_down_params* p, cudaStream_t stream);
+int rowproj_up(const gvk_rowproj_up_params* p, cudaStream_t stream);
+int skinny_wgrad(const gvk_skinny_wgrad_params* p, cudaStream_t stream);
+int small_wgrad(const float* a, int lda, int ra, const float* b, int ldb, int rb, int M, float* dw, cudaStream_t stream);
+int small_matmul(const float* a, int lda, int ra, const float* w, int rb, int M, float* out, int ldo, cudaStream_t stream);
+int colsum(const float* x, int ldx, int M, int dim, float* out, cudaStream_t stream);
+int cast_f32_bf16(const float* x, int ldx, void* y, int ldy, int M, int dim, cudaStream_t stream);
+int attn_simt_fwd(const gvk_attn_fwd_params* p, cudaStream_t stream);
+int attn_simt_bwd(const gvk_attn_bwd_params* p, cudaStream_t stream);
+int patch_gather(const float* img, int B, int C, int D, int H, int W, int fp, int ps, void* patches, int out_dtype, cudaStream_t stream);
+int fill_rows(const float* a, const float* b, int R, int dim, float* out, int ld_out, int out_batch_rows, int out_row_offset, int B, cudaStream_t stream);
+int batch_rowsum(const float* x, int ldx, int batch_rows, int row_offset, int R, int dim, int B, float* out, int accumulate, cudaStream_t stream);
+int prompt_fusion_fwd(const gvk_fusion_fwd_params* p, cudaStream_t stream);
+int prompt_fusion_bwd(const gvk_fusion_bwd_params* p, cudaStream_t stream);
+int quickgelu_bwd(const float* dy, const float* pre, float* y, size_t n, cudaStream_t stream);
+int head_fwd(const gvk_head_fwd_params* p, cudaStream_t stream);
+int head_bwd(const gvk_head_bwd_params* p, cudaStream_t stream);
+int loss_fwd_bwd(const float* logits, const long long* target, int B, int C, int kind, float gamma, float eps, long long ignore_index, float* loss, float* dlogits,
+                 cudaStream_t stream);
+
 #ifdef __CUDACC__
 // ------------------------------------------------------------------------------------------------
 // device helpers

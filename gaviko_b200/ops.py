@@ -1,50 +1,351 @@
-"""Thin torch-tensor wrappers over the C ABI (include/gvk.h).  Plumbing only: pointer/shape marshalling and allocation
-of outputs; all arithmetic happens in libgvk_sm100a.so on torch's current CUDA stream."""
+"""Thin torch-tensor wrappers over the C ABI (include/gvk.h).  Plumbing only: pointer / shape marshalling and output
+allocation; all arithmetic happens in libgvk_sm100a.so on torch's current CUDA stream.  No CPU fallback."""
 import ctypes as C
 
 import torch
 
 from . import _lib as L
-from ._lib import ACT_GELU, ACT_GELU_BWD, ACT_NONE  # noqa: F401
+from ._lib import (ACT_GELU, ACT_GELU_BWD, ACT_NONE, LOSS_CE, LOSS_FOCAL, ROWACT_NONE, ROWACT_QUICKGELU,  # noqa: F401
+                   ROWACT_RELU, GvkError)
+
+S = L.STRUCTS
 
 
 def _ld(t):
-    assert t.dim() == 2 and t.stride(1) == 1, 'expected a row-major 2-D tensor (last stride 1)'
+    if t.dim() != 2 or t.stride(1) != 1:
+        raise GvkError('expected a row-major 2-D tensor (last stride 1)')
     return t.stride(0)
 
 
+def _set(p, **kw):
+    for k, v in kw.items():
+        if isinstance(v, torch.Tensor):
+            v = L.ptr(v)
+        if v is not None:
+            setattr(p, k, v)
+    return p
+
+
+# ---------------------------------------------------------------------------------------------- GEMM
 def gemm(a, b, *, out=None, out_dtype=None, bias=None, ssf_scale=None, ssf_shift=None, act=ACT_NONE, aux=None,
          pos=None, rows_per_batch=0, out_batch_rows=0, out_row_offset=0, res1=None, res2=None, out2=None, out_rows=None):
     """out[row(m), n] = epilogue(sum_k a[m,k] * b[n,k]) — see gvk_gemm in include/gvk.h."""
     M, K = a.shape
     N, Kb = b.shape
-    assert K == Kb and a.dtype == b.dtype
+    if K != Kb or a.dtype != b.dtype:
+        raise GvkError(f'gemm: operand mismatch {tuple(a.shape)} {a.dtype} x {tuple(b.shape)} {b.dtype}')
     if out is None:
         out = torch.empty((out_rows if out_rows is not None else M, N), device=a.device, dtype=out_dtype or torch.float32)
-    p = L.GemmParams()
-    p.a, p.b = a.data_ptr(), b.data_ptr()
-    if not (a.is_cuda and b.is_cuda and out.is_cuda):
-        raise L.GvkError('gaviko_b200 kernels need CUDA tensors (there is no CPU fallback)')
-    p.ab_dtype = L.dtype_tag(a.dtype)
-    p.M, p.N, p.K = M, N, K
-    p.lda, p.ldb = _ld(a), _ld(b)
-    for name, t in (('bias', bias), ('ssf_scale', ssf_scale), ('ssf_shift', ssf_shift), ('pos', pos)):
-        if t is not None:
-            assert t.dtype == torch.float32 and t.is_contiguous() and t.is_cuda
-            setattr(p, name, t.data_ptr())
-    p.act = act
+    p = S['gvk_gemm_params']()
+    _set(p, a=a, b=b, ab_dtype=L.dtype_tag(a.dtype), M=M, N=N, K=K, lda=_ld(a), ldb=_ld(b),
+         bias=L.fptr(bias), ssf_scale=L.fptr(ssf_scale), ssf_shift=L.fptr(ssf_shift), act=act, pos=L.fptr(pos),
+         rows_per_batch=rows_per_batch, out_batch_rows=out_batch_rows, out_row_offset=out_row_offset,
+         out=out, out_dtype=L.dtype_tag(out.dtype), ld_out=_ld(out))
     if aux is not None:
-        p.aux, p.aux_dtype, p.ld_aux = aux.data_ptr(), L.dtype_tag(aux.dtype), _ld(aux)
-    p.rows_per_batch, p.out_batch_rows, p.out_row_offset = rows_per_batch, out_batch_rows, out_row_offset
+        _set(p, aux=aux, aux_dtype=L.dtype_tag(aux.dtype), ld_aux=_ld(aux))
     if res1 is not None:
-        assert res1.dtype == torch.float32
-        p.res1, p.ld_res1 = res1.data_ptr(), _ld(res1)
+        _set(p, res1=L.ptr(res1, torch.float32), ld_res1=_ld(res1))
     if res2 is not None:
-        assert res2.dtype == torch.float32
-        p.res2, p.ld_res2 = res2.data_ptr(), _ld(res2)
-    p.out, p.out_dtype, p.ld_out = out.data_ptr(), L.dtype_tag(out.dtype), _ld(out)
+        _set(p, res2=L.ptr(res2, torch.float32), ld_res2=_ld(res2))
     if out2 is not None:
-        assert out2.dtype == torch.float32
-        p.out2, p.ld_out2 = out2.data_ptr(), _ld(out2)
-    L.check(L.lib().gvk_gemm(C.byref(p), L.stream()), 'gvk_gemm')
+        _set(p, out2=L.ptr(out2, torch.float32), ld_out2=_ld(out2))
+    L.call('gvk_gemm', C.byref(p), L.stream())
     return out
+
+
+# ---------------------------------------------------------------------------------------------- row kernels
+def layernorm_fwd(x, gamma, beta, *, out=None, out_dtype=torch.float32, eps=1e-5, ssf_scale=None, ssf_shift=None, save_stats=True):
+    M, dim = x.shape
+    if out is None:
+        out = torch.empty((M, dim), device=x.device, dtype=out_dtype)
+    mean = torch.empty(M, device=x.device, dtype=torch.float32) if save_stats else None
+    rstd = torch.empty(M, device=x.device, dtype=torch.float32) if save_stats else None
+    p = S['gvk_layernorm_fwd_params']()
+    _set(p, x=L.ptr(x, torch.float32), ldx=_ld(x), gamma=L.fptr(gamma), beta=L.fptr(beta), eps=eps, ssf_scale=L.fptr(ssf_scale),
+         ssf_shift=L.fptr(ssf_shift), y=out, y_dtype=L.dtype_tag(out.dtype), ldy=_ld(out), mean=mean, rstd=rstd, M=M, dim=dim)
+    L.call('gvk_layernorm_fwd', C.byref(p), L.stream())
+    return out, mean, rstd
+
+
+def _wstrides(w, r, dim, transposed):
+    """(w_sj, w_sc) of element (j, c) for an nn.Linear weight: [r, dim] (transposed=False) or [dim, r] (True)."""
+    if not w.is_contiguous():
+        raise GvkError('weights must be contiguous')
+    if transposed:
+        assert tuple(w.shape) == (dim, r), (tuple(w.shape), dim, r)
+        return 1, r
+    assert tuple(w.shape) == (r, dim), (tuple(w.shape), r, dim)
+    return dim, 1
+
+
+def rowproj_down(x, w, bias=None, *, transposed=False, ln=None, eps=1e-5, act=ROWACT_NONE, save_pre=False, w2=None,
+                 drop_p=0.0, seed=0, offset=0):
+    """z = act(f(x) @ W^T + b) (W = w, or w^T when `transposed`); returns dict(z, pre, z2, mean, rstd)."""
+    M, dim = x.shape
+    r = w.shape[1] if transposed else w.shape[0]
+    sj, sc = _wstrides(w, r, dim, transposed)
+    z = torch.empty((M, r), device=x.device, dtype=torch.float32)
+    pre = torch.empty_like(z) if save_pre else None
+    p = S['gvk_rowproj_down_params']()
+    _set(p, x=L.ptr(x, torch.float32), ldx=_ld(x), M=M, dim=dim, r=r, w=L.ptr(w, torch.float32), w_sj=sj, w_sc=sc, bias=L.fptr(bias),
+         act=act, pre=pre, z=z, ldz=r, eps=eps, drop_p=drop_p, seed=seed, offset=offset)
+    mean = rstd = z2 = None
+    if ln is not None:
+        mean = torch.empty(M, device=x.device, dtype=torch.float32)
+        rstd = torch.empty(M, device=x.device, dtype=torch.float32)
+        _set(p, ln_gamma=L.fptr(ln[0]), ln_beta=L.fptr(ln[1]), mean=mean, rstd=rstd)
+    if w2 is not None:
+        r2 = w2.shape[0]
+        assert w2.shape[1] == r and w2.is_contiguous()
+        z2 = torch.empty((M, r2), device=x.device, dtype=torch.float32)
+        _set(p, w2=L.ptr(w2, torch.float32), r2=r2, z2=z2, ldz2=r2)
+    L.call('gvk_rowproj_down', C.byref(p), L.stream())
+    return dict(z=z, pre=pre, z2=z2, mean=mean, rstd=rstd)
+
+
+def rowproj_up(c, w, bias=None, *, transposed=False, res=None, out=None, out_lp=None, drop_p=0.0, seed=0, offset=0):
+    """out = res + dropout(c @ W + b): W element (j, col) = w[col, j] for an nn.Linear(r, dim).weight (transposed=False here means
+    `w` is [dim, r]); transposed=True takes a [r, dim] weight (dgrad of a down-projection)."""
+    M, r = c.shape
+    dim = w.shape[1] if transposed else w.shape[0]
+    if transposed:
+        assert tuple(w.shape) == (r, dim) and w.is_contiguous()
+        sj, sc = dim, 1
+    else:
+        assert tuple(w.shape) == (dim, r) and w.is_contiguous()
+        sj, sc = 1, r
+    if out is None:
+        out = torch.empty((M, dim), device=c.device, dtype=torch.float32)
+    p = S['gvk_rowproj_up_params']()
+    _set(p, c=L.ptr(c, torch.float32), ldc=_ld(c), M=M, dim=dim, r=r, w=L.ptr(w, torch.float32), w_sj=sj, w_sc=sc, bias=L.fptr(bias),
+         out=L.ptr(out, torch.float32), ld_out=_ld(out), drop_p=drop_p, seed=seed, offset=offset)
+    if res is not None:
+        _set(p, res=L.ptr(res, torch.float32), ld_res=_ld(res))
+    if out_lp is not None:
+        _set(p, out_lp=L.ptr(out_lp, torch.bfloat16), ld_out_lp=_ld(out_lp))
+    L.call('gvk_rowproj_up', C.byref(p), L.stream())
+    return out
+
+
+def skinny_wgrad(a, x, *, dw=None, dw_layout='rd', da_colsum=None, dx_colsum=None, ln=None, drop_p=0.0, seed=0, offset=0):
+    """dw(j,c) += sum_m a[m,j] f(x[m,c]).  dw_layout 'rd': dw is [r, dim]; 'dr': dw is [dim, r].  Accumulates (zero first)."""
+    M, r = a.shape
+    dim = x.shape[1]
+    p = S['gvk_skinny_wgrad_params']()
+    _set(p, a=L.ptr(a, torch.float32), lda=_ld(a), r=r, x=L.ptr(x, torch.float32), ldx=_ld(x), dim=dim, M=M,
+         da_colsum=L.fptr(da_colsum), dx_colsum=L.fptr(dx_colsum), drop_p=drop_p, seed=seed, offset=offset)
+    if dw is not None:
+        if dw_layout == 'rd':
+            assert tuple(dw.shape) == (r, dim) and dw.is_contiguous()
+            _set(p, dw=L.ptr(dw, torch.float32), dw_sj=dim, dw_sc=1)
+        else:
+            assert tuple(dw.shape) == (dim, r) and dw.is_contiguous()
+            _set(p, dw=L.ptr(dw, torch.float32), dw_sj=1, dw_sc=r)
+    if ln is not None:
+        _set(p, ln_gamma=L.fptr(ln[0]), ln_beta=L.fptr(ln[1]), mean=L.fptr(ln[2]), rstd=L.fptr(ln[3]))
+    L.call('gvk_skinny_wgrad', C.byref(p), L.stream())
+
+
+def layernorm_bwd(x, gamma, mean, rstd, *, dy=None, dz=None, w=None, dres=None, dx=None, dx_lp=None, dgamma=None, dbeta=None):
+    """dx = dres + LN'(dy);  dy dense [M, dim] or rank-r (dz [M, r], w [r, dim])."""
+    M, dim = x.shape
+    if dx is None:
+        dx = torch.empty((M, dim), device=x.device, dtype=torch.float32)
+    p = S['gvk_layernorm_bwd_params']()
+    _set(p, x=L.ptr(x, torch.float32), ldx=_ld(x), gamma=L.fptr(gamma), mean=L.fptr(mean), rstd=L.fptr(rstd),
+         dx=L.ptr(dx, torch.float32), ld_dx=_ld(dx), dgamma=L.fptr(dgamma), dbeta=L.fptr(dbeta), M=M, dim=dim)
+    if dy is not None:
+        _set(p, dy=L.ptr(dy, torch.float32), ld_dy=_ld(dy))
+    if dz is not None:
+        r = dz.shape[1]
+        assert tuple(w.shape) == (r, dim) and w.is_contiguous()
+        _set(p, dz=L.ptr(dz, torch.float32), ld_dz=_ld(dz), w=L.ptr(w, torch.float32), w_sj=dim, w_sc=1, r=r)
+    if dres is not None:
+        _set(p, dres=L.ptr(dres, torch.float32), ld_dres=_ld(dres))
+    if dx_lp is not None:
+        _set(p, dx_lp=L.ptr(dx_lp, torch.bfloat16), ld_dx_lp=_ld(dx_lp))
+    L.call('gvk_layernorm_bwd', C.byref(p), L.stream())
+    return dx
+
+
+def small_wgrad(a, b, dw):
+    """dw[j, k] += sum_m a[m, j] b[m, k]"""
+    assert tuple(dw.shape) == (a.shape[1], b.shape[1]) and dw.is_contiguous()
+    L.call('gvk_small_wgrad', C.c_void_p(L.ptr(a, torch.float32)), _ld(a), a.shape[1], C.c_void_p(L.ptr(b, torch.float32)), _ld(b), b.shape[1],
+           a.shape[0], C.c_void_p(L.fptr(dw)), L.stream())
+
+
+def small_matmul(a, w):
+    """a [M, ra] @ w [ra, rb] -> [M, rb]"""
+    assert w.is_contiguous() and w.shape[0] == a.shape[1]
+    out = torch.empty((a.shape[0], w.shape[1]), device=a.device, dtype=torch.float32)
+    L.call('gvk_small_matmul', C.c_void_p(L.ptr(a, torch.float32)), _ld(a), a.shape[1], C.c_void_p(L.fptr(w)), w.shape[1], a.shape[0],
+           C.c_void_p(L.fptr(out)), _ld(out), L.stream())
+    return out
+
+
+def colsum(x, out):
+    """out[c] += sum_m x[m, c]"""
+    L.call('gvk_colsum', C.c_void_p(L.ptr(x, torch.float32)), _ld(x), x.shape[0], x.shape[1], C.c_void_p(L.fptr(out)), L.stream())
+
+
+def cast_bf16(x, out=None):
+    M, dim = x.shape
+    if out is None:
+        out = torch.empty((M, dim), device=x.device, dtype=torch.bfloat16)
+    L.call('gvk_cast_f32_bf16', C.c_void_p(L.ptr(x, torch.float32)), _ld(x), C.c_void_p(L.ptr(out, torch.bfloat16)), _ld(out), M, dim, L.stream())
+    return out
+
+
+# ---------------------------------------------------------------------------------------------- attention (SIMT)
+def _attn_params(qkv, B, T, H, D, q_off, k_off, v_off, scale, window, grid, drop_p, seed, offset, out, lse):
+    f = S['gvk_attn_fwd_params']()
+    _set(f, qkv=qkv, dtype=L.dtype_tag(qkv.dtype), ld=_ld(qkv), q_off=q_off, k_off=k_off, v_off=v_off, B=B, T=T, H=H, D=D, scale=scale,
+         drop_p=drop_p, seed=seed, offset=offset, out=out, ld_out=_ld(out), lse=L.fptr(lse))
+    if window is not None:
+        _set(f, win_d=window[0], win_h=window[1], win_w=window[2], grid_d=grid[0], grid_h=grid[1], grid_w=grid[2])
+    return f
+
+
+def attn_simt_fwd(qkv, B, T, H, D, *, q_off, k_off, v_off, scale, window=None, grid=None, drop_p=0.0, seed=0, offset=0):
+    out = torch.empty((B * T, H * D), device=qkv.device, dtype=qkv.dtype)
+    lse = torch.empty(B * H * T, device=qkv.device, dtype=torch.float32)
+    f = _attn_params(qkv, B, T, H, D, q_off, k_off, v_off, scale, window, grid, drop_p, seed, offset, out, lse)
+    L.call('gvk_attn_simt_fwd', C.byref(f), L.stream())
+    return out, lse
+
+
+def attn_simt_bwd(qkv, out, lse, dout, B, T, H, D, *, q_off, k_off, v_off, scale, window=None, grid=None, drop_p=0.0, seed=0, offset=0, dqkv=None):
+    if dqkv is None:
+        dqkv = torch.empty_like(qkv)
+    delta = torch.empty_like(lse)
+    p = S['gvk_attn_bwd_params']()
+    p.f = _attn_params(qkv, B, T, H, D, q_off, k_off, v_off, scale, window, grid, drop_p, seed, offset, out, lse)
+    assert dout.dtype == qkv.dtype and dqkv.dtype == qkv.dtype
+    _set(p, dout=dout, ld_dout=_ld(dout), delta=delta, dqkv=dqkv, ld_dqkv=_ld(dqkv))
+    L.call('gvk_attn_simt_bwd', C.byref(p), L.stream())
+    return dqkv
+
+
+# ---------------------------------------------------------------------------------------------- token assembly
+def patch_gather(img, fp, ps, out_dtype):
+    B, Cc, D, H, W = img.shape
+    if img.dtype != torch.float32 or not img.is_contiguous():
+        raise GvkError('patch_gather: expected a contiguous fp32 (B, C, D, H, W) volume')
+    n = (D // fp) * (H // ps) * (W // ps)
+    out = torch.empty((B * n, Cc * fp * ps * ps), device=img.device, dtype=out_dtype)
+    L.call('gvk_patch_gather', C.c_void_p(L.ptr(img)), B, Cc, D, H, W, fp, ps, C.c_void_p(L.ptr(out)), L.dtype_tag(out_dtype), L.stream())
+    return out
+
+
+def fill_rows(a, b, out, out_batch_rows, out_row_offset, B):
+    R, dim = a.shape
+    L.call('gvk_fill_rows', C.c_void_p(L.fptr(a)), C.c_void_p(L.fptr(b)) if b is not None else None, R, dim, C.c_void_p(L.ptr(out, torch.float32)), _ld(out),
+           out_batch_rows, out_row_offset, B, L.stream())
+
+
+def batch_rowsum(x, batch_rows, row_offset, R, B, out=None, accumulate=False):
+    dim = x.shape[1]
+    if out is None:
+        out = torch.empty((R, dim), device=x.device, dtype=torch.float32)
+    L.call('gvk_batch_rowsum', C.c_void_p(L.ptr(x, torch.float32)), _ld(x), batch_rows, row_offset, R, dim, B, C.c_void_p(L.fptr(out)), int(accumulate), L.stream())
+    return out
+
+
+# ---------------------------------------------------------------------------------------------- prompt fusion
+FUSION_WEIGHT_FIELDS = ('wq_g', 'bq_g', 'wq_l', 'bq_l', 'a_ln_w', 'a_ln_b', 'a_w1', 'a_b1', 'a_w3', 'a_b3', 'g_ln_w', 'g_ln_b', 'g_w', 'g_b')
+FUSION_SAVED_FIELDS = ('pl', 'qg', 'ql', 'ctx_g', 'ctx_l', 'lse_g', 'lse_l', 'imp', 'gw')
+
+
+def _fusion_weights(w):
+    s = S['gvk_fusion_weights']()
+    for k in FUSION_WEIGHT_FIELDS:
+        setattr(s, k, L.fptr(w[k]))
+    return s
+
+
+def prompt_fusion_fwd(xl, ll, w, B, T, N, P):
+    """xl [B*T, r] is modified in place (rows < P of every volume become the enhanced prompts).  Returns the saved state."""
+    r = xl.shape[1]
+    dev = xl.device
+    saved = {k: torch.empty((B * P, r), device=dev, dtype=torch.float32) for k in ('pl', 'qg', 'ql', 'ctx_g', 'ctx_l')}
+    saved.update({k: torch.empty(B * P, device=dev, dtype=torch.float32) for k in ('lse_g', 'lse_l', 'imp')})
+    saved['gw'] = torch.empty(B, device=dev, dtype=torch.float32)
+    p = S['gvk_fusion_fwd_params']()
+    _set(p, xl=L.fptr(xl), ll=L.fptr(ll), B=B, T=T, N=N, P=P, r=r)
+    p.w = _fusion_weights(w)
+    for k in FUSION_SAVED_FIELDS:
+        setattr(p.s, k, L.fptr(saved[k]))
+    L.call('gvk_prompt_fusion_fwd', C.byref(p), L.stream())
+    return saved
+
+
+def prompt_fusion_bwd(xl, ll, dxl, w, saved, grads, B, T, N, P):
+    """dxl [B*T, r]: d(combined) in, d(xl) out (in place).  Returns dll [B*N, r].  `grads` (dict of zeroed tensors) accumulates."""
+    r = xl.shape[1]
+    dll = torch.empty((B * N, r), device=xl.device, dtype=torch.float32)
+    ws = torch.empty(B * P * (2 * r + 4), device=xl.device, dtype=torch.float32)
+    p = S['gvk_fusion_bwd_params']()
+    _set(p, xl=L.fptr(xl), ll=L.fptr(ll), dxl=L.fptr(dxl), dll=L.fptr(dll), B=B, T=T, N=N, P=P, r=r, ws=L.fptr(ws))
+    p.w = _fusion_weights(w)
+    for k in FUSION_SAVED_FIELDS:
+        setattr(p.s, k, L.fptr(saved[k]))
+    for k in FUSION_WEIGHT_FIELDS:
+        setattr(p.g, k, L.fptr(grads[k]))
+    L.call('gvk_prompt_fusion_bwd', C.byref(p), L.stream())
+    return dll
+
+
+def quickgelu_bwd(dy, pre, out=None):
+    if out is None:
+        out = torch.empty_like(dy)
+    L.call('gvk_quickgelu_bwd', C.c_void_p(L.fptr(dy)), C.c_void_p(L.fptr(pre)), C.c_void_p(L.fptr(out)), C.c_size_t(dy.numel()), L.stream())
+    return out
+
+
+# ---------------------------------------------------------------------------------------------- head / loss
+def _head_params(x, B, T, pool_start, pool_count, gamma, beta, wh, bh, pooled, logits, eps, ssf_scale, ssf_shift):
+    f = S['gvk_head_fwd_params']()
+    _set(f, x=L.ptr(x, torch.float32), ldx=_ld(x), B=B, T=T, dim=x.shape[1], pool_start=pool_start, pool_count=pool_count, gamma=L.fptr(gamma),
+         beta=L.fptr(beta), eps=eps, ssf_scale=L.fptr(ssf_scale), ssf_shift=L.fptr(ssf_shift), wh=L.fptr(wh), bh=L.fptr(bh),
+         num_classes=wh.shape[0], pooled=L.fptr(pooled), logits=L.fptr(logits))
+    return f
+
+
+def head_fwd(x, B, T, pool_start, pool_count, gamma, beta, wh, bh, *, eps=1e-5, ssf_scale=None, ssf_shift=None):
+    pooled = torch.empty((B, x.shape[1]), device=x.device, dtype=torch.float32)
+    logits = torch.empty((B, wh.shape[0]), device=x.device, dtype=torch.float32)
+    f = _head_params(x, B, T, pool_start, pool_count, gamma, beta, wh, bh, pooled, logits, eps, ssf_scale, ssf_shift)
+    L.call('gvk_head_fwd', C.byref(f), L.stream())
+    return logits, pooled
+
+
+def head_bwd(x, B, T, pool_start, pool_count, gamma, beta, wh, bh, pooled, dlogits, *, dx=None, dx_lp=None, eps=1e-5, ssf_scale=None,
+             ssf_shift=None, dgamma=None, dbeta=None, dssf_scale=None, dssf_shift=None, need_dx=True):
+    """Returns (dx, dwh, dbh).  dx must be pre-zeroed when pool_count < T (only pooled rows are written)."""
+    dim = x.shape[1]
+    if need_dx and dx is None:
+        dx = torch.zeros((B * T, dim), device=x.device, dtype=torch.float32)
+    dwh = torch.empty_like(wh)
+    dbh = torch.empty_like(bh)
+    p = S['gvk_head_bwd_params']()
+    p.f = _head_params(x, B, T, pool_start, pool_count, gamma, beta, wh, bh, pooled, None, eps, ssf_scale, ssf_shift)
+    _set(p, dlogits=L.fptr(dlogits), dwh=L.fptr(dwh), dbh=L.fptr(dbh), dgamma=L.fptr(dgamma), dbeta=L.fptr(dbeta),
+         dssf_scale=L.fptr(dssf_scale), dssf_shift=L.fptr(dssf_shift))
+    if need_dx:
+        _set(p, dx=L.ptr(dx, torch.float32), ld_dx=_ld(dx))
+        if dx_lp is not None:
+            _set(p, dx_lp=L.ptr(dx_lp, torch.bfloat16), ld_dx_lp=_ld(dx_lp))
+    L.call('gvk_head_bwd', C.byref(p), L.stream())
+    return dx, dwh, dbh
+
+
+def loss_fwd_bwd(logits, target, kind, gamma=1.2, eps=1e-16, ignore_index=-100, need_grad=True):
+    B, Cn = logits.shape
+    loss = torch.empty((), device=logits.device, dtype=torch.float32)
+    dlogits = torch.empty_like(logits) if need_grad else None
+    if target.dtype != torch.int64 or not target.is_contiguous():
+        raise GvkError('loss: target must be a contiguous int64 tensor')
+    L.call('gvk_loss_fwd_bwd', C.c_void_p(L.fptr(logits)), C.c_void_p(L.ptr(target)), B, Cn, kind, C.c_float(gamma), C.c_float(eps),
+           C.c_longlong(ignore_index), C.c_void_p(L.fptr(loss)), C.c_void_p(L.fptr(dlogits)) if need_grad else None, L.stream())
+    return loss, dlogits

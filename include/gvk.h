@@ -39,6 +39,8 @@ const char* gvk_last_error(void);
 int gvk_version(void);
 /* Number of kernels this library has launched in the calling process (bench.py's gpu_launches). */
 uint64_t gvk_launch_count(void);
+/* sizeof() of a parameter struct by its typedef name (-1 if unknown): lets a binding verify its mirror of this header. */
+long long gvk_struct_size(const char* name);
 
 /* ------------------------------------------------------------------------------------------------------------------
  * Dense "TN" GEMM with fused epilogue:   acc[m,n] = sum_k A[m,k] * B[n,k]        (A: [M,K], B: [N,K], both K-contiguous)
@@ -87,6 +89,237 @@ typedef struct {
 } gvk_gemm_params;
 
 int gvk_gemm(const gvk_gemm_params* p, gvk_stream_t stream);
+
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Row kernels (one warp per token row; fp32 math; HBM-bound).  dim % 64 == 0, dim <= 1024, r <= 32.
+ * Strided weights: element (j, c) of a rank-r projection is w[j * w_sj + c * w_sc], so an nn.Linear(dim, r).weight
+ * ([r, dim]) is (w_sj = dim, w_sc = 1) and an nn.Linear(r, dim).weight ([dim, r]) used transposed is (w_sj = 1, w_sc = r).
+ * Dropout (replayable): element (m, c) of an [M, dim] tensor is kept iff philox(seed, offset + m * dim + c) >= drop_p and
+ * scaled by 1 / (1 - drop_p).  `offset` must be a multiple of 4.
+ * ------------------------------------------------------------------------------------------------------------------ */
+
+/* y = LayerNorm(x) * gamma + beta  (eps inside the sqrt, biased variance — nn.LayerNorm; model/vision_transformer.py:30,49).
+ * Optional SSF scale/shift after the norm (model/ssf.py:65,102).  mean / rstd (optional, [M]) are saved for backward. */
+typedef struct {
+  const float* x; int ldx;
+  const float* gamma; const float* beta; float eps;
+  const float* ssf_scale; const float* ssf_shift;
+  void* y; int y_dtype; int ldy;
+  float* mean; float* rstd;
+  int M, dim;
+} gvk_layernorm_fwd_params;
+int gvk_layernorm_fwd(const gvk_layernorm_fwd_params* p, gvk_stream_t stream);
+
+enum { GVK_ROWACT_NONE = 0, GVK_ROWACT_QUICKGELU = 1, GVK_ROWACT_RELU = 2 };
+
+/* z[m, j] = act( sum_c f(x[m, c]) * w(j, c) + bias[j] ),  f = optional dropout mask then optional LayerNorm.
+ * pre (optional) receives the pre-activation.  Optional chained projection z2[m, k] = sum_j z[m, j] * w2[k * r + j]  (r2 <= 64).
+ * Replaces LocalSelfAttention.norm/proj_down/qkv (model/gaviko.py:231-232), Awakening_Prompt.proj_down (model/gaviko.py:155-156)
+ * and, with transposed strides, the dgrad of every rank-r up-projection. */
+typedef struct {
+  const float* x; int ldx; int M, dim, r;
+  const float* ln_gamma; const float* ln_beta; float eps; float* mean; float* rstd;
+  const float* w; int w_sj, w_sc; const float* bias; int act;
+  float* pre; float* z; int ldz;
+  const float* w2; int r2; float* z2; int ldz2;
+  float drop_p; uint64_t seed; uint64_t offset;
+} gvk_rowproj_down_params;
+int gvk_rowproj_down(const gvk_rowproj_down_params* p, gvk_stream_t stream);
+
+/* out[m, c] = res[m, c] + dropout( sum_j c[m, j] * w(j, c) + bias[c] );  out_lp is an optional bf16 copy of out.
+ * Replaces LocalSelfAttention.proj_up + proj_drop + residual (model/gaviko.py:242-243, 301), Awakening_Prompt.proj_up
+ * (model/gaviko.py:187) and, with transposed strides, the dgrad of every rank-r down-projection. */
+typedef struct {
+  const float* c; int ldc; int M, dim, r;
+  const float* w; int w_sj, w_sc; const float* bias;
+  const float* res; int ld_res;
+  float* out; int ld_out; void* out_lp; int ld_out_lp;
+  float drop_p; uint64_t seed; uint64_t offset;
+} gvk_rowproj_up_params;
+int gvk_rowproj_up(const gvk_rowproj_up_params* p, gvk_stream_t stream);
+
+/* Rank-r weight gradient:  dw(j, c) += sum_m a[m, j] * f(x[m, c]);  da_colsum[j] += sum_m a[m, j];  dx_colsum[c] += sum_m f(x[m, c]).
+ * f = optional dropout mask, then optional LayerNorm recomputed from saved mean / rstd.  Accumulates with atomics: zero first. */
+typedef struct {
+  const float* a; int lda; int r;
+  const float* x; int ldx; int dim; int M;
+  const float* ln_gamma; const float* ln_beta; const float* mean; const float* rstd;
+  float* dw; int dw_sj, dw_sc;
+  float* da_colsum; float* dx_colsum;
+  float drop_p; uint64_t seed; uint64_t offset;
+} gvk_skinny_wgrad_params;
+int gvk_skinny_wgrad(const gvk_skinny_wgrad_params* p, gvk_stream_t stream);
+
+/* LayerNorm backward:  dx = dres + LN'(dy);  dy is either dense ([M, dim] fp32) or rank-r (dy[m, c] = sum_j dz[m, j] * w(j, c)).
+ * dgamma / dbeta (optional, [dim]) accumulate with atomics.  dx may alias dres.
+ * dx_lp is an optional bf16 copy (the next dgrad GEMM's A operand). */
+typedef struct {
+  const float* dy; int ld_dy;
+  const float* dz; int ld_dz; const float* w; int w_sj, w_sc; int r;
+  const float* x; int ldx; const float* gamma; const float* mean; const float* rstd;
+  const float* dres; int ld_dres;
+  float* dx; int ld_dx; void* dx_lp; int ld_dx_lp;
+  float* dgamma; float* dbeta;
+  int M, dim;
+} gvk_layernorm_bwd_params;
+int gvk_layernorm_bwd(const gvk_layernorm_bwd_params* p, gvk_stream_t stream);
+
+/* dw[j * rb + k] += sum_m a[m, j] * b[m, k]   (ra, rb <= 64; the LocalSelfAttention.qkv weight gradient). */
+int gvk_small_wgrad(const float* a, int lda, int ra, const float* b, int ldb, int rb, int M, float* dw, gvk_stream_t stream);
+
+/* out[m, k] = sum_j a[m, j] * w[j * rb + k]   (ra, rb <= 64; dgrad of the LocalSelfAttention.qkv projection). */
+int gvk_small_matmul(const float* a, int lda, int ra, const float* w, int rb, int M, float* out, int ldo, gvk_stream_t stream);
+
+/* y[m, n] += / = colsum helpers: out[c] += sum_m x[m, c]  (bias gradients; bitfit). */
+int gvk_colsum(const float* x, int ldx, int M, int dim, float* out, gvk_stream_t stream);
+
+/* Elementwise cast fp32 -> bf16 of an [M, dim] matrix (weights, activations). */
+int gvk_cast_f32_bf16(const float* x, int ldx, void* y, int ldy, int M, int dim, gvk_stream_t stream);
+
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Softmax attention, CUDA-core (SIMT) implementation: exact fp32 math, one warp per query (forward, dQ) or per key (dK, dV),
+ * no atomics, nothing of size T x T is ever materialised.  Used for
+ *   (1) GAViKO's window-sparse LocalSelfAttention core (model/gaviko.py:235-241): D = local_dim (20), H = 1, additive
+ *       {0,-inf} window mask given by its closed form (allowed j: i_ax - k_ax/2 <= j_ax <= i_ax + k_ax - 1 - k_ax/2 per axis,
+ *       model/gaviko.py:212-227), dropout on the probabilities;
+ *   (2) the frozen MHSA core in fp32 mode (model/vision_transformer.py:65-70): D = 64, dense.
+ * Layout: rows are tokens (B*T rows); head h of q / k / v lives at columns q_off / k_off / v_off + h*D of `qkv`.
+ * Dropout element index of probability (b, h, i, j) is ((b*H + h)*T + i)*T + j  (philox(seed, offset + index)).
+ * ------------------------------------------------------------------------------------------------------------------ */
+typedef struct {
+  const void* qkv; int dtype; int ld;
+  int q_off, k_off, v_off;
+  int B, T, H, D;
+  float scale;
+  int win_d, win_h, win_w;      /* window extents; win_d == 0 selects dense attention */
+  int grid_d, grid_h, grid_w;   /* token grid (T == grid_d*grid_h*grid_w when windowed) */
+  float drop_p; uint64_t seed; uint64_t offset;
+  void* out; int ld_out;        /* [B*T, H*D], same dtype as qkv */
+  float* lse;                   /* [B*H*T] log-sum-exp of the scaled scores (saved for backward) */
+} gvk_attn_fwd_params;
+int gvk_attn_simt_fwd(const gvk_attn_fwd_params* p, gvk_stream_t stream);
+
+typedef struct {
+  gvk_attn_fwd_params f;        /* same problem description as forward (out / lse are inputs here) */
+  const void* dout; int ld_dout; /* [B*T, H*D] */
+  float* delta;                 /* workspace [B*H*T] */
+  void* dqkv; int ld_dqkv;      /* gradient in the layout of qkv (q/k/v column blocks are fully overwritten) */
+} gvk_attn_bwd_params;
+int gvk_attn_simt_bwd(const gvk_attn_bwd_params* p, gvk_stream_t stream);
+
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Token assembly (a1/a2 of the hot path)
+ * ------------------------------------------------------------------------------------------------------------------ */
+
+/* Non-overlapping 3-D patch gather in Conv3d weight order (model/gaviko.py:383-385,532-533):
+ *   patches[b*N + (d*nh + h)*nw + w, ((c*fp + kd)*ps + kh)*ps + kw] = img[b, c, d*fp + kd, h*ps + kh, w*ps + kw]
+ * img fp32 contiguous (B, C, D, H, W); patches row-major [B*N, C*fp*ps*ps] in out_dtype. */
+int gvk_patch_gather(const float* img, int B, int C, int D, int H, int W, int fp, int ps, void* patches, int out_dtype, gvk_stream_t stream);
+
+/* out[b*out_batch_rows + out_row_offset + r, :] = a[r, :] + b[r, :]   for b < B, r < R   (b may be NULL).
+ * Writes the batch-broadcast prompt / cls rows of the token matrix (model/gaviko.py:536-543). */
+int gvk_fill_rows(const float* a, const float* b, int R, int dim, float* out, int ld_out, int out_batch_rows, int out_row_offset, int B, gvk_stream_t stream);
+
+/* out[r, :] (+)= sum_b x[b*batch_rows + row_offset + r, :]   (gradient of the broadcast above). accumulate != 0 adds to out. */
+int gvk_batch_rowsum(const float* x, int ldx, int batch_rows, int row_offset, int R, int dim, int B, float* out, int accumulate, gvk_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * GAViKO gated prompt fusion — Awakening_Prompt between the two projections (model/gaviko.py:158-184, :20-47, :48-70, :84-119).
+ * Inputs are the QuickGELU'd rank-r latents xl [B, T, r] (global: P prompts, cls, N image tokens) and ll [B, N, r] (local).
+ *   imp  = sigmoid(W3 gelu(W1 LN_a(cl) + b1) + b3)            (PromptRelevantEstimator)     [B, P]
+ *   gw   = sigmoid(Wg LN_g(cl) + bg)                          (PromptContextFusion)         [B]
+ *   ctx_g[p] = softmax(r^-0.5 (Wqg pl[p] + bqg) . tok) tok,  tok = xl[:, 2P+2:]  (967 keys — the reference's double slice)
+ *   ctx_l[p] = softmax(r^-0.5 (Wql pl[p] + bql) . tok) tok,  tok = ll
+ *   enh[p] = (gw ctx_g[p] + (1 - gw) ctx_l[p]) * imp[p]   -> written IN PLACE over xl[:, p]  (xl then is `combined_latent`)
+ * pl (the original prompt latents) and the small per-prompt state are saved for backward.
+ * r in {16, 20, 32}; hidden width of the estimator fixed at 64 (model/gaviko.py:25).
+ * ------------------------------------------------------------------------------------------------------------------ */
+typedef struct {
+  const float* wq_g; const float* bq_g; const float* wq_l; const float* bq_l;   /* [r,r], [r] */
+  const float* a_ln_w; const float* a_ln_b; const float* a_w1; const float* a_b1; const float* a_w3; const float* a_b3; /* [r],[r],[64,r],[64],[P,64],[P] */
+  const float* g_ln_w; const float* g_ln_b; const float* g_w; const float* g_b;  /* [r],[r],[1,r],[1] */
+} gvk_fusion_weights;
+
+typedef struct {
+  float* wq_g; float* bq_g; float* wq_l; float* bq_l;
+  float* a_ln_w; float* a_ln_b; float* a_w1; float* a_b1; float* a_w3; float* a_b3;
+  float* g_ln_w; float* g_ln_b; float* g_w; float* g_b;
+} gvk_fusion_grads; /* accumulated with atomics: zero first */
+
+typedef struct {
+  float* pl;      /* [B, P, r]   original prompt latents */
+  float* qg;      /* [B, P, r]   global queries */
+  float* ql;      /* [B, P, r]   local queries */
+  float* ctx_g;   /* [B, P, r] */
+  float* ctx_l;   /* [B, P, r] */
+  float* lse_g;   /* [B, P] */
+  float* lse_l;   /* [B, P] */
+  float* imp;     /* [B, P] */
+  float* gw;      /* [B] */
+} gvk_fusion_saved;
+
+typedef struct {
+  float* xl; const float* ll;
+  int B, T, N, P, r;
+  gvk_fusion_weights w;
+  gvk_fusion_saved s;
+} gvk_fusion_fwd_params;
+int gvk_prompt_fusion_fwd(const gvk_fusion_fwd_params* p, gvk_stream_t stream);
+
+/* Backward.  dxl holds dL/d(combined_latent) [B, T, r] on entry and dL/d(xl) on exit (in place); dll [B, N, r] is written.
+ * ws: workspace of B*P*(2r + 4) floats. */
+typedef struct {
+  const float* xl;   /* combined latent as left by forward (rows >= P are the original xl rows) */
+  const float* ll;
+  float* dxl; float* dll;
+  int B, T, N, P, r;
+  gvk_fusion_weights w;
+  gvk_fusion_saved s;
+  gvk_fusion_grads g;
+  float* ws;
+} gvk_fusion_bwd_params;
+int gvk_prompt_fusion_bwd(const gvk_fusion_bwd_params* p, gvk_stream_t stream);
+
+/* y = dy * quick_gelu'(pre)   over n elements (may run in place: y == dy). */
+int gvk_quickgelu_bwd(const float* dy, const float* pre, float* y, size_t n, gvk_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Head: final LayerNorm on the pooled rows only, mean-pool, Linear  (model/gaviko.py:306,314-316;
+ * model/vision_transformer.py:159-164 with pool = 'cls' -> rows [0,1), 'mean' -> rows [0,T)).
+ *   pooled[b] = mean_{r in [pool_start, pool_start+pool_count)} LN(x[b, r]) (* ssf_scale + ssf_shift);  logits = pooled Wh^T + bh
+ * ------------------------------------------------------------------------------------------------------------------ */
+typedef struct {
+  const float* x; int ldx; int B, T, dim;
+  int pool_start, pool_count;
+  const float* gamma; const float* beta; float eps;
+  const float* ssf_scale; const float* ssf_shift;
+  const float* wh; const float* bh; int num_classes;
+  float* pooled;   /* [B, dim] saved for backward */
+  float* logits;   /* [B, num_classes] */
+} gvk_head_fwd_params;
+int gvk_head_fwd(const gvk_head_fwd_params* p, gvk_stream_t stream);
+
+typedef struct {
+  gvk_head_fwd_params f;
+  const float* dlogits;     /* [B, num_classes] */
+  float* dx; int ld_dx;     /* [B*T, dim]: only the pooled rows are written (zero the rest beforehand) */
+  void* dx_lp; int ld_dx_lp; /* optional bf16 copy of the same rows */
+  float* dwh; float* dbh;   /* [num_classes, dim], [num_classes]: overwritten */
+  float* dgamma; float* dbeta;  /* optional [dim]: accumulated (atomics) */
+  float* dssf_scale; float* dssf_shift; /* optional [dim]: accumulated (atomics) */
+} gvk_head_bwd_params;
+int gvk_head_bwd(const gvk_head_bwd_params* p, gvk_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Losses on [B, C] fp32 logits, int64 targets.  loss is a device scalar; dlogits (optional) is d loss / d logits.
+ * kind 0: the reference's FocalLoss (losses/focal_loss.py:84-111: clamp(logits) -> softmax -> clamp -> softmax, eps 1e-16,
+ *         ignore_index, mean over non-ignored);  kind 1: nn.CrossEntropyLoss (mean).
+ * ------------------------------------------------------------------------------------------------------------------ */
+int gvk_loss_fwd_bwd(const float* logits, const long long* target, int B, int C, int kind, float gamma, float eps, long long ignore_index,
+                     float* loss, float* dlogits, gvk_stream_t stream);
 
 #ifdef __cplusplus
 }

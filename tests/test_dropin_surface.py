@@ -1,0 +1,66 @@
+"""CPU: the drop-in boundary — parameter names / shapes / trainable set / state_dict keys equal the reference's (recorded in
+tests/golden by oracle/make_golden.py); the C-ABI library loads and exports every symbol include/gvk.h declares; struct mirrors
+match sizeof() on the C side.  When /root/reference is present (build container) also: seeded construction reproduces the
+reference's initial weights exactly."""
+import ctypes
+
+import pytest
+import torch
+
+from gaviko_b200 import _lib as L
+from oracle import refload
+from oracle.cases import GAVIKO_CASES
+
+from helpers import load_golden
+
+
+def test_library_exports_every_declared_symbol():
+    lib = L.lib()
+    assert len(L.FUNCTIONS) >= 20
+    for fn in L.FUNCTIONS + ['gvk_last_error', 'gvk_launch_count', 'gvk_struct_size']:
+        assert hasattr(lib, fn), fn
+    assert lib.gvk_version() >= 100
+
+
+def test_struct_mirrors_match_c_sizeof():
+    lib = L.lib()
+    lib.gvk_struct_size.restype = ctypes.c_longlong
+    for name, st in L.STRUCTS.items():
+        assert lib.gvk_struct_size(name.encode()) == ctypes.sizeof(st), name
+
+
+@pytest.mark.parametrize('name', list(GAVIKO_CASES))
+def test_gaviko_names_shapes_match_reference(name):
+    from gaviko_b200.model.gaviko import Gaviko
+    kw, _ = GAVIKO_CASES[name]
+    g = load_golden(name)
+    m = Gaviko(**kw)
+    assert [n for n, _ in m.named_parameters()] == g['all_names'].tolist()
+    assert [str(tuple(p.shape)) for _, p in m.named_parameters()] == g['all_shapes'].tolist()
+    assert [n for n, p in m.named_parameters() if p.requires_grad] == g['trainable_names'].tolist()
+    assert list(m.state_dict().keys()) == g['state_dict_keys'].tolist()
+    assert m.train() is None and m.training is True
+    m.eval()
+    assert m.training is True and not m.transformer.training      # reference quirk, model/gaviko.py:525-528
+
+
+def test_no_cpu_fallback():
+    from gaviko_b200.model.gaviko import Gaviko
+    kw, _ = GAVIKO_CASES['gaviko_t16_small']
+    with pytest.raises(L.GvkError):
+        Gaviko(**kw)(torch.zeros(1, 1, 48, 64, 64))
+
+
+@pytest.mark.skipif(not refload.available(), reason='live reference only exists in the build container')
+def test_seeded_construction_equals_reference_init():
+    from gaviko_b200.model.gaviko import Gaviko
+    ref = refload.load()
+    kw, _ = GAVIKO_CASES['gaviko_t16_small']
+    torch.manual_seed(7)
+    a = ref.Gaviko(**kw)
+    torch.manual_seed(7)
+    b = Gaviko(**kw)
+    sa, sb = a.state_dict(), b.state_dict()
+    assert list(sa.keys()) == list(sb.keys())
+    for k in sa:
+        assert torch.equal(sa[k], sb[k]), k

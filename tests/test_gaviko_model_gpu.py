@@ -1,0 +1,96 @@
+"""GPU parity of the drop-in Gaviko module against golden outputs of the live reference (tests/golden, oracle/make_golden.py)
+and against the oracle restatement on the same weights, through the public module API (-> C ABI -> sm_100a kernels)."""
+import pytest
+import torch
+
+from gaviko_b200.losses.focal_loss import CrossEntropyLoss, FocalLoss
+from gaviko_b200.model.gaviko import Gaviko
+from oracle.cases import GAVIKO_CASES
+from oracle.golden_fill import golden_fill, golden_labels, golden_volume
+
+from helpers import grad_parity, load_golden, rel_l2
+
+pytestmark = pytest.mark.gpu
+
+
+def _build(name, compute_dtype):
+    kw, batch = GAVIKO_CASES[name]
+    model = Gaviko(**kw, compute_dtype=compute_dtype)
+    golden_fill(model, seed=0)
+    model = model.cuda()
+    model.eval()                      # dropout off for parity (reference quirk: self.training stays True)
+    img = golden_volume(batch, kw['frames'], kw['image_size'], kw['image_size'], channels=kw['channels']).cuda()
+    y = golden_labels(batch, kw['num_classes']).cuda()
+    return model, img, y
+
+
+@pytest.mark.parametrize('name', list(GAVIKO_CASES))
+def test_gaviko_fp32_matches_reference(name):
+    """fp32 mode: logits and every trainable gradient within 1e-4 relative of the reference (north star tolerance)."""
+    g = load_golden(name)
+    model, img, y = _build(name, 'fp32')
+    assert [n for n, p in model.named_parameters() if p.requires_grad] == g['trainable_names'].tolist()
+    for loss_name, crit in (('focal', FocalLoss(gamma=1.2)), ('ce', CrossEntropyLoss())):
+        model.zero_grad(set_to_none=True)
+        logits = model(img)
+        loss = crit(logits, y)
+        loss.backward()
+        assert rel_l2(logits.detach().cpu(), g['logits']) < 1e-4, rel_l2(logits.detach().cpu(), g['logits'])
+        assert abs(loss.item() - float(g[f'loss_{loss_name}'])) < 1e-4
+        grads = {n: p.grad for n, p in model.named_parameters() if p.requires_grad}
+        glob, worst, wname = grad_parity(grads, g, loss_name, tol_global=1e-4, tol_tensor=1e-3)
+        print(f'{name} {loss_name}: logits rel {rel_l2(logits.detach().cpu(), g["logits"]):.2e} grads global {glob:.2e} worst {worst:.2e} ({wname})')
+
+
+@pytest.mark.parametrize('name', list(GAVIKO_CASES))
+def test_gaviko_bf16_matches_reference(name):
+    """bf16 mode: within 2e-2 relative (north star tolerance), identical argmax."""
+    g = load_golden(name)
+    model, img, y = _build(name, 'bf16')
+    for loss_name, crit in (('focal', FocalLoss(gamma=1.2)), ('ce', CrossEntropyLoss())):
+        model.zero_grad(set_to_none=True)
+        logits = model(img)
+        loss = crit(logits, y)
+        loss.backward()
+        rl = rel_l2(logits.detach().cpu(), g['logits'])
+        assert rl < 2e-2, rl
+        assert logits.argmax(1).cpu().tolist() == g['logits'].argmax(1).tolist()
+        grads = {n: p.grad for n, p in model.named_parameters() if p.requires_grad}
+        glob, worst, wname = grad_parity(grads, g, loss_name, tol_global=2e-2, tol_tensor=6e-2, floor=1e-3)
+        print(f'{name} {loss_name}: logits rel {rl:.2e} grads global {glob:.2e} worst {worst:.2e} ({wname})')
+
+
+def test_inference_no_grad_and_determinism():
+    model, img, y = _build('gaviko_t16_small', 'fp32')
+    with torch.no_grad():
+        a = model(img)
+        b = model(img)
+    assert torch.equal(a, b) and not a.requires_grad
+
+
+def test_train_mode_dropout_is_active_and_unbiased():
+    kw, batch = GAVIKO_CASES['gaviko_t16_small']
+    kw = dict(kw, attn_drop=0.2, proj_drop=0.2)
+    model = Gaviko(**kw, compute_dtype='fp32')
+    golden_fill(model, seed=0)
+    model = model.cuda()
+    img = golden_volume(batch, kw['frames'], kw['image_size'], kw['image_size']).cuda()
+    model.eval()
+    with torch.no_grad():
+        ref = model(img)
+    assert model.train() is None       # reference quirk (model/gaviko.py:513-528)
+    with torch.no_grad():
+        outs = torch.stack([model(img) for _ in range(8)])
+    assert (outs[0] != outs[1]).any()                      # masks differ between steps
+    assert (outs.mean(0) - ref).abs().max().item() < 0.5   # and do not change the scale
+    logits = model(img)
+    FocalLoss(gamma=1.2)(logits, golden_labels(batch, 5).cuda()).backward()
+    assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in model.parameters() if p.requires_grad)
+
+
+def test_rejects_cpu_input():
+    from gaviko_b200._lib import GvkError
+    kw, batch = GAVIKO_CASES['gaviko_t16_small']
+    model = Gaviko(**kw)
+    with pytest.raises(GvkError):
+        model(torch.zeros(1, 1, 48, 64, 64))
