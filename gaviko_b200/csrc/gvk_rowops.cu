@@ -184,21 +184,23 @@ __global__ void __launch_bounds__(kRowThreads) rowproj_down_kernel(gvk_rowproj_d
       zl = 0.f;
     }
     if (p.w2) {
-      float o0 = 0.f, o1 = 0.f;
+      float o[3] = {0.f, 0.f, 0.f};
       for (int j = 0; j < p.r; ++j) {
         const float zj = __shfl_sync(0xffffffffu, zl, j);
-        if (lane < p.r2) o0 = fmaf(zj, sw2[lane * p.r + j], o0);
-        if (lane + 32 < p.r2) o1 = fmaf(zj, sw2[(lane + 32) * p.r + j], o1);
+#pragma unroll
+        for (int u = 0; u < 3; ++u)
+          if (lane + 32 * u < p.r2) o[u] = fmaf(zj, sw2[(lane + 32 * u) * p.r + j], o[u]);
       }
-      if (lane < p.r2) p.z2[(size_t)row * p.ldz2 + lane] = o0;
-      if (lane + 32 < p.r2) p.z2[(size_t)row * p.ldz2 + lane + 32] = o1;
+#pragma unroll
+      for (int u = 0; u < 3; ++u)
+        if (lane + 32 * u < p.r2) p.z2[(size_t)row * p.ldz2 + lane + 32 * u] = o[u];
     }
   }
 }
 
 int rowproj_down(const gvk_rowproj_down_params* p, cudaStream_t stream) {
   GVK_CHECK_ARG(p && p->x && p->w && p->z, "gvk_rowproj_down: null pointer");
-  GVK_CHECK_ARG(p->r >= 1 && p->r <= 32 && p->r2 >= 0 && p->r2 <= 64, "gvk_rowproj_down: r=%d (<=32), r2=%d (<=64)", p->r, p->r2);
+  GVK_CHECK_ARG(p->r >= 1 && p->r <= 32 && p->r2 >= 0 && p->r2 <= 96, "gvk_rowproj_down: r=%d (<=32), r2=%d (<=96)", p->r, p->r2);
   GVK_CHECK_ARG(p->M > 0 && p->ldx % 2 == 0, "gvk_rowproj_down: bad shape");
   const size_t smem = ((size_t)p->r * p->dim + (size_t)p->r2 * p->r) * sizeof(float);
   GVK_DISPATCH_NITER(p->dim, {
@@ -519,7 +521,7 @@ int layernorm_bwd(const gvk_layernorm_bwd_params* p, cudaStream_t stream) {
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) small_wgrad_kernel(const float* __restrict__ a, int lda, int ra, const float* __restrict__ b, int ldb, int rb, int M,
                                                             int rows_per_cta, float* __restrict__ dw) {
-  __shared__ float sa[16][64], sb[16][64];
+  __shared__ float sa[16][96], sb[16][96];
   const int tid = threadIdx.x;
   const int nout = ra * rb;
   float acc[16];  // outputs tid, tid+256, ... (ra*rb <= 4096)
@@ -528,8 +530,8 @@ __global__ void __launch_bounds__(256) small_wgrad_kernel(const float* __restric
   const int m_begin = blockIdx.x * rows_per_cta, m_end = min(M, m_begin + rows_per_cta);
   for (int m0 = m_begin; m0 < m_end; m0 += 16) {
     __syncthreads();
-    for (int idx = tid; idx < 16 * 64; idx += 256) {
-      const int rr = idx >> 6, j = idx & 63;
+    for (int idx = tid; idx < 16 * 96; idx += 256) {
+      const int rr = idx / 96, j = idx - rr * 96;
       const int m = m0 + rr;
       sa[rr][j] = (m < m_end && j < ra) ? a[(size_t)m * lda + j] : 0.f;
       sb[rr][j] = (m < m_end && j < rb) ? b[(size_t)m * ldb + j] : 0.f;
@@ -554,7 +556,7 @@ __global__ void __launch_bounds__(256) small_wgrad_kernel(const float* __restric
 
 int small_wgrad(const float* a, int lda, int ra, const float* b, int ldb, int rb, int M, float* dw, cudaStream_t stream) {
   GVK_CHECK_ARG(a && b && dw && M > 0, "gvk_small_wgrad: null pointer");
-  GVK_CHECK_ARG(ra >= 1 && ra <= 64 && rb >= 1 && rb <= 64, "gvk_small_wgrad: ra=%d rb=%d must be in [1,64]", ra, rb);
+  GVK_CHECK_ARG(ra >= 1 && ra <= 96 && rb >= 1 && rb <= 96 && ra * rb <= 4096, "gvk_small_wgrad: ra=%d rb=%d must be in [1,96], ra*rb <= 4096", ra, rb);
   const int ctas = std::max(1, std::min(sm_count() * 2, (M + 127) / 128));
   int rows_per_cta = ((M + ctas - 1) / ctas + 15) / 16 * 16;
   const int grid = (M + rows_per_cta - 1) / rows_per_cta;
@@ -581,7 +583,7 @@ __global__ void __launch_bounds__(256) small_matmul_kernel(const float* __restri
 
 int small_matmul(const float* a, int lda, int ra, const float* w, int rb, int M, float* out, int ldo, cudaStream_t stream) {
   GVK_CHECK_ARG(a && w && out && M > 0, "gvk_small_matmul: null pointer");
-  GVK_CHECK_ARG(ra >= 1 && ra <= 64 && rb >= 1 && rb <= 64, "gvk_small_matmul: ra=%d rb=%d must be in [1,64]", ra, rb);
+  GVK_CHECK_ARG(ra >= 1 && ra <= 96 && rb >= 1 && rb <= 96 && ra * rb <= 4096, "gvk_small_matmul: ra=%d rb=%d must be in [1,96], ra*rb <= 4096", ra, rb);
   const size_t total = (size_t)M * rb;
   const int grid = (int)std::min<size_t>((total + 255) / 256, (size_t)sm_count() * 8);
   small_matmul_kernel<<<grid, 256, 0, stream>>>(a, lda, ra, w, rb, M, out, ldo);

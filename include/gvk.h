@@ -114,7 +114,7 @@ int gvk_layernorm_fwd(const gvk_layernorm_fwd_params* p, gvk_stream_t stream);
 enum { GVK_ROWACT_NONE = 0, GVK_ROWACT_QUICKGELU = 1, GVK_ROWACT_RELU = 2 };
 
 /* z[m, j] = act( sum_c f(x[m, c]) * w(j, c) + bias[j] ),  f = optional dropout mask then optional LayerNorm.
- * pre (optional) receives the pre-activation.  Optional chained projection z2[m, k] = sum_j z[m, j] * w2[k * r + j]  (r2 <= 64).
+ * pre (optional) receives the pre-activation.  Optional chained projection z2[m, k] = sum_j z[m, j] * w2[k * r + j]  (r2 <= 96).
  * Replaces LocalSelfAttention.norm/proj_down/qkv (model/gaviko.py:231-232), Awakening_Prompt.proj_down (model/gaviko.py:155-156)
  * and, with transposed strides, the dgrad of every rank-r up-projection. */
 typedef struct {
@@ -165,10 +165,10 @@ typedef struct {
 } gvk_layernorm_bwd_params;
 int gvk_layernorm_bwd(const gvk_layernorm_bwd_params* p, gvk_stream_t stream);
 
-/* dw[j * rb + k] += sum_m a[m, j] * b[m, k]   (ra, rb <= 64; the LocalSelfAttention.qkv weight gradient). */
+/* dw[j * rb + k] += sum_m a[m, j] * b[m, k]   (ra, rb <= 96, ra*rb <= 4096; the LocalSelfAttention.qkv weight gradient). */
 int gvk_small_wgrad(const float* a, int lda, int ra, const float* b, int ldb, int rb, int M, float* dw, gvk_stream_t stream);
 
-/* out[m, k] = sum_j a[m, j] * w[j * rb + k]   (ra, rb <= 64; dgrad of the LocalSelfAttention.qkv projection). */
+/* out[m, k] = sum_j a[m, j] * w[j * rb + k]   (ra, rb <= 96, ra*rb <= 4096; dgrad of the LocalSelfAttention.qkv projection). */
 int gvk_small_matmul(const float* a, int lda, int ra, const float* w, int rb, int M, float* out, int ldo, gvk_stream_t stream);
 
 /* y[m, n] += / = colsum helpers: out[c] += sum_m x[m, c]  (bias gradients; bitfit). */

@@ -39,7 +39,40 @@ def build_variant(ref, method, kw):
     raise ValueError(method)
 
 
-def run_case(ref, model, kw, batch, name):
+def reference_bf16_deviation(ref, model, img, y, fp32_out):
+    """How far the reference's OWN pure-bf16 run (``model.to(torch.bfloat16)``, window mask cast by hand, CPU) lands from its
+    fp32 run on the same weights: the bf16 noise floor our bf16 mode is judged against."""
+    m = model.to(torch.bfloat16)
+    for la in m.transformer.local_attns:
+        la.mask = la.mask.to(torch.bfloat16)          # plain attribute, does not follow .to() (model/gaviko.py:227)
+    res = {}
+    for loss_name, crit in (('focal', ref.FocalLoss(gamma=1.2)), ('ce', torch.nn.CrossEntropyLoss())):
+        m.zero_grad(set_to_none=True)
+        logits = m(img.bfloat16())
+        crit(logits.float(), y).backward()
+        num = den = 0.0
+        worst = 0.0
+        rows = []
+        for n, p in m.named_parameters():
+            if p.requires_grad:
+                r = fp32_out[f'grad_{loss_name}/{n}'].astype(np.float64)
+                d = float(np.linalg.norm(p.grad.double().numpy() - r))
+                rows.append((d, float(np.linalg.norm(r))))
+                num += d * d
+                den += rows[-1][1] ** 2
+        gn = den ** 0.5
+        for d, rn in rows:
+            if rn > 1e-3 * gn:
+                worst = max(worst, d / rn)
+        res[f'refbf16_grad_global_{loss_name}'] = np.float64(num ** 0.5 / gn)
+        res[f'refbf16_grad_worst_{loss_name}'] = np.float64(worst)
+        lf = fp32_out['logits'].astype(np.float64)
+        res['refbf16_logits_rel'] = np.float64(np.linalg.norm(logits.float().detach().numpy() - lf) / np.linalg.norm(lf))
+    print('   reference bf16 deviation:', {k: float(v) for k, v in res.items()})
+    return res
+
+
+def run_case(ref, model, kw, batch, name, bf16_floor=False):
     golden_fill(model, seed=0)
     model.eval()
     img = golden_volume(batch, kw['frames'], kw['image_size'], kw['image_size'], channels=kw['channels'])
@@ -61,6 +94,8 @@ def run_case(ref, model, kw, batch, name):
             if p.requires_grad:
                 assert p.grad is not None, (name, n)
                 out[f'grad_{loss_name}/{n}'] = p.grad.detach().numpy().copy()
+    if bf16_floor:
+        out.update(reference_bf16_deviation(ref, model, img, y, out))
     np.savez_compressed(os.path.join(OUT, name + '.npz'), **out)
     print(name, 'logits', out['logits'][0], 'focal', float(out['loss_focal']), 'ce', float(out['loss_ce']), 'trainable', len(names))
 
@@ -103,7 +138,7 @@ def main():
         focal_known_answers(ref)
         window_masks(ref)
         for name, (kw, batch) in GAVIKO_CASES.items():
-            run_case(ref, ref.Gaviko(**kw), kw, batch, name)
+            run_case(ref, ref.Gaviko(**kw), kw, batch, name, bf16_floor=True)
         for name, (method, kw, batch) in VARIANT_CASES.items():
             run_case(ref, build_variant(ref, method, kw), kw, batch, name)
     finally:
