@@ -108,5 +108,16 @@ def stream():
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
+# Optional per-entry-point timing (tools/profile_step.py): PROFILE = {} enables CUDA-event brackets around every C-ABI call.
+PROFILE = None
+
+
 def call(name, *args):
+    if PROFILE is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        check(getattr(lib(), name)(*args), name)
+        e1.record()
+        PROFILE.setdefault(name, []).append((e0, e1))
+        return
     check(getattr(lib(), name)(*args), name)

@@ -96,7 +96,7 @@ long long gvk_struct_size(const char* name) {
   GVK_SZ(gvk_gemm_params) GVK_SZ(gvk_layernorm_fwd_params) GVK_SZ(gvk_rowproj_down_params) GVK_SZ(gvk_rowproj_up_params)
   GVK_SZ(gvk_skinny_wgrad_params) GVK_SZ(gvk_layernorm_bwd_params) GVK_SZ(gvk_attn_fwd_params) GVK_SZ(gvk_attn_bwd_params)
   GVK_SZ(gvk_fusion_weights) GVK_SZ(gvk_fusion_grads) GVK_SZ(gvk_fusion_saved) GVK_SZ(gvk_fusion_fwd_params)
-  GVK_SZ(gvk_fusion_bwd_params) GVK_SZ(gvk_head_fwd_params) GVK_SZ(gvk_head_bwd_params)
+  GVK_SZ(gvk_fusion_bwd_params) GVK_SZ(gvk_head_fwd_params) GVK_SZ(gvk_head_bwd_params) GVK_SZ(gvk_mhsa_fwd_params) GVK_SZ(gvk_mhsa_bwd_params)
 #undef GVK_SZ
   return -1;
 }
@@ -134,6 +134,13 @@ int gvk_loss_fwd_bwd(const float* logits, const long long* target, int B, int C,
 int gvk_small_matmul(const float* a, int lda, int ra, const float* w, int rb, int M, float* out, int ldo, gvk_stream_t stream) {
   return gvk::small_matmul(a, lda, ra, w, rb, M, out, ldo, S(stream));
 }
+int gvk_grad_sumsq(const float* grad, size_t n, float grad_scale, float* partials, gvk_stream_t stream) { return gvk::grad_sumsq(grad, n, grad_scale, partials, S(stream)); }
+int gvk_clip_adam(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, size_t n, const float* partials, float max_norm, float grad_scale, float lr,
+                  float beta1, float beta2, float eps, float weight_decay, int step, float* grad_norm_out, gvk_stream_t stream) {
+  return gvk::clip_adam(param, grad, exp_avg, exp_avg_sq, n, partials, max_norm, grad_scale, lr, beta1, beta2, eps, weight_decay, step, grad_norm_out, S(stream));
+}
+int gvk_mhsa_fwd(const gvk_mhsa_fwd_params* p, gvk_stream_t stream) { return gvk::mhsa_fwd(p, S(stream)); }
+int gvk_mhsa_bwd(const gvk_mhsa_bwd_params* p, gvk_stream_t stream) { return gvk::mhsa_bwd(p, S(stream)); }
 int gvk_colsum(const float* x, int ldx, int M, int dim, float* out, gvk_stream_t stream) { return gvk::colsum(x, ldx, M, dim, out, S(stream)); }
 int gvk_cast_f32_bf16(const float* x, int ldx, void* y, int ldy, int M, int dim, gvk_stream_t stream) {
   return gvk::cast_f32_bf16(x, ldx, y, ldy, M, dim, S(stream));

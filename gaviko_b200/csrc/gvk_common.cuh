@@ -55,6 +55,11 @@ int attn_simt_bwd(const gvk_attn_bwd_params* p, cudaStream_t stream);
 int patch_gather(const float* img, int B, int C, int D, int H, int W, int fp, int ps, void* patches, int out_dtype, cudaStream_t stream);
 int fill_rows(const float* a, const float* b, int R, int dim, float* out, int ld_out, int out_batch_rows, int out_row_offset, int B, cudaStream_t stream);
 int batch_rowsum(const float* x, int ldx, int batch_rows, int row_offset, int R, int dim, int B, float* out, int accumulate, cudaStream_t stream);
+int grad_sumsq(const float* grad, size_t n, float grad_scale, float* partials, cudaStream_t stream);
+int clip_adam(float* param, const float* grad, float* m, float* v, size_t n, const float* partials, float max_norm, float grad_scale, float lr, float beta1,
+              float beta2, float eps, float wd, int step, float* norm_out, cudaStream_t stream);
+int mhsa_fwd(const gvk_mhsa_fwd_params* p, cudaStream_t stream);
+int mhsa_bwd(const gvk_mhsa_bwd_params* p, cudaStream_t stream);
 int prompt_fusion_fwd(const gvk_fusion_fwd_params* p, cudaStream_t stream);
 int prompt_fusion_bwd(const gvk_fusion_bwd_params* p, cudaStream_t stream);
 int quickgelu_bwd(const float* dy, const float* pre, float* y, size_t n, cudaStream_t stream);

@@ -1,0 +1,600 @@
+// gvk_mhsa_sm100.cu — flash-style multi-head self-attention on the 5th-gen tensor cores (see include/gvk.h: gvk_mhsa_fwd / _bwd).
+//
+// One CTA = 128 threads = one 128-row tile of one (volume, head).  Thread t owns row t of the tile (TMEM lane t), so the row-wise
+// softmax needs no cross-thread reductions.  Operand tiles are TMA loads with SWIZZLE_128B; S = Q K^T, P V and the backward
+// products are tcgen05.mma with fp32 accumulators in TMEM; P / dS go registers -> swizzled smem -> A operand of the next MMA.
+// "Transposed" products (P V, dS K, P^T dO, dS^T Q) read their [rows x 64] TMA tiles as MN-major B operands, so no tensor is
+// ever transposed in memory.  Two or three CTAs are resident per SM, which is what overlaps one CTA's softmax with another's MMAs.
+//
+//   forward  : grid (ceil(T/128), B*H); loop over 64-row K/V tiles; online softmax; O accumulated in registers.
+//   backward : dQ kernel  — grid (ceil(T/128), B*H) over query tiles, loops over 64-row K/V tiles (also writes delta = rowsum(dO*O));
+//              dKV kernel — grid (ceil(T/128), B*H) over key tiles, loops over 64-row Q/dO tiles.
+//              Two kernels instead of one fused kernel: no atomics on dQ, deterministic results.
+// Replaces reference model/vision_transformer.py:65-71 (+ its autograd backward), which materialises (B, H, T, T) twice.
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+
+#include "gvk_common.cuh"
+
+namespace gvk {
+
+constexpr int kFaThreads = 128;
+constexpr int kFaD = 64;               // head dim
+constexpr int kTileBytes128 = 128 * 128;  // [128 rows x 64 bf16]
+constexpr int kTileBytes64 = 64 * 128;    // [ 64 rows x 64 bf16]
+constexpr float kLog2e = 1.4426950408889634f;
+
+struct FaDesc {  // MN-major descriptor fields (debug-tunable through GVK_FA_DESC="lbo,sbo,kadv")
+  uint32_t lbo, sbo, kadv;
+};
+
+__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+// Write 64 consecutive values of row r into a [rows x 64] bf16 K-major SWIZZLE_128B tile (the layout TMA would produce).
+__device__ __forceinline__ void store_row_sw128(uint8_t* tile, int r, const float (&v)[64]) {
+  uint8_t* row = tile + r * 128;
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    uint4 pk;
+    pk.x = pack_bf16(v[8 * c + 0], v[8 * c + 1]);
+    pk.y = pack_bf16(v[8 * c + 2], v[8 * c + 3]);
+    pk.z = pack_bf16(v[8 * c + 4], v[8 * c + 5]);
+    pk.w = pack_bf16(v[8 * c + 6], v[8 * c + 7]);
+    *reinterpret_cast<uint4*>(row + ((c ^ (r & 7)) << 4)) = pk;
+  }
+}
+__device__ __forceinline__ void tmem_ld64(uint32_t taddr, float (&v)[64]) {
+  tmem_ld_32x32(taddr, *reinterpret_cast<float(*)[32]>(&v[0]));
+  tmem_ld_32x32(taddr + 32, *reinterpret_cast<float(*)[32]>(&v[32]));
+}
+// D[tmem, 128 x 64] (+)= A[128 x 64 K-major tile] * B[64 x 64 K-major tile]^T
+__device__ __forceinline__ void mma_kk(uint32_t d_tmem, const void* a, const void* b, bool accumulate) {
+  constexpr uint32_t idesc = make_idesc_bf16(128, 64, 0, 0);
+  const uint32_t a_addr = smem_u32(a), b_addr = smem_u32(b);
+#pragma unroll
+  for (int k = 0; k < 4; ++k)
+    umma_bf16(d_tmem, make_sw128_desc(a_addr + k * 32, 16, 1024), make_sw128_desc(b_addr + k * 32, 16, 1024), idesc, (accumulate || k > 0) ? 1u : 0u);
+}
+// D[tmem, 128 x 64] (+)= A[128 x 64 K-major tile] * B, with B given as a [64 (k) rows x 64 (n)] tile (n contiguous): MN-major B
+__device__ __forceinline__ void mma_kmn(uint32_t d_tmem, const void* a, const void* b, bool accumulate, const FaDesc& fd) {
+  constexpr uint32_t idesc = make_idesc_bf16(128, 64, 0, 1);
+  const uint32_t a_addr = smem_u32(a), b_addr = smem_u32(b);
+#pragma unroll
+  for (int k = 0; k < 4; ++k)
+    umma_bf16(d_tmem, make_sw128_desc(a_addr + k * 32, 16, 1024), make_sw128_desc(b_addr + k * fd.kadv, fd.lbo, fd.sbo), idesc, (accumulate || k > 0) ? 1u : 0u);
+}
+
+struct FaCommon {
+  int B, T, H, dim;
+  float scale;
+};
+
+// =================================================================================================
+// forward
+// =================================================================================================
+struct FwdArgs {
+  FaCommon c;
+  __nv_bfloat16* out;
+  int ld_out;
+  float* lse;
+  FaDesc fd;
+};
+constexpr int kFwdSmem = kTileBytes128 /*Q*/ + 2 * 2 * kTileBytes64 /*K,V x2*/ + kTileBytes128 /*P*/ + 128 + 1024;
+
+__global__ void __launch_bounds__(kFaThreads, 3)
+mhsa_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant__ CUtensorMap tma_kv, FwdArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;
+  uint8_t* sK = sQ + kTileBytes128;            // 2 stages
+  uint8_t* sV = sK + 2 * kTileBytes64;         // 2 stages
+  uint8_t* sP = sV + 2 * kTileBytes64;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + kTileBytes128);  // q, kv0, kv1, s, pv
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int q0 = blockIdx.x * 128;
+  const int bh = blockIdx.y, h = bh % a.c.H, b = bh / a.c.H;
+  const int T = a.c.T, dim = a.c.dim;
+
+  if (tid == 0) {
+    tma_prefetch_desc(&tma_q);
+    tma_prefetch_desc(&tma_kv);
+    for (int i = 0; i < 5; ++i) mbar_init(&bars[i], 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) {
+    tmem_alloc(tmem_slot, 128);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const uint32_t t_s = tmem, t_pv = tmem + 64;
+  const uint32_t lane_off = static_cast<uint32_t>(warp * 32) << 16;
+  uint64_t *bar_q = &bars[0], *bar_kv = &bars[1], *bar_s = &bars[3], *bar_pv = &bars[4];
+
+  const int nkv = (T + 63) / 64;
+  if (tid == 0) {
+    mbar_arrive_expect_tx(bar_q, kTileBytes128);
+    tma_load_3d(sQ, &tma_q, bar_q, h * kFaD, q0, b);
+    mbar_arrive_expect_tx(&bar_kv[0], 2 * kTileBytes64);
+    tma_load_3d(sK, &tma_kv, &bar_kv[0], dim + h * kFaD, 0, b);
+    tma_load_3d(sV, &tma_kv, &bar_kv[0], 2 * dim + h * kFaD, 0, b);
+  }
+  const float c2 = a.c.scale * kLog2e;
+  float m = -INFINITY, l = 0.f;
+  float o[64];
+#pragma unroll
+  for (int i = 0; i < 64; ++i) o[i] = 0.f;
+  mbar_wait(bar_q, 0);
+
+  for (int j = 0; j < nkv; ++j) {
+    const int buf = j & 1;
+    if (tid == 0 && j + 1 < nkv) {
+      mbar_arrive_expect_tx(&bar_kv[buf ^ 1], 2 * kTileBytes64);
+      tma_load_3d(sK + (buf ^ 1) * kTileBytes64, &tma_kv, &bar_kv[buf ^ 1], dim + h * kFaD, (j + 1) * 64, b);
+      tma_load_3d(sV + (buf ^ 1) * kTileBytes64, &tma_kv, &bar_kv[buf ^ 1], 2 * dim + h * kFaD, (j + 1) * 64, b);
+    }
+    mbar_wait(&bar_kv[buf], (j >> 1) & 1);
+    if (tid == 0) {
+      tc_fence_after();
+      mma_kk(t_s, sQ, sK + buf * kTileBytes64, false);
+      umma_commit(bar_s);
+    }
+    mbar_wait(bar_s, j & 1);
+    tc_fence_after();
+    float s[64];
+    tmem_ld64(t_s + lane_off, s);
+    tc_wait_ld();
+    const int valid = T - j * 64;  // columns >= valid are padding (zero-filled K rows)
+    if (valid < 64) {
+#pragma unroll
+      for (int i = 0; i < 64; ++i)
+        if (i >= valid) s[i] = -INFINITY;
+    }
+    float mx = m;
+#pragma unroll
+    for (int i = 0; i < 64; ++i) mx = fmaxf(mx, s[i]);
+    const float alpha = exp2f((m - mx) * c2);
+    m = mx;
+    const float mc = mx * c2;
+    float rs = 0.f;
+#pragma unroll
+    for (int i = 0; i < 64; ++i) {
+      s[i] = exp2f(fmaf(s[i], c2, -mc));
+      rs += s[i];
+    }
+    l = fmaf(l, alpha, rs);
+#pragma unroll
+    for (int i = 0; i < 64; ++i) o[i] *= alpha;
+    store_row_sw128(sP, tid, s);
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    if (tid == 0) {
+      tc_fence_after();
+      mma_kmn(t_pv, sP, sV + buf * kTileBytes64, false, a.fd);
+      umma_commit(bar_pv);
+    }
+    mbar_wait(bar_pv, j & 1);
+    tc_fence_after();
+    tmem_ld64(t_pv + lane_off, s);
+    tc_wait_ld();
+#pragma unroll
+    for (int i = 0; i < 64; ++i) o[i] += s[i];
+  }
+  const int row = q0 + tid;
+  if (row < T) {
+    const float inv = 1.0f / l;
+    uint4* dst = reinterpret_cast<uint4*>(a.out + ((size_t)b * T + row) * a.ld_out + h * kFaD);
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      uint4 pk;
+      pk.x = pack_bf16(o[8 * c + 0] * inv, o[8 * c + 1] * inv);
+      pk.y = pack_bf16(o[8 * c + 2] * inv, o[8 * c + 3] * inv);
+      pk.z = pack_bf16(o[8 * c + 4] * inv, o[8 * c + 5] * inv);
+      pk.w = pack_bf16(o[8 * c + 6] * inv, o[8 * c + 7] * inv);
+      dst[c] = pk;
+    }
+    a.lse[(size_t)bh * T + row] = m * a.c.scale + __logf(l);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, 128);
+}
+
+// =================================================================================================
+// backward: dQ (and delta)
+// =================================================================================================
+struct BwdArgs {
+  FaCommon c;
+  const __nv_bfloat16* out;
+  int ld_out;
+  const __nv_bfloat16* dout;
+  int ld_dout;
+  const float* lse;
+  float* delta;
+  __nv_bfloat16* dqkv;
+  int ld_dqkv;
+  FaDesc fd;
+};
+constexpr int kDqSmem = 2 * kTileBytes128 /*Q,dO*/ + 2 * 2 * kTileBytes64 /*K,V x2*/ + kTileBytes128 /*dS*/ + 128 + 1024;
+
+__global__ void __launch_bounds__(kFaThreads, 2)
+mhsa_bwd_dq_sm100_kernel(const __grid_constant__ CUtensorMap tma_q128, const __grid_constant__ CUtensorMap tma_kv64, const __grid_constant__ CUtensorMap tma_do128,
+                         BwdArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;
+  uint8_t* sdO = sQ + kTileBytes128;
+  uint8_t* sK = sdO + kTileBytes128;
+  uint8_t* sV = sK + 2 * kTileBytes64;
+  uint8_t* sdS = sV + 2 * kTileBytes64;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sdS + kTileBytes128);  // q, kv0, kv1, s, dq
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int q0 = blockIdx.x * 128;
+  const int bh = blockIdx.y, h = bh % a.c.H, b = bh / a.c.H;
+  const int T = a.c.T, dim = a.c.dim;
+
+  if (tid == 0) {
+    tma_prefetch_desc(&tma_q128);
+    tma_prefetch_desc(&tma_kv64);
+    tma_prefetch_desc(&tma_do128);
+    for (int i = 0; i < 5; ++i) mbar_init(&bars[i], 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) {
+    tmem_alloc(tmem_slot, 256);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const uint32_t t_s = tmem, t_dp = tmem + 64, t_dq = tmem + 128;
+  const uint32_t lane_off = static_cast<uint32_t>(warp * 32) << 16;
+  uint64_t *bar_q = &bars[0], *bar_kv = &bars[1], *bar_s = &bars[3], *bar_dq = &bars[4];
+  const int nkv = (T + 63) / 64;
+  if (tid == 0) {
+    mbar_arrive_expect_tx(bar_q, 2 * kTileBytes128);
+    tma_load_3d(sQ, &tma_q128, bar_q, h * kFaD, q0, b);
+    tma_load_3d(sdO, &tma_do128, bar_q, h * kFaD, q0, b);
+    mbar_arrive_expect_tx(&bar_kv[0], 2 * kTileBytes64);
+    tma_load_3d(sK, &tma_kv64, &bar_kv[0], dim + h * kFaD, 0, b);
+    tma_load_3d(sV, &tma_kv64, &bar_kv[0], 2 * dim + h * kFaD, 0, b);
+  }
+  // delta_r = sum_d dO[r,d] * O[r,d]; lse in log2 units
+  const int row = q0 + tid;
+  float delta = 0.f, lse2 = 0.f;
+  if (row < T) {
+    const uint4* po = reinterpret_cast<const uint4*>(a.out + ((size_t)b * T + row) * a.ld_out + h * kFaD);
+    const uint4* pd = reinterpret_cast<const uint4*>(a.dout + ((size_t)b * T + row) * a.ld_dout + h * kFaD);
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      const uint4 x = po[c], y = pd[c];
+      const uint32_t xs[4] = {x.x, x.y, x.z, x.w}, ys[4] = {y.x, y.y, y.z, y.w};
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const float2 fx = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&xs[u]));
+        const float2 fy = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&ys[u]));
+        delta = fmaf(fx.x, fy.x, delta);
+        delta = fmaf(fx.y, fy.y, delta);
+      }
+    }
+    a.delta[(size_t)bh * T + row] = delta;
+    lse2 = a.lse[(size_t)bh * T + row] * kLog2e;
+  }
+  const float c2 = a.c.scale * kLog2e;
+  mbar_wait(bar_q, 0);
+  for (int j = 0; j < nkv; ++j) {
+    const int buf = j & 1;
+    if (tid == 0 && j + 1 < nkv) {
+      mbar_arrive_expect_tx(&bar_kv[buf ^ 1], 2 * kTileBytes64);
+      tma_load_3d(sK + (buf ^ 1) * kTileBytes64, &tma_kv64, &bar_kv[buf ^ 1], dim + h * kFaD, (j + 1) * 64, b);
+      tma_load_3d(sV + (buf ^ 1) * kTileBytes64, &tma_kv64, &bar_kv[buf ^ 1], 2 * dim + h * kFaD, (j + 1) * 64, b);
+    }
+    mbar_wait(&bar_kv[buf], (j >> 1) & 1);
+    if (tid == 0) {
+      tc_fence_after();
+      mma_kk(t_s, sQ, sK + buf * kTileBytes64, false);      // S  = Q K^T
+      mma_kk(t_dp, sdO, sV + buf * kTileBytes64, false);    // dP = dO V^T
+      umma_commit(bar_s);
+    }
+    mbar_wait(bar_s, j & 1);
+    tc_fence_after();
+    float s[64], dp[64];
+    tmem_ld64(t_s + lane_off, s);
+    tmem_ld64(t_dp + lane_off, dp);
+    tc_wait_ld();
+    const int valid = T - j * 64;
+#pragma unroll
+    for (int i = 0; i < 64; ++i) {
+      const float p = (i < valid) ? exp2f(fmaf(s[i], c2, -lse2)) : 0.f;
+      s[i] = p * (dp[i] - delta);  // dS
+    }
+    store_row_sw128(sdS, tid, s);
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    if (tid == 0) {
+      tc_fence_after();
+      mma_kmn(t_dq, sdS, sK + buf * kTileBytes64, j > 0, a.fd);   // dQ += dS K
+      umma_commit(bar_dq);
+    }
+    mbar_wait(bar_dq, j & 1);
+  }
+  tc_fence_after();
+  {
+    float dq[64];
+    tmem_ld64(t_dq + lane_off, dq);
+    tc_wait_ld();
+    if (row < T) {
+      uint4* dst = reinterpret_cast<uint4*>(a.dqkv + ((size_t)b * T + row) * a.ld_dqkv + h * kFaD);
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        uint4 pk;
+        pk.x = pack_bf16(dq[8 * c + 0] * a.c.scale, dq[8 * c + 1] * a.c.scale);
+        pk.y = pack_bf16(dq[8 * c + 2] * a.c.scale, dq[8 * c + 3] * a.c.scale);
+        pk.z = pack_bf16(dq[8 * c + 4] * a.c.scale, dq[8 * c + 5] * a.c.scale);
+        pk.w = pack_bf16(dq[8 * c + 6] * a.c.scale, dq[8 * c + 7] * a.c.scale);
+        dst[c] = pk;
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, 256);
+}
+
+// =================================================================================================
+// backward: dK, dV
+// =================================================================================================
+constexpr int kDkvSmem = 2 * kTileBytes128 /*K,V*/ + 2 * 2 * kTileBytes64 /*Q,dO x2*/ + 2 * kTileBytes128 /*P^T, dS^T*/ + 2 * 2 * 64 * 4 /*lse2, delta x2*/ + 128 + 1024;
+
+__global__ void __launch_bounds__(kFaThreads, 2)
+mhsa_bwd_dkv_sm100_kernel(const __grid_constant__ CUtensorMap tma_kv128, const __grid_constant__ CUtensorMap tma_q64, const __grid_constant__ CUtensorMap tma_do64,
+                          BwdArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sK = smem;
+  uint8_t* sV = sK + kTileBytes128;
+  uint8_t* sQ = sV + kTileBytes128;            // 2 stages of [64 x 64]
+  uint8_t* sdO = sQ + 2 * kTileBytes64;        // 2 stages
+  uint8_t* sP = sdO + 2 * kTileBytes64;        // [128 kv x 64 q]
+  uint8_t* sdS = sP + kTileBytes128;
+  float* s_lse2 = reinterpret_cast<float*>(sdS + kTileBytes128);  // [2][64]
+  float* s_delta = s_lse2 + 128;                                  // [2][64]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_delta + 128);    // kv, q0, q1, s, acc
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int k0 = blockIdx.x * 128;
+  const int bh = blockIdx.y, h = bh % a.c.H, b = bh / a.c.H;
+  const int T = a.c.T, dim = a.c.dim;
+
+  if (tid == 0) {
+    tma_prefetch_desc(&tma_kv128);
+    tma_prefetch_desc(&tma_q64);
+    tma_prefetch_desc(&tma_do64);
+    for (int i = 0; i < 5; ++i) mbar_init(&bars[i], 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) {
+    tmem_alloc(tmem_slot, 256);
+    tmem_relinquish();
+  }
+  const int nq = (T + 63) / 64;
+  auto load_stats = [&](int i, int st) {  // lse (log2 units) and delta of q tile i -> stage st; called by threads 0..63
+    const int q = i * 64 + tid;
+    s_lse2[st * 64 + tid] = (q < T) ? a.lse[(size_t)bh * T + q] * kLog2e : 0.f;
+    s_delta[st * 64 + tid] = (q < T) ? a.delta[(size_t)bh * T + q] : 0.f;
+  };
+  if (tid < 64) load_stats(0, 0);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const uint32_t t_s = tmem, t_dp = tmem + 64, t_dv = tmem + 128, t_dk = tmem + 192;
+  const uint32_t lane_off = static_cast<uint32_t>(warp * 32) << 16;
+  uint64_t *bar_kv = &bars[0], *bar_q = &bars[1], *bar_s = &bars[3], *bar_acc = &bars[4];
+  if (tid == 0) {
+    mbar_arrive_expect_tx(bar_kv, 2 * kTileBytes128);
+    tma_load_3d(sK, &tma_kv128, bar_kv, dim + h * kFaD, k0, b);
+    tma_load_3d(sV, &tma_kv128, bar_kv, 2 * dim + h * kFaD, k0, b);
+    mbar_arrive_expect_tx(&bar_q[0], 2 * kTileBytes64);
+    tma_load_3d(sQ, &tma_q64, &bar_q[0], h * kFaD, 0, b);
+    tma_load_3d(sdO, &tma_do64, &bar_q[0], h * kFaD, 0, b);
+  }
+  const float c2 = a.c.scale * kLog2e;
+  const bool row_valid = (k0 + tid) < T;
+  mbar_wait(bar_kv, 0);
+  for (int i = 0; i < nq; ++i) {
+    const int buf = i & 1;
+    if (i + 1 < nq) {
+      if (tid == 0) {
+        mbar_arrive_expect_tx(&bar_q[buf ^ 1], 2 * kTileBytes64);
+        tma_load_3d(sQ + (buf ^ 1) * kTileBytes64, &tma_q64, &bar_q[buf ^ 1], h * kFaD, (i + 1) * 64, b);
+        tma_load_3d(sdO + (buf ^ 1) * kTileBytes64, &tma_do64, &bar_q[buf ^ 1], h * kFaD, (i + 1) * 64, b);
+      }
+      if (tid < 64) load_stats(i + 1, buf ^ 1);  // made visible by this iteration's __syncthreads
+    }
+    mbar_wait(&bar_q[buf], (i >> 1) & 1);
+    if (tid == 0) {
+      tc_fence_after();
+      mma_kk(t_s, sK, sQ + buf * kTileBytes64, false);      // S^T  = K Q^T
+      mma_kk(t_dp, sV, sdO + buf * kTileBytes64, false);    // dP^T = V dO^T
+      umma_commit(bar_s);
+    }
+    mbar_wait(bar_s, i & 1);
+    tc_fence_after();
+    float s[64], dp[64];
+    tmem_ld64(t_s + lane_off, s);
+    tmem_ld64(t_dp + lane_off, dp);
+    tc_wait_ld();
+    const int valid = row_valid ? T - i * 64 : 0;
+    const float* lse2 = s_lse2 + buf * 64;
+    const float* del = s_delta + buf * 64;
+#pragma unroll
+    for (int q = 0; q < 64; ++q) {
+      const float p = (q < valid) ? exp2f(fmaf(s[q], c2, -lse2[q])) : 0.f;
+      s[q] = p;                       // P^T
+      dp[q] = p * (dp[q] - del[q]);   // dS^T
+    }
+    store_row_sw128(sP, tid, s);
+    store_row_sw128(sdS, tid, dp);
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    if (tid == 0) {
+      tc_fence_after();
+      mma_kmn(t_dv, sP, sdO + buf * kTileBytes64, i > 0, a.fd);   // dV += P^T dO
+      mma_kmn(t_dk, sdS, sQ + buf * kTileBytes64, i > 0, a.fd);   // dK += dS^T Q
+      umma_commit(bar_acc);
+    }
+    mbar_wait(bar_acc, i & 1);
+  }
+  tc_fence_after();
+  {
+    float v[64];
+    const int row = k0 + tid;
+    __nv_bfloat16* base = a.dqkv + ((size_t)b * T + row) * a.ld_dqkv + h * kFaD;
+    tmem_ld64(t_dk + lane_off, v);
+    tc_wait_ld();
+    if (row < T) {
+      uint4* dst = reinterpret_cast<uint4*>(base + dim);
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        uint4 pk;
+        pk.x = pack_bf16(v[8 * c + 0] * a.c.scale, v[8 * c + 1] * a.c.scale);
+        pk.y = pack_bf16(v[8 * c + 2] * a.c.scale, v[8 * c + 3] * a.c.scale);
+        pk.z = pack_bf16(v[8 * c + 4] * a.c.scale, v[8 * c + 5] * a.c.scale);
+        pk.w = pack_bf16(v[8 * c + 6] * a.c.scale, v[8 * c + 7] * a.c.scale);
+        dst[c] = pk;
+      }
+    }
+    tmem_ld64(t_dv + lane_off, v);
+    tc_wait_ld();
+    if (row < T) {
+      uint4* dst = reinterpret_cast<uint4*>(base + 2 * dim);
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        uint4 pk;
+        pk.x = pack_bf16(v[8 * c + 0], v[8 * c + 1]);
+        pk.y = pack_bf16(v[8 * c + 2], v[8 * c + 3]);
+        pk.z = pack_bf16(v[8 * c + 4], v[8 * c + 5]);
+        pk.w = pack_bf16(v[8 * c + 6], v[8 * c + 7]);
+        dst[c] = pk;
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, 256);
+}
+
+// =================================================================================================
+// host
+// =================================================================================================
+static FaDesc fa_desc() {
+  static FaDesc fd = {8192, 1024, 2048};
+  static bool init = false;
+  if (!init) {
+    init = true;
+    if (const char* e = getenv("GVK_FA_DESC")) {
+      unsigned a, b, c;
+      if (sscanf(e, "%u,%u,%u", &a, &b, &c) == 3) fd = {a, b, c};
+    }
+  }
+  return fd;
+}
+
+template <typename K>
+static int set_smem(K kern, int bytes, const char* what) {
+  return cuda_status(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes), what);
+}
+
+static int check_common(const void* qkv, int ld, int B, int T, int H, const char* who) {
+  GVK_CHECK_ARG(qkv && B > 0 && T > 0 && H > 0, "%s: bad argument", who);
+  GVK_CHECK_ARG(ld % 8 == 0 && ld >= 3 * H * kFaD, "%s: ld=%d must be a multiple of 8 and >= 3*H*64", who, ld);
+  GVK_CHECK_ARG((reinterpret_cast<uintptr_t>(qkv) & 15) == 0, "%s: qkv must be 16-byte aligned", who);
+  GVK_CHECK_ARG((long long)B * H <= 65535, "%s: B*H=%lld exceeds the grid limit", who, (long long)B * H);
+  return GVK_OK;
+}
+
+int mhsa_fwd(const gvk_mhsa_fwd_params* p, cudaStream_t stream) {
+  GVK_CHECK_ARG(p && p->out && p->lse, "gvk_mhsa_fwd: null pointer");
+  int st = check_common(p->qkv, p->ld, p->B, p->T, p->H, "gvk_mhsa_fwd");
+  if (st != GVK_OK) return st;
+  GVK_CHECK_ARG(p->ld_out % 8 == 0, "gvk_mhsa_fwd: ld_out must be a multiple of 8");
+  static bool configured = false;
+  if (!configured) {
+    st = set_smem(mhsa_fwd_sm100_kernel, kFwdSmem, "mhsa_fwd smem");
+    if (st != GVK_OK) return st;
+    configured = true;
+  }
+  const int dim = p->H * kFaD;
+  CUtensorMap tq, tkv;
+  st = make_tma_3d_bf16(&tq, p->qkv, p->B, p->T, 3 * dim, p->ld, (uint64_t)p->T * p->ld, 128, 64);
+  if (st != GVK_OK) return st;
+  st = make_tma_3d_bf16(&tkv, p->qkv, p->B, p->T, 3 * dim, p->ld, (uint64_t)p->T * p->ld, 64, 64);
+  if (st != GVK_OK) return st;
+  FwdArgs a;
+  a.c = {p->B, p->T, p->H, dim, p->scale};
+  a.out = reinterpret_cast<__nv_bfloat16*>(p->out);
+  a.ld_out = p->ld_out;
+  a.lse = p->lse;
+  a.fd = fa_desc();
+  dim3 grid((p->T + 127) / 128, p->B * p->H);
+  mhsa_fwd_sm100_kernel<<<grid, kFaThreads, kFwdSmem, stream>>>(tq, tkv, a);
+  GVK_CHECK_LAUNCH("mhsa_fwd_sm100");
+  return GVK_OK;
+}
+
+int mhsa_bwd(const gvk_mhsa_bwd_params* p, cudaStream_t stream) {
+  GVK_CHECK_ARG(p && p->out && p->lse && p->dout && p->delta && p->dqkv, "gvk_mhsa_bwd: null pointer");
+  int st = check_common(p->qkv, p->ld, p->B, p->T, p->H, "gvk_mhsa_bwd");
+  if (st != GVK_OK) return st;
+  GVK_CHECK_ARG(p->ld_out % 8 == 0 && p->ld_dout % 8 == 0 && p->ld_dqkv % 8 == 0, "gvk_mhsa_bwd: leading dimensions must be multiples of 8");
+  GVK_CHECK_ARG((reinterpret_cast<uintptr_t>(p->dout) & 15) == 0, "gvk_mhsa_bwd: dout must be 16-byte aligned");
+  static bool configured = false;
+  if (!configured) {
+    st = set_smem(mhsa_bwd_dq_sm100_kernel, kDqSmem, "mhsa_bwd_dq smem");
+    if (st != GVK_OK) return st;
+    st = set_smem(mhsa_bwd_dkv_sm100_kernel, kDkvSmem, "mhsa_bwd_dkv smem");
+    if (st != GVK_OK) return st;
+    configured = true;
+  }
+  const int dim = p->H * kFaD;
+  CUtensorMap tq128, tq64, tdo128, tdo64;
+  st = make_tma_3d_bf16(&tq128, p->qkv, p->B, p->T, 3 * dim, p->ld, (uint64_t)p->T * p->ld, 128, 64);
+  if (st != GVK_OK) return st;
+  st = make_tma_3d_bf16(&tq64, p->qkv, p->B, p->T, 3 * dim, p->ld, (uint64_t)p->T * p->ld, 64, 64);
+  if (st != GVK_OK) return st;
+  st = make_tma_3d_bf16(&tdo128, p->dout, p->B, p->T, dim, p->ld_dout, (uint64_t)p->T * p->ld_dout, 128, 64);
+  if (st != GVK_OK) return st;
+  st = make_tma_3d_bf16(&tdo64, p->dout, p->B, p->T, dim, p->ld_dout, (uint64_t)p->T * p->ld_dout, 64, 64);
+  if (st != GVK_OK) return st;
+  BwdArgs a;
+  a.c = {p->B, p->T, p->H, dim, p->scale};
+  a.out = reinterpret_cast<const __nv_bfloat16*>(p->out);
+  a.ld_out = p->ld_out;
+  a.dout = reinterpret_cast<const __nv_bfloat16*>(p->dout);
+  a.ld_dout = p->ld_dout;
+  a.lse = p->lse;
+  a.delta = p->delta;
+  a.dqkv = reinterpret_cast<__nv_bfloat16*>(p->dqkv);
+  a.ld_dqkv = p->ld_dqkv;
+  a.fd = fa_desc();
+  dim3 grid((p->T + 127) / 128, p->B * p->H);
+  mhsa_bwd_dq_sm100_kernel<<<grid, kFaThreads, kDqSmem, stream>>>(tq128, tq64, tdo128, a);
+  GVK_CHECK_LAUNCH("mhsa_bwd_dq_sm100");
+  mhsa_bwd_dkv_sm100_kernel<<<grid, kFaThreads, kDkvSmem, stream>>>(tq128, tq64, tdo64, a);
+  GVK_CHECK_LAUNCH("mhsa_bwd_dkv_sm100");
+  return GVK_OK;
+}
+
+}  // namespace gvk

@@ -177,9 +177,13 @@ class GavikoEngine:
 
     # ------------------------------------------------------------------------------------------
     def mhsa_fwd(self, qkv, B, T, H, D, dim):
+        if qkv.dtype == torch.bfloat16 and D == 64:
+            return ops.mhsa_fwd(qkv, B, T, H, D ** -0.5)          # tcgen05 flash attention
         return ops.attn_simt_fwd(qkv, B, T, H, D, q_off=0, k_off=dim, v_off=2 * dim, scale=D ** -0.5)
 
     def mhsa_bwd(self, qkv, o, lse, do, B, T, H, D, dim):
+        if qkv.dtype == torch.bfloat16 and D == 64:
+            return ops.mhsa_bwd(qkv, o, lse, do, B, T, H, D ** -0.5)
         return ops.attn_simt_bwd(qkv, o, lse, do, B, T, H, D, q_off=0, k_off=dim, v_off=2 * dim, scale=D ** -0.5)
 
     def forward(self, img, training_dropout, save):

@@ -10,6 +10,9 @@ from ._lib import (ACT_GELU, ACT_GELU_BWD, ACT_NONE, LOSS_CE, LOSS_FOCAL, ROWACT
 
 S = L.STRUCTS
 
+# bench.py sets this to a list to time every GEMM launch with CUDA events on the launch stream: entries (start, end, flops)
+GEMM_HOOK = None
+
 
 def _ld(t):
     if t.dim() != 2 or t.stride(1) != 1:
@@ -49,6 +52,13 @@ def gemm(a, b, *, out=None, out_dtype=None, bias=None, ssf_scale=None, ssf_shift
         _set(p, res2=L.ptr(res2, torch.float32), ld_res2=_ld(res2))
     if out2 is not None:
         _set(p, out2=L.ptr(out2, torch.float32), ld_out2=_ld(out2))
+    if GEMM_HOOK is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        L.call('gvk_gemm', C.byref(p), L.stream())
+        e1.record()
+        GEMM_HOOK.append((e0, e1, 2.0 * M * N * K))
+        return out
     L.call('gvk_gemm', C.byref(p), L.stream())
     return out
 
@@ -224,6 +234,30 @@ def attn_simt_bwd(qkv, out, lse, dout, B, T, H, D, *, q_off, k_off, v_off, scale
     assert dout.dtype == qkv.dtype and dqkv.dtype == qkv.dtype
     _set(p, dout=dout, ld_dout=_ld(dout), delta=delta, dqkv=dqkv, ld_dqkv=_ld(dqkv))
     L.call('gvk_attn_simt_bwd', C.byref(p), L.stream())
+    return dqkv
+
+
+def mhsa_fwd(qkv, B, T, H, scale):
+    """tcgen05 flash attention forward: qkv [B*T, 3*H*64] bf16 -> (out [B*T, H*64] bf16, lse [B*H*T] fp32)."""
+    if qkv.dtype != torch.bfloat16:
+        raise GvkError('mhsa_fwd: bf16 only (fp32 mode uses attn_simt_fwd)')
+    out = torch.empty((B * T, H * 64), device=qkv.device, dtype=torch.bfloat16)
+    lse = torch.empty(B * H * T, device=qkv.device, dtype=torch.float32)
+    p = S['gvk_mhsa_fwd_params']()
+    _set(p, qkv=qkv, ld=_ld(qkv), B=B, T=T, H=H, scale=scale, out=out, ld_out=_ld(out), lse=lse)
+    L.call('gvk_mhsa_fwd', C.byref(p), L.stream())
+    return out, lse
+
+
+def mhsa_bwd(qkv, out, lse, dout, B, T, H, scale):
+    if qkv.dtype != torch.bfloat16 or dout.dtype != torch.bfloat16:
+        raise GvkError('mhsa_bwd: bf16 only')
+    dqkv = torch.empty_like(qkv)
+    delta = torch.empty_like(lse)
+    p = S['gvk_mhsa_bwd_params']()
+    _set(p, qkv=qkv, ld=_ld(qkv), B=B, T=T, H=H, scale=scale, out=out, ld_out=_ld(out), lse=lse, dout=dout, ld_dout=_ld(dout), delta=delta,
+         dqkv=dqkv, ld_dqkv=_ld(dqkv))
+    L.call('gvk_mhsa_bwd', C.byref(p), L.stream())
     return dqkv
 
 

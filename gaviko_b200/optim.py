@@ -1,0 +1,62 @@
+"""Flat-buffer optimiser step for the trainable set: global-norm clip + Adam in two kernel launches, and the data-parallel
+gradient exchange (one NCCL all-reduce of the flat gradient).  Semantics = reference ``src/train.py:183-189,315-319``
+(``clip_grad_norm_(model.parameters(), 1.0)`` then ``Adam.step()``; ``OneCycleLR`` drives ``param_groups[0]['lr']``)."""
+import ctypes as C
+
+import torch
+
+from . import _lib as L
+
+
+class FlatAdam(torch.optim.Optimizer):
+    """Adam over one contiguous fp32 buffer.  On construction the parameters (and their .grad) are re-pointed to views of
+    flat buffers, so autograd accumulates straight into the exchange buffer and no gather/scatter is needed per step."""
+
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, max_grad_norm=1.0, process_group=None, world_size=None):
+        params = [p for p in params if p.requires_grad]
+        if not params:
+            raise ValueError('FlatAdam: no trainable parameters')
+        super().__init__(params, dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay))
+        dev = params[0].device
+        if dev.type != 'cuda' or any(p.dtype != torch.float32 for p in params):
+            raise L.GvkError('FlatAdam needs fp32 CUDA parameters (master weights of the trainable set)')
+        self._params = params
+        # every view starts on a 64-byte boundary (the kernels use float2/float4 accesses on parameters); padding stays zero
+        pad = lambda k: (k + 15) // 16 * 16  # noqa: E731
+        n = sum(pad(p.numel()) for p in params)
+        self.numel = n
+        self.flat_p = torch.zeros(n, device=dev, dtype=torch.float32)
+        self.flat_g = torch.zeros(n, device=dev, dtype=torch.float32)
+        self.exp_avg = torch.zeros(n, device=dev, dtype=torch.float32)
+        self.exp_avg_sq = torch.zeros(n, device=dev, dtype=torch.float32)
+        self.partials = torch.zeros(128, device=dev, dtype=torch.float32)
+        self.grad_norm = torch.zeros((), device=dev, dtype=torch.float32)
+        off = 0
+        with torch.no_grad():
+            for p in params:
+                k = p.numel()
+                self.flat_p[off:off + k].copy_(p.reshape(-1))
+                p.data = self.flat_p[off:off + k].view_as(p)
+                p.grad = self.flat_g[off:off + k].view_as(p)
+                off += pad(k)
+        self.max_grad_norm = max_grad_norm
+        self.step_count = 0
+        self.group = process_group
+        self.world = world_size if world_size is not None else (torch.distributed.get_world_size(process_group) if torch.distributed.is_initialized() else 1)
+
+    def zero_grad(self, set_to_none=False):
+        self.flat_g.zero_()       # grads stay views of the flat buffer
+
+    @torch.no_grad()
+    def step(self, closure=None):
+        if self.world > 1:
+            torch.distributed.all_reduce(self.flat_g, group=self.group)     # SUM; the 1/world mean is folded into grad_scale
+        g = self.param_groups[0]
+        self.step_count += 1
+        scale = 1.0 / self.world
+        st = L.stream()
+        L.call('gvk_grad_sumsq', C.c_void_p(self.flat_g.data_ptr()), C.c_size_t(self.numel), C.c_float(scale), C.c_void_p(self.partials.data_ptr()), st)
+        L.call('gvk_clip_adam', C.c_void_p(self.flat_p.data_ptr()), C.c_void_p(self.flat_g.data_ptr()), C.c_void_p(self.exp_avg.data_ptr()),
+               C.c_void_p(self.exp_avg_sq.data_ptr()), C.c_size_t(self.numel), C.c_void_p(self.partials.data_ptr()),
+               C.c_float(self.max_grad_norm if self.max_grad_norm else 0.0), C.c_float(scale), C.c_float(g['lr']), C.c_float(g['betas'][0]),
+               C.c_float(g['betas'][1]), C.c_float(g['eps']), C.c_float(g['weight_decay']), self.step_count, C.c_void_p(self.grad_norm.data_ptr()), st)

@@ -211,6 +211,35 @@ int gvk_attn_simt_bwd(const gvk_attn_bwd_params* p, gvk_stream_t stream);
 
 
 /* ------------------------------------------------------------------------------------------------------------------
+ * Frozen multi-head self-attention core on the tensor cores (bf16 operands, fp32 accumulation / softmax), flash style:
+ * TMA-staged Q/K/V tiles, S = Q K^T and O += P V as tcgen05.mma with TMEM accumulators, online softmax in registers,
+ * nothing of size T x T touches HBM.  Handles the prompt-extended ragged sequence (any T; tails are masked in-kernel).
+ * Layout: qkv [B*T, 3*H*64] bf16, columns [q | k | v], head-major inside each block (einops 'b n (h d) -> b h n d',
+ * model/vision_transformer.py:62-63); out [B*T, H*64] bf16; lse [B*H*T] fp32 (natural-log, of the scaled scores).
+ * Replaces model/vision_transformer.py:65-71 and its autograd backward.  head dim is fixed at 64.
+ * ------------------------------------------------------------------------------------------------------------------ */
+typedef struct {
+  const void* qkv; int ld;
+  int B, T, H;
+  float scale;
+  void* out; int ld_out;
+  float* lse;
+} gvk_mhsa_fwd_params;
+int gvk_mhsa_fwd(const gvk_mhsa_fwd_params* p, gvk_stream_t stream);
+
+typedef struct {
+  const void* qkv; int ld;
+  int B, T, H;
+  float scale;
+  const void* out; int ld_out;
+  const float* lse;
+  const void* dout; int ld_dout;   /* [B*T, H*64] bf16 */
+  float* delta;                    /* workspace [B*H*T] */
+  void* dqkv; int ld_dqkv;         /* [B*T, 3*H*64] bf16, fully overwritten */
+} gvk_mhsa_bwd_params;
+int gvk_mhsa_bwd(const gvk_mhsa_bwd_params* p, gvk_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
  * Token assembly (a1/a2 of the hot path)
  * ------------------------------------------------------------------------------------------------------------------ */
 
@@ -320,6 +349,20 @@ int gvk_head_bwd(const gvk_head_bwd_params* p, gvk_stream_t stream);
  * ------------------------------------------------------------------------------------------------------------------ */
 int gvk_loss_fwd_bwd(const float* logits, const long long* target, int B, int C, int kind, float gamma, float eps, long long ignore_index,
                      float* loss, float* dlogits, gvk_stream_t stream);
+
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Optimiser step on the flat trainable buffer (reference src/train.py:315-319: clip_grad_norm_(params, 1.0) then Adam.step()).
+ *   gvk_grad_sumsq : partials[i] = sum of squares of a slice of (grad * grad_scale); n_partials = GVK_SUMSQ_PARTIALS
+ *   gvk_clip_adam  : norm = sqrt(sum partials); coef = min(1, max_norm / (norm + 1e-6))  (max_norm <= 0 disables clipping);
+ *                    g = grad * grad_scale * coef + weight_decay * p;  torch.optim.Adam update with bias correction at `step` (1-based).
+ * grad_scale carries the 1/world_size of the data-parallel mean, so the clip sees the gradient of the GLOBAL batch.
+ * Both are deterministic (fixed partition, no atomics): every rank computes bit-identical updates from the all-reduced buffer.
+ * ------------------------------------------------------------------------------------------------------------------ */
+enum { GVK_SUMSQ_PARTIALS = 128 };
+int gvk_grad_sumsq(const float* grad, size_t n, float grad_scale, float* partials, gvk_stream_t stream);
+int gvk_clip_adam(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, size_t n, const float* partials, float max_norm, float grad_scale,
+                  float lr, float beta1, float beta2, float eps, float weight_decay, int step, float* grad_norm_out, gvk_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,42 @@
+"""Per-entry-point time breakdown of one GAViKO training step (CUDA events around every C-ABI call).
+    python tools/profile_step.py [--backbone vit-b16] [--batch 8] [--dtype bf16]"""
+import argparse, contextlib, io, sys
+import torch
+sys.path.insert(0, '.')
+from gaviko_b200 import _lib as L
+from gaviko_b200.losses.focal_loss import FocalLoss
+from gaviko_b200.model.gaviko import Gaviko
+from gaviko_b200.optim import FlatAdam
+from bench import GAVIKO_KW
+
+ap = argparse.ArgumentParser()
+ap.add_argument('--backbone', default='vit-b16'); ap.add_argument('--batch', type=int, default=8); ap.add_argument('--dtype', default='bf16')
+ap.add_argument('--steps', type=int, default=2)
+a = ap.parse_args()
+torch.manual_seed(0)
+with contextlib.redirect_stdout(io.StringIO()):
+    model = Gaviko(**GAVIKO_KW, backbone=a.backbone, compute_dtype=a.dtype).cuda()
+model.train()
+opt = FlatAdam(model.parameters(), lr=1e-4)
+crit = FocalLoss(gamma=1.2)
+x = torch.rand(a.batch, 1, 120, 160, 160, device='cuda'); y = torch.randint(0, 5, (a.batch,), device='cuda')
+
+def step():
+    loss = crit(model(x), y); opt.zero_grad(); loss.backward(); opt.step(); return loss
+
+for _ in range(2): step()
+torch.cuda.synchronize()
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record()
+for _ in range(a.steps): step()
+e1.record(); torch.cuda.synchronize()
+total = e0.elapsed_time(e1) / a.steps
+L.PROFILE = {}
+for _ in range(a.steps): step()
+torch.cuda.synchronize()
+prof, L.PROFILE = L.PROFILE, None
+rows = sorted(((sum(s.elapsed_time(e) for s, e in v) / a.steps, len(v) // a.steps, k) for k, v in prof.items()), reverse=True)
+acc = sum(r[0] for r in rows)
+print(f'{a.backbone} {a.dtype} batch {a.batch}: {total:.2f} ms/step un-instrumented ({a.batch / total * 1e3:.1f} volumes/s); sum of bracketed calls {acc:.2f} ms; peak mem {torch.cuda.max_memory_allocated() / 2**30:.2f} GiB')
+for ms, n, k in rows:
+    print(f'  {ms:9.3f} ms  {100 * ms / acc:5.1f}%  x{n:<4d} {k}')
