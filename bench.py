@@ -155,7 +155,7 @@ def run_ours(args):
     train = args.mode == 'train'
     if train:
         model.train()
-        opt = FlatAdam(model.parameters(), lr=1e-4, eps=1e-8, max_grad_norm=1.0, world_size=world)
+        opt = FlatAdam(model.parameters(), lr=1e-4, eps=1e-8, max_grad_norm=1.0, world_size=world, model=model)
         sched = torch.optim.lr_scheduler.OneCycleLR(opt, max_lr=3e-4, total_steps=2 * (args.steps + args.warmup) + 16, pct_start=0.3, div_factor=10.0,
                                                     final_div_factor=1000.0, anneal_strategy='cos', three_phase=False)
     else:

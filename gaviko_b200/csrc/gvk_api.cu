@@ -108,6 +108,7 @@ int gvk_layernorm_bwd(const gvk_layernorm_bwd_params* p, gvk_stream_t stream) { 
 int gvk_rowproj_down(const gvk_rowproj_down_params* p, gvk_stream_t stream) { return gvk::rowproj_down(p, S(stream)); }
 int gvk_rowproj_up(const gvk_rowproj_up_params* p, gvk_stream_t stream) { return gvk::rowproj_up(p, S(stream)); }
 int gvk_skinny_wgrad(const gvk_skinny_wgrad_params* p, gvk_stream_t stream) { return gvk::skinny_wgrad(p, S(stream)); }
+size_t gvk_skinny_wgrad_ws_floats(int r, int dim, int M) { return gvk::skinny_wgrad_ws_floats(r, dim, M); }
 int gvk_small_wgrad(const float* a, int lda, int ra, const float* b, int ldb, int rb, int M, float* dw, gvk_stream_t stream) {
   return gvk::small_wgrad(a, lda, ra, b, ldb, rb, M, dw, S(stream));
 }

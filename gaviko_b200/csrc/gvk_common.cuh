@@ -46,6 +46,7 @@ int layernorm_bwd(const gvk_layernorm_bwd_params* p, cudaStream_t stream);
 int rowproj_down(const gvk_rowproj_down_params* p, cudaStream_t stream);
 int rowproj_up(const gvk_rowproj_up_params* p, cudaStream_t stream);
 int skinny_wgrad(const gvk_skinny_wgrad_params* p, cudaStream_t stream);
+size_t skinny_wgrad_ws_floats(int r, int dim, int M);
 int small_wgrad(const float* a, int lda, int ra, const float* b, int ldb, int rb, int M, float* dw, cudaStream_t stream);
 int small_matmul(const float* a, int lda, int ra, const float* w, int rb, int M, float* out, int ldo, cudaStream_t stream);
 int colsum(const float* x, int ldx, int M, int dim, float* out, cudaStream_t stream);

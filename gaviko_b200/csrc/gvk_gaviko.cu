@@ -665,12 +665,12 @@ __global__ void __launch_bounds__(256) head_bwd_w_kernel(gvk_head_bwd_params bp)
   if (c < p.dim) {
     float s = 0.f;
     for (int b = 0; b < p.B; ++b) s = fmaf(bp.dlogits[(size_t)b * p.num_classes + k], p.pooled[(size_t)b * p.dim + c], s);
-    bp.dwh[(size_t)k * p.dim + c] = s;
+    if (bp.accumulate_w) bp.dwh[(size_t)k * p.dim + c] += s; else bp.dwh[(size_t)k * p.dim + c] = s;
   }
   if (blockIdx.x == 0 && threadIdx.x == 0) {
     float s = 0.f;
     for (int b = 0; b < p.B; ++b) s += bp.dlogits[(size_t)b * p.num_classes + k];
-    bp.dbh[k] = s;
+    if (bp.accumulate_w) bp.dbh[k] += s; else bp.dbh[k] = s;
   }
 }
 

@@ -71,6 +71,124 @@ __device__ __forceinline__ void epi_elem(const EpiArgs& e, int m, int n, float v
   if (e.out2) e.out2[(size_t)m * e.ld_out2 + n] = v;
 }
 
+
+// -------------------------------------------------------------------------------------------------
+// Fast epilogues (compile-time specialised, 128-bit accesses).  One warp owns a 32-row x 32-column patch:
+// thread = row after tcgen05.ld, then an XOR-swizzled smem transpose makes lane = (sub-row, 4-column vector) so that every
+// global access is a contiguous 128 B (fp32) / 64 B (bf16) row segment.  Loads the epilogue depends on (residual, saved GELU
+// pre-activation) are issued before the TMEM wait so their latency overlaps it.
+// -------------------------------------------------------------------------------------------------
+enum { EPI_GENERIC = 0, EPI_STORE_BF16 = 1, EPI_BIAS_GELU_BF16 = 2, EPI_BIAS_RES_F32 = 3, EPI_GELU_BWD_BF16 = 4, EPI_STORE_F32 = 5 };
+
+// Standard-normal CDF Phi(x) = 0.5 (1 + erf(x / sqrt 2)) with |abs err| < 2e-7 (Abramowitz-Stegun 7.1.26), branch-free:
+// rcp.approx + ex2.approx + 7 fma/mul + select.  Also returns e = exp(-x^2 / 2) for the GELU derivative.  Used only on the bf16
+// path, whose results are rounded to bf16 anyway (the exact-fp32 kernel keeps erff).
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float rcp_approx(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float norm_cdf_fast(float x, float& e) {
+  const float z = fabsf(x) * 0.70710678118654752f;
+  const float t = rcp_approx(fmaf(0.3275911f, z, 1.0f));
+  float p = fmaf(0.5f * 1.061405429f, t, 0.5f * -1.453152027f);
+  p = fmaf(p, t, 0.5f * 1.421413741f);
+  p = fmaf(p, t, 0.5f * -0.284496736f);
+  p = fmaf(p, t, 0.5f * 0.254829592f);
+  e = ex2_approx(x * x * -0.72134752044448170f);  // exp(-x^2/2)
+  const float q = p * t * e;                      // 0.5 * erfc(|x| / sqrt 2)
+  return x < 0.f ? q : 1.0f - q;
+}
+__device__ __forceinline__ float gelu_fast(float x) {
+  float e;
+  return x * norm_cdf_fast(x, e);
+}
+__device__ __forceinline__ float gelu_grad_fast(float x) {
+  float e;
+  const float cdf = norm_cdf_fast(x, e);
+  return fmaf(x * 0.39894228040143268f, e, cdf);
+}
+__device__ __forceinline__ float4 bf16x4_to_float4(uint2 u) {
+  const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.x));
+  const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.y));
+  return make_float4(a.x, a.y, b.x, b.y);
+}
+__device__ __forceinline__ uint2 float4_to_bf16x4(float4 v) {
+  __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
+  uint2 u;
+  u.x = *reinterpret_cast<uint32_t*>(&a);
+  u.y = *reinterpret_cast<uint32_t*>(&b);
+  return u;
+}
+
+template <int EPI>
+__device__ __forceinline__ void epilogue_patch_fast(const EpiArgs& e, uint32_t taddr, float* patch, int row0, int col0, int M, int lane) {
+  const int sr = lane >> 3, cv = lane & 7;  // sub-row 0..3, 4-column vector 0..7
+  const int col = col0 + cv * 4;
+  // ---- early loads
+  float4 res[8];
+  uint2 aux_in[8];
+  if constexpr (EPI == EPI_BIAS_RES_F32) {
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+      const int m = row0 + it * 4 + sr;
+      res[it] = (m < M) ? *reinterpret_cast<const float4*>(e.res1 + (size_t)m * e.ld_res1 + col) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  }
+  if constexpr (EPI == EPI_GELU_BWD_BF16) {
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+      const int m = row0 + it * 4 + sr;
+      aux_in[it] = (m < M) ? *reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(e.aux) + (size_t)m * e.ld_aux + col) : make_uint2(0u, 0u);
+    }
+  }
+  float4 bias = make_float4(0.f, 0.f, 0.f, 0.f);
+  if constexpr (EPI == EPI_BIAS_GELU_BF16 || EPI == EPI_BIAS_RES_F32) bias = *reinterpret_cast<const float4*>(e.bias + col);
+  // ---- TMEM -> registers (thread = row) -> swizzled smem
+  float v[32];
+  tmem_ld_32x32(taddr, v);
+  tc_wait_ld();
+  {
+    float4* prow = reinterpret_cast<float4*>(patch) + lane * 8;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) prow[c ^ (lane & 7)] = make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+  }
+  __syncwarp();
+  // ---- lane = (sub-row, vector): fused elementwise + coalesced stores
+#pragma unroll
+  for (int it = 0; it < 8; ++it) {
+    const int r = it * 4 + sr;
+    const int m = row0 + r;
+    float4 x = reinterpret_cast<const float4*>(patch)[r * 8 + (cv ^ (r & 7))];
+    if (m >= M) continue;
+    if constexpr (EPI == EPI_BIAS_GELU_BF16 || EPI == EPI_BIAS_RES_F32) {
+      x.x += bias.x; x.y += bias.y; x.z += bias.z; x.w += bias.w;
+    }
+    if constexpr (EPI == EPI_BIAS_GELU_BF16) {
+      if (e.aux) *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(e.aux) + (size_t)m * e.ld_aux + col) = float4_to_bf16x4(x);
+      x.x = gelu_fast(x.x); x.y = gelu_fast(x.y); x.z = gelu_fast(x.z); x.w = gelu_fast(x.w);
+    }
+    if constexpr (EPI == EPI_GELU_BWD_BF16) {
+      const float4 pre = bf16x4_to_float4(aux_in[it]);
+      x.x *= gelu_grad_fast(pre.x); x.y *= gelu_grad_fast(pre.y); x.z *= gelu_grad_fast(pre.z); x.w *= gelu_grad_fast(pre.w);
+    }
+    if constexpr (EPI == EPI_BIAS_RES_F32) {
+      x.x += res[it].x; x.y += res[it].y; x.z += res[it].z; x.w += res[it].w;
+    }
+    if constexpr (EPI == EPI_BIAS_RES_F32 || EPI == EPI_STORE_F32) {
+      *reinterpret_cast<float4*>(reinterpret_cast<float*>(e.out) + (size_t)m * e.ld_out + col) = x;
+    } else {
+      *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(e.out) + (size_t)m * e.ld_out + col) = float4_to_bf16x4(x);
+    }
+  }
+  __syncwarp();
+}
+
 // =================================================================================================
 // tcgen05 kernel
 // =================================================================================================
@@ -90,7 +208,7 @@ struct GemmSmem {
   static constexpr int kTotal = kRing + kEpi + kBars + 1024;  // +1024: manual alignment slack
 };
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, int EPI>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_bf16_sm100_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, EpiArgs e, int M, int N, int K) {
   using L = GemmSmem<BN, STAGES>;
@@ -209,21 +327,26 @@ gemm_bf16_sm100_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_c
         const int colt = h * (BN / 2) + c * 32;
         const int col0 = n_blk * BN + colt;
         if (col0 < N && row0 < M) {  // warp-uniform
-          float v[32];
-          tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN + colt, v);
-          tc_wait_ld();
+          const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN + colt;
+          if constexpr (EPI != EPI_GENERIC) {
+            epilogue_patch_fast<EPI>(e, taddr, patch, row0, col0, M, lane);
+          } else {
+            float v[32];
+            tmem_ld_32x32(taddr, v);
+            tc_wait_ld();
 #pragma unroll
-          for (int j = 0; j < 32; ++j) patch[lane * 33 + j] = v[j];
-          __syncwarp();
-          const int n = col0 + lane;
-          const bool nvalid = n < N;
-          const EpiCol ec = epi_col(e, n, nvalid);
-          const int rmax = min(32, M - row0);
-          if (nvalid) {
+            for (int j = 0; j < 32; ++j) patch[lane * 33 + j] = v[j];
+            __syncwarp();
+            const int n = col0 + lane;
+            const bool nvalid = n < N;
+            const EpiCol ec = epi_col(e, n, nvalid);
+            const int rmax = min(32, M - row0);
+            if (nvalid) {
 #pragma unroll 4
-            for (int r = 0; r < rmax; ++r) epi_elem(e, row0 + r, n, patch[r * 33 + lane], ec);
+              for (int r = 0; r < rmax; ++r) epi_elem(e, row0 + r, n, patch[r * 33 + lane], ec);
+            }
+            __syncwarp();
           }
-          __syncwarp();
         }
       }
       tc_fence_before();
@@ -298,11 +421,11 @@ static EpiArgs to_epi(const gvk_gemm_params* p) {
   return e;
 }
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, int EPI>
 static int launch_bf16(const gvk_gemm_params* p, const EpiArgs& e, cudaStream_t stream) {
   using L = GemmSmem<BN, STAGES>;
   static bool configured = false;
-  auto kern = gemm_bf16_sm100_kernel<BN, STAGES>;
+  auto kern = gemm_bf16_sm100_kernel<BN, STAGES, EPI>;
   if (!configured) {
     int st = cuda_status(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal), "gemm smem attribute");
     if (st != GVK_OK) return st;
@@ -331,8 +454,33 @@ int gemm_dispatch(const gvk_gemm_params* p, cudaStream_t stream) {
     GVK_CHECK_ARG(p->lda % 8 == 0 && p->ldb % 8 == 0, "gvk_gemm(bf16): lda/ldb must be multiples of 8");
     GVK_CHECK_ARG((reinterpret_cast<uintptr_t>(p->a) & 15) == 0 && (reinterpret_cast<uintptr_t>(p->b) & 15) == 0,
                   "gvk_gemm(bf16): operands must be 16-byte aligned");
-    if (p->N % 256 == 0) return launch_bf16<256, 4>(p, e, stream);
-    return launch_bf16<128, 6>(p, e, stream);
+    // pick a compile-time specialised epilogue when the request matches one of the hot-path shapes
+    int epi = EPI_GENERIC;
+    const bool plain = !p->ssf_scale && !p->ssf_shift && !p->pos && p->rows_per_batch == 0 && !p->res2 && !p->out2 && p->N % 32 == 0 && p->ld_out % 4 == 0 &&
+                       (reinterpret_cast<uintptr_t>(p->out) & 15) == 0;
+    if (plain) {
+      const bool aux_ok = !p->aux || (p->aux_dtype == GVK_BF16 && p->ld_aux % 4 == 0 && (reinterpret_cast<uintptr_t>(p->aux) & 7) == 0);
+      const bool res_ok = p->res1 && p->ld_res1 % 4 == 0 && (reinterpret_cast<uintptr_t>(p->res1) & 15) == 0;
+      const bool bias_ok = p->bias && (reinterpret_cast<uintptr_t>(p->bias) & 15) == 0;
+      if (!p->bias && p->act == GVK_ACT_NONE && !p->res1 && !p->aux) epi = p->out_dtype == GVK_BF16 ? EPI_STORE_BF16 : EPI_STORE_F32;
+      else if (bias_ok && p->act == GVK_ACT_GELU && !p->res1 && p->out_dtype == GVK_BF16 && aux_ok) epi = EPI_BIAS_GELU_BF16;
+      else if (bias_ok && p->act == GVK_ACT_NONE && res_ok && p->out_dtype == GVK_F32 && !p->aux) epi = EPI_BIAS_RES_F32;
+      else if (!p->bias && p->act == GVK_ACT_GELU_BWD && !p->res1 && p->out_dtype == GVK_BF16 && p->aux && aux_ok) epi = EPI_GELU_BWD_BF16;
+    }
+#define GVK_GEMM_CASE(E)                                               \
+  case E:                                                              \
+    if (p->N % 256 == 0) return launch_bf16<256, 4, E>(p, e, stream); \
+    return launch_bf16<128, 6, E>(p, e, stream);
+    switch (epi) {
+      GVK_GEMM_CASE(EPI_STORE_BF16)
+      GVK_GEMM_CASE(EPI_BIAS_GELU_BF16)
+      GVK_GEMM_CASE(EPI_BIAS_RES_F32)
+      GVK_GEMM_CASE(EPI_GELU_BWD_BF16)
+      GVK_GEMM_CASE(EPI_STORE_F32)
+      default:
+        GVK_GEMM_CASE(EPI_GENERIC)
+    }
+#undef GVK_GEMM_CASE
   }
   if (p->ab_dtype == GVK_F32) {
     GVK_CHECK_ARG(p->K % 4 == 0 && p->lda % 4 == 0 && p->ldb % 4 == 0, "gvk_gemm(f32): K, lda, ldb must be multiples of 4");

@@ -38,11 +38,32 @@ __device__ __forceinline__ float2 drop_mult2(uint64_t seed, uint64_t e, float p,
       return GVK_ERR_UNSUPPORTED;                                                \
   }
 
-static inline int row_grid(int M) {
+static inline int row_grid(int M, size_t smem_bytes = 0) {
   const int blocks = (M + kRowWarps - 1) / kRowWarps;
-  const int cap = sm_count() * 8;
+  // kernels that stage a weight panel in smem amortise the staging over many rows: one resident wave only
+  int per_sm = 8;
+  if (smem_bytes > 0) per_sm = (int)std::max<size_t>(1, std::min<size_t>(4, (200 * 1024) / (smem_bytes + 1024)));
+  const int cap = sm_count() * per_sm;
   return blocks < cap ? blocks : cap;
 }
+
+#ifdef __CUDACC__
+// Stage the rank-r weight panel as sw[j * dim + c] = w(j, c), reading global memory in its own linear order (coalesced).
+__device__ __forceinline__ void stage_weight(float* sw, const float* __restrict__ w, int r, int dim, int w_sj, int w_sc) {
+  const int total = r * dim;
+  if (w_sc == 1) {  // [r, dim] row-major
+    for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
+      const int j = idx / dim, c = idx - j * dim;
+      sw[idx] = w[(size_t)j * w_sj + c];
+    }
+  } else {          // [dim, r] row-major (w_sj == 1): source-linear index is c * w_sc + j
+    for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
+      const int c = idx / r, j = idx - c * r;
+      sw[j * dim + c] = w[(size_t)c * w_sc + (size_t)j * w_sj];
+    }
+  }
+}
+#endif
 
 // ------------------------------------------------------------------------------------------------
 // LayerNorm forward
@@ -110,10 +131,7 @@ __global__ void __launch_bounds__(kRowThreads) rowproj_down_kernel(gvk_rowproj_d
   const int dim = NITER * 64;
   float* sw = smem;                 // [r][dim]
   float* sw2 = smem + p.r * dim;    // [r2][r]
-  for (int idx = threadIdx.x; idx < p.r * dim; idx += blockDim.x) {
-    const int j = idx / dim, c = idx - j * dim;
-    sw[idx] = p.w[(size_t)j * p.w_sj + (size_t)c * p.w_sc];
-  }
+  stage_weight(sw, p.w, p.r, dim, p.w_sj, p.w_sc);
   if (p.w2)
     for (int idx = threadIdx.x; idx < p.r2 * p.r; idx += blockDim.x) sw2[idx] = p.w2[idx];
   __syncthreads();
@@ -210,7 +228,7 @@ int rowproj_down(const gvk_rowproj_down_params* p, cudaStream_t stream) {
       if (st != GVK_OK) return st;
       configured = smem;
     }
-    rowproj_down_kernel<NITER><<<row_grid(p->M), kRowThreads, smem, stream>>>(*p);
+    rowproj_down_kernel<NITER><<<row_grid(p->M, smem), kRowThreads, smem, stream>>>(*p);
   });
   GVK_CHECK_LAUNCH("rowproj_down");
   return GVK_OK;
@@ -224,10 +242,7 @@ __global__ void __launch_bounds__(kRowThreads) rowproj_up_kernel(gvk_rowproj_up_
   extern __shared__ float smem[];
   const int dim = NITER * 64;
   float* sw = smem;  // [r][dim]
-  for (int idx = threadIdx.x; idx < p.r * dim; idx += blockDim.x) {
-    const int j = idx / dim, c = idx - j * dim;
-    sw[idx] = p.w[(size_t)j * p.w_sj + (size_t)c * p.w_sc];
-  }
+  stage_weight(sw, p.w, p.r, dim, p.w_sj, p.w_sc);
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const float inv_keep = p.drop_p > 0.f ? 1.0f / (1.0f - p.drop_p) : 1.f;
@@ -281,7 +296,7 @@ int rowproj_up(const gvk_rowproj_up_params* p, cudaStream_t stream) {
       if (st != GVK_OK) return st;
       configured = smem;
     }
-    rowproj_up_kernel<NITER><<<row_grid(p->M), kRowThreads, smem, stream>>>(*p);
+    rowproj_up_kernel<NITER><<<row_grid(p->M, smem), kRowThreads, smem, stream>>>(*p);
   });
   GVK_CHECK_LAUNCH("rowproj_up");
   return GVK_OK;
@@ -351,27 +366,67 @@ __global__ void __launch_bounds__(256) skinny_wgrad_kernel(gvk_skinny_wgrad_para
       }
     }
   }
+  // per-CTA partials (no atomics: same-address contention from ~300 CTAs serialises in L2); reduced by skinny_wgrad_reduce_kernel
+  float* ws_dw = p.ws + (size_t)blockIdx.x * p.r * p.dim;
+  float* ws_dx = p.ws + (size_t)gridDim.x * p.r * p.dim + (size_t)blockIdx.x * p.dim;
+  float* ws_da = p.ws + (size_t)gridDim.x * (p.r + 1) * p.dim + (size_t)blockIdx.x * 32;
 #pragma unroll
   for (int i = 0; i < NCOL; ++i) {
     const int c = tid + 256 * i;
     if (c < p.dim) {
-      if (p.dw) {
 #pragma unroll
-        for (int j = 0; j < R; ++j)
-          if (j < p.r) atomicAdd(p.dw + (size_t)j * p.dw_sj + (size_t)c * p.dw_sc, acc[i][j]);
-      }
-      if (p.dx_colsum) atomicAdd(p.dx_colsum + c, xsum[i]);
+      for (int j = 0; j < R; ++j)
+        if (j < p.r) ws_dw[(size_t)j * p.dim + c] = acc[i][j];
+      ws_dx[c] = xsum[i];
     }
   }
-  if (p.da_colsum && tid < p.r) atomicAdd(p.da_colsum + tid, asum);
+  if (tid < 32) ws_da[tid] = tid < p.r ? asum : 0.f;
+}
+
+__global__ void __launch_bounds__(256) skinny_wgrad_reduce_kernel(gvk_skinny_wgrad_params p, int ncta) {
+  const int rd = p.r * p.dim;
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx < rd) {
+    if (!p.dw) return;
+    float s = 0.f;
+    for (int k = 0; k < ncta; ++k) s += p.ws[(size_t)k * rd + idx];
+    const int j = idx / p.dim, c = idx - j * p.dim;
+    p.dw[(size_t)j * p.dw_sj + (size_t)c * p.dw_sc] += s;
+  } else if (idx < rd + p.dim) {
+    if (!p.dx_colsum) return;
+    const int c = idx - rd;
+    const float* base = p.ws + (size_t)ncta * rd;
+    float s = 0.f;
+    for (int k = 0; k < ncta; ++k) s += base[(size_t)k * p.dim + c];
+    p.dx_colsum[c] += s;
+  } else if (idx < rd + p.dim + p.r) {
+    if (!p.da_colsum) return;
+    const int j = idx - rd - p.dim;
+    const float* base = p.ws + (size_t)ncta * (p.r + 1) * p.dim;
+    float s = 0.f;
+    for (int k = 0; k < ncta; ++k) s += base[(size_t)k * 32 + j];
+    p.da_colsum[j] += s;
+  }
+}
+
+static void skinny_wgrad_plan(int M, int* ctas, int* rows_per_cta) {
+  const int want = std::max(1, std::min(sm_count() * 2, (M + 63) / 64));
+  int rpc = (M + want - 1) / want;
+  rpc = (rpc + kWgRows - 1) / kWgRows * kWgRows;
+  *rows_per_cta = rpc;
+  *ctas = (M + rpc - 1) / rpc;
+}
+
+size_t skinny_wgrad_ws_floats(int r, int dim, int M) {
+  int ctas, rpc;
+  skinny_wgrad_plan(M, &ctas, &rpc);
+  return (size_t)ctas * ((size_t)(r + 1) * dim + 32);
 }
 
 template <int NCOL>
 static int skinny_wgrad_launch(const gvk_skinny_wgrad_params* p, cudaStream_t stream) {
-  const int ctas = std::max(1, std::min(sm_count() * 2, (p->M + 63) / 64));
-  int rows_per_cta = (p->M + ctas - 1) / ctas;
-  rows_per_cta = (rows_per_cta + kWgRows - 1) / kWgRows * kWgRows;
-  const int grid = (p->M + rows_per_cta - 1) / rows_per_cta;
+  int grid, rows_per_cta;
+  skinny_wgrad_plan(p->M, &grid, &rows_per_cta);
   if (p->r <= 8)
     skinny_wgrad_kernel<NCOL, 8><<<grid, 256, 0, stream>>>(*p, rows_per_cta);
   else if (p->r <= 20)
@@ -379,6 +434,9 @@ static int skinny_wgrad_launch(const gvk_skinny_wgrad_params* p, cudaStream_t st
   else
     skinny_wgrad_kernel<NCOL, 32><<<grid, 256, 0, stream>>>(*p, rows_per_cta);
   GVK_CHECK_LAUNCH("skinny_wgrad");
+  const int total = p->r * p->dim + p->dim + p->r;
+  skinny_wgrad_reduce_kernel<<<(total + 255) / 256, 256, 0, stream>>>(*p, grid);
+  GVK_CHECK_LAUNCH("skinny_wgrad_reduce");
   return GVK_OK;
 }
 
@@ -386,6 +444,8 @@ int skinny_wgrad(const gvk_skinny_wgrad_params* p, cudaStream_t stream) {
   GVK_CHECK_ARG(p && p->a && p->x, "gvk_skinny_wgrad: null pointer");
   GVK_CHECK_ARG(p->r >= 1 && p->r <= 32 && p->dim >= 1 && p->dim <= 1024 && p->M > 0, "gvk_skinny_wgrad: r=%d dim=%d M=%d", p->r, p->dim, p->M);
   GVK_CHECK_ARG(!p->ln_gamma || (p->ln_beta && p->mean && p->rstd), "gvk_skinny_wgrad: LN recompute needs beta, mean, rstd");
+  GVK_CHECK_ARG(p->ws && p->ws_floats >= skinny_wgrad_ws_floats(p->r, p->dim, p->M), "gvk_skinny_wgrad: workspace of %zu floats required (gvk_skinny_wgrad_ws_floats)",
+                skinny_wgrad_ws_floats(p->r, p->dim, p->M));
   switch ((p->dim + 255) / 256) {
     case 1: return skinny_wgrad_launch<1>(p, stream);
     case 2: return skinny_wgrad_launch<2>(p, stream);
@@ -397,23 +457,19 @@ int skinny_wgrad(const gvk_skinny_wgrad_params* p, cudaStream_t stream) {
 // ------------------------------------------------------------------------------------------------
 // LayerNorm backward
 // ------------------------------------------------------------------------------------------------
-template <int NITER>
+template <int NITER, bool PGRAD>
 __global__ void __launch_bounds__(kRowThreads) layernorm_bwd_kernel(gvk_layernorm_bwd_params p) {
   extern __shared__ float smem[];
   const int dim = NITER * 64;
   float* sw = smem;  // [r][dim] when dy is given in rank-r form
-  if (p.dz) {
-    for (int idx = threadIdx.x; idx < p.r * dim; idx += blockDim.x) {
-      const int j = idx / dim, c = idx - j * dim;
-      sw[idx] = p.w[(size_t)j * p.w_sj + (size_t)c * p.w_sc];
-    }
-  }
+  if (p.dz) stage_weight(sw, p.w, p.r, dim, p.w_sj, p.w_sc);
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const float inv_dim = 1.0f / dim;
-  float2 dg[NITER], db[NITER];
+  constexpr int NG = PGRAD ? NITER : 1;
+  float2 dg[NG], db[NG];
 #pragma unroll
-  for (int i = 0; i < NITER; ++i) dg[i] = db[i] = make_float2(0.f, 0.f);
+  for (int i = 0; i < NG; ++i) dg[i] = db[i] = make_float2(0.f, 0.f);
   float2 gam[NITER];
 #pragma unroll
   for (int i = 0; i < NITER; ++i) gam[i] = *reinterpret_cast<const float2*>(p.gamma + lane * 2 + 64 * i);
@@ -445,10 +501,12 @@ __global__ void __launch_bounds__(kRowThreads) layernorm_bwd_kernel(gvk_layernor
     for (int i = 0; i < NITER; ++i) {
       const float2 x = *reinterpret_cast<const float2*>(p.x + (size_t)row * p.ldx + lane * 2 + 64 * i);
       xh[i] = make_float2((x.x - mean) * rstd, (x.y - mean) * rstd);
-      dg[i].x += dy[i].x * xh[i].x;
-      dg[i].y += dy[i].y * xh[i].y;
-      db[i].x += dy[i].x;
-      db[i].y += dy[i].y;
+      if constexpr (PGRAD) {
+        dg[i].x += dy[i].x * xh[i].x;
+        dg[i].y += dy[i].y * xh[i].y;
+        db[i].x += dy[i].x;
+        db[i].y += dy[i].y;
+      }
       dy[i].x *= gam[i].x;  // g = dy * gamma
       dy[i].y *= gam[i].y;
       s1 += dy[i].x + dy[i].y;
@@ -468,7 +526,7 @@ __global__ void __launch_bounds__(kRowThreads) layernorm_bwd_kernel(gvk_layernor
       if (p.dx_lp) *reinterpret_cast<__nv_bfloat162*>(reinterpret_cast<__nv_bfloat16*>(p.dx_lp) + (size_t)row * p.ld_dx_lp + c) = __floats2bfloat162_rn(dx.x, dx.y);
     }
   }
-  if (p.dgamma || p.dbeta) {
+  if constexpr (PGRAD) {
     // cross-warp reduction through smem (reusing the weight staging area is unsafe: use a dedicated tail region)
     float* red = smem + (p.dz ? p.r * dim : 0);  // [kRowWarps][2*dim]
     __syncthreads();
@@ -501,16 +559,20 @@ int layernorm_bwd(const gvk_layernorm_bwd_params* p, cudaStream_t stream) {
   const bool red = p->dgamma || p->dbeta;
   const size_t smem = ((p->dz ? (size_t)p->r * p->dim : 0) + (red ? (size_t)kRowWarps * 2 * p->dim : 0)) * sizeof(float);
   // With parameter gradients every CTA ends with 2*dim atomics: keep the grid modest.
-  int grid = row_grid(p->M);
+  int grid = row_grid(p->M, p->dz ? smem : 0);
   if (red) grid = std::min(grid, sm_count() * 2);
   GVK_DISPATCH_NITER(p->dim, {
-    static size_t configured = 0;
-    if (smem > configured) {
-      int st = cuda_status(cudaFuncSetAttribute(layernorm_bwd_kernel<NITER>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "layernorm_bwd smem");
+    static size_t configured[2] = {0, 0};
+    if (smem > configured[red]) {
+      int st = red ? cuda_status(cudaFuncSetAttribute(layernorm_bwd_kernel<NITER, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "layernorm_bwd smem")
+                   : cuda_status(cudaFuncSetAttribute(layernorm_bwd_kernel<NITER, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "layernorm_bwd smem");
       if (st != GVK_OK) return st;
-      configured = smem;
+      configured[red] = smem;
     }
-    layernorm_bwd_kernel<NITER><<<grid, kRowThreads, smem, stream>>>(*p);
+    if (red)
+      layernorm_bwd_kernel<NITER, true><<<grid, kRowThreads, smem, stream>>>(*p);
+    else
+      layernorm_bwd_kernel<NITER, false><<<grid, kRowThreads, smem, stream>>>(*p);
   });
   GVK_CHECK_LAUNCH("layernorm_bwd");
   return GVK_OK;

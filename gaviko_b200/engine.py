@@ -60,6 +60,9 @@ class GavikoEngine:
         self._requested = compute_dtype
         self._cache = FrozenCache()
         self._step = 0
+        # Optional {parameter name: fp32 tensor} of gradient accumulators (set by gaviko_b200.optim.FlatAdam): backward then adds
+        # straight into the optimiser's flat exchange buffer and returns no per-tensor gradients to autograd.
+        self.grad_sink = None
 
     # ------------------------------------------------------------------------------------------
     @property
@@ -248,7 +251,7 @@ class GavikoEngine:
                 layers.append(st)
             g, loc = g_out, loc_new
         logits, pooled = ops.head_fwd(g, B, T, 0, P + 1, W['norm_w'], W['norm_b'], Tr['head_w'], Tr['head_b'])
-        ctx = dict(layers=layers, g_final=g, pooled=pooled, B=B, T=T, N=N, W=W, Tr=Tr, cdt=cdt, drop_attn=drop_attn, drop_proj=drop_proj) if save else None
+        ctx = dict(layers=layers, g_final=g, pooled=pooled, B=B, T=T, N=N, W=W, Tr=Tr, cdt=cdt, drop_attn=drop_attn, drop_proj=drop_proj, names=[]) if save else None
         return logits, ctx
 
     # ------------------------------------------------------------------------------------------
@@ -260,16 +263,34 @@ class GavikoEngine:
         r_l = c['local_dim']
         dev = dlogits.device
         lp = cdt != torch.float32
-        zeros = lambda t: torch.zeros_like(t)  # noqa: E731
-        G = dict(local=[{k: zeros(v) for k, v in La.items()} for La in Tr['local']],
-                 fusion=[dict(wd=zeros(Fu['wd']), bd=zeros(Fu['bd']), wu=zeros(Fu['wu']), bu=zeros(Fu['bu']), k={k: zeros(v) for k, v in Fu['k'].items()})
-                         for Fu in Tr['fusion']])
+        # Gradient accumulators: views of the optimiser's flat buffer when a sink is attached, else of one zeroed flat buffer.
+        nmap = self._grad_name_map()
+        sink = self.grad_sink if (self.grad_sink is not None and all(n in self.grad_sink for n in ctx['names'])) else None
+        G = dict(local=[dict() for _ in Tr['local']], fusion=[dict(k=dict()) for _ in Tr['fusion']])
+        if sink is None:
+            shapes = {n: _lookup(Tr, nmap[n]).shape for n in nmap}
+            flat = torch.zeros(sum((s.numel() + 15) // 16 * 16 for s in shapes.values()), device=dev, dtype=torch.float32)
+            off = 0
+        for n, path in nmap.items():
+            if sink is not None and n in sink:
+                t = sink[n].view(_lookup(Tr, path).shape)
+            elif sink is not None:
+                t = torch.zeros_like(_lookup(Tr, path))        # frozen-by-user tensor: scratch accumulator
+            else:
+                k = shapes[n].numel()
+                t = flat[off:off + k].view(shapes[n])
+                off += (k + 15) // 16 * 16
+            d = G
+            for key in path[:-1]:
+                d = d[key]
+            d[path[-1]] = t
+        ctx['used_sink'] = sink is not None
 
         # head (model/gaviko.py:306,314-316): only rows 0..P of each volume receive gradient
         dG = torch.zeros((B * T, dim), device=dev, dtype=torch.float32)
         dG_lp = torch.zeros((B * T, dim), device=dev, dtype=cdt) if lp else None
-        _, G['head_w'], G['head_b'] = ops.head_bwd(ctx['g_final'], B, T, 0, P + 1, W['norm_w'], W['norm_b'], Tr['head_w'], Tr['head_b'], ctx['pooled'],
-                                                   dlogits, dx=dG, dx_lp=dG_lp)
+        ops.head_bwd(ctx['g_final'], B, T, 0, P + 1, W['norm_w'], W['norm_b'], Tr['head_w'], Tr['head_b'], ctx['pooled'], dlogits, dx=dG, dx_lp=dG_lp,
+                     dwh=G['head_w'], dbh=G['head_b'])
         dLoc = None
         for i in reversed(range(c['depth'])):
             s = i // c['share_factor']
@@ -317,8 +338,8 @@ class GavikoEngine:
                                      dgamma=gL['ln_w'], dbeta=gL['ln_b'])
             ctx['layers'][i] = None     # release this layer's activations
         # prompt rows of the layer-0 input (model/gaviko.py:540-543): both prompt tensors receive the same gradient
-        G['prompt_emb'] = ops.batch_rowsum(dG, T, 0, P, B)
-        G['prompt_pos'] = G['prompt_emb'].clone()
+        ops.batch_rowsum(dG, T, 0, P, B, out=G['prompt_emb'].view(P, dim), accumulate=True)
+        ops.batch_rowsum(dG, T, 0, P, B, out=G['prompt_pos'].view(P, dim), accumulate=True)
         return G
 
 
@@ -337,6 +358,8 @@ class _GavikoFn(torch.autograd.Function):
         training_dropout = bool(m.transformer.local_attns[0].attn_drop.training) if len(m.transformer.local_attns) else False
         with torch.no_grad():
             logits, saved = engine.forward(img, training_dropout, need_grad)
+        if saved is not None:
+            saved['names'] = names
         ctx.engine, ctx.saved, ctx.names = engine, saved, names
         ctx.shapes = [(t.shape, t.dtype) for t in tensors]
         return logits
@@ -345,9 +368,12 @@ class _GavikoFn(torch.autograd.Function):
     def backward(ctx, dlogits):
         if ctx.saved is None:
             raise RuntimeError('backward called on a forward that ran without gradient tracking')
+        saved = ctx.saved
         with torch.no_grad():
-            G = ctx.engine.backward(ctx.saved, dlogits.float().contiguous())
+            G = ctx.engine.backward(saved, dlogits.float().contiguous())
         ctx.saved = None
+        if saved.get('used_sink'):
+            return (None, None, None, None, *([None] * len(ctx.names)))     # already accumulated into the optimiser's flat buffer
         nmap = ctx.engine._grad_name_map()
         grads = []
         for n, (shape, dtype) in zip(ctx.names, ctx.shapes):

@@ -153,6 +153,11 @@ def skinny_wgrad(a, x, *, dw=None, dw_layout='rd', da_colsum=None, dx_colsum=Non
             _set(p, dw=L.ptr(dw, torch.float32), dw_sj=1, dw_sc=r)
     if ln is not None:
         _set(p, ln_gamma=L.fptr(ln[0]), ln_beta=L.fptr(ln[1]), mean=L.fptr(ln[2]), rstd=L.fptr(ln[3]))
+    fn = L.lib().gvk_skinny_wgrad_ws_floats
+    fn.restype = C.c_size_t
+    n_ws = int(fn(r, dim, M))
+    ws = torch.empty(n_ws, device=a.device, dtype=torch.float32)
+    _set(p, ws=ws, ws_floats=n_ws)
     L.call('gvk_skinny_wgrad', C.byref(p), L.stream())
 
 
@@ -355,14 +360,17 @@ def head_fwd(x, B, T, pool_start, pool_count, gamma, beta, wh, bh, *, eps=1e-5, 
 
 
 def head_bwd(x, B, T, pool_start, pool_count, gamma, beta, wh, bh, pooled, dlogits, *, dx=None, dx_lp=None, eps=1e-5, ssf_scale=None,
-             ssf_shift=None, dgamma=None, dbeta=None, dssf_scale=None, dssf_shift=None, need_dx=True):
+             ssf_shift=None, dgamma=None, dbeta=None, dssf_scale=None, dssf_shift=None, need_dx=True, dwh=None, dbh=None):
     """Returns (dx, dwh, dbh).  dx must be pre-zeroed when pool_count < T (only pooled rows are written)."""
     dim = x.shape[1]
     if need_dx and dx is None:
         dx = torch.zeros((B * T, dim), device=x.device, dtype=torch.float32)
-    dwh = torch.empty_like(wh)
-    dbh = torch.empty_like(bh)
+    accumulate = dwh is not None
+    if not accumulate:
+        dwh = torch.empty_like(wh)
+        dbh = torch.empty_like(bh)
     p = S['gvk_head_bwd_params']()
+    p.accumulate_w = int(accumulate)
     p.f = _head_params(x, B, T, pool_start, pool_count, gamma, beta, wh, bh, pooled, None, eps, ssf_scale, ssf_shift)
     _set(p, dlogits=L.fptr(dlogits), dwh=L.fptr(dwh), dbh=L.fptr(dbh), dgamma=L.fptr(dgamma), dbeta=L.fptr(dbeta),
          dssf_scale=L.fptr(dssf_scale), dssf_shift=L.fptr(dssf_shift))

@@ -12,7 +12,7 @@ class FlatAdam(torch.optim.Optimizer):
     """Adam over one contiguous fp32 buffer.  On construction the parameters (and their .grad) are re-pointed to views of
     flat buffers, so autograd accumulates straight into the exchange buffer and no gather/scatter is needed per step."""
 
-    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, max_grad_norm=1.0, process_group=None, world_size=None):
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, max_grad_norm=1.0, process_group=None, world_size=None, model=None):
         params = [p for p in params if p.requires_grad]
         if not params:
             raise ValueError('FlatAdam: no trainable parameters')
@@ -39,6 +39,10 @@ class FlatAdam(torch.optim.Optimizer):
                 p.data = self.flat_p[off:off + k].view_as(p)
                 p.grad = self.flat_g[off:off + k].view_as(p)
                 off += pad(k)
+        if model is not None and hasattr(model, '_engine'):
+            # let the engine's backward accumulate straight into flat_g (skips ~300 per-tensor autograd accumulations per step)
+            ids = {id(p): n for n, p in model.named_parameters()}
+            model._engine.grad_sink = {ids[id(p)]: p.grad for p in params if id(p) in ids}
         self.max_grad_norm = max_grad_norm
         self.step_count = 0
         self.group = process_group

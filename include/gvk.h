@@ -140,7 +140,10 @@ typedef struct {
 int gvk_rowproj_up(const gvk_rowproj_up_params* p, gvk_stream_t stream);
 
 /* Rank-r weight gradient:  dw(j, c) += sum_m a[m, j] * f(x[m, c]);  da_colsum[j] += sum_m a[m, j];  dx_colsum[c] += sum_m f(x[m, c]).
- * f = optional dropout mask, then optional LayerNorm recomputed from saved mean / rstd.  Accumulates with atomics: zero first. */
+ * f = optional dropout mask, then optional LayerNorm recomputed from saved mean / rstd.  Outputs ACCUMULATE (zero them first).
+ * Deterministic two-stage reduction (per-CTA partials in `ws`, then one reduce launch): `ws` must hold at least
+ * gvk_skinny_wgrad_ws_floats(r, dim, M) floats. */
+size_t gvk_skinny_wgrad_ws_floats(int r, int dim, int M);
 typedef struct {
   const float* a; int lda; int r;
   const float* x; int ldx; int dim; int M;
@@ -148,6 +151,7 @@ typedef struct {
   float* dw; int dw_sj, dw_sc;
   float* da_colsum; float* dx_colsum;
   float drop_p; uint64_t seed; uint64_t offset;
+  float* ws; size_t ws_floats;
 } gvk_skinny_wgrad_params;
 int gvk_skinny_wgrad(const gvk_skinny_wgrad_params* p, gvk_stream_t stream);
 
@@ -336,7 +340,8 @@ typedef struct {
   const float* dlogits;     /* [B, num_classes] */
   float* dx; int ld_dx;     /* [B*T, dim]: only the pooled rows are written (zero the rest beforehand) */
   void* dx_lp; int ld_dx_lp; /* optional bf16 copy of the same rows */
-  float* dwh; float* dbh;   /* [num_classes, dim], [num_classes]: overwritten */
+  float* dwh; float* dbh;   /* [num_classes, dim], [num_classes]: overwritten, or accumulated into when accumulate_w != 0 */
+  int accumulate_w;
   float* dgamma; float* dbeta;  /* optional [dim]: accumulated (atomics) */
   float* dssf_scale; float* dssf_shift; /* optional [dim]: accumulated (atomics) */
 } gvk_head_bwd_params;

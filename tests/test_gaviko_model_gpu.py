@@ -98,3 +98,30 @@ def test_rejects_cpu_input():
     model = Gaviko(**kw)
     with pytest.raises(GvkError):
         model(torch.zeros(1, 1, 48, 64, 64))
+
+
+def test_flat_adam_sink_and_step_match_torch():
+    """FlatAdam (engine accumulates straight into the flat buffer; fused clip+Adam kernels) == autograd grads + torch clip + torch Adam."""
+    from gaviko_b200.optim import FlatAdam
+    ma, img, y = _build('gaviko_t16_small', 'fp32')
+    mb, _, _ = _build('gaviko_t16_small', 'fp32')
+    crit = CrossEntropyLoss()
+    opt_a = FlatAdam(ma.parameters(), lr=1e-3, eps=1e-8, max_grad_norm=1.0, model=ma)
+    tb = [p for p in mb.parameters() if p.requires_grad]
+    opt_b = torch.optim.Adam(tb, lr=1e-3, eps=1e-8)
+    for step in range(3):
+        opt_a.zero_grad()
+        crit(ma(img), y).backward()
+        opt_b.zero_grad()
+        crit(mb(img), y).backward()
+        if step == 0:
+            for (n, pa), (_, pb) in zip(ma.named_parameters(), mb.named_parameters()):
+                if pa.requires_grad:
+                    assert torch.allclose(pa.grad, pb.grad, rtol=1e-4, atol=1e-7), n
+        norm_b = torch.nn.utils.clip_grad_norm_(mb.parameters(), 1.0)
+        opt_a.step()
+        opt_b.step()
+        assert abs(opt_a.grad_norm.item() - norm_b.item()) <= 1e-4 * norm_b.item()
+    for (n, pa), (_, pb) in zip(ma.named_parameters(), mb.named_parameters()):
+        if pa.requires_grad:
+            assert torch.allclose(pa, pb, rtol=1e-4, atol=1e-6), n

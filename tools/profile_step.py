@@ -17,7 +17,7 @@ torch.manual_seed(0)
 with contextlib.redirect_stdout(io.StringIO()):
     model = Gaviko(**GAVIKO_KW, backbone=a.backbone, compute_dtype=a.dtype).cuda()
 model.train()
-opt = FlatAdam(model.parameters(), lr=1e-4)
+opt = FlatAdam(model.parameters(), lr=1e-4, model=model)
 crit = FocalLoss(gamma=1.2)
 x = torch.rand(a.batch, 1, 120, 160, 160, device='cuda'); y = torch.randint(0, 5, (a.batch,), device='cuda')
 
