@@ -123,104 +123,186 @@ int layernorm_fwd(const gvk_layernorm_fwd_params* p, cudaStream_t stream) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// rank-r down projection (+ optional LN prologue, activation, chained second projection)
+// Register-blocked rank-r kernels.  A warp owns ROWS token rows at a time (ROWS = 4, or 2 for dim = 1024) so every weight value
+// fetched from shared memory feeds ROWS FMAs (the one-row-per-warp form is bound by the LDS pipe, not by HBM), and all of the
+// group's global loads are issued before the first use (ROWS x 3 KB in flight per warp).
+// ------------------------------------------------------------------------------------------------
+template <int N>
+struct ReduceStep {
+  // Halving exchange: lanes with bit `o` set keep the upper half of v[0, 2N), the others the lower half; the partner's copy is added.
+  static __device__ __forceinline__ void run(float* v, int lane, int o) {
+    const bool upper = (lane & o) != 0;
+#pragma unroll
+    for (int k = 0; k < N; ++k) {
+      const float keep = upper ? v[k + N] : v[k];
+      const float send = upper ? v[k] : v[k + N];
+      v[k] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+    }
+  }
+};
+// Sum 96 per-lane partials across the warp with 93 shuffles (a plain butterfly needs 480).  On return lane L holds in v[0..2] the
+// totals of indices base, base+1, base+2 with base = 48 b4 + 24 b3 + 12 b2 + 6 b1 + 3 b0 (b_k = bit k of L).
+__device__ __forceinline__ void warp_reduce_scatter96(float (&v)[96], int lane) {
+  ReduceStep<48>::run(v, lane, 16);
+  ReduceStep<24>::run(v, lane, 8);
+  ReduceStep<12>::run(v, lane, 4);
+  ReduceStep<6>::run(v, lane, 2);
+  ReduceStep<3>::run(v, lane, 1);
+}
+__device__ __forceinline__ int reduce_scatter96_base(int lane) {
+  return 48 * ((lane >> 4) & 1) + 24 * ((lane >> 3) & 1) + 12 * ((lane >> 2) & 1) + 6 * ((lane >> 1) & 1) + 3 * (lane & 1);
+}
+
+template <int NITER>
+struct RowBlock {
+  static constexpr int ROWS = NITER <= 12 ? 4 : 2;
+  static constexpr int JCH = 96 / ROWS;  // projection outputs handled per pass over the row registers
+};
+
+static inline int row_block_grid(int M, int rows_per_warp) {
+  const int blocks = (M + kRowWarps * rows_per_warp - 1) / (kRowWarps * rows_per_warp);
+  return std::max(1, std::min(blocks, sm_count()));
+}
+
+// ------------------------------------------------------------------------------------------------
+// rank-r down projection (+ optional dropout / LN prologue, activation, chained second projection)
 // ------------------------------------------------------------------------------------------------
 template <int NITER>
-__global__ void __launch_bounds__(kRowThreads) rowproj_down_kernel(gvk_rowproj_down_params p) {
+__global__ void __launch_bounds__(kRowThreads, 1) rowproj_down_kernel(gvk_rowproj_down_params p, int rpad) {
   extern __shared__ float smem[];
-  const int dim = NITER * 64;
-  float* sw = smem;                 // [r][dim]
-  float* sw2 = smem + p.r * dim;    // [r2][r]
+  constexpr int dim = NITER * 64;
+  constexpr int ROWS = RowBlock<NITER>::ROWS, JCH = RowBlock<NITER>::JCH;
+  float* sw = smem;                       // [rpad][dim], rows >= r are zero
+  float* sw2 = sw + (size_t)rpad * dim;   // [r2][r]
+  float* sz = sw2 + p.r2 * p.r;           // [kRowWarps][ROWS][rpad] activated latents (chained projection only)
   stage_weight(sw, p.w, p.r, dim, p.w_sj, p.w_sc);
+  for (int idx = p.r * dim + threadIdx.x; idx < rpad * dim; idx += blockDim.x) sw[idx] = 0.f;
   if (p.w2)
     for (int idx = threadIdx.x; idx < p.r2 * p.r; idx += blockDim.x) sw2[idx] = p.w2[idx];
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const float inv_dim = 1.0f / dim;
   const float inv_keep = p.drop_p > 0.f ? 1.0f / (1.0f - p.drop_p) : 1.f;
-  for (int row = blockIdx.x * kRowWarps + warp; row < p.M; row += gridDim.x * kRowWarps) {
-    float2 xv[NITER];
-    const float* xr = p.x + (size_t)row * p.ldx;
+  const int base = reduce_scatter96_base(lane);
+  const int q_out = base / JCH, j_out = base % JCH;   // this lane's outputs after the reduce: row q_out, latents j_out .. j_out + 2
+  float* szw = sz + (size_t)warp * ROWS * rpad;
+  const int ngroups = (p.M + ROWS - 1) / ROWS;
+  for (int grp = blockIdx.x * kRowWarps + warp; grp < ngroups; grp += gridDim.x * kRowWarps) {
+    const int row0 = grp * ROWS;
+    float2 xv[ROWS][NITER];
 #pragma unroll
-    for (int i = 0; i < NITER; ++i) xv[i] = *reinterpret_cast<const float2*>(xr + lane * 2 + 64 * i);
+    for (int q = 0; q < ROWS; ++q) {
+      const float* xr = p.x + (size_t)min(row0 + q, p.M - 1) * p.ldx + lane * 2;
+#pragma unroll
+      for (int i = 0; i < NITER; ++i) xv[q][i] = *reinterpret_cast<const float2*>(xr + 64 * i);
+    }
     if (p.drop_p > 0.f) {
 #pragma unroll
-      for (int i = 0; i < NITER; ++i) {
-        const float2 m = drop_mult2(p.seed, p.offset + (uint64_t)row * dim + lane * 2 + 64 * i, p.drop_p, inv_keep);
-        xv[i].x *= m.x;
-        xv[i].y *= m.y;
+      for (int q = 0; q < ROWS; ++q) {
+        const uint64_t e0 = p.offset + (uint64_t)min(row0 + q, p.M - 1) * dim + lane * 2;
+#pragma unroll
+        for (int i = 0; i < NITER; ++i) {
+          const float2 m = drop_mult2(p.seed, e0 + 64 * i, p.drop_p, inv_keep);
+          xv[q][i].x *= m.x;
+          xv[q][i].y *= m.y;
+        }
       }
     }
     if (p.ln_gamma) {
-      float s = 0.f;
 #pragma unroll
-      for (int i = 0; i < NITER; ++i) s += xv[i].x + xv[i].y;
-      const float mean = warp_sum(s) * inv_dim;
-      float v = 0.f;
+      for (int q = 0; q < ROWS; ++q) {
+        float s = 0.f;
 #pragma unroll
-      for (int i = 0; i < NITER; ++i) {
-        const float a = xv[i].x - mean, b = xv[i].y - mean;
-        v += a * a + b * b;
-      }
-      const float rstd = rsqrtf(warp_sum(v) * inv_dim + p.eps);
-      if (lane == 0) {
-        if (p.mean) p.mean[row] = mean;
-        if (p.rstd) p.rstd[row] = rstd;
-      }
+        for (int i = 0; i < NITER; ++i) s += xv[q][i].x + xv[q][i].y;
+        const float mean = warp_sum(s) * inv_dim;
+        float v = 0.f;
 #pragma unroll
-      for (int i = 0; i < NITER; ++i) {
-        const int c = lane * 2 + 64 * i;
-        const float2 g = *reinterpret_cast<const float2*>(p.ln_gamma + c);
-        const float2 b = *reinterpret_cast<const float2*>(p.ln_beta + c);
-        xv[i].x = (xv[i].x - mean) * rstd * g.x + b.x;
-        xv[i].y = (xv[i].y - mean) * rstd * g.y + b.y;
+        for (int i = 0; i < NITER; ++i) {
+          const float a = xv[q][i].x - mean, b = xv[q][i].y - mean;
+          v += a * a + b * b;
+        }
+        const float rstd = rsqrtf(warp_sum(v) * inv_dim + p.eps);
+        if (lane == 0 && row0 + q < p.M) {
+          if (p.mean) p.mean[row0 + q] = mean;
+          if (p.rstd) p.rstd[row0 + q] = rstd;
+        }
+#pragma unroll
+        for (int i = 0; i < NITER; ++i) {
+          const int c = lane * 2 + 64 * i;
+          const float2 g = *reinterpret_cast<const float2*>(p.ln_gamma + c);
+          const float2 b = *reinterpret_cast<const float2*>(p.ln_beta + c);
+          xv[q][i].x = (xv[q][i].x - mean) * rstd * g.x + b.x;
+          xv[q][i].y = (xv[q][i].y - mean) * rstd * g.y + b.y;
+        }
       }
     }
-    float zl = 0.f;  // lane j keeps z[j]
-    for (int j = 0; j < p.r; ++j) {
-      const float* wj = sw + j * dim + lane * 2;
-      float acc = 0.f;
+    const int orow = row0 + q_out;
+    for (int j0 = 0; j0 < p.r; j0 += JCH) {
+      float acc[96];
 #pragma unroll
-      for (int i = 0; i < NITER; ++i) {
-        const float2 w = *reinterpret_cast<const float2*>(wj + 64 * i);
-        acc = fmaf(xv[i].x, w.x, acc);
-        acc = fmaf(xv[i].y, w.y, acc);
+      for (int jj = 0; jj < JCH; ++jj) {
+        const float* wj = sw + (size_t)(j0 + jj) * dim + lane * 2;
+        float a[ROWS];
+#pragma unroll
+        for (int q = 0; q < ROWS; ++q) a[q] = 0.f;
+#pragma unroll
+        for (int i = 0; i < NITER; ++i) {
+          const float2 w = *reinterpret_cast<const float2*>(wj + 64 * i);
+#pragma unroll
+          for (int q = 0; q < ROWS; ++q) a[q] = fmaf(xv[q][i].y, w.y, fmaf(xv[q][i].x, w.x, a[q]));
+        }
+#pragma unroll
+        for (int q = 0; q < ROWS; ++q) acc[q * JCH + jj] = a[q];
       }
-      acc = warp_sum(acc);
-      if (lane == j) zl = acc;
-    }
-    if (lane < p.r) {
-      float pre = zl + (p.bias ? p.bias[lane] : 0.f);
-      if (p.pre) p.pre[(size_t)row * p.ldz + lane] = pre;
-      if (p.act == GVK_ROWACT_QUICKGELU)
-        pre = quick_gelu(pre);
-      else if (p.act == GVK_ROWACT_RELU)
-        pre = fmaxf(pre, 0.f);
-      zl = pre;
-      p.z[(size_t)row * p.ldz + lane] = zl;
-    } else {
-      zl = 0.f;
+      warp_reduce_scatter96(acc, lane);
+#pragma unroll
+      for (int u = 0; u < 3; ++u) {
+        const int j = j0 + j_out + u;
+        if (j < p.r) {
+          float pre = acc[u] + (p.bias ? p.bias[j] : 0.f);
+          if (orow < p.M && p.pre) p.pre[(size_t)orow * p.ldz + j] = pre;
+          if (p.act == GVK_ROWACT_QUICKGELU)
+            pre = quick_gelu(pre);
+          else if (p.act == GVK_ROWACT_RELU)
+            pre = fmaxf(pre, 0.f);
+          if (orow < p.M) p.z[(size_t)orow * p.ldz + j] = pre;
+          if (p.w2) szw[q_out * rpad + j] = pre;
+        }
+      }
     }
     if (p.w2) {
-      float o[3] = {0.f, 0.f, 0.f};
-      for (int j = 0; j < p.r; ++j) {
-        const float zj = __shfl_sync(0xffffffffu, zl, j);
-#pragma unroll
-        for (int u = 0; u < 3; ++u)
-          if (lane + 32 * u < p.r2) o[u] = fmaf(zj, sw2[(lane + 32 * u) * p.r + j], o[u]);
+      __syncwarp();
+      for (int o = lane; o < ROWS * p.r2; o += 32) {
+        const int q = o / p.r2, k = o - q * p.r2;
+        const float* zq = szw + q * rpad;
+        const float* wk = sw2 + k * p.r;
+        float s = 0.f;
+        for (int j = 0; j < p.r; ++j) s = fmaf(zq[j], wk[j], s);
+        if (row0 + q < p.M) p.z2[(size_t)(row0 + q) * p.ldz2 + k] = s;
       }
-#pragma unroll
-      for (int u = 0; u < 3; ++u)
-        if (lane + 32 * u < p.r2) p.z2[(size_t)row * p.ldz2 + lane + 32 * u] = o[u];
+      __syncwarp();
     }
   }
 }
 
+static size_t rowproj_down_smem(int r, int r2, int dim, int* rpad_out) {
+  const int jch = dim <= 768 ? 24 : 48, rows = dim <= 768 ? 4 : 2;
+  const int rpad = (r + jch - 1) / jch * jch;
+  *rpad_out = rpad;
+  return ((size_t)rpad * dim + (size_t)r2 * r + (r2 > 0 ? (size_t)kRowWarps * rows * rpad : 0)) * sizeof(float);
+}
+
 int rowproj_down(const gvk_rowproj_down_params* p, cudaStream_t stream) {
   GVK_CHECK_ARG(p && p->x && p->w && p->z, "gvk_rowproj_down: null pointer");
-  GVK_CHECK_ARG(p->r >= 1 && p->r <= 32 && p->r2 >= 0 && p->r2 <= 96, "gvk_rowproj_down: r=%d (<=32), r2=%d (<=96)", p->r, p->r2);
+  GVK_CHECK_ARG(p->r >= 1 && p->r <= 96 && p->r2 >= 0 && p->r2 <= 96, "gvk_rowproj_down: r=%d (<=96), r2=%d (<=96)", p->r, p->r2);
   GVK_CHECK_ARG(p->M > 0 && p->ldx % 2 == 0, "gvk_rowproj_down: bad shape");
-  const size_t smem = ((size_t)p->r * p->dim + (size_t)p->r2 * p->r) * sizeof(float);
+  GVK_CHECK_ARG(!p->w2 || p->z2, "gvk_rowproj_down: chained projection needs z2");
+  int rpad = 0;
+  const size_t smem = rowproj_down_smem(p->r, p->w2 ? p->r2 : 0, p->dim, &rpad);
+  if (smem > 227 * 1024) {
+    set_last_error("gvk_rowproj_down: r=%d at dim=%d needs %zu B of shared memory (> 227 KB)", p->r, p->dim, smem);
+    return GVK_ERR_UNSUPPORTED;
+  }
   GVK_DISPATCH_NITER(p->dim, {
     static size_t configured = 0;
     if (smem > configured) {
@@ -228,7 +310,7 @@ int rowproj_down(const gvk_rowproj_down_params* p, cudaStream_t stream) {
       if (st != GVK_OK) return st;
       configured = smem;
     }
-    rowproj_down_kernel<NITER><<<row_grid(p->M, smem), kRowThreads, smem, stream>>>(*p);
+    rowproj_down_kernel<NITER><<<row_block_grid(p->M, RowBlock<NITER>::ROWS), kRowThreads, smem, stream>>>(*p, rpad);
   });
   GVK_CHECK_LAUNCH("rowproj_down");
   return GVK_OK;
@@ -238,57 +320,90 @@ int rowproj_down(const gvk_rowproj_down_params* p, cudaStream_t stream) {
 // rank-r up projection + bias + dropout + residual
 // ------------------------------------------------------------------------------------------------
 template <int NITER>
-__global__ void __launch_bounds__(kRowThreads) rowproj_up_kernel(gvk_rowproj_up_params p) {
+__global__ void __launch_bounds__(kRowThreads, 1) rowproj_up_kernel(gvk_rowproj_up_params p) {
   extern __shared__ float smem[];
-  const int dim = NITER * 64;
+  constexpr int dim = NITER * 64;
+  constexpr int ROWS = RowBlock<NITER>::ROWS;
   float* sw = smem;  // [r][dim]
   stage_weight(sw, p.w, p.r, dim, p.w_sj, p.w_sc);
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const float inv_keep = p.drop_p > 0.f ? 1.0f / (1.0f - p.drop_p) : 1.f;
-  for (int row = blockIdx.x * kRowWarps + warp; row < p.M; row += gridDim.x * kRowWarps) {
-    const float cl = lane < p.r ? p.c[(size_t)row * p.ldc + lane] : 0.f;
-    float2 acc[NITER];
+  const bool early_res = p.res && !(p.drop_p > 0.f);
+  const int ngroups = (p.M + ROWS - 1) / ROWS;
+  for (int grp = blockIdx.x * kRowWarps + warp; grp < ngroups; grp += gridDim.x * kRowWarps) {
+    const int row0 = grp * ROWS;
+    float cl[ROWS][3];   // lane holds latents lane, lane + 32, lane + 64 of each row
+    float2 acc[ROWS][NITER];
 #pragma unroll
-    for (int i = 0; i < NITER; ++i) {
-      const int c = lane * 2 + 64 * i;
-      acc[i] = p.bias ? *reinterpret_cast<const float2*>(p.bias + c) : make_float2(0.f, 0.f);
+    for (int q = 0; q < ROWS; ++q) {
+      const size_t row = (size_t)min(row0 + q, p.M - 1);
+#pragma unroll
+      for (int u = 0; u < 3; ++u) cl[q][u] = (lane + 32 * u < p.r) ? p.c[row * p.ldc + lane + 32 * u] : 0.f;
+#pragma unroll
+      for (int i = 0; i < NITER; ++i) {
+        const int c = lane * 2 + 64 * i;
+        float2 a = p.bias ? *reinterpret_cast<const float2*>(p.bias + c) : make_float2(0.f, 0.f);
+        if (early_res) {
+          const float2 r = *reinterpret_cast<const float2*>(p.res + row * p.ld_res + c);
+          a.x += r.x;
+          a.y += r.y;
+        }
+        acc[q][i] = a;
+      }
     }
     for (int j = 0; j < p.r; ++j) {
-      const float cj = __shfl_sync(0xffffffffu, cl, j);
-      const float* wj = sw + j * dim + lane * 2;
+      float cj[ROWS];
+#pragma unroll
+      for (int q = 0; q < ROWS; ++q) {
+        const float src = j < 32 ? cl[q][0] : (j < 64 ? cl[q][1] : cl[q][2]);
+        cj[q] = __shfl_sync(0xffffffffu, src, j & 31);
+      }
+      const float* wj = sw + (size_t)j * dim + lane * 2;
 #pragma unroll
       for (int i = 0; i < NITER; ++i) {
         const float2 w = *reinterpret_cast<const float2*>(wj + 64 * i);
-        acc[i].x = fmaf(cj, w.x, acc[i].x);
-        acc[i].y = fmaf(cj, w.y, acc[i].y);
+#pragma unroll
+        for (int q = 0; q < ROWS; ++q) {
+          acc[q][i].x = fmaf(cj[q], w.x, acc[q][i].x);
+          acc[q][i].y = fmaf(cj[q], w.y, acc[q][i].y);
+        }
       }
     }
 #pragma unroll
-    for (int i = 0; i < NITER; ++i) {
-      const int c = lane * 2 + 64 * i;
-      float2 v = acc[i];
-      if (p.drop_p > 0.f) {
-        const float2 m = drop_mult2(p.seed, p.offset + (uint64_t)row * dim + c, p.drop_p, inv_keep);
-        v.x *= m.x;
-        v.y *= m.y;
+    for (int q = 0; q < ROWS; ++q) {
+      const int row = row0 + q;
+      if (row >= p.M) break;
+#pragma unroll
+      for (int i = 0; i < NITER; ++i) {
+        const int c = lane * 2 + 64 * i;
+        float2 v = acc[q][i];
+        if (p.drop_p > 0.f) {
+          const float2 m = drop_mult2(p.seed, p.offset + (uint64_t)row * dim + c, p.drop_p, inv_keep);
+          v.x *= m.x;
+          v.y *= m.y;
+          if (p.res) {
+            const float2 r = *reinterpret_cast<const float2*>(p.res + (size_t)row * p.ld_res + c);
+            v.x += r.x;
+            v.y += r.y;
+          }
+        }
+        *reinterpret_cast<float2*>(p.out + (size_t)row * p.ld_out + c) = v;
+        if (p.out_lp) *reinterpret_cast<__nv_bfloat162*>(reinterpret_cast<__nv_bfloat16*>(p.out_lp) + (size_t)row * p.ld_out_lp + c) = __floats2bfloat162_rn(v.x, v.y);
       }
-      if (p.res) {
-        const float2 r = *reinterpret_cast<const float2*>(p.res + (size_t)row * p.ld_res + c);
-        v.x += r.x;
-        v.y += r.y;
-      }
-      *reinterpret_cast<float2*>(p.out + (size_t)row * p.ld_out + c) = v;
-      if (p.out_lp) *reinterpret_cast<__nv_bfloat162*>(reinterpret_cast<__nv_bfloat16*>(p.out_lp) + (size_t)row * p.ld_out_lp + c) = __floats2bfloat162_rn(v.x, v.y);
     }
   }
 }
 
 int rowproj_up(const gvk_rowproj_up_params* p, cudaStream_t stream) {
   GVK_CHECK_ARG(p && p->c && p->w && p->out, "gvk_rowproj_up: null pointer");
-  GVK_CHECK_ARG(p->r >= 1 && p->r <= 32, "gvk_rowproj_up: r=%d must be in [1,32]", p->r);
+  GVK_CHECK_ARG(p->r >= 1 && p->r <= 96, "gvk_rowproj_up: r=%d must be in [1,96]", p->r);
   GVK_CHECK_ARG(p->M > 0 && p->ld_out % 2 == 0 && (!p->res || p->ld_res % 2 == 0), "gvk_rowproj_up: bad shape");
   const size_t smem = (size_t)p->r * p->dim * sizeof(float);
+  if (smem > 227 * 1024) {
+    set_last_error("gvk_rowproj_up: r=%d at dim=%d needs %zu B of shared memory (> 227 KB)", p->r, p->dim, smem);
+    return GVK_ERR_UNSUPPORTED;
+  }
   GVK_DISPATCH_NITER(p->dim, {
     static size_t configured = 0;
     if (smem > configured) {
@@ -296,7 +411,7 @@ int rowproj_up(const gvk_rowproj_up_params* p, cudaStream_t stream) {
       if (st != GVK_OK) return st;
       configured = smem;
     }
-    rowproj_up_kernel<NITER><<<row_grid(p->M, smem), kRowThreads, smem, stream>>>(*p);
+    rowproj_up_kernel<NITER><<<row_block_grid(p->M, RowBlock<NITER>::ROWS), kRowThreads, smem, stream>>>(*p);
   });
   GVK_CHECK_LAUNCH("rowproj_up");
   return GVK_OK;
@@ -304,44 +419,47 @@ int rowproj_up(const gvk_rowproj_up_params* p, cudaStream_t stream) {
 
 // ------------------------------------------------------------------------------------------------
 // rank-r weight gradient  dw(j,c) += sum_m a[m,j] * f(x[m,c])
+// A thread owns NCOL columns and all r latents of them (r*NCOL accumulators); rows are consumed kWgRows at a time with every
+// global load of the chunk issued before the FMAs (clamped row index, zeroed latent for the tail: no break in the load path).
 // ------------------------------------------------------------------------------------------------
 constexpr int kWgRows = 8;  // rows staged per step
 
-template <int NCOL, int R>
-__global__ void __launch_bounds__(256) skinny_wgrad_kernel(gvk_skinny_wgrad_params p, int rows_per_cta) {
-  __shared__ float sa[kWgRows][R];
+template <int R, int THREADS>
+__global__ void __launch_bounds__(THREADS, 2) skinny_wgrad_kernel(gvk_skinny_wgrad_params p, int rows_per_cta) {
+  __shared__ __align__(16) float sa[kWgRows][R];
   __shared__ float smean[kWgRows], srstd[kWgRows];
   const int tid = threadIdx.x;
   const int m_begin = blockIdx.x * rows_per_cta;
   const int m_end = min(p.M, m_begin + rows_per_cta);
-  float acc[NCOL][R];
-  float xsum[NCOL];
+  const bool colv = tid * 4 < p.dim;            // thread owns columns 4 tid .. 4 tid + 3 (dim % 4 == 0)
+  const int c0 = colv ? tid * 4 : 0;
+  float acc[4][R];
+  float xsum[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-  for (int i = 0; i < NCOL; ++i) {
-    xsum[i] = 0.f;
+  for (int i = 0; i < 4; ++i)
 #pragma unroll
     for (int j = 0; j < R; ++j) acc[i][j] = 0.f;
-  }
   float asum = 0.f;  // thread j < r
-  float g[NCOL], b[NCOL];
-#pragma unroll
-  for (int i = 0; i < NCOL; ++i) {
-    const int c = tid + 256 * i;
-    g[i] = (p.ln_gamma && c < p.dim) ? p.ln_gamma[c] : 1.f;
-    b[i] = (p.ln_gamma && c < p.dim) ? p.ln_beta[c] : 0.f;
+  float4 g = make_float4(1.f, 1.f, 1.f, 1.f), b = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (p.ln_gamma) {
+    g = *reinterpret_cast<const float4*>(p.ln_gamma + c0);
+    b = *reinterpret_cast<const float4*>(p.ln_beta + c0);
   }
   const float inv_keep = p.drop_p > 0.f ? 1.0f / (1.0f - p.drop_p) : 1.f;
   for (int m0 = m_begin; m0 < m_end; m0 += kWgRows) {
-    __syncthreads();
-    for (int idx = tid; idx < kWgRows * R; idx += 256) {
+    float4 xr[kWgRows];
+#pragma unroll
+    for (int rr = 0; rr < kWgRows; ++rr) xr[rr] = *reinterpret_cast<const float4*>(p.x + (size_t)min(m0 + rr, m_end - 1) * p.ldx + c0);
+    __syncthreads();   // previous chunk's sa fully consumed
+    for (int idx = tid; idx < kWgRows * R; idx += THREADS) {
       const int rr = idx / R, j = idx - rr * R;
       const int m = m0 + rr;
-      sa[rr][j] = (m < m_end && j < p.r) ? p.a[(size_t)m * p.lda + j] : 0.f;
+      sa[rr][j] = (m < m_end && j < p.r) ? p.a[(size_t)m * p.lda + j] : 0.f;   // zero latent: tail rows contribute nothing to dw
     }
     if (tid < kWgRows) {
-      const int m = m0 + tid;
-      smean[tid] = (p.mean && m < m_end) ? p.mean[m] : 0.f;
-      srstd[tid] = (p.rstd && m < m_end) ? p.rstd[m] : 1.f;
+      const int m = min(m0 + tid, m_end - 1);
+      smean[tid] = p.mean ? p.mean[m] : 0.f;
+      srstd[tid] = p.rstd ? p.rstd[m] : 1.f;
     }
     __syncthreads();
     if (tid < R) {
@@ -350,37 +468,49 @@ __global__ void __launch_bounds__(256) skinny_wgrad_kernel(gvk_skinny_wgrad_para
     }
 #pragma unroll
     for (int rr = 0; rr < kWgRows; ++rr) {
-      const int m = m0 + rr;
-      if (m >= m_end) break;
+      float x[4] = {xr[rr].x, xr[rr].y, xr[rr].z, xr[rr].w};
+      if (p.drop_p > 0.f) {
+        const uint64_t e = p.offset + (uint64_t)min(m0 + rr, m_end - 1) * p.dim + c0;
+        const float2 ma = drop_mult2(p.seed, e, p.drop_p, inv_keep), mb = drop_mult2(p.seed, e + 2, p.drop_p, inv_keep);
+        x[0] *= ma.x; x[1] *= ma.y; x[2] *= mb.x; x[3] *= mb.y;
+      }
+      if (p.ln_gamma) {
+        const float mu = smean[rr], rs = srstd[rr];
+        x[0] = (x[0] - mu) * rs * g.x + b.x;
+        x[1] = (x[1] - mu) * rs * g.y + b.y;
+        x[2] = (x[2] - mu) * rs * g.z + b.z;
+        x[3] = (x[3] - mu) * rs * g.w + b.w;
+      }
+      if (m0 + rr < m_end) {
 #pragma unroll
-      for (int i = 0; i < NCOL; ++i) {
-        const int c = tid + 256 * i;
-        if (c < p.dim) {
-          float x = p.x[(size_t)m * p.ldx + c];
-          if (p.drop_p > 0.f) x *= drop_mult(p.seed, p.offset + (uint64_t)m * p.dim + c, p.drop_p, inv_keep);
-          if (p.ln_gamma) x = (x - smean[rr]) * srstd[rr] * g[i] + b[i];
-          xsum[i] += x;
+        for (int i = 0; i < 4; ++i) xsum[i] += x[i];
+      }
 #pragma unroll
-          for (int j = 0; j < R; ++j) acc[i][j] = fmaf(sa[rr][j], x, acc[i][j]);
+      for (int j = 0; j < R; j += 4) {
+        const float4 a4 = *reinterpret_cast<const float4*>(&sa[rr][j]);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          acc[i][j] = fmaf(a4.x, x[i], acc[i][j]);
+          acc[i][j + 1] = fmaf(a4.y, x[i], acc[i][j + 1]);
+          acc[i][j + 2] = fmaf(a4.z, x[i], acc[i][j + 2]);
+          acc[i][j + 3] = fmaf(a4.w, x[i], acc[i][j + 3]);
         }
       }
     }
   }
   // per-CTA partials (no atomics: same-address contention from ~300 CTAs serialises in L2); reduced by skinny_wgrad_reduce_kernel
-  float* ws_dw = p.ws + (size_t)blockIdx.x * p.r * p.dim;
-  float* ws_dx = p.ws + (size_t)gridDim.x * p.r * p.dim + (size_t)blockIdx.x * p.dim;
-  float* ws_da = p.ws + (size_t)gridDim.x * (p.r + 1) * p.dim + (size_t)blockIdx.x * 32;
+  if (colv) {
+    float* ws_dw = p.ws + (size_t)blockIdx.x * p.r * p.dim;
+    float* ws_dx = p.ws + (size_t)gridDim.x * p.r * p.dim + (size_t)blockIdx.x * p.dim;
 #pragma unroll
-  for (int i = 0; i < NCOL; ++i) {
-    const int c = tid + 256 * i;
-    if (c < p.dim) {
-#pragma unroll
-      for (int j = 0; j < R; ++j)
-        if (j < p.r) ws_dw[(size_t)j * p.dim + c] = acc[i][j];
-      ws_dx[c] = xsum[i];
-    }
+    for (int j = 0; j < R; ++j)
+      if (j < p.r) *reinterpret_cast<float4*>(ws_dw + (size_t)j * p.dim + c0) = make_float4(acc[0][j], acc[1][j], acc[2][j], acc[3][j]);
+    *reinterpret_cast<float4*>(ws_dx + c0) = make_float4(xsum[0], xsum[1], xsum[2], xsum[3]);
   }
-  if (tid < 32) ws_da[tid] = tid < p.r ? asum : 0.f;
+  if (tid < 32) {
+    float* ws_da = p.ws + (size_t)gridDim.x * (p.r + 1) * p.dim + (size_t)blockIdx.x * 32;
+    ws_da[tid] = tid < p.r ? asum : 0.f;
+  }
 }
 
 __global__ void __launch_bounds__(256) skinny_wgrad_reduce_kernel(gvk_skinny_wgrad_params p, int ncta) {
@@ -388,10 +518,17 @@ __global__ void __launch_bounds__(256) skinny_wgrad_reduce_kernel(gvk_skinny_wgr
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx < rd) {
     if (!p.dw) return;
-    float s = 0.f;
-    for (int k = 0; k < ncta; ++k) s += p.ws[(size_t)k * rd + idx];
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+    int k = 0;
+    for (; k + 4 <= ncta; k += 4) {
+      s0 += p.ws[(size_t)k * rd + idx];
+      s1 += p.ws[(size_t)(k + 1) * rd + idx];
+      s2 += p.ws[(size_t)(k + 2) * rd + idx];
+      s3 += p.ws[(size_t)(k + 3) * rd + idx];
+    }
+    for (; k < ncta; ++k) s0 += p.ws[(size_t)k * rd + idx];
     const int j = idx / p.dim, c = idx - j * p.dim;
-    p.dw[(size_t)j * p.dw_sj + (size_t)c * p.dw_sc] += s;
+    p.dw[(size_t)j * p.dw_sj + (size_t)c * p.dw_sc] += (s0 + s1) + (s2 + s3);
   } else if (idx < rd + p.dim) {
     if (!p.dx_colsum) return;
     const int c = idx - rd;
@@ -410,7 +547,7 @@ __global__ void __launch_bounds__(256) skinny_wgrad_reduce_kernel(gvk_skinny_wgr
 }
 
 static void skinny_wgrad_plan(int M, int* ctas, int* rows_per_cta) {
-  const int want = std::max(1, std::min(sm_count() * 2, (M + 63) / 64));
+  const int want = std::max(1, std::min(sm_count() * 2, (M + 31) / 32));
   int rpc = (M + want - 1) / want;
   rpc = (rpc + kWgRows - 1) / kWgRows * kWgRows;
   *rows_per_cta = rpc;
@@ -423,16 +560,16 @@ size_t skinny_wgrad_ws_floats(int r, int dim, int M) {
   return (size_t)ctas * ((size_t)(r + 1) * dim + 32);
 }
 
-template <int NCOL>
+template <int THREADS>
 static int skinny_wgrad_launch(const gvk_skinny_wgrad_params* p, cudaStream_t stream) {
   int grid, rows_per_cta;
   skinny_wgrad_plan(p->M, &grid, &rows_per_cta);
   if (p->r <= 8)
-    skinny_wgrad_kernel<NCOL, 8><<<grid, 256, 0, stream>>>(*p, rows_per_cta);
+    skinny_wgrad_kernel<8, THREADS><<<grid, THREADS, 0, stream>>>(*p, rows_per_cta);
   else if (p->r <= 20)
-    skinny_wgrad_kernel<NCOL, 20><<<grid, 256, 0, stream>>>(*p, rows_per_cta);
+    skinny_wgrad_kernel<20, THREADS><<<grid, THREADS, 0, stream>>>(*p, rows_per_cta);
   else
-    skinny_wgrad_kernel<NCOL, 32><<<grid, 256, 0, stream>>>(*p, rows_per_cta);
+    skinny_wgrad_kernel<32, THREADS><<<grid, THREADS, 0, stream>>>(*p, rows_per_cta);
   GVK_CHECK_LAUNCH("skinny_wgrad");
   const int total = p->r * p->dim + p->dim + p->r;
   skinny_wgrad_reduce_kernel<<<(total + 255) / 256, 256, 0, stream>>>(*p, grid);
@@ -442,27 +579,35 @@ static int skinny_wgrad_launch(const gvk_skinny_wgrad_params* p, cudaStream_t st
 
 int skinny_wgrad(const gvk_skinny_wgrad_params* p, cudaStream_t stream) {
   GVK_CHECK_ARG(p && p->a && p->x, "gvk_skinny_wgrad: null pointer");
-  GVK_CHECK_ARG(p->r >= 1 && p->r <= 32 && p->dim >= 1 && p->dim <= 1024 && p->M > 0, "gvk_skinny_wgrad: r=%d dim=%d M=%d", p->r, p->dim, p->M);
+  GVK_CHECK_ARG(p->r >= 1 && p->r <= 32 && p->dim >= 4 && p->dim <= 1024 && p->dim % 4 == 0 && p->ldx % 4 == 0 && p->M > 0,
+                "gvk_skinny_wgrad: r=%d dim=%d ldx=%d M=%d (r <= 32, dim and ldx multiples of 4, dim <= 1024)", p->r, p->dim, p->ldx, p->M);
+  GVK_CHECK_ARG((reinterpret_cast<uintptr_t>(p->x) & 15) == 0, "gvk_skinny_wgrad: x must be 16-byte aligned");
   GVK_CHECK_ARG(!p->ln_gamma || (p->ln_beta && p->mean && p->rstd), "gvk_skinny_wgrad: LN recompute needs beta, mean, rstd");
   GVK_CHECK_ARG(p->ws && p->ws_floats >= skinny_wgrad_ws_floats(p->r, p->dim, p->M), "gvk_skinny_wgrad: workspace of %zu floats required (gvk_skinny_wgrad_ws_floats)",
                 skinny_wgrad_ws_floats(p->r, p->dim, p->M));
-  switch ((p->dim + 255) / 256) {
-    case 1: return skinny_wgrad_launch<1>(p, stream);
-    case 2: return skinny_wgrad_launch<2>(p, stream);
-    case 3: return skinny_wgrad_launch<3>(p, stream);
-    default: return skinny_wgrad_launch<4>(p, stream);
-  }
+  // thread = 4 adjacent columns x all r latents (one 16-byte load per row); 2+ CTAs per SM keep >= 48 KB of loads in flight
+  if (p->dim <= 256) return skinny_wgrad_launch<64>(p, stream);
+  if (p->dim <= 384) return skinny_wgrad_launch<96>(p, stream);
+  if (p->dim <= 768) return skinny_wgrad_launch<192>(p, stream);
+  return skinny_wgrad_launch<256>(p, stream);
 }
 
 // ------------------------------------------------------------------------------------------------
 // LayerNorm backward
+//   dx = dres + LN'(dy) + az @ aw        dy dense, or rank-r (dy = dz @ w);  az @ aw is an optional rank-ra term added OUTSIDE the
+//   norm (the dgrad of a down-projection that reads the same residual stream: model/gaviko.py:155 after :304's LayerNorm input).
+// Two rows per warp so the rank-r panels read from shared memory feed two rows of FMAs, and both rows' loads are in flight together.
 // ------------------------------------------------------------------------------------------------
 template <int NITER, bool PGRAD>
-__global__ void __launch_bounds__(kRowThreads) layernorm_bwd_kernel(gvk_layernorm_bwd_params p) {
+__global__ void __launch_bounds__(kRowThreads, 1) layernorm_bwd_kernel(gvk_layernorm_bwd_params p) {
   extern __shared__ float smem[];
-  const int dim = NITER * 64;
-  float* sw = smem;  // [r][dim] when dy is given in rank-r form
+  constexpr int dim = NITER * 64;
+  constexpr int ROWS = 2;
+  float* sw = smem;                                   // [r][dim] when dy is given in rank-r form
+  float* saw = sw + (p.dz ? (size_t)p.r * dim : 0);   // [ra][dim] additive rank-ra term
+  float* red = saw + (p.az ? (size_t)p.ra * dim : 0); // [kRowWarps][2*dim] parameter-gradient staging
   if (p.dz) stage_weight(sw, p.w, p.r, dim, p.w_sj, p.w_sc);
+  if (p.az) stage_weight(saw, p.aw, p.ra, dim, p.aw_sj, p.aw_sc);
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const float inv_dim = 1.0f / dim;
@@ -470,65 +615,125 @@ __global__ void __launch_bounds__(kRowThreads) layernorm_bwd_kernel(gvk_layernor
   float2 dg[NG], db[NG];
 #pragma unroll
   for (int i = 0; i < NG; ++i) dg[i] = db[i] = make_float2(0.f, 0.f);
-  float2 gam[NITER];
+  const int ngroups = (p.M + ROWS - 1) / ROWS;
+  for (int grp = blockIdx.x * kRowWarps + warp; grp < ngroups; grp += gridDim.x * kRowWarps) {
+    const int row0 = grp * ROWS;
+    size_t rowc[ROWS];
 #pragma unroll
-  for (int i = 0; i < NITER; ++i) gam[i] = *reinterpret_cast<const float2*>(p.gamma + lane * 2 + 64 * i);
-
-  for (int row = blockIdx.x * kRowWarps + warp; row < p.M; row += gridDim.x * kRowWarps) {
-    float2 dy[NITER];
+    for (int q = 0; q < ROWS; ++q) rowc[q] = (size_t)min(row0 + q, p.M - 1);
+    float2 dy[ROWS][NITER], xh[ROWS][NITER];
+    // ---- issue the streaming loads first
+#pragma unroll
+    for (int q = 0; q < ROWS; ++q)
+#pragma unroll
+      for (int i = 0; i < NITER; ++i) xh[q][i] = *reinterpret_cast<const float2*>(p.x + rowc[q] * p.ldx + lane * 2 + 64 * i);
     if (p.dz) {
-      const float zl = lane < p.r ? p.dz[(size_t)row * p.ld_dz + lane] : 0.f;
+      float zl[ROWS];
 #pragma unroll
-      for (int i = 0; i < NITER; ++i) dy[i] = make_float2(0.f, 0.f);
+      for (int q = 0; q < ROWS; ++q) {
+        zl[q] = lane < p.r ? p.dz[rowc[q] * p.ld_dz + lane] : 0.f;
+#pragma unroll
+        for (int i = 0; i < NITER; ++i) dy[q][i] = make_float2(0.f, 0.f);
+      }
       for (int j = 0; j < p.r; ++j) {
-        const float zj = __shfl_sync(0xffffffffu, zl, j);
-        const float* wj = sw + j * dim + lane * 2;
+        float zj[ROWS];
+#pragma unroll
+        for (int q = 0; q < ROWS; ++q) zj[q] = __shfl_sync(0xffffffffu, zl[q], j);
+        const float* wj = sw + (size_t)j * dim + lane * 2;
 #pragma unroll
         for (int i = 0; i < NITER; ++i) {
           const float2 w = *reinterpret_cast<const float2*>(wj + 64 * i);
-          dy[i].x = fmaf(zj, w.x, dy[i].x);
-          dy[i].y = fmaf(zj, w.y, dy[i].y);
+#pragma unroll
+          for (int q = 0; q < ROWS; ++q) {
+            dy[q][i].x = fmaf(zj[q], w.x, dy[q][i].x);
+            dy[q][i].y = fmaf(zj[q], w.y, dy[q][i].y);
+          }
         }
       }
     } else {
 #pragma unroll
-      for (int i = 0; i < NITER; ++i) dy[i] = *reinterpret_cast<const float2*>(p.dy + (size_t)row * p.ld_dy + lane * 2 + 64 * i);
-    }
-    const float mean = p.mean[row], rstd = p.rstd[row];
-    float2 xh[NITER];
-    float s1 = 0.f, s2 = 0.f;
+      for (int q = 0; q < ROWS; ++q)
 #pragma unroll
-    for (int i = 0; i < NITER; ++i) {
-      const float2 x = *reinterpret_cast<const float2*>(p.x + (size_t)row * p.ldx + lane * 2 + 64 * i);
-      xh[i] = make_float2((x.x - mean) * rstd, (x.y - mean) * rstd);
-      if constexpr (PGRAD) {
-        dg[i].x += dy[i].x * xh[i].x;
-        dg[i].y += dy[i].y * xh[i].y;
-        db[i].x += dy[i].x;
-        db[i].y += dy[i].y;
-      }
-      dy[i].x *= gam[i].x;  // g = dy * gamma
-      dy[i].y *= gam[i].y;
-      s1 += dy[i].x + dy[i].y;
-      s2 += dy[i].x * xh[i].x + dy[i].y * xh[i].y;
+        for (int i = 0; i < NITER; ++i) dy[q][i] = *reinterpret_cast<const float2*>(p.dy + rowc[q] * p.ld_dy + lane * 2 + 64 * i);
     }
-    const float m1 = warp_sum(s1) * inv_dim, m2 = warp_sum(s2) * inv_dim;
+    float m1[ROWS], m2[ROWS], rstd[ROWS];
 #pragma unroll
-    for (int i = 0; i < NITER; ++i) {
-      const int c = lane * 2 + 64 * i;
-      float2 dx = make_float2(rstd * (dy[i].x - m1 - xh[i].x * m2), rstd * (dy[i].y - m1 - xh[i].y * m2));
-      if (p.dres) {
-        const float2 r = *reinterpret_cast<const float2*>(p.dres + (size_t)row * p.ld_dres + c);
-        dx.x += r.x;
-        dx.y += r.y;
+    for (int q = 0; q < ROWS; ++q) {
+      const float mean = p.mean[rowc[q]];
+      rstd[q] = p.rstd[rowc[q]];
+      const bool live = row0 + q < p.M;
+      float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+      for (int i = 0; i < NITER; ++i) {
+        const float2 gam = *reinterpret_cast<const float2*>(p.gamma + lane * 2 + 64 * i);
+        xh[q][i] = make_float2((xh[q][i].x - mean) * rstd[q], (xh[q][i].y - mean) * rstd[q]);
+        if constexpr (PGRAD) {
+          if (live) {
+            dg[i].x += dy[q][i].x * xh[q][i].x;
+            dg[i].y += dy[q][i].y * xh[q][i].y;
+            db[i].x += dy[q][i].x;
+            db[i].y += dy[q][i].y;
+          }
+        }
+        dy[q][i].x *= gam.x;  // g = dy * gamma
+        dy[q][i].y *= gam.y;
+        s1 += dy[q][i].x + dy[q][i].y;
+        s2 += dy[q][i].x * xh[q][i].x + dy[q][i].y * xh[q][i].y;
       }
-      *reinterpret_cast<float2*>(p.dx + (size_t)row * p.ld_dx + c) = dx;
-      if (p.dx_lp) *reinterpret_cast<__nv_bfloat162*>(reinterpret_cast<__nv_bfloat16*>(p.dx_lp) + (size_t)row * p.ld_dx_lp + c) = __floats2bfloat162_rn(dx.x, dx.y);
+      m1[q] = warp_sum(s1) * inv_dim;
+      m2[q] = warp_sum(s2) * inv_dim;
+    }
+    // dx (before the additive terms) overwrites dy
+#pragma unroll
+    for (int q = 0; q < ROWS; ++q)
+#pragma unroll
+      for (int i = 0; i < NITER; ++i) {
+        dy[q][i].x = rstd[q] * (dy[q][i].x - m1[q] - xh[q][i].x * m2[q]);
+        dy[q][i].y = rstd[q] * (dy[q][i].y - m1[q] - xh[q][i].y * m2[q]);
+      }
+    if (p.dres) {
+#pragma unroll
+      for (int q = 0; q < ROWS; ++q)
+#pragma unroll
+        for (int i = 0; i < NITER; ++i) {
+          const float2 r = *reinterpret_cast<const float2*>(p.dres + rowc[q] * p.ld_dres + lane * 2 + 64 * i);
+          dy[q][i].x += r.x;
+          dy[q][i].y += r.y;
+        }
+    }
+    if (p.az) {
+      float zl[ROWS];
+#pragma unroll
+      for (int q = 0; q < ROWS; ++q) zl[q] = lane < p.ra ? p.az[rowc[q] * p.ld_az + lane] : 0.f;
+      for (int j = 0; j < p.ra; ++j) {
+        float zj[ROWS];
+#pragma unroll
+        for (int q = 0; q < ROWS; ++q) zj[q] = __shfl_sync(0xffffffffu, zl[q], j);
+        const float* wj = saw + (size_t)j * dim + lane * 2;
+#pragma unroll
+        for (int i = 0; i < NITER; ++i) {
+          const float2 w = *reinterpret_cast<const float2*>(wj + 64 * i);
+#pragma unroll
+          for (int q = 0; q < ROWS; ++q) {
+            dy[q][i].x = fmaf(zj[q], w.x, dy[q][i].x);
+            dy[q][i].y = fmaf(zj[q], w.y, dy[q][i].y);
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < ROWS; ++q) {
+      const int row = row0 + q;
+      if (row >= p.M) break;
+#pragma unroll
+      for (int i = 0; i < NITER; ++i) {
+        const int c = lane * 2 + 64 * i;
+        *reinterpret_cast<float2*>(p.dx + (size_t)row * p.ld_dx + c) = dy[q][i];
+        if (p.dx_lp) *reinterpret_cast<__nv_bfloat162*>(reinterpret_cast<__nv_bfloat16*>(p.dx_lp) + (size_t)row * p.ld_dx_lp + c) = __floats2bfloat162_rn(dy[q][i].x, dy[q][i].y);
+      }
     }
   }
   if constexpr (PGRAD) {
-    // cross-warp reduction through smem (reusing the weight staging area is unsafe: use a dedicated tail region)
-    float* red = smem + (p.dz ? p.r * dim : 0);  // [kRowWarps][2*dim]
     __syncthreads();
 #pragma unroll
     for (int i = 0; i < NITER; ++i) {
@@ -556,11 +761,14 @@ int layernorm_bwd(const gvk_layernorm_bwd_params* p, cudaStream_t stream) {
   GVK_CHECK_ARG(p && p->x && p->gamma && p->mean && p->rstd && p->dx, "gvk_layernorm_bwd: null pointer");
   GVK_CHECK_ARG((p->dy != nullptr) != (p->dz != nullptr), "gvk_layernorm_bwd: exactly one of dy / dz must be given");
   GVK_CHECK_ARG(!p->dz || (p->w && p->r >= 1 && p->r <= 32), "gvk_layernorm_bwd: rank-r form needs w and 1 <= r <= 32");
+  GVK_CHECK_ARG(!p->az || (p->aw && p->ra >= 1 && p->ra <= 32), "gvk_layernorm_bwd: additive rank term needs aw and 1 <= ra <= 32");
   const bool red = p->dgamma || p->dbeta;
-  const size_t smem = ((p->dz ? (size_t)p->r * p->dim : 0) + (red ? (size_t)kRowWarps * 2 * p->dim : 0)) * sizeof(float);
-  // With parameter gradients every CTA ends with 2*dim atomics: keep the grid modest.
-  int grid = row_grid(p->M, p->dz ? smem : 0);
-  if (red) grid = std::min(grid, sm_count() * 2);
+  const size_t smem = ((p->dz ? (size_t)p->r * p->dim : 0) + (p->az ? (size_t)p->ra * p->dim : 0) + (red ? (size_t)kRowWarps * 2 * p->dim : 0)) * sizeof(float);
+  if (smem > 227 * 1024) {
+    set_last_error("gvk_layernorm_bwd: needs %zu B of shared memory (> 227 KB)", smem);
+    return GVK_ERR_UNSUPPORTED;
+  }
+  const int grid = row_block_grid(p->M, 2);
   GVK_DISPATCH_NITER(p->dim, {
     static size_t configured[2] = {0, 0};
     if (smem > configured[red]) {

@@ -310,9 +310,8 @@ class GavikoEngine:
             ops.skinny_wgrad(du, st['g_mid'], dw=gF['wd'], dw_layout='rd', da_colsum=gF['bd'])
             ops.skinny_wgrad(dul, st['loc_out'], dw=gF['wd'], dw_layout='rd', da_colsum=gF['bd'])
             # ---- d(g_mid) = dG + LN2'(dH2) + du Wd
-            dGm = ops.layernorm_bwd(st['g_mid'], Lw['ln2_w'], st['mean2'], st['rstd2'], dy=dH2, dres=dG, dx=dH2)
             dGm_lp = torch.empty((B * T, dim), device=dev, dtype=cdt) if lp else None
-            ops.rowproj_up(du, Fu['wd'], transposed=True, res=dGm, out=dGm, out_lp=dGm_lp)
+            dGm = ops.layernorm_bwd(st['g_mid'], Lw['ln2_w'], st['mean2'], st['rstd2'], dy=dH2, dres=dG, dx=dH2, dx_lp=dGm_lp, az=du, aw=Fu['wd'])
             # ---- d(loc_out) += dul Wd
             if dLoc is None:
                 dLoc = ops.rowproj_up(dul, Fu['wd'], transposed=True)

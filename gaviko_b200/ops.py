@@ -161,8 +161,8 @@ def skinny_wgrad(a, x, *, dw=None, dw_layout='rd', da_colsum=None, dx_colsum=Non
     L.call('gvk_skinny_wgrad', C.byref(p), L.stream())
 
 
-def layernorm_bwd(x, gamma, mean, rstd, *, dy=None, dz=None, w=None, dres=None, dx=None, dx_lp=None, dgamma=None, dbeta=None):
-    """dx = dres + LN'(dy);  dy dense [M, dim] or rank-r (dz [M, r], w [r, dim])."""
+def layernorm_bwd(x, gamma, mean, rstd, *, dy=None, dz=None, w=None, dres=None, dx=None, dx_lp=None, dgamma=None, dbeta=None, az=None, aw=None):
+    """dx = dres + LN'(dy) + az @ aw;  dy dense [M, dim] or rank-r (dz [M, r], w [r, dim]);  az [M, ra], aw [ra, dim]."""
     M, dim = x.shape
     if dx is None:
         dx = torch.empty((M, dim), device=x.device, dtype=torch.float32)
@@ -179,6 +179,10 @@ def layernorm_bwd(x, gamma, mean, rstd, *, dy=None, dz=None, w=None, dres=None, 
         _set(p, dres=L.ptr(dres, torch.float32), ld_dres=_ld(dres))
     if dx_lp is not None:
         _set(p, dx_lp=L.ptr(dx_lp, torch.bfloat16), ld_dx_lp=_ld(dx_lp))
+    if az is not None:
+        ra = az.shape[1]
+        assert tuple(aw.shape) == (ra, dim) and aw.is_contiguous()
+        _set(p, az=L.ptr(az, torch.float32), ld_az=_ld(az), aw=L.ptr(aw, torch.float32), aw_sj=dim, aw_sc=1, ra=ra)
     L.call('gvk_layernorm_bwd', C.byref(p), L.stream())
     return dx
 

@@ -92,7 +92,8 @@ int gvk_gemm(const gvk_gemm_params* p, gvk_stream_t stream);
 
 
 /* ------------------------------------------------------------------------------------------------------------------
- * Row kernels (one warp per token row; fp32 math; HBM-bound).  dim % 64 == 0, dim <= 1024, r <= 32.
+ * Row kernels (a warp owns 1-4 token rows at a time; fp32 math; HBM-bound).  dim in {192, 384, 768, 1024}; rank r <= 96 for the
+ * projections (as far as the [r, dim] fp32 panel fits 227 KB of shared memory), r <= 32 for weight gradients and LayerNorm backward.
  * Strided weights: element (j, c) of a rank-r projection is w[j * w_sj + c * w_sc], so an nn.Linear(dim, r).weight
  * ([r, dim]) is (w_sj = dim, w_sc = 1) and an nn.Linear(r, dim).weight ([dim, r]) used transposed is (w_sj = 1, w_sc = r).
  * Dropout (replayable): element (m, c) of an [M, dim] tensor is kept iff philox(seed, offset + m * dim + c) >= drop_p and
@@ -155,8 +156,10 @@ typedef struct {
 } gvk_skinny_wgrad_params;
 int gvk_skinny_wgrad(const gvk_skinny_wgrad_params* p, gvk_stream_t stream);
 
-/* LayerNorm backward:  dx = dres + LN'(dy);  dy is either dense ([M, dim] fp32) or rank-r (dy[m, c] = sum_j dz[m, j] * w(j, c)).
- * dgamma / dbeta (optional, [dim]) accumulate with atomics.  dx may alias dres.
+/* LayerNorm backward:  dx = dres + LN'(dy) + az @ aw;  dy is either dense ([M, dim] fp32) or rank-r (dy[m, c] = sum_j dz[m, j] * w(j, c)).
+ * az @ aw (optional, az [M, ra], aw(j, c) strided like w) is added OUTSIDE the norm: the dgrad of a rank-ra down-projection that reads
+ * the same residual stream as the LayerNorm (Awakening_Prompt.proj_down next to FeedForward's norm, model/gaviko.py:155,304).
+ * dgamma / dbeta (optional, [dim]) accumulate with atomics.  dx may alias dres or dy.
  * dx_lp is an optional bf16 copy (the next dgrad GEMM's A operand). */
 typedef struct {
   const float* dy; int ld_dy;
@@ -166,6 +169,7 @@ typedef struct {
   float* dx; int ld_dx; void* dx_lp; int ld_dx_lp;
   float* dgamma; float* dbeta;
   int M, dim;
+  const float* az; int ld_az; const float* aw; int aw_sj, aw_sc; int ra;
 } gvk_layernorm_bwd_params;
 int gvk_layernorm_bwd(const gvk_layernorm_bwd_params* p, gvk_stream_t stream);
 

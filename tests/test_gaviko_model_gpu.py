@@ -122,6 +122,8 @@ def test_flat_adam_sink_and_step_match_torch():
         opt_a.step()
         opt_b.step()
         assert abs(opt_a.grad_norm.item() - norm_b.item()) <= 1e-4 * norm_b.item()
+    # three Adam updates of lr = 1e-3 each: 1e-5 absolute is 0.3 % of the distance moved (Adam's 1/sqrt(v) normalisation passes the
+    # fp32 summation-order noise of tiny-norm gradients straight into the update)
     for (n, pa), (_, pb) in zip(ma.named_parameters(), mb.named_parameters()):
         if pa.requires_grad:
-            assert torch.allclose(pa, pb, rtol=1e-4, atol=1e-6), n
+            assert torch.allclose(pa, pb, rtol=1e-4, atol=1e-5), n

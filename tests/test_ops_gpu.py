@@ -100,6 +100,14 @@ def test_rowproj_down_up_wgrad(dim, r):
     xr = x.double().requires_grad_(True)
     (F.layer_norm(xr, (dim,), g.double(), be.double(), 1e-5) @ w.double().t()).backward(dz.double())
     close(ops.layernorm_bwd(x, g, d['mean'], d['rstd'], dz=dz, w=w), xr.grad, 1e-4)
+    # dense dy + additive rank-r term outside the norm (+ residual), in place over dy
+    dy = torch.randn(M, dim, device=DEV)
+    dres = torch.randn(M, dim, device=DEV)
+    xr2 = x.double().requires_grad_(True)
+    F.layer_norm(xr2, (dim,), g.double(), be.double(), 1e-5).backward(dy.double())
+    want = xr2.grad + dres.double() + dz.double() @ w.double()
+    got = ops.layernorm_bwd(x, g, d['mean'], d['rstd'], dy=dy, dres=dres, dx=dy, az=dz, aw=w)
+    close(got, want, 1e-4)
 
 
 def test_rowproj_dropout_replay():
