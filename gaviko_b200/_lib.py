@@ -112,12 +112,25 @@ def stream():
 PROFILE = None
 
 
+PROFILE_BY_SITE = False      # key the profile by engine.py call site (name@line) instead of by entry point
+
+
+def _site(name):
+    import sys
+    f = sys._getframe(2)
+    while f is not None:
+        if f.f_code.co_filename.endswith('engine.py'):
+            return f'{name}@{f.f_lineno}'
+        f = f.f_back
+    return name
+
+
 def call(name, *args):
     if PROFILE is not None:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         check(getattr(lib(), name)(*args), name)
         e1.record()
-        PROFILE.setdefault(name, []).append((e0, e1))
+        PROFILE.setdefault(_site(name) if PROFILE_BY_SITE else name, []).append((e0, e1))
         return
     check(getattr(lib(), name)(*args), name)

@@ -297,6 +297,7 @@ int rowproj_down(const gvk_rowproj_down_params* p, cudaStream_t stream) {
   GVK_CHECK_ARG(p->r >= 1 && p->r <= 96 && p->r2 >= 0 && p->r2 <= 96, "gvk_rowproj_down: r=%d (<=96), r2=%d (<=96)", p->r, p->r2);
   GVK_CHECK_ARG(p->M > 0 && p->ldx % 2 == 0, "gvk_rowproj_down: bad shape");
   GVK_CHECK_ARG(!p->w2 || p->z2, "gvk_rowproj_down: chained projection needs z2");
+  if (p->precision == GVK_PREC_TF32) return rowproj_down_tc(p, stream);
   int rpad = 0;
   const size_t smem = rowproj_down_smem(p->r, p->w2 ? p->r2 : 0, p->dim, &rpad);
   if (smem > 227 * 1024) {
@@ -399,6 +400,7 @@ int rowproj_up(const gvk_rowproj_up_params* p, cudaStream_t stream) {
   GVK_CHECK_ARG(p && p->c && p->w && p->out, "gvk_rowproj_up: null pointer");
   GVK_CHECK_ARG(p->r >= 1 && p->r <= 96, "gvk_rowproj_up: r=%d must be in [1,96]", p->r);
   GVK_CHECK_ARG(p->M > 0 && p->ld_out % 2 == 0 && (!p->res || p->ld_res % 2 == 0), "gvk_rowproj_up: bad shape");
+  if (p->precision == GVK_PREC_TF32) return rowproj_up_tc(p, stream);
   const size_t smem = (size_t)p->r * p->dim * sizeof(float);
   if (smem > 227 * 1024) {
     set_last_error("gvk_rowproj_up: r=%d at dim=%d needs %zu B of shared memory (> 227 KB)", p->r, p->dim, smem);
@@ -513,40 +515,52 @@ __global__ void __launch_bounds__(THREADS, 2) skinny_wgrad_kernel(gvk_skinny_wgr
   }
 }
 
-__global__ void __launch_bounds__(256) skinny_wgrad_reduce_kernel(gvk_skinny_wgrad_params p, int ncta) {
+// Sum the per-CTA partials: a block owns 32 consecutive outputs, its 16 warps each sum every 16th CTA's partial (coalesced 128-byte
+// reads, independent loads in flight), then a fixed-order shared-memory tree adds the 16 subtotals: deterministic, ~500 blocks.
+constexpr int kRedSplit = 16;
+__global__ void __launch_bounds__(32 * kRedSplit) skinny_wgrad_reduce_kernel(gvk_skinny_wgrad_params p, int ncta) {
+  __shared__ float part[kRedSplit][33];
   const int rd = p.r * p.dim;
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx < rd) {
-    if (!p.dw) return;
-    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-    int k = 0;
-    for (; k + 4 <= ncta; k += 4) {
-      s0 += p.ws[(size_t)k * rd + idx];
-      s1 += p.ws[(size_t)(k + 1) * rd + idx];
-      s2 += p.ws[(size_t)(k + 2) * rd + idx];
-      s3 += p.ws[(size_t)(k + 3) * rd + idx];
+  const int lane = threadIdx.x & 31, grp = threadIdx.x >> 5;
+  const int idx = blockIdx.x * 32 + lane;
+  const int total = rd + p.dim + 32;
+  float s = 0.f;
+  if (idx < total) {
+    const float* base;
+    size_t stride;
+    if (idx < rd) { base = p.ws + idx; stride = rd; }
+    else if (idx < rd + p.dim) { base = p.ws + (size_t)ncta * rd + (idx - rd); stride = p.dim; }
+    else { base = p.ws + (size_t)ncta * (p.r + 1) * p.dim + (idx - rd - p.dim); stride = 32; }
+    float s0 = 0.f, s1 = 0.f;
+    int k = grp;
+    for (; k + kRedSplit < ncta; k += 2 * kRedSplit) {
+      s0 += base[(size_t)k * stride];
+      s1 += base[(size_t)(k + kRedSplit) * stride];
     }
-    for (; k < ncta; ++k) s0 += p.ws[(size_t)k * rd + idx];
-    const int j = idx / p.dim, c = idx - j * p.dim;
-    p.dw[(size_t)j * p.dw_sj + (size_t)c * p.dw_sc] += (s0 + s1) + (s2 + s3);
-  } else if (idx < rd + p.dim) {
-    if (!p.dx_colsum) return;
-    const int c = idx - rd;
-    const float* base = p.ws + (size_t)ncta * rd;
-    float s = 0.f;
-    for (int k = 0; k < ncta; ++k) s += base[(size_t)k * p.dim + c];
-    p.dx_colsum[c] += s;
-  } else if (idx < rd + p.dim + p.r) {
-    if (!p.da_colsum) return;
-    const int j = idx - rd - p.dim;
-    const float* base = p.ws + (size_t)ncta * (p.r + 1) * p.dim;
-    float s = 0.f;
-    for (int k = 0; k < ncta; ++k) s += base[(size_t)k * 32 + j];
-    p.da_colsum[j] += s;
+    if (k < ncta) s0 += base[(size_t)k * stride];
+    s = s0 + s1;
+  }
+  part[grp][lane] = s;
+  __syncthreads();
+  if (grp == 0 && idx < total) {
+    float tot = 0.f;
+#pragma unroll
+    for (int w = 0; w < kRedSplit; ++w) tot += part[w][lane];
+    if (idx < rd) {
+      if (p.dw) {
+        const int j = idx / p.dim, c = idx - j * p.dim;
+        p.dw[(size_t)j * p.dw_sj + (size_t)c * p.dw_sc] += tot;
+      }
+    } else if (idx < rd + p.dim) {
+      if (p.dx_colsum) p.dx_colsum[idx - rd] += tot;
+    } else {
+      const int j = idx - rd - p.dim;
+      if (p.da_colsum && j < p.r) p.da_colsum[j] += tot;
+    }
   }
 }
 
-static void skinny_wgrad_plan(int M, int* ctas, int* rows_per_cta) {
+void skinny_wgrad_plan(int M, int* ctas, int* rows_per_cta) {
   const int want = std::max(1, std::min(sm_count() * 2, (M + 31) / 32));
   int rpc = (M + want - 1) / want;
   rpc = (rpc + kWgRows - 1) / kWgRows * kWgRows;
@@ -560,6 +574,11 @@ size_t skinny_wgrad_ws_floats(int r, int dim, int M) {
   return (size_t)ctas * ((size_t)(r + 1) * dim + 32);
 }
 
+void skinny_wgrad_launch_reduce(const gvk_skinny_wgrad_params* p, int ncta, cudaStream_t stream) {
+  const int total = p->r * p->dim + p->dim + 32;
+  skinny_wgrad_reduce_kernel<<<(total + 31) / 32, 32 * kRedSplit, 0, stream>>>(*p, ncta);
+}
+
 template <int THREADS>
 static int skinny_wgrad_launch(const gvk_skinny_wgrad_params* p, cudaStream_t stream) {
   int grid, rows_per_cta;
@@ -571,8 +590,7 @@ static int skinny_wgrad_launch(const gvk_skinny_wgrad_params* p, cudaStream_t st
   else
     skinny_wgrad_kernel<32, THREADS><<<grid, THREADS, 0, stream>>>(*p, rows_per_cta);
   GVK_CHECK_LAUNCH("skinny_wgrad");
-  const int total = p->r * p->dim + p->dim + p->r;
-  skinny_wgrad_reduce_kernel<<<(total + 255) / 256, 256, 0, stream>>>(*p, grid);
+  skinny_wgrad_launch_reduce(p, grid, stream);
   GVK_CHECK_LAUNCH("skinny_wgrad_reduce");
   return GVK_OK;
 }
@@ -585,6 +603,7 @@ int skinny_wgrad(const gvk_skinny_wgrad_params* p, cudaStream_t stream) {
   GVK_CHECK_ARG(!p->ln_gamma || (p->ln_beta && p->mean && p->rstd), "gvk_skinny_wgrad: LN recompute needs beta, mean, rstd");
   GVK_CHECK_ARG(p->ws && p->ws_floats >= skinny_wgrad_ws_floats(p->r, p->dim, p->M), "gvk_skinny_wgrad: workspace of %zu floats required (gvk_skinny_wgrad_ws_floats)",
                 skinny_wgrad_ws_floats(p->r, p->dim, p->M));
+  if (p->precision == GVK_PREC_TF32 && skinny_wgrad_tc_supported(p)) return skinny_wgrad_tc(p, stream);
   // thread = 4 adjacent columns x all r latents (one 16-byte load per row); 2+ CTAs per SM keep >= 48 KB of loads in flight
   if (p->dim <= 256) return skinny_wgrad_launch<64>(p, stream);
   if (p->dim <= 384) return skinny_wgrad_launch<96>(p, stream);

@@ -1,0 +1,595 @@
+// gvk_rowops_tc.cu — tensor-core forms of the rank-r row kernels (precision = GVK_PREC_TF32 in include/gvk.h).
+//
+// The exact-fp32 forms in gvk_rowops.cu are bound by FMA issue (M * dim * r FMAs ~ 15 us on 148 SMs for M = 33k, dim = 768, r = 20,
+// the same as the HBM time of the one pass over the [M, dim] operand), so they cannot get within 2x of the memory roofline.  Here the
+// rank-r products run as mma.sync m16n8k8 (tf32 operands rounded to nearest, fp32 accumulate) on register fragments loaded straight
+// from global memory with 16-byte accesses; what is left is the HBM stream.  The k (or n) index inside a 16-wide group is permuted so
+// that one float4 per lane feeds two MMAs (both operands use the same permutation, so the product is unchanged).
+//
+// Used by the bf16 compute mode for LocalSelfAttention / Awakening_Prompt projections and their weight gradients
+// (reference model/gaviko.py:149-187, 229-244 and the autograd of those lines).
+#include <algorithm>
+
+#include "gvk_common.cuh"
+
+namespace gvk {
+
+constexpr int kTcWarps = 8;
+constexpr int kTcThreads = kTcWarps * 32;
+
+__device__ __forceinline__ uint32_t f2tf32(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ float tf32_round(float x) { return __uint_as_float(f2tf32(x)); }
+// D(16x8) += A(16x8, row) * B(8x8, col).  lane = 4 g + t:  a0 (g, t) a1 (g+8, t) a2 (g, t+4) a3 (g+8, t+4);  b0 (k=t, n=g) b1 (k=t+4, n=g);
+// d0 (g, 2t) d1 (g, 2t+1) d2 (g+8, 2t) d3 (g+8, 2t+1).
+__device__ __forceinline__ void mma_tf32(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+               : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ float2 tc_drop2(uint64_t seed, uint64_t e, float p, float inv_keep) {
+  const uint64_t ctr = e >> 2;
+  const uint4 r = philox4x32(make_uint4((uint32_t)ctr, (uint32_t)(ctr >> 32), 0u, 0u), make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+  const bool hi = (e & 2) != 0;
+  const uint32_t a = hi ? r.z : r.x, b = hi ? r.w : r.y;
+  return make_float2(u32_to_unit(a) >= p ? inv_keep : 0.f, u32_to_unit(b) >= p ? inv_keep : 0.f);
+}
+// mask of 4 consecutive elements starting at e (e % 4 == 0): one Philox call
+__device__ __forceinline__ float4 tc_drop4(uint64_t seed, uint64_t e, float p, float inv_keep) {
+  const uint64_t ctr = e >> 2;
+  const uint4 r = philox4x32(make_uint4((uint32_t)ctr, (uint32_t)(ctr >> 32), 0u, 0u), make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+  return make_float4(u32_to_unit(r.x) >= p ? inv_keep : 0.f, u32_to_unit(r.y) >= p ? inv_keep : 0.f, u32_to_unit(r.z) >= p ? inv_keep : 0.f,
+                     u32_to_unit(r.w) >= p ? inv_keep : 0.f);
+}
+
+
+// Stage a rank-r panel w(j, c) (strided, see include/gvk.h) into shared memory as dst[j * S + perm(c)] = tf32(scale[c] * w(j, c)) for
+// j < RP (rows >= r zero), reading global memory with 16-byte loads in its own linear order, all loads of a thread in flight at once.
+// PERM swaps the two low column bits (tc_up); scale may be null.
+template <int RP, int S, bool PERM>
+__device__ __forceinline__ void tc_stage_panel(float* dst, const float* __restrict__ w, int r, int dim, int w_sj, int w_sc, const float* __restrict__ scale) {
+  const int tid = threadIdx.x;
+  auto pos = [](int c) { return PERM ? ((c & ~3) | ((c & 1) << 1) | ((c >> 1) & 1)) : c; };
+  const bool vec_ok = (reinterpret_cast<uintptr_t>(w) & 15) == 0 && (scale == nullptr || (reinterpret_cast<uintptr_t>(scale) & 15) == 0);
+  if (w_sc == 1 && w_sj % 4 == 0 && dim % 4 == 0 && vec_ok) {           // [r, dim] row-major: float4 along c
+    const int nv = r * (dim / 4);
+    for (int v0 = tid; v0 < nv; v0 += kTcThreads * 4) {
+      float4 q[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int v = min(v0 + u * kTcThreads, nv - 1);
+        const int j = v / (dim / 4), c = (v - j * (dim / 4)) * 4;
+        q[u] = *reinterpret_cast<const float4*>(w + (size_t)j * w_sj + c);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int v = v0 + u * kTcThreads;
+        if (v >= nv) break;
+        const int j = v / (dim / 4), c = (v - j * (dim / 4)) * 4;
+        float4 sc4 = make_float4(1.f, 1.f, 1.f, 1.f);
+        if (scale) sc4 = *reinterpret_cast<const float4*>(scale + c);
+        if (PERM) {
+          dst[j * S + pos(c)] = tf32_round(q[u].x * sc4.x); dst[j * S + pos(c + 1)] = tf32_round(q[u].y * sc4.y);
+          dst[j * S + pos(c + 2)] = tf32_round(q[u].z * sc4.z); dst[j * S + pos(c + 3)] = tf32_round(q[u].w * sc4.w);
+        } else {
+          *reinterpret_cast<float4*>(dst + j * S + c) = make_float4(tf32_round(q[u].x * sc4.x), tf32_round(q[u].y * sc4.y), tf32_round(q[u].z * sc4.z), tf32_round(q[u].w * sc4.w));
+        }
+      }
+    }
+  } else if (w_sj == 1 && w_sc == r && r % 4 == 0 && vec_ok) {            // [dim, r] row-major: float4 along j
+    const int nv = dim * (r / 4);
+    for (int v0 = tid; v0 < nv; v0 += kTcThreads * 4) {
+      float4 q[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int v = min(v0 + u * kTcThreads, nv - 1);
+        q[u] = *reinterpret_cast<const float4*>(w + (size_t)v * 4);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int v = v0 + u * kTcThreads;
+        if (v >= nv) break;
+        const int c = v / (r / 4), j = (v - c * (r / 4)) * 4;
+        const float sc = scale ? scale[c] : 1.f;
+        const int pc = pos(c);
+        dst[j * S + pc] = tf32_round(q[u].x * sc); dst[(j + 1) * S + pc] = tf32_round(q[u].y * sc);
+        dst[(j + 2) * S + pc] = tf32_round(q[u].z * sc); dst[(j + 3) * S + pc] = tf32_round(q[u].w * sc);
+      }
+    }
+  } else {
+    for (int idx = tid; idx < r * dim; idx += kTcThreads) {
+      int j, c;
+      if (w_sc == 1) { j = idx / dim; c = idx - j * dim; } else { c = idx / r; j = idx - c * r; }
+      dst[j * S + pos(c)] = tf32_round(w[(size_t)j * w_sj + (size_t)c * w_sc] * (scale ? scale[c] : 1.f));
+    }
+  }
+  for (int idx = r * dim + tid; idx < RP * dim; idx += kTcThreads) {       // zero rows r .. RP-1 (positions are a permutation: any order)
+    const int j = idx / dim, c = idx - j * dim;
+    dst[j * S + c] = 0.f;
+  }
+}
+
+static inline int tc_grid(int tiles, int per_sm) { return std::max(1, std::min((tiles + kTcWarps - 1) / kTcWarps, sm_count() * per_sm)); }
+
+// =================================================================================================
+// down projection:  z = act(LN?(drop?(x)) W^T + b)  (+ pre-activation, + chained z2 = z W2^T)
+// A warp owns 16 rows; lane (g, t) streams rows g and g+8 as float4 at columns 16 kk + 4 t.
+// LayerNorm is folded algebraically: LN(x) . w_j = rstd (x . (gamma * w_j) - mean sum(gamma * w_j)) + beta . w_j, with mean / rstd taken
+// from the same registers in the same pass.
+// =================================================================================================
+template <int NITER, int NT>
+__global__ void __launch_bounds__(kTcThreads, NT <= 4 ? 2 : 1) tc_down_kernel(gvk_rowproj_down_params p) {
+  constexpr int dim = NITER * 64, S = dim + 16, KG = dim / 16, RP = NT * 8;
+  constexpr int S2 = 40;  // chained-projection panel row stride (floats): conflict-free float2 fragment loads for RP <= 32
+  constexpr int U = (KG % 8 == 0) ? 8 : 4;   // 16-column groups loaded per batch (2 U float4 in flight per lane); KG % U == 0
+  static_assert(KG % U == 0, "column groups must tile the row");
+  extern __shared__ __align__(16) float smem[];
+  float* sW = smem;            // [RP][S]  tf32(gamma * W), rows >= r zero
+  float* s_cs = sW + RP * S;   // [RP]     sum_c sW[j][c]
+  float* s_b = s_cs + RP;      // [RP]     b_j + beta . w_j
+  float* sW2 = s_b + RP;       // [r2pad][S2] tf32(W2), zero padded
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+  const bool has_ln = p.ln_gamma != nullptr;
+  tc_stage_panel<RP, S, false>(sW, p.w, p.r, dim, p.w_sj, p.w_sc, p.ln_gamma);
+  const int r2pad = p.w2 ? (p.r2 + 7) / 8 * 8 : 0;
+  for (int idx = tid; idx < r2pad * S2; idx += kTcThreads) {
+    const int k = idx / S2, j = idx - k * S2;
+    sW2[idx] = (k < p.r2 && j < p.r) ? tf32_round(p.w2[k * p.r + j]) : 0.f;
+  }
+  __syncthreads();
+  for (int j = warp; j < RP; j += kTcWarps) {
+    float cs = 0.f, bb = 0.f;
+    if (has_ln && j < p.r) {
+      for (int c = lane; c < dim; c += 32) {
+        cs += sW[j * S + c];
+        bb = fmaf(p.ln_beta[c], p.w[(size_t)j * p.w_sj + (size_t)c * p.w_sc], bb);
+      }
+      cs = warp_sum(cs);
+      bb = warp_sum(bb);
+    }
+    if (lane == 0) {
+      s_cs[j] = cs;
+      s_b[j] = bb + ((p.bias && j < p.r) ? p.bias[j] : 0.f);
+    }
+  }
+  __syncthreads();
+
+  const float inv_dim = 1.0f / dim;
+  const float inv_keep = p.drop_p > 0.f ? 1.0f / (1.0f - p.drop_p) : 1.f;
+  const int ntiles = (p.M + 15) / 16;
+  for (int tile = blockIdx.x * kTcWarps + warp; tile < ntiles; tile += gridDim.x * kTcWarps) {
+    const int rA = tile * 16 + g, rB = rA + 8;
+    const size_t cA = (size_t)min(rA, p.M - 1), cB = (size_t)min(rB, p.M - 1);
+    const float* xa = p.x + cA * p.ldx + 4 * t;
+    const float* xb = p.x + cB * p.ldx + 4 * t;
+    float acc[NT][4];
+#pragma unroll
+    for (int j = 0; j < NT; ++j) acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f;
+    float sA = 0.f, qA = 0.f, sB = 0.f, qB = 0.f;
+#pragma unroll 1
+    for (int k0 = 0; k0 < KG; k0 += U) {
+      float4 va[U], vb[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        va[u] = *reinterpret_cast<const float4*>(xa + 16 * (k0 + u));
+        vb[u] = *reinterpret_cast<const float4*>(xb + 16 * (k0 + u));
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int kk = k0 + u;
+        if (p.drop_p > 0.f) {
+          const float4 ma = tc_drop4(p.seed, p.offset + cA * dim + 16 * kk + 4 * t, p.drop_p, inv_keep);
+          const float4 mb = tc_drop4(p.seed, p.offset + cB * dim + 16 * kk + 4 * t, p.drop_p, inv_keep);
+          va[u].x *= ma.x; va[u].y *= ma.y; va[u].z *= ma.z; va[u].w *= ma.w;
+          vb[u].x *= mb.x; vb[u].y *= mb.y; vb[u].z *= mb.z; vb[u].w *= mb.w;
+        }
+        if (has_ln) {
+          sA += (va[u].x + va[u].y) + (va[u].z + va[u].w);
+          qA = fmaf(va[u].x, va[u].x, fmaf(va[u].y, va[u].y, fmaf(va[u].z, va[u].z, fmaf(va[u].w, va[u].w, qA))));
+          sB += (vb[u].x + vb[u].y) + (vb[u].z + vb[u].w);
+          qB = fmaf(vb[u].x, vb[u].x, fmaf(vb[u].y, vb[u].y, fmaf(vb[u].z, vb[u].z, fmaf(vb[u].w, vb[u].w, qB))));
+        }
+        const uint32_t ax = f2tf32(va[u].x), ay = f2tf32(va[u].y), az = f2tf32(va[u].z), aw = f2tf32(va[u].w);
+        const uint32_t bx = f2tf32(vb[u].x), by = f2tf32(vb[u].y), bz = f2tf32(vb[u].z), bw = f2tf32(vb[u].w);
+#pragma unroll
+        for (int j = 0; j < NT; ++j) {
+          const float4 w = *reinterpret_cast<const float4*>(sW + (8 * j + g) * S + 16 * kk + 4 * t);
+          mma_tf32(acc[j], ax, bx, ay, by, __float_as_uint(w.x), __float_as_uint(w.y));
+          mma_tf32(acc[j], az, bz, aw, bw, __float_as_uint(w.z), __float_as_uint(w.w));
+        }
+      }
+    }
+    float meanA = 0.f, rstdA = 1.f, meanB = 0.f, rstdB = 1.f;
+    if (has_ln) {
+      sA += __shfl_xor_sync(0xffffffffu, sA, 1); sA += __shfl_xor_sync(0xffffffffu, sA, 2);
+      qA += __shfl_xor_sync(0xffffffffu, qA, 1); qA += __shfl_xor_sync(0xffffffffu, qA, 2);
+      sB += __shfl_xor_sync(0xffffffffu, sB, 1); sB += __shfl_xor_sync(0xffffffffu, sB, 2);
+      qB += __shfl_xor_sync(0xffffffffu, qB, 1); qB += __shfl_xor_sync(0xffffffffu, qB, 2);
+      meanA = sA * inv_dim; meanB = sB * inv_dim;
+      rstdA = rsqrtf(fmaxf(qA * inv_dim - meanA * meanA, 0.f) + p.eps);
+      rstdB = rsqrtf(fmaxf(qB * inv_dim - meanB * meanB, 0.f) + p.eps);
+      if (t == 0) {
+        if (rA < p.M) { if (p.mean) p.mean[rA] = meanA; if (p.rstd) p.rstd[rA] = rstdA; }
+        if (rB < p.M) { if (p.mean) p.mean[rB] = meanB; if (p.rstd) p.rstd[rB] = rstdB; }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < NT; ++j) {
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int n = 8 * j + 2 * t + e;
+        float zA = acc[j][e], zB = acc[j][2 + e];
+        if (has_ln) {
+          zA = rstdA * (zA - meanA * s_cs[n]);
+          zB = rstdB * (zB - meanB * s_cs[n]);
+        }
+        zA += s_b[n];
+        zB += s_b[n];
+        if (n < p.r && p.pre) {
+          if (rA < p.M) p.pre[(size_t)rA * p.ldz + n] = zA;
+          if (rB < p.M) p.pre[(size_t)rB * p.ldz + n] = zB;
+        }
+        if (p.act == GVK_ROWACT_QUICKGELU) {
+          zA = quick_gelu(zA); zB = quick_gelu(zB);
+        } else if (p.act == GVK_ROWACT_RELU) {
+          zA = fmaxf(zA, 0.f); zB = fmaxf(zB, 0.f);
+        }
+        if (n >= p.r) zA = zB = 0.f;
+        if (n < p.r) {
+          if (rA < p.M) p.z[(size_t)rA * p.ldz + n] = zA;
+          if (rB < p.M) p.z[(size_t)rB * p.ldz + n] = zB;
+        }
+        acc[j][e] = zA;
+        acc[j][2 + e] = zB;
+      }
+    }
+    if (p.w2) {
+      // z2 = z W2^T: the C fragments of z are exactly the A fragments of the next MMA (k slot t <-> latent 8j+2t, slot t+4 <-> 8j+2t+1)
+      for (int jj = 0; jj < r2pad / 8; ++jj) {
+        float d[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int j = 0; j < NT; ++j) {
+          const float2 w = *reinterpret_cast<const float2*>(sW2 + (8 * jj + g) * S2 + 8 * j + 2 * t);
+          mma_tf32(d, f2tf32(acc[j][0]), f2tf32(acc[j][2]), f2tf32(acc[j][1]), f2tf32(acc[j][3]), __float_as_uint(w.x), __float_as_uint(w.y));
+        }
+        const int n2 = 8 * jj + 2 * t;
+        if (n2 + 1 < p.r2) {
+          if (rA < p.M) *reinterpret_cast<float2*>(p.z2 + (size_t)rA * p.ldz2 + n2) = make_float2(d[0], d[1]);
+          if (rB < p.M) *reinterpret_cast<float2*>(p.z2 + (size_t)rB * p.ldz2 + n2) = make_float2(d[2], d[3]);
+        } else if (n2 < p.r2) {
+          if (rA < p.M) p.z2[(size_t)rA * p.ldz2 + n2] = d[0];
+          if (rB < p.M) p.z2[(size_t)rB * p.ldz2 + n2] = d[2];
+        }
+      }
+    }
+  }
+}
+
+template <int NITER, int NT>
+static int tc_down_launch(const gvk_rowproj_down_params* p, cudaStream_t stream) {
+  constexpr int dim = NITER * 64;
+  const int r2pad = p->w2 ? (p->r2 + 7) / 8 * 8 : 0;
+  const size_t smem = ((size_t)NT * 8 * (dim + 16) + 2 * NT * 8 + (size_t)r2pad * 40) * sizeof(float);
+  if (smem > 227 * 1024) {
+    set_last_error("gvk_rowproj_down(tf32): r=%d at dim=%d needs %zu B of shared memory", p->r, p->dim, smem);
+    return GVK_ERR_UNSUPPORTED;
+  }
+  static size_t configured = 0;
+  if (smem > configured) {
+    int st = cuda_status(cudaFuncSetAttribute(tc_down_kernel<NITER, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "tc_down smem");
+    if (st != GVK_OK) return st;
+    configured = smem;
+  }
+  const int per_sm = (NT <= 4 && smem <= 110 * 1024) ? 2 : 1;
+  tc_down_kernel<NITER, NT><<<tc_grid((p->M + 15) / 16, per_sm), kTcThreads, smem, stream>>>(*p);
+  GVK_CHECK_LAUNCH("rowproj_down_tc");
+  return GVK_OK;
+}
+
+int rowproj_down_tc(const gvk_rowproj_down_params* p, cudaStream_t stream) {
+  GVK_CHECK_ARG(p->ldx % 4 == 0 && (reinterpret_cast<uintptr_t>(p->x) & 15) == 0, "gvk_rowproj_down(tf32): x must be 16-byte aligned with ldx %% 4 == 0");
+  GVK_CHECK_ARG(!p->w2 || (p->r <= 32 && p->ldz2 % 2 == 0 && (reinterpret_cast<uintptr_t>(p->z2) & 7) == 0), "gvk_rowproj_down(tf32): chained projection needs r <= 32 and an 8-byte aligned z2");
+#define GVK_TC_DOWN(NITER)                                              \
+  if (p->r <= 8) return tc_down_launch<NITER, 1>(p, stream);            \
+  if (p->r <= 24) return tc_down_launch<NITER, 3>(p, stream);           \
+  if (p->r <= 32) return tc_down_launch<NITER, 4>(p, stream);           \
+  return tc_down_launch<NITER, 8>(p, stream);
+  GVK_CHECK_ARG(p->r <= 64, "gvk_rowproj_down(tf32): r=%d must be <= 64", p->r);
+  switch (p->dim / 64) {
+    case 3: GVK_TC_DOWN(3)
+    case 6: GVK_TC_DOWN(6)
+    case 12: GVK_TC_DOWN(12)
+    case 16: GVK_TC_DOWN(16)
+    default:
+      set_last_error("row kernels support dim in {192, 384, 768, 1024}, got %d", p->dim);
+      return GVK_ERR_UNSUPPORTED;
+  }
+#undef GVK_TC_DOWN
+}
+
+// =================================================================================================
+// up projection:  out = res + drop(c W + b)  (+ bf16 copy).  W is staged with the two low column bits of every 16-column group swapped,
+// which makes lane (g, t) own the four consecutive output columns 16 kk + 4 t .. + 3 of rows g and g+8 (float4 stores).
+// =================================================================================================
+template <int NITER, int KS>
+__global__ void __launch_bounds__(kTcThreads, KS <= 4 ? 2 : 1) tc_up_kernel(gvk_rowproj_up_params p) {
+  constexpr int dim = NITER * 64, S = dim + 8, KG = dim / 16, RP = KS * 8;
+  constexpr int U = 4;
+  static_assert(KG % U == 0, "column groups must tile the row");
+  extern __shared__ __align__(16) float smem[];
+  float* sW = smem;           // [RP][S]
+  float* s_bias = sW + RP * S;  // [dim]
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+  tc_stage_panel<RP, S, true>(sW, p.w, p.r, dim, p.w_sj, p.w_sc, nullptr);
+  for (int c = tid; c < dim; c += kTcThreads) s_bias[c] = p.bias ? p.bias[c] : 0.f;
+  __syncthreads();
+  const float inv_keep = p.drop_p > 0.f ? 1.0f / (1.0f - p.drop_p) : 1.f;
+  const int ntiles = (p.M + 15) / 16;
+  for (int tile = blockIdx.x * kTcWarps + warp; tile < ntiles; tile += gridDim.x * kTcWarps) {
+    const int rA = tile * 16 + g, rB = rA + 8;
+    const size_t cA = (size_t)min(rA, p.M - 1), cB = (size_t)min(rB, p.M - 1);
+    uint32_t a[KS][4];
+#pragma unroll
+    for (int s = 0; s < KS; ++s) {
+      const int k0 = 8 * s + t, k1 = k0 + 4;
+      a[s][0] = f2tf32(k0 < p.r ? p.c[cA * p.ldc + k0] : 0.f);
+      a[s][1] = f2tf32(k0 < p.r ? p.c[cB * p.ldc + k0] : 0.f);
+      a[s][2] = f2tf32(k1 < p.r ? p.c[cA * p.ldc + k1] : 0.f);
+      a[s][3] = f2tf32(k1 < p.r ? p.c[cB * p.ldc + k1] : 0.f);
+    }
+#pragma unroll 1
+    for (int k0 = 0; k0 < KG; k0 += U) {
+      float4 ra[U], rb[U];
+      if (p.res) {
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          ra[u] = *reinterpret_cast<const float4*>(p.res + cA * p.ld_res + 16 * (k0 + u) + 4 * t);
+          rb[u] = *reinterpret_cast<const float4*>(p.res + cB * p.ld_res + 16 * (k0 + u) + 4 * t);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int col = 16 * (k0 + u) + 4 * t;
+        float d0[4] = {0.f, 0.f, 0.f, 0.f}, d1[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int s = 0; s < KS; ++s) {
+          const float2 b0 = *reinterpret_cast<const float2*>(sW + (8 * s + t) * S + 16 * (k0 + u) + 2 * g);
+          const float2 b1 = *reinterpret_cast<const float2*>(sW + (8 * s + t + 4) * S + 16 * (k0 + u) + 2 * g);
+          mma_tf32(d0, a[s][0], a[s][1], a[s][2], a[s][3], __float_as_uint(b0.x), __float_as_uint(b1.x));
+          mma_tf32(d1, a[s][0], a[s][1], a[s][2], a[s][3], __float_as_uint(b0.y), __float_as_uint(b1.y));
+        }
+        const float4 bias = *reinterpret_cast<const float4*>(s_bias + col);
+        float4 vA = make_float4(d0[0] + bias.x, d0[1] + bias.y, d1[0] + bias.z, d1[1] + bias.w);
+        float4 vB = make_float4(d0[2] + bias.x, d0[3] + bias.y, d1[2] + bias.z, d1[3] + bias.w);
+        if (p.drop_p > 0.f) {
+          const float4 ma = tc_drop4(p.seed, p.offset + cA * dim + col, p.drop_p, inv_keep);
+          const float4 mb = tc_drop4(p.seed, p.offset + cB * dim + col, p.drop_p, inv_keep);
+          vA.x *= ma.x; vA.y *= ma.y; vA.z *= ma.z; vA.w *= ma.w;
+          vB.x *= mb.x; vB.y *= mb.y; vB.z *= mb.z; vB.w *= mb.w;
+        }
+        if (p.res) {
+          vA.x += ra[u].x; vA.y += ra[u].y; vA.z += ra[u].z; vA.w += ra[u].w;
+          vB.x += rb[u].x; vB.y += rb[u].y; vB.z += rb[u].z; vB.w += rb[u].w;
+        }
+        if (rA < p.M) {
+          *reinterpret_cast<float4*>(p.out + (size_t)rA * p.ld_out + col) = vA;
+          if (p.out_lp) {
+            __nv_bfloat162 lo = __floats2bfloat162_rn(vA.x, vA.y), hi = __floats2bfloat162_rn(vA.z, vA.w);
+            *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.out_lp) + (size_t)rA * p.ld_out_lp + col) =
+                make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
+          }
+        }
+        if (rB < p.M) {
+          *reinterpret_cast<float4*>(p.out + (size_t)rB * p.ld_out + col) = vB;
+          if (p.out_lp) {
+            __nv_bfloat162 lo = __floats2bfloat162_rn(vB.x, vB.y), hi = __floats2bfloat162_rn(vB.z, vB.w);
+            *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.out_lp) + (size_t)rB * p.ld_out_lp + col) =
+                make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
+          }
+        }
+      }
+    }
+  }
+}
+
+template <int NITER, int KS>
+static int tc_up_launch(const gvk_rowproj_up_params* p, cudaStream_t stream) {
+  constexpr int dim = NITER * 64;
+  const size_t smem = ((size_t)KS * 8 * (dim + 8) + dim) * sizeof(float);
+  if (smem > 227 * 1024) {
+    set_last_error("gvk_rowproj_up(tf32): r=%d at dim=%d needs %zu B of shared memory", p->r, p->dim, smem);
+    return GVK_ERR_UNSUPPORTED;
+  }
+  static size_t configured = 0;
+  if (smem > configured) {
+    int st = cuda_status(cudaFuncSetAttribute(tc_up_kernel<NITER, KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "tc_up smem");
+    if (st != GVK_OK) return st;
+    configured = smem;
+  }
+  const int per_sm = (KS <= 4 && smem <= 110 * 1024) ? 2 : 1;
+  tc_up_kernel<NITER, KS><<<tc_grid((p->M + 15) / 16, per_sm), kTcThreads, smem, stream>>>(*p);
+  GVK_CHECK_LAUNCH("rowproj_up_tc");
+  return GVK_OK;
+}
+
+int rowproj_up_tc(const gvk_rowproj_up_params* p, cudaStream_t stream) {
+  GVK_CHECK_ARG(p->ld_out % 4 == 0 && (reinterpret_cast<uintptr_t>(p->out) & 15) == 0 && (!p->res || (p->ld_res % 4 == 0 && (reinterpret_cast<uintptr_t>(p->res) & 15) == 0)) &&
+                    (!p->out_lp || (p->ld_out_lp % 4 == 0 && (reinterpret_cast<uintptr_t>(p->out_lp) & 7) == 0)),
+                "gvk_rowproj_up(tf32): out / res must be 16-byte aligned with leading dimensions %% 4 == 0");
+  GVK_CHECK_ARG(p->r <= 64, "gvk_rowproj_up(tf32): r=%d must be <= 64", p->r);
+#define GVK_TC_UP(NITER)                                             \
+  if (p->r <= 8) return tc_up_launch<NITER, 1>(p, stream);           \
+  if (p->r <= 24) return tc_up_launch<NITER, 3>(p, stream);          \
+  if (p->r <= 32) return tc_up_launch<NITER, 4>(p, stream);          \
+  return tc_up_launch<NITER, 8>(p, stream);
+  switch (p->dim / 64) {
+    case 3: GVK_TC_UP(3)
+    case 6: GVK_TC_UP(6)
+    case 12: GVK_TC_UP(12)
+    case 16: GVK_TC_UP(16)
+    default:
+      set_last_error("row kernels support dim in {192, 384, 768, 1024}, got %d", p->dim);
+      return GVK_ERR_UNSUPPORTED;
+  }
+#undef GVK_TC_UP
+}
+
+// =================================================================================================
+// weight gradient:  dw(j, c) += sum_m a[m, j] f(x[m, c])  as  D[j, c] += A^T[j, m] X[m, c]  with the row index m as the MMA k dimension.
+// A warp owns 32 NG columns (NG = 3: 96, NG = 4: 128) and all 32 (padded) latents; lane (g, t) loads x[m0 + t][.. 4 g ..] and
+// x[m0 + t + 4][.. 4 g ..] as float4 (n slot g of MMA i <-> column 32 G + 4 g + i).  Per-CTA partials go to the workspace and are
+// summed by skinny_wgrad_reduce (deterministic, same layout as the fp32 kernel).
+// =================================================================================================
+template <int NG>
+__global__ void __launch_bounds__(kTcThreads, 1) tc_wgrad_kernel(gvk_skinny_wgrad_params p, int rows_per_cta, int nwarps) {
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+  if (warp >= nwarps) return;
+  const int m_begin = blockIdx.x * rows_per_cta;
+  const int m_end = min(p.M, m_begin + rows_per_cta);
+  const int cbase = warp * 32 * NG;
+  float acc[NG][4][2][4];
+  float cs[NG][4];
+#pragma unroll
+  for (int G = 0; G < NG; ++G)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      cs[G][i] = 0.f;
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt) acc[G][i][mt][0] = acc[G][i][mt][1] = acc[G][i][mt][2] = acc[G][i][mt][3] = 0.f;
+    }
+  float as[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
+  const float inv_keep = p.drop_p > 0.f ? 1.0f / (1.0f - p.drop_p) : 1.f;
+  const bool has_ln = p.ln_gamma != nullptr;
+#pragma unroll 1
+  for (int mb = m_begin; mb < m_end; mb += 16) {
+    // two 8-row k-steps per iteration: all 4 NG float4 loads (and the latents) are issued before the first MMA
+    float4 x0[2][NG], x1[2][NG];
+    float fa[2][2][4];
+    size_t c0[2], c1[2];
+    bool v0[2], v1[2];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int r0 = mb + 8 * h + t, r1 = r0 + 4;
+      v0[h] = r0 < m_end; v1[h] = r1 < m_end;
+      c0[h] = (size_t)min(r0, m_end - 1); c1[h] = (size_t)min(r1, m_end - 1);
+#pragma unroll
+      for (int G = 0; G < NG; ++G) {
+        x0[h][G] = *reinterpret_cast<const float4*>(p.x + c0[h] * p.ldx + cbase + 32 * G + 4 * g);
+        x1[h][G] = *reinterpret_cast<const float4*>(p.x + c1[h] * p.ldx + cbase + 32 * G + 4 * g);
+      }
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt) {
+        const int j0 = 16 * mt + g, j1 = j0 + 8;
+        fa[h][mt][0] = (v0[h] && j0 < p.r) ? p.a[c0[h] * p.lda + j0] : 0.f;
+        fa[h][mt][1] = (v0[h] && j1 < p.r) ? p.a[c0[h] * p.lda + j1] : 0.f;
+        fa[h][mt][2] = (v1[h] && j0 < p.r) ? p.a[c1[h] * p.lda + j0] : 0.f;
+        fa[h][mt][3] = (v1[h] && j1 < p.r) ? p.a[c1[h] * p.lda + j1] : 0.f;
+      }
+    }
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      uint32_t a[2][4];
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt) {
+        as[mt][0] += fa[h][mt][0] + fa[h][mt][2];
+        as[mt][1] += fa[h][mt][1] + fa[h][mt][3];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) a[mt][k] = f2tf32(fa[h][mt][k]);
+      }
+      float mu0 = 0.f, rs0 = 1.f, mu1 = 0.f, rs1 = 1.f;
+      if (has_ln) {
+        mu0 = p.mean[c0[h]]; rs0 = p.rstd[c0[h]]; mu1 = p.mean[c1[h]]; rs1 = p.rstd[c1[h]];
+      }
+#pragma unroll
+      for (int G = 0; G < NG; ++G) {
+        const int col = cbase + 32 * G + 4 * g;
+        float y0[4] = {x0[h][G].x, x0[h][G].y, x0[h][G].z, x0[h][G].w}, y1[4] = {x1[h][G].x, x1[h][G].y, x1[h][G].z, x1[h][G].w};
+        if (p.drop_p > 0.f) {
+          const float4 ma = tc_drop4(p.seed, p.offset + c0[h] * p.dim + col, p.drop_p, inv_keep);
+          const float4 mb4 = tc_drop4(p.seed, p.offset + c1[h] * p.dim + col, p.drop_p, inv_keep);
+          y0[0] *= ma.x; y0[1] *= ma.y; y0[2] *= ma.z; y0[3] *= ma.w;
+          y1[0] *= mb4.x; y1[1] *= mb4.y; y1[2] *= mb4.z; y1[3] *= mb4.w;
+        }
+        if (has_ln) {
+          const float4 gm = *reinterpret_cast<const float4*>(p.ln_gamma + col), bt = *reinterpret_cast<const float4*>(p.ln_beta + col);
+          const float gg[4] = {gm.x, gm.y, gm.z, gm.w}, bb[4] = {bt.x, bt.y, bt.z, bt.w};
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            y0[i] = (y0[i] - mu0) * rs0 * gg[i] + bb[i];
+            y1[i] = (y1[i] - mu1) * rs1 * gg[i] + bb[i];
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          if (!v0[h]) y0[i] = 0.f;
+          if (!v1[h]) y1[i] = 0.f;
+          cs[G][i] += y0[i] + y1[i];
+          const uint32_t b0 = f2tf32(y0[i]), b1 = f2tf32(y1[i]);
+          mma_tf32(acc[G][i][0], a[0][0], a[0][1], a[0][2], a[0][3], b0, b1);
+          mma_tf32(acc[G][i][1], a[1][0], a[1][1], a[1][2], a[1][3], b0, b1);
+        }
+      }
+    }
+  }
+  float* ws_dw = p.ws + (size_t)blockIdx.x * p.r * p.dim;
+  float* ws_dx = p.ws + (size_t)gridDim.x * p.r * p.dim + (size_t)blockIdx.x * p.dim;
+  float* ws_da = p.ws + (size_t)gridDim.x * (p.r + 1) * p.dim + (size_t)blockIdx.x * 32;
+  // acc[G][i][mt][k]: k = 0 (j, slot 2t) 1 (j, slot 2t+1) 2 (j+8, slot 2t) 3 (j+8, slot 2t+1), j = 16 mt + g, column = 32 G + 4 slot + i
+#pragma unroll
+  for (int G = 0; G < NG; ++G)
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int j = 16 * mt + g + 8 * (k >> 1);
+        const int col = cbase + 32 * G + 4 * (2 * t + (k & 1));
+        if (j < p.r) *reinterpret_cast<float4*>(ws_dw + (size_t)j * p.dim + col) = make_float4(acc[G][0][mt][k], acc[G][1][mt][k], acc[G][2][mt][k], acc[G][3][mt][k]);
+      }
+#pragma unroll
+  for (int G = 0; G < NG; ++G) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      cs[G][i] += __shfl_xor_sync(0xffffffffu, cs[G][i], 1);
+      cs[G][i] += __shfl_xor_sync(0xffffffffu, cs[G][i], 2);
+    }
+    if (t == 0) *reinterpret_cast<float4*>(ws_dx + cbase + 32 * G + 4 * g) = make_float4(cs[G][0], cs[G][1], cs[G][2], cs[G][3]);
+  }
+  if (warp == 0) {
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        float v = as[mt][h];
+        v += __shfl_xor_sync(0xffffffffu, v, 1);
+        v += __shfl_xor_sync(0xffffffffu, v, 2);
+        if (t == 0) ws_da[16 * mt + 8 * h + g] = v;
+      }
+  }
+}
+
+void skinny_wgrad_plan(int M, int* ctas, int* rows_per_cta);
+void skinny_wgrad_launch_reduce(const gvk_skinny_wgrad_params* p, int ncta, cudaStream_t stream);
+
+int skinny_wgrad_tc(const gvk_skinny_wgrad_params* p, cudaStream_t stream) {
+  int grid, rows_per_cta;
+  skinny_wgrad_plan(p->M, &grid, &rows_per_cta);
+  if (p->dim % 128 == 0 && p->dim % 96 != 0) {
+    tc_wgrad_kernel<4><<<grid, kTcThreads, 0, stream>>>(*p, rows_per_cta, p->dim / 128);
+  } else {
+    tc_wgrad_kernel<3><<<grid, kTcThreads, 0, stream>>>(*p, rows_per_cta, p->dim / 96);
+  }
+  GVK_CHECK_LAUNCH("skinny_wgrad_tc");
+  skinny_wgrad_launch_reduce(p, grid, stream);
+  GVK_CHECK_LAUNCH("skinny_wgrad_reduce");
+  return GVK_OK;
+}
+
+bool skinny_wgrad_tc_supported(const gvk_skinny_wgrad_params* p) {
+  const bool dim_ok = (p->dim % 96 == 0 && p->dim / 96 <= kTcWarps) || (p->dim % 128 == 0 && p->dim / 128 <= kTcWarps);
+  return dim_ok && p->r <= 32 && p->ldx % 4 == 0 && (reinterpret_cast<uintptr_t>(p->x) & 15) == 0;
+}
+
+}  // namespace gvk

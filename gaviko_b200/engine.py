@@ -211,6 +211,7 @@ class GavikoEngine:
         ops.fill_rows(Tr['prompt_emb'], Tr['prompt_pos'], g, T, 0, B)
         ops.fill_rows(W['cls'], W['pos_cls'], g, T, P, B)
 
+        pr = ops.PREC_TF32 if cdt != torch.float32 else ops.PREC_FP32     # arithmetic of the rank-r side products
         drop_attn = c['attn_drop'] if training_dropout else 0.0
         drop_proj = c['proj_drop'] if training_dropout else 0.0
         self._step += 1
@@ -220,11 +221,11 @@ class GavikoEngine:
             Lw, La, Fu = W['layers'][i], Tr['local'][s], Tr['fusion'][s]
             st = {}
             # ---- local branch (model/gaviko.py:229-244, residual :301)
-            d = ops.rowproj_down(loc, La['wd'], La['bd'], ln=(La['ln_w'], La['ln_b']), w2=La['wqkv'])
+            d = ops.rowproj_down(loc, La['wd'], La['bd'], ln=(La['ln_w'], La['ln_b']), w2=La['wqkv'], prec=pr)
             seed_a, seed_p = self._seed(i, 1), self._seed(i, 2)
             ctx_l, lse_l = ops.attn_simt_fwd(d['z2'], B, N, 1, r_l, q_off=0, k_off=r_l, v_off=2 * r_l, scale=dim ** -0.5,
                                              window=c['local_k'], grid=c['DHW'], drop_p=drop_attn, seed=seed_a)
-            loc_new = ops.rowproj_up(ctx_l, La['wu'], La['bu'], res=loc, drop_p=drop_proj, seed=seed_p)
+            loc_new = ops.rowproj_up(ctx_l, La['wu'], La['bu'], res=loc, drop_p=drop_proj, seed=seed_p, prec=pr)
             # ---- frozen MHSA (model/vision_transformer.py:60-72, residual gaviko.py:302)
             h1, mean1, rstd1 = ops.layernorm_fwd(g, Lw['ln1_w'], Lw['ln1_b'], out_dtype=cdt, save_stats=save)
             qkv = ops.gemm(h1, Lw['wqkv'], out_dtype=cdt)
@@ -232,11 +233,11 @@ class GavikoEngine:
             o, lse = self.mhsa_fwd(qkv, B, T, H, D, H * D)
             g_mid = ops.gemm(o, Lw['wo'], bias=Lw['bo'], res1=g)
             # ---- Awakening_Prompt (model/gaviko.py:149-187)
-            dg = ops.rowproj_down(g_mid, Fu['wd'], Fu['bd'], act=ops.ROWACT_QUICKGELU, save_pre=save)
-            dl = ops.rowproj_down(loc_new, Fu['wd'], Fu['bd'], act=ops.ROWACT_QUICKGELU, save_pre=save)
+            dg = ops.rowproj_down(g_mid, Fu['wd'], Fu['bd'], act=ops.ROWACT_QUICKGELU, save_pre=save, prec=pr)
+            dl = ops.rowproj_down(loc_new, Fu['wd'], Fu['bd'], act=ops.ROWACT_QUICKGELU, save_pre=save, prec=pr)
             comb, ll = dg['z'], dl['z']
             fsaved = ops.prompt_fusion_fwd(comb, ll, Fu['k'], B, T, N, P)      # comb: xl -> combined latent, in place
-            g_tmp = ops.rowproj_up(comb, Fu['wu'], Fu['bu'], res=g_mid)
+            g_tmp = ops.rowproj_up(comb, Fu['wu'], Fu['bu'], res=g_mid, prec=pr)
             # ---- frozen MLP (model/vision_transformer.py:26-38, residual + prompt gaviko.py:304)
             h2, mean2, rstd2 = ops.layernorm_fwd(g_mid, Lw['ln2_w'], Lw['ln2_b'], out_dtype=cdt, save_stats=save)
             hpre = torch.empty((B * T, c['mlp_dim']), device=img.device, dtype=cdt) if save else None
@@ -263,6 +264,7 @@ class GavikoEngine:
         r_l = c['local_dim']
         dev = dlogits.device
         lp = cdt != torch.float32
+        pr = ops.PREC_TF32 if lp else ops.PREC_FP32
         # Gradient accumulators: views of the optimiser's flat buffer when a sink is attached, else of one zeroed flat buffer.
         nmap = self._grad_name_map()
         sink = self.grad_sink if (self.grad_sink is not None and all(n in self.grad_sink for n in ctx['names'])) else None
@@ -302,21 +304,21 @@ class GavikoEngine:
             dH2 = ops.gemm(dA, Lw['w1_t'])
             del dA
             # ---- prompt up-projection: d(comb) = dG Wu ; dWu, dbu
-            dcomb = ops.rowproj_down(dG, Fu['wu'], transposed=True)['z']
-            ops.skinny_wgrad(st['comb'], dG, dw=gF['wu'], dw_layout='dr', dx_colsum=gF['bu'])
+            dcomb = ops.rowproj_down(dG, Fu['wu'], transposed=True, prec=pr)['z']
+            ops.skinny_wgrad(st['comb'], dG, dw=gF['wu'], dw_layout='dr', dx_colsum=gF['bu'], prec=pr)
             dll = ops.prompt_fusion_bwd(st['comb'], st['ll'], dcomb, Fu['k'], st['fsaved'], gF['k'], B, T, N, P)
             du = ops.quickgelu_bwd(dcomb, st['pre_g'], out=dcomb)
             dul = ops.quickgelu_bwd(dll, st['pre_l'], out=dll)
-            ops.skinny_wgrad(du, st['g_mid'], dw=gF['wd'], dw_layout='rd', da_colsum=gF['bd'])
-            ops.skinny_wgrad(dul, st['loc_out'], dw=gF['wd'], dw_layout='rd', da_colsum=gF['bd'])
+            ops.skinny_wgrad(du, st['g_mid'], dw=gF['wd'], dw_layout='rd', da_colsum=gF['bd'], prec=pr)
+            ops.skinny_wgrad(dul, st['loc_out'], dw=gF['wd'], dw_layout='rd', da_colsum=gF['bd'], prec=pr)
             # ---- d(g_mid) = dG + LN2'(dH2) + du Wd
             dGm_lp = torch.empty((B * T, dim), device=dev, dtype=cdt) if lp else None
             dGm = ops.layernorm_bwd(st['g_mid'], Lw['ln2_w'], st['mean2'], st['rstd2'], dy=dH2, dres=dG, dx=dH2, dx_lp=dGm_lp, az=du, aw=Fu['wd'])
             # ---- d(loc_out) += dul Wd
             if dLoc is None:
-                dLoc = ops.rowproj_up(dul, Fu['wd'], transposed=True)
+                dLoc = ops.rowproj_up(dul, Fu['wd'], transposed=True, prec=pr)
             else:
-                ops.rowproj_up(dul, Fu['wd'], transposed=True, res=dLoc, out=dLoc)
+                ops.rowproj_up(dul, Fu['wd'], transposed=True, res=dLoc, out=dLoc, prec=pr)
             # ---- MHSA dgrad
             dO = ops.gemm(dGm_lp if lp else dGm, Lw['wo_t'], out_dtype=cdt)
             dqkv = self.mhsa_bwd(st['qkv'], st['o'], st['lse'], dO, B, T, H, D, H * D)
@@ -326,13 +328,13 @@ class GavikoEngine:
             dG = ops.layernorm_bwd(st['g_in'], Lw['ln1_w'], st['mean1'], st['rstd1'], dy=dH1, dres=dGm, dx=dH1, dx_lp=dG_lp)
             del dGm
             # ---- local branch backward
-            dctx = ops.rowproj_down(dLoc, La['wu'], transposed=True, drop_p=ctx['drop_proj'], seed=st['seed_p'])['z']
-            ops.skinny_wgrad(st['ctx_l'], dLoc, dw=gL['wu'], dw_layout='dr', dx_colsum=gL['bu'], drop_p=ctx['drop_proj'], seed=st['seed_p'])
+            dctx = ops.rowproj_down(dLoc, La['wu'], transposed=True, drop_p=ctx['drop_proj'], seed=st['seed_p'], prec=pr)['z']
+            ops.skinny_wgrad(st['ctx_l'], dLoc, dw=gL['wu'], dw_layout='dr', dx_colsum=gL['bu'], drop_p=ctx['drop_proj'], seed=st['seed_p'], prec=pr)
             dqkv_l = ops.attn_simt_bwd(st['qkv_l'], st['ctx_l'], st['lse_l'], dctx, B, N, 1, r_l, q_off=0, k_off=r_l, v_off=2 * r_l, scale=dim ** -0.5,
                                        window=c['local_k'], grid=c['DHW'], drop_p=ctx['drop_attn'], seed=st['seed_a'])
             ops.small_wgrad(dqkv_l, st['z'], gL['wqkv'])
             dz = ops.small_matmul(dqkv_l, La['wqkv'])
-            ops.skinny_wgrad(dz, st['loc_in'], dw=gL['wd'], dw_layout='rd', da_colsum=gL['bd'], ln=(La['ln_w'], La['ln_b'], st['mean_l'], st['rstd_l']))
+            ops.skinny_wgrad(dz, st['loc_in'], dw=gL['wd'], dw_layout='rd', da_colsum=gL['bd'], ln=(La['ln_w'], La['ln_b'], st['mean_l'], st['rstd_l']), prec=pr)
             dLoc = ops.layernorm_bwd(st['loc_in'], La['ln_w'], st['mean_l'], st['rstd_l'], dz=dz, w=La['wd'], dres=dLoc, dx=dLoc,
                                      dgamma=gL['ln_w'], dbeta=gL['ln_b'])
             ctx['layers'][i] = None     # release this layer's activations

@@ -13,6 +13,11 @@ S = L.STRUCTS
 # bench.py sets this to a list to time every GEMM launch with CUDA events on the launch stream: entries (start, end, flops)
 GEMM_HOOK = None
 
+PREC_FP32, PREC_TF32 = 0, 1
+# debugging aid: GVK_TF32_OFF=down,up,wgrad forces the exact-fp32 kernels for those rank-r products even in bf16 mode
+import os as _os
+_TF32_OFF = set(x for x in _os.environ.get('GVK_TF32_OFF', '').split(',') if x)
+
 
 def _ld(t):
     if t.dim() != 2 or t.stride(1) != 1:
@@ -89,16 +94,18 @@ def _wstrides(w, r, dim, transposed):
 
 
 def rowproj_down(x, w, bias=None, *, transposed=False, ln=None, eps=1e-5, act=ROWACT_NONE, save_pre=False, w2=None,
-                 drop_p=0.0, seed=0, offset=0):
+                 drop_p=0.0, seed=0, offset=0, prec=PREC_FP32):
     """z = act(f(x) @ W^T + b) (W = w, or w^T when `transposed`); returns dict(z, pre, z2, mean, rstd)."""
     M, dim = x.shape
     r = w.shape[1] if transposed else w.shape[0]
+    if 'down' in _TF32_OFF:
+        prec = PREC_FP32
     sj, sc = _wstrides(w, r, dim, transposed)
     z = torch.empty((M, r), device=x.device, dtype=torch.float32)
     pre = torch.empty_like(z) if save_pre else None
     p = S['gvk_rowproj_down_params']()
     _set(p, x=L.ptr(x, torch.float32), ldx=_ld(x), M=M, dim=dim, r=r, w=L.ptr(w, torch.float32), w_sj=sj, w_sc=sc, bias=L.fptr(bias),
-         act=act, pre=pre, z=z, ldz=r, eps=eps, drop_p=drop_p, seed=seed, offset=offset)
+         act=act, pre=pre, z=z, ldz=r, eps=eps, drop_p=drop_p, seed=seed, offset=offset, precision=prec)
     mean = rstd = z2 = None
     if ln is not None:
         mean = torch.empty(M, device=x.device, dtype=torch.float32)
@@ -113,11 +120,13 @@ def rowproj_down(x, w, bias=None, *, transposed=False, ln=None, eps=1e-5, act=RO
     return dict(z=z, pre=pre, z2=z2, mean=mean, rstd=rstd)
 
 
-def rowproj_up(c, w, bias=None, *, transposed=False, res=None, out=None, out_lp=None, drop_p=0.0, seed=0, offset=0):
+def rowproj_up(c, w, bias=None, *, transposed=False, res=None, out=None, out_lp=None, drop_p=0.0, seed=0, offset=0, prec=PREC_FP32):
     """out = res + dropout(c @ W + b): W element (j, col) = w[col, j] for an nn.Linear(r, dim).weight (transposed=False here means
     `w` is [dim, r]); transposed=True takes a [r, dim] weight (dgrad of a down-projection)."""
     M, r = c.shape
     dim = w.shape[1] if transposed else w.shape[0]
+    if 'up' in _TF32_OFF:
+        prec = PREC_FP32
     if transposed:
         assert tuple(w.shape) == (r, dim) and w.is_contiguous()
         sj, sc = dim, 1
@@ -128,7 +137,7 @@ def rowproj_up(c, w, bias=None, *, transposed=False, res=None, out=None, out_lp=
         out = torch.empty((M, dim), device=c.device, dtype=torch.float32)
     p = S['gvk_rowproj_up_params']()
     _set(p, c=L.ptr(c, torch.float32), ldc=_ld(c), M=M, dim=dim, r=r, w=L.ptr(w, torch.float32), w_sj=sj, w_sc=sc, bias=L.fptr(bias),
-         out=L.ptr(out, torch.float32), ld_out=_ld(out), drop_p=drop_p, seed=seed, offset=offset)
+         out=L.ptr(out, torch.float32), ld_out=_ld(out), drop_p=drop_p, seed=seed, offset=offset, precision=prec)
     if res is not None:
         _set(p, res=L.ptr(res, torch.float32), ld_res=_ld(res))
     if out_lp is not None:
@@ -137,13 +146,15 @@ def rowproj_up(c, w, bias=None, *, transposed=False, res=None, out=None, out_lp=
     return out
 
 
-def skinny_wgrad(a, x, *, dw=None, dw_layout='rd', da_colsum=None, dx_colsum=None, ln=None, drop_p=0.0, seed=0, offset=0):
+def skinny_wgrad(a, x, *, dw=None, dw_layout='rd', da_colsum=None, dx_colsum=None, ln=None, drop_p=0.0, seed=0, offset=0, prec=PREC_FP32):
     """dw(j,c) += sum_m a[m,j] f(x[m,c]).  dw_layout 'rd': dw is [r, dim]; 'dr': dw is [dim, r].  Accumulates (zero first)."""
     M, r = a.shape
     dim = x.shape[1]
+    if 'wgrad' in _TF32_OFF:
+        prec = PREC_FP32
     p = S['gvk_skinny_wgrad_params']()
     _set(p, a=L.ptr(a, torch.float32), lda=_ld(a), r=r, x=L.ptr(x, torch.float32), ldx=_ld(x), dim=dim, M=M,
-         da_colsum=L.fptr(da_colsum), dx_colsum=L.fptr(dx_colsum), drop_p=drop_p, seed=seed, offset=offset)
+         da_colsum=L.fptr(da_colsum), dx_colsum=L.fptr(dx_colsum), drop_p=drop_p, seed=seed, offset=offset, precision=prec)
     if dw is not None:
         if dw_layout == 'rd':
             assert tuple(dw.shape) == (r, dim) and dw.is_contiguous()

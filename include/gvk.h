@@ -114,6 +114,12 @@ int gvk_layernorm_fwd(const gvk_layernorm_fwd_params* p, gvk_stream_t stream);
 
 enum { GVK_ROWACT_NONE = 0, GVK_ROWACT_QUICKGELU = 1, GVK_ROWACT_RELU = 2 };
 
+/* Arithmetic of the rank-r products in gvk_rowproj_down / gvk_rowproj_up / gvk_skinny_wgrad (`precision` field):
+ *   GVK_PREC_FP32: exact fp32 FMAs (the 1e-4 parity mode);
+ *   GVK_PREC_TF32: operands rounded to tf32 (10-bit mantissa), fp32 accumulation, on the tensor cores — used by the bf16 compute mode,
+ *                  where these kernels then run at the HBM roofline instead of the FMA-issue limit. */
+enum { GVK_PREC_FP32 = 0, GVK_PREC_TF32 = 1 };
+
 /* z[m, j] = act( sum_c f(x[m, c]) * w(j, c) + bias[j] ),  f = optional dropout mask then optional LayerNorm.
  * pre (optional) receives the pre-activation.  Optional chained projection z2[m, k] = sum_j z[m, j] * w2[k * r + j]  (r2 <= 96).
  * Replaces LocalSelfAttention.norm/proj_down/qkv (model/gaviko.py:231-232), Awakening_Prompt.proj_down (model/gaviko.py:155-156)
@@ -125,6 +131,7 @@ typedef struct {
   float* pre; float* z; int ldz;
   const float* w2; int r2; float* z2; int ldz2;
   float drop_p; uint64_t seed; uint64_t offset;
+  int precision;
 } gvk_rowproj_down_params;
 int gvk_rowproj_down(const gvk_rowproj_down_params* p, gvk_stream_t stream);
 
@@ -137,6 +144,7 @@ typedef struct {
   const float* res; int ld_res;
   float* out; int ld_out; void* out_lp; int ld_out_lp;
   float drop_p; uint64_t seed; uint64_t offset;
+  int precision;
 } gvk_rowproj_up_params;
 int gvk_rowproj_up(const gvk_rowproj_up_params* p, gvk_stream_t stream);
 
@@ -153,6 +161,7 @@ typedef struct {
   float* da_colsum; float* dx_colsum;
   float drop_p; uint64_t seed; uint64_t offset;
   float* ws; size_t ws_floats;
+  int precision;
 } gvk_skinny_wgrad_params;
 int gvk_skinny_wgrad(const gvk_skinny_wgrad_params* p, gvk_stream_t stream);
 

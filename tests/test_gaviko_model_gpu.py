@@ -60,7 +60,10 @@ def test_gaviko_bf16_matches_reference(name):
         grads = {n: p.grad for n, p in model.named_parameters() if p.requires_grad}
         tol_g = max(2e-2, float(g[f'refbf16_grad_global_{loss_name}']))
         tol_t = max(6e-2, float(g[f'refbf16_grad_worst_{loss_name}']))
-        glob, worst, wname = grad_parity(grads, g, loss_name, tol_global=tol_g, tol_tensor=tol_t, floor=1e-3)
+        # sub-floor tensors (< 1e-3 of the global norm, e.g. gl_balancer gates = sums of ctx_g - ctx_l differences) are cancellation noise in
+        # any 8-bit-mantissa run: their absolute error moves by +-2x between otherwise equivalent kernel orderings; they may each add at
+        # most 2 * tol_t * 1e-3 of the global norm, i.e. < 1 % of the global tolerance
+        glob, worst, wname = grad_parity(grads, g, loss_name, tol_global=tol_g, tol_tensor=tol_t, floor=1e-3, floor_slack=2.0)
         print(f'{name} {loss_name}: logits rel {rl:.2e} grads global {glob:.2e} worst {worst:.2e} ({wname})')
 
 

@@ -43,8 +43,12 @@ def test_layernorm_fwd_bwd(dim):
     close(dbet, br.grad, 1e-4)
 
 
-@pytest.mark.parametrize('dim,r', [(192, 20), (768, 20), (1024, 32), (768, 4)])
-def test_rowproj_down_up_wgrad(dim, r):
+@pytest.mark.parametrize('prec', [ops.PREC_FP32, ops.PREC_TF32])
+@pytest.mark.parametrize('dim,r', [(192, 20), (768, 20), (1024, 32), (768, 4), (384, 20)])
+def test_rowproj_down_up_wgrad(dim, r, prec):
+    """prec = TF32: operands rounded to 10 mantissa bits (rel 4.9e-4 each), fp32 accumulation -> tolerance 3e-3 of the output scale."""
+    tc = prec == ops.PREC_TF32
+    t5, t4 = (3e-3, 3e-3) if tc else (2e-5, 1e-4)
     torch.manual_seed(dim + r)
     M = 1033
     x = torch.randn(M, dim, device=DEV)
@@ -54,47 +58,47 @@ def test_rowproj_down_up_wgrad(dim, r):
     be = torch.randn(dim, device=DEV) * 0.1
     w2 = torch.randn(3 * r, r, device=DEV)
     # LN + down + chained projection
-    d = ops.rowproj_down(x, w, b, ln=(g, be), w2=w2)
+    d = ops.rowproj_down(x, w, b, ln=(g, be), w2=w2, prec=prec)
     zr = F.layer_norm(x.double(), (dim,), g.double(), be.double(), 1e-5) @ w.double().t() + b.double()
-    close(d['z'], zr)
-    close(d['z2'], zr @ w2.double().t(), 1e-4)
+    close(d['z'], zr, t5)
+    close(d['z2'], zr @ w2.double().t(), t4)
     # QuickGELU variant with saved pre-activation
-    d2 = ops.rowproj_down(x, w, b, act=ops.ROWACT_QUICKGELU, save_pre=True)
+    d2 = ops.rowproj_down(x, w, b, act=ops.ROWACT_QUICKGELU, save_pre=True, prec=prec)
     pre = x.double() @ w.double().t() + b.double()
-    close(d2['pre'], pre)
-    close(d2['z'], pre * torch.sigmoid(1.702 * pre))
+    close(d2['pre'], pre, t5)
+    close(d2['z'], pre * torch.sigmoid(1.702 * pre), t5)
     # transposed weight ([dim, r] used as dgrad of an up-projection)
     wu = torch.randn(dim, r, device=DEV) / r ** 0.5
-    close(ops.rowproj_down(x, wu, transposed=True)['z'], x.double() @ wu.double())
+    close(ops.rowproj_down(x, wu, transposed=True, prec=prec)['z'], x.double() @ wu.double(), t5)
     # up projection + residual (+ bf16 copy)
     c = torch.randn(M, r, device=DEV)
     bu = torch.randn(dim, device=DEV) * 0.1
     res = torch.randn(M, dim, device=DEV)
     lp = torch.empty(M, dim, device=DEV, dtype=torch.bfloat16)
-    out = ops.rowproj_up(c, wu, bu, res=res, out_lp=lp)
+    out = ops.rowproj_up(c, wu, bu, res=res, out_lp=lp, prec=prec)
     ref = c.double() @ wu.double().t() + bu.double() + res.double()
-    close(out, ref)
+    close(out, ref, t5)
     close(lp, ref, 1e-2)
-    close(ops.rowproj_up(c, w, transposed=True), c.double() @ w.double())
+    close(ops.rowproj_up(c, w, transposed=True, prec=prec), c.double() @ w.double(), t5)
     # in-place accumulate
     acc = res.clone()
-    ops.rowproj_up(c, w, transposed=True, res=acc, out=acc)
-    close(acc, res.double() + c.double() @ w.double())
+    ops.rowproj_up(c, w, transposed=True, res=acc, out=acc, prec=prec)
+    close(acc, res.double() + c.double() @ w.double(), t5)
     # skinny wgrad, both layouts, with colsums, with LN recompute
     a = torch.randn(M, r, device=DEV)
     dw = torch.zeros(r, dim, device=DEV)
     dac = torch.zeros(r, device=DEV)
     dxc = torch.zeros(dim, device=DEV)
-    ops.skinny_wgrad(a, x, dw=dw, da_colsum=dac, dx_colsum=dxc)
-    close(dw, a.double().t() @ x.double(), 1e-4)
+    ops.skinny_wgrad(a, x, dw=dw, da_colsum=dac, dx_colsum=dxc, prec=prec)
+    close(dw, a.double().t() @ x.double(), t4)
     close(dac, a.double().sum(0), 1e-4)
     close(dxc, x.double().sum(0), 1e-4)
     dwt = torch.zeros(dim, r, device=DEV)
-    ops.skinny_wgrad(a, x, dw=dwt, dw_layout='dr')
-    close(dwt, x.double().t() @ a.double(), 1e-4)
+    ops.skinny_wgrad(a, x, dw=dwt, dw_layout='dr', prec=prec)
+    close(dwt, x.double().t() @ a.double(), t4)
     dwl = torch.zeros(r, dim, device=DEV)
-    ops.skinny_wgrad(a, x, dw=dwl, ln=(g, be, d['mean'], d['rstd']))
-    close(dwl, a.double().t() @ F.layer_norm(x.double(), (dim,), g.double(), be.double(), 1e-5), 1e-4)
+    ops.skinny_wgrad(a, x, dw=dwl, ln=(g, be, d['mean'], d['rstd']), prec=prec)
+    close(dwl, a.double().t() @ F.layer_norm(x.double(), (dim,), g.double(), be.double(), 1e-5), t4)
     # LN backward in rank-r form
     dz = torch.randn(M, r, device=DEV)
     xr = x.double().requires_grad_(True)
@@ -110,8 +114,10 @@ def test_rowproj_down_up_wgrad(dim, r):
     close(got, want, 1e-4)
 
 
-def test_rowproj_dropout_replay():
-    """The forward mask of rowproj_up is replayed by rowproj_down / skinny_wgrad in backward."""
+@pytest.mark.parametrize('prec', [ops.PREC_FP32, ops.PREC_TF32])
+def test_rowproj_dropout_replay(prec):
+    """The forward mask of rowproj_up is replayed by rowproj_down / skinny_wgrad in backward (same mask in both precisions)."""
+    tol = 3e-3 if prec == ops.PREC_TF32 else 1e-4
     torch.manual_seed(3)
     M, dim, r, p = 640, 768, 20, 0.2
     c = torch.randn(M, r, device=DEV)
@@ -119,18 +125,19 @@ def test_rowproj_dropout_replay():
     ones = torch.ones(M, dim, device=DEV)
     # recover the mask: out = drop(c @ wu^T) with c @ wu^T replaced by a known tensor through r=... use bias-only path
     zero_c = torch.zeros(M, r, device=DEV)
-    mask = ops.rowproj_up(zero_c, wu, torch.ones(dim, device=DEV), drop_p=p, seed=1234)        # = mask / (1-p)
+    mask = ops.rowproj_up(zero_c, wu, torch.ones(dim, device=DEV), drop_p=p, seed=1234, prec=prec)        # = mask / (1-p)
+    assert torch.equal(mask, ops.rowproj_up(zero_c, wu, torch.ones(dim, device=DEV), drop_p=p, seed=1234))
     keep = (mask > 0).float()
     assert abs(keep.mean().item() - (1 - p)) < 0.01
     assert torch.allclose(mask, keep / (1 - p))
-    mask2 = ops.rowproj_up(zero_c, wu, torch.ones(dim, device=DEV), drop_p=p, seed=1235)
+    mask2 = ops.rowproj_up(zero_c, wu, torch.ones(dim, device=DEV), drop_p=p, seed=1235, prec=prec)
     assert (mask2 != mask).float().mean().item() > 0.2
     x = torch.randn(M, dim, device=DEV)
-    close(ops.rowproj_down(x, wu, transposed=True, drop_p=p, seed=1234)['z'], (x * mask).double() @ wu.double(), 1e-4)
+    close(ops.rowproj_down(x, wu, transposed=True, drop_p=p, seed=1234, prec=prec)['z'], (x * mask).double() @ wu.double(), tol)
     dw = torch.zeros(dim, r, device=DEV)
     dxc = torch.zeros(dim, device=DEV)
-    ops.skinny_wgrad(c, x, dw=dw, dw_layout='dr', dx_colsum=dxc, drop_p=p, seed=1234)
-    close(dw, (x * mask).double().t() @ c.double(), 1e-4)
+    ops.skinny_wgrad(c, x, dw=dw, dw_layout='dr', dx_colsum=dxc, drop_p=p, seed=1234, prec=prec)
+    close(dw, (x * mask).double().t() @ c.double(), tol)
     close(dxc, (x * mask).double().sum(0), 1e-4)
     del ones
 

@@ -11,12 +11,13 @@ from bench import GAVIKO_KW
 
 ap = argparse.ArgumentParser()
 ap.add_argument('--backbone', default='vit-b16'); ap.add_argument('--batch', type=int, default=8); ap.add_argument('--dtype', default='bf16')
-ap.add_argument('--steps', type=int, default=2)
+ap.add_argument('--steps', type=int, default=2); ap.add_argument('--by-site', action='store_true'); ap.add_argument('--eval', action='store_true')
 a = ap.parse_args()
 torch.manual_seed(0)
 with contextlib.redirect_stdout(io.StringIO()):
     model = Gaviko(**GAVIKO_KW, backbone=a.backbone, compute_dtype=a.dtype).cuda()
 model.train()
+if a.eval: model.eval()
 opt = FlatAdam(model.parameters(), lr=1e-4, model=model)
 crit = FocalLoss(gamma=1.2)
 x = torch.rand(a.batch, 1, 120, 160, 160, device='cuda'); y = torch.randint(0, 5, (a.batch,), device='cuda')
@@ -32,6 +33,7 @@ for _ in range(a.steps): step()
 e1.record(); torch.cuda.synchronize()
 total = e0.elapsed_time(e1) / a.steps
 L.PROFILE = {}
+L.PROFILE_BY_SITE = a.by_site
 for _ in range(a.steps): step()
 torch.cuda.synchronize()
 prof, L.PROFILE = L.PROFILE, None
