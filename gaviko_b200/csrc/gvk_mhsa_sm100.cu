@@ -27,6 +27,7 @@ constexpr float kLog2e = 1.4426950408889634f;
 
 struct FaDesc {  // MN-major descriptor fields (debug-tunable through GVK_FA_DESC="lbo,sbo,kadv")
   uint32_t lbo, sbo, kadv;
+  uint32_t tmem_p;   // 1: P / dS go registers -> TMEM and feed the next MMA as its A operand (no shared-memory round trip)
 };
 
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
@@ -67,6 +68,23 @@ __device__ __forceinline__ void mma_kmn(uint32_t d_tmem, const void* a, const vo
     umma_bf16(d_tmem, make_sw128_desc(a_addr + k * 32, 16, 1024), make_sw128_desc(b_addr + k * fd.kadv, fd.lbo, fd.sbo), idesc, (accumulate || k > 0) ? 1u : 0u);
 }
 
+// D[tmem, 128 x 64] (+)= A * B with A = [128 x 64] bf16 in TMEM (32 columns starting at a_tmem) and B a [64 (k) x 64 (n)] MN-major smem tile
+__device__ __forceinline__ void mma_tmn(uint32_t d_tmem, uint32_t a_tmem, const void* b, bool accumulate, const FaDesc& fd) {
+  constexpr uint32_t idesc = make_idesc_bf16(128, 64, 0, 1);
+  const uint32_t b_addr = smem_u32(b);
+#pragma unroll
+  for (int k = 0; k < 4; ++k)
+    umma_bf16_ts(d_tmem, a_tmem + 8 * k, make_sw128_desc(b_addr + k * fd.kadv, fd.lbo, fd.sbo), idesc, (accumulate || k > 0) ? 1u : 0u);
+}
+// Row of 64 probabilities -> bf16 pairs -> 32 TMEM columns of this thread's lane
+__device__ __forceinline__ void store_row_tmem(uint32_t taddr, const float (&v)[64]) {
+  uint32_t r[32];
+#pragma unroll
+  for (int i = 0; i < 32; ++i) r[i] = pack_bf16(v[2 * i], v[2 * i + 1]);
+  tmem_st_32x32(taddr, r);
+  tc_wait_st();
+}
+
 struct FaCommon {
   int B, T, H, dim;
   float scale;
@@ -82,17 +100,18 @@ struct FwdArgs {
   float* lse;
   FaDesc fd;
 };
-constexpr int kFwdSmem = kTileBytes128 /*Q*/ + 2 * 2 * kTileBytes64 /*K,V x2*/ + kTileBytes128 /*P*/ + 128 + 1024;
+constexpr int kKvStages = 3;   // K/V (or Q/dO) ring depth: a TMA tile must be requested >= 2 iterations (~1.5 us) ahead to hide the L2 -> smem latency
+constexpr int kFwdSmem = kTileBytes128 /*Q*/ + 2 * kKvStages * kTileBytes64 /*K,V ring*/ + kTileBytes128 /*P*/ + 128 + 1024;
 
 __global__ void __launch_bounds__(kFaThreads, 3)
 mhsa_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant__ CUtensorMap tma_kv, FwdArgs a) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sQ = smem;
-  uint8_t* sK = sQ + kTileBytes128;            // 2 stages
-  uint8_t* sV = sK + 2 * kTileBytes64;         // 2 stages
-  uint8_t* sP = sV + 2 * kTileBytes64;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + kTileBytes128);  // q, kv0, kv1, s, pv
+  uint8_t* sK = sQ + kTileBytes128;                    // kKvStages stages
+  uint8_t* sV = sK + kKvStages * kTileBytes64;         // kKvStages stages
+  uint8_t* sP = sV + kKvStages * kTileBytes64;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + kTileBytes128);  // q, s, pv, kv[kKvStages]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
   const int tid = threadIdx.x, warp = tid >> 5;
   const int q0 = blockIdx.x * 128;
@@ -102,7 +121,7 @@ mhsa_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_co
   if (tid == 0) {
     tma_prefetch_desc(&tma_q);
     tma_prefetch_desc(&tma_kv);
-    for (int i = 0; i < 5; ++i) mbar_init(&bars[i], 1);
+    for (int i = 0; i < 3 + kKvStages; ++i) mbar_init(&bars[i], 1);
     fence_barrier_init();
   }
   if (warp == 0) {
@@ -115,15 +134,19 @@ mhsa_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_co
   const uint32_t tmem = *tmem_slot;
   const uint32_t t_s = tmem, t_pv = tmem + 64;
   const uint32_t lane_off = static_cast<uint32_t>(warp * 32) << 16;
-  uint64_t *bar_q = &bars[0], *bar_kv = &bars[1], *bar_s = &bars[3], *bar_pv = &bars[4];
+  uint64_t *bar_q = &bars[0], *bar_s = &bars[1], *bar_pv = &bars[2], *bar_kv = &bars[3];
 
   const int nkv = (T + 63) / 64;
+  auto load_kv = [&](int j) {   // tid 0 only
+    const int st = j % kKvStages;
+    mbar_arrive_expect_tx(&bar_kv[st], 2 * kTileBytes64);
+    tma_load_3d(sK + st * kTileBytes64, &tma_kv, &bar_kv[st], dim + h * kFaD, j * 64, b);
+    tma_load_3d(sV + st * kTileBytes64, &tma_kv, &bar_kv[st], 2 * dim + h * kFaD, j * 64, b);
+  };
   if (tid == 0) {
     mbar_arrive_expect_tx(bar_q, kTileBytes128);
     tma_load_3d(sQ, &tma_q, bar_q, h * kFaD, q0, b);
-    mbar_arrive_expect_tx(&bar_kv[0], 2 * kTileBytes64);
-    tma_load_3d(sK, &tma_kv, &bar_kv[0], dim + h * kFaD, 0, b);
-    tma_load_3d(sV, &tma_kv, &bar_kv[0], 2 * dim + h * kFaD, 0, b);
+    for (int j = 0; j < kKvStages - 1 && j < nkv; ++j) load_kv(j);
   }
   const float c2 = a.c.scale * kLog2e;
   float m = -INFINITY, l = 0.f;
@@ -133,13 +156,10 @@ mhsa_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_co
   mbar_wait(bar_q, 0);
 
   for (int j = 0; j < nkv; ++j) {
-    const int buf = j & 1;
-    if (tid == 0 && j + 1 < nkv) {
-      mbar_arrive_expect_tx(&bar_kv[buf ^ 1], 2 * kTileBytes64);
-      tma_load_3d(sK + (buf ^ 1) * kTileBytes64, &tma_kv, &bar_kv[buf ^ 1], dim + h * kFaD, (j + 1) * 64, b);
-      tma_load_3d(sV + (buf ^ 1) * kTileBytes64, &tma_kv, &bar_kv[buf ^ 1], 2 * dim + h * kFaD, (j + 1) * 64, b);
-    }
-    mbar_wait(&bar_kv[buf], (j >> 1) & 1);
+    const int buf = j % kKvStages;
+    // stage (j + kKvStages - 1) % kKvStages was read by iteration j - 1, whose MMAs completed before its bar_pv wait returned
+    if (tid == 0 && j + kKvStages - 1 < nkv) load_kv(j + kKvStages - 1);
+    mbar_wait(&bar_kv[buf], (j / kKvStages) & 1);
     if (tid == 0) {
       tc_fence_after();
       mma_kk(t_s, sQ, sK + buf * kTileBytes64, false);
@@ -159,25 +179,30 @@ mhsa_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_co
     float mx = m;
 #pragma unroll
     for (int i = 0; i < 64; ++i) mx = fmaxf(mx, s[i]);
-    const float alpha = exp2f((m - mx) * c2);
+    const float alpha = fast_ex2((m - mx) * c2);
     m = mx;
     const float mc = mx * c2;
     float rs = 0.f;
 #pragma unroll
     for (int i = 0; i < 64; ++i) {
-      s[i] = exp2f(fmaf(s[i], c2, -mc));
+      s[i] = fast_ex2(fmaf(s[i], c2, -mc));
       rs += s[i];
     }
     l = fmaf(l, alpha, rs);
 #pragma unroll
     for (int i = 0; i < 64; ++i) o[i] *= alpha;
-    store_row_sw128(sP, tid, s);
-    fence_proxy_async();
+    if (a.fd.tmem_p) {
+      store_row_tmem(t_s + lane_off, s);   // P overwrites the first 32 columns of S (this thread has already read its S row)
+    } else {
+      store_row_sw128(sP, tid, s);
+      fence_proxy_async();
+    }
     tc_fence_before();
     __syncthreads();
     if (tid == 0) {
       tc_fence_after();
-      mma_kmn(t_pv, sP, sV + buf * kTileBytes64, false, a.fd);
+      if (a.fd.tmem_p) mma_tmn(t_pv, t_s, sV + buf * kTileBytes64, false, a.fd);
+      else mma_kmn(t_pv, sP, sV + buf * kTileBytes64, false, a.fd);
       umma_commit(bar_pv);
     }
     mbar_wait(bar_pv, j & 1);
@@ -222,7 +247,7 @@ struct BwdArgs {
   int ld_dqkv;
   FaDesc fd;
 };
-constexpr int kDqSmem = 2 * kTileBytes128 /*Q,dO*/ + 2 * 2 * kTileBytes64 /*K,V x2*/ + kTileBytes128 /*dS*/ + 128 + 1024;
+constexpr int kDqSmem = 2 * kTileBytes128 /*Q,dO*/ + 2 * kKvStages * kTileBytes64 /*K,V ring*/ + 128 + 1024;
 
 __global__ void __launch_bounds__(kFaThreads, 2)
 mhsa_bwd_dq_sm100_kernel(const __grid_constant__ CUtensorMap tma_q128, const __grid_constant__ CUtensorMap tma_kv64, const __grid_constant__ CUtensorMap tma_do128,
@@ -232,9 +257,8 @@ mhsa_bwd_dq_sm100_kernel(const __grid_constant__ CUtensorMap tma_q128, const __g
   uint8_t* sQ = smem;
   uint8_t* sdO = sQ + kTileBytes128;
   uint8_t* sK = sdO + kTileBytes128;
-  uint8_t* sV = sK + 2 * kTileBytes64;
-  uint8_t* sdS = sV + 2 * kTileBytes64;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sdS + kTileBytes128);  // q, kv0, kv1, s, dq
+  uint8_t* sV = sK + kKvStages * kTileBytes64;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + kKvStages * kTileBytes64);  // q, s, dq, kv[kKvStages]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
   const int tid = threadIdx.x, warp = tid >> 5;
   const int q0 = blockIdx.x * 128;
@@ -245,7 +269,7 @@ mhsa_bwd_dq_sm100_kernel(const __grid_constant__ CUtensorMap tma_q128, const __g
     tma_prefetch_desc(&tma_q128);
     tma_prefetch_desc(&tma_kv64);
     tma_prefetch_desc(&tma_do128);
-    for (int i = 0; i < 5; ++i) mbar_init(&bars[i], 1);
+    for (int i = 0; i < 3 + kKvStages; ++i) mbar_init(&bars[i], 1);
     fence_barrier_init();
   }
   if (warp == 0) {
@@ -258,15 +282,19 @@ mhsa_bwd_dq_sm100_kernel(const __grid_constant__ CUtensorMap tma_q128, const __g
   const uint32_t tmem = *tmem_slot;
   const uint32_t t_s = tmem, t_dp = tmem + 64, t_dq = tmem + 128;
   const uint32_t lane_off = static_cast<uint32_t>(warp * 32) << 16;
-  uint64_t *bar_q = &bars[0], *bar_kv = &bars[1], *bar_s = &bars[3], *bar_dq = &bars[4];
+  uint64_t *bar_q = &bars[0], *bar_s = &bars[1], *bar_dq = &bars[2], *bar_kv = &bars[3];
   const int nkv = (T + 63) / 64;
+  auto load_kv = [&](int j) {   // tid 0 only
+    const int st = j % kKvStages;
+    mbar_arrive_expect_tx(&bar_kv[st], 2 * kTileBytes64);
+    tma_load_3d(sK + st * kTileBytes64, &tma_kv64, &bar_kv[st], dim + h * kFaD, j * 64, b);
+    tma_load_3d(sV + st * kTileBytes64, &tma_kv64, &bar_kv[st], 2 * dim + h * kFaD, j * 64, b);
+  };
   if (tid == 0) {
     mbar_arrive_expect_tx(bar_q, 2 * kTileBytes128);
     tma_load_3d(sQ, &tma_q128, bar_q, h * kFaD, q0, b);
     tma_load_3d(sdO, &tma_do128, bar_q, h * kFaD, q0, b);
-    mbar_arrive_expect_tx(&bar_kv[0], 2 * kTileBytes64);
-    tma_load_3d(sK, &tma_kv64, &bar_kv[0], dim + h * kFaD, 0, b);
-    tma_load_3d(sV, &tma_kv64, &bar_kv[0], 2 * dim + h * kFaD, 0, b);
+    for (int j = 0; j < kKvStages - 1 && j < nkv; ++j) load_kv(j);
   }
   // delta_r = sum_d dO[r,d] * O[r,d]; lse in log2 units
   const int row = q0 + tid;
@@ -292,18 +320,17 @@ mhsa_bwd_dq_sm100_kernel(const __grid_constant__ CUtensorMap tma_q128, const __g
   const float c2 = a.c.scale * kLog2e;
   mbar_wait(bar_q, 0);
   for (int j = 0; j < nkv; ++j) {
-    const int buf = j & 1;
-    if (tid == 0 && j + 1 < nkv) {
-      mbar_arrive_expect_tx(&bar_kv[buf ^ 1], 2 * kTileBytes64);
-      tma_load_3d(sK + (buf ^ 1) * kTileBytes64, &tma_kv64, &bar_kv[buf ^ 1], dim + h * kFaD, (j + 1) * 64, b);
-      tma_load_3d(sV + (buf ^ 1) * kTileBytes64, &tma_kv64, &bar_kv[buf ^ 1], 2 * dim + h * kFaD, (j + 1) * 64, b);
-    }
-    mbar_wait(&bar_kv[buf], (j >> 1) & 1);
-    if (tid == 0) {
+    const int buf = j % kKvStages;
+    if (tid == 0 && j + kKvStages - 1 < nkv) load_kv(j + kKvStages - 1);   // that stage was last read by iteration j - 1 (complete)
+    mbar_wait(&bar_kv[buf], (j / kKvStages) & 1);
+    if (warp == 0) {   // warp-uniform control flow around the issue: only the tcgen05 instructions sit under elect_one
       tc_fence_after();
-      mma_kk(t_s, sQ, sK + buf * kTileBytes64, false);      // S  = Q K^T
-      mma_kk(t_dp, sdO, sV + buf * kTileBytes64, false);    // dP = dO V^T
-      umma_commit(bar_s);
+      if (elect_one()) {
+        mma_kk(t_s, sQ, sK + buf * kTileBytes64, false);      // S  = Q K^T
+        mma_kk(t_dp, sdO, sV + buf * kTileBytes64, false);    // dP = dO V^T
+        umma_commit(bar_s);
+      }
+      __syncwarp();
     }
     mbar_wait(bar_s, j & 1);
     tc_fence_after();
@@ -314,17 +341,19 @@ mhsa_bwd_dq_sm100_kernel(const __grid_constant__ CUtensorMap tma_q128, const __g
     const int valid = T - j * 64;
 #pragma unroll
     for (int i = 0; i < 64; ++i) {
-      const float p = (i < valid) ? exp2f(fmaf(s[i], c2, -lse2)) : 0.f;
+      const float p = (i < valid) ? fast_ex2(fmaf(s[i], c2, -lse2)) : 0.f;
       s[i] = p * (dp[i] - delta);  // dS
     }
-    store_row_sw128(sdS, tid, s);
-    fence_proxy_async();
+    store_row_tmem(t_s + lane_off, s);   // dS (bf16 pairs) over the first 32 columns of S: the A operand of the next MMA, read from TMEM
     tc_fence_before();
     __syncthreads();
-    if (tid == 0) {
+    if (warp == 0) {
       tc_fence_after();
-      mma_kmn(t_dq, sdS, sK + buf * kTileBytes64, j > 0, a.fd);   // dQ += dS K
-      umma_commit(bar_dq);
+      if (elect_one()) {
+        mma_tmn(t_dq, t_s, sK + buf * kTileBytes64, j > 0, a.fd);   // dQ += dS K
+        umma_commit(bar_dq);
+      }
+      __syncwarp();
     }
     mbar_wait(bar_dq, j & 1);
   }
@@ -354,7 +383,14 @@ mhsa_bwd_dq_sm100_kernel(const __grid_constant__ CUtensorMap tma_q128, const __g
 // =================================================================================================
 // backward: dK, dV
 // =================================================================================================
-constexpr int kDkvSmem = 2 * kTileBytes128 /*K,V*/ + 2 * 2 * kTileBytes64 /*Q,dO x2*/ + 2 * kTileBytes128 /*P^T, dS^T*/ + 2 * 2 * 64 * 4 /*lse2, delta x2*/ + 128 + 1024;
+constexpr int kDkvStages = 3;
+constexpr int kDkvSmem = 2 * kTileBytes128 /*K,V*/ + 2 * kDkvStages * kTileBytes64 /*Q,dO ring*/ + 2 * kDkvStages * 64 * 4 /*lse, delta ring*/ + 128 + 1024;
+__device__ __forceinline__ void cp_async4(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 __global__ void __launch_bounds__(kFaThreads, 2)
 mhsa_bwd_dkv_sm100_kernel(const __grid_constant__ CUtensorMap tma_kv128, const __grid_constant__ CUtensorMap tma_q64, const __grid_constant__ CUtensorMap tma_do64,
@@ -363,14 +399,12 @@ mhsa_bwd_dkv_sm100_kernel(const __grid_constant__ CUtensorMap tma_kv128, const _
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sK = smem;
   uint8_t* sV = sK + kTileBytes128;
-  uint8_t* sQ = sV + kTileBytes128;            // 2 stages of [64 x 64]
-  uint8_t* sdO = sQ + 2 * kTileBytes64;        // 2 stages
-  uint8_t* sP = sdO + 2 * kTileBytes64;        // [128 kv x 64 q]
-  uint8_t* sdS = sP + kTileBytes128;
-  float* s_lse2 = reinterpret_cast<float*>(sdS + kTileBytes128);  // [2][64]
-  float* s_delta = s_lse2 + 128;                                  // [2][64]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(s_delta + 128);    // kv, q0, q1, s, acc
+  uint8_t* sQ = sV + kTileBytes128;                    // kDkvStages stages of [64 x 64]
+  uint8_t* sdO = sQ + kDkvStages * kTileBytes64;        // kDkvStages stages
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sdO + kDkvStages * kTileBytes64);    // kv, s, acc, q[kDkvStages]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+  float* s_lse = reinterpret_cast<float*>(bars + 16);    // [kDkvStages][64] natural-log lse of the q tile in flight
+  float* s_delta = s_lse + kDkvStages * 64;               // [kDkvStages][64]
   const int tid = threadIdx.x, warp = tid >> 5;
   const int k0 = blockIdx.x * 128;
   const int bh = blockIdx.y, h = bh % a.c.H, b = bh / a.c.H;
@@ -380,7 +414,7 @@ mhsa_bwd_dkv_sm100_kernel(const __grid_constant__ CUtensorMap tma_kv128, const _
     tma_prefetch_desc(&tma_kv128);
     tma_prefetch_desc(&tma_q64);
     tma_prefetch_desc(&tma_do64);
-    for (int i = 0; i < 5; ++i) mbar_init(&bars[i], 1);
+    for (int i = 0; i < 3 + kDkvStages; ++i) mbar_init(&bars[i], 1);
     fence_barrier_init();
   }
   if (warp == 0) {
@@ -388,46 +422,55 @@ mhsa_bwd_dkv_sm100_kernel(const __grid_constant__ CUtensorMap tma_kv128, const _
     tmem_relinquish();
   }
   const int nq = (T + 63) / 64;
-  auto load_stats = [&](int i, int st) {  // lse (log2 units) and delta of q tile i -> stage st; called by threads 0..63
-    const int q = i * 64 + tid;
-    s_lse2[st * 64 + tid] = (q < T) ? a.lse[(size_t)bh * T + q] * kLog2e : 0.f;
-    s_delta[st * 64 + tid] = (q < T) ? a.delta[(size_t)bh * T + q] : 0.f;
+  // lse / delta of q tile i travel with cp.async two iterations ahead (a blocking global load here sat on every iteration's critical
+  // path); rows past T read a clamped (finite) element and are masked by `valid` below
+  auto load_stats = [&](int i) {   // threads 0..63; always commits a group so the wait_group accounting stays uniform
+    if (i < nq) {
+      const size_t q = (size_t)bh * T + min(i * 64 + tid, T - 1);
+      cp_async4(&s_lse[(i % kDkvStages) * 64 + tid], a.lse + q);
+      cp_async4(&s_delta[(i % kDkvStages) * 64 + tid], a.delta + q);
+    }
+    cp_async_commit();
   };
-  if (tid < 64) load_stats(0, 0);
+  if (tid < 64) {
+    for (int i = 0; i < kDkvStages - 1; ++i) load_stats(i);
+    cp_async_wait<kDkvStages - 2>();   // tile 0 landed; made visible to everyone by the __syncthreads below
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
   const uint32_t t_s = tmem, t_dp = tmem + 64, t_dv = tmem + 128, t_dk = tmem + 192;
   const uint32_t lane_off = static_cast<uint32_t>(warp * 32) << 16;
-  uint64_t *bar_kv = &bars[0], *bar_q = &bars[1], *bar_s = &bars[3], *bar_acc = &bars[4];
+  uint64_t *bar_kv = &bars[0], *bar_s = &bars[1], *bar_acc = &bars[2], *bar_q = &bars[3];
+  auto load_q = [&](int i) {   // tid 0 only
+    const int st = i % kDkvStages;
+    mbar_arrive_expect_tx(&bar_q[st], 2 * kTileBytes64);
+    tma_load_3d(sQ + st * kTileBytes64, &tma_q64, &bar_q[st], h * kFaD, i * 64, b);
+    tma_load_3d(sdO + st * kTileBytes64, &tma_do64, &bar_q[st], h * kFaD, i * 64, b);
+  };
   if (tid == 0) {
     mbar_arrive_expect_tx(bar_kv, 2 * kTileBytes128);
     tma_load_3d(sK, &tma_kv128, bar_kv, dim + h * kFaD, k0, b);
     tma_load_3d(sV, &tma_kv128, bar_kv, 2 * dim + h * kFaD, k0, b);
-    mbar_arrive_expect_tx(&bar_q[0], 2 * kTileBytes64);
-    tma_load_3d(sQ, &tma_q64, &bar_q[0], h * kFaD, 0, b);
-    tma_load_3d(sdO, &tma_do64, &bar_q[0], h * kFaD, 0, b);
+    for (int i = 0; i < kDkvStages - 1 && i < nq; ++i) load_q(i);
   }
   const float c2 = a.c.scale * kLog2e;
   const bool row_valid = (k0 + tid) < T;
   mbar_wait(bar_kv, 0);
   for (int i = 0; i < nq; ++i) {
-    const int buf = i & 1;
-    if (i + 1 < nq) {
-      if (tid == 0) {
-        mbar_arrive_expect_tx(&bar_q[buf ^ 1], 2 * kTileBytes64);
-        tma_load_3d(sQ + (buf ^ 1) * kTileBytes64, &tma_q64, &bar_q[buf ^ 1], h * kFaD, (i + 1) * 64, b);
-        tma_load_3d(sdO + (buf ^ 1) * kTileBytes64, &tma_do64, &bar_q[buf ^ 1], h * kFaD, (i + 1) * 64, b);
-      }
-      if (tid < 64) load_stats(i + 1, buf ^ 1);  // made visible by this iteration's __syncthreads
-    }
-    mbar_wait(&bar_q[buf], (i >> 1) & 1);
-    if (tid == 0) {
+    const int buf = i % kDkvStages;
+    if (tid == 0 && i + kDkvStages - 1 < nq) load_q(i + kDkvStages - 1);   // that stage was last read by iteration i - 1 (complete)
+    if (tid < 64) load_stats(i + kDkvStages - 1);
+    mbar_wait(&bar_q[buf], (i / kDkvStages) & 1);
+    if (warp == 0) {
       tc_fence_after();
-      mma_kk(t_s, sK, sQ + buf * kTileBytes64, false);      // S^T  = K Q^T
-      mma_kk(t_dp, sV, sdO + buf * kTileBytes64, false);    // dP^T = V dO^T
-      umma_commit(bar_s);
+      if (elect_one()) {
+        mma_kk(t_s, sK, sQ + buf * kTileBytes64, false);      // S^T  = K Q^T
+        mma_kk(t_dp, sV, sdO + buf * kTileBytes64, false);    // dP^T = V dO^T
+        umma_commit(bar_s);
+      }
+      __syncwarp();
     }
     mbar_wait(bar_s, i & 1);
     tc_fence_after();
@@ -436,24 +479,27 @@ mhsa_bwd_dkv_sm100_kernel(const __grid_constant__ CUtensorMap tma_kv128, const _
     tmem_ld64(t_dp + lane_off, dp);
     tc_wait_ld();
     const int valid = row_valid ? T - i * 64 : 0;
-    const float* lse2 = s_lse2 + buf * 64;
+    const float* lse = s_lse + buf * 64;
     const float* del = s_delta + buf * 64;
 #pragma unroll
     for (int q = 0; q < 64; ++q) {
-      const float p = (q < valid) ? exp2f(fmaf(s[q], c2, -lse2[q])) : 0.f;
+      const float p = (q < valid) ? fast_ex2(fmaf(s[q], c2, -kLog2e * lse[q])) : 0.f;
       s[q] = p;                       // P^T
       dp[q] = p * (dp[q] - del[q]);   // dS^T
     }
-    store_row_sw128(sP, tid, s);
-    store_row_sw128(sdS, tid, dp);
-    fence_proxy_async();
+    store_row_tmem(t_s + lane_off, s);     // P^T  over S^T  (TMEM-resident A operands of the two accumulating MMAs)
+    store_row_tmem(t_dp + lane_off, dp);   // dS^T over dP^T
+    if (tid < 64) cp_async_wait<kDkvStages - 2>();   // stats of tile i + 1 landed: visible after this barrier
     tc_fence_before();
     __syncthreads();
-    if (tid == 0) {
+    if (warp == 0) {
       tc_fence_after();
-      mma_kmn(t_dv, sP, sdO + buf * kTileBytes64, i > 0, a.fd);   // dV += P^T dO
-      mma_kmn(t_dk, sdS, sQ + buf * kTileBytes64, i > 0, a.fd);   // dK += dS^T Q
-      umma_commit(bar_acc);
+      if (elect_one()) {
+        mma_tmn(t_dv, t_s, sdO + buf * kTileBytes64, i > 0, a.fd);   // dV += P^T dO
+        mma_tmn(t_dk, t_dp, sQ + buf * kTileBytes64, i > 0, a.fd);   // dK += dS^T Q
+        umma_commit(bar_acc);
+      }
+      __syncwarp();
     }
     mbar_wait(bar_acc, i & 1);
   }
@@ -500,14 +546,15 @@ mhsa_bwd_dkv_sm100_kernel(const __grid_constant__ CUtensorMap tma_kv128, const _
 // host
 // =================================================================================================
 static FaDesc fa_desc() {
-  static FaDesc fd = {8192, 1024, 2048};
+  static FaDesc fd = {8192, 1024, 2048, 0};
   static bool init = false;
   if (!init) {
     init = true;
     if (const char* e = getenv("GVK_FA_DESC")) {
       unsigned a, b, c;
-      if (sscanf(e, "%u,%u,%u", &a, &b, &c) == 3) fd = {a, b, c};
+      if (sscanf(e, "%u,%u,%u", &a, &b, &c) == 3) fd = {a, b, c, fd.tmem_p};
     }
+    if (const char* e = getenv("GVK_FA_TMEM_P")) fd.tmem_p = atoi(e) != 0;
   }
   return fd;
 }
@@ -530,6 +577,11 @@ int mhsa_fwd(const gvk_mhsa_fwd_params* p, cudaStream_t stream) {
   int st = check_common(p->qkv, p->ld, p->B, p->T, p->H, "gvk_mhsa_fwd");
   if (st != GVK_OK) return st;
   GVK_CHECK_ARG(p->ld_out % 8 == 0, "gvk_mhsa_fwd: ld_out must be a multiple of 8");
+  {
+    static int impl = -1;   // GVK_MHSA_IMPL=1 selects the older one-tile-per-CTA kernel (kept for A/B comparison)
+    if (impl < 0) { const char* e = getenv("GVK_MHSA_IMPL"); impl = e ? atoi(e) : 2; }
+    if (impl == 2) return mhsa_ws_fwd(p, stream);
+  }
   static bool configured = false;
   if (!configured) {
     st = set_smem(mhsa_fwd_sm100_kernel, kFwdSmem, "mhsa_fwd smem");
