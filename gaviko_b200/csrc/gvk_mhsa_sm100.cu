@@ -314,8 +314,9 @@ mhsa_bwd_dq_sm100_kernel(const __grid_constant__ CUtensorMap tma_q128, const __g
         delta = fmaf(fx.y, fy.y, delta);
       }
     }
-    a.delta[(size_t)bh * T + row] = delta;
     lse2 = a.lse[(size_t)bh * T + row] * kLog2e;
+    a.delta[(size_t)bh * T + row] = delta;
+    a.delta[(size_t)a.c.B * a.c.H * T + (size_t)bh * T + row] = lse2;   // second half of the workspace: log2-domain lse for the dK/dV kernel
   }
   const float c2 = a.c.scale * kLog2e;
   mbar_wait(bar_q, 0);
@@ -339,10 +340,18 @@ mhsa_bwd_dq_sm100_kernel(const __grid_constant__ CUtensorMap tma_q128, const __g
     tmem_ld64(t_dp + lane_off, dp);
     tc_wait_ld();
     const int valid = T - j * 64;
+    if (valid >= 64) {
 #pragma unroll
-    for (int i = 0; i < 64; ++i) {
-      const float p = (i < valid) ? fast_ex2(fmaf(s[i], c2, -lse2)) : 0.f;
-      s[i] = p * (dp[i] - delta);  // dS
+      for (int i = 0; i < 64; ++i) {
+        const float p = fast_ex2(fmaf(s[i], c2, -lse2));
+        s[i] = p * (dp[i] - delta);  // dS
+      }
+    } else {                         // last K/V tile: key columns >= valid are zero-filled padding
+#pragma unroll
+      for (int i = 0; i < 64; ++i) {
+        const float p = (i < valid) ? fast_ex2(fmaf(s[i], c2, -lse2)) : 0.f;
+        s[i] = p * (dp[i] - delta);
+      }
     }
     store_row_tmem(t_s + lane_off, s);   // dS (bf16 pairs) over the first 32 columns of S: the A operand of the next MMA, read from TMEM
     tc_fence_before();
@@ -403,7 +412,7 @@ mhsa_bwd_dkv_sm100_kernel(const __grid_constant__ CUtensorMap tma_kv128, const _
   uint8_t* sdO = sQ + kDkvStages * kTileBytes64;        // kDkvStages stages
   uint64_t* bars = reinterpret_cast<uint64_t*>(sdO + kDkvStages * kTileBytes64);    // kv, s, acc, q[kDkvStages]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
-  float* s_lse = reinterpret_cast<float*>(bars + 16);    // [kDkvStages][64] natural-log lse of the q tile in flight
+  float* s_lse = reinterpret_cast<float*>(bars + 16);    // [kDkvStages][64] log2-domain lse of the q tile in flight (16-byte aligned)
   float* s_delta = s_lse + kDkvStages * 64;               // [kDkvStages][64]
   const int tid = threadIdx.x, warp = tid >> 5;
   const int k0 = blockIdx.x * 128;
@@ -427,7 +436,7 @@ mhsa_bwd_dkv_sm100_kernel(const __grid_constant__ CUtensorMap tma_kv128, const _
   auto load_stats = [&](int i) {   // threads 0..63; always commits a group so the wait_group accounting stays uniform
     if (i < nq) {
       const size_t q = (size_t)bh * T + min(i * 64 + tid, T - 1);
-      cp_async4(&s_lse[(i % kDkvStages) * 64 + tid], a.lse + q);
+      cp_async4(&s_lse[(i % kDkvStages) * 64 + tid], a.delta + (size_t)a.c.B * a.c.H * T + q);   // log2-domain lse written by the dQ kernel
       cp_async4(&s_delta[(i % kDkvStages) * 64 + tid], a.delta + q);
     }
     cp_async_commit();
@@ -479,13 +488,34 @@ mhsa_bwd_dkv_sm100_kernel(const __grid_constant__ CUtensorMap tma_kv128, const _
     tmem_ld64(t_dp + lane_off, dp);
     tc_wait_ld();
     const int valid = row_valid ? T - i * 64 : 0;
-    const float* lse = s_lse + buf * 64;
-    const float* del = s_delta + buf * 64;
+    const float4* lse4 = reinterpret_cast<const float4*>(s_lse + buf * 64);
+    const float4* del4 = reinterpret_cast<const float4*>(s_delta + buf * 64);
+    if (valid >= 64) {
 #pragma unroll
-    for (int q = 0; q < 64; ++q) {
-      const float p = (q < valid) ? fast_ex2(fmaf(s[q], c2, -kLog2e * lse[q])) : 0.f;
-      s[q] = p;                       // P^T
-      dp[q] = p * (dp[q] - del[q]);   // dS^T
+      for (int q4 = 0; q4 < 16; ++q4) {
+        const float4 l4 = lse4[q4], d4 = del4[q4];
+        const float ls[4] = {l4.x, l4.y, l4.z, l4.w}, dl[4] = {d4.x, d4.y, d4.z, d4.w};
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int q = 4 * q4 + u;
+          const float p = fast_ex2(fmaf(s[q], c2, -ls[u]));
+          s[q] = p;                        // P^T
+          dp[q] = p * (dp[q] - dl[u]);     // dS^T
+        }
+      }
+    } else {                               // last query tile / key rows past T
+#pragma unroll
+      for (int q4 = 0; q4 < 16; ++q4) {
+        const float4 l4 = lse4[q4], d4 = del4[q4];
+        const float ls[4] = {l4.x, l4.y, l4.z, l4.w}, dl[4] = {d4.x, d4.y, d4.z, d4.w};
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int q = 4 * q4 + u;
+          const float p = (q < valid) ? fast_ex2(fmaf(s[q], c2, -ls[u])) : 0.f;
+          s[q] = p;
+          dp[q] = p * (dp[q] - dl[u]);
+        }
+      }
     }
     store_row_tmem(t_s + lane_off, s);     // P^T  over S^T  (TMEM-resident A operands of the two accumulating MMAs)
     store_row_tmem(t_dp + lane_off, dp);   // dS^T over dP^T

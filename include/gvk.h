@@ -251,7 +251,7 @@ typedef struct {
   const void* out; int ld_out;
   const float* lse;
   const void* dout; int ld_dout;   /* [B*T, H*64] bf16 */
-  float* delta;                    /* workspace [B*H*T] */
+  float* delta;                    /* workspace [2*B*H*T]: rowsum(dO*O), then the log2-domain lse handed from the dQ to the dK/dV kernel */
   void* dqkv; int ld_dqkv;         /* [B*T, 3*H*64] bf16, fully overwritten */
 } gvk_mhsa_bwd_params;
 int gvk_mhsa_bwd(const gvk_mhsa_bwd_params* p, gvk_stream_t stream);
