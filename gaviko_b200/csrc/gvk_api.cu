@@ -94,7 +94,7 @@ long long gvk_struct_size(const char* name) {
 #define GVK_SZ(T) \
   if (strcmp(name, #T) == 0) return (long long)sizeof(T);
   GVK_SZ(gvk_gemm_params) GVK_SZ(gvk_layernorm_fwd_params) GVK_SZ(gvk_rowproj_down_params) GVK_SZ(gvk_rowproj_up_params)
-  GVK_SZ(gvk_skinny_wgrad_params) GVK_SZ(gvk_layernorm_bwd_params) GVK_SZ(gvk_attn_fwd_params) GVK_SZ(gvk_attn_bwd_params)
+  GVK_SZ(gvk_skinny_wgrad_params) GVK_SZ(gvk_layernorm_bwd_params) GVK_SZ(gvk_ssf_bwd_params) GVK_SZ(gvk_dropout_params) GVK_SZ(gvk_attn_fwd_params) GVK_SZ(gvk_attn_bwd_params)
   GVK_SZ(gvk_fusion_weights) GVK_SZ(gvk_fusion_grads) GVK_SZ(gvk_fusion_saved) GVK_SZ(gvk_fusion_fwd_params)
   GVK_SZ(gvk_fusion_bwd_params) GVK_SZ(gvk_head_fwd_params) GVK_SZ(gvk_head_bwd_params) GVK_SZ(gvk_mhsa_fwd_params) GVK_SZ(gvk_mhsa_bwd_params)
 #undef GVK_SZ
@@ -109,6 +109,10 @@ int gvk_rowproj_down(const gvk_rowproj_down_params* p, gvk_stream_t stream) { re
 int gvk_rowproj_up(const gvk_rowproj_up_params* p, gvk_stream_t stream) { return gvk::rowproj_up(p, S(stream)); }
 int gvk_skinny_wgrad(const gvk_skinny_wgrad_params* p, gvk_stream_t stream) { return gvk::skinny_wgrad(p, S(stream)); }
 size_t gvk_skinny_wgrad_ws_floats(int r, int dim, int M) { return gvk::skinny_wgrad_ws_floats(r, dim, M); }
+int gvk_cast_bf16_f32(const void* x, int ldx, float* y, int ldy, int M, int dim, gvk_stream_t stream) { return gvk::cast_bf16_f32(x, ldx, y, ldy, M, dim, S(stream)); }
+int gvk_relu_bwd(const float* dy, const float* z, float* y, size_t n, gvk_stream_t stream) { return gvk::relu_bwd(dy, z, y, n, S(stream)); }
+int gvk_ssf_bwd(const gvk_ssf_bwd_params* p, gvk_stream_t stream) { return gvk::ssf_bwd(p, S(stream)); }
+int gvk_dropout(const gvk_dropout_params* p, gvk_stream_t stream) { return gvk::dropout(p, S(stream)); }
 int gvk_small_wgrad(const float* a, int lda, int ra, const float* b, int ldb, int rb, int M, float* dw, gvk_stream_t stream) {
   return gvk::small_wgrad(a, lda, ra, b, ldb, rb, M, dw, S(stream));
 }

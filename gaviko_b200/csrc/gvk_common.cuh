@@ -55,6 +55,9 @@ int small_wgrad(const float* a, int lda, int ra, const float* b, int ldb, int rb
 int small_matmul(const float* a, int lda, int ra, const float* w, int rb, int M, float* out, int ldo, cudaStream_t stream);
 int colsum(const float* x, int ldx, int M, int dim, float* out, cudaStream_t stream);
 int cast_f32_bf16(const float* x, int ldx, void* y, int ldy, int M, int dim, cudaStream_t stream);
+int cast_bf16_f32(const void* x, int ldx, float* y, int ldy, int M, int dim, cudaStream_t stream);
+int ssf_bwd(const gvk_ssf_bwd_params* p, cudaStream_t stream);
+int dropout(const gvk_dropout_params* p, cudaStream_t stream);
 int attn_simt_fwd(const gvk_attn_fwd_params* p, cudaStream_t stream);
 int attn_simt_bwd(const gvk_attn_bwd_params* p, cudaStream_t stream);
 int patch_gather(const float* img, int B, int C, int D, int H, int W, int fp, int ps, void* patches, int out_dtype, cudaStream_t stream);
@@ -69,6 +72,7 @@ int mhsa_ws_fwd(const gvk_mhsa_fwd_params* p, cudaStream_t stream);
 int prompt_fusion_fwd(const gvk_fusion_fwd_params* p, cudaStream_t stream);
 int prompt_fusion_bwd(const gvk_fusion_bwd_params* p, cudaStream_t stream);
 int quickgelu_bwd(const float* dy, const float* pre, float* y, size_t n, cudaStream_t stream);
+int relu_bwd(const float* dy, const float* z, float* y, size_t n, cudaStream_t stream);
 int head_fwd(const gvk_head_fwd_params* p, cudaStream_t stream);
 int head_bwd(const gvk_head_bwd_params* p, cudaStream_t stream);
 int loss_fwd_bwd(const float* logits, const long long* target, int B, int C, int kind, float gamma, float eps, long long ignore_index, float* loss, float* dlogits,

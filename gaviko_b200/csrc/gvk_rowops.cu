@@ -631,9 +631,9 @@ __global__ void __launch_bounds__(kRowThreads, 1) layernorm_bwd_kernel(gvk_layer
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const float inv_dim = 1.0f / dim;
   constexpr int NG = PGRAD ? NITER : 1;
-  float2 dg[NG], db[NG];
+  float2 dg[NG], db[NG], dsc[NG], dsh[NG];
 #pragma unroll
-  for (int i = 0; i < NG; ++i) dg[i] = db[i] = make_float2(0.f, 0.f);
+  for (int i = 0; i < NG; ++i) dg[i] = db[i] = dsc[i] = dsh[i] = make_float2(0.f, 0.f);
   const int ngroups = (p.M + ROWS - 1) / ROWS;
   for (int grp = blockIdx.x * kRowWarps + warp; grp < ngroups; grp += gridDim.x * kRowWarps) {
     const int row0 = grp * ROWS;
@@ -680,11 +680,20 @@ __global__ void __launch_bounds__(kRowThreads, 1) layernorm_bwd_kernel(gvk_layer
           }
         }
       }
-    } else {
+    }
+    if (p.dy) {
 #pragma unroll
       for (int q = 0; q < ROWS; ++q)
 #pragma unroll
-        for (int i = 0; i < NITER; ++i) dy[q][i] = *reinterpret_cast<const float2*>(p.dy + rowc[q] * p.ld_dy + lane * 2 + 64 * i);
+        for (int i = 0; i < NITER; ++i) {
+          const float2 d = *reinterpret_cast<const float2*>(p.dy + rowc[q] * p.ld_dy + lane * 2 + 64 * i);
+          if (p.dz) {
+            dy[q][i].x += d.x;
+            dy[q][i].y += d.y;
+          } else {
+            dy[q][i] = d;
+          }
+        }
     }
     float m1[ROWS], m2[ROWS], rstd[ROWS];
 #pragma unroll
@@ -698,6 +707,19 @@ __global__ void __launch_bounds__(kRowThreads, 1) layernorm_bwd_kernel(gvk_layer
         const float2 gam = *reinterpret_cast<const float2*>(p.gamma + lane * 2 + 64 * i);
         xh[q][i] = make_float2((xh[q][i].x - mean) * rstd[q], (xh[q][i].y - mean) * rstd[q]);
         if constexpr (PGRAD) {
+          if (p.ssf_scale) {   // y = (xh * gamma + beta) * ssf_scale + ssf_shift: reduce the SSF gradients, then continue with dy * ssf_scale
+            const int c = lane * 2 + 64 * i;
+            const float2 bt = *reinterpret_cast<const float2*>(p.beta + c);
+            const float2 sc = *reinterpret_cast<const float2*>(p.ssf_scale + c);
+            if (live) {
+              dsc[i].x += dy[q][i].x * (xh[q][i].x * gam.x + bt.x);
+              dsc[i].y += dy[q][i].y * (xh[q][i].y * gam.y + bt.y);
+              dsh[i].x += dy[q][i].x;
+              dsh[i].y += dy[q][i].y;
+            }
+            dy[q][i].x *= sc.x;
+            dy[q][i].y *= sc.y;
+          }
           if (live) {
             dg[i].x += dy[q][i].x * xh[q][i].x;
             dg[i].y += dy[q][i].y * xh[q][i].y;
@@ -784,15 +806,38 @@ __global__ void __launch_bounds__(kRowThreads, 1) layernorm_bwd_kernel(gvk_layer
         if (p.dbeta) atomicAdd(p.dbeta + idx - dim, s);
       }
     }
+    if (p.ssf_scale) {   // second round through the same staging area for the SSF gradients
+      __syncthreads();
+#pragma unroll
+      for (int i = 0; i < NITER; ++i) {
+        const int c = lane * 2 + 64 * i;
+        red[warp * 2 * dim + c] = dsc[i].x;
+        red[warp * 2 * dim + c + 1] = dsc[i].y;
+        red[warp * 2 * dim + dim + c] = dsh[i].x;
+        red[warp * 2 * dim + dim + c + 1] = dsh[i].y;
+      }
+      __syncthreads();
+      for (int idx = threadIdx.x; idx < 2 * dim; idx += blockDim.x) {
+        float s = 0.f;
+#pragma unroll
+        for (int w = 0; w < kRowWarps; ++w) s += red[w * 2 * dim + idx];
+        if (idx < dim) {
+          if (p.dssf_scale) atomicAdd(p.dssf_scale + idx, s);
+        } else {
+          if (p.dssf_shift) atomicAdd(p.dssf_shift + idx - dim, s);
+        }
+      }
+    }
   }
 }
 
 int layernorm_bwd(const gvk_layernorm_bwd_params* p, cudaStream_t stream) {
   GVK_CHECK_ARG(p && p->x && p->gamma && p->mean && p->rstd && p->dx, "gvk_layernorm_bwd: null pointer");
-  GVK_CHECK_ARG((p->dy != nullptr) != (p->dz != nullptr), "gvk_layernorm_bwd: exactly one of dy / dz must be given");
+  GVK_CHECK_ARG(p->dy != nullptr || p->dz != nullptr, "gvk_layernorm_bwd: dy and / or dz must be given");
+  GVK_CHECK_ARG(!p->ssf_scale || p->beta, "gvk_layernorm_bwd: the SSF form needs beta (to rebuild the LayerNorm output)");
   GVK_CHECK_ARG(!p->dz || (p->w && p->r >= 1 && p->r <= 32), "gvk_layernorm_bwd: rank-r form needs w and 1 <= r <= 32");
   GVK_CHECK_ARG(!p->az || (p->aw && p->ra >= 1 && p->ra <= 32), "gvk_layernorm_bwd: additive rank term needs aw and 1 <= ra <= 32");
-  const bool red = p->dgamma || p->dbeta;
+  const bool red = p->dgamma || p->dbeta || p->ssf_scale;
   const size_t smem = ((p->dz ? (size_t)p->r * p->dim : 0) + (p->az ? (size_t)p->ra * p->dim : 0) + (red ? (size_t)kRowWarps * 2 * p->dim : 0)) * sizeof(float);
   if (smem > 227 * 1024) {
     set_last_error("gvk_layernorm_bwd: needs %zu B of shared memory (> 227 KB)", smem);
@@ -907,6 +952,116 @@ int colsum(const float* x, int ldx, int M, int dim, float* out, cudaStream_t str
   dim3 grid((M + rows_per_cta - 1) / rows_per_cta, (dim + 255) / 256);
   colsum_kernel<<<grid, 256, 0, stream>>>(x, ldx, M, dim, rows_per_cta, out);
   GVK_CHECK_LAUNCH("colsum");
+  return GVK_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// SSF site backward / bias gradients (include/gvk.h: gvk_ssf_bwd)
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) ssf_bwd_kernel(gvk_ssf_bwd_params p, int rows_per_cta) {
+  const int n = blockIdx.y * 256 + threadIdx.x;
+  if (n >= p.N) return;
+  const int m_begin = blockIdx.x * rows_per_cta, m_end = min(p.M, m_begin + rows_per_cta);
+  const T* dy = reinterpret_cast<const T*>(p.dy);
+  const T* y = reinterpret_cast<const T*>(p.y);
+  T* dx = reinterpret_cast<T*>(p.dx);
+  const float sc = p.scale ? p.scale[n] : 1.f, sh = p.shift ? p.shift[n] : 0.f;
+  const float inv_sc = 1.0f / sc;
+  float ds = 0.f, db = 0.f;
+  for (int m = m_begin; m < m_end; ++m) {
+    int row = m, r = 0;
+    if (p.rows_per_batch > 0) {
+      const int b = m / p.rows_per_batch;
+      r = m - b * p.rows_per_batch;
+      row = b * p.batch_rows + r;
+    }
+    const float g = ld_as_float(dy + (size_t)row * p.ld_dy + n);
+    db += g;
+    if (p.scale) {
+      float xin = ld_as_float(y + (size_t)row * p.ld_y + n);
+      if (p.sub) xin -= p.sub[(size_t)r * p.ld_sub + n];
+      xin = (xin - sh) * inv_sc;
+      ds = fmaf(g, xin, ds);
+      if (dx) st_from_float(dx + (size_t)row * p.ld_dx + n, g * sc);
+    }
+  }
+  if (p.dshift) atomicAdd(p.dshift + n, db);
+  if (p.scale && p.dscale) atomicAdd(p.dscale + n, ds);
+}
+
+int ssf_bwd(const gvk_ssf_bwd_params* p, cudaStream_t stream) {
+  GVK_CHECK_ARG(p && p->dy && p->M > 0 && p->N > 0, "gvk_ssf_bwd: bad argument");
+  GVK_CHECK_ARG(!p->scale || (p->y && p->shift), "gvk_ssf_bwd: the SSF form needs y and shift");
+  GVK_CHECK_ARG(!p->sub || p->rows_per_batch > 0, "gvk_ssf_bwd: sub needs rows_per_batch");
+  const int ctas = std::max(1, std::min(sm_count() * 8 / ((p->N + 255) / 256), (p->M + 15) / 16));
+  const int rows_per_cta = (p->M + ctas - 1) / ctas;
+  dim3 grid((p->M + rows_per_cta - 1) / rows_per_cta, (p->N + 255) / 256);
+  if (p->dtype == GVK_F32) ssf_bwd_kernel<float><<<grid, 256, 0, stream>>>(*p, rows_per_cta);
+  else ssf_bwd_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>(*p, rows_per_cta);
+  GVK_CHECK_LAUNCH("ssf_bwd");
+  return GVK_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// elementwise dropout (+ residual)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) dropout_kernel(gvk_dropout_params p) {
+  const int n4 = p.N / 4;
+  const size_t total = (size_t)p.M * n4;
+  const float inv_keep = 1.0f / (1.0f - p.drop_p);
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int m = (int)(i / n4), c = (int)(i - (size_t)m * n4) * 4;
+    float v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) v[u] = ld_dyn(p.x, (size_t)m * p.ldx + c + u, p.x_dtype);
+    const uint64_t e = p.offset + (uint64_t)m * p.N + c;
+    const float2 ma = drop_mult2(p.seed, e, p.drop_p, inv_keep), mb = drop_mult2(p.seed, e + 2, p.drop_p, inv_keep);
+    v[0] *= ma.x; v[1] *= ma.y; v[2] *= mb.x; v[3] *= mb.y;
+    if (p.res) {
+#pragma unroll
+      for (int u = 0; u < 4; ++u) v[u] += p.res[(size_t)m * p.ld_res + c + u];
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) st_dyn(p.out, (size_t)m * p.ld_out + c + u, p.out_dtype, v[u]);
+  }
+}
+
+int dropout(const gvk_dropout_params* p, cudaStream_t stream) {
+  GVK_CHECK_ARG(p && p->x && p->out && p->M > 0 && p->N > 0 && p->N % 4 == 0, "gvk_dropout: bad argument (N %% 4 == 0)");
+  GVK_CHECK_ARG(p->drop_p >= 0.f && p->drop_p < 1.f && (p->offset & 3) == 0, "gvk_dropout: drop_p in [0,1), offset %% 4 == 0");
+  const size_t total = (size_t)p->M * (p->N / 4);
+  const int grid = (int)std::min<size_t>((total + 255) / 256, (size_t)sm_count() * 16);
+  dropout_kernel<<<grid, 256, 0, stream>>>(*p);
+  GVK_CHECK_LAUNCH("dropout");
+  return GVK_OK;
+}
+
+__global__ void __launch_bounds__(256) relu_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ z, float* __restrict__ y, size_t n) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) y[i] = z[i] > 0.f ? dy[i] : 0.f;
+}
+int relu_bwd(const float* dy, const float* z, float* y, size_t n, cudaStream_t stream) {
+  GVK_CHECK_ARG(dy && z && y && n > 0, "gvk_relu_bwd: bad argument");
+  relu_bwd_kernel<<<(int)std::min<size_t>((n + 255) / 256, (size_t)sm_count() * 16), 256, 0, stream>>>(dy, z, y, n);
+  GVK_CHECK_LAUNCH("relu_bwd");
+  return GVK_OK;
+}
+
+__global__ void __launch_bounds__(256) cast_bf16_f32_kernel(const __nv_bfloat16* __restrict__ x, int ldx, float* __restrict__ y, int ldy, int M, int dim2) {
+  const size_t total = (size_t)M * dim2;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int m = (int)(i / dim2), c = (int)(i - (size_t)m * dim2) * 2;
+    const float2 v = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(x + (size_t)m * ldx + c));
+    *reinterpret_cast<float2*>(y + (size_t)m * ldy + c) = v;
+  }
+}
+
+int cast_bf16_f32(const void* x, int ldx, float* y, int ldy, int M, int dim, cudaStream_t stream) {
+  GVK_CHECK_ARG(x && y && M > 0 && dim > 0 && dim % 2 == 0 && ldx % 2 == 0 && ldy % 2 == 0, "gvk_cast_bf16_f32: bad argument");
+  const size_t total = (size_t)M * (dim / 2);
+  const int grid = (int)std::min<size_t>((total + 255) / 256, (size_t)sm_count() * 16);
+  cast_bf16_f32_kernel<<<grid, 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(x), ldx, y, ldy, M, dim / 2);
+  GVK_CHECK_LAUNCH("cast_bf16_f32");
   return GVK_OK;
 }
 

@@ -1,73 +1,65 @@
-"""Parameter containers for the frozen ViT blocks (reference ``src/model/vision_transformer.py:26-72``) and the plain
-``VisionTransformer`` drop-in (``:91-164``; methods linear / bitfit / melo build on it)."""
+"""Drop-in for the reference ``src/model/ssf.py`` (``--method ssf``): a trainable ``x * scale + shift`` after the patch embedding,
+every LayerNorm and every Linear (``ssf.py:24-31,64-116,133-138,236``)."""
 import logging
 
 import torch
 from torch import nn
 
 from ..utils.load_pretrained import load_pretrain, mapping_vit
+from .vision_transformer import _Container, _vit_cfg, pair
 
 
-def pair(t):
-    return t if isinstance(t, tuple) else (t, t)
-
-
-class _Container(nn.Module):
-    def forward(self, *a, **k):  # pragma: no cover
-        raise RuntimeError('gaviko_b200 sub-modules are parameter containers; call the top-level model')
+def init_ssf_scale_shift(dim):
+    scale = nn.Parameter(torch.ones(dim))
+    shift = nn.Parameter(torch.zeros(dim))
+    nn.init.normal_(scale, mean=1, std=.02)
+    nn.init.normal_(shift, std=.02)
+    return scale, shift
 
 
 class FeedForward(_Container):
-    """net = [LayerNorm, Linear(dim, hidden), GELU, Dropout, Linear(hidden, dim), Dropout] -> keys net.0 / net.1 / net.4."""
-
     def __init__(self, dim, hidden_dim, dropout=0.):
         super().__init__()
+        self.ssf_scale_0, self.ssf_shift_0 = init_ssf_scale_shift(dim)
+        self.ssf_scale_1, self.ssf_shift_1 = init_ssf_scale_shift(hidden_dim)
+        self.ssf_scale_2, self.ssf_shift_2 = init_ssf_scale_shift(dim)
         self.net = nn.Sequential(nn.LayerNorm(dim), nn.Linear(dim, hidden_dim), nn.GELU(), nn.Dropout(dropout),
                                  nn.Linear(hidden_dim, dim), nn.Dropout(dropout))
 
 
 class Attention(_Container):
-    """norm, to_qkv (no bias), to_out = [Linear, Dropout]; softmax scale dim_head**-0.5."""
-
     def __init__(self, dim, heads=8, dim_head=64, dropout=0.):
         super().__init__()
         inner_dim = dim_head * heads
+        project_out = not (heads == 1 and dim_head == dim)
         self.heads = heads
-        self.dim_head = dim_head
         self.scale = dim_head ** -0.5
         self.norm = nn.LayerNorm(dim)
         self.attend = nn.Softmax(dim=-1)
         self.dropout = nn.Dropout(dropout)
         self.to_qkv = nn.Linear(dim, inner_dim * 3, bias=False)
-        project_out = not (heads == 1 and dim_head == dim)
         self.to_out = nn.Sequential(nn.Linear(inner_dim, dim), nn.Dropout(dropout)) if project_out else nn.Identity()
+        self.ssf_scale_0, self.ssf_shift_0 = init_ssf_scale_shift(dim)
+        self.ssf_scale_1, self.ssf_shift_1 = init_ssf_scale_shift(inner_dim * 3)
+        self.ssf_scale_2, self.ssf_shift_2 = init_ssf_scale_shift(dim)
 
 
 class Transformer(_Container):
-    """layers.{i}.0 = Attention, layers.{i}.1 = FeedForward, final norm (reference model/vision_transformer.py:74-89)."""
-
     def __init__(self, dim, depth, heads, dim_head, mlp_dim, dropout=0.):
         super().__init__()
+        self.ls1 = nn.Identity()
+        self.ls2 = nn.Identity()
         self.norm = nn.LayerNorm(dim)
+        self.ssf_scale_1, self.ssf_shift_1 = init_ssf_scale_shift(dim)
         self.layers = nn.ModuleList([])
         for _ in range(depth):
             self.layers.append(nn.ModuleList([Attention(dim, heads=heads, dim_head=dim_head, dropout=dropout),
                                               FeedForward(dim, mlp_dim, dropout=dropout)]))
 
 
-def _vit_cfg(depth, heads, dim, mlp_dim, dim_head, channels, frames, frame_patch_size, image_height, image_width, patch_height, patch_width, num_patches):
-    assert patch_height == patch_width, 'square in-plane patches only'
-    return dict(depth=depth, heads=heads, dim=dim, mlp_dim=mlp_dim, dim_head=dim_head, channels=channels,
-                grid=(frames // frame_patch_size, image_height // patch_height, image_width // patch_width), fp=frame_patch_size, ps=patch_height,
-                num_patches=num_patches)
-
-
-class VisionTransformer(nn.Module):
-    """Drop-in for reference model/vision_transformer.py:91-164 (``--method linear | bitfit | fft``; wrapped by MeLO and VPT).
-    Same constructor, parameter names and forward signature; forward / backward run the sm_100a kernels through ``VitEngine``."""
-
+class ScalingShiftingFeatures(nn.Module):
     def __init__(self, *, image_size, image_patch_size, frames, frame_patch_size, num_classes, pool='cls', channels=3, dim_head=64,
-                 dropout=0., emb_dropout=0., backbone=None, compute_dtype=None, **kwargs):
+                 dropout=0., emb_dropout=0., backbone=None, freeze_vit=False, compute_dtype=None, **kwargs):
         super().__init__()
         depth, heads, dim, mlp_dim = mapping_vit(backbone)
         image_height, image_width = pair(image_size)
@@ -80,10 +72,10 @@ class VisionTransformer(nn.Module):
         self.image_patch_size = image_patch_size
         self.frames = frames
         self.frame_patch_size = frame_patch_size
-        self.depth = depth
         assert pool in {'cls', 'mean'}, 'pool type must be either cls (cls token) or mean (mean pooling)'
         self.conv_proj = nn.Sequential(nn.Conv3d(channels, dim, kernel_size=(frame_patch_size, image_patch_size, image_patch_size),
                                                  stride=(frame_patch_size, image_patch_size, image_patch_size)))
+        self.ssf_scale_1, self.ssf_shift_1 = init_ssf_scale_shift(dim)
         self.pos_embedding = nn.Parameter(torch.randn(1, num_patches + 1, dim))
         self.cls_token = nn.Parameter(torch.randn(1, 1, dim))
         self.dropout = nn.Dropout(emb_dropout)
@@ -91,15 +83,41 @@ class VisionTransformer(nn.Module):
         self.pool = pool
         self.to_latent = nn.Identity()
         self.mlp_head = nn.Linear(dim, num_classes)
+        self.freeze_vit = freeze_vit
+        self.init_head_weights()
         if backbone is not None:
             logging.info(f'Loading pretrained {backbone}...')
             new_dict = load_pretrain(backbone, self.num_patches, self.conv_proj[0].weight.shape[2], './pretrained')
             self.load_state_dict(new_dict, strict=False)
             logging.info(f'Load pretrained {backbone} sucessfully!')
+        if self.freeze_vit:
+            for k, p in self.named_parameters():
+                if "transformer" in k or "cls_token" in k or "conv_proj" in k or "pos_embedding" in k:
+                    p.requires_grad = False
+                if "scale" in k or "shift" in k:
+                    p.requires_grad = True
         self._cfg = _vit_cfg(depth, heads, dim, mlp_dim, dim_head, channels, frames, frame_patch_size, image_height, image_width,
                              patch_height, patch_width, num_patches)
         from ..vit_engine import VitEngine
-        self._engine = VitEngine(self, 'vit', compute_dtype)
+        self._engine = VitEngine(self, 'ssf', compute_dtype)
+
+    def init_head_weights(self):
+        nn.init.xavier_uniform_(self.mlp_head.weight)
+        nn.init.zeros_(self.mlp_head.bias)
+        logging.info("Initialize head weight successfully!")
+
+    def train(self, mode=True):
+        """Reference quirk preserved (ssf.py:216-228)."""
+        if mode:
+            super().train(mode)
+            if self.freeze_vit:
+                self.transformer.eval()
+                self.conv_proj.eval()
+                self.dropout.eval()
+                self.mlp_head.train()
+        else:
+            for module in self.children():
+                module.eval()
 
     def set_compute_dtype(self, compute_dtype):
         self._engine.set_compute_dtype(compute_dtype)

@@ -146,7 +146,7 @@ def rowproj_up(c, w, bias=None, *, transposed=False, res=None, out=None, out_lp=
     return out
 
 
-def skinny_wgrad(a, x, *, dw=None, dw_layout='rd', da_colsum=None, dx_colsum=None, ln=None, drop_p=0.0, seed=0, offset=0, prec=PREC_FP32):
+def skinny_wgrad(a, x, *, dw=None, dw_layout='rd', da_colsum=None, dx_colsum=None, ln=None, drop_p=0.0, seed=0, offset=0, prec=PREC_FP32, dw_strides=None):
     """dw(j,c) += sum_m a[m,j] f(x[m,c]).  dw_layout 'rd': dw is [r, dim]; 'dr': dw is [dim, r].  Accumulates (zero first)."""
     M, r = a.shape
     dim = x.shape[1]
@@ -155,7 +155,9 @@ def skinny_wgrad(a, x, *, dw=None, dw_layout='rd', da_colsum=None, dx_colsum=Non
     p = S['gvk_skinny_wgrad_params']()
     _set(p, a=L.ptr(a, torch.float32), lda=_ld(a), r=r, x=L.ptr(x, torch.float32), ldx=_ld(x), dim=dim, M=M,
          da_colsum=L.fptr(da_colsum), dx_colsum=L.fptr(dx_colsum), drop_p=drop_p, seed=seed, offset=offset, precision=prec)
-    if dw is not None:
+    if dw is not None and dw_strides is not None:      # explicit (sj, sc) element strides: a column / row slice of a larger gradient
+        _set(p, dw=L.ptr(dw, torch.float32), dw_sj=dw_strides[0], dw_sc=dw_strides[1])
+    elif dw is not None:
         if dw_layout == 'rd':
             assert tuple(dw.shape) == (r, dim) and dw.is_contiguous()
             _set(p, dw=L.ptr(dw, torch.float32), dw_sj=dim, dw_sc=1)
@@ -172,7 +174,8 @@ def skinny_wgrad(a, x, *, dw=None, dw_layout='rd', da_colsum=None, dx_colsum=Non
     L.call('gvk_skinny_wgrad', C.byref(p), L.stream())
 
 
-def layernorm_bwd(x, gamma, mean, rstd, *, dy=None, dz=None, w=None, dres=None, dx=None, dx_lp=None, dgamma=None, dbeta=None, az=None, aw=None):
+def layernorm_bwd(x, gamma, mean, rstd, *, dy=None, dz=None, w=None, dres=None, dx=None, dx_lp=None, dgamma=None, dbeta=None, az=None, aw=None,
+                  beta=None, ssf_scale=None, dssf_scale=None, dssf_shift=None):
     """dx = dres + LN'(dy) + az @ aw;  dy dense [M, dim] or rank-r (dz [M, r], w [r, dim]);  az [M, ra], aw [ra, dim]."""
     M, dim = x.shape
     if dx is None:
@@ -190,6 +193,8 @@ def layernorm_bwd(x, gamma, mean, rstd, *, dy=None, dz=None, w=None, dres=None, 
         _set(p, dres=L.ptr(dres, torch.float32), ld_dres=_ld(dres))
     if dx_lp is not None:
         _set(p, dx_lp=L.ptr(dx_lp, torch.bfloat16), ld_dx_lp=_ld(dx_lp))
+    if ssf_scale is not None:
+        _set(p, beta=L.fptr(beta), ssf_scale=L.fptr(ssf_scale), dssf_scale=L.fptr(dssf_scale), dssf_shift=L.fptr(dssf_shift))
     if az is not None:
         ra = az.shape[1]
         assert tuple(aw.shape) == (ra, dim) and aw.is_contiguous()
@@ -224,6 +229,46 @@ def cast_bf16(x, out=None):
     if out is None:
         out = torch.empty((M, dim), device=x.device, dtype=torch.bfloat16)
     L.call('gvk_cast_f32_bf16', C.c_void_p(L.ptr(x, torch.float32)), _ld(x), C.c_void_p(L.ptr(out, torch.bfloat16)), _ld(out), M, dim, L.stream())
+    return out
+
+
+def cast_f32(x, out=None):
+    """bf16 [M, dim] (row-major view) -> fp32"""
+    M, dim = x.shape
+    if out is None:
+        out = torch.empty((M, dim), device=x.device, dtype=torch.float32)
+    L.call('gvk_cast_bf16_f32', C.c_void_p(L.ptr(x, torch.bfloat16)), _ld(x), C.c_void_p(L.ptr(out, torch.float32)), _ld(out), M, dim, L.stream())
+    return out
+
+
+def ssf_bwd(dy, *, y=None, scale=None, shift=None, dx=None, dscale=None, dshift=None, sub=None, rows_per_batch=0, batch_rows=0, M=None):
+    """SSF site backward (scale given) or bias gradient (scale None): see gvk_ssf_bwd in include/gvk.h.  dx may be dy (in place)."""
+    N = dy.shape[1]
+    p = S['gvk_ssf_bwd_params']()
+    _set(p, dy=dy, ld_dy=_ld(dy), dtype=L.dtype_tag(dy.dtype), M=dy.shape[0] if M is None else M, N=N, rows_per_batch=rows_per_batch, batch_rows=batch_rows,
+         dscale=L.fptr(dscale), dshift=L.fptr(dshift))
+    if scale is not None:
+        assert y is not None and y.dtype == dy.dtype
+        _set(p, y=y, ld_y=_ld(y), scale=L.fptr(scale), shift=L.fptr(shift))
+        if dx is not None:
+            assert dx.dtype == dy.dtype
+            _set(p, dx=dx, ld_dx=_ld(dx))
+    if sub is not None:
+        _set(p, sub=L.ptr(sub, torch.float32), ld_sub=_ld(sub))
+    L.call('gvk_ssf_bwd', C.byref(p), L.stream())
+    return dx
+
+
+def dropout(x, drop_p, seed, *, res=None, out=None, out_dtype=None, offset=0):
+    """out = res + dropout(x) with the replayable Philox mask of element (m, n) = philox(seed, offset + m*N + n)."""
+    M, N = x.shape
+    if out is None:
+        out = torch.empty((M, N), device=x.device, dtype=out_dtype or x.dtype)
+    p = S['gvk_dropout_params']()
+    _set(p, x=x, x_dtype=L.dtype_tag(x.dtype), ldx=_ld(x), out=out, out_dtype=L.dtype_tag(out.dtype), ld_out=_ld(out), M=M, N=N, drop_p=drop_p, seed=seed, offset=offset)
+    if res is not None:
+        _set(p, res=L.ptr(res, torch.float32), ld_res=_ld(res))
+    L.call('gvk_dropout', C.byref(p), L.stream())
     return out
 
 
@@ -348,6 +393,13 @@ def prompt_fusion_bwd(xl, ll, dxl, w, saved, grads, B, T, N, P):
         setattr(p.g, k, L.fptr(grads[k]))
     L.call('gvk_prompt_fusion_bwd', C.byref(p), L.stream())
     return dll
+
+
+def relu_bwd(dy, z, out=None):
+    if out is None:
+        out = torch.empty_like(dy)
+    L.call('gvk_relu_bwd', C.c_void_p(L.fptr(dy)), C.c_void_p(L.fptr(z)), C.c_void_p(L.fptr(out)), C.c_size_t(dy.numel()), L.stream())
+    return out
 
 
 def quickgelu_bwd(dy, pre, out=None):

@@ -1,0 +1,505 @@
+"""Host-side orchestration of the ViT-family PEFT variants over the C-ABI kernels: ``--method linear | bitfit | adaptformer | melo |
+ssf | shallow_vpt | deep_vpt`` of the reference (``src/train.py:111-153``).  All of them run the frozen blocks of
+``src/model/vision_transformer.py:26-89`` with method-specific side paths:
+
+* adaptformer — ``up(ReLU(down(LN_a(x))))`` in parallel to the MLP (``src/model/adaptformer.py:58-78,93-99``);
+* melo        — rank-r LoRA on the q and v column blocks of ``to_qkv`` (``src/model/melo.py:41-47``);
+* ssf         — ``x * scale + shift`` after the patch embedding, every LayerNorm and every Linear (``src/model/ssf.py:24-31,64-116,138,236``);
+* vpt         — prompt tokens inserted after cls, once (shallow) or re-inserted at every layer with the reference's
+                ``1 + prompt_dim`` slice (``src/model/vpt.py:124-161``), so the sequence length changes per layer;
+* linear / bitfit — freeze rules only (``src/train.py:114-137``); bitfit needs the column sums of dY at every bias.
+
+Backward follows the freeze rule: dX through the frozen GEMMs / attention only as far as a trainable tensor needs it, dW only
+for tensors with ``requires_grad``.  Same two compute modes as ``engine.GavikoEngine`` ('fp32' exact, 'bf16' tensor cores).
+PyTorch is plumbing here (allocation, views, concatenation of token blocks, autograd glue); no arithmetic of the path runs in torch.
+"""
+import torch
+
+from . import ops
+from ._lib import GvkError
+from .engine import FrozenCache, _f32, _resolve_dtype
+
+_SEED_MIX = 0x9E3779B97F4A7C15
+_MASK63 = (1 << 63) - 1
+
+
+def _p(mod):
+    """active dropout probability of an nn.Dropout (0 in eval mode)"""
+    return float(mod.p) if (mod is not None and mod.training and mod.p > 0) else 0.0
+
+
+class VitEngine:
+    """kind: 'vit' (VisionTransformer: linear / bitfit / wrapped by MeLO), 'adaptformer', 'ssf', 'vpt'."""
+
+    def __init__(self, module, kind, compute_dtype=None):
+        self.__dict__['_module_ref'] = module
+        self.kind = kind
+        self._requested = compute_dtype
+        self._cache = FrozenCache()
+        self._step = 0
+
+    @property
+    def module(self):
+        return self._module_ref
+
+    def set_compute_dtype(self, compute_dtype):
+        _resolve_dtype(compute_dtype, torch.float32)
+        self._requested = compute_dtype
+        self._cache.clear()
+
+    def compute_dtype(self):
+        return _resolve_dtype(self._requested, self.vt.pos_embedding.dtype)
+
+    @property
+    def vt(self):
+        m = self.module
+        if self.kind == 'vpt':
+            return m.vision_transformer
+        if hasattr(m, 'lora_vit'):
+            return m.lora_vit
+        return m
+
+    # ------------------------------------------------------------------------------------------
+    def __call__(self, img):
+        m = self.module
+        if not img.is_cuda:
+            raise GvkError('gaviko_b200 models run on CUDA only (no CPU fallback): move the model and the input to a B200')
+        names, tensors = [], []
+        for n, p in m.named_parameters():
+            if p.requires_grad:
+                names.append(n)
+                tensors.append(p)
+        need_grad = torch.is_grad_enabled() and len(tensors) > 0
+        logits = _VitFn.apply(self, img, need_grad, names, *tensors)
+        return logits.to(img.dtype) if logits.dtype != img.dtype else logits
+
+    def _seed(self, layer, kind):
+        return (torch.initial_seed() * _SEED_MIX + self._step * 1315423911 + layer * 2654435761 + kind * 97) & _MASK63
+
+    # ------------------------------------------------------------------------------------------
+    def _layer_modules(self, i):
+        layer = self.vt.transformer.layers[i]
+        if self.kind == 'adaptformer':
+            return layer[0], layer[2], layer[1]
+        return layer[0], layer[1], None
+
+    def _weights(self, cdt):
+        """Per-layer tensors: GEMM operands in compute dtype (+ transposes for dgrad), vectors in fp32.  Cached on (data_ptr, version)."""
+        vt, cache, c = self.vt, self._cache, self.module._cfg
+        dim = c['dim']
+        prefix = self._vt_prefix()
+
+        def mat(key, src):
+            return cache.get((key, cdt), src, lambda t: t.reshape(t.shape[0], -1).to(cdt).contiguous())
+
+        def mat_t(key, src):
+            return cache.get((key, 't', cdt), src, lambda t: t.reshape(t.shape[0], -1).t().to(cdt).contiguous())
+
+        def vec(key, src):
+            return None if src is None else cache.get((key, 'v'), src, lambda t: t.float().contiguous())
+
+        W = dict(conv_w=mat('conv_w', vt.conv_proj[0].weight), conv_b=vec('conv_b', vt.conv_proj[0].bias),
+                 pos_patch=cache.get(('pos_patch',), vt.pos_embedding, lambda t: t[0, 1:].float().contiguous()),
+                 pos_cls=cache.get(('pos_cls',), vt.pos_embedding, lambda t: t[0, :1].float().contiguous()),
+                 cls=cache.get(('cls',), vt.cls_token, lambda t: t.reshape(1, dim).float().contiguous()),
+                 norm_w=vec('norm_w', vt.transformer.norm.weight), norm_b=vec('norm_b', vt.transformer.norm.bias),
+                 head_w=vec('head_w', vt.mlp_head.weight), head_b=vec('head_b', vt.mlp_head.bias), layers=[], names={})
+        nm = W['names']
+        nm['conv_b'] = prefix + 'conv_proj.0.bias'
+        nm['norm_b'] = prefix + 'transformer.norm.bias'
+        nm['head_w'], nm['head_b'] = prefix + 'mlp_head.weight', prefix + 'mlp_head.bias'
+        ssf = self.kind == 'ssf'
+        if ssf:
+            W['ssf_patch'] = (vec('ssfp_s', vt.ssf_scale_1), vec('ssfp_h', vt.ssf_shift_1))
+            W['ssf_final'] = (vec('ssff_s', vt.transformer.ssf_scale_1), vec('ssff_h', vt.transformer.ssf_shift_1))
+            nm['ssf_patch'] = (prefix + 'ssf_scale_1', prefix + 'ssf_shift_1')
+            nm['ssf_final'] = (prefix + 'transformer.ssf_scale_1', prefix + 'transformer.ssf_shift_1')
+        for i in range(c['depth']):
+            a, f, ad = self._layer_modules(i)
+            ai, fi = (0, 2) if self.kind == 'adaptformer' else (0, 1)
+            pa, pf = f'{prefix}transformer.layers.{i}.{ai}.', f'{prefix}transformer.layers.{i}.{fi}.'
+            qkv_mod = a.to_qkv
+            lora = hasattr(qkv_mod, 'linear_a_q')
+            qkv_lin = qkv_mod.qkv if lora else qkv_mod
+            Lw = dict(
+                ln1_w=vec(('ln1w', i), a.norm.weight), ln1_b=vec(('ln1b', i), a.norm.bias),
+                wqkv=mat(('wqkv', i), qkv_lin.weight), wqkv_t=mat_t(('wqkv', i), qkv_lin.weight),
+                wo=mat(('wo', i), a.to_out[0].weight), wo_t=mat_t(('wo', i), a.to_out[0].weight), bo=vec(('bo', i), a.to_out[0].bias),
+                ln2_w=vec(('ln2w', i), f.net[0].weight), ln2_b=vec(('ln2b', i), f.net[0].bias),
+                w1=mat(('w1', i), f.net[1].weight), w1_t=mat_t(('w1', i), f.net[1].weight), b1=vec(('b1', i), f.net[1].bias),
+                w2=mat(('w2', i), f.net[4].weight), w2_t=mat_t(('w2', i), f.net[4].weight), b2=vec(('b2', i), f.net[4].bias),
+                drop_attn=a.dropout, drop_out=a.to_out[1], drop_ff1=f.net[3], drop_ff2=f.net[5],
+                n=dict(ln1_b=pa + 'norm.bias', bo=pa + 'to_out.0.bias', ln2_b=pf + 'net.0.bias', b1=pf + 'net.1.bias', b2=pf + 'net.4.bias'))
+            if ssf:
+                Lw['ssf'] = dict(a0=(vec(('sa0s', i), a.ssf_scale_0), vec(('sa0h', i), a.ssf_shift_0)), a1=(vec(('sa1s', i), a.ssf_scale_1), vec(('sa1h', i), a.ssf_shift_1)),
+                                 a2=(vec(('sa2s', i), a.ssf_scale_2), vec(('sa2h', i), a.ssf_shift_2)), f0=(vec(('sf0s', i), f.ssf_scale_0), vec(('sf0h', i), f.ssf_shift_0)),
+                                 f1=(vec(('sf1s', i), f.ssf_scale_1), vec(('sf1h', i), f.ssf_shift_1)), f2=(vec(('sf2s', i), f.ssf_scale_2), vec(('sf2h', i), f.ssf_shift_2)))
+                Lw['n'].update({k: (p_ + f'ssf_scale_{k[1]}', p_ + f'ssf_shift_{k[1]}') for k, p_ in (('a0', pa), ('a1', pa), ('a2', pa), ('f0', pf), ('f1', pf), ('f2', pf))})
+            if lora:
+                r, s = qkv_mod.r, float(qkv_mod.alpha // qkv_mod.r)
+                Aq, Av, Bq, Bv = qkv_mod.linear_a_q.weight, qkv_mod.linear_a_v.weight, qkv_mod.linear_b_q.weight, qkv_mod.linear_b_v.weight
+                tag = (Aq._version, Av._version, Bq._version, Bv._version)
+                Lw['lora'] = dict(r=r, s=s,
+                                  # LN1(x) @ (s A)^T gives the scaled latents; B and s B are the up weights of forward / the down weights of backward
+                                  a_stack=cache.get(('loraA', i, tag), Aq, lambda t: torch.cat([Aq.detach().float(), Av.detach().float()], 0).contiguous()),
+                                  sa_stack=cache.get(('lorasA', i, tag), Aq, lambda t: (s * torch.cat([Aq.detach().float(), Av.detach().float()], 0)).contiguous()),
+                                  bq=_f32(Bq), bv=_f32(Bv),
+                                  sbq=cache.get(('lorasBq', i, tag), Bq, lambda t: (s * t.float()).contiguous()),
+                                  sbv=cache.get(('lorasBv', i, tag), Bv, lambda t: (s * t.float()).contiguous()))
+                pq = pa + 'to_qkv.'
+                Lw['n'].update(aq=pq + 'linear_a_q.weight', av=pq + 'linear_a_v.weight', bq=pq + 'linear_b_q.weight', bv=pq + 'linear_b_v.weight')
+            if ad is not None:
+                if not isinstance(ad.scale, float) or ad.scale != 1.0 or ad.adapter_layernorm_option != 'in':
+                    raise NotImplementedError('gaviko_b200 AdaptFormer supports the reference defaults (adapter_scalar="1.0", layernorm "in")')
+                pd_ = f'{prefix}transformer.layers.{i}.1.'
+                Lw['ad'] = dict(ln_w=_f32(ad.adapter_layer_norm_before.weight), ln_b=_f32(ad.adapter_layer_norm_before.bias),
+                                wd=_f32(ad.down_adapter_proj.weight), bd=_f32(ad.down_adapter_proj.bias),
+                                wu=_f32(ad.up_adapter_proj.weight), bu=_f32(ad.up_adapter_proj.bias), drop=float(ad.dropout))
+                if ad.dropout != 0.0:
+                    raise NotImplementedError('Adapter dropout > 0 is not implemented (reference default 0.0)')
+                Lw['n'].update(ad_ln_w=pd_ + 'adapter_layer_norm_before.weight', ad_ln_b=pd_ + 'adapter_layer_norm_before.bias',
+                               ad_wd=pd_ + 'down_adapter_proj.weight', ad_bd=pd_ + 'down_adapter_proj.bias',
+                               ad_wu=pd_ + 'up_adapter_proj.weight', ad_bu=pd_ + 'up_adapter_proj.bias')
+            W['layers'].append(Lw)
+        return W
+
+    def _vt_prefix(self):
+        if self.kind == 'vpt':
+            return 'vision_transformer.'
+        if hasattr(self.module, 'lora_vit'):
+            return 'lora_vit.'
+        return ''
+
+    # ------------------------------------------------------------------------------------------
+    def _attention(self, qkv, B, T, H, D, dim, drop_p, seed):
+        if qkv.dtype == torch.bfloat16 and D == 64 and drop_p == 0.0:
+            return ops.mhsa_fwd(qkv, B, T, H, D ** -0.5)
+        return ops.attn_simt_fwd(qkv, B, T, H, D, q_off=0, k_off=dim, v_off=2 * dim, scale=D ** -0.5, drop_p=drop_p, seed=seed)
+
+    def _attention_bwd(self, qkv, o, lse, do, B, T, H, D, dim, drop_p, seed):
+        if qkv.dtype == torch.bfloat16 and D == 64 and drop_p == 0.0:
+            return ops.mhsa_bwd(qkv, o, lse, do, B, T, H, D ** -0.5)
+        return ops.attn_simt_bwd(qkv, o, lse, do, B, T, H, D, q_off=0, k_off=dim, v_off=2 * dim, scale=D ** -0.5, drop_p=drop_p, seed=seed)
+
+    def _prompts(self, i):
+        """(P, dim) projected prompt tokens of layer i (model/vpt.py:127-131,146-153) and the embedding they came from."""
+        m = self.module
+        E = _f32(m.deep_prompt_embeddings[i] if m.deep_prompt else m.prompt_embeddings[0])
+        return ops.rowproj_up(E, _f32(m.prompt_proj.weight), _f32(m.prompt_proj.bias)), E
+
+    def forward(self, img, save):
+        m, vt, c = self.module, self.vt, self.module._cfg
+        cdt = self.compute_dtype()
+        lp = cdt != torch.float32
+        pr = ops.PREC_TF32 if lp else ops.PREC_FP32
+        W = self._weights(cdt)
+        B = img.shape[0]
+        N, dim, H, D = c['num_patches'], c['dim'], c['heads'], c['dim_head']
+        if img.dtype != torch.float32 or not img.is_contiguous():
+            img = img.float().contiguous()
+        if tuple(img.shape[1:]) != (c['channels'], c['grid'][0] * c['fp'], c['grid'][1] * c['ps'], c['grid'][2] * c['ps']):
+            raise GvkError(f'unexpected volume shape {tuple(img.shape)}')
+        self._step += 1
+        ssf = self.kind == 'ssf'
+        # ---- patch embedding + [cls ; patches] + pos (model/vision_transformer.py:149-157), SSF site model/ssf.py:236
+        T = N + 1
+        patches = ops.patch_gather(img, c['fp'], c['ps'], cdt)
+        x = torch.empty((B * T, dim), device=img.device, dtype=torch.float32)
+        sp = W.get('ssf_patch', (None, None))
+        ops.gemm(patches, W['conv_w'], bias=W['conv_b'], ssf_scale=sp[0], ssf_shift=sp[1], pos=W['pos_patch'], rows_per_batch=N, out_batch_rows=T,
+                 out_row_offset=1, out=x)
+        del patches
+        ops.fill_rows(W['cls'], W['pos_cls'], x, T, 0, B)
+        ctx = dict(B=B, N=N, W=W, cdt=cdt, layers=[], x0=x if save else None, emb_drop=(_p(vt.dropout), self._seed(0, 9)))
+        if ctx['emb_drop'][0] > 0:
+            x = ops.dropout(x, ctx['emb_drop'][0], ctx['emb_drop'][1])
+        vpt = self.kind == 'vpt'
+        if vpt and _p(m.prompt_dropout) > 0:
+            raise NotImplementedError('prompt_dropout > 0 in training mode is not implemented (reference default 0.0)')
+        for i in range(c['depth']):
+            Lw = W['layers'][i]
+            st = dict(T_in=T)
+            if vpt and (i == 0 or m.deep_prompt):
+                # [cls ; P prompts ; rest]: at layers >= 1 the reference drops rows 1 .. prompt_dim (NOT 1 .. P), model/vpt.py:151-153
+                pr_tok, E = self._prompts(i)
+                P = pr_tok.shape[0]
+                skip = 0 if i == 0 else m.deep_prompt_embeddings.shape[2]
+                x3 = x.view(B, T, dim)
+                x = torch.cat([x3[:, :1], pr_tok.unsqueeze(0).expand(B, P, dim), x3[:, 1 + skip:]], 1).reshape(-1, dim)
+                st.update(vpt=(P, skip, E))
+                T = x.shape[0] // B
+            st['T'] = T
+            sa = Lw.get('ssf', {})
+            s_a0, s_a1, s_a2 = sa.get('a0', (None, None)), sa.get('a1', (None, None)), sa.get('a2', (None, None))
+            s_f0, s_f1, s_f2 = sa.get('f0', (None, None)), sa.get('f1', (None, None)), sa.get('f2', (None, None))
+            p_attn, p_out, p_ff1, p_ff2 = _p(Lw['drop_attn']), _p(Lw['drop_out']), _p(Lw['drop_ff1']), _p(Lw['drop_ff2'])
+            seeds = [self._seed(i, k) for k in range(4)]
+            # ---- attention (model/vision_transformer.py:60-72)
+            h1, mean1, rstd1 = ops.layernorm_fwd(x, Lw['ln1_w'], Lw['ln1_b'], out_dtype=cdt, ssf_scale=s_a0[0], ssf_shift=s_a0[1], save_stats=save)
+            lo = Lw.get('lora')
+            if lo is not None:
+                qkv32 = ops.gemm(h1, Lw['wqkv'])
+                z = ops.rowproj_down(x, lo['sa_stack'], ln=(Lw['ln1_w'], Lw['ln1_b']), prec=pr)['z']          # [M, 2r] = s * A LN1(x)
+                r = lo['r']
+                ops.rowproj_up(z[:, :r], lo['bq'], res=qkv32[:, :dim], out=qkv32[:, :dim], prec=pr)           # q += B_q (s A_q x)
+                ops.rowproj_up(z[:, r:], lo['bv'], res=qkv32[:, 2 * dim:], out=qkv32[:, 2 * dim:], prec=pr)  # v += B_v (s A_v x)
+                qkv = ops.cast_bf16(qkv32) if lp else qkv32
+                st['lora_z'] = z
+                del qkv32
+            else:
+                qkv = ops.gemm(h1, Lw['wqkv'], ssf_scale=s_a1[0], ssf_shift=s_a1[1], out_dtype=cdt)
+            del h1
+            o, lse = self._attention(qkv, B, T, H, D, H * D, p_attn, seeds[0])
+            if ssf or p_out > 0:
+                y_a = ops.gemm(o, Lw['wo'], bias=Lw['bo'], ssf_scale=s_a2[0], ssf_shift=s_a2[1])
+                x_mid = ops.dropout(y_a, p_out, seeds[1], res=x, out_dtype=torch.float32)
+                st['y_a'] = y_a if ssf else None
+            else:
+                x_mid = ops.gemm(o, Lw['wo'], bias=Lw['bo'], res1=x)
+            # ---- MLP (model/vision_transformer.py:26-38) + parallel adapter (model/adaptformer.py:93-99)
+            h2, mean2, rstd2 = ops.layernorm_fwd(x_mid, Lw['ln2_w'], Lw['ln2_b'], out_dtype=cdt, ssf_scale=s_f0[0], ssf_shift=s_f0[1], save_stats=save)
+            hpre = torch.empty((B * T, c['mlp_dim']), device=img.device, dtype=cdt) if save else None
+            act = ops.gemm(h2, Lw['w1'], bias=Lw['b1'], ssf_scale=s_f1[0], ssf_shift=s_f1[1], act=ops.ACT_GELU, aux=hpre, out_dtype=cdt)
+            del h2
+            if p_ff1 > 0:
+                act = ops.dropout(act, p_ff1, seeds[2])
+            if ssf or p_ff2 > 0:
+                y_f = ops.gemm(act, Lw['w2'], bias=Lw['b2'], ssf_scale=s_f2[0], ssf_shift=s_f2[1])
+                x_out = ops.dropout(y_f, p_ff2, seeds[3], res=x_mid, out_dtype=torch.float32)
+                st['y_f'] = y_f if ssf else None
+            else:
+                x_out = ops.gemm(act, Lw['w2'], bias=Lw['b2'], res1=x_mid)
+            del act
+            ad = Lw.get('ad')
+            if ad is not None:
+                d = ops.rowproj_down(x_mid, ad['wd'], ad['bd'], ln=(ad['ln_w'], ad['ln_b']), act=ops.ROWACT_RELU, prec=pr)
+                self._up_chunked(d['z'], ad['wu'], ad['bu'], x_out, pr)
+                st.update(ad_z=d['z'], ad_mean=d['mean'], ad_rstd=d['rstd'])
+            if save:
+                st.update(x_in=x, mean1=mean1, rstd1=rstd1, qkv=qkv, o=o, lse=lse, x_mid=x_mid, mean2=mean2, rstd2=rstd2, hpre=hpre,
+                          drops=(p_attn, p_out, p_ff1, p_ff2), seeds=seeds)
+                ctx['layers'].append(st)
+            x = x_out
+        pool = (0, 1) if vt.pool == 'cls' else (0, T)
+        sf = W.get('ssf_final', (None, None))
+        logits, pooled = ops.head_fwd(x, B, T, pool[0], pool[1], W['norm_w'], W['norm_b'], W['head_w'], W['head_b'], ssf_scale=sf[0], ssf_shift=sf[1])
+        if not save:
+            return logits, None
+        ctx.update(x_final=x, pooled=pooled, T_final=T, pool=pool)
+        return logits, ctx
+
+    @staticmethod
+    def _up_chunked(z, wu, bu, out, pr):
+        """out += z @ wu^T + bu for a rank that may exceed what one staged [r, dim] panel allows (Adapter: r = 64)."""
+        r, dim = z.shape[1], wu.shape[0]
+        step = r if r * dim * 4 <= 160 * 1024 else 32
+        for j0 in range(0, r, step):
+            ops.rowproj_up(z[:, j0:j0 + step], wu[:, j0:j0 + step].contiguous(), bu if j0 == 0 else None, res=out, out=out, prec=pr)
+
+    # ------------------------------------------------------------------------------------------
+    def backward(self, ctx, dlogits, names):
+        m, vt, c = self.module, self.vt, self.module._cfg
+        W, cdt, B, N = ctx['W'], ctx['cdt'], ctx['B'], ctx['N']
+        lp = cdt != torch.float32
+        pr = ops.PREC_TF32 if lp else ops.PREC_FP32
+        dim, H, D = c['dim'], c['heads'], c['dim_head']
+        dev = dlogits.device
+        params = dict(m.named_parameters())
+        want = set(names)
+        G = {n: torch.zeros(params[n].shape, device=dev, dtype=torch.float32) for n in names}
+
+        def g(name):      # accumulator of a trainable tensor, or None when it is frozen
+            return G[name] if name in want else None
+
+        def g2(pair):
+            return (g(pair[0]), g(pair[1])) if pair is not None else (None, None)
+
+        nm = W['names']
+        T = ctx['T_final']
+        # which parts of the graph carry gradient to a trainable tensor?
+        body_names = [n for n in names if 'mlp_head' not in n and n not in (nm['norm_b'],) and n not in nm.get('ssf_final', ())]
+        need_body = len(body_names) > 0
+        dX = torch.zeros((B * T, dim), device=dev, dtype=torch.float32) if need_body else None
+        dX_lp = torch.zeros((B * T, dim), device=dev, dtype=cdt) if (need_body and lp) else None
+        sf = W.get('ssf_final', (None, None))
+        dsf = g2(nm.get('ssf_final'))
+        ops.head_bwd(ctx['x_final'], B, T, ctx['pool'][0], ctx['pool'][1], W['norm_w'], W['norm_b'], W['head_w'], W['head_b'], ctx['pooled'], dlogits,
+                     dx=dX, dx_lp=dX_lp, need_dx=need_body, ssf_scale=sf[0], ssf_shift=sf[1], dbeta=g(nm['norm_b']), dssf_scale=dsf[0], dssf_shift=dsf[1],
+                     dwh=G.get(nm['head_w']) if nm['head_w'] in want else torch.zeros_like(W['head_w']),
+                     dbh=G.get(nm['head_b']) if nm['head_b'] in want else torch.zeros_like(W['head_b']))
+        if not need_body:
+            return G
+        vpt = self.kind == 'vpt'
+        for i in reversed(range(c['depth'])):
+            Lw, st = W['layers'][i], ctx['layers'][i]
+            n_ = Lw['n']
+            T = st['T']
+            sa = Lw.get('ssf', {})
+            p_attn, p_out, p_ff1, p_ff2 = st['drops']
+            seeds = st['seeds']
+
+            def site_bwd(dy, y_saved, key, bias_name, drop_p, seed, have_lp):
+                """Gradient entering a [Linear -> SSF -> Dropout] site: replays the dropout mask, reduces the SSF / bias gradients and
+                returns (d wrt the Linear output in compute dtype for the dgrad GEMM)."""
+                d = dy
+                fresh = False
+                if drop_p > 0:
+                    d = ops.dropout(d, drop_p, seed)
+                    fresh = True
+                if key in sa:
+                    ds_, dh_ = g2(n_[key])
+                    out = d if fresh else torch.empty_like(d)
+                    ops.ssf_bwd(d, y=y_saved, scale=sa[key][0], shift=sa[key][1], dx=out, dscale=ds_, dshift=dh_)
+                    d, fresh = out, True
+                if g(bias_name) is not None:
+                    ops.ssf_bwd(d, dshift=g(bias_name))
+                if lp and d.dtype != cdt:
+                    return have_lp if (have_lp is not None and not fresh) else ops.cast_bf16(d)
+                return d
+
+            # ---- MLP
+            dY2 = site_bwd(dX, st.get('y_f'), 'f2', n_['b2'], p_ff2, seeds[3], dX_lp)
+            dA = ops.gemm(dY2, Lw['w2_t'], act=ops.ACT_GELU_BWD, aux=st['hpre'], out_dtype=cdt)
+            if p_ff1 > 0:
+                dA = ops.dropout(dA, p_ff1, seeds[2])
+            if 'f1' in sa:
+                ds_, dh_ = g2(n_['f1'])
+                ops.ssf_bwd(dA, y=st['hpre'], scale=sa['f1'][0], shift=sa['f1'][1], dx=dA, dscale=ds_, dshift=dh_)
+            if g(n_['b1']) is not None:
+                ops.ssf_bwd(dA, dshift=g(n_['b1']))
+            dH2 = ops.gemm(dA, Lw['w1_t'])
+            del dA
+            f0 = sa.get('f0')
+            dXm = ops.layernorm_bwd(st['x_mid'], Lw['ln2_w'], st['mean2'], st['rstd2'], dy=dH2, dres=dX, dx=dH2, dbeta=g(n_['ln2_b']),
+                                    beta=Lw['ln2_b'] if f0 else None, ssf_scale=f0[0] if f0 else None,
+                                    dssf_scale=g2(n_['f0'])[0] if f0 else None, dssf_shift=g2(n_['f0'])[1] if f0 else None)
+            ad = Lw.get('ad')
+            if ad is not None:
+                self._adapter_bwd(ad, n_, st, dX, dXm, g, pr)
+            # ---- attention
+            dYa = site_bwd(dXm, st.get('y_a'), 'a2', n_['bo'], p_out, seeds[1], None)
+            dO = ops.gemm(dYa, Lw['wo_t'], out_dtype=cdt)
+            dqkv = self._attention_bwd(st['qkv'], st['o'], st['lse'], dO, B, T, H, D, H * D, p_attn, seeds[0])
+            del dO
+            if 'a1' in sa:
+                ds_, dh_ = g2(n_['a1'])
+                ops.ssf_bwd(dqkv, y=st['qkv'], scale=sa['a1'][0], shift=sa['a1'][1], dx=dqkv, dscale=ds_, dshift=dh_)
+            lo = Lw.get('lora')
+            dz = None
+            if lo is not None:
+                r = lo['r']
+                d32 = ops.cast_f32(dqkv) if lp else dqkv
+                dq, dv, z = d32[:, :dim], d32[:, 2 * dim:], st['lora_z']
+                if g(n_['bq']) is not None:
+                    ops.skinny_wgrad(z[:, :r], dq, dw=g(n_['bq']), dw_layout='dr', prec=pr)
+                if g(n_['bv']) is not None:
+                    ops.skinny_wgrad(z[:, r:], dv, dw=g(n_['bv']), dw_layout='dr', prec=pr)
+                dz = torch.cat([ops.rowproj_down(dq, lo['sbq'], transposed=True, prec=pr)['z'],
+                                ops.rowproj_down(dv, lo['sbv'], transposed=True, prec=pr)['z']], 1)      # s * d(A LN1(x)), [M, 2r]
+                ln = (Lw['ln1_w'], Lw['ln1_b'], st['mean1'], st['rstd1'])
+                if g(n_['aq']) is not None:
+                    ops.skinny_wgrad(dz[:, :r], st['x_in'], dw=g(n_['aq']), dw_layout='rd', ln=ln, prec=pr)
+                if g(n_['av']) is not None:
+                    ops.skinny_wgrad(dz[:, r:], st['x_in'], dw=g(n_['av']), dw_layout='rd', ln=ln, prec=pr)
+                del d32
+            dH1 = ops.gemm(dqkv, Lw['wqkv_t'])
+            del dqkv
+            a0 = sa.get('a0')
+            dX_lp = torch.empty((B * T, dim), device=dev, dtype=cdt) if lp else None
+            dX = ops.layernorm_bwd(st['x_in'], Lw['ln1_w'], st['mean1'], st['rstd1'], dy=dH1, dz=dz, w=lo['a_stack'] if lo is not None else None,
+                                   dres=dXm, dx=dH1, dx_lp=dX_lp, dbeta=g(n_['ln1_b']), beta=Lw['ln1_b'] if a0 else None,
+                                   ssf_scale=a0[0] if a0 else None, dssf_scale=g2(n_['a0'])[0] if a0 else None, dssf_shift=g2(n_['a0'])[1] if a0 else None)
+            del dXm
+            if 'vpt' in st:
+                # undo the token insertion: prompt rows feed prompt_proj / the embeddings, dropped rows get zero gradient
+                P, skip, E = st['vpt']
+                T_in = st['T_in']
+                dPr = ops.batch_rowsum(dX, T, 1, P, B)                                                   # [P, dim] = sum over the batch
+                wp = _f32(m.prompt_proj.weight)
+                pd = wp.shape[1]
+                if g('prompt_proj.weight') is not None:
+                    for j0 in range(0, pd, 32):
+                        j1 = min(pd, j0 + 32)
+                        ops.skinny_wgrad(E[:, j0:j1], dPr, dw=G['prompt_proj.weight'][:, j0:j1], dw_strides=(1, pd),
+                                         dx_colsum=g('prompt_proj.bias') if j0 == 0 else None)
+                elif g('prompt_proj.bias') is not None:
+                    ops.ssf_bwd(dPr, dshift=G['prompt_proj.bias'])
+                dE = ops.rowproj_down(dPr, wp, transposed=True)['z']                                     # [P, prompt_dim]
+                ename = 'deep_prompt_embeddings' if m.deep_prompt else 'prompt_embeddings'
+                if g(ename) is not None:
+                    G[ename][i if m.deep_prompt else 0] += dE      # torch add of a [P, prompt_dim] tile: accumulation plumbing
+                d3 = dX.view(B, T, dim)
+                dX = torch.cat([d3[:, :1], torch.zeros((B, skip, dim), device=dev, dtype=torch.float32), d3[:, 1 + P:]], 1).reshape(-1, dim)
+                assert dX.shape[0] == B * T_in
+                dX_lp = ops.cast_bf16(dX) if lp else None
+            ctx['layers'][i] = None
+            if not self._needs_below(i, names, nm):
+                return G
+        # ---- below layer 0: patch-embedding SSF site and the conv bias (bitfit)
+        T0 = N + 1
+        p_emb, seed_emb = ctx['emb_drop']
+        if p_emb > 0:
+            dX = ops.dropout(dX, p_emb, seed_emb)
+        d_patch = dX[1:]     # logical row m -> physical row (m // N) * T0 + m % N of this view (cls rows skipped)
+        if 'ssf_patch' in W:
+            ds_, dh_ = g2(nm['ssf_patch'])
+            ops.ssf_bwd(d_patch, y=ctx['x0'][1:], scale=W['ssf_patch'][0], shift=W['ssf_patch'][1], dscale=ds_, dshift=dh_, sub=W['pos_patch'],
+                        rows_per_batch=N, batch_rows=T0, M=B * N)
+        if g(nm['conv_b']) is not None:
+            if 'ssf_patch' in W:
+                raise NotImplementedError('conv bias gradient below an SSF site')
+            ops.ssf_bwd(d_patch, dshift=G[nm['conv_b']], rows_per_batch=N, batch_rows=T0, M=B * N)
+        return G
+
+    def _needs_below(self, i, names, nm):
+        """Does any trainable tensor live below layer i (so dX must keep flowing)?"""
+        if i == 0:
+            return True     # the post-loop block handles (and ignores) what is left
+        prefix = self._vt_prefix()
+        below = [f'{prefix}transformer.layers.{k}.' for k in range(i)]
+        for n in names:
+            if any(n.startswith(b) for b in below) or n in (nm['conv_b'],) or n in nm.get('ssf_patch', ()) or \
+                    n.startswith('prompt_proj') or n.endswith('prompt_embeddings'):
+                return True
+        return False
+
+    def _adapter_bwd(self, ad, n_, st, dX, dXm, g, pr):
+        """x_out = ... + up(ReLU(down(LN_a(x_mid)))): gradients of the six adapter tensors and the contribution to d x_mid
+        (model/adaptformer.py:58-78).  Rank 64 is processed in 32-wide slices (kernel limit of the rank-r gradient kernels)."""
+        z = st['ad_z']
+        r, dim = z.shape[1], dX.shape[1]
+        ln = (ad['ln_w'], ad['ln_b'], st['ad_mean'], st['ad_rstd'])
+        dz = torch.empty_like(z)
+        for j0 in range(0, r, 32):
+            j1 = min(r, j0 + 32)
+            if g(n_['ad_wu']) is not None:
+                ops.skinny_wgrad(z[:, j0:j1], dX, dw=g(n_['ad_wu'])[:, j0:j1], dw_strides=(1, r), dx_colsum=g(n_['ad_bu']) if j0 == 0 else None, prec=pr)
+            dz[:, j0:j1] = ops.rowproj_down(dX, ad['wu'][:, j0:j1].contiguous(), transposed=True, prec=pr)['z']   # column-block copy: plumbing
+        ops.relu_bwd(dz, z, out=dz)
+        for j0 in range(0, r, 32):
+            j1 = min(r, j0 + 32)
+            dzc = dz[:, j0:j1]
+            if g(n_['ad_wd']) is not None:
+                ops.skinny_wgrad(dzc, st['x_mid'], dw=g(n_['ad_wd'])[j0:j1], dw_layout='rd', da_colsum=g(n_['ad_bd'])[j0:j1] if g(n_['ad_bd']) is not None else None,
+                                 ln=ln, prec=pr)
+            ops.layernorm_bwd(st['x_mid'], ad['ln_w'], st['ad_mean'], st['ad_rstd'], dz=dzc, w=ad['wd'][j0:j1].contiguous(), dres=dXm, dx=dXm,
+                              dgamma=g(n_['ad_ln_w']), dbeta=g(n_['ad_ln_b']))
+
+
+class _VitFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, engine, img, need_grad, names, *tensors):
+        with torch.no_grad():
+            logits, saved = engine.forward(img, need_grad)
+        ctx.engine, ctx.saved, ctx.names = engine, saved, names
+        ctx.shapes = [(t.shape, t.dtype) for t in tensors]
+        return logits
+
+    @staticmethod
+    def backward(ctx, dlogits):
+        if ctx.saved is None:
+            raise RuntimeError('backward called on a forward that ran without gradient tracking')
+        saved, ctx.saved = ctx.saved, None
+        with torch.no_grad():
+            G = ctx.engine.backward(saved, dlogits.float().contiguous(), ctx.names)
+        return (None, None, None, None, *[G[n].reshape(s).to(d) for n, (s, d) in zip(ctx.names, ctx.shapes)])

@@ -165,7 +165,9 @@ typedef struct {
 } gvk_skinny_wgrad_params;
 int gvk_skinny_wgrad(const gvk_skinny_wgrad_params* p, gvk_stream_t stream);
 
-/* LayerNorm backward:  dx = dres + LN'(dy) + az @ aw;  dy is either dense ([M, dim] fp32) or rank-r (dy[m, c] = sum_j dz[m, j] * w(j, c)).
+/* LayerNorm backward:  dx = dres + LN'(dy) + az @ aw;  dy = dense ([M, dim] fp32) and / or rank-r (sum_j dz[m, j] * w(j, c)), added together.
+ * With ssf_scale the forward was y = LN(x) * ssf_scale + ssf_shift (model/ssf.py:65,102): the incoming gradient is first reduced into
+ * dssf_scale += colsum(dy * LN(x)), dssf_shift += colsum(dy) (needs beta) and multiplied by ssf_scale.
  * az @ aw (optional, az [M, ra], aw(j, c) strided like w) is added OUTSIDE the norm: the dgrad of a rank-ra down-projection that reads
  * the same residual stream as the LayerNorm (Awakening_Prompt.proj_down next to FeedForward's norm, model/gaviko.py:155,304).
  * dgamma / dbeta (optional, [dim]) accumulate with atomics.  dx may alias dres or dy.
@@ -179,6 +181,7 @@ typedef struct {
   float* dgamma; float* dbeta;
   int M, dim;
   const float* az; int ld_az; const float* aw; int aw_sj, aw_sc; int ra;
+  const float* beta; const float* ssf_scale; float* dssf_scale; float* dssf_shift;
 } gvk_layernorm_bwd_params;
 int gvk_layernorm_bwd(const gvk_layernorm_bwd_params* p, gvk_stream_t stream);
 
@@ -191,8 +194,33 @@ int gvk_small_matmul(const float* a, int lda, int ra, const float* w, int rb, in
 /* y[m, n] += / = colsum helpers: out[c] += sum_m x[m, c]  (bias gradients; bitfit). */
 int gvk_colsum(const float* x, int ldx, int M, int dim, float* out, gvk_stream_t stream);
 
-/* Elementwise cast fp32 -> bf16 of an [M, dim] matrix (weights, activations). */
+/* Elementwise cast fp32 -> bf16 of an [M, dim] matrix (weights, activations), and back. */
 int gvk_cast_f32_bf16(const float* x, int ldx, void* y, int ldy, int M, int dim, gvk_stream_t stream);
+int gvk_cast_bf16_f32(const void* x, int ldx, float* y, int ldy, int M, int dim, gvk_stream_t stream);
+
+/* Backward of an SSF site y = x * scale + shift (model/ssf.py:24-31) and of plain bias adds (bitfit), over logical rows m < M whose
+ * physical row is (m / rows_per_batch) * batch_rows + m % rows_per_batch in dy, y and dx (rows_per_batch == 0: identity):
+ *   dshift[n] += sum_m dy[m, n];   dscale[n] += sum_m dy[m, n] * x[m, n];   dx[m, n] = dy[m, n] * scale[n]
+ * The site's INPUT x is recovered from its saved OUTPUT: x = (y - sub[m % rows_per_batch, n] - shift[n]) / scale[n]  (`sub` = optional
+ * term added after the site, e.g. the positional embedding after the patch-embedding site, model/ssf.py:236-240).
+ * scale == NULL: bias-gradient mode (only dshift; y / dx unused).  dy, y, dx share `dtype` (GVK_F32 / GVK_BF16); dx may alias dy. */
+typedef struct {
+  const void* dy; int ld_dy; const void* y; int ld_y; void* dx; int ld_dx; int dtype;
+  const float* scale; const float* shift; const float* sub; int ld_sub;
+  float* dscale; float* dshift;
+  int M, N, rows_per_batch, batch_rows;
+} gvk_ssf_bwd_params;
+int gvk_ssf_bwd(const gvk_ssf_bwd_params* p, gvk_stream_t stream);
+
+/* out = res + dropout(x) elementwise over an [M, N] matrix (x / out in `dtype`, res optional fp32 [M, N] with out then fp32... see below).
+ * Replayable mask: element (m, n) kept iff philox(seed, offset + m * N + n) >= drop_p, scaled by 1 / (1 - drop_p).  N % 4 == 0.
+ * x_dtype / out_dtype in {GVK_F32, GVK_BF16}; res (optional) is fp32.  Used for the nn.Dropout sites of the un-frozen train mode
+ * (model/vision_transformer.py:33,35,58 and :157) and, applied to gradients with the same seed, for their backward. */
+typedef struct {
+  const void* x; int x_dtype; int ldx; const float* res; int ld_res; void* out; int out_dtype; int ld_out;
+  int M, N; float drop_p; uint64_t seed; uint64_t offset;
+} gvk_dropout_params;
+int gvk_dropout(const gvk_dropout_params* p, gvk_stream_t stream);
 
 
 /* ------------------------------------------------------------------------------------------------------------------
@@ -331,6 +359,8 @@ int gvk_prompt_fusion_bwd(const gvk_fusion_bwd_params* p, gvk_stream_t stream);
 
 /* y = dy * quick_gelu'(pre)   over n elements (may run in place: y == dy). */
 int gvk_quickgelu_bwd(const float* dy, const float* pre, float* y, size_t n, gvk_stream_t stream);
+/* y = dy * (z > 0)   over n elements (ReLU backward from the activation output; Adapter, model/adaptformer.py:63; in place allowed). */
+int gvk_relu_bwd(const float* dy, const float* z, float* y, size_t n, gvk_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------------------------
  * Head: final LayerNorm on the pooled rows only, mean-pool, Linear  (model/gaviko.py:306,314-316;

@@ -64,3 +64,18 @@ def test_seeded_construction_equals_reference_init():
     assert list(sa.keys()) == list(sb.keys())
     for k in sa:
         assert torch.equal(sa[k], sb[k]), k
+
+
+@pytest.mark.parametrize('name', list(__import__('oracle.cases', fromlist=['VARIANT_CASES']).VARIANT_CASES))
+def test_variant_names_shapes_match_reference(name, tmp_path, monkeypatch):
+    """Every --method variant exposes the reference's parameter names, shapes and trainable set (= the checkpoint layout, train.py:161-167)."""
+    from oracle.cases import VARIANT_CASES
+    from variant_factory import build_variant
+    monkeypatch.chdir(tmp_path)
+    method, kw, _ = VARIANT_CASES[name]
+    model = build_variant(method, kw)
+    g = load_golden(name)
+    assert [n for n, _ in model.named_parameters()] == g['all_names'].tolist()
+    assert [str(tuple(p.shape)) for _, p in model.named_parameters()] == [s.replace(' ', '') if False else s for s in g['all_shapes'].tolist()]
+    assert [n for n, p in model.named_parameters() if p.requires_grad] == g['trainable_names'].tolist()
+    assert model.train() is None or method in ('linear', 'bitfit', 'melo')      # the overriding classes return None like the reference
