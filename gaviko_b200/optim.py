@@ -6,6 +6,7 @@ import ctypes as C
 import torch
 
 from . import _lib as L
+from .parallel import exchange_flat_gradient
 
 
 class FlatAdam(torch.optim.Optimizer):
@@ -53,11 +54,9 @@ class FlatAdam(torch.optim.Optimizer):
 
     @torch.no_grad()
     def step(self, closure=None):
-        if self.world > 1:
-            torch.distributed.all_reduce(self.flat_g, group=self.group)     # SUM; the 1/world mean is folded into grad_scale
+        scale = exchange_flat_gradient(self.flat_g, self.group) if self.world > 1 else 1.0   # SUM; the 1/world mean is folded into grad_scale
         g = self.param_groups[0]
         self.step_count += 1
-        scale = 1.0 / self.world
         st = L.stream()
         L.call('gvk_grad_sumsq', C.c_void_p(self.flat_g.data_ptr()), C.c_size_t(self.numel), C.c_float(scale), C.c_void_p(self.partials.data_ptr()), st)
         L.call('gvk_clip_adam', C.c_void_p(self.flat_p.data_ptr()), C.c_void_p(self.flat_g.data_ptr()), C.c_void_p(self.exp_avg.data_ptr()),
