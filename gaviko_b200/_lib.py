@@ -12,7 +12,7 @@ LIB_PATH = os.path.join(_HERE, 'libgvk_sm100a.so')
 HEADER_PATH = os.path.join(os.path.dirname(_HERE), 'include', 'gvk.h')
 
 GVK_F32, GVK_BF16 = 0, 1
-ACT_NONE, ACT_GELU, ACT_GELU_BWD = 0, 1, 2
+ACT_NONE, ACT_GELU, ACT_GELU_BWD, ACT_GELU_SAVE_GRAD, ACT_MUL_AUX = 0, 1, 2, 3, 4
 ROWACT_NONE, ROWACT_QUICKGELU, ROWACT_RELU = 0, 1, 2
 LOSS_FOCAL, LOSS_CE = 0, 1
 

@@ -57,6 +57,11 @@ __device__ __forceinline__ void epi_elem(const EpiArgs& e, int m, int n, float v
     v = gelu_erf(v);
   } else if (e.act == GVK_ACT_GELU_BWD) {
     v *= gelu_erf_grad(ld_dyn(e.aux, (size_t)m * e.ld_aux + n, e.aux_dtype));
+  } else if (e.act == GVK_ACT_GELU_SAVE_GRAD) {
+    if (e.aux) st_dyn(e.aux, (size_t)m * e.ld_aux + n, e.aux_dtype, gelu_erf_grad(v));
+    v = gelu_erf(v);
+  } else if (e.act == GVK_ACT_MUL_AUX) {
+    v *= ld_dyn(e.aux, (size_t)m * e.ld_aux + n, e.aux_dtype);
   }
   int orow = m;
   if (e.rows_per_batch > 0) {
@@ -78,7 +83,7 @@ __device__ __forceinline__ void epi_elem(const EpiArgs& e, int m, int n, float v
 // global access is a contiguous 128 B (fp32) / 64 B (bf16) row segment.  Loads the epilogue depends on (residual, saved GELU
 // pre-activation) are issued before the TMEM wait so their latency overlaps it.
 // -------------------------------------------------------------------------------------------------
-enum { EPI_GENERIC = 0, EPI_STORE_BF16 = 1, EPI_BIAS_GELU_BF16 = 2, EPI_BIAS_RES_F32 = 3, EPI_GELU_BWD_BF16 = 4, EPI_STORE_F32 = 5 };
+enum { EPI_GENERIC = 0, EPI_STORE_BF16 = 1, EPI_BIAS_GELU_BF16 = 2, EPI_BIAS_RES_F32 = 3, EPI_GELU_BWD_BF16 = 4, EPI_STORE_F32 = 5, EPI_BIAS_GELU_SAVEGRAD_BF16 = 6, EPI_MUL_AUX_BF16 = 7 };
 
 // Standard-normal CDF Phi(x) = 0.5 (1 + erf(x / sqrt 2)) with |abs err| < 2e-7 (Abramowitz-Stegun 7.1.26), branch-free:
 // rcp.approx + ex2.approx + 7 fma/mul + select.  Also returns e = exp(-x^2 / 2) for the GELU derivative.  Used only on the bf16
@@ -107,6 +112,13 @@ __device__ __forceinline__ float norm_cdf_fast(float x, float& e) {
 __device__ __forceinline__ float gelu_fast(float x) {
   float e;
   return x * norm_cdf_fast(x, e);
+}
+// GELU and its derivative together: they share the CDF and exp(-x^2/2)
+__device__ __forceinline__ float gelu_and_grad_fast(float x, float& grad) {
+  float e;
+  const float cdf = norm_cdf_fast(x, e);
+  grad = fmaf(x * 0.39894228040143268f, e, cdf);
+  return x * cdf;
 }
 __device__ __forceinline__ float gelu_grad_fast(float x) {
   float e;
@@ -140,7 +152,7 @@ __device__ __forceinline__ void epilogue_patch_fast(const EpiArgs& e, uint32_t t
       res[it] = (m < M) ? *reinterpret_cast<const float4*>(e.res1 + (size_t)m * e.ld_res1 + col) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
   }
-  if constexpr (EPI == EPI_GELU_BWD_BF16) {
+  if constexpr (EPI == EPI_GELU_BWD_BF16 || EPI == EPI_MUL_AUX_BF16) {
 #pragma unroll
     for (int it = 0; it < 8; ++it) {
       const int m = row0 + it * 4 + sr;
@@ -148,7 +160,7 @@ __device__ __forceinline__ void epilogue_patch_fast(const EpiArgs& e, uint32_t t
     }
   }
   float4 bias = make_float4(0.f, 0.f, 0.f, 0.f);
-  if constexpr (EPI == EPI_BIAS_GELU_BF16 || EPI == EPI_BIAS_RES_F32) bias = *reinterpret_cast<const float4*>(e.bias + col);
+  if constexpr (EPI == EPI_BIAS_GELU_BF16 || EPI == EPI_BIAS_RES_F32 || EPI == EPI_BIAS_GELU_SAVEGRAD_BF16) bias = *reinterpret_cast<const float4*>(e.bias + col);
   // ---- TMEM -> registers (thread = row) -> swizzled smem
   float v[32];
   tmem_ld_32x32(taddr, v);
@@ -166,8 +178,17 @@ __device__ __forceinline__ void epilogue_patch_fast(const EpiArgs& e, uint32_t t
     const int m = row0 + r;
     float4 x = reinterpret_cast<const float4*>(patch)[r * 8 + (cv ^ (r & 7))];
     if (m >= M) continue;
-    if constexpr (EPI == EPI_BIAS_GELU_BF16 || EPI == EPI_BIAS_RES_F32) {
+    if constexpr (EPI == EPI_BIAS_GELU_BF16 || EPI == EPI_BIAS_RES_F32 || EPI == EPI_BIAS_GELU_SAVEGRAD_BF16) {
       x.x += bias.x; x.y += bias.y; x.z += bias.z; x.w += bias.w;
+    }
+    if constexpr (EPI == EPI_BIAS_GELU_SAVEGRAD_BF16) {
+      float4 gr;
+      x.x = gelu_and_grad_fast(x.x, gr.x); x.y = gelu_and_grad_fast(x.y, gr.y); x.z = gelu_and_grad_fast(x.z, gr.z); x.w = gelu_and_grad_fast(x.w, gr.w);
+      if (e.aux) *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(e.aux) + (size_t)m * e.ld_aux + col) = float4_to_bf16x4(gr);
+    }
+    if constexpr (EPI == EPI_MUL_AUX_BF16) {
+      const float4 a4 = bf16x4_to_float4(aux_in[it]);
+      x.x *= a4.x; x.y *= a4.y; x.z *= a4.z; x.w *= a4.w;
     }
     if constexpr (EPI == EPI_BIAS_GELU_BF16) {
       if (e.aux) *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(e.aux) + (size_t)m * e.ld_aux + col) = float4_to_bf16x4(x);
@@ -446,7 +467,7 @@ static int launch_bf16(const gvk_gemm_params* p, const EpiArgs& e, cudaStream_t 
 int gemm_dispatch(const gvk_gemm_params* p, cudaStream_t stream) {
   GVK_CHECK_ARG(p && p->a && p->b && p->out, "gvk_gemm: null operand");
   GVK_CHECK_ARG(p->M > 0 && p->N > 0 && p->K > 0, "gvk_gemm: non-positive shape M=%d N=%d K=%d", p->M, p->N, p->K);
-  GVK_CHECK_ARG(p->act != GVK_ACT_GELU_BWD || p->aux, "gvk_gemm: GELU_BWD needs aux");
+  GVK_CHECK_ARG((p->act != GVK_ACT_GELU_BWD && p->act != GVK_ACT_MUL_AUX) || p->aux, "gvk_gemm: GELU_BWD / MUL_AUX need aux");
   GVK_CHECK_ARG(p->rows_per_batch >= 0, "gvk_gemm: rows_per_batch < 0");
   const EpiArgs e = to_epi(p);
   if (p->ab_dtype == GVK_BF16) {
@@ -466,6 +487,8 @@ int gemm_dispatch(const gvk_gemm_params* p, cudaStream_t stream) {
       else if (bias_ok && p->act == GVK_ACT_GELU && !p->res1 && p->out_dtype == GVK_BF16 && aux_ok) epi = EPI_BIAS_GELU_BF16;
       else if (bias_ok && p->act == GVK_ACT_NONE && res_ok && p->out_dtype == GVK_F32 && !p->aux) epi = EPI_BIAS_RES_F32;
       else if (!p->bias && p->act == GVK_ACT_GELU_BWD && !p->res1 && p->out_dtype == GVK_BF16 && p->aux && aux_ok) epi = EPI_GELU_BWD_BF16;
+      else if (bias_ok && p->act == GVK_ACT_GELU_SAVE_GRAD && !p->res1 && p->out_dtype == GVK_BF16 && aux_ok) epi = EPI_BIAS_GELU_SAVEGRAD_BF16;
+      else if (!p->bias && p->act == GVK_ACT_MUL_AUX && !p->res1 && p->out_dtype == GVK_BF16 && p->aux && aux_ok) epi = EPI_MUL_AUX_BF16;
     }
 #define GVK_GEMM_CASE(E)                                               \
   case E:                                                              \
@@ -477,6 +500,8 @@ int gemm_dispatch(const gvk_gemm_params* p, cudaStream_t stream) {
       GVK_GEMM_CASE(EPI_BIAS_RES_F32)
       GVK_GEMM_CASE(EPI_GELU_BWD_BF16)
       GVK_GEMM_CASE(EPI_STORE_F32)
+      GVK_GEMM_CASE(EPI_BIAS_GELU_SAVEGRAD_BF16)
+      GVK_GEMM_CASE(EPI_MUL_AUX_BF16)
       default:
         GVK_GEMM_CASE(EPI_GENERIC)
     }

@@ -241,7 +241,7 @@ class GavikoEngine:
             # ---- frozen MLP (model/vision_transformer.py:26-38, residual + prompt gaviko.py:304)
             h2, mean2, rstd2 = ops.layernorm_fwd(g_mid, Lw['ln2_w'], Lw['ln2_b'], out_dtype=cdt, save_stats=save)
             hpre = torch.empty((B * T, c['mlp_dim']), device=img.device, dtype=cdt) if save else None
-            act = ops.gemm(h2, Lw['w1'], bias=Lw['b1'], act=ops.ACT_GELU, aux=hpre, out_dtype=cdt)
+            act = ops.gemm(h2, Lw['w1'], bias=Lw['b1'], act=ops.ACT_GELU_SAVE_GRAD if save else ops.ACT_GELU, aux=hpre, out_dtype=cdt)   # aux = gelu'(pre)
             del h2
             g_out = ops.gemm(act, Lw['w2'], bias=Lw['b2'], res1=g_tmp)
             del act, g_tmp
@@ -300,7 +300,7 @@ class GavikoEngine:
             gL, gF = G['local'][s], G['fusion'][s]
             a_in = dG_lp if lp else dG
             # ---- MLP dgrad: dH2 = (dG W2) * gelu'(hpre) W1
-            dA = ops.gemm(a_in, Lw['w2_t'], act=ops.ACT_GELU_BWD, aux=st['hpre'], out_dtype=cdt)
+            dA = ops.gemm(a_in, Lw['w2_t'], act=ops.ACT_MUL_AUX, aux=st['hpre'], out_dtype=cdt)
             dH2 = ops.gemm(dA, Lw['w1_t'])
             del dA
             # ---- prompt up-projection: d(comb) = dG Wu ; dWu, dbu

@@ -5,7 +5,7 @@ import ctypes as C
 import torch
 
 from . import _lib as L
-from ._lib import (ACT_GELU, ACT_GELU_BWD, ACT_NONE, LOSS_CE, LOSS_FOCAL, ROWACT_NONE, ROWACT_QUICKGELU,  # noqa: F401
+from ._lib import (ACT_GELU, ACT_GELU_BWD, ACT_GELU_SAVE_GRAD, ACT_MUL_AUX, ACT_NONE, LOSS_CE, LOSS_FOCAL, ROWACT_NONE, ROWACT_QUICKGELU,  # noqa: F401
                    ROWACT_RELU, GvkError)
 
 S = L.STRUCTS

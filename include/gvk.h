@@ -33,7 +33,7 @@ typedef enum {
 enum { GVK_F32 = 0, GVK_BF16 = 1 };
 
 /* activation selector of the GEMM epilogue */
-enum { GVK_ACT_NONE = 0, GVK_ACT_GELU = 1, GVK_ACT_GELU_BWD = 2 };
+enum { GVK_ACT_NONE = 0, GVK_ACT_GELU = 1, GVK_ACT_GELU_BWD = 2, GVK_ACT_GELU_SAVE_GRAD = 3, GVK_ACT_MUL_AUX = 4 };
 
 const char* gvk_last_error(void);
 int gvk_version(void);
@@ -48,6 +48,8 @@ long long gvk_struct_size(const char* name);
  *     v = v * ssf_scale[n] + ssf_shift[n]                 (optional; model/ssf.py:24-31)
  *     act == GELU     : if aux: aux[m,n] = v  (pre-activation, saved for backward);  v = gelu_erf(v)
  *     act == GELU_BWD : v = v * gelu_erf'(aux[m,n])
+ *     act == GELU_SAVE_GRAD : aux[m,n] = gelu_erf'(v) (the derivative, which shares its erf / exp with the activation);  v = gelu_erf(v)
+ *     act == MUL_AUX  : v = v * aux[m,n]           (backward of GELU_SAVE_GRAD: the dgrad epilogue is one multiply instead of an erf)
  *     v += pos[(m % rows_per_batch), n]                   (optional; positional embedding, model/gaviko.py:542-547)
  *     v += res1[m,n] + res2[m,n]                          (optional fp32 residuals)
  *     out [row(m), n] = v      row(m) = (m / rows_per_batch) * out_batch_rows + out_row_offset + m % rows_per_batch

@@ -104,7 +104,9 @@ def test_rejects_cpu_input():
 
 
 def test_flat_adam_sink_and_step_match_torch():
-    """FlatAdam (engine accumulates straight into the flat buffer; fused clip+Adam kernels) == autograd grads + torch clip + torch Adam."""
+    """FlatAdam (engine accumulates straight into the flat buffer; fused clip+Adam kernels) == autograd grads + torch clip + torch Adam.
+    Gradients are compared every step; the torch side then steps on a copy of OUR gradients, so the parameter comparison isolates the
+    optimiser kernels (Adam's 1/sqrt(v) normalisation would otherwise amplify the atomics-order noise of near-zero gradient elements)."""
     from gaviko_b200.optim import FlatAdam
     ma, img, y = _build('gaviko_t16_small', 'fp32')
     mb, _, _ = _build('gaviko_t16_small', 'fp32')
@@ -117,16 +119,15 @@ def test_flat_adam_sink_and_step_match_torch():
         crit(ma(img), y).backward()
         opt_b.zero_grad()
         crit(mb(img), y).backward()
-        if step == 0:
-            for (n, pa), (_, pb) in zip(ma.named_parameters(), mb.named_parameters()):
-                if pa.requires_grad:
-                    assert torch.allclose(pa.grad, pb.grad, rtol=1e-4, atol=1e-7), n
+        for (n, pa), (_, pb) in zip(ma.named_parameters(), mb.named_parameters()):
+            if pa.requires_grad:
+                scale = pb.grad.abs().max().item()
+                assert (pa.grad - pb.grad).abs().max().item() <= 1e-3 * scale + 1e-9, (step, n)
+                pb.grad.copy_(pa.grad)
         norm_b = torch.nn.utils.clip_grad_norm_(mb.parameters(), 1.0)
         opt_a.step()
         opt_b.step()
-        assert abs(opt_a.grad_norm.item() - norm_b.item()) <= 1e-4 * norm_b.item()
-    # three Adam updates of lr = 1e-3 each: 1e-5 absolute is 0.3 % of the distance moved (Adam's 1/sqrt(v) normalisation passes the
-    # fp32 summation-order noise of tiny-norm gradients straight into the update)
-    for (n, pa), (_, pb) in zip(ma.named_parameters(), mb.named_parameters()):
-        if pa.requires_grad:
-            assert torch.allclose(pa, pb, rtol=1e-4, atol=1e-5), n
+        assert abs(opt_a.grad_norm.item() - norm_b.item()) <= 1e-5 * norm_b.item()
+        for (n, pa), (_, pb) in zip(ma.named_parameters(), mb.named_parameters()):
+            if pa.requires_grad:
+                assert torch.allclose(pa, pb, rtol=1e-5, atol=2e-7), (step, n, (pa - pb).abs().max().item())

@@ -60,6 +60,16 @@ def test_gemm_epilogues(dt):
     # gelu backward epilogue + two residuals, fp32 output
     out = ops.gemm(a, b, act=ops.ACT_GELU_BWD, aux=aux, res1=res1, res2=res2, out_dtype=torch.float32)
     assert (out.double() - _ref(a, b, None, 'gelu_bwd', res1, res2, pre=aux)).abs().max().item() < 1e-3
+    # GELU with the derivative saved instead of the pre-activation, and its one-multiply backward epilogue (same result as GELU_BWD)
+    pre = _ref(a, b, bias)
+    dgelu = 0.5 * (1 + torch.erf(pre / 2 ** 0.5)) + pre * torch.exp(-0.5 * pre * pre) / (2 * torch.pi) ** 0.5
+    aux2 = torch.empty(M, N, device='cuda', dtype=dt)
+    out = ops.gemm(a, b, bias=bias, act=ops.ACT_GELU_SAVE_GRAD, aux=aux2, out_dtype=dt)
+    assert (out.double() - _ref(a, b, bias, 'gelu')).abs().max().item() < (3e-2 if dt == torch.bfloat16 else 1e-3)
+    assert (aux2.double() - dgelu).abs().max().item() < (1e-2 if dt == torch.bfloat16 else 1e-3)
+    out = ops.gemm(a, b, act=ops.ACT_MUL_AUX, aux=aux2, out_dtype=dt)
+    want = _ref(a, b) * aux2.double()
+    assert (out.double() - want).abs().max().item() < (3e-2 if dt == torch.bfloat16 else 1e-3) * max(1.0, want.abs().max().item())
     # in-place residual update (out aliases res1), as the residual stream does
     r = res1.clone()
     ops.gemm(a, b, bias=bias, res1=r, out=r)
