@@ -322,7 +322,12 @@ mhsa_bwd_dq_sm100_kernel(const __grid_constant__ CUtensorMap tma_q128, const __g
   mbar_wait(bar_q, 0);
   for (int j = 0; j < nkv; ++j) {
     const int buf = j % kKvStages;
-    if (tid == 0 && j + kKvStages - 1 < nkv) load_kv(j + kKvStages - 1);   // that stage was last read by iteration j - 1 (complete)
+    if (tid == 0 && j + kKvStages - 1 < nkv) {
+      // the stage being refilled was last read by the MMAs of iteration j - 1: wait for them here (thread 0 only) instead of stalling every
+      // thread at the end of each iteration — tcgen05.mma executes in issue order, so S(j) cannot overtake dQ(j-1)'s read of dS(j-1)
+      if (j > 0) mbar_wait(bar_dq, (j - 1) & 1);
+      load_kv(j + kKvStages - 1);
+    }
     mbar_wait(&bar_kv[buf], (j / kKvStages) & 1);
     if (warp == 0) {   // warp-uniform control flow around the issue: only the tcgen05 instructions sit under elect_one
       tc_fence_after();
@@ -364,8 +369,8 @@ mhsa_bwd_dq_sm100_kernel(const __grid_constant__ CUtensorMap tma_q128, const __g
       }
       __syncwarp();
     }
-    mbar_wait(bar_dq, j & 1);
   }
+  mbar_wait(bar_dq, (nkv - 1) & 1);
   tc_fence_after();
   {
     float dq[64];
@@ -469,7 +474,10 @@ mhsa_bwd_dkv_sm100_kernel(const __grid_constant__ CUtensorMap tma_kv128, const _
   mbar_wait(bar_kv, 0);
   for (int i = 0; i < nq; ++i) {
     const int buf = i % kDkvStages;
-    if (tid == 0 && i + kDkvStages - 1 < nq) load_q(i + kDkvStages - 1);   // that stage was last read by iteration i - 1 (complete)
+    if (tid == 0 && i + kDkvStages - 1 < nq) {
+      if (i > 0) mbar_wait(bar_acc, (i - 1) & 1);     // the stage being refilled was last read by the MMAs of iteration i - 1
+      load_q(i + kDkvStages - 1);
+    }
     if (tid < 64) load_stats(i + kDkvStages - 1);
     mbar_wait(&bar_q[buf], (i / kDkvStages) & 1);
     if (warp == 0) {
@@ -531,8 +539,8 @@ mhsa_bwd_dkv_sm100_kernel(const __grid_constant__ CUtensorMap tma_kv128, const _
       }
       __syncwarp();
     }
-    mbar_wait(bar_acc, i & 1);
   }
+  mbar_wait(bar_acc, (nq - 1) & 1);
   tc_fence_after();
   {
     float v[64];
