@@ -35,36 +35,54 @@ def peaks():
     return dict(hbm_gbs=6650.0, bf16_tflops=1590.0, bf16_tflops_sustained=1400.0), 'fallback'
 
 
-class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons while the timed region runs (B200_PROFILING.md recipe)."""
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 100 ms by ONE background `nvidia-smi -lms` process while the timed region runs
+    (B200_PROFILING.md recipe); the median SM clock is taken over samples drawing > 300 W (= under load)."""
     Q = 'clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap'
 
     def __init__(self, index):
-        super().__init__(daemon=True)
-        self.index, self.rows, self._stop_evt = index, [], threading.Event()
+        self.index, self.proc, self.rows = index, None, []
 
-    def run(self):
-        while not self._stop_evt.is_set():
-            try:
-                out = subprocess.run(['nvidia-smi', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits', '-i', str(self.index)],
-                                     capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.rows.append([x.strip() for x in out.split(',')])
-            except Exception:
-                pass
-            self._stop_evt.wait(0.2)
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits', '-i', str(self.index), '-lms', '100'],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self._t = threading.Thread(target=self._read, daemon=True)
+            self._t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            parts = [x.strip() for x in line.split(',')]
+            if len(parts) >= 7:
+                self.rows.append(parts)
 
     def stop(self):
-        self._stop_evt.set()
-        self.join(timeout=3)
-        sm = sorted(int(float(r[0])) for r in self.rows if r and r[0].replace('.', '').isdigit())
+        if self.proc is not None:
+            time.sleep(0.15)
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=3)
+            except Exception:
+                self.proc.kill()
+            self._t.join(timeout=2)
+
+        def num(x):
+            try:
+                return float(x)
+            except ValueError:
+                return None
+        loaded = [r for r in self.rows if (num(r[2]) or 0) > 300.0] or self.rows
+        sm = sorted(int(num(r[0])) for r in loaded if num(r[0]) is not None)
         reasons = set()
         for r in self.rows:
             for name, v in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), r[3:7]):
                 if v.lower().startswith('active'):
                     reasons.add(name)
-        return dict(sm_mhz=sm[len(sm) // 2] if sm else None, sm_max_mhz=int(float(self.rows[0][1])) if self.rows else None,
-                    samples=len(self.rows), reasons=sorted(reasons))
+        pw = [num(r[2]) for r in self.rows if num(r[2]) is not None]
+        return dict(sm_mhz=sm[len(sm) // 2] if sm else None, sm_max_mhz=int(num(self.rows[0][1])) if self.rows and num(self.rows[0][1]) else None,
+                    samples=len(self.rows), samples_under_load=len(loaded), power_w_max=max(pw) if pw else None, reasons=sorted(reasons))
 
 
 # ----------------------------------------------------------------------------------------------------------------
@@ -293,7 +311,7 @@ def main():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--mode', default='train', choices=['train', 'infer'])
     ap.add_argument('--backbone', default='vit-b16')
-    ap.add_argument('--batch', type=int, default=32, help='volumes per GPU per step')
+    ap.add_argument('--batch', type=int, default=64, help='volumes per GPU per step (SURVEY 8d: 16 | 32 | 64)')
     ap.add_argument('--dtype', default='bf16', choices=['bf16', 'fp32'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
     args = ap.parse_args()

@@ -234,7 +234,11 @@ mhsa_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_co
 
 // =================================================================================================
 // backward: dQ (and delta)
+// 256 threads per 128-row tile: thread (half, r) owns row r and score columns 32*half .. 32*half+31.  Four warps per tile left each
+// sub-partition with two warps (two CTAs per SM) and the per-thread chain of 64 exp / multiply steps latency-bound at ~0.13 IPC per warp;
+// eight warps halve the chain and double the warps that can hide TMEM / SFU latency.
 // =================================================================================================
+constexpr int kBwdThreads = 256;
 struct BwdArgs {
   FaCommon c;
   const __nv_bfloat16* out;
@@ -247,9 +251,45 @@ struct BwdArgs {
   int ld_dqkv;
   FaDesc fd;
 };
+// D[tmem, 128 x 64] (+)= A * B, A = [128 x 64] bf16 in TMEM as two 16-column pieces (k 0..31 at a_lo, k 32..63 at a_hi), B MN-major smem tile
+__device__ __forceinline__ void mma_tmn_split(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, const void* b, bool accumulate, const FaDesc& fd) {
+  constexpr uint32_t idesc = make_idesc_bf16(128, 64, 0, 1);
+  const uint32_t b_addr = smem_u32(b);
+#pragma unroll
+  for (int k = 0; k < 4; ++k)
+    umma_bf16_ts(d_tmem, (k < 2 ? a_lo + 8 * k : a_hi + 8 * (k - 2)), make_sw128_desc(b_addr + k * fd.kadv, fd.lbo, fd.sbo), idesc, (accumulate || k > 0) ? 1u : 0u);
+}
+__device__ __forceinline__ void tmem_st_32x16b(uint32_t taddr, const uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]),
+      "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
+// 32 values of this thread's row -> 16 packed bf16 pairs -> 16 TMEM columns
+__device__ __forceinline__ void store_half_row_tmem(uint32_t taddr, const float (&v)[32]) {
+  uint32_t r[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) r[i] = pack_bf16(v[2 * i], v[2 * i + 1]);
+  tmem_st_32x16b(taddr, r);
+  tc_wait_st();
+}
+// 32 fp32 values -> bf16 -> 64 bytes of a global row
+__device__ __forceinline__ void store_half_row_global(__nv_bfloat16* dst, const float (&v)[32], float scale) {
+  uint4* d4 = reinterpret_cast<uint4*>(dst);
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    uint4 pk;
+    pk.x = pack_bf16(v[8 * c + 0] * scale, v[8 * c + 1] * scale);
+    pk.y = pack_bf16(v[8 * c + 2] * scale, v[8 * c + 3] * scale);
+    pk.z = pack_bf16(v[8 * c + 4] * scale, v[8 * c + 5] * scale);
+    pk.w = pack_bf16(v[8 * c + 6] * scale, v[8 * c + 7] * scale);
+    d4[c] = pk;
+  }
+}
 constexpr int kDqSmem = 2 * kTileBytes128 /*Q,dO*/ + 2 * kKvStages * kTileBytes64 /*K,V ring*/ + 128 + 1024;
 
-__global__ void __launch_bounds__(kFaThreads, 2)
+__global__ void __launch_bounds__(kBwdThreads, 2)
 mhsa_bwd_dq_sm100_kernel(const __grid_constant__ CUtensorMap tma_q128, const __grid_constant__ CUtensorMap tma_kv64, const __grid_constant__ CUtensorMap tma_do128,
                          BwdArgs a) {
   extern __shared__ uint8_t smem_raw[];
@@ -261,6 +301,7 @@ mhsa_bwd_dq_sm100_kernel(const __grid_constant__ CUtensorMap tma_q128, const __g
   uint64_t* bars = reinterpret_cast<uint64_t*>(sV + kKvStages * kTileBytes64);  // q, s, dq, kv[kKvStages]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
   const int tid = threadIdx.x, warp = tid >> 5;
+  const int half = tid >> 7, r = tid & 127;
   const int q0 = blockIdx.x * 128;
   const int bh = blockIdx.y, h = bh % a.c.H, b = bh / a.c.H;
   const int T = a.c.T, dim = a.c.dim;
@@ -281,7 +322,7 @@ mhsa_bwd_dq_sm100_kernel(const __grid_constant__ CUtensorMap tma_q128, const __g
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
   const uint32_t t_s = tmem, t_dp = tmem + 64, t_dq = tmem + 128;
-  const uint32_t lane_off = static_cast<uint32_t>(warp * 32) << 16;
+  const uint32_t lane_off = static_cast<uint32_t>((warp & 3) * 32) << 16;
   uint64_t *bar_q = &bars[0], *bar_s = &bars[1], *bar_dq = &bars[2], *bar_kv = &bars[3];
   const int nkv = (T + 63) / 64;
   auto load_kv = [&](int j) {   // tid 0 only
@@ -296,8 +337,8 @@ mhsa_bwd_dq_sm100_kernel(const __grid_constant__ CUtensorMap tma_q128, const __g
     tma_load_3d(sdO, &tma_do128, bar_q, h * kFaD, q0, b);
     for (int j = 0; j < kKvStages - 1 && j < nkv; ++j) load_kv(j);
   }
-  // delta_r = sum_d dO[r,d] * O[r,d]; lse in log2 units
-  const int row = q0 + tid;
+  // delta_r = sum_d dO[r,d] * O[r,d] (both halves compute it; half 0 publishes it together with the log2-domain lse)
+  const int row = q0 + r;
   float delta = 0.f, lse2 = 0.f;
   if (row < T) {
     const uint4* po = reinterpret_cast<const uint4*>(a.out + ((size_t)b * T + row) * a.ld_out + h * kFaD);
@@ -315,10 +356,14 @@ mhsa_bwd_dq_sm100_kernel(const __grid_constant__ CUtensorMap tma_q128, const __g
       }
     }
     lse2 = a.lse[(size_t)bh * T + row] * kLog2e;
-    a.delta[(size_t)bh * T + row] = delta;
-    a.delta[(size_t)a.c.B * a.c.H * T + (size_t)bh * T + row] = lse2;   // second half of the workspace: log2-domain lse for the dK/dV kernel
+    if (half == 0) {
+      a.delta[(size_t)bh * T + row] = delta;
+      a.delta[(size_t)a.c.B * a.c.H * T + (size_t)bh * T + row] = lse2;   // second half of the workspace: log2-domain lse for the dK/dV kernel
+    }
   }
   const float c2 = a.c.scale * kLog2e;
+  // this thread's dS piece goes over S columns it has itself consumed: [0,16) for half 0, [32,48) for half 1
+  const uint32_t t_s_mine = t_s + 32 * half + lane_off, t_dp_mine = t_dp + 32 * half + lane_off;
   mbar_wait(bar_q, 0);
   for (int j = 0; j < nkv; ++j) {
     const int buf = j % kKvStages;
@@ -340,31 +385,31 @@ mhsa_bwd_dq_sm100_kernel(const __grid_constant__ CUtensorMap tma_q128, const __g
     }
     mbar_wait(bar_s, j & 1);
     tc_fence_after();
-    float s[64], dp[64];
-    tmem_ld64(t_s + lane_off, s);
-    tmem_ld64(t_dp + lane_off, dp);
+    float s[32], dp[32];
+    tmem_ld_32x32(t_s_mine, s);
+    tmem_ld_32x32(t_dp_mine, dp);
     tc_wait_ld();
-    const int valid = T - j * 64;
-    if (valid >= 64) {
+    const int valid = T - j * 64 - 32 * half;   // columns >= valid of this thread's 32 are zero-filled padding
+    if (valid >= 32) {
 #pragma unroll
-      for (int i = 0; i < 64; ++i) {
+      for (int i = 0; i < 32; ++i) {
         const float p = fast_ex2(fmaf(s[i], c2, -lse2));
         s[i] = p * (dp[i] - delta);  // dS
       }
-    } else {                         // last K/V tile: key columns >= valid are zero-filled padding
+    } else {
 #pragma unroll
-      for (int i = 0; i < 64; ++i) {
+      for (int i = 0; i < 32; ++i) {
         const float p = (i < valid) ? fast_ex2(fmaf(s[i], c2, -lse2)) : 0.f;
         s[i] = p * (dp[i] - delta);
       }
     }
-    store_row_tmem(t_s + lane_off, s);   // dS (bf16 pairs) over the first 32 columns of S: the A operand of the next MMA, read from TMEM
+    store_half_row_tmem(t_s_mine, s);   // dS (bf16 pairs): the TMEM-resident A operand of the next MMA
     tc_fence_before();
     __syncthreads();
     if (warp == 0) {
       tc_fence_after();
       if (elect_one()) {
-        mma_tmn(t_dq, t_s, sK + buf * kTileBytes64, j > 0, a.fd);   // dQ += dS K
+        mma_tmn_split(t_dq, t_s, t_s + 32, sK + buf * kTileBytes64, j > 0, a.fd);   // dQ += dS K
         umma_commit(bar_dq);
       }
       __syncwarp();
@@ -373,21 +418,10 @@ mhsa_bwd_dq_sm100_kernel(const __grid_constant__ CUtensorMap tma_q128, const __g
   mbar_wait(bar_dq, (nkv - 1) & 1);
   tc_fence_after();
   {
-    float dq[64];
-    tmem_ld64(t_dq + lane_off, dq);
+    float dq[32];
+    tmem_ld_32x32(t_dq + 32 * half + lane_off, dq);
     tc_wait_ld();
-    if (row < T) {
-      uint4* dst = reinterpret_cast<uint4*>(a.dqkv + ((size_t)b * T + row) * a.ld_dqkv + h * kFaD);
-#pragma unroll
-      for (int c = 0; c < 8; ++c) {
-        uint4 pk;
-        pk.x = pack_bf16(dq[8 * c + 0] * a.c.scale, dq[8 * c + 1] * a.c.scale);
-        pk.y = pack_bf16(dq[8 * c + 2] * a.c.scale, dq[8 * c + 3] * a.c.scale);
-        pk.z = pack_bf16(dq[8 * c + 4] * a.c.scale, dq[8 * c + 5] * a.c.scale);
-        pk.w = pack_bf16(dq[8 * c + 6] * a.c.scale, dq[8 * c + 7] * a.c.scale);
-        dst[c] = pk;
-      }
-    }
+    if (row < T) store_half_row_global(a.dqkv + ((size_t)b * T + row) * a.ld_dqkv + h * kFaD + 32 * half, dq, a.c.scale);
   }
   tc_fence_before();
   __syncthreads();
@@ -395,7 +429,7 @@ mhsa_bwd_dq_sm100_kernel(const __grid_constant__ CUtensorMap tma_q128, const __g
 }
 
 // =================================================================================================
-// backward: dK, dV
+// backward: dK, dV  (same thread layout: half = 32-column block of the 64 queries of the tile in flight)
 // =================================================================================================
 constexpr int kDkvStages = 3;
 constexpr int kDkvSmem = 2 * kTileBytes128 /*K,V*/ + 2 * kDkvStages * kTileBytes64 /*Q,dO ring*/ + 2 * kDkvStages * 64 * 4 /*lse, delta ring*/ + 128 + 1024;
@@ -406,20 +440,21 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-__global__ void __launch_bounds__(kFaThreads, 2)
+__global__ void __launch_bounds__(kBwdThreads, 2)
 mhsa_bwd_dkv_sm100_kernel(const __grid_constant__ CUtensorMap tma_kv128, const __grid_constant__ CUtensorMap tma_q64, const __grid_constant__ CUtensorMap tma_do64,
                           BwdArgs a) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sK = smem;
   uint8_t* sV = sK + kTileBytes128;
-  uint8_t* sQ = sV + kTileBytes128;                    // kDkvStages stages of [64 x 64]
+  uint8_t* sQ = sV + kTileBytes128;                     // kDkvStages stages of [64 x 64]
   uint8_t* sdO = sQ + kDkvStages * kTileBytes64;        // kDkvStages stages
   uint64_t* bars = reinterpret_cast<uint64_t*>(sdO + kDkvStages * kTileBytes64);    // kv, s, acc, q[kDkvStages]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
   float* s_lse = reinterpret_cast<float*>(bars + 16);    // [kDkvStages][64] log2-domain lse of the q tile in flight (16-byte aligned)
-  float* s_delta = s_lse + kDkvStages * 64;               // [kDkvStages][64]
+  float* s_delta = s_lse + kDkvStages * 64;              // [kDkvStages][64]
   const int tid = threadIdx.x, warp = tid >> 5;
+  const int half = tid >> 7, r = tid & 127;
   const int k0 = blockIdx.x * 128;
   const int bh = blockIdx.y, h = bh % a.c.H, b = bh / a.c.H;
   const int T = a.c.T, dim = a.c.dim;
@@ -455,7 +490,7 @@ mhsa_bwd_dkv_sm100_kernel(const __grid_constant__ CUtensorMap tma_kv128, const _
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
   const uint32_t t_s = tmem, t_dp = tmem + 64, t_dv = tmem + 128, t_dk = tmem + 192;
-  const uint32_t lane_off = static_cast<uint32_t>(warp * 32) << 16;
+  const uint32_t lane_off = static_cast<uint32_t>((warp & 3) * 32) << 16;
   uint64_t *bar_kv = &bars[0], *bar_s = &bars[1], *bar_acc = &bars[2], *bar_q = &bars[3];
   auto load_q = [&](int i) {   // tid 0 only
     const int st = i % kDkvStages;
@@ -470,7 +505,8 @@ mhsa_bwd_dkv_sm100_kernel(const __grid_constant__ CUtensorMap tma_kv128, const _
     for (int i = 0; i < kDkvStages - 1 && i < nq; ++i) load_q(i);
   }
   const float c2 = a.c.scale * kLog2e;
-  const bool row_valid = (k0 + tid) < T;
+  const bool row_valid = (k0 + r) < T;
+  const uint32_t t_s_mine = t_s + 32 * half + lane_off, t_dp_mine = t_dp + 32 * half + lane_off;
   mbar_wait(bar_kv, 0);
   for (int i = 0; i < nq; ++i) {
     const int buf = i % kDkvStages;
@@ -491,16 +527,16 @@ mhsa_bwd_dkv_sm100_kernel(const __grid_constant__ CUtensorMap tma_kv128, const _
     }
     mbar_wait(bar_s, i & 1);
     tc_fence_after();
-    float s[64], dp[64];
-    tmem_ld64(t_s + lane_off, s);
-    tmem_ld64(t_dp + lane_off, dp);
+    float s[32], dp[32];
+    tmem_ld_32x32(t_s_mine, s);
+    tmem_ld_32x32(t_dp_mine, dp);
     tc_wait_ld();
-    const int valid = row_valid ? T - i * 64 : 0;
-    const float4* lse4 = reinterpret_cast<const float4*>(s_lse + buf * 64);
-    const float4* del4 = reinterpret_cast<const float4*>(s_delta + buf * 64);
-    if (valid >= 64) {
+    const int valid = row_valid ? T - i * 64 - 32 * half : 0;
+    const float4* lse4 = reinterpret_cast<const float4*>(s_lse + buf * 64 + 32 * half);
+    const float4* del4 = reinterpret_cast<const float4*>(s_delta + buf * 64 + 32 * half);
+    if (valid >= 32) {
 #pragma unroll
-      for (int q4 = 0; q4 < 16; ++q4) {
+      for (int q4 = 0; q4 < 8; ++q4) {
         const float4 l4 = lse4[q4], d4 = del4[q4];
         const float ls[4] = {l4.x, l4.y, l4.z, l4.w}, dl[4] = {d4.x, d4.y, d4.z, d4.w};
 #pragma unroll
@@ -513,7 +549,7 @@ mhsa_bwd_dkv_sm100_kernel(const __grid_constant__ CUtensorMap tma_kv128, const _
       }
     } else {                               // last query tile / key rows past T
 #pragma unroll
-      for (int q4 = 0; q4 < 16; ++q4) {
+      for (int q4 = 0; q4 < 8; ++q4) {
         const float4 l4 = lse4[q4], d4 = del4[q4];
         const float ls[4] = {l4.x, l4.y, l4.z, l4.w}, dl[4] = {d4.x, d4.y, d4.z, d4.w};
 #pragma unroll
@@ -525,16 +561,16 @@ mhsa_bwd_dkv_sm100_kernel(const __grid_constant__ CUtensorMap tma_kv128, const _
         }
       }
     }
-    store_row_tmem(t_s + lane_off, s);     // P^T  over S^T  (TMEM-resident A operands of the two accumulating MMAs)
-    store_row_tmem(t_dp + lane_off, dp);   // dS^T over dP^T
+    store_half_row_tmem(t_s_mine, s);     // P^T  over the S^T  columns this thread consumed
+    store_half_row_tmem(t_dp_mine, dp);   // dS^T over the dP^T columns this thread consumed
     if (tid < 64) cp_async_wait<kDkvStages - 2>();   // stats of tile i + 1 landed: visible after this barrier
     tc_fence_before();
     __syncthreads();
     if (warp == 0) {
       tc_fence_after();
       if (elect_one()) {
-        mma_tmn(t_dv, t_s, sdO + buf * kTileBytes64, i > 0, a.fd);   // dV += P^T dO
-        mma_tmn(t_dk, t_dp, sQ + buf * kTileBytes64, i > 0, a.fd);   // dK += dS^T Q
+        mma_tmn_split(t_dv, t_s, t_s + 32, sdO + buf * kTileBytes64, i > 0, a.fd);    // dV += P^T dO
+        mma_tmn_split(t_dk, t_dp, t_dp + 32, sQ + buf * kTileBytes64, i > 0, a.fd);   // dK += dS^T Q
         umma_commit(bar_acc);
       }
       __syncwarp();
@@ -543,37 +579,15 @@ mhsa_bwd_dkv_sm100_kernel(const __grid_constant__ CUtensorMap tma_kv128, const _
   mbar_wait(bar_acc, (nq - 1) & 1);
   tc_fence_after();
   {
-    float v[64];
-    const int row = k0 + tid;
-    __nv_bfloat16* base = a.dqkv + ((size_t)b * T + row) * a.ld_dqkv + h * kFaD;
-    tmem_ld64(t_dk + lane_off, v);
+    float v[32];
+    const int row = k0 + r;
+    __nv_bfloat16* base = a.dqkv + ((size_t)b * T + row) * a.ld_dqkv + h * kFaD + 32 * half;
+    tmem_ld_32x32(t_dk + 32 * half + lane_off, v);
     tc_wait_ld();
-    if (row < T) {
-      uint4* dst = reinterpret_cast<uint4*>(base + dim);
-#pragma unroll
-      for (int c = 0; c < 8; ++c) {
-        uint4 pk;
-        pk.x = pack_bf16(v[8 * c + 0] * a.c.scale, v[8 * c + 1] * a.c.scale);
-        pk.y = pack_bf16(v[8 * c + 2] * a.c.scale, v[8 * c + 3] * a.c.scale);
-        pk.z = pack_bf16(v[8 * c + 4] * a.c.scale, v[8 * c + 5] * a.c.scale);
-        pk.w = pack_bf16(v[8 * c + 6] * a.c.scale, v[8 * c + 7] * a.c.scale);
-        dst[c] = pk;
-      }
-    }
-    tmem_ld64(t_dv + lane_off, v);
+    if (row < T) store_half_row_global(base + dim, v, a.c.scale);
+    tmem_ld_32x32(t_dv + 32 * half + lane_off, v);
     tc_wait_ld();
-    if (row < T) {
-      uint4* dst = reinterpret_cast<uint4*>(base + 2 * dim);
-#pragma unroll
-      for (int c = 0; c < 8; ++c) {
-        uint4 pk;
-        pk.x = pack_bf16(v[8 * c + 0], v[8 * c + 1]);
-        pk.y = pack_bf16(v[8 * c + 2], v[8 * c + 3]);
-        pk.z = pack_bf16(v[8 * c + 4], v[8 * c + 5]);
-        pk.w = pack_bf16(v[8 * c + 6], v[8 * c + 7]);
-        dst[c] = pk;
-      }
-    }
+    if (row < T) store_half_row_global(base + 2 * dim, v, 1.0f);
   }
   tc_fence_before();
   __syncthreads();
@@ -680,9 +694,9 @@ int mhsa_bwd(const gvk_mhsa_bwd_params* p, cudaStream_t stream) {
   a.ld_dqkv = p->ld_dqkv;
   a.fd = fa_desc();
   dim3 grid((p->T + 127) / 128, p->B * p->H);
-  mhsa_bwd_dq_sm100_kernel<<<grid, kFaThreads, kDqSmem, stream>>>(tq128, tq64, tdo128, a);
+  mhsa_bwd_dq_sm100_kernel<<<grid, kBwdThreads, kDqSmem, stream>>>(tq128, tq64, tdo128, a);
   GVK_CHECK_LAUNCH("mhsa_bwd_dq_sm100");
-  mhsa_bwd_dkv_sm100_kernel<<<grid, kFaThreads, kDkvSmem, stream>>>(tq128, tq64, tdo64, a);
+  mhsa_bwd_dkv_sm100_kernel<<<grid, kBwdThreads, kDkvSmem, stream>>>(tq128, tq64, tdo64, a);
   GVK_CHECK_LAUNCH("mhsa_bwd_dkv_sm100");
   return GVK_OK;
 }
