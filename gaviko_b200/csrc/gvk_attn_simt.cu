@@ -94,6 +94,24 @@ __device__ __forceinline__ void axpy_row(float a, const __nv_bfloat16* p, float 
     acc[c] = fmaf(a, x.x, acc[c]); acc[c + 1] = fmaf(a, x.y, acc[c + 1]); acc[c + 2] = fmaf(a, y.x, acc[c + 2]); acc[c + 3] = fmaf(a, y.y, acc[c + 3]);
   }
 }
+// Halving exchange (see gvk_rowops.cu): sums N per-lane partials across the warp with N - N/32 shuffles instead of 5 N.
+// N = 32: lane L ends with the total of v[L] in v[0];  N = 64: totals of v[2L], v[2L+1] in v[0], v[1].
+template <int N>
+__device__ __forceinline__ void reduce_half_step(float* v, int lane, int o) {
+  const bool upper = (lane & o) != 0;
+#pragma unroll
+  for (int k = 0; k < N; ++k) {
+    const float keep = upper ? v[k + N] : v[k];
+    const float send = upper ? v[k] : v[k + N];
+    v[k] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+  }
+}
+__device__ __forceinline__ void warp_reduce_scatter32(float (&v)[32], int lane) {
+  reduce_half_step<16>(v, lane, 16); reduce_half_step<8>(v, lane, 8); reduce_half_step<4>(v, lane, 4); reduce_half_step<2>(v, lane, 2); reduce_half_step<1>(v, lane, 1);
+}
+__device__ __forceinline__ void warp_reduce_scatter64(float (&v)[64], int lane) {
+  reduce_half_step<32>(v, lane, 16); reduce_half_step<16>(v, lane, 8); reduce_half_step<8>(v, lane, 4); reduce_half_step<4>(v, lane, 2); reduce_half_step<2>(v, lane, 1);
+}
 __device__ __forceinline__ void store_elem(float* p, float v) { *p = v; }
 __device__ __forceinline__ void store_elem(__nv_bfloat16* p, float v) { *p = __float2bfloat16_rn(v); }
 
@@ -153,10 +171,18 @@ __global__ void __launch_bounds__(kAttnWarps * 32) attn_fwd_kernel(gvk_attn_fwd_
   l = warp_sum(l * corr);
   const float inv_l = 1.0f / l;
   T* orow = reinterpret_cast<T*>(p.out) + ((size_t)b * p.T + i) * p.ld_out + h * D;
+  if constexpr (D <= 32) {
+    float v[32];
 #pragma unroll
-  for (int c = 0; c < D; ++c) {
-    const float v = warp_sum(acc[c] * corr) * inv_l;
-    if (lane == (c & 31)) store_elem(orow + c, v);
+    for (int c = 0; c < 32; ++c) v[c] = c < D ? acc[c] * corr : 0.f;
+    warp_reduce_scatter32(v, lane);
+    if (lane < D) store_elem(orow + lane, v[0] * inv_l);
+  } else {
+#pragma unroll
+    for (int c = 0; c < D; ++c) {
+      const float v = warp_sum(acc[c] * corr) * inv_l;
+      if (lane == (c & 31)) store_elem(orow + c, v);
+    }
   }
   if (lane == 0) p.lse[idx] = M + __logf(l);
 }
@@ -207,10 +233,18 @@ __global__ void __launch_bounds__(kAttnWarps * 32) attn_bwd_q_kernel(gvk_attn_bw
     axpy_row<D>(ds, kr, dq);
   }
   T* drow = reinterpret_cast<T*>(bp.dqkv) + ((size_t)b * p.T + i) * bp.ld_dqkv + h * D + p.q_off;
+  if constexpr (D <= 32) {
+    float v[32];
 #pragma unroll
-  for (int c = 0; c < D; ++c) {
-    const float v = warp_sum(dq[c]) * p.scale;
-    if (lane == (c & 31)) store_elem(drow + c, v);
+    for (int c = 0; c < 32; ++c) v[c] = c < D ? dq[c] : 0.f;
+    warp_reduce_scatter32(v, lane);
+    if (lane < D) store_elem(drow + lane, v[0] * p.scale);
+  } else {
+#pragma unroll
+    for (int c = 0; c < D; ++c) {
+      const float v = warp_sum(dq[c]) * p.scale;
+      if (lane == (c & 31)) store_elem(drow + c, v);
+    }
   }
   if (lane == 0) bp.delta[idx] = delta;
 }
@@ -219,7 +253,6 @@ __global__ void __launch_bounds__(kAttnWarps * 32) attn_bwd_q_kernel(gvk_attn_bw
 template <int D, typename T>
 __global__ void __launch_bounds__(kAttnWarps * 32) attn_bwd_kv_kernel(gvk_attn_bwd_params bp) {
   const gvk_attn_fwd_params& p = bp.f;
-  __shared__ float skv[kAttnWarps][2][D];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long idx = (long long)blockIdx.x * kAttnWarps + warp;
   if (idx >= (long long)p.B * p.H * p.T) return;
@@ -228,13 +261,28 @@ __global__ void __launch_bounds__(kAttnWarps * 32) attn_bwd_kv_kernel(gvk_attn_b
   const int h = bh % p.H, b = bh / p.H;
   const T* base = reinterpret_cast<const T*>(p.qkv) + (size_t)b * p.T * p.ld + h * D;
   const T* dbase = reinterpret_cast<const T*>(bp.dout) + (size_t)b * p.T * bp.ld_dout + h * D;
-  for (int c = lane; c < D; c += 32) {
-    skv[warp][0][c] = ld_as_float(base + (size_t)j * p.ld + p.k_off + c) * p.scale;
-    skv[warp][1][c] = ld_as_float(base + (size_t)j * p.ld + p.v_off + c);
+  // this key's (pre-scaled) k and v rows, the same in every lane: registers for the 20/32-wide latents, shared memory for D = 64
+  constexpr int DR = D <= 32 ? D : 1;
+  __shared__ float skv[D <= 32 ? 1 : kAttnWarps][2][D <= 32 ? 1 : D];
+  float ks_r[DR], vs_r[DR];
+  const float* ks;
+  const float* vs;
+  if constexpr (D <= 32) {
+    load_vec<D>(base + (size_t)j * p.ld + p.k_off, ks_r);
+    load_vec<D>(base + (size_t)j * p.ld + p.v_off, vs_r);
+#pragma unroll
+    for (int c = 0; c < D; ++c) ks_r[c] *= p.scale;
+    ks = ks_r;
+    vs = vs_r;
+  } else {
+    for (int c = lane; c < D; c += 32) {
+      skv[warp][0][c] = ld_as_float(base + (size_t)j * p.ld + p.k_off + c) * p.scale;
+      skv[warp][1][c] = ld_as_float(base + (size_t)j * p.ld + p.v_off + c);
+    }
+    __syncwarp();
+    ks = skv[warp][0];
+    vs = skv[warp][1];
   }
-  __syncwarp();
-  const float* ks = skv[warp][0];
-  const float* vs = skv[warp][1];
   const bool windowed = p.win_d > 0;
   Box box;
   int count = p.T;
@@ -271,13 +319,27 @@ __global__ void __launch_bounds__(kAttnWarps * 32) attn_bwd_kv_kernel(gvk_attn_b
     axpy_row<D>(ds, qr, dk);
   }
   T* drow = reinterpret_cast<T*>(bp.dqkv) + ((size_t)b * p.T + j) * bp.ld_dqkv + h * D;
+  if constexpr (D <= 32) {
+    float v[64];           // interleaved so that lane c ends with dk[c], dv[c]
 #pragma unroll
-  for (int c = 0; c < D; ++c) {
-    const float a = warp_sum(dk[c]) * p.scale;
-    const float v = warp_sum(dv[c]);
-    if (lane == (c & 31)) {
-      store_elem(drow + p.k_off + c, a);
-      store_elem(drow + p.v_off + c, v);
+    for (int c = 0; c < 32; ++c) {
+      v[2 * c] = c < D ? dk[c] : 0.f;
+      v[2 * c + 1] = c < D ? dv[c] : 0.f;
+    }
+    warp_reduce_scatter64(v, lane);
+    if (lane < D) {
+      store_elem(drow + p.k_off + lane, v[0] * p.scale);
+      store_elem(drow + p.v_off + lane, v[1]);
+    }
+  } else {
+#pragma unroll
+    for (int c = 0; c < D; ++c) {
+      const float a = warp_sum(dk[c]) * p.scale;
+      const float v = warp_sum(dv[c]);
+      if (lane == (c & 31)) {
+        store_elem(drow + p.k_off + c, a);
+        store_elem(drow + p.v_off + c, v);
+      }
     }
   }
 }
