@@ -74,3 +74,17 @@ def golden_labels(batch: int, num_classes: int = 5, seed: int = 1234):
     g = torch.Generator(device='cpu')
     g.manual_seed(seed)
     return torch.randint(0, num_classes, (batch,), generator=g, dtype=torch.int64)
+
+
+def golden_eval_volume(seed: int, frames: int, height: int, width: int):
+    """One structured synthetic volume for the argmax-identity eval set: a smooth random field (trilinear upsampling of a coarse
+    6x8x8 lattice) with per-volume contrast, offset and noise level, clipped to [0, 1].  Unlike ``golden_volume`` (i.i.d. uniform
+    voxels, which all look alike to the network) these spread the logits over several classes."""
+    import torch.nn.functional as F
+    g = torch.Generator(device='cpu')
+    g.manual_seed(seed)
+    coarse = torch.randn(1, 1, 6, 8, 8, generator=g)
+    field = F.interpolate(coarse, size=(frames, height, width), mode='trilinear', align_corners=True)
+    contrast, offset, noise = torch.rand(3, generator=g).tolist()
+    v = 0.5 + (0.15 + 0.6 * contrast) * field + (offset - 0.5) * 0.6 + (0.02 + 0.2 * noise) * torch.randn(field.shape, generator=g)
+    return v.clamp_(0.0, 1.0)

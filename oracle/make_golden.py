@@ -14,7 +14,7 @@ import torch
 
 from . import refload
 from .cases import GAVIKO_CASES, VARIANT_CASES
-from .golden_fill import golden_fill, golden_labels, golden_volume
+from .golden_fill import golden_eval_volume, golden_fill, golden_labels, golden_volume
 
 OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'tests', 'golden')
 
@@ -130,6 +130,23 @@ def window_masks(ref):
     np.savez_compressed(os.path.join(OUT, 'window_masks.npz'), **out)
 
 
+def eval_set(ref, n=256):
+    """Logits of the reference on an "eval set" of n seeded volumes (full GAViKO shape, ViT-T): the GPU test checks identical argmax."""
+    kw, _ = GAVIKO_CASES['gaviko_t16_full']
+    model = ref.Gaviko(**kw)
+    golden_fill(model, seed=0)
+    model.eval()
+    out = []
+    with torch.no_grad():
+        for s0 in range(0, n, 8):
+            img = torch.cat([golden_eval_volume(10_000 + s, kw['frames'], kw['image_size'], kw['image_size']) for s in range(s0, min(n, s0 + 8))])
+            out.append(model(img))
+    logits = torch.cat(out).numpy()
+    top2 = np.sort(logits, 1)[:, -2:]
+    print('eval set: min top-2 margin', float((top2[:, 1] - top2[:, 0]).min()), 'class histogram', np.bincount(logits.argmax(1), minlength=5))
+    np.savez_compressed(os.path.join(OUT, 'gaviko_t16_full_eval256.npz'), logits=logits, seeds=np.arange(n) + 10_000)
+
+
 def main():
     torch.manual_seed(0)
     torch.set_num_threads(os.cpu_count())
@@ -140,6 +157,7 @@ def main():
     try:
         focal_known_answers(ref)
         window_masks(ref)
+        eval_set(ref)
         for name, (kw, batch) in GAVIKO_CASES.items():
             run_case(ref, ref.Gaviko(**kw), kw, batch, name, bf16_floor=True)
         for name, (method, kw, batch) in VARIANT_CASES.items():

@@ -131,3 +131,60 @@ def test_flat_adam_sink_and_step_match_torch():
         for (n, pa), (_, pb) in zip(ma.named_parameters(), mb.named_parameters()):
             if pa.requires_grad:
                 assert torch.allclose(pa, pb, rtol=1e-5, atol=2e-7), (step, n, (pa - pb).abs().max().item())
+
+
+@pytest.mark.parametrize('mode,margin', [('fp32', 1e-3), ('bf16', 5e-2)])
+def test_eval_set_argmax_identical(mode, margin):
+    """North star: identical argmax predictions on the eval set.  256 structured synthetic volumes (oracle.golden_fill.golden_eval_volume) run
+    through the reference (golden logits from oracle/make_golden.py) and through the CUDA path.  With random-init weights the raw argmax is the
+    same class for every volume, so the test also compares the argmax of the logits centred on the reference's per-class means — the part that
+    depends on the input — for every volume whose reference top-2 margin there exceeds `margin`."""
+    import numpy as np
+    from oracle.golden_fill import golden_eval_volume
+    g = load_golden('gaviko_t16_full_eval256')
+    ref = g['logits']
+    kw, _ = GAVIKO_CASES['gaviko_t16_full']
+    model = Gaviko(**kw, compute_dtype=mode)
+    golden_fill(model, seed=0)
+    model = model.cuda()
+    model.eval()
+    outs = []
+    with torch.no_grad():
+        for s0 in range(0, len(ref), 32):
+            img = torch.cat([golden_eval_volume(int(s), kw['frames'], kw['image_size'], kw['image_size']) for s in g['seeds'][s0:s0 + 32]]).cuda()
+            outs.append(model(img).float().cpu())
+    got = torch.cat(outs).numpy()
+    assert (got.argmax(1) == ref.argmax(1)).all()
+    mean = ref.mean(0)
+    cr, cg = ref - mean, got - mean
+    top2 = np.sort(cr, 1)[:, -2:]
+    decided = (top2[:, 1] - top2[:, 0]) > margin
+    assert decided.mean() > 0.5
+    assert (cg.argmax(1)[decided] == cr.argmax(1)[decided]).all(), int((cg.argmax(1)[decided] != cr.argmax(1)[decided]).sum())
+    print(f'{mode}: max |logit diff| {np.abs(got - ref).max():.2e}; centred argmax compared on {int(decided.sum())} of {len(ref)} volumes')
+
+
+def test_trainable_only_checkpoint_roundtrip(tmp_path):
+    """Checkpoint contract of reference train.py:161-167,478-483 and eval.py:87-92: save {k: v for k in tuning_params}, load it with
+    strict=False over a freshly built model holding the same frozen backbone, get identical logits."""
+    ma, img, y = _build('gaviko_t16_small', 'fp32')
+    tuning = [n for n, p in ma.named_parameters() if p.requires_grad]
+    opt = torch.optim.Adam([p for p in ma.parameters() if p.requires_grad], lr=1e-2)
+    for _ in range(2):                                   # move the trainables away from their initial values
+        opt.zero_grad()
+        CrossEntropyLoss()(ma(img), y).backward()
+        torch.nn.utils.clip_grad_norm_(ma.parameters(), 1.0)
+        opt.step()
+    ckpt = {k: v for k, v in ma.state_dict().items() if k in tuning}
+    assert sorted(ckpt) == sorted(tuning)
+    path = tmp_path / 'gaviko_vit-t16_best_model.pt'
+    torch.save(ckpt, path)
+    mb, _, _ = _build('gaviko_t16_small', 'fp32')        # same frozen backbone (golden_fill), initial trainables
+    with torch.no_grad():
+        before = mb(img)
+        want = ma(img)
+    assert not torch.allclose(before, want, atol=1e-4)
+    missing, unexpected = mb.load_state_dict(torch.load(path), strict=False)
+    assert not unexpected and all(k not in tuning for k in missing)
+    with torch.no_grad():
+        assert torch.equal(mb(img), want)

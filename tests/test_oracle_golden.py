@@ -74,3 +74,18 @@ def test_window_mask_formula():
         assert np.array_equal(np.packbits(allow.numpy()), g[f'allow{i}'])
     a = O.window_allow((10, 10, 10), (6, 6, 6))
     assert int(a.sum()) == 132651 and int(a.sum(1).min()) == 27 and int(a.sum(1).max()) == 216
+
+
+def test_eval_set_oracle_matches_reference():
+    """The eval-set golden (reference logits of 256 structured volumes, eval mode) against the oracle on a few of its volumes."""
+    from oracle.golden_fill import golden_eval_volume
+    g = load_golden('gaviko_t16_full_eval256')
+    kw, _ = GAVIKO_CASES['gaviko_t16_full']
+    sd = sd_from_golden(load_golden('gaviko_t16_full'))
+    pick = [0, 101, 255]
+    img = torch.cat([golden_eval_volume(int(g['seeds'][i]), kw['frames'], kw['image_size'], kw['image_size']) for i in pick])
+    with torch.no_grad():
+        logits = O.gaviko_forward(sd, img, backbone=kw['backbone'], num_prompts=kw['num_prompts'], frame_patch_size=kw['frame_patch_size'],
+                                  image_patch_size=kw['image_patch_size'], local_k=kw['local_k'], DHW=kw['DHW'], share_factor=kw['share_factor'])
+    assert rel_l2(logits, g['logits'][pick]) < TOL
+    assert (logits.argmax(1).numpy() == g['logits'][pick].argmax(1)).all()
