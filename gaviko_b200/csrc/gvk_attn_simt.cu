@@ -377,6 +377,7 @@ int attn_simt_fwd(const gvk_attn_fwd_params* p, cudaStream_t stream) {
   GVK_CHECK_ARG(p, "gvk_attn_simt_fwd: null params");
   int st = check_attn(*p, "gvk_attn_simt_fwd");
   if (st != GVK_OK) return st;
+  if (p->precision == GVK_PREC_TF32 && attn_win_tc_supported(p)) return attn_win_tc_fwd(p, stream);
   GVK_ATTN_DISPATCH(*p, attn_fwd_kernel, *p);
   GVK_CHECK_LAUNCH("attn_simt_fwd");
   return GVK_OK;
@@ -387,6 +388,7 @@ int attn_simt_bwd(const gvk_attn_bwd_params* bp, cudaStream_t stream) {
   int st = check_attn(bp->f, "gvk_attn_simt_bwd");
   if (st != GVK_OK) return st;
   GVK_CHECK_ARG(bp->ld_dout % 4 == 0 && bp->ld_dqkv % 4 == 0, "gvk_attn_simt_bwd: ld must be multiples of 4");
+  if (bp->f.precision == GVK_PREC_TF32 && attn_win_tc_supported(&bp->f)) return attn_win_tc_bwd(bp, stream);
   GVK_ATTN_DISPATCH(bp->f, attn_bwd_q_kernel, *bp);
   GVK_CHECK_LAUNCH("attn_simt_bwd_q");
   GVK_ATTN_DISPATCH(bp->f, attn_bwd_kv_kernel, *bp);

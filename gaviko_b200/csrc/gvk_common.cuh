@@ -60,6 +60,9 @@ int ssf_bwd(const gvk_ssf_bwd_params* p, cudaStream_t stream);
 int dropout(const gvk_dropout_params* p, cudaStream_t stream);
 int attn_simt_fwd(const gvk_attn_fwd_params* p, cudaStream_t stream);
 int attn_simt_bwd(const gvk_attn_bwd_params* p, cudaStream_t stream);
+bool attn_win_tc_supported(const gvk_attn_fwd_params* p);
+int attn_win_tc_fwd(const gvk_attn_fwd_params* p, cudaStream_t stream);
+int attn_win_tc_bwd(const gvk_attn_bwd_params* p, cudaStream_t stream);
 int patch_gather(const float* img, int B, int C, int D, int H, int W, int fp, int ps, void* patches, int out_dtype, cudaStream_t stream);
 int fill_rows(const float* a, const float* b, int R, int dim, float* out, int ld_out, int out_batch_rows, int out_row_offset, int B, cudaStream_t stream);
 int batch_rowsum(const float* x, int ldx, int batch_rows, int row_offset, int R, int dim, int B, float* out, int accumulate, cudaStream_t stream);
@@ -284,6 +287,21 @@ __device__ __forceinline__ void st_dyn(void* base, size_t idx, int dtype, float 
     reinterpret_cast<float*>(base)[idx] = v;
   else
     reinterpret_cast<__nv_bfloat16*>(base)[idx] = __float2bfloat16_rn(v);
+}
+
+// tf32 mma.sync helpers (rank-r side paths and window attention in the bf16 compute mode)
+__device__ __forceinline__ uint32_t f2tf32(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ float tf32_round(float x) { return __uint_as_float(f2tf32(x)); }
+// D(16x8) += A(16x8, row) * B(8x8, col).  lane = 4 g + t:  a0 (g, t) a1 (g+8, t) a2 (g, t+4) a3 (g+8, t+4);  b0 (k=t, n=g) b1 (k=t+4, n=g);
+// d0 (g, 2t) d1 (g, 2t+1) d2 (g+8, 2t) d3 (g+8, 2t+1).
+__device__ __forceinline__ void mma_tf32(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+               : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
 }
 
 // Philox4x32-10 (counter-based RNG for replayable dropout masks).

@@ -224,7 +224,7 @@ class GavikoEngine:
             d = ops.rowproj_down(loc, La['wd'], La['bd'], ln=(La['ln_w'], La['ln_b']), w2=La['wqkv'], prec=pr)
             seed_a, seed_p = self._seed(i, 1), self._seed(i, 2)
             ctx_l, lse_l = ops.attn_simt_fwd(d['z2'], B, N, 1, r_l, q_off=0, k_off=r_l, v_off=2 * r_l, scale=dim ** -0.5,
-                                             window=c['local_k'], grid=c['DHW'], drop_p=drop_attn, seed=seed_a)
+                                             window=c['local_k'], grid=c['DHW'], drop_p=drop_attn, seed=seed_a, prec=pr)
             loc_new = ops.rowproj_up(ctx_l, La['wu'], La['bu'], res=loc, drop_p=drop_proj, seed=seed_p, prec=pr)
             # ---- frozen MHSA (model/vision_transformer.py:60-72, residual gaviko.py:302)
             h1, mean1, rstd1 = ops.layernorm_fwd(g, Lw['ln1_w'], Lw['ln1_b'], out_dtype=cdt, save_stats=save)
@@ -331,7 +331,7 @@ class GavikoEngine:
             dctx = ops.rowproj_down(dLoc, La['wu'], transposed=True, drop_p=ctx['drop_proj'], seed=st['seed_p'], prec=pr)['z']
             ops.skinny_wgrad(st['ctx_l'], dLoc, dw=gL['wu'], dw_layout='dr', dx_colsum=gL['bu'], drop_p=ctx['drop_proj'], seed=st['seed_p'], prec=pr)
             dqkv_l = ops.attn_simt_bwd(st['qkv_l'], st['ctx_l'], st['lse_l'], dctx, B, N, 1, r_l, q_off=0, k_off=r_l, v_off=2 * r_l, scale=dim ** -0.5,
-                                       window=c['local_k'], grid=c['DHW'], drop_p=ctx['drop_attn'], seed=st['seed_a'])
+                                       window=c['local_k'], grid=c['DHW'], drop_p=ctx['drop_attn'], seed=st['seed_a'], prec=pr)
             ops.small_wgrad(dqkv_l, st['z'], gL['wqkv'])
             dz = ops.small_matmul(dqkv_l, La['wqkv'])
             ops.skinny_wgrad(dz, st['loc_in'], dw=gL['wd'], dw_layout='rd', da_colsum=gL['bd'], ln=(La['ln_w'], La['ln_b'], st['mean_l'], st['rstd_l']), prec=pr)

@@ -273,29 +273,30 @@ def dropout(x, drop_p, seed, *, res=None, out=None, out_dtype=None, offset=0):
 
 
 # ---------------------------------------------------------------------------------------------- attention (SIMT)
-def _attn_params(qkv, B, T, H, D, q_off, k_off, v_off, scale, window, grid, drop_p, seed, offset, out, lse):
+def _attn_params(qkv, B, T, H, D, q_off, k_off, v_off, scale, window, grid, drop_p, seed, offset, out, lse, prec=PREC_FP32):
     f = S['gvk_attn_fwd_params']()
-    _set(f, qkv=qkv, dtype=L.dtype_tag(qkv.dtype), ld=_ld(qkv), q_off=q_off, k_off=k_off, v_off=v_off, B=B, T=T, H=H, D=D, scale=scale,
+    _set(f, precision=PREC_FP32 if 'attn' in _TF32_OFF else prec, qkv=qkv, dtype=L.dtype_tag(qkv.dtype), ld=_ld(qkv), q_off=q_off, k_off=k_off, v_off=v_off, B=B, T=T, H=H, D=D, scale=scale,
          drop_p=drop_p, seed=seed, offset=offset, out=out, ld_out=_ld(out), lse=L.fptr(lse))
     if window is not None:
         _set(f, win_d=window[0], win_h=window[1], win_w=window[2], grid_d=grid[0], grid_h=grid[1], grid_w=grid[2])
     return f
 
 
-def attn_simt_fwd(qkv, B, T, H, D, *, q_off, k_off, v_off, scale, window=None, grid=None, drop_p=0.0, seed=0, offset=0):
+def attn_simt_fwd(qkv, B, T, H, D, *, q_off, k_off, v_off, scale, window=None, grid=None, drop_p=0.0, seed=0, offset=0, prec=PREC_FP32):
     out = torch.empty((B * T, H * D), device=qkv.device, dtype=qkv.dtype)
     lse = torch.empty(B * H * T, device=qkv.device, dtype=torch.float32)
-    f = _attn_params(qkv, B, T, H, D, q_off, k_off, v_off, scale, window, grid, drop_p, seed, offset, out, lse)
+    f = _attn_params(qkv, B, T, H, D, q_off, k_off, v_off, scale, window, grid, drop_p, seed, offset, out, lse, prec)
     L.call('gvk_attn_simt_fwd', C.byref(f), L.stream())
     return out, lse
 
 
-def attn_simt_bwd(qkv, out, lse, dout, B, T, H, D, *, q_off, k_off, v_off, scale, window=None, grid=None, drop_p=0.0, seed=0, offset=0, dqkv=None):
+def attn_simt_bwd(qkv, out, lse, dout, B, T, H, D, *, q_off, k_off, v_off, scale, window=None, grid=None, drop_p=0.0, seed=0, offset=0, dqkv=None,
+                  prec=PREC_FP32):
     if dqkv is None:
         dqkv = torch.empty_like(qkv)
     delta = torch.empty_like(lse)
     p = S['gvk_attn_bwd_params']()
-    p.f = _attn_params(qkv, B, T, H, D, q_off, k_off, v_off, scale, window, grid, drop_p, seed, offset, out, lse)
+    p.f = _attn_params(qkv, B, T, H, D, q_off, k_off, v_off, scale, window, grid, drop_p, seed, offset, out, lse, prec)
     assert dout.dtype == qkv.dtype and dqkv.dtype == qkv.dtype
     _set(p, dout=dout, ld_dout=_ld(dout), delta=delta, dqkv=dqkv, ld_dqkv=_ld(dqkv))
     L.call('gvk_attn_simt_bwd', C.byref(p), L.stream())

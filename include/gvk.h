@@ -234,6 +234,10 @@ int gvk_dropout(const gvk_dropout_params* p, gvk_stream_t stream);
  *   (2) the frozen MHSA core in fp32 mode (model/vision_transformer.py:65-70): D = 64, dense.
  * Layout: rows are tokens (B*T rows); head h of q / k / v lives at columns q_off / k_off / v_off + h*D of `qkv`.
  * Dropout element index of probability (b, h, i, j) is ((b*H + h)*T + i)*T + j  (philox(seed, offset + index)).
+ * precision = GVK_PREC_TF32 (bf16 compute mode) runs case (1) on the tensor cores instead: mma.sync m16n8k8 with tf32 operands,
+ * fp32 accumulation and softmax, K / V rows of the chunk's window staged once in shared memory (fp32 rows, D in {20, 32},
+ * grid_d + grid_h + grid_w <= 31, the staged window must fit in shared memory; other problems silently use the exact path).  Its dropout
+ * mask is drawn per aligned 2x2 (query, key) block, so forward and backward must use the same precision.
  * ------------------------------------------------------------------------------------------------------------------ */
 typedef struct {
   const void* qkv; int dtype; int ld;
@@ -245,6 +249,7 @@ typedef struct {
   float drop_p; uint64_t seed; uint64_t offset;
   void* out; int ld_out;        /* [B*T, H*D], same dtype as qkv */
   float* lse;                   /* [B*H*T] log-sum-exp of the scaled scores (saved for backward) */
+  int precision;                /* GVK_PREC_FP32 (exact, default) or GVK_PREC_TF32 (windowed case only) */
 } gvk_attn_fwd_params;
 int gvk_attn_simt_fwd(const gvk_attn_fwd_params* p, gvk_stream_t stream);
 

@@ -189,46 +189,79 @@ def test_attn_simt_dense(dt):
     close(dqkv, qr.grad, 5e-2 if dt == torch.bfloat16 else 2e-5)
 
 
-@pytest.mark.parametrize('dhw,k', [((10, 10, 10), (6, 6, 6)), ((4, 4, 4), (3, 2, 2)), ((5, 4, 3), (5, 4, 2))])
-def test_attn_simt_window(dhw, k):
+@pytest.mark.parametrize('prec', [ops.PREC_FP32, ops.PREC_TF32])
+@pytest.mark.parametrize('dhw,k,r', [((10, 10, 10), (6, 6, 6), 20), ((4, 4, 4), (3, 2, 2), 20), ((5, 4, 3), (5, 4, 2), 20), ((3, 5, 7), (3, 6, 6), 20),
+                                     ((10, 10, 10), (3, 6, 6), 32), ((2, 13, 13), (1, 4, 5), 20)])
+def test_attn_simt_window(dhw, k, r, prec):
+    """exact SIMT form and the tf32 tensor-core form (odd planes, chunks of several planes, planes larger than a chunk, r = 32)"""
     torch.manual_seed(6)
-    B, r = 2, 20
+    B = 2
     N = dhw[0] * dhw[1] * dhw[2]
     qkv = torch.randn(B * N, 3 * r, device=DEV)
     allow = O.window_allow(dhw, k)
-    o, lse = ops.attn_simt_fwd(qkv, B, N, 1, r, q_off=0, k_off=r, v_off=2 * r, scale=0.3, window=k, grid=dhw)
+    tol = 1e-5 if prec == ops.PREC_FP32 else 2e-3
+    kw = dict(q_off=0, k_off=r, v_off=2 * r, scale=0.3, window=k, grid=dhw, prec=prec)
+    o, lse = ops.attn_simt_fwd(qkv, B, N, 1, r, **kw)
     qr = qkv.double().requires_grad_(True)
     ref = _dense_attn_ref(qr, B, N, 1, r, 0.3, allow)
-    close(o, ref.detach(), 1e-5)
+    close(o, ref.detach(), tol)
+    s = torch.einsum('bid,bjd->bij', qr.detach().view(B, N, 3 * r)[..., :r], qr.detach().view(B, N, 3 * r)[..., r:2 * r]) * 0.3
+    close(lse, torch.logsumexp(s.masked_fill(~allow.to(DEV), float('-inf')), -1).reshape(-1), tol)
     do = torch.randn(B * N, r, device=DEV)
     ref.backward(do.double())
-    dqkv = ops.attn_simt_bwd(qkv, o, lse, do, B, N, 1, r, q_off=0, k_off=r, v_off=2 * r, scale=0.3, window=k, grid=dhw)
-    close(dqkv, qr.grad, 2e-5)
+    dqkv = ops.attn_simt_bwd(qkv, o, lse, do, B, N, 1, r, **kw)
+    close(dqkv, qr.grad, 2 * tol)
+    for blk in range(3):
+        close(dqkv[:, blk * r:(blk + 1) * r], qr.grad[:, blk * r:(blk + 1) * r], 2 * tol)
 
 
-def test_attn_window_dropout_statistics_and_replay():
+@pytest.mark.parametrize('prec', [ops.PREC_FP32, ops.PREC_TF32])
+def test_attn_window_dropout_statistics_and_replay(prec):
     torch.manual_seed(7)
     B, r, dhw, k, p = 2, 20, (10, 10, 10), (6, 6, 6), 0.2
     N = 1000
     qkv = torch.randn(B * N, 3 * r, device=DEV)
     qkv[:, 2 * r:] = 1.0                      # v == 1  =>  out_i = sum_j p_ij m_ij / (1-p), expectation 1
-    o, lse = ops.attn_simt_fwd(qkv, B, N, 1, r, q_off=0, k_off=r, v_off=2 * r, scale=0.05, window=k, grid=dhw, drop_p=p, seed=99)
+    o, lse = ops.attn_simt_fwd(qkv, B, N, 1, r, q_off=0, k_off=r, v_off=2 * r, scale=0.05, window=k, grid=dhw, drop_p=p, seed=99, prec=prec)
     assert abs(o.mean().item() - 1.0) < 0.01
     assert o.std().item() > 0.01              # masks are actually applied
-    o2, _ = ops.attn_simt_fwd(qkv, B, N, 1, r, q_off=0, k_off=r, v_off=2 * r, scale=0.05, window=k, grid=dhw, drop_p=p, seed=99)
+    o2, _ = ops.attn_simt_fwd(qkv, B, N, 1, r, q_off=0, k_off=r, v_off=2 * r, scale=0.05, window=k, grid=dhw, drop_p=p, seed=99, prec=prec)
     assert torch.equal(o, o2)                 # replayable
-    # finite-difference check of the backward under a fixed mask
+
+
+@pytest.mark.parametrize('prec', [ops.PREC_FP32, ops.PREC_TF32])
+def test_attn_window_dropout_mask_is_the_same_in_forward_and_backward(prec):
+    """Recover the dropout mask from the forward (q = k = 0 gives uniform probabilities, V = indicator columns), then check the forward and
+    every gradient block against autograd through a dense reference that applies that mask."""
+    torch.manual_seed(8)
+    B, r, dhw, k, p = 2, 20, (4, 5, 6), (3, 4, 4), 0.25
+    N = dhw[0] * dhw[1] * dhw[2]
+    allow = O.window_allow(dhw, k).to(DEV)
+    kw = dict(q_off=0, k_off=r, v_off=2 * r, scale=0.3, window=k, grid=dhw, drop_p=p, seed=11, offset=77, prec=prec)
+    mask = torch.zeros(B, N, N, device=DEV, dtype=torch.float64)
+    for c0 in range(0, N, r):
+        probe = torch.zeros(B, N, 3 * r, device=DEV)
+        probe[:, c0:c0 + r, 2 * r:] = torch.eye(r, device=DEV)
+        o, _ = ops.attn_simt_fwd(probe.view(B * N, 3 * r), B, N, 1, r, **kw)
+        mask[:, :, c0:c0 + r] = o.view(B, N, r).double() * allow.sum(1).double()[None, :, None] * (1 - p)
+    assert ((mask - mask.round()).abs() < 5e-3).all()
+    mask = mask.round()
+    assert set(mask.unique().tolist()) == {0.0, 1.0} and (mask[~allow.expand(B, N, N)] == 0).all()
+    keep = mask[allow.expand(B, N, N)].mean().item()
+    assert abs(keep - (1 - p)) < 0.02 and not torch.equal(mask[0], mask[1])
     qkv = torch.randn(B * N, 3 * r, device=DEV)
     do = torch.randn(B * N, r, device=DEV)
-    o, lse = ops.attn_simt_fwd(qkv, B, N, 1, r, q_off=0, k_off=r, v_off=2 * r, scale=0.2, window=k, grid=dhw, drop_p=p, seed=5)
-    dqkv = ops.attn_simt_bwd(qkv, o, lse, do, B, N, 1, r, q_off=0, k_off=r, v_off=2 * r, scale=0.2, window=k, grid=dhw, drop_p=p, seed=5)
-    dirn = torch.randn_like(qkv)
-    eps = 1e-2
-    op, _ = ops.attn_simt_fwd(qkv + eps * dirn, B, N, 1, r, q_off=0, k_off=r, v_off=2 * r, scale=0.2, window=k, grid=dhw, drop_p=p, seed=5)
-    om, _ = ops.attn_simt_fwd(qkv - eps * dirn, B, N, 1, r, q_off=0, k_off=r, v_off=2 * r, scale=0.2, window=k, grid=dhw, drop_p=p, seed=5)
-    fd = ((op.double() - om.double()) * do.double()).sum().item() / (2 * eps)
-    an = (dqkv.double() * dirn.double()).sum().item()
-    assert abs(fd - an) <= 2e-3 * max(1.0, abs(an)), (fd, an)
+    qr = qkv.double().requires_grad_(True)
+    q, kk, v = qr.view(B, N, 3, r).unbind(2)
+    s = (q @ kk.transpose(1, 2) * 0.3).masked_fill(~allow, float('-inf'))
+    ref = ((torch.softmax(s, -1) * mask / (1 - p)) @ v).reshape(B * N, r)
+    ref.backward(do.double())
+    tol = 1e-5 if prec == ops.PREC_FP32 else 2e-3
+    o, lse = ops.attn_simt_fwd(qkv, B, N, 1, r, **kw)
+    close(o, ref.detach(), tol)
+    dqkv = ops.attn_simt_bwd(qkv, o, lse, do, B, N, 1, r, **kw)
+    for blk in range(3):
+        close(dqkv[:, blk * r:(blk + 1) * r], qr.grad[:, blk * r:(blk + 1) * r], 2 * tol)
 
 
 def _fusion_sd(P, r, dim, dev):
