@@ -289,6 +289,21 @@ __device__ __forceinline__ void st_dyn(void* base, size_t idx, int dtype, float 
     reinterpret_cast<__nv_bfloat16*>(base)[idx] = __float2bfloat16_rn(v);
 }
 
+// cp.async (Ampere-style asynchronous global -> shared copies; used for small per-warp software pipelines)
+__device__ __forceinline__ void cp_async4(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+
+__device__ __forceinline__ void cp_async16_zfill(void* smem_dst, const void* gsrc, bool valid) {   // !valid: 16 zero bytes, gsrc not read
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc), "r"(valid ? 16 : 0) : "memory");
+}
+
 // tf32 mma.sync helpers (rank-r side paths and window attention in the bf16 compute mode)
 __device__ __forceinline__ uint32_t f2tf32(float x) {
   uint32_t r;
@@ -296,6 +311,9 @@ __device__ __forceinline__ uint32_t f2tf32(float x) {
   return r;
 }
 __device__ __forceinline__ float tf32_round(float x) { return __uint_as_float(f2tf32(x)); }
+// Round-to-nearest (ties away) for an MMA operand in one integer add: the tensor core ignores the low 13 mantissa bits of a tf32 operand,
+// so adding half an ulp of the 10-bit mantissa is all the rounding needs (finite inputs; the carry into the exponent is the right result).
+__device__ __forceinline__ uint32_t tf32_bits(float x) { return __float_as_uint(x) + 0x1000u; }
 // D(16x8) += A(16x8, row) * B(8x8, col).  lane = 4 g + t:  a0 (g, t) a1 (g+8, t) a2 (g, t+4) a3 (g+8, t+4);  b0 (k=t, n=g) b1 (k=t+4, n=g);
 // d0 (g, 2t) d1 (g, 2t+1) d2 (g+8, 2t) d3 (g+8, 2t+1).
 __device__ __forceinline__ void mma_tf32(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {

@@ -113,6 +113,14 @@ __device__ __forceinline__ void axpyR(float a, const float* __restrict__ row, fl
     acc[c] = fmaf(a, t.x, acc[c]); acc[c + 1] = fmaf(a, t.y, acc[c + 1]); acc[c + 2] = fmaf(a, t.z, acc[c + 2]); acc[c + 3] = fmaf(a, t.w, acc[c + 3]);
   }
 }
+template <int R>
+__device__ __forceinline__ void load_vec_f4(const float* __restrict__ row, float (&v)[R]) {
+#pragma unroll
+  for (int c = 0; c < R; c += 4) {
+    const float4 t = *reinterpret_cast<const float4*>(row + c);
+    v[c] = t.x; v[c + 1] = t.y; v[c + 2] = t.z; v[c + 3] = t.w;
+  }
+}
 // lane j holds v[j] -> every lane gets the full vector
 template <int R>
 __device__ __forceinline__ void gatherR(float v_lane, float (&v)[R]) {
@@ -277,82 +285,129 @@ __device__ __forceinline__ float single_query_attn_dq(const float* __restrict__ 
   return out;  // lane c: sum_j ds_j tok_j[c]   (caller multiplies by the softmax scale)
 }
 
-// One CTA per (b, prompt): lse and delta are known, so the key range of each of the two cross-attentions is simply split over the CTA's
-// warps (a single warp walking ~1000 keys was pure latency: 185 us for 41 MFMA) and the partial dQ vectors are summed through smem.
+// One CTA per volume.  A lane owns one prompt (its pre-scaled query, d ctx, lse and delta live in registers), a warp walks a slice of the
+// keys of one of the two cross-attentions (warps [0, W/2): global keys xl[:, 2P+2:], warps [W/2, W): local keys ll) reading each key row
+// once as a warp-wide broadcast, so dQ needs no shuffles at all; the W/2 partial dQ of a side are summed through shared memory and the
+// query-projection gradients leave the CTA as one atomicAdd per weight (B x 840 atomics per call instead of B x P x 840).
+// (History: one warp per (b, prompt) was pure latency, 185 us; one CTA per (b, prompt) with the keys split over 8 warps was 108 us for
+// 41 MFMA at B = 32 — 2 CTAs / SM by registers, 7 waves, 1.7 M contended atomics.)
+constexpr int kFusBwdWarps = 16;
 template <int R>
-__global__ void __launch_bounds__(kFusWarps * 32) fusion_bwd_prompts_kernel(gvk_fusion_bwd_params p) {
-  __shared__ float part[2][kFusWarps][32];
+struct FusBwdSmem {
+  static constexpr int kPart = kFusBwdWarps * R * 32;     // part[warp][c][prompt]
+  static constexpr int kDq = 2 * 32 * (R + 1);            // dq[side][prompt][c], scaled
+  static constexpr int kPl = 32 * (R + 1);                // pl[prompt][j]
+  static constexpr size_t kBytes = (size_t)(kPart + kDq + kPl) * sizeof(float);
+};
+template <int R>
+__global__ void __launch_bounds__(kFusBwdWarps * 32) fusion_bwd_prompts_kernel(gvk_fusion_bwd_params p) {
+  extern __shared__ __align__(16) float fus_smem[];
+  float* part = fus_smem;
+  float* s_dq = part + FusBwdSmem<R>::kPart;
+  float* s_pl = s_dq + FusBwdSmem<R>::kDq;
+  constexpr int HW = kFusBwdWarps / 2;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int idx = blockIdx.x;
-  const int b = idx / p.P, pp = idx % p.P;
-  const size_t o = ((size_t)b * p.P + pp) * R + lane;
+  const int side = warp / HW, wl = warp % HW;
+  const int b = blockIdx.x;
   const float scale = rsqrtf((float)R);
-  const float gw = p.s.gw[b], imp = p.s.imp[(size_t)b * p.P + pp];
-  const float ctx_g = lane < R ? p.s.ctx_g[o] : 0.f, ctx_l = lane < R ? p.s.ctx_l[o] : 0.f;
+  const float gw = p.s.gw[b];
   float* dxl_b = p.dxl + (size_t)b * p.T * R;
-  const float d_enh = lane < R ? dxl_b[(size_t)pp * R + lane] : 0.f;
-  const float fused = gw * ctx_g + (1.f - gw) * ctx_l;
-  const float d_imp = warp_sum(d_enh * fused);
-  const float d_fused = d_enh * imp;
-  const float d_gw = warp_sum(d_fused * (ctx_g - ctx_l));
-  const float dcg_lane = gw * d_fused, dcl_lane = (1.f - gw) * d_fused;
-  const float delta_g = warp_sum(dcg_lane * ctx_g), delta_l = warp_sum(dcl_lane * ctx_l);
-  float q[R], dctx[R];
-  {  // global attention: keys xl[:, 2P+2:]
-    const float q_lane = lane < R ? p.s.qg[o] : 0.f;
-    gatherR<R>(q_lane * scale, q);
-    gatherR<R>(dcg_lane, dctx);
-    const int n_g = p.T - 2 * p.P - 2;
-    const int per = (n_g + kFusWarps - 1) / kFusWarps;
-    part[0][warp][lane] = single_query_attn_dq<R>(p.xl + ((size_t)b * p.T + 2 * p.P + 2) * R, warp * per, min(n_g, (warp + 1) * per), q, dctx,
-                                                  p.s.lse_g[(size_t)b * p.P + pp], delta_g, lane);
-  }
-  {  // local attention: keys ll
-    const float q_lane = lane < R ? p.s.ql[o] : 0.f;
-    gatherR<R>(q_lane * scale, q);
-    gatherR<R>(dcl_lane, dctx);
-    const int per = (p.N + kFusWarps - 1) / kFusWarps;
-    part[1][warp][lane] = single_query_attn_dq<R>(p.ll + (size_t)b * p.N * R, warp * per, min(p.N, (warp + 1) * per), q, dctx, p.s.lse_l[(size_t)b * p.P + pp],
-                                                  delta_l, lane);
-  }
-  __syncthreads();   // dxl row pp was read above by every warp before warp 0 overwrites it below
-  if (warp != 0) return;
-  float* ws = p.ws + (size_t)idx * (2 * R + 4);
-  if (lane < R) {
-    ws[lane] = dcg_lane;
-    ws[R + lane] = dcl_lane;
-  }
-  if (lane == 0) {
-    ws[2 * R + 0] = delta_g;
-    ws[2 * R + 1] = delta_l;
-    ws[2 * R + 2] = d_imp;
-    ws[2 * R + 3] = d_gw;
-  }
-  const float pl_lane = lane < R ? p.s.pl[o] : 0.f;
-  float pl[R];
-  gatherR<R>(pl_lane, pl);
-  float d_pl = 0.f;  // lane j
+  const int n = side == 0 ? p.T - 2 * p.P - 2 : p.N;
+  const float* tokbase = side == 0 ? p.xl + ((size_t)b * p.T + 2 * p.P + 2) * R : p.ll + (size_t)b * p.N * R;
+  const int per = (n + HW - 1) / HW;
+  const int t0 = wl * per, t1 = min(n, t0 + per);
+  for (int pg = 0; pg < p.P; pg += 32) {
+    const int pp = pg + lane;
+    const bool valid = pp < p.P;
+    const size_t o = ((size_t)b * p.P + (valid ? pp : 0)) * R;
+    float q[R], dctx[R];
+    float lse = INFINITY, delta = 0.f;
+    {
+      float cg[R], cl[R];
+      load_vec_f4<R>(p.s.ctx_g + o, cg);
+      load_vec_f4<R>(p.s.ctx_l + o, cl);
+      load_vec_f4<R>(dxl_b + (size_t)(valid ? pp : 0) * R, dctx);   // d enh
+      const float imp = p.s.imp[(size_t)b * p.P + (valid ? pp : 0)];
+      float d_imp = 0.f, d_gw = 0.f;
 #pragma unroll
-  for (int which = 0; which < 2; ++which) {
-    float dq_lane = 0.f;
+      for (int c = 0; c < R; ++c) {
+        d_imp = fmaf(dctx[c], gw * cg[c] + (1.f - gw) * cl[c], d_imp);
+        const float d_fused = dctx[c] * imp;
+        d_gw = fmaf(d_fused, cg[c] - cl[c], d_gw);
+        dctx[c] = (side == 0 ? gw : 1.f - gw) * d_fused;
+        delta = fmaf(dctx[c], side == 0 ? cg[c] : cl[c], delta);
+      }
+      load_vec_f4<R>((side == 0 ? p.s.qg : p.s.ql) + o, q);
+      if (valid) {
+        lse = (side == 0 ? p.s.lse_g : p.s.lse_l)[(size_t)b * p.P + pp];
+        if (wl == 0) {                                                   // hand-off to the token / gate kernels
+          float* ws = p.ws + ((size_t)b * p.P + pp) * (2 * R + 4);
 #pragma unroll
-    for (int w = 0; w < kFusWarps; ++w) dq_lane += part[which][w][lane];
-    dq_lane *= scale;
+          for (int c = 0; c < R; ++c) ws[side * R + c] = dctx[c];
+          ws[2 * R + side] = delta;
+          if (side == 0) {
+            ws[2 * R + 2] = d_imp;
+            ws[2 * R + 3] = d_gw;
+            load_vec_f4<R>(p.s.pl + o, cg);
+#pragma unroll
+            for (int c = 0; c < R; ++c) s_pl[lane * (R + 1) + c] = cg[c];
+          }
+        }
+      } else if (wl == 0 && side == 0) {
+#pragma unroll
+        for (int c = 0; c < R; ++c) s_pl[lane * (R + 1) + c] = 0.f;
+      }
+#pragma unroll
+      for (int c = 0; c < R; ++c) q[c] = valid ? q[c] * scale : 0.f;
+    }
     float dq[R];
-    gatherR<R>(dq_lane, dq);
-    float* g_b = which == 0 ? p.g.bq_g : p.g.bq_l;
-    float* g_w = which == 0 ? p.g.wq_g : p.g.wq_l;
-    const float* w_q = which == 0 ? p.w.wq_g : p.w.wq_l;
-    if (lane < R) {
-      atomicAdd(g_b + lane, dq_lane);
 #pragma unroll
-      for (int j = 0; j < R; ++j) {
-        atomicAdd(g_w + lane * R + j, dq_lane * pl[j]);
-        d_pl = fmaf(w_q[j * R + lane], dq[j], d_pl);
+    for (int c = 0; c < R; ++c) dq[c] = 0.f;
+#pragma unroll(R <= 20 ? 4 : 1)
+    for (int t = t0; t < t1; ++t) {
+      float tok[R];
+      load_vec_f4<R>(tokbase + (size_t)t * R, tok);                      // the same address in every lane: one broadcast transaction
+      float sc = 0.f, da = 0.f;
+#pragma unroll
+      for (int c = 0; c < R; ++c) {
+        sc = fmaf(q[c], tok[c], sc);
+        da = fmaf(dctx[c], tok[c], da);
+      }
+      const float ds = __expf(sc - lse) * (da - delta);
+#pragma unroll
+      for (int c = 0; c < R; ++c) dq[c] = fmaf(ds, tok[c], dq[c]);
+    }
+#pragma unroll
+    for (int c = 0; c < R; ++c) part[(warp * R + c) * 32 + lane] = dq[c];
+    __syncthreads();   // also orders every warp's read of the d enh rows before they are overwritten below
+    if (wl == 0) {
+#pragma unroll
+      for (int c = 0; c < R; ++c) {
+        float v = 0.f;
+#pragma unroll
+        for (int w = 0; w < HW; ++w) v += part[((side * HW + w) * R + c) * 32 + lane];
+        s_dq[(side * 32 + lane) * (R + 1) + c] = valid ? v * scale : 0.f;
       }
     }
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < 2 * R * (R + 1); idx += blockDim.x) {   // d Wq[c][j] and (j == R) d bq[c] of both sides
+      const int sd = idx / (R * (R + 1)), c = (idx / (R + 1)) % R, j = idx % (R + 1);
+      float v = 0.f;
+      for (int k = 0; k < 32; ++k) v = fmaf(s_dq[(sd * 32 + k) * (R + 1) + c], j < R ? s_pl[k * (R + 1) + j] : 1.f, v);
+      float* dst = j < R ? (sd == 0 ? p.g.wq_g : p.g.wq_l) + c * R + j : (sd == 0 ? p.g.bq_g : p.g.bq_l) + c;
+      atomicAdd(dst, v);
+    }
+    for (int idx = threadIdx.x; idx < 32 * R; idx += blockDim.x) {            // dL/d(prompt latent) = Wq_g^T dq_g + Wq_l^T dq_l
+      const int k = idx / R, j = idx % R;
+      if (pg + k < p.P) {
+        float v = 0.f;
+#pragma unroll
+        for (int c = 0; c < R; ++c) v = fmaf(p.w.wq_g[c * R + j], s_dq[k * (R + 1) + c], fmaf(p.w.wq_l[c * R + j], s_dq[(32 + k) * (R + 1) + c], v));
+        dxl_b[(size_t)(pg + k) * R + j] = v;
+      }
+    }
+    __syncthreads();   // shared buffers are reused by the next group of 32 prompts
   }
-  if (lane < R) dxl_b[(size_t)pp * R + lane] = d_pl;  // dL/d(prompt latent p)
 }
 
 // ---- backward B: one thread per key token ------------------------------------------------------
@@ -496,7 +551,9 @@ static int fusion_fwd_launch(const gvk_fusion_fwd_params* p, cudaStream_t stream
 }
 template <int R>
 static int fusion_bwd_launch(const gvk_fusion_bwd_params* p, cudaStream_t stream) {
-  fusion_bwd_prompts_kernel<R><<<p->B * p->P, kFusWarps * 32, 0, stream>>>(*p);
+  static const int attr = cudaFuncSetAttribute(fusion_bwd_prompts_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FusBwdSmem<R>::kBytes);
+  if (attr != cudaSuccess) return cuda_status((cudaError_t)attr, "prompt_fusion_bwd (smem attribute)");
+  fusion_bwd_prompts_kernel<R><<<p->B, kFusBwdWarps * 32, FusBwdSmem<R>::kBytes, stream>>>(*p);
   GVK_CHECK_LAUNCH("prompt_fusion_bwd_prompts");
   const int nmax = std::max(p->N, p->T - 2 * p->P - 2);
   const size_t smem = ((size_t)2 * p->P * R + 2 * p->P) * sizeof(float);

@@ -433,12 +433,6 @@ mhsa_bwd_dq_sm100_kernel(const __grid_constant__ CUtensorMap tma_q128, const __g
 // =================================================================================================
 constexpr int kDkvStages = 3;
 constexpr int kDkvSmem = 2 * kTileBytes128 /*K,V*/ + 2 * kDkvStages * kTileBytes64 /*Q,dO ring*/ + 2 * kDkvStages * 64 * 4 /*lse, delta ring*/ + 128 + 1024;
-__device__ __forceinline__ void cp_async4(void* smem_dst, const void* gsrc) {
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 __global__ void __launch_bounds__(kBwdThreads, 2)
 mhsa_bwd_dkv_sm100_kernel(const __grid_constant__ CUtensorMap tma_kv128, const __grid_constant__ CUtensorMap tma_q64, const __grid_constant__ CUtensorMap tma_do64,

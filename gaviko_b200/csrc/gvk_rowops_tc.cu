@@ -446,17 +446,93 @@ int rowproj_up_tc(const gvk_rowproj_up_params* p, cudaStream_t stream) {
 // x[m0 + t + 4][.. 4 g ..] as float4 (n slot g of MMA i <-> column 32 G + 4 g + i).  Per-CTA partials go to the workspace and are
 // summed by skinny_wgrad_reduce (deterministic, same layout as the fp32 kernel).
 // =================================================================================================
+// The operand stream is software-pipelined: every warp copies its own 16-row x (32 NG)-column slice (plus the 16 latent rows and LN
+// statistics) with cp.async into a private ring of shared-memory stages, two stages (NG = 3) ahead of the MMAs, so ~100 KB per SM are in
+// flight at any time and no warp ever waits on a global load it has just issued.  Rows are padded to a stride of 32 bytes mod 128 so
+// that the float4 fragment reads (rows t / t + 4, columns 4 g) are bank-conflict free.
+template <int NG>
+struct WgPipe {
+  static constexpr int kCols = 32 * NG;
+  static constexpr int kRS = kCols + 8;            // x row stride (floats)
+  static constexpr int kAS = 40;                   // latent row stride: 8 t + g hits 32 distinct banks
+  static constexpr int kRows = 16;                 // rows per stage = two 8-row MMA k steps
+  static constexpr int kStages = NG == 3 ? 3 : 2;
+  static constexpr int kStageFloats = kRows * kRS + kRows * kAS + 2 * kRows;
+  static constexpr size_t kSmem = (size_t)kTcWarps * kStages * kStageFloats * sizeof(float);
+};
+
 template <int NG>
 __global__ void __launch_bounds__(kTcThreads, 1) tc_wgrad_kernel(gvk_skinny_wgrad_params p, int rows_per_cta, int nwarps) {
+  using L = WgPipe<NG>;
+  extern __shared__ __align__(16) float wg_smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
   if (warp >= nwarps) return;
   const int m_begin = blockIdx.x * rows_per_cta;
   const int m_end = min(p.M, m_begin + rows_per_cta);
   const int cbase = warp * 32 * NG;
-  for (int m = m_begin + lane; m < m_end; m += 32) {   // this warp's slice: 32 NG floats = NG 128-byte lines per row
-#pragma unroll
-    for (int G = 0; G < NG; ++G) prefetch_l2(p.x + (size_t)m * p.ldx + cbase + 32 * G);
+  float* ring = wg_smem + (size_t)warp * L::kStages * L::kStageFloats;
+  const bool has_ln = p.ln_gamma != nullptr;
+  // The column sum of f(x) (bias gradients) rides on the MMA: latent slot r (a padding slot when r < 32) holds 1.0 for every row, so
+  // accumulator row r is the column sum.  Only r == 32 needs explicit adds.
+  const bool cs_mma = p.dx_colsum != nullptr && p.r < 32, cs_add = p.dx_colsum != nullptr && p.r == 32;
+  // latent slots >= r are zero (never written by the copies); slot r is the ones column
+  for (int i = lane; i < L::kStages * L::kRows * L::kAS; i += 32) {
+    const int st = i / (L::kRows * L::kAS), rem = i - st * (L::kRows * L::kAS);
+    ring[st * L::kStageFloats + L::kRows * L::kRS + rem] = (cs_mma && rem % L::kAS == p.r) ? 1.f : 0.f;
   }
+  __syncwarp();
+  // per-lane copy plan, fixed for the whole kernel: chunk k of a stage is 16 bytes at (row_k, 4 c4_k)
+  constexpr int KX = L::kRows * 8 * NG / 32;
+  int xsrc[KX], xdst[KX];
+#pragma unroll
+  for (int k = 0; k < KX; ++k) {
+    const int idx = lane + 32 * k, row = idx / (8 * NG), c4 = idx - row * (8 * NG);
+    xsrc[k] = row * p.ldx + c4 * 4;
+    xdst[k] = row * L::kRS + c4 * 4;
+  }
+  const int a_chunks = p.r / 4;
+  int asrc[3], adst[3];        // 16 rows x r / 4 <= 128 chunks = 4 per lane; r <= 24 needs 3, r in (24, 32] a fourth handled below
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    const int idx = lane + 32 * k, row = idx / a_chunks, c4 = idx - row * a_chunks;
+    asrc[k] = idx < L::kRows * a_chunks ? row * p.lda + c4 * 4 : -1;
+    adst[k] = L::kRows * L::kRS + row * L::kAS + c4 * 4;
+  }
+  auto issue = [&](int step) {
+    const int mb = m_begin + step * L::kRows;
+    if (mb < m_end) {
+      float* st = ring + (step % L::kStages) * L::kStageFloats;
+      const float* xs = p.x + (size_t)mb * p.ldx + cbase;
+      const float* as_ = p.a + (size_t)mb * p.lda;
+      if (mb + L::kRows <= m_end) {
+#pragma unroll
+        for (int k = 0; k < KX; ++k) cp_async16(st + xdst[k], xs + xsrc[k]);
+#pragma unroll
+        for (int k = 0; k < 3; ++k)
+          if (asrc[k] >= 0) cp_async16(st + adst[k], as_ + asrc[k]);
+        for (int idx = lane + 96; idx < L::kRows * a_chunks; idx += 32) {
+          const int row = idx / a_chunks, c4 = idx - row * a_chunks;
+          cp_async16(st + L::kRows * L::kRS + row * L::kAS + c4 * 4, as_ + row * p.lda + c4 * 4);
+        }
+      } else {                                     // last, partial stage of this CTA: rows >= m_end are zero-filled
+        for (int idx = lane; idx < L::kRows * 8 * NG; idx += 32) {
+          const int row = idx / (8 * NG), c4 = idx - row * (8 * NG);
+          const bool ok = mb + row < m_end;
+          cp_async16_zfill(st + row * L::kRS + c4 * 4, xs + (ok ? row * p.ldx : 0) + c4 * 4, ok);
+        }
+        for (int idx = lane; idx < L::kRows * a_chunks; idx += 32) {
+          const int row = idx / a_chunks, c4 = idx - row * a_chunks;
+          const bool ok = mb + row < m_end;
+          cp_async16_zfill(st + L::kRows * L::kRS + row * L::kAS + c4 * 4, as_ + (ok ? row * p.lda : 0) + c4 * 4, ok);
+        }
+      }
+      if (has_ln) {
+        const int row = min(mb + (lane & 15), m_end - 1);
+        cp_async4(st + L::kRows * L::kRS + L::kRows * L::kAS + lane, (lane < 16 ? p.mean : p.rstd) + row);
+      }
+    }
+    cp_async_commit();
+  };
   float acc[NG][4][2][4];
   float cs[NG][4];
 #pragma unroll
@@ -469,54 +545,48 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_wgrad_kernel(gvk_skinny_wgra
     }
   float as[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
   const float inv_keep = p.drop_p > 0.f ? 1.0f / (1.0f - p.drop_p) : 1.f;
-  const bool has_ln = p.ln_gamma != nullptr;
+  const int nsteps = (m_end - m_begin + L::kRows - 1) / L::kRows;
+#pragma unroll
+  for (int s0 = 0; s0 < L::kStages - 1; ++s0) issue(s0);
 #pragma unroll 1
-  for (int mb = m_begin; mb < m_end; mb += 16) {
-    // two 8-row k-steps per iteration: all 4 NG float4 loads (and the latents) are issued before the first MMA
-    float4 x0[2][NG], x1[2][NG];
-    float fa[2][2][4];
-    size_t c0[2], c1[2];
-    bool v0[2], v1[2];
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      const int r0 = mb + 8 * h + t, r1 = r0 + 4;
-      v0[h] = r0 < m_end; v1[h] = r1 < m_end;
-      c0[h] = (size_t)min(r0, m_end - 1); c1[h] = (size_t)min(r1, m_end - 1);
-#pragma unroll
-      for (int G = 0; G < NG; ++G) {
-        x0[h][G] = *reinterpret_cast<const float4*>(p.x + c0[h] * p.ldx + cbase + 32 * G + 4 * g);
-        x1[h][G] = *reinterpret_cast<const float4*>(p.x + c1[h] * p.ldx + cbase + 32 * G + 4 * g);
-      }
-#pragma unroll
-      for (int mt = 0; mt < 2; ++mt) {
-        const int j0 = 16 * mt + g, j1 = j0 + 8;
-        fa[h][mt][0] = (v0[h] && j0 < p.r) ? p.a[c0[h] * p.lda + j0] : 0.f;
-        fa[h][mt][1] = (v0[h] && j1 < p.r) ? p.a[c0[h] * p.lda + j1] : 0.f;
-        fa[h][mt][2] = (v1[h] && j0 < p.r) ? p.a[c1[h] * p.lda + j0] : 0.f;
-        fa[h][mt][3] = (v1[h] && j1 < p.r) ? p.a[c1[h] * p.lda + j1] : 0.f;
-      }
+  for (int step = 0; step < nsteps; ++step) {
+    issue(step + L::kStages - 1);
+    cp_async_wait<L::kStages - 1>();
+    __syncwarp();
+    const int mb = m_begin + step * L::kRows;
+    float* st = ring + (step % L::kStages) * L::kStageFloats;
+    float* sa = st + L::kRows * L::kRS;
+    const float* sstat = sa + L::kRows * L::kAS;
+    if (cs_mma && mb + L::kRows > m_end) {         // partial stage: no ones for the zero-filled rows (f(0) != 0 under LayerNorm)
+      if (lane < L::kRows && mb + lane >= m_end) sa[lane * L::kAS + p.r] = 0.f;
+      __syncwarp();
     }
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
+      const int l0 = 8 * h + t, l1 = l0 + 4;                     // rows of this lane inside the stage
       uint32_t a[2][4];
 #pragma unroll
       for (int mt = 0; mt < 2; ++mt) {
-        as[mt][0] += fa[h][mt][0] + fa[h][mt][2];
-        as[mt][1] += fa[h][mt][1] + fa[h][mt][3];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) a[mt][k] = f2tf32(fa[h][mt][k]);
+        const float f0 = sa[l0 * L::kAS + 16 * mt + g], f1 = sa[l0 * L::kAS + 16 * mt + g + 8];
+        const float f2 = sa[l1 * L::kAS + 16 * mt + g], f3 = sa[l1 * L::kAS + 16 * mt + g + 8];
+        as[mt][0] += f0 + f2;
+        as[mt][1] += f1 + f3;
+        a[mt][0] = tf32_bits(f0); a[mt][1] = tf32_bits(f1); a[mt][2] = tf32_bits(f2); a[mt][3] = tf32_bits(f3);
       }
       float mu0 = 0.f, rs0 = 1.f, mu1 = 0.f, rs1 = 1.f;
       if (has_ln) {
-        mu0 = p.mean[c0[h]]; rs0 = p.rstd[c0[h]]; mu1 = p.mean[c1[h]]; rs1 = p.rstd[c1[h]];
+        mu0 = sstat[l0]; rs0 = sstat[16 + l0]; mu1 = sstat[l1]; rs1 = sstat[16 + l1];
       }
 #pragma unroll
       for (int G = 0; G < NG; ++G) {
         const int col = cbase + 32 * G + 4 * g;
-        float y0[4] = {x0[h][G].x, x0[h][G].y, x0[h][G].z, x0[h][G].w}, y1[4] = {x1[h][G].x, x1[h][G].y, x1[h][G].z, x1[h][G].w};
+        const float4 x0 = *reinterpret_cast<const float4*>(st + l0 * L::kRS + 32 * G + 4 * g);
+        const float4 x1 = *reinterpret_cast<const float4*>(st + l1 * L::kRS + 32 * G + 4 * g);
+        float y0[4] = {x0.x, x0.y, x0.z, x0.w}, y1[4] = {x1.x, x1.y, x1.z, x1.w};
         if (p.drop_p > 0.f) {
-          const float4 ma = tc_drop4(p.seed, p.offset + c0[h] * p.dim + col, p.drop_p, inv_keep);
-          const float4 mb4 = tc_drop4(p.seed, p.offset + c1[h] * p.dim + col, p.drop_p, inv_keep);
+          const size_t c0 = (size_t)min(mb + l0, m_end - 1), c1 = (size_t)min(mb + l1, m_end - 1);
+          const float4 ma = tc_drop4(p.seed, p.offset + c0 * p.dim + col, p.drop_p, inv_keep);
+          const float4 mb4 = tc_drop4(p.seed, p.offset + c1 * p.dim + col, p.drop_p, inv_keep);
           y0[0] *= ma.x; y0[1] *= ma.y; y0[2] *= ma.z; y0[3] *= ma.w;
           y1[0] *= mb4.x; y1[1] *= mb4.y; y1[2] *= mb4.z; y1[3] *= mb4.w;
         }
@@ -529,17 +599,20 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_wgrad_kernel(gvk_skinny_wgra
             y1[i] = (y1[i] - mu1) * rs1 * gg[i] + bb[i];
           }
         }
+        if (cs_add) {
+          const bool v0 = mb + l0 < m_end, v1 = mb + l1 < m_end;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) cs[G][i] += (v0 ? y0[i] : 0.f) + (v1 ? y1[i] : 0.f);
+        }
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-          if (!v0[h]) y0[i] = 0.f;
-          if (!v1[h]) y1[i] = 0.f;
-          cs[G][i] += y0[i] + y1[i];
-          const uint32_t b0 = f2tf32(y0[i]), b1 = f2tf32(y1[i]);
+          const uint32_t b0 = tf32_bits(y0[i]), b1 = tf32_bits(y1[i]);
           mma_tf32(acc[G][i][0], a[0][0], a[0][1], a[0][2], a[0][3], b0, b1);
           mma_tf32(acc[G][i][1], a[1][0], a[1][1], a[1][2], a[1][3], b0, b1);
         }
       }
     }
+    __syncwarp();   // every lane is done with this stage before the next iteration's copies overwrite the oldest one
   }
   float* ws_dw = p.ws + (size_t)blockIdx.x * p.r * p.dim;
   float* ws_dx = p.ws + (size_t)gridDim.x * p.r * p.dim + (size_t)blockIdx.x * p.dim;
@@ -555,14 +628,25 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_wgrad_kernel(gvk_skinny_wgra
         const int col = cbase + 32 * G + 4 * (2 * t + (k & 1));
         if (j < p.r) *reinterpret_cast<float4*>(ws_dw + (size_t)j * p.dim + col) = make_float4(acc[G][0][mt][k], acc[G][1][mt][k], acc[G][2][mt][k], acc[G][3][mt][k]);
       }
+  if (cs_mma) {   // accumulator row r is the column sum (ones slot of the latent operand)
 #pragma unroll
-  for (int G = 0; G < NG; ++G) {
+    for (int G = 0; G < NG; ++G)
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      cs[G][i] += __shfl_xor_sync(0xffffffffu, cs[G][i], 1);
-      cs[G][i] += __shfl_xor_sync(0xffffffffu, cs[G][i], 2);
+      for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          if (16 * mt + g + 8 * (k >> 1) == p.r)
+            *reinterpret_cast<float4*>(ws_dx + cbase + 32 * G + 4 * (2 * t + (k & 1))) = make_float4(acc[G][0][mt][k], acc[G][1][mt][k], acc[G][2][mt][k], acc[G][3][mt][k]);
+  } else {
+#pragma unroll
+    for (int G = 0; G < NG; ++G) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        cs[G][i] += __shfl_xor_sync(0xffffffffu, cs[G][i], 1);
+        cs[G][i] += __shfl_xor_sync(0xffffffffu, cs[G][i], 2);
+      }
+      if (t == 0) *reinterpret_cast<float4*>(ws_dx + cbase + 32 * G + 4 * g) = make_float4(cs[G][0], cs[G][1], cs[G][2], cs[G][3]);
     }
-    if (t == 0) *reinterpret_cast<float4*>(ws_dx + cbase + 32 * G + 4 * g) = make_float4(cs[G][0], cs[G][1], cs[G][2], cs[G][3]);
   }
   if (warp == 0) {
 #pragma unroll
@@ -583,10 +667,19 @@ void skinny_wgrad_launch_reduce(const gvk_skinny_wgrad_params* p, int ncta, cuda
 int skinny_wgrad_tc(const gvk_skinny_wgrad_params* p, cudaStream_t stream) {
   int grid, rows_per_cta;
   skinny_wgrad_plan(p->M, &grid, &rows_per_cta);
+  {   // one CTA per SM (the ring takes all of its shared memory): a single wave, measured 50 us vs 60 us with two CTAs per SM in sequence
+    const int want = std::max(1, std::min(grid, sm_count()));
+    rows_per_cta = ((p->M + want - 1) / want + 15) / 16 * 16;
+    grid = (p->M + rows_per_cta - 1) / rows_per_cta;
+  }
   if (p->dim % 128 == 0 && p->dim % 96 != 0) {
-    tc_wgrad_kernel<4><<<grid, kTcThreads, 0, stream>>>(*p, rows_per_cta, p->dim / 128);
+    static const int attr4 = cudaFuncSetAttribute(tc_wgrad_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WgPipe<4>::kSmem);
+    if (attr4 != cudaSuccess) return cuda_status((cudaError_t)attr4, "skinny_wgrad_tc (smem attribute)");
+    tc_wgrad_kernel<4><<<grid, kTcThreads, WgPipe<4>::kSmem, stream>>>(*p, rows_per_cta, p->dim / 128);
   } else {
-    tc_wgrad_kernel<3><<<grid, kTcThreads, 0, stream>>>(*p, rows_per_cta, p->dim / 96);
+    static const int attr3 = cudaFuncSetAttribute(tc_wgrad_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WgPipe<3>::kSmem);
+    if (attr3 != cudaSuccess) return cuda_status((cudaError_t)attr3, "skinny_wgrad_tc (smem attribute)");
+    tc_wgrad_kernel<3><<<grid, kTcThreads, WgPipe<3>::kSmem, stream>>>(*p, rows_per_cta, p->dim / 96);
   }
   GVK_CHECK_LAUNCH("skinny_wgrad_tc");
   skinny_wgrad_launch_reduce(p, grid, stream);
@@ -596,7 +689,8 @@ int skinny_wgrad_tc(const gvk_skinny_wgrad_params* p, cudaStream_t stream) {
 
 bool skinny_wgrad_tc_supported(const gvk_skinny_wgrad_params* p) {
   const bool dim_ok = (p->dim % 96 == 0 && p->dim / 96 <= kTcWarps) || (p->dim % 128 == 0 && p->dim / 128 <= kTcWarps);
-  return dim_ok && p->r <= 32 && p->ldx % 4 == 0 && (reinterpret_cast<uintptr_t>(p->x) & 15) == 0;
+  return dim_ok && p->r <= 32 && p->r % 4 == 0 && p->ldx % 4 == 0 && p->lda % 4 == 0 && (reinterpret_cast<uintptr_t>(p->x) & 15) == 0 &&
+         (reinterpret_cast<uintptr_t>(p->a) & 15) == 0;
 }
 
 }  // namespace gvk

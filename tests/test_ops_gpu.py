@@ -92,7 +92,7 @@ def test_rowproj_down_up_wgrad(dim, r, prec):
     ops.skinny_wgrad(a, x, dw=dw, da_colsum=dac, dx_colsum=dxc, prec=prec)
     close(dw, a.double().t() @ x.double(), t4)
     close(dac, a.double().sum(0), 1e-4)
-    close(dxc, x.double().sum(0), 1e-4)
+    close(dxc, x.double().sum(0), t5 if tc else 1e-4)      # tf32 form: the column sum rides on the MMA (ones slot), operands rounded to tf32
     dwt = torch.zeros(dim, r, device=DEV)
     ops.skinny_wgrad(a, x, dw=dwt, dw_layout='dr', prec=prec)
     close(dwt, x.double().t() @ a.double(), t4)
@@ -138,7 +138,7 @@ def test_rowproj_dropout_replay(prec):
     dxc = torch.zeros(dim, device=DEV)
     ops.skinny_wgrad(c, x, dw=dw, dw_layout='dr', dx_colsum=dxc, drop_p=p, seed=1234, prec=prec)
     close(dw, (x * mask).double().t() @ c.double(), tol)
-    close(dxc, (x * mask).double().sum(0), 1e-4)
+    close(dxc, (x * mask).double().sum(0), tol)
     del ones
 
 
