@@ -637,17 +637,6 @@ __global__ void __launch_bounds__(kRowThreads, 1) layernorm_bwd_kernel(gvk_layer
   const int ngroups = (p.M + ROWS - 1) / ROWS;
   for (int grp = blockIdx.x * kRowWarps + warp; grp < ngroups; grp += gridDim.x * kRowWarps) {
     const int row0 = grp * ROWS;
-    {  // request the next group's rows from HBM while this one is processed
-      const int nrow0 = (grp + gridDim.x * kRowWarps) * ROWS;
-#pragma unroll
-      for (int q = 0; q < ROWS; ++q) {
-        if (nrow0 + q < p.M) {
-          warp_prefetch_l2(p.x + (size_t)(nrow0 + q) * p.ldx, dim * 4, lane);
-          if (p.dy) warp_prefetch_l2(p.dy + (size_t)(nrow0 + q) * p.ld_dy, dim * 4, lane);
-          if (p.dres) warp_prefetch_l2(p.dres + (size_t)(nrow0 + q) * p.ld_dres, dim * 4, lane);
-        }
-      }
-    }
     size_t rowc[ROWS];
 #pragma unroll
     for (int q = 0; q < ROWS; ++q) rowc[q] = (size_t)min(row0 + q, p.M - 1);
