@@ -138,27 +138,43 @@ __device__ __forceinline__ uint2 float4_to_bf16x4(float4 v) {
   return u;
 }
 
+// The saved-activation operand of the GELU-backward / multiply-by-aux epilogues streams from HBM.  A warp requests the operand of all its
+// patches of a tile (8 KB) before it waits for the tile's accumulator, so 64 KB per SM are in flight and the latency hides behind the main
+// loop; loading patch by patch put four DRAM round trips (~8 us) on the critical path of a 5 us tile.  Rows past M are clamped, not
+// predicated: a select on the loaded value would make the warp wait for each load where it is issued.
 template <int EPI>
-__device__ __forceinline__ void epilogue_patch_fast(const EpiArgs& e, uint32_t taddr, float* patch, int row0, int col0, int M, int lane) {
+constexpr bool kEpiAuxIn = (EPI == EPI_GELU_BWD_BF16 || EPI == EPI_MUL_AUX_BF16);
+template <int EPI>
+__device__ __forceinline__ void epilogue_prefetch_aux(const EpiArgs& e, int row0, int col0, int M, int lane, uint2 (&aux)[8]) {
+  if constexpr (kEpiAuxIn<EPI>) {
+    if (col0 < e.N && row0 < M) {   // warp-uniform
+      const int sr = lane >> 3, col = col0 + (lane & 7) * 4;
+#pragma unroll
+      for (int it = 0; it < 8; ++it) {
+        const int m = row0 + it * 4 + sr;
+        aux[it] = *reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(e.aux) + (size_t)min(m, M - 1) * e.ld_aux + col);
+      }
+    }
+  }
+}
+
+// The fp32 residual of a patch (32 registers) is requested one patch ahead of its use.
+template <int EPI>
+__device__ __forceinline__ void epilogue_prefetch_res(const EpiArgs& e, int row0, int col0, int M, int lane, float4 (&res)[8]) {
+  if constexpr (EPI == EPI_BIAS_RES_F32) {
+    if (col0 < e.N && row0 < M) {   // warp-uniform
+      const int sr = lane >> 3, col = col0 + (lane & 7) * 4;
+#pragma unroll
+      for (int it = 0; it < 8; ++it) res[it] = *reinterpret_cast<const float4*>(e.res1 + (size_t)min(row0 + it * 4 + sr, M - 1) * e.ld_res1 + col);
+    }
+  }
+}
+
+template <int EPI>
+__device__ __forceinline__ void epilogue_patch_fast(const EpiArgs& e, uint32_t taddr, float* patch, int row0, int col0, int M, int lane, const uint2 (&aux_in)[8],
+                                                    const float4 (&res)[8]) {
   const int sr = lane >> 3, cv = lane & 7;  // sub-row 0..3, 4-column vector 0..7
   const int col = col0 + cv * 4;
-  // ---- early loads
-  float4 res[8];
-  uint2 aux_in[8];
-  if constexpr (EPI == EPI_BIAS_RES_F32) {
-#pragma unroll
-    for (int it = 0; it < 8; ++it) {
-      const int m = row0 + it * 4 + sr;
-      res[it] = (m < M) ? *reinterpret_cast<const float4*>(e.res1 + (size_t)m * e.ld_res1 + col) : make_float4(0.f, 0.f, 0.f, 0.f);
-    }
-  }
-  if constexpr (EPI == EPI_GELU_BWD_BF16 || EPI == EPI_MUL_AUX_BF16) {
-#pragma unroll
-    for (int it = 0; it < 8; ++it) {
-      const int m = row0 + it * 4 + sr;
-      aux_in[it] = (m < M) ? *reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(e.aux) + (size_t)m * e.ld_aux + col) : make_uint2(0u, 0u);
-    }
-  }
   float4 bias = make_float4(0.f, 0.f, 0.f, 0.f);
   if constexpr (EPI == EPI_BIAS_GELU_BF16 || EPI == EPI_BIAS_RES_F32 || EPI == EPI_BIAS_GELU_SAVEGRAD_BF16) bias = *reinterpret_cast<const float4*>(e.bias + col);
   // ---- TMEM -> registers (thread = row) -> swizzled smem
@@ -336,21 +352,32 @@ gemm_bf16_sm100_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_c
     const int h = ew >> 2;    // column half
     float* patch = epi_patch + ew * kEpiPatch;
     int lt = 0;
+    constexpr int kPatches = BN / 64;
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++lt) {
       const int m_blk = t / num_n, n_blk = t % num_n;
       const int as = lt & 1;
       const uint32_t aphase = (lt >> 1) & 1;
+      const int row0 = m_blk * kBM + q * 32;
+      constexpr bool kRes = EPI == EPI_BIAS_RES_F32;
+      uint2 aux_in[kEpiAuxIn<EPI> ? kPatches : 1][8];
+      float4 res[kRes ? 2 : 1][8];
+      const int tile_col0 = n_blk * BN + h * (BN / 2);
+      if constexpr (kEpiAuxIn<EPI>) {
+#pragma unroll
+        for (int c = 0; c < kPatches; ++c) epilogue_prefetch_aux<EPI>(e, row0, tile_col0 + c * 32, M, lane, aux_in[c]);
+      }
+      epilogue_prefetch_res<EPI>(e, row0, tile_col0, M, lane, res[0]);
       mbar_wait(&tfull_bar[as], aphase);
       tc_fence_after();
-      const int row0 = m_blk * kBM + q * 32;
-#pragma unroll 1
-      for (int c = 0; c < BN / 64; ++c) {
+#pragma unroll((kEpiAuxIn<EPI> || kRes) ? kPatches : 1)
+      for (int c = 0; c < kPatches; ++c) {
         const int colt = h * (BN / 2) + c * 32;
         const int col0 = n_blk * BN + colt;
+        if (c + 1 < kPatches) epilogue_prefetch_res<EPI>(e, row0, col0 + 32, M, lane, res[kRes ? (c + 1) & 1 : 0]);
         if (col0 < N && row0 < M) {  // warp-uniform
           const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN + colt;
           if constexpr (EPI != EPI_GENERIC) {
-            epilogue_patch_fast<EPI>(e, taddr, patch, row0, col0, M, lane);
+            epilogue_patch_fast<EPI>(e, taddr, patch, row0, col0, M, lane, aux_in[kEpiAuxIn<EPI> ? c : 0], res[kRes ? c & 1 : 0]);
           } else {
             float v[32];
             tmem_ld_32x32(taddr, v);
