@@ -96,7 +96,7 @@ long long gvk_struct_size(const char* name) {
   GVK_SZ(gvk_gemm_params) GVK_SZ(gvk_layernorm_fwd_params) GVK_SZ(gvk_rowproj_down_params) GVK_SZ(gvk_rowproj_up_params)
   GVK_SZ(gvk_skinny_wgrad_params) GVK_SZ(gvk_layernorm_bwd_params) GVK_SZ(gvk_ssf_bwd_params) GVK_SZ(gvk_dropout_params) GVK_SZ(gvk_attn_fwd_params) GVK_SZ(gvk_attn_bwd_params)
   GVK_SZ(gvk_fusion_weights) GVK_SZ(gvk_fusion_grads) GVK_SZ(gvk_fusion_saved) GVK_SZ(gvk_fusion_fwd_params)
-  GVK_SZ(gvk_fusion_bwd_params) GVK_SZ(gvk_head_fwd_params) GVK_SZ(gvk_head_bwd_params) GVK_SZ(gvk_mhsa_fwd_params) GVK_SZ(gvk_mhsa_bwd_params)
+  GVK_SZ(gvk_fusion_bwd_params) GVK_SZ(gvk_head_fwd_params) GVK_SZ(gvk_head_bwd_params) GVK_SZ(gvk_mhsa_fwd_params) GVK_SZ(gvk_mhsa_bwd_params) GVK_SZ(gvk_rescale_intensity_params)
 #undef GVK_SZ
   return -1;
 }
@@ -118,6 +118,7 @@ int gvk_small_wgrad(const float* a, int lda, int ra, const float* b, int ldb, in
 }
 int gvk_attn_simt_fwd(const gvk_attn_fwd_params* p, gvk_stream_t stream) { return gvk::attn_simt_fwd(p, S(stream)); }
 int gvk_attn_simt_bwd(const gvk_attn_bwd_params* p, gvk_stream_t stream) { return gvk::attn_simt_bwd(p, S(stream)); }
+int gvk_rescale_intensity(const gvk_rescale_intensity_params* p, gvk_stream_t stream) { return gvk::rescale_intensity(p, S(stream)); }
 int gvk_patch_gather(const float* img, int B, int C, int D, int H, int W, int fp, int ps, void* patches, int out_dtype, gvk_stream_t stream) {
   return gvk::patch_gather(img, B, C, D, H, W, fp, ps, patches, out_dtype, S(stream));
 }

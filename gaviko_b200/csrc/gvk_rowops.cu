@@ -853,48 +853,76 @@ int layernorm_bwd(const gvk_layernorm_bwd_params* p, cudaStream_t stream) {
 // ------------------------------------------------------------------------------------------------
 // small helpers
 // ------------------------------------------------------------------------------------------------
+// dw[j, k] += sum_m a[m, j] b[m, k]:  a thread owns up to 16 outputs (their operand columns are fixed for the whole kernel), the CTA
+// stages 32 rows of both operands per step with 16-byte loads when the layout allows.
+constexpr int kSwRows = 32;
 __global__ void __launch_bounds__(256) small_wgrad_kernel(const float* __restrict__ a, int lda, int ra, const float* __restrict__ b, int ldb, int rb, int M,
-                                                            int rows_per_cta, float* __restrict__ dw) {
-  __shared__ float sa[16][96], sb[16][96];
+                                                            int rows_per_cta, float* __restrict__ dw, int vec) {
+  __shared__ __align__(16) float sa[kSwRows][96], sb[kSwRows][96];
   const int tid = threadIdx.x;
   const int nout = ra * rb;
   float acc[16];  // outputs tid, tid+256, ... (ra*rb <= 4096)
+  int ja[16], kb[16];
 #pragma unroll
-  for (int i = 0; i < 16; ++i) acc[i] = 0.f;
+  for (int i = 0; i < 16; ++i) {
+    acc[i] = 0.f;
+    const int o = min(tid + 256 * i, nout - 1);
+    ja[i] = o / rb;
+    kb[i] = o - ja[i] * rb;
+  }
+  const int nmine = (nout - tid + 255) / 256;   // outputs this thread owns (may be <= 0)
   const int m_begin = blockIdx.x * rows_per_cta, m_end = min(M, m_begin + rows_per_cta);
-  for (int m0 = m_begin; m0 < m_end; m0 += 16) {
+  for (int m0 = m_begin; m0 < m_end; m0 += kSwRows) {
     __syncthreads();
-    for (int idx = tid; idx < 16 * 96; idx += 256) {
-      const int rr = idx / 96, j = idx - rr * 96;
-      const int m = m0 + rr;
-      sa[rr][j] = (m < m_end && j < ra) ? a[(size_t)m * lda + j] : 0.f;
-      sb[rr][j] = (m < m_end && j < rb) ? b[(size_t)m * ldb + j] : 0.f;
+    if (vec) {
+      const int va = ra / 4, vb = rb / 4;
+      for (int idx = tid; idx < kSwRows * (va + vb); idx += 256) {
+        const int rr = idx / (va + vb), c = idx - rr * (va + vb);
+        const int m = m0 + rr;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (c < va) {
+          if (m < m_end) v = *reinterpret_cast<const float4*>(a + (size_t)m * lda + 4 * c);
+          *reinterpret_cast<float4*>(&sa[rr][4 * c]) = v;
+        } else {
+          if (m < m_end) v = *reinterpret_cast<const float4*>(b + (size_t)m * ldb + 4 * (c - va));
+          *reinterpret_cast<float4*>(&sb[rr][4 * (c - va)]) = v;
+        }
+      }
+    } else {
+      for (int idx = tid; idx < kSwRows * 96; idx += 256) {
+        const int rr = idx / 96, j = idx - rr * 96;
+        const int m = m0 + rr;
+        sa[rr][j] = (m < m_end && j < ra) ? a[(size_t)m * lda + j] : 0.f;
+        sb[rr][j] = (m < m_end && j < rb) ? b[(size_t)m * ldb + j] : 0.f;
+      }
     }
     __syncthreads();
 #pragma unroll
     for (int i = 0; i < 16; ++i) {
-      const int o = tid + 256 * i;
-      if (o < nout) {
-        const int j = o / rb, k = o - j * rb;
+      if (i < nmine) {
+        float s0 = 0.f, s1 = 0.f;
 #pragma unroll
-        for (int rr = 0; rr < 16; ++rr) acc[i] = fmaf(sa[rr][j], sb[rr][k], acc[i]);
+        for (int rr = 0; rr < kSwRows; rr += 2) {
+          s0 = fmaf(sa[rr][ja[i]], sb[rr][kb[i]], s0);
+          s1 = fmaf(sa[rr + 1][ja[i]], sb[rr + 1][kb[i]], s1);
+        }
+        acc[i] += s0 + s1;
       }
     }
   }
 #pragma unroll
-  for (int i = 0; i < 16; ++i) {
-    const int o = tid + 256 * i;
-    if (o < nout) atomicAdd(dw + o, acc[i]);
-  }
+  for (int i = 0; i < 16; ++i)
+    if (i < nmine) atomicAdd(dw + tid + 256 * i, acc[i]);
 }
 
 int small_wgrad(const float* a, int lda, int ra, const float* b, int ldb, int rb, int M, float* dw, cudaStream_t stream) {
   GVK_CHECK_ARG(a && b && dw && M > 0, "gvk_small_wgrad: null pointer");
   GVK_CHECK_ARG(ra >= 1 && ra <= 96 && rb >= 1 && rb <= 96 && ra * rb <= 4096, "gvk_small_wgrad: ra=%d rb=%d must be in [1,96], ra*rb <= 4096", ra, rb);
   const int ctas = std::max(1, std::min(sm_count() * 2, (M + 127) / 128));
-  int rows_per_cta = ((M + ctas - 1) / ctas + 15) / 16 * 16;
+  int rows_per_cta = ((M + ctas - 1) / ctas + kSwRows - 1) / kSwRows * kSwRows;
   const int grid = (M + rows_per_cta - 1) / rows_per_cta;
-  small_wgrad_kernel<<<grid, 256, 0, stream>>>(a, lda, ra, b, ldb, rb, M, rows_per_cta, dw);
+  const int vec = ra % 4 == 0 && rb % 4 == 0 && lda % 4 == 0 && ldb % 4 == 0 && ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b)) & 15) == 0;
+  small_wgrad_kernel<<<grid, 256, 0, stream>>>(a, lda, ra, b, ldb, rb, M, rows_per_cta, dw, vec);
   GVK_CHECK_LAUNCH("small_wgrad");
   return GVK_OK;
 }

@@ -328,6 +328,23 @@ def mhsa_bwd(qkv, out, lse, dout, B, T, H, scale):
 
 
 # ---------------------------------------------------------------------------------------------- token assembly
+def rescale_intensity(x, out_min=0.0, out_max=1.0, *, out=None, out_dtype=None):
+    """Per-volume (x - min) / (max - min) * (out_max - out_min) + out_min over x[b] (see gvk_rescale_intensity); x fp32 contiguous, leading
+    dimension = volumes.  out may be x itself (fp32)."""
+    if x.dtype != torch.float32 or not x.is_contiguous() or x.dim() < 2:
+        raise GvkError('rescale_intensity: expected a contiguous fp32 tensor (B, ...)')
+    B = x.shape[0]
+    n = x.numel() // B
+    if out is None:
+        out = torch.empty(x.shape, device=x.device, dtype=out_dtype or torch.float32)
+    ws = torch.empty(2 * 64 * B, device=x.device, dtype=torch.float32)
+    p = S['gvk_rescale_intensity_params']()
+    _set(p, out=out, out_dtype=L.dtype_tag(out.dtype), B=B, n=n, out_min=out_min, out_max=out_max, ws=ws)
+    setattr(p, 'in', L.ptr(x, torch.float32))       # 'in' is a Python keyword
+    L.call('gvk_rescale_intensity', C.byref(p), L.stream())
+    return out
+
+
 def patch_gather(img, fp, ps, out_dtype):
     B, Cc, D, H, W = img.shape
     if img.dtype != torch.float32 or not img.is_contiguous():

@@ -295,6 +295,21 @@ int gvk_mhsa_bwd(const gvk_mhsa_bwd_params* p, gvk_stream_t stream);
  * Token assembly (a1/a2 of the hot path)
  * ------------------------------------------------------------------------------------------------------------------ */
 
+/* Per-volume intensity rescale in front of the path: torchio.RescaleIntensity(out_min_max=(lo, hi)) with its default
+ * percentiles (0, 100), the last transform of every pipeline of the reference (train.py:53,57,61; eval.py:31; inference.py:30), there run on
+ * the CPU in the DataLoader workers.  For each of the B volumes of n contiguous fp32 values:
+ *   y = (x - min) / (max - min) * (hi - lo) + lo      (fp32, IEEE division, this order of operations: bit-identical to the CPU transform);
+ * a constant volume is passed through unchanged (torchio warns and returns its input).  out may alias in when out_dtype is GVK_F32.
+ * ws: 2 * GVK_RESCALE_PARTS * B floats of workspace (per-volume min / max partials; no atomics, deterministic). */
+#define GVK_RESCALE_PARTS 64
+typedef struct {
+  const float* in; void* out; int out_dtype;
+  int B; long long n;
+  float out_min, out_max;
+  float* ws;
+} gvk_rescale_intensity_params;
+int gvk_rescale_intensity(const gvk_rescale_intensity_params* p, gvk_stream_t stream);
+
 /* Non-overlapping 3-D patch gather in Conv3d weight order (model/gaviko.py:383-385,532-533):
  *   patches[b*N + (d*nh + h)*nw + w, ((c*fp + kd)*ps + kh)*ps + kw] = img[b, c, d*fp + kd, h*ps + kh, w*ps + kw]
  * img fp32 contiguous (B, C, D, H, W); patches row-major [B*N, C*fp*ps*ps] in out_dtype. */
