@@ -218,47 +218,182 @@ __device__ __forceinline__ float gate_imp(const gvk_fusion_weights& w, const Gat
   return sigmoidf_(o);
 }
 
-template <int R>
-__global__ void __launch_bounds__(kFusWarps * 32) fusion_fwd_kernel(gvk_fusion_fwd_params p) {
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int idx = blockIdx.x * kFusWarps + warp;
-  if (idx >= p.B * p.P) return;
-  const int b = idx / p.P, pp = idx % p.P;
-  float* xl_b = p.xl + (size_t)b * p.T * R;
-  const float pl_lane = lane < R ? xl_b[(size_t)pp * R + lane] : 0.f;
-  const float cl_lane = lane < R ? xl_b[(size_t)p.P * R + lane] : 0.f;
-  GateState<R> st;
-  float gw;
-  gates_hidden<R>(p.w, cl_lane, lane, st, gw);
-  const float imp = gate_imp<R>(p.w, st, pp, lane);
+// Both key sets of a volume (xl[:, 2P+2:] and ll: 157 KB for T = 1033, N = 1000, r = 20) fit in shared memory next to the merge buffers,
+// so the CTA copies them once with coalesced 16-byte loads and the per-key walk reads broadcast shared memory (~30 cycles) instead of L2
+// (~600): with one warp-wide global load per key the walk was latency-bound at 67 - 84 us per call.  `staged` is 0 when they do not fit.
+__device__ __forceinline__ void fus_stage_keys(float* dst, const float* __restrict__ src, int nfloats) {
+#pragma unroll 4
+  for (int i = threadIdx.x * 4; i < nfloats; i += blockDim.x * 4) *reinterpret_cast<float4*>(dst + i) = *reinterpret_cast<const float4*>(src + i);
+}
+static bool fus_can_stage(const float* xl, const float* ll, int T, int N, int P, int r, size_t base_bytes, size_t* total) {
+  const size_t keys = ((size_t)(T - 2 * P - 2) + N) * r * sizeof(float);
+  const bool aligned = r % 4 == 0 && (((size_t)T * r) % 4 == 0) && ((reinterpret_cast<uintptr_t>(xl) | reinterpret_cast<uintptr_t>(ll)) & 15) == 0;
+  const bool ok = aligned && base_bytes + keys <= 227 * 1024;
+  *total = base_bytes + (ok ? keys : 0);
+  return ok;
+}
 
-  float pl[R];
-  gatherR<R>(pl_lane, pl);
+// Forward: one CTA per volume.  A lane owns one prompt (query, running max / sum and context accumulator in registers), a warp walks a
+// slice of the keys of one of the two cross-attentions (warps [0, W/2): global keys xl[:, 2P+2:], warps [W/2, W): local keys ll) reading
+// each key row once as a warp-wide broadcast; the W/2 partial softmax states of a side are merged through shared memory.  Warp 0 computes
+// the gates (they depend on the cls latent only) before it joins the key walk.
+// (History: one warp per (b, prompt) walking all ~2000 keys with a shuffle reduction per context element was pure latency, 54 us.)
+constexpr int kFusFwdWarps = 16;
+template <int R>
+struct FusFwdSmem {
+  static constexpr int kPart = kFusFwdWarps * (R + 2) * 32;   // part[warp][R acc | m | l][prompt]
+  static constexpr int kW = 2 * (R * R + R);                  // wq_g | bq_g | wq_l | bq_l
+  static constexpr int kCtx = 2 * 32 * (R + 1);               // ctx[side][prompt][c]
+  static constexpr int kGate = 32 + 4;                        // imp[prompt of the group], gw
+  static constexpr size_t kBytes = (size_t)(kPart + kW + kCtx + kGate) * sizeof(float);
+};
+template <int R>
+__global__ void __launch_bounds__(kFusFwdWarps * 32) fusion_fwd_kernel(gvk_fusion_fwd_params p, int staged) {
+  extern __shared__ __align__(16) float fus_smem[];
+  float* part = fus_smem;
+  float* s_w = part + FusFwdSmem<R>::kPart;
+  float* s_ctx = s_w + FusFwdSmem<R>::kW;
+  float* s_imp = s_ctx + FusFwdSmem<R>::kCtx;
+  float* s_keys = s_imp + FusFwdSmem<R>::kGate;
+  constexpr int HW = kFusFwdWarps / 2;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int side = warp / HW, wl = warp % HW;
+  const int b = blockIdx.x;
+  float* xl_b = p.xl + (size_t)b * p.T * R;
   const float scale = rsqrtf((float)R);
-  const float qg_lane = matvecR<R>(p.w.wq_g, p.w.bq_g, pl, lane);
-  const float ql_lane = matvecR<R>(p.w.wq_l, p.w.bq_l, pl, lane);
-  float q[R];
-  float lse_g, lse_l;
-  gatherR<R>(qg_lane * scale, q);
-  const int n_g = p.T - 2 * p.P - 2;
-  const float ctx_g = single_query_attn<R>(xl_b + (size_t)(2 * p.P + 2) * R, n_g, q, lane, lse_g);
-  gatherR<R>(ql_lane * scale, q);
-  const float ctx_l = single_query_attn<R>(p.ll + (size_t)b * p.N * R, p.N, q, lane, lse_l);
-  const float enh = (gw * ctx_g + (1.f - gw) * ctx_l) * imp;
-  const size_t o = ((size_t)b * p.P + pp) * R + lane;
-  if (lane < R) {
-    p.s.pl[o] = pl_lane;
-    p.s.qg[o] = qg_lane;
-    p.s.ql[o] = ql_lane;
-    p.s.ctx_g[o] = ctx_g;
-    p.s.ctx_l[o] = ctx_l;
-    xl_b[(size_t)pp * R + lane] = enh;  // combined_latent row p
+  for (int i = threadIdx.x; i < R * R + R; i += blockDim.x) {
+    s_w[i] = i < R * R ? p.w.wq_g[i] : p.w.bq_g[i - R * R];
+    s_w[R * R + R + i] = i < R * R ? p.w.wq_l[i] : p.w.bq_l[i - R * R];
   }
-  if (lane == 0) {
-    p.s.lse_g[(size_t)b * p.P + pp] = lse_g;
-    p.s.lse_l[(size_t)b * p.P + pp] = lse_l;
-    p.s.imp[(size_t)b * p.P + pp] = imp;
-    if (pp == 0) p.s.gw[b] = gw;
+  const int n_g = p.T - 2 * p.P - 2;
+  const int n = side == 0 ? n_g : p.N;
+  const float* tokbase = side == 0 ? xl_b + (size_t)(2 * p.P + 2) * R : p.ll + (size_t)b * p.N * R;
+  if (staged) {
+    fus_stage_keys(s_keys, xl_b + (size_t)(2 * p.P + 2) * R, n_g * R);
+    fus_stage_keys(s_keys + n_g * R, p.ll + (size_t)b * p.N * R, p.N * R);
+    tokbase = side == 0 ? s_keys : s_keys + n_g * R;
+  }
+  const int per = (n + HW - 1) / HW;
+  const int t0 = wl * per, t1 = min(n, t0 + per);
+  GateState<R> gst;
+  float gw = 0.f;
+  if (warp == 0) {
+    const float cl_lane = lane < R ? xl_b[(size_t)p.P * R + lane] : 0.f;
+    gates_hidden<R>(p.w, cl_lane, lane, gst, gw);
+    if (lane == 0) {
+      s_imp[32] = gw;
+      p.s.gw[b] = gw;
+    }
+  }
+  __syncthreads();
+  const float* wq = s_w + side * (R * R + R);
+  for (int pg = 0; pg < p.P; pg += 32) {
+    const int pp = pg + lane;
+    const bool valid = pp < p.P;
+    const size_t o = ((size_t)b * p.P + (valid ? pp : 0)) * R;
+    if (warp == 0) {                                  // importance gate of this lane's prompt: sigmoid(W3[pp, :] . gelu(hidden) + b3[pp])
+      float* s_hact = s_ctx;                          // 64 floats of scratch; s_ctx is not written before the barrier below
+      if (pg == 0) {
+        s_hact[lane] = gelu_erf(gst.hpre[0]);
+        s_hact[lane + 32] = gelu_erf(gst.hpre[1]);
+      }
+      __syncwarp();
+      if (valid) {
+        const float* w3 = p.w.a_w3 + (size_t)pp * kHid;
+        float o0 = p.w.a_b3[pp], o1 = 0.f;
+#pragma unroll
+        for (int k = 0; k < kHid; k += 8) {
+          const float4 wa = *reinterpret_cast<const float4*>(w3 + k), wb = *reinterpret_cast<const float4*>(w3 + k + 4);
+          o0 = fmaf(wa.x, s_hact[k], fmaf(wa.y, s_hact[k + 1], fmaf(wa.z, s_hact[k + 2], fmaf(wa.w, s_hact[k + 3], o0))));
+          o1 = fmaf(wb.x, s_hact[k + 4], fmaf(wb.y, s_hact[k + 5], fmaf(wb.z, s_hact[k + 6], fmaf(wb.w, s_hact[k + 7], o1))));
+        }
+        const float imp = sigmoidf_(o0 + o1);
+        s_imp[lane] = imp;
+        p.s.imp[(size_t)b * p.P + pp] = imp;
+      }
+    }
+    float q[R];
+    {
+      float pl[R];
+      load_vec_f4<R>(xl_b + (size_t)(valid ? pp : 0) * R, pl);
+#pragma unroll
+      for (int c = 0; c < R; ++c) {
+        float v = wq[R * R + c];
+#pragma unroll
+        for (int j = 0; j < R; ++j) v = fmaf(wq[c * R + j], pl[j], v);
+        q[c] = v;
+      }
+      if (valid && wl == 0) {
+        float* qdst = (side == 0 ? p.s.qg : p.s.ql) + o;
+#pragma unroll
+        for (int c = 0; c < R; ++c) {
+          qdst[c] = q[c];
+          if (side == 0) p.s.pl[o + c] = pl[c];
+        }
+      }
+#pragma unroll
+      for (int c = 0; c < R; ++c) q[c] *= scale;
+    }
+    float m = -INFINITY, l = 0.f;
+    float acc[R];
+#pragma unroll
+    for (int c = 0; c < R; ++c) acc[c] = 0.f;
+#pragma unroll(R <= 20 ? 2 : 1)
+    for (int t = t0; t < t1; ++t) {
+      float tok[R];
+      load_vec_f4<R>(tokbase + (size_t)t * R, tok);      // the same address in every lane: one broadcast transaction
+      float sc = 0.f;
+#pragma unroll
+      for (int c = 0; c < R; ++c) sc = fmaf(q[c], tok[c], sc);
+      const float mn = fmaxf(m, sc);
+      const float corr = __expf(m - mn), pr = __expf(sc - mn);   // exp(-inf) = 0 on the first key
+      m = mn;
+      l = fmaf(l, corr, pr);
+#pragma unroll
+      for (int c = 0; c < R; ++c) acc[c] = fmaf(acc[c], corr, pr * tok[c]);
+    }
+    float* mine = part + (size_t)warp * (R + 2) * 32 + lane;
+#pragma unroll
+    for (int c = 0; c < R; ++c) mine[c * 32] = acc[c];
+    mine[R * 32] = m;
+    mine[(R + 1) * 32] = l;
+    __syncthreads();   // also orders every warp's read of the prompt rows before they are overwritten below
+    if (wl == 0) {
+      float M = -INFINITY;
+#pragma unroll
+      for (int w = 0; w < HW; ++w) M = fmaxf(M, part[((side * HW + w) * (R + 2) + R) * 32 + lane]);
+      float L = 0.f;
+      float ctx[R];
+#pragma unroll
+      for (int c = 0; c < R; ++c) ctx[c] = 0.f;
+#pragma unroll
+      for (int w = 0; w < HW; ++w) {
+        const float* pw = part + (size_t)(side * HW + w) * (R + 2) * 32 + lane;
+        const float mw = pw[R * 32];
+        const float f = mw == -INFINITY ? 0.f : __expf(mw - M);
+        L = fmaf(pw[(R + 1) * 32], f, L);
+#pragma unroll
+        for (int c = 0; c < R; ++c) ctx[c] = fmaf(pw[c * 32], f, ctx[c]);
+      }
+      const float inv_l = 1.0f / L;
+      if (valid) {
+        float* cdst = (side == 0 ? p.s.ctx_g : p.s.ctx_l) + o;
+#pragma unroll
+        for (int c = 0; c < R; ++c) {
+          ctx[c] *= inv_l;
+          cdst[c] = ctx[c];
+          s_ctx[(side * 32 + lane) * (R + 1) + c] = ctx[c];
+        }
+        (side == 0 ? p.s.lse_g : p.s.lse_l)[(size_t)b * p.P + pp] = M + __logf(L);
+      }
+    }
+    __syncthreads();
+    const float gwv = s_imp[32];
+    for (int idx = threadIdx.x; idx < 32 * R; idx += blockDim.x) {   // combined_latent row p = (gw ctx_g + (1 - gw) ctx_l) imp_p
+      const int k = idx / R, c = idx - k * R;
+      if (pg + k < p.P) xl_b[(size_t)(pg + k) * R + c] = (gwv * s_ctx[k * (R + 1) + c] + (1.f - gwv) * s_ctx[(32 + k) * (R + 1) + c]) * s_imp[k];
+    }
+    __syncthreads();   // shared buffers are reused by the next group of 32 prompts
   }
 }
 
@@ -300,11 +435,12 @@ struct FusBwdSmem {
   static constexpr size_t kBytes = (size_t)(kPart + kDq + kPl) * sizeof(float);
 };
 template <int R>
-__global__ void __launch_bounds__(kFusBwdWarps * 32) fusion_bwd_prompts_kernel(gvk_fusion_bwd_params p) {
+__global__ void __launch_bounds__(kFusBwdWarps * 32) fusion_bwd_prompts_kernel(gvk_fusion_bwd_params p, int staged) {
   extern __shared__ __align__(16) float fus_smem[];
   float* part = fus_smem;
   float* s_dq = part + FusBwdSmem<R>::kPart;
   float* s_pl = s_dq + FusBwdSmem<R>::kDq;
+  float* s_keys = s_pl + FusBwdSmem<R>::kPl;
   constexpr int HW = kFusBwdWarps / 2;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int side = warp / HW, wl = warp % HW;
@@ -312,8 +448,15 @@ __global__ void __launch_bounds__(kFusBwdWarps * 32) fusion_bwd_prompts_kernel(g
   const float scale = rsqrtf((float)R);
   const float gw = p.s.gw[b];
   float* dxl_b = p.dxl + (size_t)b * p.T * R;
-  const int n = side == 0 ? p.T - 2 * p.P - 2 : p.N;
+  const int n_g = p.T - 2 * p.P - 2;
+  const int n = side == 0 ? n_g : p.N;
   const float* tokbase = side == 0 ? p.xl + ((size_t)b * p.T + 2 * p.P + 2) * R : p.ll + (size_t)b * p.N * R;
+  if (staged) {
+    fus_stage_keys(s_keys, p.xl + ((size_t)b * p.T + 2 * p.P + 2) * R, n_g * R);
+    fus_stage_keys(s_keys + n_g * R, p.ll + (size_t)b * p.N * R, p.N * R);
+    tokbase = side == 0 ? s_keys : s_keys + n_g * R;
+    __syncthreads();
+  }
   const int per = (n + HW - 1) / HW;
   const int t0 = wl * per, t1 = min(n, t0 + per);
   for (int pg = 0; pg < p.P; pg += 32) {
@@ -480,19 +623,37 @@ __global__ void __launch_bounds__(32) fusion_bwd_gates_kernel(gvk_fusion_bwd_par
   const float hact[2] = {gelu_erf(st.hpre[0]), gelu_erf(st.hpre[1])};
   float d_hact[2] = {0.f, 0.f};
   float d_gw = 0.f;
-  for (int pp = 0; pp < p.P; ++pp) {
-    const float* ws = p.ws + ((size_t)b * p.P + pp) * (2 * R + 4);
-    const float imp = p.s.imp[(size_t)b * p.P + pp];
-    const float d_o = ws[2 * R + 2] * imp * (1.f - imp);
-    d_gw += ws[2 * R + 3];
-#pragma unroll
-    for (int u = 0; u < 2; ++u) {
-      const int k = lane + 32 * u;
-      atomicAdd(p.g.a_w3 + pp * kHid + k, d_o * hact[u]);
-      d_hact[u] = fmaf(d_o, p.w.a_w3[pp * kHid + k], d_hact[u]);
+  // per-prompt terms are loaded 32 prompts at a time, one per lane, before the dependent chain of atomics starts
+  for (int pg = 0; pg < p.P; pg += 32) {
+    const int pl = pg + lane;
+    float d_o_lane = 0.f;
+    if (pl < p.P) {
+      const float* ws = p.ws + ((size_t)b * p.P + pl) * (2 * R + 4);
+      const float imp = p.s.imp[(size_t)b * p.P + pl];
+      d_o_lane = ws[2 * R + 2] * imp * (1.f - imp);
+      d_gw += ws[2 * R + 3];
     }
-    if (lane == 0) atomicAdd(p.g.a_b3 + pp, d_o);
+    const int cnt = min(32, p.P - pg);
+    float w3[2][32];
+#pragma unroll
+    for (int k = 0; k < 32; ++k) {
+      const int pp = pg + min(k, cnt - 1);
+      w3[0][k] = p.w.a_w3[pp * kHid + lane];
+      w3[1][k] = p.w.a_w3[pp * kHid + lane + 32];
+    }
+#pragma unroll
+    for (int k = 0; k < 32; ++k) {
+      if (k < cnt) {
+        const float d_o = __shfl_sync(0xffffffffu, d_o_lane, k);
+        atomicAdd(p.g.a_w3 + (pg + k) * kHid + lane, d_o * hact[0]);
+        atomicAdd(p.g.a_w3 + (pg + k) * kHid + lane + 32, d_o * hact[1]);
+        d_hact[0] = fmaf(d_o, w3[0][k], d_hact[0]);
+        d_hact[1] = fmaf(d_o, w3[1][k], d_hact[1]);
+      }
+    }
+    if (pl < p.P) atomicAdd(p.g.a_b3 + pl, d_o_lane);
   }
+  d_gw = warp_sum(d_gw);
   // estimator: hidden -> LN_a(cl)
   const float ya = lane < R ? st.cn_a * p.w.a_ln_w[lane] + p.w.a_ln_b[lane] : 0.f;
   float ya_all[R];
@@ -544,20 +705,25 @@ __global__ void __launch_bounds__(32) fusion_bwd_gates_kernel(gvk_fusion_bwd_par
 
 template <int R>
 static int fusion_fwd_launch(const gvk_fusion_fwd_params* p, cudaStream_t stream) {
-  const int grid = (p->B * p->P + kFusWarps - 1) / kFusWarps;
-  fusion_fwd_kernel<R><<<grid, kFusWarps * 32, 0, stream>>>(*p);
+  static const int attr = cudaFuncSetAttribute(fusion_fwd_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  if (attr != cudaSuccess) return cuda_status((cudaError_t)attr, "prompt_fusion_fwd (smem attribute)");
+  size_t smem;
+  const int staged = fus_can_stage(p->xl, p->ll, p->T, p->N, p->P, R, FusFwdSmem<R>::kBytes, &smem);
+  fusion_fwd_kernel<R><<<p->B, kFusFwdWarps * 32, smem, stream>>>(*p, staged);
   GVK_CHECK_LAUNCH("prompt_fusion_fwd");
   return GVK_OK;
 }
 template <int R>
 static int fusion_bwd_launch(const gvk_fusion_bwd_params* p, cudaStream_t stream) {
-  static const int attr = cudaFuncSetAttribute(fusion_bwd_prompts_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FusBwdSmem<R>::kBytes);
+  static const int attr = cudaFuncSetAttribute(fusion_bwd_prompts_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   if (attr != cudaSuccess) return cuda_status((cudaError_t)attr, "prompt_fusion_bwd (smem attribute)");
-  fusion_bwd_prompts_kernel<R><<<p->B, kFusBwdWarps * 32, FusBwdSmem<R>::kBytes, stream>>>(*p);
+  size_t smem;
+  const int staged = fus_can_stage(p->xl, p->ll, p->T, p->N, p->P, R, FusBwdSmem<R>::kBytes, &smem);
+  fusion_bwd_prompts_kernel<R><<<p->B, kFusBwdWarps * 32, smem, stream>>>(*p, staged);
   GVK_CHECK_LAUNCH("prompt_fusion_bwd_prompts");
   const int nmax = std::max(p->N, p->T - 2 * p->P - 2);
-  const size_t smem = ((size_t)2 * p->P * R + 2 * p->P) * sizeof(float);
-  fusion_bwd_tokens_kernel<R><<<dim3((nmax + 255) / 256, p->B, 2), 256, smem, stream>>>(*p);
+  const size_t smem_tok = ((size_t)2 * p->P * R + 2 * p->P) * sizeof(float);
+  fusion_bwd_tokens_kernel<R><<<dim3((nmax + 255) / 256, p->B, 2), 256, smem_tok, stream>>>(*p);
   GVK_CHECK_LAUNCH("prompt_fusion_bwd_tokens");
   fusion_bwd_gates_kernel<R><<<p->B, 32, 0, stream>>>(*p);
   GVK_CHECK_LAUNCH("prompt_fusion_bwd_gates");

@@ -151,7 +151,16 @@ def test_small_ops():
     ops.small_wgrad(a, b, dw)
     close(dw, a.double().t() @ b.double(), 1e-4)
     w = torch.randn(60, 20, device=DEV)
-    close(ops.small_matmul(a, w), a.double() @ w.double(), 1e-4)
+    close(ops.small_matmul(a, w), a.double() @ w.double(), 1e-4)                     # row-per-thread form (60 -> 20)
+    a2, w2 = torch.randn(M + 3, 44, device=DEV), torch.randn(44, 12, device=DEV)      # generic form, odd sizes
+    close(ops.small_matmul(a2, w2), a2.double() @ w2.double(), 1e-4)
+    dw2 = torch.zeros(44, 12, device=DEV)
+    ops.small_wgrad(a2, torch.randn(M + 3, 12, device=DEV) * 0 + 1, dw2)
+    close(dw2, a2.double().sum(0)[:, None].expand(44, 12), 1e-4)
+    a3, b3 = torch.randn(M + 3, 7, device=DEV), torch.randn(M + 3, 5, device=DEV)     # scalar staging path (sizes not multiples of 4)
+    dw3 = torch.zeros(7, 5, device=DEV)
+    ops.small_wgrad(a3, b3, dw3)
+    close(dw3, a3.double().t() @ b3.double(), 1e-4)
     out = torch.zeros(60, device=DEV)
     ops.colsum(a, out)
     close(out, a.double().sum(0), 1e-4)
