@@ -280,8 +280,15 @@ def run_ours(args):
         gsec = sum(a.elapsed_time(b) for a, b, _ in gemm_events) / 1e3
         gflop = sum(f for _, _, f in gemm_events)
         peak = pk['bf16_tflops_sustained'] if args.dtype == 'bf16' else 80.0
+        traffic = None      # DRAM bytes per GEMM launch from the committed ncu capture of this configuration (profiles/), else null
+        try:
+            tj = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'profiles', 'ncu_r01_gemm_traffic.json')))
+            if (tj['batch'], tj['backbone'], tj['dtype']) == (B, args.backbone, args.dtype) and train:
+                traffic = tj['dram_bytes_per_launch']
+        except Exception:  # noqa: BLE001
+            pass
         roof = dict(bound='tensor', kernel='gemm_bf16_sm100_kernel' if args.dtype == 'bf16' else 'gemm_f32_kernel', achieved=(gflop / gsec / 1e12) if gsec > 0 else None,
-                    peak=peak, unit='TFLOP/s', frac=(gflop / gsec / 1e12 / peak) if gsec > 0 else None, traffic=None, peak_source=f'{pk_src} (bf16_tflops_sustained)',
+                    peak=peak, unit='TFLOP/s', frac=(gflop / gsec / 1e12 / peak) if gsec > 0 else None, traffic=traffic, peak_source=f'{pk_src} (bf16_tflops_sustained)',
                     launches=len(gemm_events), share_of_step=gsec * 1e3 / ms if ms > 0 else None,
                     step_tensor_frac=world and (B * args.steps * flops_per_vol / (ms / 1e3) / 1e12 / peak))
         cpu = None
