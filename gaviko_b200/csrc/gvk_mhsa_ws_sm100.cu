@@ -244,21 +244,24 @@ mhsa_ws_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_const
           m_used = m_new;
         }
         const float mc = m_used * c2;
-        float rs0 = 0.f, rs1 = 0.f, rs2 = 0.f, rs3 = 0.f;
+        const float2 c2v = make_float2(c2, c2), mcv = make_float2(-mc, -mc);
+        float2 rs01 = make_float2(0.f, 0.f), rs23 = make_float2(0.f, 0.f);
 #pragma unroll
         for (int c = 0; c < 2; ++c) {           // 32 scores -> 16 packed registers -> P columns 16c .. 16c+15 (over S columns already read)
           uint32_t pk[16];
 #pragma unroll
           for (int i = 0; i < 16; i += 2) {
-            float p0 = fmaf(s[32 * c + 2 * i], c2, -mc), p1 = fmaf(s[32 * c + 2 * i + 1], c2, -mc);
-            float p2 = fmaf(s[32 * c + 2 * i + 2], c2, -mc), p3 = fmaf(s[32 * c + 2 * i + 3], c2, -mc);
-            if ((a.dbg & 3) != 1) { p0 = fast_ex2(p0); p1 = fast_ex2(p1); p2 = fast_ex2(p2); p3 = fast_ex2(p3); }
-            rs0 += p0; rs1 += p1; rs2 += p2; rs3 += p3;
-            pk[i] = pack_bf16x2(p0, p1);
-            pk[i + 1] = pack_bf16x2(p2, p3);
+            float2 pa = ffma2(make_float2(s[32 * c + 2 * i], s[32 * c + 2 * i + 1]), c2v, mcv);
+            float2 pb = ffma2(make_float2(s[32 * c + 2 * i + 2], s[32 * c + 2 * i + 3]), c2v, mcv);
+            if ((a.dbg & 3) != 1) { pa.x = fast_ex2(pa.x); pa.y = fast_ex2(pa.y); pb.x = fast_ex2(pb.x); pb.y = fast_ex2(pb.y); }
+            rs01 = fadd2(rs01, pa);
+            rs23 = fadd2(rs23, pb);
+            pk[i] = pack_bf16x2(pa.x, pa.y);
+            pk[i + 1] = pack_bf16x2(pb.x, pb.y);
           }
           tmem_st_32x16(tS + 16 * c, pk);
         }
+        const float rs0 = rs01.x, rs1 = rs01.y, rs2 = rs23.x, rs3 = rs23.y;
         l = fmaf(l, alpha, (rs0 + rs1) + (rs2 + rs3));
         if (j > 0 && __any_sync(0xffffffffu, resc)) {
           // O (accumulated by PV of the previous iterations) must be in the units of the new maximum before PV(j) adds to it
@@ -270,8 +273,13 @@ mhsa_ws_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_const
           tmem_ld_32x32(tO, *reinterpret_cast<float(*)[32]>(&o[0]));
           tmem_ld_32x32(tO + 32, *reinterpret_cast<float(*)[32]>(&o[32]));
           tc_wait_ld();
+          const float2 av = make_float2(alpha, alpha);
 #pragma unroll
-          for (int i = 0; i < 64; ++i) o[i] *= alpha;
+          for (int i = 0; i < 64; i += 2) {
+            const float2 v = fmul2(make_float2(o[i], o[i + 1]), av);
+            o[i] = v.x;
+            o[i + 1] = v.y;
+          }
           tmem_st_32x32(tO, *reinterpret_cast<uint32_t(*)[32]>(&o[0]));
           tmem_st_32x32(tO + 32, *reinterpret_cast<uint32_t(*)[32]>(&o[32]));
         }
