@@ -120,6 +120,25 @@ __device__ __forceinline__ float gelu_and_grad_fast(float x, float& grad) {
   grad = fmaf(x * 0.39894228040143268f, e, cdf);
   return x * cdf;
 }
+// Two elements at a time on the packed fp32 instructions (FFMA2 / FMUL2 / FADD2): the epilogue of the fc1 forward GEMM is bound by its own
+// instruction count (8 warps against a 5 us main loop), and the polynomial / products of the pair share issue slots this way.
+__device__ __forceinline__ void gelu_and_grad_fast2(float2 x, float2& y, float2& grad) {
+  const float2 ax = make_float2(fabsf(x.x), fabsf(x.y));
+  float2 t = ffma2(ax, make_float2(0.3275911f * 0.70710678118654752f, 0.3275911f * 0.70710678118654752f), make_float2(1.0f, 1.0f));
+  t.x = rcp_approx(t.x);
+  t.y = rcp_approx(t.y);
+  float2 p = ffma2(make_float2(0.5f * 1.061405429f, 0.5f * 1.061405429f), t, make_float2(0.5f * -1.453152027f, 0.5f * -1.453152027f));
+  p = ffma2(p, t, make_float2(0.5f * 1.421413741f, 0.5f * 1.421413741f));
+  p = ffma2(p, t, make_float2(0.5f * -0.284496736f, 0.5f * -0.284496736f));
+  p = ffma2(p, t, make_float2(0.5f * 0.254829592f, 0.5f * 0.254829592f));
+  float2 e = fmul2(fmul2(x, x), make_float2(-0.72134752044448170f, -0.72134752044448170f));
+  e.x = ex2_approx(e.x);
+  e.y = ex2_approx(e.y);                                   // exp(-x^2 / 2)
+  const float2 q = fmul2(fmul2(p, t), e);                  // 0.5 erfc(|x| / sqrt 2)
+  const float2 cdf = make_float2(x.x < 0.f ? q.x : 1.0f - q.x, x.y < 0.f ? q.y : 1.0f - q.y);
+  y = fmul2(x, cdf);
+  grad = ffma2(fmul2(x, make_float2(0.39894228040143268f, 0.39894228040143268f)), e, cdf);
+}
 __device__ __forceinline__ float gelu_grad_fast(float x) {
   float e;
   const float cdf = norm_cdf_fast(x, e);
@@ -199,7 +218,11 @@ __device__ __forceinline__ void epilogue_patch_fast(const EpiArgs& e, uint32_t t
     }
     if constexpr (EPI == EPI_BIAS_GELU_SAVEGRAD_BF16) {
       float4 gr;
-      x.x = gelu_and_grad_fast(x.x, gr.x); x.y = gelu_and_grad_fast(x.y, gr.y); x.z = gelu_and_grad_fast(x.z, gr.z); x.w = gelu_and_grad_fast(x.w, gr.w);
+      float2 y01, y23, g01, g23;
+      gelu_and_grad_fast2(make_float2(x.x, x.y), y01, g01);
+      gelu_and_grad_fast2(make_float2(x.z, x.w), y23, g23);
+      x = make_float4(y01.x, y01.y, y23.x, y23.y);
+      gr = make_float4(g01.x, g01.y, g23.x, g23.y);
       if (e.aux) *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(e.aux) + (size_t)m * e.ld_aux + col) = float4_to_bf16x4(gr);
     }
     if constexpr (EPI == EPI_MUL_AUX_BF16) {
