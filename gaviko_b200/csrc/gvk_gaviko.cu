@@ -244,7 +244,7 @@ struct FusFwdSmem {
   static constexpr int kPart = kFusFwdWarps * (R + 2) * 32;   // part[warp][R acc | m | l][prompt]
   static constexpr int kW = 2 * (R * R + R);                  // wq_g | bq_g | wq_l | bq_l
   static constexpr int kCtx = 2 * 32 * (R + 1);               // ctx[side][prompt][c]
-  static constexpr int kGate = 32 + 4;                        // imp[prompt of the group], gw
+  static constexpr int kGate = 32 + 4 + kHid;                 // imp[prompt of the group], gw, gelu(hidden) of the estimator
   static constexpr size_t kBytes = (size_t)(kPart + kW + kCtx + kGate) * sizeof(float);
 };
 template <int R>
@@ -292,7 +292,7 @@ __global__ void __launch_bounds__(kFusFwdWarps * 32) fusion_fwd_kernel(gvk_fusio
     const bool valid = pp < p.P;
     const size_t o = ((size_t)b * p.P + (valid ? pp : 0)) * R;
     if (warp == 0) {                                  // importance gate of this lane's prompt: sigmoid(W3[pp, :] . gelu(hidden) + b3[pp])
-      float* s_hact = s_ctx;                          // 64 floats of scratch; s_ctx is not written before the barrier below
+      float* s_hact = s_imp + 36;                     // gelu(hidden), written once, read by every group of 32 prompts
       if (pg == 0) {
         s_hact[lane] = gelu_erf(gst.hpre[0]);
         s_hact[lane + 32] = gelu_erf(gst.hpre[1]);

@@ -294,11 +294,12 @@ FUSION_KEYS = {'wq_g': 'global_attention.query_proj.weight', 'bq_g': 'global_att
                'g_w': 'gl_balancer.gl_balancer_.1.weight', 'g_b': 'gl_balancer.gl_balancer_.1.bias'}
 
 
-@pytest.mark.parametrize('P,N', [(32, 1000), (8, 64)])
-def test_prompt_fusion_fwd_bwd(P, N):
-    """Whole Awakening_Prompt (down-proj, fusion core, up-proj) against the oracle restatement in fp64."""
+@pytest.mark.parametrize('P,N,r', [(32, 1000, 20), (8, 64, 20), (40, 333, 20), (5, 97, 32), (33, 50, 16)])
+def test_prompt_fusion_fwd_bwd(P, N, r):
+    """Whole Awakening_Prompt (down-proj, fusion core, up-proj) against the oracle restatement in fp64 (more than 32 prompts = two lane
+    groups per CTA, latent widths 16 / 20 / 32, key sets that do / do not fit the shared-memory staging)."""
     torch.manual_seed(12)
-    B, r, dim = 2, 20, 192
+    B, dim = 2, 192
     T = P + 1 + N
     sd = _fusion_sd(P, r, dim, DEV)
     g = torch.randn(B, T, dim, device=DEV)
