@@ -152,6 +152,8 @@ def test_small_ops():
     close(dw, a.double().t() @ b.double(), 1e-4)
     w = torch.randn(60, 20, device=DEV)
     close(ops.small_matmul(a, w), a.double() @ w.double(), 1e-4)                     # row-per-thread form (60 -> 20)
+    a96, w96 = torch.randn(M + 1, 96, device=DEV), torch.randn(96, 32, device=DEV)    # row-per-thread form (96 -> 32)
+    close(ops.small_matmul(a96, w96), a96.double() @ w96.double(), 1e-4)
     a2, w2 = torch.randn(M + 3, 44, device=DEV), torch.randn(44, 12, device=DEV)      # generic form, odd sizes
     close(ops.small_matmul(a2, w2), a2.double() @ w2.double(), 1e-4)
     dw2 = torch.zeros(44, 12, device=DEV)
@@ -222,6 +224,25 @@ def test_attn_simt_window(dhw, k, r, prec):
     close(dqkv, qr.grad, 2 * tol)
     for blk in range(3):
         close(dqkv[:, blk * r:(blk + 1) * r], qr.grad[:, blk * r:(blk + 1) * r], 2 * tol)
+
+
+@pytest.mark.parametrize('prec', [ops.PREC_FP32, ops.PREC_TF32])
+def test_attn_window_two_heads(prec):
+    """head h of q / k / v at columns q_off / k_off / v_off + h * D (the API allows H > 1 although LocalSelfAttention uses one head)"""
+    torch.manual_seed(9)
+    B, H, r, dhw, k = 2, 2, 20, (4, 5, 6), (3, 4, 4)
+    N = dhw[0] * dhw[1] * dhw[2]
+    qkv = torch.randn(B * N, 3 * H * r, device=DEV)
+    allow = O.window_allow(dhw, k)
+    kw = dict(q_off=0, k_off=H * r, v_off=2 * H * r, scale=0.3, window=k, grid=dhw, prec=prec)
+    tol = 1e-5 if prec == ops.PREC_FP32 else 2e-3
+    o, lse = ops.attn_simt_fwd(qkv, B, N, H, r, **kw)
+    qr = qkv.double().requires_grad_(True)
+    ref = _dense_attn_ref(qr, B, N, H, r, 0.3, allow)
+    close(o, ref.detach(), tol)
+    do = torch.randn(B * N, H * r, device=DEV)
+    ref.backward(do.double())
+    close(ops.attn_simt_bwd(qkv, o, lse, do, B, N, H, r, **kw), qr.grad, 2 * tol)
 
 
 @pytest.mark.parametrize('prec', [ops.PREC_FP32, ops.PREC_TF32])
