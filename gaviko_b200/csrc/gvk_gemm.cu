@@ -196,7 +196,7 @@ __device__ __forceinline__ void epilogue_patch_fast(const EpiArgs& e, uint32_t t
   const int col = col0 + cv * 4;
   float4 bias = make_float4(0.f, 0.f, 0.f, 0.f);
   if constexpr (EPI == EPI_BIAS_GELU_BF16 || EPI == EPI_BIAS_RES_F32 || EPI == EPI_BIAS_GELU_SAVEGRAD_BF16) bias = *reinterpret_cast<const float4*>(e.bias + col);
-  // ---- TMEM -> registers (thread = row) -> swizzled smem
+  // ---- TMEM -> registers (thread = row) -> swizzled smem  (loading the next patch's accumulator during this one's math was tried: no gain)
   float v[32];
   tmem_ld_32x32(taddr, v);
   tc_wait_ld();
@@ -212,7 +212,8 @@ __device__ __forceinline__ void epilogue_patch_fast(const EpiArgs& e, uint32_t t
     const int r = it * 4 + sr;
     const int m = row0 + r;
     float4 x = reinterpret_cast<const float4*>(patch)[r * 8 + (cv ^ (r & 7))];
-    if (m >= M) continue;
+    const bool live = m < M;   // rows past M are computed like any other and only their stores are predicated: a `continue` here put a
+                               // branch between the eight unrolled iterations and kept the scheduler from interleaving their math
     if constexpr (EPI == EPI_BIAS_GELU_BF16 || EPI == EPI_BIAS_RES_F32 || EPI == EPI_BIAS_GELU_SAVEGRAD_BF16) {
       x.x += bias.x; x.y += bias.y; x.z += bias.z; x.w += bias.w;
     }
@@ -223,14 +224,14 @@ __device__ __forceinline__ void epilogue_patch_fast(const EpiArgs& e, uint32_t t
       gelu_and_grad_fast2(make_float2(x.z, x.w), y23, g23);
       x = make_float4(y01.x, y01.y, y23.x, y23.y);
       gr = make_float4(g01.x, g01.y, g23.x, g23.y);
-      if (e.aux) *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(e.aux) + (size_t)m * e.ld_aux + col) = float4_to_bf16x4(gr);
+      if (e.aux && live) *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(e.aux) + (size_t)m * e.ld_aux + col) = float4_to_bf16x4(gr);
     }
     if constexpr (EPI == EPI_MUL_AUX_BF16) {
       const float4 a4 = bf16x4_to_float4(aux_in[it]);
       x.x *= a4.x; x.y *= a4.y; x.z *= a4.z; x.w *= a4.w;
     }
     if constexpr (EPI == EPI_BIAS_GELU_BF16) {
-      if (e.aux) *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(e.aux) + (size_t)m * e.ld_aux + col) = float4_to_bf16x4(x);
+      if (e.aux && live) *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(e.aux) + (size_t)m * e.ld_aux + col) = float4_to_bf16x4(x);
       x.x = gelu_fast(x.x); x.y = gelu_fast(x.y); x.z = gelu_fast(x.z); x.w = gelu_fast(x.w);
     }
     if constexpr (EPI == EPI_GELU_BWD_BF16) {
@@ -240,10 +241,12 @@ __device__ __forceinline__ void epilogue_patch_fast(const EpiArgs& e, uint32_t t
     if constexpr (EPI == EPI_BIAS_RES_F32) {
       x.x += res[it].x; x.y += res[it].y; x.z += res[it].z; x.w += res[it].w;
     }
-    if constexpr (EPI == EPI_BIAS_RES_F32 || EPI == EPI_STORE_F32) {
-      *reinterpret_cast<float4*>(reinterpret_cast<float*>(e.out) + (size_t)m * e.ld_out + col) = x;
-    } else {
-      *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(e.out) + (size_t)m * e.ld_out + col) = float4_to_bf16x4(x);
+    if (live) {
+      if constexpr (EPI == EPI_BIAS_RES_F32 || EPI == EPI_STORE_F32) {
+        *reinterpret_cast<float4*>(reinterpret_cast<float*>(e.out) + (size_t)m * e.ld_out + col) = x;
+      } else {
+        *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(e.out) + (size_t)m * e.ld_out + col) = float4_to_bf16x4(x);
+      }
     }
   }
   __syncwarp();
@@ -273,7 +276,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_bf16_sm100_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, EpiArgs e, int M, int N, int K) {
   using L = GemmSmem<BN, STAGES>;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // 1 KB alignment by pointer arithmetic: keeps the shared address space (LDS / STS, not generic LD / ST)
   uint8_t* sA = smem;
   uint8_t* sB = smem + STAGES * L::kABytes;
   float* epi_patch = reinterpret_cast<float*>(smem + L::kRing);
@@ -392,13 +395,14 @@ gemm_bf16_sm100_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_c
       epilogue_prefetch_res<EPI>(e, row0, tile_col0, M, lane, res[0]);
       mbar_wait(&tfull_bar[as], aphase);
       tc_fence_after();
+      const uint32_t taddr0 = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN + h * (BN / 2);
 #pragma unroll((kEpiAuxIn<EPI> || kRes) ? kPatches : 1)
       for (int c = 0; c < kPatches; ++c) {
         const int colt = h * (BN / 2) + c * 32;
         const int col0 = n_blk * BN + colt;
         if (c + 1 < kPatches) epilogue_prefetch_res<EPI>(e, row0, col0 + 32, M, lane, res[kRes ? (c + 1) & 1 : 0]);
         if (col0 < N && row0 < M) {  // warp-uniform
-          const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN + colt;
+          const uint32_t taddr = taddr0 + c * 32;
           if constexpr (EPI != EPI_GENERIC) {
             epilogue_patch_fast<EPI>(e, taddr, patch, row0, col0, M, lane, aux_in[kEpiAuxIn<EPI> ? c : 0], res[kRes ? c & 1 : 0]);
           } else {

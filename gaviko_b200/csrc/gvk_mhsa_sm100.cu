@@ -106,7 +106,7 @@ constexpr int kFwdSmem = kTileBytes128 /*Q*/ + 2 * kKvStages * kTileBytes64 /*K,
 __global__ void __launch_bounds__(kFaThreads, 3)
 mhsa_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant__ CUtensorMap tma_kv, FwdArgs a) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // 1 KB alignment by pointer arithmetic: keeps the shared address space (LDS / STS, not generic LD / ST)
   uint8_t* sQ = smem;
   uint8_t* sK = sQ + kTileBytes128;                    // kKvStages stages
   uint8_t* sV = sK + kKvStages * kTileBytes64;         // kKvStages stages
@@ -293,7 +293,7 @@ __global__ void __launch_bounds__(kBwdThreads, 2)
 mhsa_bwd_dq_sm100_kernel(const __grid_constant__ CUtensorMap tma_q128, const __grid_constant__ CUtensorMap tma_kv64, const __grid_constant__ CUtensorMap tma_do128,
                          BwdArgs a) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // 1 KB alignment by pointer arithmetic: keeps the shared address space (LDS / STS, not generic LD / ST)
   uint8_t* sQ = smem;
   uint8_t* sdO = sQ + kTileBytes128;
   uint8_t* sK = sdO + kTileBytes128;
@@ -443,7 +443,7 @@ __global__ void __launch_bounds__(kBwdThreads, 2)
 mhsa_bwd_dkv_sm100_kernel(const __grid_constant__ CUtensorMap tma_kv128, const __grid_constant__ CUtensorMap tma_q64, const __grid_constant__ CUtensorMap tma_do64,
                           BwdArgs a) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // 1 KB alignment by pointer arithmetic: keeps the shared address space (LDS / STS, not generic LD / ST)
   uint8_t* sK = smem;
   uint8_t* sV = sK + kTileBytes128;
   uint8_t* sQ = sV + kTileBytes128;                     // kDkvStages stages of [64 x 64]

@@ -72,7 +72,7 @@ constexpr int kFwdSmem = 2 * kQBytes /*Q A,B*/ + 2 * kStages * kKVBytes /*K,V ri
 __global__ void __launch_bounds__(kThreads, 1)
 mhsa_ws_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant__ CUtensorMap tma_kv, FwdArgs a) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // 1 KB alignment by pointer arithmetic: keeps the shared address space (LDS / STS, not generic LD / ST)
   uint8_t* sQ = smem;                              // [2][16 KB]
   uint8_t* sK = sQ + 2 * kQBytes;                  // [kStages][8 KB]
   uint8_t* sV = sK + kStages * kKVBytes;           // [kStages][8 KB]
