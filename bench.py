@@ -294,9 +294,9 @@ def run_ours(args):
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
             try:
-                sec, threads = cpu_reference_step_time(args.backbone, 2, 2, 1, args.mode)
+                sec, threads = cpu_reference_step_time(args.backbone, 2, 8, 1, args.mode)
                 cpu = dict(value=2 / sec, unit='volumes/s', cores=threads, kind='port',
-                           sample=f'1 warm-up + 2 timed steps of batch 2 of the same {args.backbone} GAViKO {args.mode} workload (oracle port, fp32, torch CPU threads)')
+                           sample=f'1 warm-up + 8 timed steps of batch 2 (~10 s) of the same {args.backbone} GAViKO {args.mode} workload (oracle port, fp32, torch CPU threads)')
             except Exception as ex:  # noqa: BLE001
                 cpu = dict(value=None, unit='volumes/s', cores=os.cpu_count(), kind='port', sample=f'failed: {ex}')
         line = dict(metric=metric_name(args), value=value, unit='volumes/s', n_gpus=world, steps=args.steps, warmup=args.warmup, ms_per_step=ms / args.steps,
