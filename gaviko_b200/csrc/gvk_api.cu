@@ -118,6 +118,9 @@ int gvk_small_wgrad(const float* a, int lda, int ra, const float* b, int ldb, in
 }
 int gvk_attn_simt_fwd(const gvk_attn_fwd_params* p, gvk_stream_t stream) { return gvk::attn_simt_fwd(p, S(stream)); }
 int gvk_attn_simt_bwd(const gvk_attn_bwd_params* p, gvk_stream_t stream) { return gvk::attn_simt_bwd(p, S(stream)); }
+int gvk_split_pack_bf16(const float* src, int ld_src, int rows, int r, void* dst, int ld_dst, int width, int pattern, gvk_stream_t stream) {
+  return gvk::split_pack_bf16(src, ld_src, rows, r, dst, ld_dst, width, pattern, S(stream));
+}
 int gvk_rescale_intensity(const gvk_rescale_intensity_params* p, gvk_stream_t stream) { return gvk::rescale_intensity(p, S(stream)); }
 int gvk_patch_gather(const float* img, int B, int C, int D, int H, int W, int fp, int ps, void* patches, int out_dtype, gvk_stream_t stream) {
   return gvk::patch_gather(img, B, C, D, H, W, fp, ps, patches, out_dtype, S(stream));

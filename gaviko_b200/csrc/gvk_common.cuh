@@ -64,6 +64,7 @@ bool attn_win_tc_supported(const gvk_attn_fwd_params* p);
 int attn_win_tc_fwd(const gvk_attn_fwd_params* p, cudaStream_t stream);
 int attn_win_tc_bwd(const gvk_attn_bwd_params* p, cudaStream_t stream);
 int rescale_intensity(const gvk_rescale_intensity_params* p, cudaStream_t stream);
+int split_pack_bf16(const float* src, int ld_src, int rows, int r, void* dst, int ld_dst, int width, int pattern, cudaStream_t stream);
 int patch_gather(const float* img, int B, int C, int D, int H, int W, int fp, int ps, void* patches, int out_dtype, cudaStream_t stream);
 int fill_rows(const float* a, const float* b, int R, int dim, float* out, int ld_out, int out_batch_rows, int out_row_offset, int B, cudaStream_t stream);
 int batch_rowsum(const float* x, int ldx, int batch_rows, int row_offset, int R, int dim, int B, float* out, int accumulate, cudaStream_t stream);

@@ -986,6 +986,32 @@ int small_matmul(const float* a, int lda, int ra, const float* w, int rb, int M,
   return GVK_OK;
 }
 
+// dst[row, s * r + j] = (pattern bit s ? lo : hi)(src[row, j]) for s = 0..2, zero up to `width`:  hi = bf16(x), lo = bf16(x - hi).
+// With A rows packed as (hi, lo, hi) and B rows as (hi, hi, lo) a bf16 GEMM over these 3 r columns yields hi*hi + lo*hi + hi*lo, i.e. the
+// fp32 product to ~2^-16 relative: this is how the rank-r prompt up-projection rides on the fc2 GEMM as one extra K block.
+__global__ void __launch_bounds__(256) split_pack_bf16_kernel(const float* __restrict__ src, int ld_src, int rows, int r, __nv_bfloat16* __restrict__ dst, int ld_dst,
+                                                              int width, int pattern) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= rows * width) return;
+  const int row = idx / width, c = idx - row * width;
+  const int slot = c / r, j = c - slot * r;
+  float out = 0.f;
+  if (slot < 3) {
+    const float x = src[(size_t)row * ld_src + j];
+    const float hi = __bfloat162float(__float2bfloat16_rn(x));
+    out = (pattern >> slot) & 1 ? x - hi : hi;
+  }
+  dst[(size_t)row * ld_dst + c] = __float2bfloat16_rn(out);
+}
+
+int split_pack_bf16(const float* src, int ld_src, int rows, int r, void* dst, int ld_dst, int width, int pattern, cudaStream_t stream) {
+  GVK_CHECK_ARG(src && dst && rows > 0 && r > 0 && width >= 3 * r, "gvk_split_pack_bf16: bad argument (rows=%d r=%d width=%d)", rows, r, width);
+  const long long total = (long long)rows * width;
+  split_pack_bf16_kernel<<<(int)((total + 255) / 256), 256, 0, stream>>>(src, ld_src, rows, r, reinterpret_cast<__nv_bfloat16*>(dst), ld_dst, width, pattern);
+  GVK_CHECK_LAUNCH("split_pack_bf16");
+  return GVK_OK;
+}
+
 __global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ x, int ldx, int M, int dim, int rows_per_cta, float* __restrict__ out) {
   const int c = blockIdx.y * 256 + threadIdx.x;
   if (c >= dim) return;

@@ -30,6 +30,9 @@ def _resolve_dtype(compute_dtype, param_dtype):
     raise ValueError(f"compute_dtype must be 'fp32' or 'bf16', got {compute_dtype!r}")
 
 
+_KEXT = 64   # K columns appended to the fc2 GEMM for the rank-r prompt up-projection (one 64-wide K block of the tcgen05 kernel)
+
+
 class FrozenCache:
     """Compute-dtype copies (and transposes, for dgrad) of frozen tensors, rebuilt when the source tensor changes."""
 
@@ -128,6 +131,11 @@ class GavikoEngine:
                 ln2_w=vec(('ln2w', i), f.net[0].weight), ln2_b=vec(('ln2b', i), f.net[0].bias),
                 w1=mat(('w1', i), f.net[1].weight), w1_t=mat_t(('w1', i), f.net[1].weight), b1=vec(('b1', i), f.net[1].bias),
                 w2=mat(('w2', i), f.net[4].weight), w2_t=mat_t(('w2', i), f.net[4].weight), b2=vec(('b2', i), f.net[4].bias)))
+            if cdt == torch.bfloat16:
+                # fc2 weight with _KEXT extra K columns: the forward writes the prompt up-projection weight there every call, so that
+                # fc2(act) + prompt comes out of ONE GEMM over [act | combined latent] (see forward)
+                W['layers'][-1]['w2x'] = cache.get((('w2x', i), cdt), f.net[4].weight,
+                                                   lambda t: torch.cat([t.to(cdt), torch.zeros(t.shape[0], _KEXT, device=t.device, dtype=cdt)], 1).contiguous())
         return W
 
     def _trainables(self):
@@ -237,14 +245,27 @@ class GavikoEngine:
             dl = ops.rowproj_down(loc_new, Fu['wd'], Fu['bd'], act=ops.ROWACT_QUICKGELU, save_pre=save, prec=pr)
             comb, ll = dg['z'], dl['z']
             fsaved = ops.prompt_fusion_fwd(comb, ll, Fu['k'], B, T, N, P)      # comb: xl -> combined latent, in place
-            g_tmp = ops.rowproj_up(comb, Fu['wu'], Fu['bu'], res=g_mid, prec=pr)
             # ---- frozen MLP (model/vision_transformer.py:26-38, residual + prompt gaviko.py:304)
             h2, mean2, rstd2 = ops.layernorm_fwd(g_mid, Lw['ln2_w'], Lw['ln2_b'], out_dtype=cdt, save_stats=save)
             hpre = torch.empty((B * T, c['mlp_dim']), device=img.device, dtype=cdt) if save else None
-            act = ops.gemm(h2, Lw['w1'], bias=Lw['b1'], act=ops.ACT_GELU_SAVE_GRAD if save else ops.ACT_GELU, aux=hpre, out_dtype=cdt)   # aux = gelu'(pre)
-            del h2
-            g_out = ops.gemm(act, Lw['w2'], bias=Lw['b2'], res1=g_tmp)
-            del act, g_tmp
+            mlp = c['mlp_dim']
+            if 'w2x' in Lw and 3 * r_p <= _KEXT:
+                # bf16 mode: g_out = g_mid + [act | comb] [W2 | Wu]^T + (b2 + bu) in one GEMM (K = mlp + 64).  The separate up-projection
+                # pass (read g_mid, write g_mid + prompt: 406 MB per layer at B = 64) disappears.  The rank-r operands enter as bf16 hi / lo
+                # pairs in three r-wide slots (hi*hi + lo*hi + hi*lo), so the trainable path keeps ~16 mantissa bits
+                act_x = torch.empty((B * T, mlp + _KEXT), device=img.device, dtype=cdt)
+                ops.gemm(h2, Lw['w1'], bias=Lw['b1'], act=ops.ACT_GELU_SAVE_GRAD if save else ops.ACT_GELU, aux=hpre, out=act_x[:, :mlp])   # aux = gelu'(pre)
+                del h2
+                ops.split_pack_bf16(comb, act_x[:, mlp:], 0b010)             # (hi, lo, hi)
+                ops.split_pack_bf16(Fu['wu'], Lw['w2x'][:, mlp:], 0b100)     # (hi, hi, lo)
+                g_out = ops.gemm(act_x, Lw['w2x'], bias=Lw['b2'] + Fu['bu'], res1=g_mid)
+                del act_x
+            else:
+                g_tmp = ops.rowproj_up(comb, Fu['wu'], Fu['bu'], res=g_mid, prec=pr)
+                act = ops.gemm(h2, Lw['w1'], bias=Lw['b1'], act=ops.ACT_GELU_SAVE_GRAD if save else ops.ACT_GELU, aux=hpre, out_dtype=cdt)   # aux = gelu'(pre)
+                del h2
+                g_out = ops.gemm(act, Lw['w2'], bias=Lw['b2'], res1=g_tmp)
+                del act, g_tmp
             if save:
                 st.update(loc_in=loc, mean_l=d['mean'], rstd_l=d['rstd'], z=d['z'], qkv_l=d['z2'], ctx_l=ctx_l, lse_l=lse_l, seed_a=seed_a, seed_p=seed_p,
                           g_in=g, mean1=mean1, rstd1=rstd1, qkv=qkv, o=o, lse=lse, g_mid=g_mid, mean2=mean2, rstd2=rstd2, hpre=hpre,

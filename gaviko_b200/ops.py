@@ -345,6 +345,15 @@ def rescale_intensity(x, out_min=0.0, out_max=1.0, *, out=None, out_dtype=None):
     return out
 
 
+def split_pack_bf16(src, dst, pattern):
+    """dst [rows, width] bf16 (a view with a row stride is fine) <- hi / lo split of src [rows, r] fp32 in three r-wide slots (see gvk_split_pack_bf16)."""
+    rows, r = src.shape
+    if dst.dtype != torch.bfloat16 or dst.shape[0] != rows or dst.shape[1] < 3 * r:
+        raise GvkError('split_pack_bf16: dst must be bf16 [rows, >= 3 r]')
+    L.call('gvk_split_pack_bf16', C.c_void_p(L.ptr(src, torch.float32)), _ld(src), rows, r, C.c_void_p(L.ptr(dst)), _ld(dst), dst.shape[1], pattern, L.stream())
+    return dst
+
+
 def patch_gather(img, fp, ps, out_dtype):
     B, Cc, D, H, W = img.shape
     if img.dtype != torch.float32 or not img.is_contiguous():

@@ -379,6 +379,12 @@ typedef struct {
 } gvk_fusion_bwd_params;
 int gvk_prompt_fusion_bwd(const gvk_fusion_bwd_params* p, gvk_stream_t stream);
 
+/* K-extension operand of a bf16 GEMM for a rank-r fp32 product (bf16 mode: the Awakening_Prompt up-projection, model/gaviko.py:183-187, rides on
+ * the fc2 GEMM of the same layer as 64 extra K columns).  dst[row, s*r + j] (bf16, s = 0..2) = hi(src[row, j]) or lo(src[row, j]) according to
+ * bit s of `pattern` (0 = hi = bf16(x), 1 = lo = bf16(x - hi)); columns [3r, width) are zero.  Pack the A side with pattern 0b010 (hi, lo, hi)
+ * and the B side with 0b100 (hi, hi, lo): the GEMM then accumulates hi*hi + lo*hi + hi*lo, the fp32 product to ~2^-16 relative. */
+int gvk_split_pack_bf16(const float* src, int ld_src, int rows, int r, void* dst, int ld_dst, int width, int pattern, gvk_stream_t stream);
+
 /* y = dy * quick_gelu'(pre)   over n elements (may run in place: y == dy). */
 int gvk_quickgelu_bwd(const float* dy, const float* pre, float* y, size_t n, gvk_stream_t stream);
 /* y = dy * (z > 0)   over n elements (ReLU backward from the activation output; Adapter, model/adaptformer.py:63; in place allowed). */

@@ -99,3 +99,25 @@ def test_gemm_rejects_cpu_tensors():
     from gaviko_b200._lib import GvkError
     with pytest.raises(GvkError):
         ops.gemm(torch.zeros(4, 64), torch.zeros(4, 64))
+
+
+def test_k_extension_with_split_operands():
+    """The rank-r fp32 product rides on a bf16 GEMM as one extra K block: [A | (hi, lo, hi)(c)] [B | (hi, hi, lo)(wu)]^T = A B^T + c wu^T with the
+    rank-r term accurate to ~2^-16 (three bf16 products), far inside the tf32 accuracy of the separate up-projection kernel it replaces."""
+    torch.manual_seed(5)
+    M, N, K, r = 1033, 256, 128, 20
+    c = torch.randn(M, r, device='cuda')
+    wu = torch.randn(N, r, device='cuda') / r ** 0.5
+    a = torch.zeros(M, K + 64, device='cuda', dtype=torch.bfloat16)       # A part zero: isolates the rank-r term
+    b = torch.zeros(N, K + 64, device='cuda', dtype=torch.bfloat16)
+    ops.split_pack_bf16(c, a[:, K:], 0b010)
+    ops.split_pack_bf16(wu, b[:, K:], 0b100)
+    hi = c.bfloat16()
+    assert torch.equal(a[:, K:K + r], hi) and torch.equal(a[:, K + 2 * r:K + 3 * r], hi) and torch.equal(a[:, K + r:K + 2 * r], (c - hi.float()).bfloat16())
+    assert (a[:, K + 3 * r:] == 0).all() and torch.equal(b[:, K + 2 * r:K + 3 * r], (wu - wu.bfloat16().float()).bfloat16())
+    out = ops.gemm(a, b)
+    want = c.double() @ wu.double().t()
+    rel = ((out.double() - want).norm() / want.norm()).item()
+    assert rel < 5e-5, rel
+    plain = (c.bfloat16().double() @ wu.bfloat16().double().t())          # what a single bf16 product would give
+    assert rel < 0.05 * ((plain - want).norm() / want.norm()).item()
