@@ -25,3 +25,11 @@ VARIANT_CASES = {
     'deep_vpt_t16_small': ('deep_vpt', dict(SMALL, num_classes=5, channels=1, pool='cls', backbone='vit-t16', dropout=0.0, emb_dropout=0.0,
                                             freeze_vit=True, prompt_dropout=0.0, prompt_dim=6, num_prompts=4, deep_prompt=True), 2),
 }
+
+# SURVEY.md §8 (f) "next" methods: oracle + goldens exist, the CUDA path does not yet (tests/test_oracle_golden.py covers the oracle only)
+NEXT_CASES = {
+    'dvpt_t16_small': ('dvpt', dict(SMALL, num_classes=5, channels=1, pool='mean', backbone='vit-t16', dropout=0.0, emb_dropout=0.0,
+                                    num_prompts=4, freeze_vit=True), 2),
+    'dvpt_cls_t16_small': ('dvpt', dict(SMALL, num_classes=5, channels=1, pool='cls', backbone='vit-t16', dropout=0.0, emb_dropout=0.0,
+                                        num_prompts=6, freeze_vit=True), 2),
+}

@@ -303,3 +303,36 @@ def vpt_forward(sd, img, *, backbone, frame_patch_size, image_patch_size, deep_p
         x = _vit_block(x, sd, p, heads, dim_head)
         x = feed_forward(x, sd, p + '1.') + x
     return _pool_head(x, sd, pool, pre + 'transformer.norm.', pre + 'mlp_head.')
+
+
+def dvpt_share_mlp(x, sd, p, P, dim):
+    """model/dvpt.py:36-47 (share_MLP.forward): QuickGELU BEFORE the down-projection, one prompt -> token cross-attention in the 20-wide
+    latent with scale d_model ** -0.5 (dvpt.py:34), cls and token latents passed through, up-projection times the scalar gate."""
+    z = quick_gelu(x) @ sd[p + 'prompt_key_proj_d.weight'].t() + sd[p + 'prompt_key_proj_d.bias']
+    prompt, cls, tok = z[:, :P], z[:, P:P + 1], z[:, P + 1:]
+    a = torch.softmax(prompt @ tok.transpose(-1, -2) * dim ** -0.5, dim=-1)
+    out = torch.cat([a @ tok, cls, tok], dim=1)
+    return (out @ sd[p + 'prompt_key_proj_u.weight'].t() + sd[p + 'prompt_key_proj_u.bias']) * sd[p + 'prompt_gate']
+
+
+def dvpt_forward(sd, img, *, backbone, frame_patch_size, image_patch_size, num_prompts, pool='mean', dim_head=64):
+    """model/dvpt.py:186-207 -> :49-63 (ResidualAttentionBlock) -> :65-82 (Transformer) — SURVEY.md §8 f3, oracle only so far.
+    Tokens are [prompts ; cls ; patches] (dvpt.py:194-196); pool = 'mean' averages the normed rows 0..P (dvpt.py:81-82,201), pool = 'cls'
+    takes row 0 of the normed sequence, which is the FIRST PROMPT row, not the cls row (reference behaviour)."""
+    depth, heads, dim, _ = mapping_vit(backbone)
+    P = num_prompts
+    e = patch_embed(sd, img, frame_patch_size, image_patch_size)
+    B = e.shape[0]
+    x = torch.cat([sd['prompt_embeddings'].expand(B, -1, -1), sd['cls_token'].expand(B, -1, -1), e], dim=1)
+    x = x + torch.cat([sd['prompt_positional_embedding'], sd['pos_embedding']], dim=1)
+    for i in range(depth):
+        p = f'transformer.layers.{i}.0.'
+        a = p + 'attn.'
+        x = mhsa(x, sd[a + 'norm.weight'], sd[a + 'norm.bias'], sd[a + 'to_qkv.weight'], sd[a + 'to_out.0.weight'], sd[a + 'to_out.0.bias'], heads, dim_head) + x
+        prompt = dvpt_share_mlp(x, sd, p + 'prompt_proj.', P, dim)
+        x = feed_forward(x, sd, p + 'mlp.') + x + prompt
+    if pool == 'cls':
+        y = layer_norm(x, sd['transformer.norm.weight'], sd['transformer.norm.bias'])[:, 0]
+    else:
+        y = layer_norm(x[:, :P + 1], sd['transformer.norm.weight'], sd['transformer.norm.bias']).mean(dim=1)
+    return y @ sd['mlp_head.weight'].t() + sd['mlp_head.bias']

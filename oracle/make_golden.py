@@ -13,7 +13,7 @@ import numpy as np
 import torch
 
 from . import refload
-from .cases import GAVIKO_CASES, VARIANT_CASES
+from .cases import GAVIKO_CASES, NEXT_CASES, VARIANT_CASES
 from .golden_fill import golden_eval_volume, golden_fill, golden_labels, golden_volume
 
 OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'tests', 'golden')
@@ -36,6 +36,8 @@ def build_variant(ref, method, kw):
         return ref.MeLO(vit=ref.VisionTransformer(**kw), **kw)   # train.py:145-147
     if method in ('deep_vpt', 'shallow_vpt'):
         return ref.PromptedVisionTransformer(**kw)
+    if method == 'dvpt':
+        return ref.DynamicVisualPromptTuning(**kw)
     raise ValueError(method)
 
 
@@ -161,6 +163,8 @@ def main():
         for name, (kw, batch) in GAVIKO_CASES.items():
             run_case(ref, ref.Gaviko(**kw), kw, batch, name, bf16_floor=True)
         for name, (method, kw, batch) in VARIANT_CASES.items():
+            run_case(ref, build_variant(ref, method, kw), kw, batch, name, bf16_floor=True)
+        for name, (method, kw, batch) in NEXT_CASES.items():
             run_case(ref, build_variant(ref, method, kw), kw, batch, name, bf16_floor=True)
     finally:
         os.chdir(cwd)

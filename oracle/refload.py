@@ -31,10 +31,12 @@ def load():
     import model.ssf as ssf
     import model.melo as melo
     import model.vpt as vpt
-    for m in (g, vt, af, ssf):
+    import model.dvpt as dvpt
+    for m in (g, vt, af, ssf, dvpt):
         m.load_pretrain = lambda *a, **k: {}       # names bound by `from ... import` (e.g. gaviko.py:7)
     from losses.focal_loss import FocalLoss
     return types.SimpleNamespace(Gaviko=g.Gaviko, VisionTransformer=vt.VisionTransformer, AdaptFormer=af.AdaptFormer,
                                  ScalingShiftingFeatures=ssf.ScalingShiftingFeatures, MeLO=melo.MeLO,
-                                 PromptedVisionTransformer=vpt.PromptedVisionTransformer, FocalLoss=FocalLoss,
+                                 PromptedVisionTransformer=vpt.PromptedVisionTransformer, DynamicVisualPromptTuning=dvpt.DynamicVisualPromptTuning,
+                                 FocalLoss=FocalLoss,
                                  gaviko=g, vision_transformer=vt)

@@ -4,7 +4,7 @@ import pytest
 import torch
 
 from oracle import gaviko_oracle as O
-from oracle.cases import GAVIKO_CASES, VARIANT_CASES
+from oracle.cases import GAVIKO_CASES, NEXT_CASES, VARIANT_CASES
 from oracle.golden_fill import golden_labels, golden_volume
 
 from helpers import grad_parity, load_golden, rel_l2, sd_from_golden
@@ -53,6 +53,21 @@ def test_variant_oracle_matches_reference(name):
         fn = lambda sd, img: O.ssf_forward(sd, img, **common)
     else:
         fn = lambda sd, img: O.vpt_forward(sd, img, deep_prompt=kw['deep_prompt'], **common)
+    _check(g, sd, fn, kw, batch)
+
+
+@pytest.mark.parametrize('name', list(NEXT_CASES))
+def test_next_method_oracle_matches_reference(name):
+    """DVPT.  The oracle restatement is pinned against the live reference ahead of the CUDA path (both pool modes; the
+    trainable set recorded from the reference = prompts + every prompt_proj tensor + head)."""
+    method, kw, batch = NEXT_CASES[name]
+    g = load_golden(name)
+    sd = sd_from_golden(g)
+    names = g['trainable_names'].tolist()
+    assert 'prompt_embeddings' in names and 'prompt_positional_embedding' in names and 'mlp_head.weight' in names
+    assert all(('prompt' in n) or ('head' in n) for n in names) and len(names) == 2 + 5 * 12 + 2
+    fn = lambda sd, img: O.dvpt_forward(sd, img, backbone=kw['backbone'], frame_patch_size=kw['frame_patch_size'], image_patch_size=kw['image_patch_size'],
+                                        num_prompts=kw['num_prompts'], pool=kw['pool'])
     _check(g, sd, fn, kw, batch)
 
 
