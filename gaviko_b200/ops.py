@@ -25,11 +25,21 @@ def _ld(t):
     return t.stride(0)
 
 
+_Tensor, _Parameter = torch.Tensor, torch.nn.Parameter
+
+
 def _set(p, **kw):
+    """Fill a parameter struct; tensors become device addresses, None leaves the field zero.  (The class identity test first: isinstance() on
+    torch.Tensor goes through a Python-level __instancecheck__ and was 9 of the 13 us this helper cost per call, x 564 calls per step.)"""
     for k, v in kw.items():
-        if isinstance(v, torch.Tensor):
-            v = L.ptr(v)
-        if v is not None:
+        if v is None:
+            continue
+        c = v.__class__
+        if c is int or c is float:
+            setattr(p, k, v)
+        elif c is _Tensor or c is _Parameter or isinstance(v, _Tensor):
+            setattr(p, k, L.ptr(v))
+        else:
             setattr(p, k, v)
     return p
 
