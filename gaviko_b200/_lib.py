@@ -105,7 +105,12 @@ def fptr(t):
 
 
 def stream():
-    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    """torch's current stream of the current device as a raw handle.  (torch.cuda.current_stream() builds a Stream object through several
+    Python layers: 14 us per call under the profiler, 20 % of the host time of a training step; the two C calls below are ~0.3 us.)"""
+    try:
+        return C.c_void_p(torch._C._cuda_getCurrentRawStream(torch._C._cuda_getDevice()))
+    except AttributeError:      # private torch entry points moved: fall back to the public API
+        return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
 # Optional per-entry-point timing (tools/profile_step.py): PROFILE = {} enables CUDA-event brackets around every C-ABI call.
