@@ -126,7 +126,7 @@ def run_reference(args):
     value = batch / sec
     line = dict(impl='reference', metric=metric_name(args), value=value, unit='volumes/s', n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
                 ms_per_step=sec * 1e3, higher_is_better=True, scaling='weak', vs_baseline=None, dtype='f32', data='synthetic',
-                config=workload(args, batch, 1), gpu_launches=0,
+                config=workload(args, batch, 1, reference=True), gpu_launches=0,
                 cpu_baseline=dict(value=value, unit='volumes/s', cores=threads, kind='port',
                                   sample=f'{args.steps} steps of batch {batch} (fwd+focal+bwd) of the same {args.backbone} GAViKO workload, fp32, torch CPU'),
                 e2e=dict(value=value, unit='volumes/s', h2d_bytes_per_step=0, d2h_bytes_per_step=0))
@@ -137,8 +137,14 @@ def metric_name(args):
     return f"{'train' if args.mode == 'train' else 'infer'} volumes/sec {args.backbone} GAViKO"
 
 
-def workload(args, batch, world):
-    return dict(workload=f"GAViKO {args.backbone} {'training step (fwd + focal loss + frozen-backbone bwd + clip + Adam)' if args.mode == 'train' else 'batched inference forward'}, "
+def workload(args, batch, world, reference=False):
+    if args.mode != 'train':
+        what = 'batched inference forward'
+    elif reference:       # the CPU arm times what the reference's loop does per step up to loss.backward() (train.py:305-311), dropout off, no clip / Adam
+        what = 'training step WITHOUT the optimiser (fwd + focal loss + frozen-backbone bwd; dropout off)'
+    else:
+        what = 'training step (fwd + focal loss + frozen-backbone bwd + clip + Adam)'
+    return dict(workload=f"GAViKO {args.backbone} {what}, "
                          'synthetic 1x120x160x160 volumes, random-init weights', backbone=args.backbone, per_gpu_batch=batch, global_batch=batch * world,
                 volume='1x120x160x160 fp32', num_prompts=32, tokens=1033, parallelism=f'dp{world}',
                 l2_policy=f'inputs larger than L2: {batch * 12.288:.0f} MB of volumes + >1 GB of activations per step vs 126 MB L2')

@@ -946,6 +946,12 @@ __global__ void __launch_bounds__(256) loss_kernel(const float* __restrict__ log
         for (int k = 0; k < C; ++k) dz[k] = 0.f;
       continue;
     }
+    if (y < 0 || y >= C) {   // out-of-range label: the reference's one_hot / CrossEntropyLoss raise; a device kernel cannot, so poison the result
+      my_loss = __int_as_float(0x7fc00000);
+      if (dz)
+        for (int k = 0; k < C; ++k) dz[k] = __int_as_float(0x7fc00000);
+      continue;
+    }
     if (kind == 1) {  // cross entropy
       float m = -INFINITY;
       for (int k = 0; k < C; ++k) m = fmaxf(m, z[k]);

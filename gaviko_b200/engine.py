@@ -39,8 +39,9 @@ class FrozenCache:
     def __init__(self):
         self._store = {}
 
-    def get(self, key, src, fn):
-        tag = (src.data_ptr(), src._version, src.device, src.dtype)
+    def get(self, key, src, fn, extra=None):
+        """`extra`: versions of further tensors the value depends on (the key stays stable, so a changed tensor REPLACES the entry)."""
+        tag = (src.data_ptr(), src._version, src.device, src.dtype, extra)
         hit = self._store.get(key)
         if hit is not None and hit[0] == tag:
             return hit[1]
@@ -99,7 +100,8 @@ class GavikoEngine:
                 raise NotImplementedError('gaviko_b200 implements the frozen-backbone backward (freeze_vit=True); '
                                           f'backbone tensors require grad: {bad[:3]}...')
         out_dtype = img.dtype
-        logits = _GavikoFn.apply(self, img, need_grad, names, *tensors)
+        with torch.cuda.device(img.device):      # kernels launch on the CURRENT device's stream: make the input's device current (train.py never calls set_device)
+            logits = _GavikoFn.apply(self, img, need_grad, names, *tensors)
         return logits.to(out_dtype) if logits.dtype != out_dtype else logits
 
     # ------------------------------------------------------------------------------------------
@@ -391,7 +393,7 @@ class _GavikoFn(torch.autograd.Function):
         if ctx.saved is None:
             raise RuntimeError('backward called on a forward that ran without gradient tracking')
         saved = ctx.saved
-        with torch.no_grad():
+        with torch.no_grad(), torch.cuda.device(dlogits.device):
             G = ctx.engine.backward(saved, dlogits.float().contiguous())
         ctx.saved = None
         if saved.get('used_sink'):

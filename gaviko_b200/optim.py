@@ -14,6 +14,13 @@ class FlatAdam(torch.optim.Optimizer):
     flat buffers, so autograd accumulates straight into the exchange buffer and no gather/scatter is needed per step."""
 
     def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, max_grad_norm=1.0, process_group=None, world_size=None, model=None):
+        params = list(params)
+        if params and isinstance(params[0], dict):
+            if len(params) != 1:
+                raise ValueError('FlatAdam supports ONE parameter group (the reference trains with one, src/train.py:185-189)')
+            extra = {k: v for k, v in params[0].items() if k != 'params'}
+            lr, betas, eps, weight_decay = extra.get('lr', lr), extra.get('betas', betas), extra.get('eps', eps), extra.get('weight_decay', weight_decay)
+            params = list(params[0]['params'])
         params = [p for p in params if p.requires_grad]
         if not params:
             raise ValueError('FlatAdam: no trainable parameters')
@@ -48,12 +55,59 @@ class FlatAdam(torch.optim.Optimizer):
         self.step_count = 0
         self.group = process_group
         self.world = world_size if world_size is not None else (torch.distributed.get_world_size(process_group) if torch.distributed.is_initialized() else 1)
+        if self.world > 1:
+            # replicas must start identical (DDP broadcasts at construction; the reference's train.py does not seed its RNG): rank 0's values win
+            torch.distributed.broadcast(self.flat_p, src=torch.distributed.get_global_rank(self.group, 0) if self.group is not None else 0, group=self.group)
+
+    def add_param_group(self, param_group):
+        if getattr(self, '_params', None) is not None:
+            raise ValueError('FlatAdam supports ONE parameter group')
+        super().add_param_group(param_group)
 
     def zero_grad(self, set_to_none=False):
         self.flat_g.zero_()       # grads stay views of the flat buffer
+        self._realias()
+
+    def _realias(self, gather=False):
+        """`model.zero_grad()` (set_to_none=True by default) or an autograd path that replaced p.grad detaches a gradient from the flat
+        buffer: fold any such stray gradient in (gather) and point p.grad at its view again."""
+        off = 0
+        pad = lambda k: (k + 15) // 16 * 16  # noqa: E731
+        for p in self._params:
+            k = p.numel()
+            view = self.flat_g[off:off + k].view_as(p)
+            if p.grad is None or p.grad.data_ptr() != view.data_ptr():
+                if gather and p.grad is not None:
+                    view.add_(p.grad.to(view.dtype))
+                p.grad = view
+            off += pad(k)
+
+    def state_dict(self):
+        """torch.optim layout plus the flat Adam moments and the step (they live outside Optimizer.state)."""
+        sd = super().state_dict()
+        sd['flat_adam'] = dict(exp_avg=self.exp_avg.clone(), exp_avg_sq=self.exp_avg_sq.clone(), step=self.step_count, numel=self.numel)
+        return sd
+
+    def load_state_dict(self, state_dict):
+        state_dict = dict(state_dict)
+        fa = state_dict.pop('flat_adam', None)
+        super().load_state_dict(state_dict)
+        if fa is not None:
+            if fa['numel'] != self.numel:
+                raise ValueError('FlatAdam.load_state_dict: the trainable set changed')
+            self.exp_avg.copy_(fa['exp_avg'])
+            self.exp_avg_sq.copy_(fa['exp_avg_sq'])
+            self.step_count = int(fa['step'])
 
     @torch.no_grad()
     def step(self, closure=None):
+        """NB with FlatAdam the clip is part of step(): a `clip_grad_norm_` call left in the training loop would clip the LOCAL gradient before
+        the all-reduce under data parallelism — remove it."""
+        self._realias(gather=True)
+        with torch.cuda.device(self.flat_p.device):
+            self._step()
+
+    def _step(self):
         scale = exchange_flat_gradient(self.flat_g, self.group) if self.world > 1 else 1.0   # SUM; the 1/world mean is folded into grad_scale
         g = self.param_groups[0]
         self.step_count += 1

@@ -12,6 +12,7 @@ import os
 import torch
 import torch.nn.functional as F
 
+_WARNED = False      # warn once per process
 _ARCH = {
     'vit-t16': (12, 3, 192, 768),
     'vit-s16': (12, 6, 384, 1536),
@@ -66,7 +67,14 @@ def load_pretrain(backbone, num_patches, depth_dim, save_dir):
     if path and os.path.exists(path):
         logging.info(f'Converting local pretrained weights {path}')
         return _convert(torch.load(path, map_location='cpu'), num_patches, depth_dim)
-    logging.info('No local pretrained weights (offline build): the ViT backbone keeps its random initialisation.')
+    # The reference downloads the timm ImageNet-21k weights here (load_pretrained.py:24-31).  Offline there is nothing to download: say so loudly,
+    # because fine-tuning PEFT modules on a frozen RANDOM backbone is rarely what a user of the reference configs wants.
+    global _WARNED
+    if _WARNED:
+        return {}
+    _WARNED = True
+    logging.warning(f'gaviko_b200: no local pretrained weights at {path!r} (no network in this build): the frozen ViT backbone keeps its RANDOM '
+                    'initialisation.  Place a timm state_dict there (torch.save(timm_model.state_dict(), path)) to fine-tune a pretrained backbone.')
     return {}
 
 

@@ -70,8 +70,37 @@ class VitEngine:
                 names.append(n)
                 tensors.append(p)
         need_grad = torch.is_grad_enabled() and len(tensors) > 0
-        logits = _VitFn.apply(self, img, need_grad, names, *tensors)
+        if need_grad:
+            self._check_trainable(names)
+        with torch.cuda.device(img.device):      # kernels launch on the CURRENT device's stream
+            logits = _VitFn.apply(self, img, need_grad, names, *tensors)
         return logits.to(img.dtype) if logits.dtype != img.dtype else logits
+
+    def _check_trainable(self, names):
+        """The engine computes gradients for the PEFT tensors only (biases, head, SSF, LoRA, adapter, prompts).  Any other tensor with
+        requires_grad (--method fft, or AdaptFormer / SSF / VPT built with freeze_vit=False) would silently receive zeros: refuse instead."""
+        key = tuple(names)
+        if getattr(self, '_checked_names', None) == key:
+            return
+        W = self._weights(self.compute_dtype())
+        ok = set()
+
+        def add(v):
+            if isinstance(v, (tuple, list)):
+                for x in v:
+                    add(x)
+            elif isinstance(v, str):
+                ok.add(v)
+        add(list(W['names'].values()))
+        for Lw in W['layers']:
+            add(list(Lw['n'].values()))
+        ok.update(('prompt_proj.weight', 'prompt_proj.bias', 'deep_prompt_embeddings', 'prompt_embeddings'))
+        bad = [n for n in names if n not in ok]
+        if bad:
+            raise NotImplementedError('gaviko_b200 implements the frozen-backbone backward of the PEFT methods (linear, bitfit, adaptformer, melo, ssf, '
+                                      f'shallow_vpt, deep_vpt); these tensors require grad but have no weight-gradient kernel: {bad[:4]}'
+                                      f'{" ..." if len(bad) > 4 else ""} ({len(bad)} tensors; full fine-tuning / freeze_vit=False is not supported)')
+        self._checked_names = key
 
     def _seed(self, layer, kind):
         return (torch.initial_seed() * _SEED_MIX + self._step * 1315423911 + layer * 2654435761 + kind * 97) & _MASK63
@@ -138,14 +167,15 @@ class VitEngine:
             if lora:
                 r, s = qkv_mod.r, float(qkv_mod.alpha // qkv_mod.r)
                 Aq, Av, Bq, Bv = qkv_mod.linear_a_q.weight, qkv_mod.linear_a_v.weight, qkv_mod.linear_b_q.weight, qkv_mod.linear_b_v.weight
-                tag = (Aq._version, Av._version, Bq._version, Bv._version)
+                # stable keys + the versions of BOTH stacked tensors in the tag: an optimiser step replaces the entry instead of adding one
+                tag = (Av.data_ptr(), Av._version)
                 Lw['lora'] = dict(r=r, s=s,
                                   # LN1(x) @ (s A)^T gives the scaled latents; B and s B are the up weights of forward / the down weights of backward
-                                  a_stack=cache.get(('loraA', i, tag), Aq, lambda t: torch.cat([Aq.detach().float(), Av.detach().float()], 0).contiguous()),
-                                  sa_stack=cache.get(('lorasA', i, tag), Aq, lambda t: (s * torch.cat([Aq.detach().float(), Av.detach().float()], 0)).contiguous()),
+                                  a_stack=cache.get(('loraA', i), Aq, lambda t: torch.cat([Aq.detach().float(), Av.detach().float()], 0).contiguous(), extra=tag),
+                                  sa_stack=cache.get(('lorasA', i), Aq, lambda t: (s * torch.cat([Aq.detach().float(), Av.detach().float()], 0)).contiguous(), extra=tag),
                                   bq=_f32(Bq), bv=_f32(Bv),
-                                  sbq=cache.get(('lorasBq', i, tag), Bq, lambda t: (s * t.float()).contiguous()),
-                                  sbv=cache.get(('lorasBv', i, tag), Bv, lambda t: (s * t.float()).contiguous()))
+                                  sbq=cache.get(('lorasBq', i), Bq, lambda t: (s * t.float()).contiguous()),
+                                  sbv=cache.get(('lorasBv', i), Bv, lambda t: (s * t.float()).contiguous()))
                 pq = pa + 'to_qkv.'
                 Lw['n'].update(aq=pq + 'linear_a_q.weight', av=pq + 'linear_a_v.weight', bq=pq + 'linear_b_q.weight', bv=pq + 'linear_b_v.weight')
             if ad is not None:
@@ -500,6 +530,6 @@ class _VitFn(torch.autograd.Function):
         if ctx.saved is None:
             raise RuntimeError('backward called on a forward that ran without gradient tracking')
         saved, ctx.saved = ctx.saved, None
-        with torch.no_grad():
+        with torch.no_grad(), torch.cuda.device(dlogits.device):
             G = ctx.engine.backward(saved, dlogits.float().contiguous(), ctx.names)
         return (None, None, None, None, *[G[n].reshape(s).to(d) for n, (s, d) in zip(ctx.names, ctx.shapes)])

@@ -13,6 +13,22 @@ GAVIKO_CASES = {
                               dropout=0.0, emb_dropout=0.0, attn_drop=0.0, proj_drop=0.0, share_factor=2, fp16=False), 3),
 }
 
+# Cases on the reference's OWN random initialisation (the north star's "same random-init ViT weights"): the reference constructor and the drop-in
+# constructor consume the RNG identically (tests/test_dropin_surface.py::test_seeded_construction_equals_reference_init), so
+# `torch.manual_seed(seed); Gaviko(**kw)` gives both sides the same weights without shipping them.  The golden file carries a fingerprint of
+# every tensor (sum, sum of squares) so a drifted init is detected rather than reported as a parity failure.
+# name: (ctor kwargs, batch, seed, store)   store 'all' = every trainable gradient, 'subset' = full gradients of the prompts / head / three
+# layers + 32-element chunk sums of every other tensor (ViT-B / ViT-L gradients are 7 / 18 MB per case otherwise)
+_G = dict(num_classes=5, channels=1, freeze_vit=True, pool='cls', prompt_latent_dim=20, local_dim=20, dropout=0.0, emb_dropout=0.0, attn_drop=0.0,
+          proj_drop=0.0, fp16=False)
+GAVIKO_INIT_CASES = {
+    'gaviko_t16_small_init': (dict(SMALL, **_G, backbone='vit-t16', num_prompts=8, local_k=[3, 2, 2], DHW=[4, 4, 4], share_factor=2), 3, 11, 'all'),
+    'gaviko_t16_full_init': (dict(FULL, **_G, backbone='vit-t16', num_prompts=32, local_k=[6, 6, 6], DHW=[10, 10, 10], share_factor=1), 2, 12, 'all'),
+    # BASELINE.json configs 2/3 (the headline model) and 5
+    'gaviko_b16_full_init': (dict(FULL, **_G, backbone='vit-b16', num_prompts=32, local_k=[6, 6, 6], DHW=[10, 10, 10], share_factor=1), 2, 13, 'subset'),
+    'gaviko_l16_small_init': (dict(SMALL, **_G, backbone='vit-l16', num_prompts=8, local_k=[3, 2, 2], DHW=[4, 4, 4], share_factor=1), 2, 14, 'subset'),
+}
+
 VARIANT_CASES = {
     # name: (method, ctor kwargs, batch)
     'linear_t16_small': ('linear', dict(SMALL, num_classes=5, channels=1, pool='cls', backbone='vit-t16', dropout=0.0, emb_dropout=0.0), 2),

@@ -13,7 +13,8 @@ import numpy as np
 import torch
 
 from . import refload
-from .cases import GAVIKO_CASES, NEXT_CASES, VARIANT_CASES
+from .cases import GAVIKO_CASES, GAVIKO_INIT_CASES, NEXT_CASES, VARIANT_CASES
+from .golden_store import chunk_sums, fingerprint, stored_in_full
 from .golden_fill import golden_eval_volume, golden_fill, golden_labels, golden_volume
 
 OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'tests', 'golden')
@@ -77,8 +78,9 @@ def reference_bf16_deviation(ref, model, img, y, fp32_out):
     return res
 
 
-def run_case(ref, model, kw, batch, name, bf16_floor=False):
-    golden_fill(model, seed=0)
+def run_case(ref, model, kw, batch, name, bf16_floor=False, fill=True, store='all'):
+    if fill:
+        golden_fill(model, seed=0)
     model.eval()
     img = golden_volume(batch, kw['frames'], kw['image_size'], kw['image_size'], channels=kw['channels'])
     y = golden_labels(batch, kw['num_classes'])
@@ -88,6 +90,11 @@ def run_case(ref, model, kw, batch, name, bf16_floor=False):
     out['all_names'] = np.array([n for n, _ in model.named_parameters()])
     out['all_shapes'] = np.array([str(tuple(p.shape)) for _, p in model.named_parameters()])
     out['state_dict_keys'] = np.array(list(model.state_dict().keys()))
+    if not fill:           # weights = the constructor's own seeded init: record a fingerprint of every tensor
+        fp = fingerprint(model.state_dict())
+        out['fingerprint_names'] = np.array(list(fp.keys()))
+        out['fingerprint'] = np.array(list(fp.values()), dtype=np.float64)
+    depth = len(model.transformer.attns) if hasattr(model, 'transformer') and hasattr(model.transformer, 'attns') else 0
     for loss_name, crit in (('focal', ref.FocalLoss(gamma=1.2)), ('ce', torch.nn.CrossEntropyLoss())):
         model.zero_grad(set_to_none=True)
         logits = model(img)
@@ -98,7 +105,11 @@ def run_case(ref, model, kw, batch, name, bf16_floor=False):
         for n, p in model.named_parameters():
             if p.requires_grad:
                 assert p.grad is not None, (name, n)
-                out[f'grad_{loss_name}/{n}'] = p.grad.detach().numpy().copy()
+                if store == 'all' or stored_in_full(n, depth):
+                    out[f'grad_{loss_name}/{n}'] = p.grad.detach().numpy().copy()
+                else:
+                    out[f'gradsum_{loss_name}/{n}'] = chunk_sums(p.grad.detach().numpy())
+                    out[f'gradnorm_{loss_name}/{n}'] = np.float64(p.grad.detach().double().norm().item())
     if bf16_floor:
         out.update(reference_bf16_deviation(ref, model, img, y, out))
     np.savez_compressed(os.path.join(OUT, name + '.npz'), **out)
@@ -150,6 +161,10 @@ def eval_set(ref, n=256):
 
 
 def main():
+    """python -m oracle.make_golden [case ...]   (no arguments: every golden file)"""
+    import sys
+    only = set(sys.argv[1:])
+    want = lambda n: not only or n in only  # noqa: E731
     torch.manual_seed(0)
     torch.set_num_threads(os.cpu_count())
     os.makedirs(OUT, exist_ok=True)
@@ -157,15 +172,26 @@ def main():
     cwd = os.getcwd()
     os.chdir(tempfile.mkdtemp())       # vpt.py:54 appends deep_prompt.txt to the cwd
     try:
-        focal_known_answers(ref)
-        window_masks(ref)
-        eval_set(ref)
+        if want('focal_known_answers'):
+            focal_known_answers(ref)
+        if want('window_masks'):
+            window_masks(ref)
+        if want('gaviko_t16_full_eval256'):
+            eval_set(ref)
         for name, (kw, batch) in GAVIKO_CASES.items():
-            run_case(ref, ref.Gaviko(**kw), kw, batch, name, bf16_floor=True)
+            if want(name):
+                run_case(ref, ref.Gaviko(**kw), kw, batch, name, bf16_floor=True)
+        for name, (kw, batch, seed, store) in GAVIKO_INIT_CASES.items():
+            if want(name):
+                torch.manual_seed(seed)
+                model = ref.Gaviko(**kw)          # the reference's own random init (gaviko.py:445-511 + nn defaults)
+                run_case(ref, model, kw, batch, name, bf16_floor=(store == 'all'), fill=False, store=store)
         for name, (method, kw, batch) in VARIANT_CASES.items():
-            run_case(ref, build_variant(ref, method, kw), kw, batch, name, bf16_floor=True)
+            if want(name):
+                run_case(ref, build_variant(ref, method, kw), kw, batch, name, bf16_floor=True)
         for name, (method, kw, batch) in NEXT_CASES.items():
-            run_case(ref, build_variant(ref, method, kw), kw, batch, name, bf16_floor=True)
+            if want(name):
+                run_case(ref, build_variant(ref, method, kw), kw, batch, name, bf16_floor=True)
     finally:
         os.chdir(cwd)
 

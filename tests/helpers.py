@@ -6,6 +6,7 @@ import numpy as np
 import torch
 
 from oracle.golden_fill import golden_fill
+from oracle.golden_store import chunk_sums, fingerprint
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
 
@@ -45,18 +46,28 @@ def grad_parity(got, g, loss_name, tol_global, tol_tensor, floor=1e-4, floor_sla
     Returns (global_rel, worst_tensor_rel, worst_name).
     """
     names = g['trainable_names'].tolist()
+    files = set(g.files)
+
+    def ref_of(n):
+        """(reference vector, transform applied to our gradient): the full gradient, or its 32-element chunk sums ('subset' store)"""
+        if f'grad_{loss_name}/{n}' in files:
+            return g[f'grad_{loss_name}/{n}'].astype(np.float64), None
+        return g[f'gradsum_{loss_name}/{n}'].astype(np.float64), chunk_sums
+
     num = den = 0.0
     for n in names:
-        r = g[f'grad_{loss_name}/{n}'].astype(np.float64)
+        r, _ = ref_of(n)
         den += float((r ** 2).sum())
     gnorm = den ** 0.5
     worst, worst_name = 0.0, None
     for n in names:
-        r = g[f'grad_{loss_name}/{n}'].astype(np.float64)
+        r, tf = ref_of(n)
         assert n in got and got[n] is not None, f'missing gradient for {n}'
         a = torch.as_tensor(got[n]).detach().double().cpu().numpy()
-        assert a.shape == r.shape, (n, a.shape, r.shape)
         assert np.isfinite(a).all(), f'non-finite gradient in {n}'
+        if tf is not None:
+            a = tf(a)
+        assert a.shape == r.shape, (n, a.shape, r.shape)
         d = float(np.linalg.norm(a - r))
         num += d * d
         rn = float(np.linalg.norm(r))
@@ -70,3 +81,16 @@ def grad_parity(got, g, loss_name, tol_global, tol_tensor, floor=1e-4, floor_sla
     glob = (num ** 0.5) / (gnorm if gnorm > 0 else 1.0)
     assert glob <= tol_global, (loss_name, 'global', glob)
     return glob, worst, worst_name
+
+
+def check_fingerprint(model_or_sd, g, rtol=1e-6):
+    """The seeded constructor init must reproduce the weights the golden file was generated on (oracle/cases.py GAVIKO_INIT_CASES)."""
+    sd = model_or_sd.state_dict() if hasattr(model_or_sd, 'state_dict') else model_or_sd
+    fp = fingerprint(sd)
+    names = g['fingerprint_names'].tolist()
+    assert list(fp.keys()) == names
+    ref = g['fingerprint']
+    for i, n in enumerate(names):
+        s, q = fp[n]
+        assert abs(s - ref[i, 0]) <= rtol * max(1.0, abs(ref[i, 0]), ref[i, 1] ** 0.5) and abs(q - ref[i, 1]) <= rtol * max(1e-30, ref[i, 1]), \
+            f'init drift in {n}: {(s, q)} vs {tuple(ref[i])}'

@@ -79,3 +79,44 @@ def test_variant_names_shapes_match_reference(name, tmp_path, monkeypatch):
     assert [str(tuple(p.shape)) for _, p in model.named_parameters()] == [s.replace(' ', '') if False else s for s in g['all_shapes'].tolist()]
     assert [n for n, p in model.named_parameters() if p.requires_grad] == g['trainable_names'].tolist()
     assert model.train() is None or method in ('linear', 'bitfit', 'melo')      # the overriding classes return None like the reference
+
+
+def test_engine_refuses_trainable_backbone_tensors(tmp_path, monkeypatch):
+    """--method fft, or AdaptFormer / SSF built with freeze_vit=False (their constructor default), must raise instead of silently
+    returning zero gradients for backbone weights the engine has no weight-gradient kernel for; every shipped PEFT trainable set passes."""
+    from oracle.cases import VARIANT_CASES
+    from variant_factory import build_variant
+    from gaviko_b200.model.adaptformer import AdaptFormer
+    from gaviko_b200.model.vision_transformer import VisionTransformer
+    monkeypatch.chdir(tmp_path)
+    for name, (method, kw, _) in VARIANT_CASES.items():
+        m = build_variant(method, kw)
+        m._engine._check_trainable([n for n, p in m.named_parameters() if p.requires_grad])
+    _, kw, _ = VARIANT_CASES['linear_t16_small']
+    fft = VisionTransformer(**kw)
+    with pytest.raises(NotImplementedError, match='no weight-gradient kernel'):
+        fft._engine._check_trainable([n for n, p in fft.named_parameters() if p.requires_grad])
+    _, kw, _ = VARIANT_CASES['adaptformer_t16_small']
+    unfrozen = AdaptFormer(**dict(kw, freeze_vit=False))
+    with pytest.raises(NotImplementedError):
+        unfrozen._engine._check_trainable([n for n, p in unfrozen.named_parameters() if p.requires_grad])
+
+
+def test_lora_cache_does_not_grow_with_optimizer_steps(tmp_path, monkeypatch):
+    """the MeLO side-tensor cache used to key its entries on the parameter versions, adding four entries per layer per step."""
+    from oracle.cases import VARIANT_CASES
+    from variant_factory import build_variant
+    monkeypatch.chdir(tmp_path)
+    method, kw, _ = VARIANT_CASES['melo_t16_small']
+    m = build_variant(method, kw)
+    eng = m._engine
+    W = eng._weights(torch.float32)
+    n0 = len(eng._cache._store)
+    a0 = W['layers'][0]['lora']['a_stack'].clone()
+    with torch.no_grad():
+        for p in m.parameters():
+            if p.requires_grad:
+                p.add_(0.25)                     # an optimiser step bumps every trainable tensor's version
+    W = eng._weights(torch.float32)
+    assert len(eng._cache._store) == n0
+    assert torch.allclose(W['layers'][0]['lora']['a_stack'], a0 + 0.25)      # ... and the cached stack follows BOTH A_q and A_v

@@ -4,10 +4,10 @@ import pytest
 import torch
 
 from oracle import gaviko_oracle as O
-from oracle.cases import GAVIKO_CASES, NEXT_CASES, VARIANT_CASES
+from oracle.cases import GAVIKO_CASES, GAVIKO_INIT_CASES, NEXT_CASES, VARIANT_CASES
 from oracle.golden_fill import golden_labels, golden_volume
 
-from helpers import grad_parity, load_golden, rel_l2, sd_from_golden
+from helpers import check_fingerprint, grad_parity, load_golden, rel_l2, sd_from_golden
 
 TOL = 2e-5   # fp32 noise floor of the reference itself is <=6.5e-6 per tensor
 
@@ -31,6 +31,28 @@ def test_gaviko_oracle_matches_reference(name):
     kw, batch = GAVIKO_CASES[name]
     g = load_golden(name)
     sd = sd_from_golden(g)
+    fn = lambda sd, img: O.gaviko_forward(sd, img, backbone=kw['backbone'], num_prompts=kw['num_prompts'],
+                                          frame_patch_size=kw['frame_patch_size'], image_patch_size=kw['image_patch_size'],
+                                          local_k=kw['local_k'], DHW=kw['DHW'], share_factor=kw['share_factor'])
+    _check(g, sd, fn, kw, batch)
+
+
+@pytest.mark.parametrize('name', list(GAVIKO_INIT_CASES))
+def test_gaviko_oracle_matches_reference_on_its_own_init(name):
+    """The reference's own seeded random init (ViT-T, and the ViT-B / ViT-L models BASELINE.json's configs 2/3/5 name): the drop-in constructor
+    reproduces the weights (fingerprint of every tensor recorded from the live reference), and the oracle restatement reproduces the
+    reference's logits, losses and gradients on them."""
+    import contextlib
+    import io
+    from gaviko_b200.model.gaviko import Gaviko
+    kw, batch, seed, _ = GAVIKO_INIT_CASES[name]
+    g = load_golden(name)
+    torch.manual_seed(seed)
+    with contextlib.redirect_stdout(io.StringIO()):
+        m = Gaviko(**kw)
+    check_fingerprint(m, g)
+    tn = set(g['trainable_names'].tolist())
+    sd = {k: v.detach().clone().requires_grad_(k in tn) for k, v in m.state_dict().items()}
     fn = lambda sd, img: O.gaviko_forward(sd, img, backbone=kw['backbone'], num_prompts=kw['num_prompts'],
                                           frame_patch_size=kw['frame_patch_size'], image_patch_size=kw['image_patch_size'],
                                           local_k=kw['local_k'], DHW=kw['DHW'], share_factor=kw['share_factor'])

@@ -12,19 +12,25 @@ sys.path.insert(0, 'tests')
 from gaviko_b200.losses.focal_loss import CrossEntropyLoss, FocalLoss  # noqa: E402
 from gaviko_b200.model.gaviko import Gaviko  # noqa: E402
 from helpers import load_golden, rel_l2  # noqa: E402
-from oracle.cases import GAVIKO_CASES  # noqa: E402
+from oracle.cases import GAVIKO_CASES, GAVIKO_INIT_CASES  # noqa: E402
 from oracle.golden_fill import golden_fill, golden_labels, golden_volume  # noqa: E402
 
 import contextlib, io  # noqa: E402
 
-cases = sys.argv[1:] or list(GAVIKO_CASES)
+from oracle.golden_store import chunk_sums  # noqa: E402
+
+cases = sys.argv[1:] or (list(GAVIKO_CASES) + list(GAVIKO_INIT_CASES))
 for name in cases:
-    kw, batch = GAVIKO_CASES[name]
+    init = name in GAVIKO_INIT_CASES
+    kw, batch = GAVIKO_INIT_CASES[name][:2] if init else GAVIKO_CASES[name]
     g = load_golden(name)
     for mode in ('fp32', 'bf16'):
+        if init:
+            torch.manual_seed(GAVIKO_INIT_CASES[name][2])
         with contextlib.redirect_stdout(io.StringIO()):
             model = Gaviko(**kw, compute_dtype=mode)
-        golden_fill(model, seed=0)
+        if not init:
+            golden_fill(model, seed=0)
         model = model.cuda()
         model.eval()
         img = golden_volume(batch, kw['frames'], kw['image_size'], kw['image_size']).cuda()
@@ -38,8 +44,11 @@ for name in cases:
             for n, p in model.named_parameters():
                 if not p.requires_grad:
                     continue
-                r = g[f'grad_{loss_name}/{n}'].astype(np.float64)
                 a = p.grad.double().cpu().numpy()
+                if f'grad_{loss_name}/{n}' in g.files:
+                    r = g[f'grad_{loss_name}/{n}'].astype(np.float64)
+                else:                                   # 'subset' store: 32-element chunk sums
+                    r, a = g[f'gradsum_{loss_name}/{n}'].astype(np.float64), chunk_sums(a)
                 d = float(np.linalg.norm(a - r))
                 rn = float(np.linalg.norm(r))
                 num += d * d
