@@ -117,6 +117,47 @@ def cpu_reference_step_time(backbone, batch, steps, warmup, mode):
     return sum(times) / len(times), torch.get_num_threads()
 
 
+def gpu_eager_step_time(backbone, batch, steps, warmup, mode, dtype, dev):
+    """The reference's algorithm in eager PyTorch ON THE SAME B200 (SURVEY 8d "beat it on the same box"): the oracle port moved to `dev` unchanged, so
+    every op dispatches to ATen / cuBLAS as the reference's own modules would; fp32 as the scripts ship it, or `.to(bfloat16)`.  Train step =
+    fwd + focal loss + bwd + clip_grad_norm_ + Adam over the trainable set (train.py:305-319), dropout off.  The oracle is the checker and sits outside
+    our timed region; this leg is a reported baseline.  Returns seconds / step."""
+    from oracle import gaviko_oracle as O
+    from oracle.golden_fill import golden_fill, golden_labels, golden_volume
+    from tests_support import sd_for_backbone
+    sd, trainable = sd_for_backbone(backbone)
+    golden_fill(sd, seed=0)
+    sd = {k: v.to(dev, dtype) for k, v in sd.items()}
+    params = []
+    for n in trainable:
+        sd[n].requires_grad_(True)
+        params.append(sd[n])
+    opt = torch.optim.Adam(params, lr=1e-4, eps=1e-8) if mode == 'train' else None
+    img = golden_volume(batch, 120, 160, 160).to(dev, dtype)
+    y = golden_labels(batch).to(dev)
+    kw = dict(backbone=backbone, num_prompts=32, frame_patch_size=12, image_patch_size=16, local_k=[6, 6, 6], DHW=[10, 10, 10])
+
+    def step():
+        if mode == 'train':
+            opt.zero_grad(set_to_none=True)
+            O.focal_loss(O.gaviko_forward(sd, img, **kw).float(), y).backward()
+            torch.nn.utils.clip_grad_norm_(params, 1.0)
+            opt.step()
+        else:
+            with torch.no_grad():
+                O.gaviko_forward(sd, img, **kw)
+    for _ in range(warmup):
+        step()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(steps):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / 1e3 / steps
+
+
 def run_reference(args):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
@@ -305,11 +346,27 @@ def run_ours(args):
                            sample=f'1 warm-up + 8 timed steps of batch 2 (~10 s) of the same {args.backbone} GAViKO {args.mode} workload (oracle port, fp32, torch CPU threads)')
             except Exception as ex:  # noqa: BLE001
                 cpu = dict(value=None, unit='volumes/s', cores=os.cpu_count(), kind='port', sample=f'failed: {ex}')
+        eager = None
+        if world == 1 and not args.no_gpu_eager_baseline:
+            del model, x_dev, bufs
+            if train:
+                del opt, sched
+            torch.cuda.empty_cache()
+            eager = {}
+            eb = min(B, 8)         # the eager path materialises (B, 12, T, T) scores per layer and keeps them for backward: ~1.2 GB / volume fp32
+            for name, dt in (('fp32', torch.float32), ('bf16', torch.bfloat16)):
+                try:
+                    sec = gpu_eager_step_time(args.backbone, eb, 3, 2, args.mode, dt, dev)
+                    eager[name] = dict(value=eb / sec, unit='volumes/s', ms_per_step=sec * 1e3,
+                                       sample=f'2 warm-up + 3 timed steps of batch {eb}: oracle port of the reference in eager PyTorch on this GPU ({name}; ATen / cuBLAS; dropout off)')
+                except Exception as ex:  # noqa: BLE001
+                    eager[name] = dict(value=None, unit='volumes/s', sample=f'failed: {type(ex).__name__}: {ex}'[:300])
+                torch.cuda.empty_cache()
         line = dict(metric=metric_name(args), value=value, unit='volumes/s', n_gpus=world, steps=args.steps, warmup=args.warmup, ms_per_step=ms / args.steps,
                     higher_is_better=True, scaling='weak', vs_baseline=None, dtype=args.dtype, data='synthetic', config=workload(args, B, world), clocks=clocks,
                     e2e=dict(value=e2e_value, unit='volumes/s', h2d_bytes_per_step=world * (B * 120 * 160 * 160 * 4 + B * 8), d2h_bytes_per_step=world * 4,
                              ms_per_step=ms_e2e / args.steps),
-                    gpu_launches=launches, roofline=roof, cpu_baseline=cpu,
+                    gpu_launches=launches, roofline=roof, cpu_baseline=cpu, gpu_eager_baseline=eager,
                     tflops_algorithmic=world * B * args.steps * flops_per_vol / (ms / 1e3) / 1e12)
         print(json.dumps(line))
     if world > 1:
@@ -327,6 +384,7 @@ def main():
     ap.add_argument('--batch', type=int, default=64, help='volumes per GPU per step (SURVEY 8d: 16 | 32 | 64)')
     ap.add_argument('--dtype', default='bf16', choices=['bf16', 'fp32'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-gpu-eager-baseline', action='store_true', help='skip timing the eager-PyTorch port of the reference on this GPU (N=1 only)')
     args = ap.parse_args()
     if args.impl == 'reference':
         run_reference(args)

@@ -97,6 +97,18 @@ def ptr(t, dtype=None):
     return t.data_ptr()
 
 
+def require_cuda(t, what='gaviko_b200 models'):
+    """There is no CPU fallback: a CPU tensor is an error, not a slow path."""
+    if not t.is_cuda:
+        raise GvkError(f'{what} run on CUDA only (no CPU fallback): move the model and the input to a B200')
+
+
+def device_guard(t):
+    """Make the tensor's device current for the enclosed launches: kernels go to the CURRENT device's stream, and the reference's scripts never
+    call torch.cuda.set_device (train.py:99)."""
+    return torch.cuda.device(t.device)
+
+
 def fptr(t):
     """fp32, contiguous device tensor (or None)."""
     if t is not None and not t.is_contiguous():

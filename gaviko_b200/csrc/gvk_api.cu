@@ -97,6 +97,7 @@ long long gvk_struct_size(const char* name) {
   GVK_SZ(gvk_skinny_wgrad_params) GVK_SZ(gvk_layernorm_bwd_params) GVK_SZ(gvk_ssf_bwd_params) GVK_SZ(gvk_dropout_params) GVK_SZ(gvk_attn_fwd_params) GVK_SZ(gvk_attn_bwd_params)
   GVK_SZ(gvk_fusion_weights) GVK_SZ(gvk_fusion_grads) GVK_SZ(gvk_fusion_saved) GVK_SZ(gvk_fusion_fwd_params)
   GVK_SZ(gvk_fusion_bwd_params) GVK_SZ(gvk_head_fwd_params) GVK_SZ(gvk_head_bwd_params) GVK_SZ(gvk_mhsa_fwd_params) GVK_SZ(gvk_mhsa_bwd_params) GVK_SZ(gvk_rescale_intensity_params)
+  GVK_SZ(gvk_latent_xattn_fwd_params) GVK_SZ(gvk_latent_xattn_bwd_params)
 #undef GVK_SZ
   return -1;
 }
@@ -134,6 +135,16 @@ int gvk_batch_rowsum(const float* x, int ldx, int batch_rows, int row_offset, in
 int gvk_prompt_fusion_fwd(const gvk_fusion_fwd_params* p, gvk_stream_t stream) { return gvk::prompt_fusion_fwd(p, S(stream)); }
 int gvk_prompt_fusion_bwd(const gvk_fusion_bwd_params* p, gvk_stream_t stream) { return gvk::prompt_fusion_bwd(p, S(stream)); }
 int gvk_quickgelu_bwd(const float* dy, const float* pre, float* y, size_t n, gvk_stream_t stream) { return gvk::quickgelu_bwd(dy, pre, y, n, S(stream)); }
+int gvk_quickgelu_fwd(const float* x, float* y, size_t n, gvk_stream_t stream) { return gvk::quickgelu_fwd(x, y, n, S(stream)); }
+int gvk_quickgelu_bwd_add(const float* dy, const float* pre, const float* res, float* y, size_t n, gvk_stream_t stream) {
+  return gvk::quickgelu_bwd_add(dy, pre, res, y, n, S(stream));
+}
+int gvk_latent_xattn_fwd(const gvk_latent_xattn_fwd_params* p, gvk_stream_t stream) { return gvk::latent_xattn_fwd(p, S(stream)); }
+int gvk_latent_xattn_bwd(const gvk_latent_xattn_bwd_params* p, gvk_stream_t stream) { return gvk::latent_xattn_bwd(p, S(stream)); }
+int gvk_gate_scale(const float* x, const float* gate, float* y, size_t n, gvk_stream_t stream) { return gvk::gate_scale(x, gate, y, n, S(stream)); }
+int gvk_gate_grads(const float* x, const float* dy, const float* gate, float* dx, float* dgate, size_t n, gvk_stream_t stream) {
+  return gvk::gate_grads(x, dy, gate, dx, dgate, n, S(stream));
+}
 int gvk_head_fwd(const gvk_head_fwd_params* p, gvk_stream_t stream) { return gvk::head_fwd(p, S(stream)); }
 int gvk_head_bwd(const gvk_head_bwd_params* p, gvk_stream_t stream) { return gvk::head_bwd(p, S(stream)); }
 int gvk_loss_fwd_bwd(const float* logits, const long long* target, int B, int C, int kind, float gamma, float eps, long long ignore_index, float* loss, float* dlogits,

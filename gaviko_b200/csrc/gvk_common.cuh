@@ -77,6 +77,12 @@ int mhsa_ws_fwd(const gvk_mhsa_fwd_params* p, cudaStream_t stream);
 int prompt_fusion_fwd(const gvk_fusion_fwd_params* p, cudaStream_t stream);
 int prompt_fusion_bwd(const gvk_fusion_bwd_params* p, cudaStream_t stream);
 int quickgelu_bwd(const float* dy, const float* pre, float* y, size_t n, cudaStream_t stream);
+int quickgelu_fwd(const float* x, float* y, size_t n, cudaStream_t stream);
+int quickgelu_bwd_add(const float* dy, const float* pre, const float* res, float* y, size_t n, cudaStream_t stream);
+int latent_xattn_fwd(const gvk_latent_xattn_fwd_params* p, cudaStream_t stream);
+int latent_xattn_bwd(const gvk_latent_xattn_bwd_params* p, cudaStream_t stream);
+int gate_scale(const float* x, const float* gate, float* y, size_t n, cudaStream_t stream);
+int gate_grads(const float* x, const float* dy, const float* gate, float* dx, float* dgate, size_t n, cudaStream_t stream);
 int relu_bwd(const float* dy, const float* z, float* y, size_t n, cudaStream_t stream);
 int head_fwd(const gvk_head_fwd_params* p, cudaStream_t stream);
 int head_bwd(const gvk_head_bwd_params* p, cudaStream_t stream);

@@ -10,6 +10,7 @@ fp32 accumulation; residual streams, LayerNorm statistics, softmax and every ran
 """
 import torch
 
+from . import _lib as _L
 from . import ops
 from ._lib import GvkError
 
@@ -84,8 +85,7 @@ class GavikoEngine:
     # ------------------------------------------------------------------------------------------
     def __call__(self, img):
         m = self.module
-        if not img.is_cuda:
-            raise GvkError('gaviko_b200.Gaviko runs on CUDA only (no CPU fallback): move the model and the input to a B200')
+        _L.require_cuda(img)
         if m.pos_embedding.device != img.device:
             raise GvkError('model and input are on different devices')
         names, tensors = [], []
@@ -100,7 +100,7 @@ class GavikoEngine:
                 raise NotImplementedError('gaviko_b200 implements the frozen-backbone backward (freeze_vit=True); '
                                           f'backbone tensors require grad: {bad[:3]}...')
         out_dtype = img.dtype
-        with torch.cuda.device(img.device):      # kernels launch on the CURRENT device's stream: make the input's device current (train.py never calls set_device)
+        with _L.device_guard(img):      # kernels launch on the CURRENT device's stream: make the input's device current (train.py never calls set_device)
             logits = _GavikoFn.apply(self, img, need_grad, names, *tensors)
         return logits.to(out_dtype) if logits.dtype != out_dtype else logits
 
@@ -393,7 +393,7 @@ class _GavikoFn(torch.autograd.Function):
         if ctx.saved is None:
             raise RuntimeError('backward called on a forward that ran without gradient tracking')
         saved = ctx.saved
-        with torch.no_grad(), torch.cuda.device(dlogits.device):
+        with torch.no_grad(), _L.device_guard(dlogits):
             G = ctx.engine.backward(saved, dlogits.float().contiguous())
         ctx.saved = None
         if saved.get('used_sink'):

@@ -446,6 +446,54 @@ def quickgelu_bwd(dy, pre, out=None):
     return out
 
 
+# ---------------------------------------------------------------------------------------------- DVPT side path
+def quickgelu_fwd(x, out=None):
+    if out is None:
+        out = torch.empty_like(x)
+    L.call('gvk_quickgelu_fwd', C.c_void_p(L.fptr(x)), C.c_void_p(L.fptr(out)), C.c_size_t(x.numel()), L.stream())
+    return out
+
+
+def quickgelu_bwd_add(dy, pre, res=None, out=None):
+    """out = res + dy * quickgelu'(pre)"""
+    if out is None:
+        out = torch.empty_like(dy)
+    L.call('gvk_quickgelu_bwd_add', C.c_void_p(L.fptr(dy)), C.c_void_p(L.fptr(pre)), C.c_void_p(L.fptr(res)) if res is not None else None,
+           C.c_void_p(L.fptr(out)), C.c_size_t(dy.numel()), L.stream())
+    return out
+
+
+def latent_xattn_fwd(z, B, T, P, scale):
+    """z [B*T, r] modified in place (prompt rows <- attention output); returns (pl [B*P, r], lse [B*P])."""
+    r = z.shape[1]
+    pl = torch.empty((B * P, r), device=z.device, dtype=torch.float32)
+    lse = torch.empty(B * P, device=z.device, dtype=torch.float32)
+    p = S['gvk_latent_xattn_fwd_params']()
+    _set(p, z=L.fptr(z), B=B, T=T, P=P, r=r, scale=scale, pl=pl, lse=lse)
+    L.call('gvk_latent_xattn_fwd', C.byref(p), L.stream())
+    return pl, lse
+
+
+def latent_xattn_bwd(z, pl, lse, dz, B, T, P, scale):
+    """dz [B*T, r]: d(combined) in, d(latent) out (in place)."""
+    p = S['gvk_latent_xattn_bwd_params']()
+    _set(p, z=L.fptr(z), pl=L.fptr(pl), lse=L.fptr(lse), dz=L.fptr(dz), B=B, T=T, P=P, r=z.shape[1], scale=scale)
+    L.call('gvk_latent_xattn_bwd', C.byref(p), L.stream())
+    return dz
+
+
+def gate_scale(x, gate):
+    out = torch.empty_like(x)
+    L.call('gvk_gate_scale', C.c_void_p(L.fptr(x)), C.c_void_p(L.fptr(gate)), C.c_void_p(L.fptr(out)), C.c_size_t(x.numel()), L.stream())
+    return out
+
+
+def gate_grads(x, dy, gate, dx, dgate):
+    """dx += gate * dy; dgate += <x, dy>"""
+    L.call('gvk_gate_grads', C.c_void_p(L.fptr(x)), C.c_void_p(L.fptr(dy)), C.c_void_p(L.fptr(gate)), C.c_void_p(L.fptr(dx)), C.c_void_p(L.fptr(dgate)),
+           C.c_size_t(x.numel()), L.stream())
+
+
 # ---------------------------------------------------------------------------------------------- head / loss
 def _head_params(x, B, T, pool_start, pool_count, gamma, beta, wh, bh, pooled, logits, eps, ssf_scale, ssf_shift):
     f = S['gvk_head_fwd_params']()

@@ -15,6 +15,7 @@ PyTorch is plumbing here (allocation, views, concatenation of token blocks, auto
 """
 import torch
 
+from . import _lib as _L
 from . import ops
 from ._lib import GvkError
 from .engine import FrozenCache, _f32, _resolve_dtype
@@ -62,8 +63,7 @@ class VitEngine:
     # ------------------------------------------------------------------------------------------
     def __call__(self, img):
         m = self.module
-        if not img.is_cuda:
-            raise GvkError('gaviko_b200 models run on CUDA only (no CPU fallback): move the model and the input to a B200')
+        _L.require_cuda(img)
         names, tensors = [], []
         for n, p in m.named_parameters():
             if p.requires_grad:
@@ -72,7 +72,7 @@ class VitEngine:
         need_grad = torch.is_grad_enabled() and len(tensors) > 0
         if need_grad:
             self._check_trainable(names)
-        with torch.cuda.device(img.device):      # kernels launch on the CURRENT device's stream
+        with _L.device_guard(img):      # kernels launch on the CURRENT device's stream
             logits = _VitFn.apply(self, img, need_grad, names, *tensors)
         return logits.to(img.dtype) if logits.dtype != img.dtype else logits
 
@@ -530,6 +530,6 @@ class _VitFn(torch.autograd.Function):
         if ctx.saved is None:
             raise RuntimeError('backward called on a forward that ran without gradient tracking')
         saved, ctx.saved = ctx.saved, None
-        with torch.no_grad(), torch.cuda.device(dlogits.device):
+        with torch.no_grad(), _L.device_guard(dlogits):
             G = ctx.engine.backward(saved, dlogits.float().contiguous(), ctx.names)
         return (None, None, None, None, *[G[n].reshape(s).to(d) for n, (s, d) in zip(ctx.names, ctx.shapes)])

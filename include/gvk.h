@@ -391,6 +391,38 @@ int gvk_quickgelu_bwd(const float* dy, const float* pre, float* y, size_t n, gvk
 int gvk_relu_bwd(const float* dy, const float* z, float* y, size_t n, gvk_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------------------------
+ * DVPT side path — share_MLP of model/dvpt.py:25-47:  prompt = (W_u cat[softmax(pl tok^T d_model^-0.5) tok ; cl ; tok] + b_u) * gate,
+ * [pl ; cl ; tok] = W_d QuickGELU(x) + b_d.  The two projections are gvk_rowproj_down / gvk_rowproj_up on QuickGELU(x) and on gate-scaled
+ * copies of (W_u, b_u); the pieces below are what DVPT adds.
+ * ------------------------------------------------------------------------------------------------------------------ */
+/* y = x * sigmoid(1.702 x) over n elements (n % 4 == 0): QuickGELU BEFORE the down-projection (model/dvpt.py:37). */
+int gvk_quickgelu_fwd(const float* x, float* y, size_t n, gvk_stream_t stream);
+/* y = res + dy * quick_gelu'(pre) over n elements (res optional; y may alias dy or res). */
+int gvk_quickgelu_bwd_add(const float* dy, const float* pre, const float* res, float* y, size_t n, gvk_stream_t stream);
+
+/* Cross attention of the P prompt latents over the N = T - P - 1 token latents of each volume (model/dvpt.py:38-45), r = 20:
+ *   z[b, p] <- softmax(scale * z[b, p] . tok) tok,   tok = z[b, P+1:]          (IN PLACE over the prompt rows; cls and token rows untouched)
+ * pl receives the prompt latents the rows held before (the queries), lse the log-sum-exp of every row of the attention. */
+typedef struct {
+  float* z; int B, T, P, r; float scale;
+  float* pl;   /* [B, P, r] */
+  float* lse;  /* [B, P] */
+} gvk_latent_xattn_fwd_params;
+int gvk_latent_xattn_fwd(const gvk_latent_xattn_fwd_params* p, gvk_stream_t stream);
+/* Backward: dz holds d(combined latent) [B, T, r] on entry and d(latent before the attention) on exit (in place). */
+typedef struct {
+  const float* z;   /* combined latent as left by the forward */
+  const float* pl; const float* lse;
+  float* dz; int B, T, P, r; float scale;
+} gvk_latent_xattn_bwd_params;
+int gvk_latent_xattn_bwd(const gvk_latent_xattn_bwd_params* p, gvk_stream_t stream);
+
+/* The scalar prompt_gate folded into the up-projection parameters (model/dvpt.py:30,46): y = gate[0] * x, and from the gradient dy of
+ * y:  dx += gate[0] * dy,  dgate[0] += <x, dy>  (one CTA, deterministic). */
+int gvk_gate_scale(const float* x, const float* gate, float* y, size_t n, gvk_stream_t stream);
+int gvk_gate_grads(const float* x, const float* dy, const float* gate, float* dx, float* dgate, size_t n, gvk_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
  * Head: final LayerNorm on the pooled rows only, mean-pool, Linear  (model/gaviko.py:306,314-316;
  * model/vision_transformer.py:159-164 with pool = 'cls' -> rows [0,1), 'mean' -> rows [0,T)).
  *   pooled[b] = mean_{r in [pool_start, pool_start+pool_count)} LN(x[b, r]) (* ssf_scale + ssf_shift);  logits = pooled Wh^T + bh

@@ -66,19 +66,41 @@ def test_seeded_construction_equals_reference_init():
         assert torch.equal(sa[k], sb[k]), k
 
 
-@pytest.mark.parametrize('name', list(__import__('oracle.cases', fromlist=['VARIANT_CASES']).VARIANT_CASES))
+def _all_variant_cases():
+    from oracle.cases import NEXT_CASES, VARIANT_CASES
+    return dict(VARIANT_CASES, **NEXT_CASES)
+
+
+@pytest.mark.parametrize('name', list(_all_variant_cases()))
 def test_variant_names_shapes_match_reference(name, tmp_path, monkeypatch):
-    """Every --method variant exposes the reference's parameter names, shapes and trainable set (= the checkpoint layout, train.py:161-167)."""
-    from oracle.cases import VARIANT_CASES
+    """Every --method variant (incl. dvpt) exposes the reference's parameter names, shapes and trainable set (= the checkpoint layout,
+    train.py:161-167)."""
     from variant_factory import build_variant
     monkeypatch.chdir(tmp_path)
-    method, kw, _ = VARIANT_CASES[name]
+    method, kw, _ = _all_variant_cases()[name]
     model = build_variant(method, kw)
     g = load_golden(name)
     assert [n for n, _ in model.named_parameters()] == g['all_names'].tolist()
     assert [str(tuple(p.shape)) for _, p in model.named_parameters()] == [s.replace(' ', '') if False else s for s in g['all_shapes'].tolist()]
     assert [n for n, p in model.named_parameters() if p.requires_grad] == g['trainable_names'].tolist()
     assert model.train() is None or method in ('linear', 'bitfit', 'melo')      # the overriding classes return None like the reference
+
+
+@pytest.mark.skipif(not refload.available(), reason='live reference only exists in the build container')
+def test_dvpt_seeded_construction_equals_reference_init():
+    from oracle.cases import NEXT_CASES
+    from gaviko_b200.model.dvpt import DynamicVisualPromptTuning
+    ref = refload.load()
+    _, kw, _ = NEXT_CASES['dvpt_t16_small']
+    torch.manual_seed(3)
+    a = ref.DynamicVisualPromptTuning(**kw)
+    torch.manual_seed(3)
+    b = DynamicVisualPromptTuning(**kw)
+    sa, sb = a.state_dict(), b.state_dict()
+    assert list(sa.keys()) == list(sb.keys())
+    for k in sa:
+        assert torch.equal(sa[k], sb[k]), k
+    assert [n for n, p in a.named_parameters() if p.requires_grad] == [n for n, p in b.named_parameters() if p.requires_grad]
 
 
 def test_engine_refuses_trainable_backbone_tensors(tmp_path, monkeypatch):

@@ -423,3 +423,44 @@ def test_patch_gather_and_token_rows():
     assert out.view(3, 20, 192)[:, 7:].abs().max().item() == 0
     x = torch.randn(3 * 20, 192, device=DEV)
     close(ops.batch_rowsum(x, 20, 2, 5, 3), x.view(3, 20, 192)[:, 2:7].double().sum(0))
+
+
+# ---------------------------------------------------------------------------------------------- DVPT side path (csrc/gvk_dvpt.cu)
+@pytest.mark.parametrize('B,T,P', [(3, 69, 4), (2, 71, 6), (2, 1051, 50), (1, 1033, 32)])
+def test_dvpt_latent_xattn_fwd_bwd(B, T, P):
+    """Prompt -> token cross attention in the 20-wide latent (model/dvpt.py:38-45) against its torch restatement (tests/ops_double.py)."""
+    import ops_double as D
+    torch.manual_seed(T + P)
+    r, scale = 20, 192 ** -0.5
+    z = torch.randn(B * T, r, device=DEV)
+    zc, zr = z.clone(), z.cpu().clone()
+    pl, lse = ops.latent_xattn_fwd(zc, B, T, P, scale)
+    plr, lser = D.latent_xattn_fwd(zr, B, T, P, scale)
+    close(zc.cpu(), zr)
+    close(pl.cpu(), plr)
+    close(lse.cpu(), lser)
+    dz = torch.randn(B * T, r, device=DEV)
+    dzr = dz.cpu().clone()
+    ops.latent_xattn_bwd(zc, pl, lse, dz, B, T, P, scale)
+    D.latent_xattn_bwd(zr, plr, lser, dzr, B, T, P, scale)
+    close(dz.cpu(), dzr, 1e-4)
+
+
+def test_dvpt_quickgelu_and_gate_kernels():
+    import ops_double as D
+    torch.manual_seed(3)
+    x = torch.randn(517, 768, device=DEV) * 2
+    close(ops.quickgelu_fwd(x).cpu(), D.quickgelu_fwd(x.cpu()))
+    dy, res = torch.randn_like(x), torch.randn_like(x)
+    close(ops.quickgelu_bwd_add(dy, x, res=res).cpu(), D.quickgelu_bwd_add(dy.cpu(), x.cpu(), res=res.cpu()))
+    close(ops.quickgelu_bwd_add(dy, x).cpu(), D.quickgelu_bwd_add(dy.cpu(), x.cpu()))
+    out = res.clone()
+    ops.quickgelu_bwd_add(dy, x, res=out, out=out)                 # in place over the residual
+    close(out.cpu(), D.quickgelu_bwd_add(dy.cpu(), x.cpu(), res=res.cpu()))
+    w, dw = torch.randn(768, 20, device=DEV), torch.randn(768, 20, device=DEV)
+    gate = torch.tensor([0.37], device=DEV)
+    close(ops.gate_scale(w, gate).cpu(), 0.37 * w.cpu())
+    acc, dgate = torch.ones_like(w), torch.tensor([2.0], device=DEV)
+    ops.gate_grads(w, dw, gate, acc, dgate)
+    close(acc.cpu(), 1 + 0.37 * dw.cpu())
+    close(dgate.cpu(), 2.0 + (w.double() * dw.double()).sum().cpu().reshape(1), 1e-5)

@@ -6,7 +6,7 @@ import pytest
 import torch
 
 from gaviko_b200.losses.focal_loss import CrossEntropyLoss, FocalLoss
-from oracle.cases import VARIANT_CASES
+from oracle.cases import NEXT_CASES, VARIANT_CASES
 from oracle.golden_fill import golden_fill, golden_labels, golden_volume
 
 from helpers import grad_parity, load_golden, rel_l2
@@ -15,8 +15,11 @@ from variant_factory import build_variant
 pytestmark = pytest.mark.gpu
 
 
+ALL_CASES = dict(VARIANT_CASES, **NEXT_CASES)       # NEXT_CASES: SURVEY f3 (dvpt, both pool modes)
+
+
 def _build(name, compute_dtype, tmp_path):
-    method, kw, batch = VARIANT_CASES[name]
+    method, kw, batch = ALL_CASES[name]
     cwd = os.getcwd()
     os.chdir(tmp_path)                      # PromptedVisionTransformer appends to ./deep_prompt.txt like the reference
     try:
@@ -31,7 +34,7 @@ def _build(name, compute_dtype, tmp_path):
     return model, img, y
 
 
-@pytest.mark.parametrize('name', list(VARIANT_CASES))
+@pytest.mark.parametrize('name', list(ALL_CASES))
 def test_variant_fp32_matches_reference(name, tmp_path):
     """fp32 mode: logits and every trainable gradient within 1e-4 relative of the reference (north star tolerance)."""
     g = load_golden(name)
@@ -50,7 +53,7 @@ def test_variant_fp32_matches_reference(name, tmp_path):
         print(f'{name} {loss_name}: logits rel {rl:.2e} grads global {glob:.2e} worst {worst:.2e} ({wname})')
 
 
-@pytest.mark.parametrize('name', list(VARIANT_CASES))
+@pytest.mark.parametrize('name', list(ALL_CASES))
 def test_variant_bf16_matches_reference(name, tmp_path):
     """bf16 mode (tcgen05 GEMMs / attention): logits within 2e-2 relative with identical argmax; gradients within 2e-2 relative globally or,
     where pure bf16 arithmetic cannot reach that on these weights (adaptformer: the reference's own bf16 run deviates 2e-2 .. 1e-1), at

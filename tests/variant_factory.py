@@ -1,5 +1,6 @@
 """Build a drop-in variant the way reference src/train.py:111-153 does for its --method switch."""
 from gaviko_b200.model.adaptformer import AdaptFormer
+from gaviko_b200.model.dvpt import DynamicVisualPromptTuning
 from gaviko_b200.model.melo import MeLO
 from gaviko_b200.model.ssf import ScalingShiftingFeatures
 from gaviko_b200.model.vision_transformer import VisionTransformer
@@ -20,4 +21,6 @@ def build_variant(method, kw):
         return MeLO(vit=VisionTransformer(**kw), **kw)           # train.py:145-147
     if method in ('deep_vpt', 'shallow_vpt'):
         return PromptedVisionTransformer(**kw)
+    if method == 'dvpt':
+        return DynamicVisualPromptTuning(**kw)
     raise ValueError(method)
