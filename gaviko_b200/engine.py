@@ -8,6 +8,8 @@ and the autograd graph ``src/train.py:305-311`` builds over it.  PyTorch is plum
 Compute modes: 'fp32' (exact FFMA GEMMs + SIMT attention; the 1e-4 parity mode) and 'bf16' (tcgen05 GEMMs / attention with
 fp32 accumulation; residual streams, LayerNorm statistics, softmax and every rank-r side path stay fp32).
 """
+import os
+
 import torch
 
 from . import _lib as _L
@@ -19,6 +21,8 @@ _MASK63 = (1 << 63) - 1
 
 
 def _resolve_dtype(compute_dtype, param_dtype):
+    if compute_dtype is None:
+        compute_dtype = os.environ.get('GAVIKO_COMPUTE_DTYPE') or None      # lets an unmodified script pick the mode (gaviko_b200/launch.py)
     if compute_dtype is None:
         return torch.float32 if param_dtype == torch.float32 else torch.bfloat16
     if isinstance(compute_dtype, torch.dtype):
