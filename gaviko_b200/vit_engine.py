@@ -459,7 +459,7 @@ class VitEngine:
                 if g(ename) is not None:
                     G[ename][i if m.deep_prompt else 0] += dE      # torch add of a [P, prompt_dim] tile: accumulation plumbing
                 d3 = dX.view(B, T, dim)
-                dX = torch.cat([d3[:, :1], torch.zeros((B, skip, dim), device=dev, dtype=torch.float32), d3[:, 1 + P:]], 1).reshape(-1, dim)
+                dX = torch.cat([d3[:, :1], torch.zeros((B, min(skip, T_in - 1), dim), device=dev, dtype=torch.float32), d3[:, 1 + P:]], 1).reshape(-1, dim)   # (a depleted sequence has fewer than `skip` rows to drop)
                 assert dX.shape[0] == B * T_in
                 dX_lp = ops.cast_bf16(dX) if lp else None
             ctx['layers'][i] = None

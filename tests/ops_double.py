@@ -3,7 +3,8 @@
 Purpose: exercise the HOST logic of the engines (``engine.py``, ``vit_engine.py``, ``dvpt_engine.py``: call order, in-place conventions, token /
 row bookkeeping, which gradients go where) in the ``-m "not gpu"`` suite, against the same golden vectors the GPU tests use.  It is test
 infrastructure only: it is installed by monkeypatching the engines' ``ops`` reference (``install()`` below) and never ships — the product path has no
-CPU fallback (``tests/test_dropin_surface.py::test_no_cpu_fallback``).  fp32 mode only; dropout must be off.
+CPU fallback (``tests/test_dropin_surface.py::test_no_cpu_fallback``).  fp32 mode only; dropout masks are replayable functions of the seed (not the
+kernels' Philox values).
 """
 import contextlib
 import math
@@ -20,6 +21,15 @@ GEMM_HOOK = None
 
 class GvkError(RuntimeError):
     pass
+
+
+def _keep(shape, drop_p, seed, offset=0):
+    """Replayable dropout multiplier (0 or 1 / (1 - p)) of a tensor: a function of (seed, offset, shape) only, like the Philox masks of the
+    kernels (the VALUES differ from the CUDA masks; forward / backward consistency is what the engines rely on)."""
+    if drop_p <= 0.0:
+        return None
+    g = torch.Generator().manual_seed((int(seed) * 1000003 + int(offset)) % (2 ** 63 - 1))
+    return (torch.rand(shape, generator=g) >= drop_p).float() / (1.0 - drop_p)
 
 
 def _gelu_grad(x):
@@ -88,9 +98,10 @@ def layernorm_fwd(x, gamma, beta, *, out=None, out_dtype=torch.float32, eps=1e-5
 
 
 def rowproj_down(x, w, bias=None, *, transposed=False, ln=None, eps=1e-5, act=ROWACT_NONE, save_pre=False, w2=None, drop_p=0.0, seed=0, offset=0, prec=PREC_FP32):
-    assert drop_p == 0.0
     mean = rstd = z2 = None
-    fx = x
+    k = _keep(x.shape, drop_p, seed, offset)
+    fx = x if k is None else x * k
+    x = fx
     if ln is not None:
         mean = x.mean(1)
         rstd = torch.rsqrt(x.var(1, unbiased=False) + eps)
@@ -107,10 +118,12 @@ def rowproj_down(x, w, bias=None, *, transposed=False, ln=None, eps=1e-5, act=RO
 
 
 def rowproj_up(c, w, bias=None, *, transposed=False, res=None, out=None, out_lp=None, drop_p=0.0, seed=0, offset=0, prec=PREC_FP32):
-    assert drop_p == 0.0
     v = c @ (w if transposed else w.t())
     if bias is not None:
         v = v + bias
+    k = _keep(v.shape, drop_p, seed, offset)
+    if k is not None:
+        v = v * k
     if res is not None:
         v = v + res
     if out is None:
@@ -122,8 +135,9 @@ def rowproj_up(c, w, bias=None, *, transposed=False, res=None, out=None, out_lp=
 
 
 def skinny_wgrad(a, x, *, dw=None, dw_layout='rd', da_colsum=None, dx_colsum=None, ln=None, drop_p=0.0, seed=0, offset=0, prec=PREC_FP32, dw_strides=None):
-    assert drop_p == 0.0
-    fx = x
+    k = _keep(x.shape, drop_p, seed, offset)
+    fx = x if k is None else x * k
+    x = fx
     if ln is not None:
         fx = (x - ln[2][:, None]) * ln[3][:, None] * ln[0] + ln[1]
     if dw is not None:
@@ -213,8 +227,8 @@ def ssf_bwd(dy, *, y=None, scale=None, shift=None, dx=None, dscale=None, dshift=
 
 
 def dropout(x, drop_p, seed, *, res=None, out=None, out_dtype=None, offset=0):
-    assert drop_p == 0.0
-    v = x.float() + (res if res is not None else 0)
+    k = _keep(x.shape, drop_p, seed, offset)
+    v = (x.float() if k is None else x.float() * k) + (res if res is not None else 0)
     if out is None:
         out = torch.empty(x.shape, dtype=out_dtype or x.dtype)
     return out.copy_(v)
@@ -257,20 +271,24 @@ def _attn(qkv, B, T, H, D, q_off, k_off, v_off, scale, window, grid):
 
 
 def attn_simt_fwd(qkv, B, T, H, D, *, q_off, k_off, v_off, scale, window=None, grid=None, drop_p=0.0, seed=0, offset=0, prec=PREC_FP32):
-    assert drop_p == 0.0
     q, k, v, p, lse = _attn(qkv, B, T, H, D, q_off, k_off, v_off, scale, window, grid)
-    out = (p @ v).transpose(1, 2).reshape(B * T, H * D).to(qkv.dtype)
+    keep = _keep(p.shape, drop_p, seed, offset)
+    out = ((p if keep is None else p * keep) @ v).transpose(1, 2).reshape(B * T, H * D).to(qkv.dtype)
     return out, lse.reshape(-1)
 
 
 def attn_simt_bwd(qkv, out, lse, dout, B, T, H, D, *, q_off, k_off, v_off, scale, window=None, grid=None, drop_p=0.0, seed=0, offset=0, dqkv=None,
                   prec=PREC_FP32):
-    assert drop_p == 0.0
     q, k, v, p, _ = _attn(qkv, B, T, H, D, q_off, k_off, v_off, scale, window, grid)
     do = dout.float().reshape(B, T, H, D).transpose(1, 2)
     o = out.float().reshape(B, T, H, D).transpose(1, 2)
+    keep = _keep(p.shape, drop_p, seed, offset)
     dp = do @ v.transpose(-1, -2)
+    if keep is not None:
+        dp = dp * keep
     ds = p * (dp - (do * o).sum(-1, keepdim=True))
+    if keep is not None:
+        p = p * keep                     # dV uses the dropped probabilities
     if dqkv is None:
         dqkv = torch.zeros_like(qkv)
     for off, t in ((q_off, ds @ k * scale), (k_off, ds.transpose(-1, -2) @ q * scale), (v_off, p.transpose(-1, -2) @ do)):
