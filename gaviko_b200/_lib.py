@@ -109,6 +109,29 @@ def device_guard(t):
     return torch.cuda.device(t.device)
 
 
+class untraced:
+    """Pause a torch.jit trace around the engine call.  The reference's validation loop jit-TRACES the model (train.py:246-252,405-407:
+    torchprofile.profile_macs -> torch.jit._get_trace_graph); under a trace every `tensor.shape[i]` is a traced 0-d tensor, which neither ctypes
+    nor the host-side bookkeeping can use, and the kernels are opaque to the tracer anyway.  With the trace paused the forward runs normally and the
+    tracer records the logits as a constant of the graph (profile_macs then counts no MACs for the model, as it does for any op without a handler)."""
+
+    def __enter__(self):
+        self.state = torch._C._get_tracing_state()
+        if self.state is not None:
+            torch._C._set_tracing_state(None)
+
+    def __exit__(self, *exc):
+        if self.state is not None:
+            torch._C._set_tracing_state(self.state)
+        return False
+
+    def reattach(self, logits, img):
+        """After the paused region: give the traced graph a data dependence of the output on the input (the tracer refuses a graph without one)."""
+        if self.state is None:
+            return logits
+        return logits + (img.reshape(-1)[:1] * 0).to(logits.dtype)
+
+
 def fptr(t):
     """fp32, contiguous device tensor (or None)."""
     if t is not None and not t.is_contiguous():

@@ -74,6 +74,8 @@ int clip_adam(float* param, const float* grad, float* m, float* v, size_t n, con
 int mhsa_fwd(const gvk_mhsa_fwd_params* p, cudaStream_t stream);
 int mhsa_bwd(const gvk_mhsa_bwd_params* p, cudaStream_t stream);
 int mhsa_ws_fwd(const gvk_mhsa_fwd_params* p, cudaStream_t stream);
+int mhsa_bwd_ws(const gvk_mhsa_bwd_params* p, cudaStream_t stream);
+size_t mhsa_bwd_ws_floats(int B, int T, int H);
 int prompt_fusion_fwd(const gvk_fusion_fwd_params* p, cudaStream_t stream);
 int prompt_fusion_bwd(const gvk_fusion_bwd_params* p, cudaStream_t stream);
 int quickgelu_bwd(const float* dy, const float* pre, float* y, size_t n, cudaStream_t stream);

@@ -668,6 +668,12 @@ int mhsa_bwd(const gvk_mhsa_bwd_params* p, cudaStream_t stream) {
   if (st != GVK_OK) return st;
   GVK_CHECK_ARG(p->ld_out % 8 == 0 && p->ld_dout % 8 == 0 && p->ld_dqkv % 8 == 0, "gvk_mhsa_bwd: leading dimensions must be multiples of 8");
   GVK_CHECK_ARG((reinterpret_cast<uintptr_t>(p->dout) & 15) == 0, "gvk_mhsa_bwd: dout must be 16-byte aligned");
+  GVK_CHECK_ARG((reinterpret_cast<uintptr_t>(p->delta) & 15) == 0, "gvk_mhsa_bwd: the workspace must be 16-byte aligned");
+  {
+    static int impl = -1;   // GVK_MHSA_BWD_IMPL=1 selects the older one-tile-per-CTA kernels (kept for A/B comparison)
+    if (impl < 0) { const char* e = getenv("GVK_MHSA_BWD_IMPL"); impl = e ? atoi(e) : 2; }
+    if (impl == 2) return mhsa_bwd_ws(p, stream);
+  }
   static bool configured = false;
   if (!configured) {
     st = set_smem(mhsa_bwd_dq_sm100_kernel, kDqSmem, "mhsa_bwd_dq smem");

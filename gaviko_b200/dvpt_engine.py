@@ -52,8 +52,10 @@ class DvptEngine:
         if active:
             raise NotImplementedError('DVPT with active backbone dropout is not implemented: call model.train() (with freeze_vit=True the reference puts the '
                                       'backbone in eval mode, model/dvpt.py:170-181) or model.eval() first')
-        with _L.device_guard(img):
+        pause = _L.untraced()      # a jit trace (profile_macs in the reference's validation loop) cannot follow the kernels
+        with pause, _L.device_guard(img):
             logits = _DvptFn.apply(self, img, need_grad, names, *tensors)
+        logits = pause.reattach(logits, img)
         return logits.to(img.dtype) if logits.dtype != img.dtype else logits
 
     def _weights(self, cdt):

@@ -104,8 +104,10 @@ class GavikoEngine:
                 raise NotImplementedError('gaviko_b200 implements the frozen-backbone backward (freeze_vit=True); '
                                           f'backbone tensors require grad: {bad[:3]}...')
         out_dtype = img.dtype
-        with _L.device_guard(img):      # kernels launch on the CURRENT device's stream: make the input's device current (train.py never calls set_device)
+        pause = _L.untraced()      # a jit trace (profile_macs in the reference's validation loop) cannot follow the kernels
+        with pause, _L.device_guard(img):      # kernels launch on the CURRENT device's stream: make the input's device current (train.py never calls set_device)
             logits = _GavikoFn.apply(self, img, need_grad, names, *tensors)
+        logits = pause.reattach(logits, img)
         return logits.to(out_dtype) if logits.dtype != out_dtype else logits
 
     # ------------------------------------------------------------------------------------------

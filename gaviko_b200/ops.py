@@ -329,7 +329,9 @@ def mhsa_bwd(qkv, out, lse, dout, B, T, H, scale):
     if qkv.dtype != torch.bfloat16 or dout.dtype != torch.bfloat16:
         raise GvkError('mhsa_bwd: bf16 only')
     dqkv = torch.empty_like(qkv)
-    delta = torch.empty(2 * lse.numel(), device=lse.device, dtype=torch.float32)
+    fn = L.lib().gvk_mhsa_bwd_ws_floats
+    fn.restype = C.c_size_t
+    delta = torch.empty(int(fn(B, T, H)), device=lse.device, dtype=torch.float32)
     p = S['gvk_mhsa_bwd_params']()
     _set(p, qkv=qkv, ld=_ld(qkv), B=B, T=T, H=H, scale=scale, out=out, ld_out=_ld(out), lse=lse, dout=dout, ld_dout=_ld(dout), delta=delta,
          dqkv=dqkv, ld_dqkv=_ld(dqkv))

@@ -72,8 +72,10 @@ class VitEngine:
         need_grad = torch.is_grad_enabled() and len(tensors) > 0
         if need_grad:
             self._check_trainable(names)
-        with _L.device_guard(img):      # kernels launch on the CURRENT device's stream
+        pause = _L.untraced()      # a jit trace (profile_macs in the reference's validation loop) cannot follow the kernels
+        with pause, _L.device_guard(img):      # kernels launch on the CURRENT device's stream
             logits = _VitFn.apply(self, img, need_grad, names, *tensors)
+        logits = pause.reattach(logits, img)
         return logits.to(img.dtype) if logits.dtype != img.dtype else logits
 
     def _check_trainable(self, names):

@@ -286,10 +286,12 @@ typedef struct {
   const void* out; int ld_out;
   const float* lse;
   const void* dout; int ld_dout;   /* [B*T, H*64] bf16 */
-  float* delta;                    /* workspace [2*B*H*T]: rowsum(dO*O), then the log2-domain lse handed from the dQ to the dK/dV kernel */
+  float* delta;                    /* workspace of gvk_mhsa_bwd_ws_floats(B, T, H) floats (16-byte aligned): rowsum(dO*O) and the log2-domain lse handed
+                                      from the dQ to the dK/dV kernel, rows padded to the 64-row query tiles of the latter */
   void* dqkv; int ld_dqkv;         /* [B*T, 3*H*64] bf16, fully overwritten */
 } gvk_mhsa_bwd_params;
 int gvk_mhsa_bwd(const gvk_mhsa_bwd_params* p, gvk_stream_t stream);
+size_t gvk_mhsa_bwd_ws_floats(int B, int T, int H);
 
 /* ------------------------------------------------------------------------------------------------------------------
  * Token assembly (a1/a2 of the hot path)

@@ -216,6 +216,7 @@ def test_flat_adam_survives_model_zero_grad_and_round_trips_its_state():
         assert torch.allclose(pa, pb, rtol=1e-4, atol=1e-6), (n, (pa - pb).abs().max().item())
     # a stray gradient (not a view of the flat buffer) is folded in
     mb._engine.grad_sink = None
+    opt_b.flat_g.zero_()
     for p in mb.parameters():
         p.grad = None
     crit(mb(img), y).backward()
