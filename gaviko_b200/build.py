@@ -30,9 +30,12 @@ def build(force: bool = False, verbose: bool = False) -> str:
     objs = []
     os.makedirs(os.path.join(HERE, 'build'), exist_ok=True)
     procs = []
+    hdrs = glob.glob(os.path.join(CSRC, '*.cuh')) + [os.path.join(os.path.dirname(HERE), 'include', 'gvk.h')]
     for src in sources():
         obj = os.path.join(HERE, 'build', os.path.basename(src)[:-3] + '.o')
         objs.append(obj)
+        if not force and os.path.exists(obj) and all(os.path.getmtime(d) < os.path.getmtime(obj) for d in [src] + hdrs):
+            continue   # object is newer than its source and every header
         cmd = [nvcc] + flags + ['-Xcompiler', '-fPIC', '-c', src, '-o', obj] + (['-Xptxas', '-v'] if verbose else [])
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     failed = False

@@ -162,6 +162,7 @@ int gvk_clip_adam(float* param, const float* grad, float* exp_avg, float* exp_av
 int gvk_mhsa_fwd(const gvk_mhsa_fwd_params* p, gvk_stream_t stream) { return gvk::mhsa_fwd(p, S(stream)); }
 int gvk_mhsa_bwd(const gvk_mhsa_bwd_params* p, gvk_stream_t stream) { return gvk::mhsa_bwd(p, S(stream)); }
 size_t gvk_mhsa_bwd_ws_floats(int B, int T, int H) { return gvk::mhsa_bwd_ws_floats(B, T, H); }
+int gvk_debug_trace(uint32_t* out, int n_words) { return gvk::debug_trace(out, n_words); }
 int gvk_colsum(const float* x, int ldx, int M, int dim, float* out, gvk_stream_t stream) { return gvk::colsum(x, ldx, M, dim, out, S(stream)); }
 int gvk_cast_f32_bf16(const float* x, int ldx, void* y, int ldy, int M, int dim, gvk_stream_t stream) {
   return gvk::cast_f32_bf16(x, ldx, y, ldy, M, dim, S(stream));

@@ -75,6 +75,8 @@ int mhsa_fwd(const gvk_mhsa_fwd_params* p, cudaStream_t stream);
 int mhsa_bwd(const gvk_mhsa_bwd_params* p, cudaStream_t stream);
 int mhsa_ws_fwd(const gvk_mhsa_fwd_params* p, cudaStream_t stream);
 int mhsa_bwd_ws(const gvk_mhsa_bwd_params* p, cudaStream_t stream);
+int mhsa_bwd_pipe(const gvk_mhsa_bwd_params* p, cudaStream_t stream);
+int debug_trace(uint32_t* out, int n_words);
 size_t mhsa_bwd_ws_floats(int B, int T, int H);
 int prompt_fusion_fwd(const gvk_fusion_fwd_params* p, cudaStream_t stream);
 int prompt_fusion_bwd(const gvk_fusion_bwd_params* p, cudaStream_t stream);

@@ -524,7 +524,7 @@ mhsa_bwd_dkv_ws_kernel(const __grid_constant__ CUtensorMap tma_kv, const __grid_
 }  // namespace wsb
 
 size_t mhsa_bwd_ws_floats(int B, int T, int H) {
-  const size_t tpad = (size_t)(T + wsb::kStep - 1) / wsb::kStep * wsb::kStep;
+  const size_t tpad = (size_t)(T + 127) / 128 * 128;   // the pipelined kernels pad to their 128-row blocks (covers the 64-row padding of this file's kernels)
   return 2 * (size_t)B * H * tpad;
 }
 

@@ -670,8 +670,9 @@ int mhsa_bwd(const gvk_mhsa_bwd_params* p, cudaStream_t stream) {
   GVK_CHECK_ARG((reinterpret_cast<uintptr_t>(p->dout) & 15) == 0, "gvk_mhsa_bwd: dout must be 16-byte aligned");
   GVK_CHECK_ARG((reinterpret_cast<uintptr_t>(p->delta) & 15) == 0, "gvk_mhsa_bwd: the workspace must be 16-byte aligned");
   {
-    static int impl = -1;   // GVK_MHSA_BWD_IMPL=1 selects the older one-tile-per-CTA kernels (kept for A/B comparison)
-    if (impl < 0) { const char* e = getenv("GVK_MHSA_BWD_IMPL"); impl = e ? atoi(e) : 2; }
+    static int impl = -1;   // GVK_MHSA_BWD_IMPL: 3 = software-pipelined kernels (default), 2 = ping-pong kernels, 1 = one tile per CTA (A/B comparison)
+    if (impl < 0) { const char* e = getenv("GVK_MHSA_BWD_IMPL"); impl = e ? atoi(e) : 3; }
+    if (impl == 3) return mhsa_bwd_pipe(p, stream);
     if (impl == 2) return mhsa_bwd_ws(p, stream);
   }
   static bool configured = false;

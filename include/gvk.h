@@ -287,11 +287,13 @@ typedef struct {
   const float* lse;
   const void* dout; int ld_dout;   /* [B*T, H*64] bf16 */
   float* delta;                    /* workspace of gvk_mhsa_bwd_ws_floats(B, T, H) floats (16-byte aligned): rowsum(dO*O) and the log2-domain lse handed
-                                      from the dQ to the dK/dV kernel, rows padded to the 64-row query tiles of the latter */
+                                      from the dQ to the dK/dV kernel, rows padded to the 128-row blocks of the kernels */
   void* dqkv; int ld_dqkv;         /* [B*T, 3*H*64] bf16, fully overwritten */
 } gvk_mhsa_bwd_params;
 int gvk_mhsa_bwd(const gvk_mhsa_bwd_params* p, gvk_stream_t stream);
 size_t gvk_mhsa_bwd_ws_floats(int B, int T, int H);
+/* Tuning aid: with GVK_PIPE_DBG & 4 the backward kernels record a (tag, clock) timeline of CTA 0; copies up to n_words 32-bit words of it to the host. */
+int gvk_debug_trace(uint32_t* out, int n_words);
 
 /* ------------------------------------------------------------------------------------------------------------------
  * Token assembly (a1/a2 of the hot path)
