@@ -51,7 +51,39 @@ static EncodeTiledFn encode_fn() {
   return fn;
 }
 
+// Encoded maps are cached: the caching allocator hands a training loop the same activation addresses step after step, so almost every
+// (base, shape, strides, box) of a step was encoded before (2-3 driver calls per GEMM / attention launch otherwise).  A tensor map holds no
+// device state beyond the address and the geometry in the key, so a stale entry cannot be wrong, only unused.
+struct TmaKey {
+  const void* base;
+  uint64_t dims[3], strides[2];
+  uint32_t box[3], rank;
+  bool operator==(const TmaKey& o) const { return memcmp(this, &o, sizeof(TmaKey)) == 0; }
+};
+struct TmaSlot {
+  TmaKey key;
+  CUtensorMap map;
+  bool valid;
+};
+static constexpr int kTmaSlots = 4096;   // direct-mapped; ~0.6 MB per thread that launches kernels
+static thread_local TmaSlot* g_tma_cache = nullptr;
+
 static int encode_bf16(CUtensorMap* out, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes, const cuuint32_t* box) {
+  TmaKey key;
+  memset(&key, 0, sizeof(key));
+  key.base = base;
+  key.rank = static_cast<uint32_t>(rank);
+  for (int i = 0; i < rank; ++i) { key.dims[i] = dims[i]; key.box[i] = box[i]; }
+  for (int i = 0; i + 1 < rank; ++i) key.strides[i] = strides_bytes[i];
+  uint64_t h = reinterpret_cast<uint64_t>(base) * 0x9E3779B97F4A7C15ull;
+  for (int i = 0; i < rank; ++i) h = (h ^ (key.dims[i] + 0x100000001B3ull * key.box[i])) * 0xFF51AFD7ED558CCDull;
+  for (int i = 0; i + 1 < rank; ++i) h = (h ^ key.strides[i]) * 0xC4CEB9FE1A85EC53ull;
+  if (!g_tma_cache) g_tma_cache = new TmaSlot[kTmaSlots]();
+  TmaSlot& slot = g_tma_cache[(h >> 32) & (kTmaSlots - 1)];
+  if (slot.valid && slot.key == key) {
+    *out = slot.map;
+    return GVK_OK;
+  }
   EncodeTiledFn fn = encode_fn();
   if (!fn) {
     set_last_error("cuTensorMapEncodeTiled is unavailable (no CUDA driver?)");
@@ -65,6 +97,9 @@ static int encode_bf16(CUtensorMap* out, const void* base, int rank, const cuuin
                    (unsigned long long)dims[1], (unsigned long long)(rank > 2 ? dims[2] : 0), box[0], box[1], rank > 2 ? box[2] : 0);
     return GVK_ERR_CUDA;
   }
+  slot.key = key;
+  slot.map = *out;
+  slot.valid = true;
   return GVK_OK;
 }
 
@@ -162,6 +197,7 @@ int gvk_clip_adam(float* param, const float* grad, float* exp_avg, float* exp_av
 int gvk_mhsa_fwd(const gvk_mhsa_fwd_params* p, gvk_stream_t stream) { return gvk::mhsa_fwd(p, S(stream)); }
 int gvk_mhsa_bwd(const gvk_mhsa_bwd_params* p, gvk_stream_t stream) { return gvk::mhsa_bwd(p, S(stream)); }
 size_t gvk_mhsa_bwd_ws_floats(int B, int T, int H) { return gvk::mhsa_bwd_ws_floats(B, T, H); }
+size_t gvk_mhsa_bwd_mask_words(int B, int T, int H) { return gvk::mhsa_bwd_mask_words(B, T, H); }
 int gvk_debug_trace(uint32_t* out, int n_words) { return gvk::debug_trace(out, n_words); }
 int gvk_colsum(const float* x, int ldx, int M, int dim, float* out, gvk_stream_t stream) { return gvk::colsum(x, ldx, M, dim, out, S(stream)); }
 int gvk_cast_f32_bf16(const float* x, int ldx, void* y, int ldy, int M, int dim, gvk_stream_t stream) {

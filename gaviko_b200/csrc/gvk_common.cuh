@@ -78,6 +78,7 @@ int mhsa_bwd_ws(const gvk_mhsa_bwd_params* p, cudaStream_t stream);
 int mhsa_bwd_pipe(const gvk_mhsa_bwd_params* p, cudaStream_t stream);
 int debug_trace(uint32_t* out, int n_words);
 size_t mhsa_bwd_ws_floats(int B, int T, int H);
+size_t mhsa_bwd_mask_words(int B, int T, int H);
 int prompt_fusion_fwd(const gvk_fusion_fwd_params* p, cudaStream_t stream);
 int prompt_fusion_bwd(const gvk_fusion_bwd_params* p, cudaStream_t stream);
 int quickgelu_bwd(const float* dy, const float* pre, float* y, size_t n, cudaStream_t stream);
@@ -363,6 +364,29 @@ __device__ __forceinline__ uint4 philox4x32(uint4 ctr, uint2 key) {
     key.y += W1;
   }
   return ctr;
+}
+// Attention-probability dropout of the tcgen05 MHSA kernels (gvk.h, gvk_mhsa_fwd_params): one Philox call decides 16 consecutive keys of a
+// query row with 8-bit thresholds.  Returns bit e = 1 iff key 16 * k16 + e of query row q is KEPT.
+struct MhsaDrop {
+  uint32_t thr4;     // the 8-bit keep threshold replicated into the four bytes
+  uint2 key;
+  float inv_keep;    // 256 / threshold
+};
+__host__ inline MhsaDrop make_mhsa_drop(float drop_p, unsigned long long seed) {
+  MhsaDrop d;
+  int thr = static_cast<int>(256.0f * (1.0f - drop_p) + 0.5f);
+  thr = thr < 1 ? 1 : (thr > 256 ? 256 : thr);
+  d.thr4 = thr >= 256 ? 0u : static_cast<uint32_t>(thr) * 0x01010101u;   // 0: keep everything (drop_p rounds to 0)
+  d.key = make_uint2(static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32));
+  d.inv_keep = 256.0f / static_cast<float>(thr);
+  return d;
+}
+__device__ __forceinline__ uint32_t mhsa_keep16(const MhsaDrop& d, uint32_t bh, uint32_t q, uint32_t k16) {
+  if (d.thr4 == 0u) return 0xFFFFu;
+  const uint4 r = philox4x32(make_uint4(q, k16, bh, 0x6d687361u), d.key);
+  // per byte: r < thr  <=>  the carry out of r + (256 - thr) is clear; __vcmpltu4 gives 0xFF per true byte, the multiply gathers the four flags
+  auto keep4 = [&](uint32_t w) { return ((__vcmpltu4(w, d.thr4) & 0x01010101u) * 0x01020408u) >> 24; };
+  return (keep4(r.x) & 15u) | ((keep4(r.y) & 15u) << 4) | ((keep4(r.z) & 15u) << 8) | ((keep4(r.w) & 15u) << 12);
 }
 __device__ __forceinline__ float u32_to_unit(uint32_t x) { return (x >> 8) * (1.0f / 16777216.0f); }  // [0,1)
 #endif  // __CUDACC__

@@ -116,6 +116,8 @@ struct Args {
   __nv_bfloat16* dqkv;
   int ld_dqkv;
   int num_items;   // B * H * nb
+  MhsaDrop drop;   // attention-probability dropout of the forward call (kDrop instantiations)
+  uint32_t* mask;  // [B*H][nb (key block)][Tpad (query)][4]: keep bits of the 128 keys of a block, written by the dQ kernel for the dK/dV kernel
   int dbg;         // timing experiments only (GVK_PIPE_DBG): 1 = no exp2, 2 = softmax warps only pass the barriers on (results are wrong); 4 = record the timeline of CTA 0
 };
 
@@ -128,6 +130,7 @@ enum { BAR_Q_FULL = 0 /*[2]*/, BAR_Q_EMPTY = 2 /*[2]*/, BAR_KV_FULL = 4, BAR_KV_
        BAR_DP_FULL = BAR_S_FULL + 2, BAR_DP_FREE, BAR_DS_FULL /*[2]*/, BAR_DQ_STEP = BAR_DS_FULL + 2 /*[2]*/, BAR_DQ_FULL = BAR_DQ_STEP + 2, BAR_COUNT };
 constexpr int kSmem = 6 * kTileBytes /*Q, dO, O x 2*/ + 2 * kStages * kTileBytes /*K, V ring*/ + BAR_COUNT * 8 + 64 + 1024;
 
+template <bool kDrop>
 __global__ void __launch_bounds__(kThreads, 1)
 mhsa_bwd_dq_pipe_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_constant__ CUtensorMap tma_do, const __grid_constant__ CUtensorMap tma_o, Args a) {
   extern __shared__ uint8_t smem_raw[];
@@ -270,12 +273,13 @@ mhsa_bwd_dq_pipe_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __gri
     Tracer tr; tr.init(1 + grp, (a.dbg & 4) && (warp & 3) == 0 && lane == 0);
     // Per-item set-up (row statistics), software-pipelined one item ahead: the set-up of item n+1 runs in the shadow of item n's last dQ MMAs
     // (the groups would otherwise idle there), so block 0 of the next item starts right behind the epilogue.
-    struct ItemCtx { int b, h, row; float lse2, delta; };
+    struct ItemCtx { int b, h, bh, row; float lse2, delta; };
     auto setup = [&](int item, uint32_t wk) {
       ItemCtx c;
       const int bh = item / nb, qt = item - bh * nb;
       c.h = bh % a.H;
       c.b = bh / a.H;
+      c.bh = bh;
       c.row = qt * kTile + r;
       const int ib = wk & 1;
       c.lse2 = c.row < T ? a.lse[(size_t)bh * T + c.row] * kLog2e : INFINITY;
@@ -306,7 +310,7 @@ mhsa_bwd_dq_pipe_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __gri
     ItemCtx cur{};
     if ((int)blockIdx.x < a.num_items) cur = setup(blockIdx.x, 0);
     for (int item = blockIdx.x; item < a.num_items; item += gridDim.x, ++work) {
-      const int b = cur.b, h = cur.h, row = cur.row;
+      const int b = cur.b, h = cur.h, bh = cur.bh, row = cur.row;
       const float2 nl = make_float2(-cur.lse2, -cur.lse2), nd = make_float2(-cur.delta, -cur.delta);
       tr(0x900);
       for (int j = 0; j < nb; ++j, ++g) {
@@ -326,6 +330,12 @@ mhsa_bwd_dq_pipe_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __gri
         // 32 scores at a time; the second half's TMEM loads travel while the first half is in its exp2 phase
         auto chunk = [&](const float (&s)[32], const float (&dp)[32], int c) {
           uint32_t pk[16];
+          uint32_t keep = 0xFFFFFFFFu;
+          if (kDrop) {     // replay the forward's dropout decisions of these 32 keys and hand them to the dK/dV kernel
+            keep = mhsa_keep16(a.drop, bh, row, 8 * j + 4 * grp + 2 * c) | (mhsa_keep16(a.drop, bh, row, 8 * j + 4 * grp + 2 * c + 1) << 16);
+            a.mask[(((size_t)bh * nb + j) * a.Tpad + row) * 4 + 2 * grp + c] = keep;
+          }
+          const float2 ik = make_float2(a.drop.inv_keep, a.drop.inv_keep);
 #pragma unroll
           for (int i = 0; i < 32; i += 2) {
             float2 e = ffma2(make_float2(s[i], s[i + 1]), c2v, nl);
@@ -333,7 +343,13 @@ mhsa_bwd_dq_pipe_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __gri
               e.x = fast_ex2(e.x);
               e.y = fast_ex2(e.y);
             }
-            const float2 ds = fmul2(e, fadd2(make_float2(dp[i], dp[i + 1]), nd));   // dS = P (dP - delta)
+            float2 dpe = make_float2(dp[i], dp[i + 1]);
+            if (kDrop) {   // d(P dropped) / dP = keep / (1 - p)
+              dpe = fmul2(dpe, ik);
+              if (!((keep >> i) & 1u)) dpe.x = 0.f;
+              if (!((keep >> (i + 1)) & 1u)) dpe.y = 0.f;
+            }
+            const float2 ds = fmul2(e, fadd2(dpe, nd));   // dS = P (dP - delta)
             pk[i >> 1] = pack_bf16x2(ds.x, ds.y);
           }
           tmem_st_32x16(tS + 16 * c, pk);     // packed dS over S columns this thread has already read
@@ -402,13 +418,16 @@ mhsa_bwd_dq_pipe_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __gri
 namespace dkv {
 constexpr int kStages = 4;
 constexpr int kStatBytes = 2 * kTile * 4;                         // delta[128], lse2[128] of the streamed query block
+constexpr int kMaskBytes = kTile * 16;                            // dropout keep bits: [128 queries][4 words = 128 keys]
 constexpr int kStageBytes = 2 * kTileBytes + kStatBytes;
 constexpr int kColDV = 384, kColDK = 448;
 enum { BAR_KV_FULL = 0 /*[2]*/, BAR_KV_EMPTY = 2 /*[2]*/, BAR_Q_FULL = 4, BAR_Q_EMPTY = BAR_Q_FULL + kStages, BAR_S_FULL = BAR_Q_EMPTY + kStages /*[2]*/,
        BAR_DP_FULL = BAR_S_FULL + 2, BAR_P_FULL /*[2]*/, BAR_DS_FULL = BAR_P_FULL + 2 /*[2]*/, BAR_DV_STEP = BAR_DS_FULL + 2 /*[2]*/, BAR_DK_STEP = BAR_DV_STEP + 2,
        BAR_ACC_FULL, BAR_COUNT };
 constexpr int kSmem = 4 * kTileBytes /*K, V x 2*/ + kStages * kStageBytes + BAR_COUNT * 8 + 64 + 1024;
+constexpr int kSmemDrop = kSmem + kStages * kMaskBytes;
 
+template <bool kDrop>
 __global__ void __launch_bounds__(kThreads, 1)
 mhsa_bwd_dkv_pipe_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_constant__ CUtensorMap tma_do, Args a) {
   extern __shared__ uint8_t smem_raw[];
@@ -418,7 +437,8 @@ mhsa_bwd_dkv_pipe_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __gr
   uint8_t* sQ = sV + 2 * kTileBytes;               // [kStages][16 KB]
   uint8_t* sdO = sQ + kStages * kTileBytes;        // [kStages][16 KB]
   float* sStat = reinterpret_cast<float*>(sdO + kStages * kTileBytes);   // [kStages][delta 128 | lse2 128]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(sStat) + kStages * kStatBytes);
+  uint32_t* sMask = reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(sStat) + kStages * kStatBytes);   // [kStages][128][4] (kDrop only)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(sMask) + (kDrop ? kStages * kMaskBytes : 0));
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + BAR_COUNT);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int T = a.T, dim = a.dim, nb = a.nb;
@@ -460,7 +480,8 @@ mhsa_bwd_dkv_pipe_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __gr
         for (int i = 0; i < nb; ++i, ++q_iter) {
           const int st = q_iter % kStages;
           mbar_wait(&bars[BAR_Q_EMPTY + st], ((q_iter / kStages) & 1) ^ 1);
-          mbar_arrive_expect_tx(&bars[BAR_Q_FULL + st], kStageBytes);
+          mbar_arrive_expect_tx(&bars[BAR_Q_FULL + st], kStageBytes + (kDrop ? kMaskBytes : 0));
+          if (kDrop) bulk_load(sMask + st * kTile * 4, a.mask + (((size_t)bh * nb + kt) * a.Tpad + (size_t)i * kTile) * 4, kMaskBytes, &bars[BAR_Q_FULL + st]);
           tma_load_3d(sQ + st * kTileBytes, &tma_qkv, &bars[BAR_Q_FULL + st], h * kD, i * kTile, b);
           tma_load_3d(sdO + st * kTileBytes, &tma_do, &bars[BAR_Q_FULL + st], h * kD, i * kTile, b);
           bulk_load(sStat + st * 2 * kTile, g_delta + i * kTile, kTile * 4, &bars[BAR_Q_FULL + st]);
@@ -572,6 +593,8 @@ mhsa_bwd_dkv_pipe_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __gr
           continue;
         }
         float p0[32], p1[32];
+        const uint32_t* s_mask = sMask + (st * kTile + 64 * grp) * 4 + (warp & 3);     // this thread's key is bit `lane` of word (warp & 3) of each query
+        auto kept = [&](int q) { return kDrop ? ((s_mask[4 * q] >> lane) & 1u) != 0u : true; };
         auto p_chunk = [&](float (&p)[32], int c) {      // P^T = 2^(S^T c - lse2[q]) in place, packed copy over S^T columns already read
           uint32_t pk[16];
 #pragma unroll
@@ -585,6 +608,12 @@ mhsa_bwd_dkv_pipe_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __gr
             p[q + 1] = e0.y;
             p[q + 2] = e1.x;
             p[q + 3] = e1.y;
+            if (kDrop) {      // dV sees the dropped probabilities (their 1 / (1 - p) is applied in the epilogue)
+              if (!kept(32 * c + q)) e0.x = 0.f;
+              if (!kept(32 * c + q + 1)) e0.y = 0.f;
+              if (!kept(32 * c + q + 2)) e1.x = 0.f;
+              if (!kept(32 * c + q + 3)) e1.y = 0.f;
+            }
             pk[2 * q4] = pack_bf16x2(e0.x, e0.y);
             pk[2 * q4 + 1] = pack_bf16x2(e1.x, e1.y);
           }
@@ -596,8 +625,18 @@ mhsa_bwd_dkv_pipe_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __gr
           for (int q4 = 0; q4 < 8; ++q4) {
             const float4 d4 = *reinterpret_cast<const float4*>(s_delta + 32 * c + 4 * q4);
             const int q = 4 * q4;
-            const float2 a0 = fmul2(make_float2(p[q], p[q + 1]), fadd2(make_float2(dp[q], dp[q + 1]), make_float2(-d4.x, -d4.y)));
-            const float2 a1 = fmul2(make_float2(p[q + 2], p[q + 3]), fadd2(make_float2(dp[q + 2], dp[q + 3]), make_float2(-d4.z, -d4.w)));
+            float2 e0 = make_float2(dp[q], dp[q + 1]), e1 = make_float2(dp[q + 2], dp[q + 3]);
+            if (kDrop) {
+              const float2 ik = make_float2(a.drop.inv_keep, a.drop.inv_keep);
+              e0 = fmul2(e0, ik);
+              e1 = fmul2(e1, ik);
+              if (!kept(32 * c + q)) e0.x = 0.f;
+              if (!kept(32 * c + q + 1)) e0.y = 0.f;
+              if (!kept(32 * c + q + 2)) e1.x = 0.f;
+              if (!kept(32 * c + q + 3)) e1.y = 0.f;
+            }
+            const float2 a0 = fmul2(make_float2(p[q], p[q + 1]), fadd2(e0, make_float2(-d4.x, -d4.y)));
+            const float2 a1 = fmul2(make_float2(p[q + 2], p[q + 3]), fadd2(e1, make_float2(-d4.z, -d4.w)));
             pk[2 * q4] = pack_bf16x2(a0.x, a0.y);
             pk[2 * q4 + 1] = pack_bf16x2(a1.x, a1.y);
           }
@@ -639,7 +678,7 @@ mhsa_bwd_dkv_pipe_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __gr
       mbar_wait_warp(&bars[BAR_ACC_FULL], work & 1, lane);
       tc_fence_after();
       const int row = kt * kTile + r;
-      const float sc = grp == 0 ? a.scale : 1.0f;
+      const float sc = grp == 0 ? a.scale : (kDrop ? a.drop.inv_keep : 1.0f);
       __nv_bfloat16* base = a.dqkv + ((size_t)b * T + row) * a.ld_dqkv + (grp == 0 ? dim : 2 * dim) + h * kD;
 #pragma unroll
       for (int c = 0; c < 2; ++c) {
@@ -668,6 +707,11 @@ mhsa_bwd_dkv_pipe_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __gr
 }  // namespace dkv
 }  // namespace pb
 
+size_t mhsa_bwd_mask_words(int B, int T, int H) {
+  const size_t nb = (size_t)(T + pb::kTile - 1) / pb::kTile;
+  return (size_t)B * H * nb * (nb * pb::kTile) * 4;
+}
+
 int debug_trace(uint32_t* out, int n_words) {
   const size_t bytes = std::min<size_t>(sizeof(pb::g_trace), (size_t)n_words * 4);
   return cuda_status(cudaMemcpyFromSymbol(out, pb::g_trace, bytes), "debug_trace");
@@ -677,9 +721,13 @@ int mhsa_bwd_pipe(const gvk_mhsa_bwd_params* p, cudaStream_t stream) {
   using namespace pb;
   static bool configured = false;
   if (!configured) {
-    int st = cuda_status(cudaFuncSetAttribute(dq::mhsa_bwd_dq_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, dq::kSmem), "mhsa_bwd_dq_pipe smem");
+    int st = cuda_status(cudaFuncSetAttribute(dq::mhsa_bwd_dq_pipe_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, dq::kSmem), "mhsa_bwd_dq_pipe smem");
     if (st != GVK_OK) return st;
-    st = cuda_status(cudaFuncSetAttribute(dkv::mhsa_bwd_dkv_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, dkv::kSmem), "mhsa_bwd_dkv_pipe smem");
+    st = cuda_status(cudaFuncSetAttribute(dq::mhsa_bwd_dq_pipe_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, dq::kSmem), "mhsa_bwd_dq_pipe smem");
+    if (st != GVK_OK) return st;
+    st = cuda_status(cudaFuncSetAttribute(dkv::mhsa_bwd_dkv_pipe_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, dkv::kSmem), "mhsa_bwd_dkv_pipe smem");
+    if (st != GVK_OK) return st;
+    st = cuda_status(cudaFuncSetAttribute(dkv::mhsa_bwd_dkv_pipe_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, dkv::kSmemDrop), "mhsa_bwd_dkv_pipe smem");
     if (st != GVK_OK) return st;
     configured = true;
   }
@@ -704,10 +752,22 @@ int mhsa_bwd_pipe(const gvk_mhsa_bwd_params* p, cudaStream_t stream) {
   a.num_items = p->B * p->H * a.nb;
   { const char* e = getenv("GVK_PIPE_DBG"); a.dbg = e ? atoi(e) : 0; }
   const int grid = std::min(a.num_items, sm_count());
-  dq::mhsa_bwd_dq_pipe_kernel<<<grid, kThreads, dq::kSmem, stream>>>(tqkv, tdo, to, a);
-  GVK_CHECK_LAUNCH("mhsa_bwd_dq_pipe");
-  dkv::mhsa_bwd_dkv_pipe_kernel<<<grid, kThreads, dkv::kSmem, stream>>>(tqkv, tdo, a);
-  GVK_CHECK_LAUNCH("mhsa_bwd_dkv_pipe");
+  const bool drop = p->drop_p > 0.f;
+  GVK_CHECK_ARG(p->drop_p >= 0.f && p->drop_p < 1.f, "gvk_mhsa_bwd: drop_p must be in [0, 1)");
+  GVK_CHECK_ARG(!drop || (p->mask_ws && (reinterpret_cast<uintptr_t>(p->mask_ws) & 15) == 0), "gvk_mhsa_bwd: dropout needs a 16-byte aligned mask workspace");
+  a.drop = make_mhsa_drop(p->drop_p, p->seed);
+  a.mask = p->mask_ws;
+  if (drop) {
+    dq::mhsa_bwd_dq_pipe_kernel<true><<<grid, kThreads, dq::kSmem, stream>>>(tqkv, tdo, to, a);
+    GVK_CHECK_LAUNCH("mhsa_bwd_dq_pipe");
+    dkv::mhsa_bwd_dkv_pipe_kernel<true><<<grid, kThreads, dkv::kSmemDrop, stream>>>(tqkv, tdo, a);
+    GVK_CHECK_LAUNCH("mhsa_bwd_dkv_pipe");
+  } else {
+    dq::mhsa_bwd_dq_pipe_kernel<false><<<grid, kThreads, dq::kSmem, stream>>>(tqkv, tdo, to, a);
+    GVK_CHECK_LAUNCH("mhsa_bwd_dq_pipe");
+    dkv::mhsa_bwd_dkv_pipe_kernel<false><<<grid, kThreads, dkv::kSmem, stream>>>(tqkv, tdo, a);
+    GVK_CHECK_LAUNCH("mhsa_bwd_dkv_pipe");
+  }
   return GVK_OK;
 }
 

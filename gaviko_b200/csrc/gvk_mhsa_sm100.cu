@@ -633,11 +633,13 @@ int mhsa_fwd(const gvk_mhsa_fwd_params* p, cudaStream_t stream) {
   int st = check_common(p->qkv, p->ld, p->B, p->T, p->H, "gvk_mhsa_fwd");
   if (st != GVK_OK) return st;
   GVK_CHECK_ARG(p->ld_out % 8 == 0, "gvk_mhsa_fwd: ld_out must be a multiple of 8");
+  GVK_CHECK_ARG(p->drop_p >= 0.f && p->drop_p < 1.f, "gvk_mhsa_fwd: drop_p must be in [0, 1)");
   {
     static int impl = -1;   // GVK_MHSA_IMPL=1 selects the older one-tile-per-CTA kernel (kept for A/B comparison)
     if (impl < 0) { const char* e = getenv("GVK_MHSA_IMPL"); impl = e ? atoi(e) : 2; }
     if (impl == 2) return mhsa_ws_fwd(p, stream);
   }
+  GVK_CHECK_ARG(p->drop_p == 0.f, "gvk_mhsa_fwd: attention dropout needs the warp-specialised kernel (GVK_MHSA_IMPL unset)");
   static bool configured = false;
   if (!configured) {
     st = set_smem(mhsa_fwd_sm100_kernel, kFwdSmem, "mhsa_fwd smem");
@@ -673,6 +675,7 @@ int mhsa_bwd(const gvk_mhsa_bwd_params* p, cudaStream_t stream) {
     static int impl = -1;   // GVK_MHSA_BWD_IMPL: 3 = software-pipelined kernels (default), 2 = ping-pong kernels, 1 = one tile per CTA (A/B comparison)
     if (impl < 0) { const char* e = getenv("GVK_MHSA_BWD_IMPL"); impl = e ? atoi(e) : 3; }
     if (impl == 3) return mhsa_bwd_pipe(p, stream);
+    GVK_CHECK_ARG(p->drop_p == 0.f || impl == 3, "gvk_mhsa_bwd: attention dropout needs the pipelined kernels (GVK_MHSA_BWD_IMPL unset)");
     if (impl == 2) return mhsa_bwd_ws(p, stream);
   }
   static bool configured = false;

@@ -57,6 +57,7 @@ struct FwdArgs {
   int num_items;   // B * H * pairs
   uint32_t mn_lbo, mn_sbo, mn_kadv;   // MN-major B descriptor fields of the V tile
   int dbg;   // timing experiments only (GVK_WS_DBG): 1 = no exp2, 2 = no TMEM load of S; results are wrong
+  MhsaDrop drop;   // attention-probability dropout (kDrop instantiation only)
 };
 
 // TMEM columns: S_{X,buf} (fp32, 64 columns; P overwrites its first 32) at (X*kSBuf + buf)*64; O_X (fp32, 64 columns) at kOCol + X*64.
@@ -69,6 +70,7 @@ enum { BAR_Q_FULL = 0, BAR_Q_EMPTY = 1, BAR_K_FULL = 2, BAR_V_FULL = BAR_K_FULL 
 
 constexpr int kFwdSmem = 2 * kQBytes /*Q A,B*/ + 2 * kStages * kKVBytes /*K,V ring*/ + BAR_COUNT * 8 + 64 + 1024;
 
+template <bool kDrop>
 __global__ void __launch_bounds__(kThreads, 1)
 mhsa_ws_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant__ CUtensorMap tma_kv, FwdArgs a) {
   extern __shared__ uint8_t smem_raw[];
@@ -249,6 +251,8 @@ mhsa_ws_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_const
 #pragma unroll
         for (int c = 0; c < 2; ++c) {           // 32 scores -> 16 packed registers -> P columns 16c .. 16c+15 (over S columns already read)
           uint32_t pk[16];
+          uint32_t keep = 0xFFFFFFFFu;          // dropout decisions of these 32 keys (the row sum l stays that of the un-dropped softmax)
+          if (kDrop) keep = mhsa_keep16(a.drop, bh, q0 + r, 4 * j + 2 * c) | (mhsa_keep16(a.drop, bh, q0 + r, 4 * j + 2 * c + 1) << 16);
 #pragma unroll
           for (int i = 0; i < 16; i += 2) {
             float2 pa = ffma2(make_float2(s[32 * c + 2 * i], s[32 * c + 2 * i + 1]), c2v, mcv);
@@ -256,6 +260,12 @@ mhsa_ws_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_const
             if ((a.dbg & 3) != 1) { pa.x = fast_ex2(pa.x); pa.y = fast_ex2(pa.y); pb.x = fast_ex2(pb.x); pb.y = fast_ex2(pb.y); }
             rs01 = fadd2(rs01, pa);
             rs23 = fadd2(rs23, pb);
+            if (kDrop) {
+              if (!((keep >> (2 * i)) & 1u)) pa.x = 0.f;
+              if (!((keep >> (2 * i + 1)) & 1u)) pa.y = 0.f;
+              if (!((keep >> (2 * i + 2)) & 1u)) pb.x = 0.f;
+              if (!((keep >> (2 * i + 3)) & 1u)) pb.y = 0.f;
+            }
             pk[i] = pack_bf16x2(pa.x, pa.y);
             pk[i + 1] = pack_bf16x2(pb.x, pb.y);
           }
@@ -297,7 +307,7 @@ mhsa_ws_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_const
       tc_wait_ld();
       const int row = q0 + r;
       if (row < T) {
-        const float inv = 1.0f / l;
+        const float inv = (kDrop ? a.drop.inv_keep : 1.0f) / l;
         uint4* dst = reinterpret_cast<uint4*>(a.out + ((size_t)b * T + row) * a.ld_out + h * kD);
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
@@ -324,7 +334,9 @@ int mhsa_ws_fwd(const gvk_mhsa_fwd_params* p, cudaStream_t stream) {
   using namespace ws;
   static bool configured = false;
   if (!configured) {
-    int st = cuda_status(cudaFuncSetAttribute(mhsa_ws_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFwdSmem), "mhsa_ws_fwd smem");
+    int st = cuda_status(cudaFuncSetAttribute(mhsa_ws_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFwdSmem), "mhsa_ws_fwd smem");
+    if (st != GVK_OK) return st;
+    st = cuda_status(cudaFuncSetAttribute(mhsa_ws_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFwdSmem), "mhsa_ws_fwd (dropout) smem");
     if (st != GVK_OK) return st;
     configured = true;
   }
@@ -344,7 +356,11 @@ int mhsa_ws_fwd(const gvk_mhsa_fwd_params* p, cudaStream_t stream) {
   a.mn_lbo = 8192; a.mn_sbo = 1024; a.mn_kadv = 2048;
   { const char* e = getenv("GVK_WS_DBG"); a.dbg = e ? atoi(e) : 0; }
   const int grid = std::min(a.num_items, sm_count());
-  mhsa_ws_fwd_kernel<<<grid, kThreads, kFwdSmem, stream>>>(tq, tkv, a);
+  a.drop = make_mhsa_drop(p->drop_p, p->seed);
+  if (p->drop_p > 0.f)
+    mhsa_ws_fwd_kernel<true><<<grid, kThreads, kFwdSmem, stream>>>(tq, tkv, a);
+  else
+    mhsa_ws_fwd_kernel<false><<<grid, kThreads, kFwdSmem, stream>>>(tq, tkv, a);
   GVK_CHECK_LAUNCH("mhsa_ws_fwd");
   return GVK_OK;
 }

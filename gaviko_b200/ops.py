@@ -313,19 +313,19 @@ def attn_simt_bwd(qkv, out, lse, dout, B, T, H, D, *, q_off, k_off, v_off, scale
     return dqkv
 
 
-def mhsa_fwd(qkv, B, T, H, scale):
-    """tcgen05 flash attention forward: qkv [B*T, 3*H*64] bf16 -> (out [B*T, H*64] bf16, lse [B*H*T] fp32)."""
+def mhsa_fwd(qkv, B, T, H, scale, drop_p=0.0, seed=0):
+    """tcgen05 flash attention forward: qkv [B*T, 3*H*64] bf16 -> (out [B*T, H*64] bf16, lse [B*H*T] fp32); optional Philox dropout on the probabilities."""
     if qkv.dtype != torch.bfloat16:
         raise GvkError('mhsa_fwd: bf16 only (fp32 mode uses attn_simt_fwd)')
     out = torch.empty((B * T, H * 64), device=qkv.device, dtype=torch.bfloat16)
     lse = torch.empty(B * H * T, device=qkv.device, dtype=torch.float32)
     p = S['gvk_mhsa_fwd_params']()
-    _set(p, qkv=qkv, ld=_ld(qkv), B=B, T=T, H=H, scale=scale, out=out, ld_out=_ld(out), lse=lse)
+    _set(p, qkv=qkv, ld=_ld(qkv), B=B, T=T, H=H, scale=scale, out=out, ld_out=_ld(out), lse=lse, drop_p=float(drop_p), seed=int(seed) & 0xFFFFFFFFFFFFFFFF)
     L.call('gvk_mhsa_fwd', C.byref(p), L.stream())
     return out, lse
 
 
-def mhsa_bwd(qkv, out, lse, dout, B, T, H, scale):
+def mhsa_bwd(qkv, out, lse, dout, B, T, H, scale, drop_p=0.0, seed=0):
     if qkv.dtype != torch.bfloat16 or dout.dtype != torch.bfloat16:
         raise GvkError('mhsa_bwd: bf16 only')
     dqkv = torch.empty_like(qkv)
@@ -333,8 +333,13 @@ def mhsa_bwd(qkv, out, lse, dout, B, T, H, scale):
     fn.restype = C.c_size_t
     delta = torch.empty(int(fn(B, T, H)), device=lse.device, dtype=torch.float32)
     p = S['gvk_mhsa_bwd_params']()
+    mask = None
+    if drop_p > 0.0:
+        fm = L.lib().gvk_mhsa_bwd_mask_words
+        fm.restype = C.c_size_t
+        mask = torch.empty(int(fm(B, T, H)), device=lse.device, dtype=torch.int32)
     _set(p, qkv=qkv, ld=_ld(qkv), B=B, T=T, H=H, scale=scale, out=out, ld_out=_ld(out), lse=lse, dout=dout, ld_dout=_ld(dout), delta=delta,
-         dqkv=dqkv, ld_dqkv=_ld(dqkv))
+         dqkv=dqkv, ld_dqkv=_ld(dqkv), drop_p=float(drop_p), seed=int(seed) & 0xFFFFFFFFFFFFFFFF, mask_ws=mask)
     L.call('gvk_mhsa_bwd', C.byref(p), L.stream())
     return dqkv
 

@@ -204,13 +204,13 @@ class VitEngine:
 
     # ------------------------------------------------------------------------------------------
     def _attention(self, qkv, B, T, H, D, dim, drop_p, seed):
-        if qkv.dtype == torch.bfloat16 and D == 64 and drop_p == 0.0:
-            return ops.mhsa_fwd(qkv, B, T, H, D ** -0.5)
+        if qkv.dtype == torch.bfloat16 and D == 64:      # tcgen05 flash attention, Philox dropout on the probabilities inside the softmax pass
+            return ops.mhsa_fwd(qkv, B, T, H, D ** -0.5, drop_p=drop_p, seed=seed)
         return ops.attn_simt_fwd(qkv, B, T, H, D, q_off=0, k_off=dim, v_off=2 * dim, scale=D ** -0.5, drop_p=drop_p, seed=seed)
 
     def _attention_bwd(self, qkv, o, lse, do, B, T, H, D, dim, drop_p, seed):
-        if qkv.dtype == torch.bfloat16 and D == 64 and drop_p == 0.0:
-            return ops.mhsa_bwd(qkv, o, lse, do, B, T, H, D ** -0.5)
+        if qkv.dtype == torch.bfloat16 and D == 64:
+            return ops.mhsa_bwd(qkv, o, lse, do, B, T, H, D ** -0.5, drop_p=drop_p, seed=seed)
         return ops.attn_simt_bwd(qkv, o, lse, do, B, T, H, D, q_off=0, k_off=dim, v_off=2 * dim, scale=D ** -0.5, drop_p=drop_p, seed=seed)
 
     def _prompts(self, i):

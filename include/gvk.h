@@ -276,6 +276,10 @@ typedef struct {
   float scale;
   void* out; int ld_out;
   float* lse;
+  /* Attention-probability dropout (model/vision_transformer.py:50,69; active for --method melo / linear / bitfit in train mode): probability
+   * (b, h, i, j) is kept iff byte (j % 16) of philox4x32-10(counter = (i, j / 16, b*H + h, 'mhsa'), key = seed) < round(256 (1 - drop_p)); the
+   * kept ones are scaled by 256 / round(256 (1 - drop_p)).  lse stays that of the un-dropped softmax.  drop_p = 0: no dropout. */
+  float drop_p; uint64_t seed;
 } gvk_mhsa_fwd_params;
 int gvk_mhsa_fwd(const gvk_mhsa_fwd_params* p, gvk_stream_t stream);
 
@@ -289,9 +293,12 @@ typedef struct {
   float* delta;                    /* workspace of gvk_mhsa_bwd_ws_floats(B, T, H) floats (16-byte aligned): rowsum(dO*O) and the log2-domain lse handed
                                       from the dQ to the dK/dV kernel, rows padded to the 128-row blocks of the kernels */
   void* dqkv; int ld_dqkv;         /* [B*T, 3*H*64] bf16, fully overwritten */
+  float drop_p; uint64_t seed;     /* the forward call's dropout: the mask is regenerated (dQ kernel) and handed to the dK/dV kernel through mask_ws */
+  uint32_t* mask_ws;               /* drop_p > 0: workspace of gvk_mhsa_bwd_mask_words(B, T, H) 32-bit words (16-byte aligned); else unused */
 } gvk_mhsa_bwd_params;
 int gvk_mhsa_bwd(const gvk_mhsa_bwd_params* p, gvk_stream_t stream);
 size_t gvk_mhsa_bwd_ws_floats(int B, int T, int H);
+size_t gvk_mhsa_bwd_mask_words(int B, int T, int H);
 /* Tuning aid: with GVK_PIPE_DBG & 4 the backward kernels record a (tag, clock) timeline of CTA 0; copies up to n_words 32-bit words of it to the host. */
 int gvk_debug_trace(uint32_t* out, int n_words);
 

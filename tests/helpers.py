@@ -94,3 +94,24 @@ def check_fingerprint(model_or_sd, g, rtol=1e-6):
         s, q = fp[n]
         assert abs(s - ref[i, 0]) <= rtol * max(1.0, abs(ref[i, 0]), ref[i, 1] ** 0.5) and abs(q - ref[i, 1]) <= rtol * max(1e-30, ref[i, 1]), \
             f'init drift in {n}: {(s, q)} vs {tuple(ref[i])}'
+
+
+def mhsa_keep_mask(B, H, T, drop_p, seed):
+    """Host restatement of the dropout decisions of the tcgen05 attention kernels (include/gvk.h, gvk_mhsa_fwd_params): probability
+    (b, h, i, j) is kept iff byte (j % 16) of philox4x32-10(counter = (i, j // 16, b*H + h, 'mhsa'), key = seed) < round(256 (1 - drop_p)).
+    Returns (keep [B, H, T, T] bool, scale)."""
+    thr = min(256, max(1, int(256.0 * (1.0 - drop_p) + 0.5)))
+    n16 = (T + 15) // 16
+    bh, q, k16 = np.meshgrid(np.arange(B * H, dtype=np.uint64), np.arange(T, dtype=np.uint64), np.arange(n16, dtype=np.uint64), indexing='ij')
+    x, y, z, w = q.copy(), k16.copy(), bh.copy(), np.full_like(q, 0x6d687361)
+    k0, k1 = np.uint64(seed & 0xFFFFFFFF), np.uint64((seed >> 32) & 0xFFFFFFFF)
+    M0, M1, W0, W1, MASK = np.uint64(0xD2511F53), np.uint64(0xCD9E8D57), np.uint64(0x9E3779B9), np.uint64(0xBB67AE85), np.uint64(0xFFFFFFFF)
+    for _ in range(10):
+        p0, p1 = M0 * x, M1 * z
+        hi0, lo0, hi1, lo1 = p0 >> np.uint64(32), p0 & MASK, p1 >> np.uint64(32), p1 & MASK
+        x, y, z, w = hi1 ^ y ^ k0, lo1, hi0 ^ w ^ k1, lo0
+        k0, k1 = (k0 + W0) & MASK, (k1 + W1) & MASK
+    words = np.stack([x, y, z, w], -1)                                                    # [BH, T, n16, 4]
+    bytes_ = np.stack([(words >> np.uint64(8 * b)) & np.uint64(0xFF) for b in range(4)], -1)   # [..., word, byte]
+    keep = (bytes_.reshape(B * H, T, n16 * 16) < thr)[:, :, :T]
+    return torch.from_numpy(keep.reshape(B, H, T, T)), 256.0 / thr
