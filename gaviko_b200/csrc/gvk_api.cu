@@ -56,8 +56,8 @@ static EncodeTiledFn encode_fn() {
 // device state beyond the address and the geometry in the key, so a stale entry cannot be wrong, only unused.
 struct TmaKey {
   const void* base;
-  uint64_t dims[3], strides[2];
-  uint32_t box[3], rank;
+  uint64_t dims[5], strides[4];
+  uint32_t box[5], rank, dtype;
   bool operator==(const TmaKey& o) const { return memcmp(this, &o, sizeof(TmaKey)) == 0; }
 };
 struct TmaSlot {
@@ -68,14 +68,16 @@ struct TmaSlot {
 static constexpr int kTmaSlots = 4096;   // direct-mapped; ~0.6 MB per thread that launches kernels
 static thread_local TmaSlot* g_tma_cache = nullptr;
 
-static int encode_bf16(CUtensorMap* out, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes, const cuuint32_t* box) {
+static int encode_map(CUtensorMap* out, CUtensorMapDataType dtype, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
+                      const cuuint32_t* box) {
   TmaKey key;
   memset(&key, 0, sizeof(key));
   key.base = base;
   key.rank = static_cast<uint32_t>(rank);
+  key.dtype = static_cast<uint32_t>(dtype);
   for (int i = 0; i < rank; ++i) { key.dims[i] = dims[i]; key.box[i] = box[i]; }
   for (int i = 0; i + 1 < rank; ++i) key.strides[i] = strides_bytes[i];
-  uint64_t h = reinterpret_cast<uint64_t>(base) * 0x9E3779B97F4A7C15ull;
+  uint64_t h = (reinterpret_cast<uint64_t>(base) + key.dtype) * 0x9E3779B97F4A7C15ull;
   for (int i = 0; i < rank; ++i) h = (h ^ (key.dims[i] + 0x100000001B3ull * key.box[i])) * 0xFF51AFD7ED558CCDull;
   for (int i = 0; i + 1 < rank; ++i) h = (h ^ key.strides[i]) * 0xC4CEB9FE1A85EC53ull;
   if (!g_tma_cache) g_tma_cache = new TmaSlot[kTmaSlots]();
@@ -90,7 +92,7 @@ static int encode_bf16(CUtensorMap* out, const void* base, int rank, const cuuin
     return GVK_ERR_NO_DEVICE;
   }
   cuuint32_t estr[5] = {1, 1, 1, 1, 1};
-  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, const_cast<void*>(base), dims, strides_bytes, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+  CUresult r = fn(out, dtype, rank, const_cast<void*>(base), dims, strides_bytes, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_last_error("cuTensorMapEncodeTiled failed (CUresult %d): rank %d dims [%llu,%llu,%llu] box [%u,%u,%u]", (int)r, rank, (unsigned long long)dims[0],
@@ -101,6 +103,17 @@ static int encode_bf16(CUtensorMap* out, const void* base, int rank, const cuuin
   slot.map = *out;
   slot.valid = true;
   return GVK_OK;
+}
+
+static int encode_bf16(CUtensorMap* out, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes, const cuuint32_t* box) {
+  return encode_map(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, base, rank, dims, strides_bytes, box);
+}
+int make_tma_f32(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes, const uint32_t* box) {
+  cuuint64_t d[5], s[4];
+  cuuint32_t b[5];
+  for (int i = 0; i < rank; ++i) { d[i] = dims[i]; b[i] = box[i]; }
+  for (int i = 0; i + 1 < rank; ++i) s[i] = strides_bytes[i];
+  return encode_map(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, base, rank, d, s, b);
 }
 
 int make_tma_2d_bf16(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld_elems, uint32_t box_rows, uint32_t box_cols) {
@@ -132,7 +145,7 @@ long long gvk_struct_size(const char* name) {
   GVK_SZ(gvk_skinny_wgrad_params) GVK_SZ(gvk_layernorm_bwd_params) GVK_SZ(gvk_ssf_bwd_params) GVK_SZ(gvk_dropout_params) GVK_SZ(gvk_attn_fwd_params) GVK_SZ(gvk_attn_bwd_params)
   GVK_SZ(gvk_fusion_weights) GVK_SZ(gvk_fusion_grads) GVK_SZ(gvk_fusion_saved) GVK_SZ(gvk_fusion_fwd_params)
   GVK_SZ(gvk_fusion_bwd_params) GVK_SZ(gvk_head_fwd_params) GVK_SZ(gvk_head_bwd_params) GVK_SZ(gvk_mhsa_fwd_params) GVK_SZ(gvk_mhsa_bwd_params) GVK_SZ(gvk_rescale_intensity_params)
-  GVK_SZ(gvk_latent_xattn_fwd_params) GVK_SZ(gvk_latent_xattn_bwd_params)
+  GVK_SZ(gvk_latent_xattn_fwd_params) GVK_SZ(gvk_latent_xattn_bwd_params) GVK_SZ(gvk_patch_embed_params)
 #undef GVK_SZ
   return -1;
 }
@@ -194,6 +207,8 @@ int gvk_clip_adam(float* param, const float* grad, float* exp_avg, float* exp_av
                   float beta1, float beta2, float eps, float weight_decay, int step, float* grad_norm_out, gvk_stream_t stream) {
   return gvk::clip_adam(param, grad, exp_avg, exp_avg_sq, n, partials, max_norm, grad_scale, lr, beta1, beta2, eps, weight_decay, step, grad_norm_out, S(stream));
 }
+int gvk_patch_embed(const gvk_patch_embed_params* p, gvk_stream_t stream) { return gvk::patch_embed(p, S(stream)); }
+int gvk_patch_embed_supported(const gvk_patch_embed_params* p) { return gvk::patch_embed_supported(p); }
 int gvk_mhsa_fwd(const gvk_mhsa_fwd_params* p, gvk_stream_t stream) { return gvk::mhsa_fwd(p, S(stream)); }
 int gvk_mhsa_bwd(const gvk_mhsa_bwd_params* p, gvk_stream_t stream) { return gvk::mhsa_bwd(p, S(stream)); }
 size_t gvk_mhsa_bwd_ws_floats(int B, int T, int H) { return gvk::mhsa_bwd_ws_floats(B, T, H); }

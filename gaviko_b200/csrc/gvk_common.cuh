@@ -39,6 +39,8 @@ int make_tma_2d_bf16(CUtensorMap* out, const void* base, uint64_t rows, uint64_t
 int make_tma_3d_bf16(CUtensorMap* out, const void* base, uint64_t d2, uint64_t rows, uint64_t cols,
                      uint64_t ld_row_elems, uint64_t ld_d2_elems, uint32_t box_rows, uint32_t box_cols);
 
+int make_tma_f32(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes, const uint32_t* box);   // rank <= 5
+
 // op dispatchers (one per extern "C" entry point; defined next to their kernels)
 int gemm_dispatch(const gvk_gemm_params* p, cudaStream_t stream);
 int layernorm_fwd(const gvk_layernorm_fwd_params* p, cudaStream_t stream);
@@ -71,6 +73,8 @@ int batch_rowsum(const float* x, int ldx, int batch_rows, int row_offset, int R,
 int grad_sumsq(const float* grad, size_t n, float grad_scale, float* partials, cudaStream_t stream);
 int clip_adam(float* param, const float* grad, float* m, float* v, size_t n, const float* partials, float max_norm, float grad_scale, float lr, float beta1,
               float beta2, float eps, float wd, int step, float* norm_out, cudaStream_t stream);
+int patch_embed(const gvk_patch_embed_params* p, cudaStream_t stream);
+int patch_embed_supported(const gvk_patch_embed_params* p);
 int mhsa_fwd(const gvk_mhsa_fwd_params* p, cudaStream_t stream);
 int mhsa_bwd(const gvk_mhsa_bwd_params* p, cudaStream_t stream);
 int mhsa_ws_fwd(const gvk_mhsa_fwd_params* p, cudaStream_t stream);

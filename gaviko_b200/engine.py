@@ -126,6 +126,7 @@ class GavikoEngine:
             return cache.get((key, 'v'), src, lambda t: t.float().contiguous())
 
         W = dict(conv_w=mat('conv_w', m.conv_proj[0].weight), conv_b=vec('conv_b', m.conv_proj[0].bias),
+                 conv_w32=cache.get(('conv_w32',), m.conv_proj[0].weight, lambda t: t.reshape(t.shape[0], -1).float().contiguous()),
                  pos_patch=cache.get(('pos_patch',), m.pos_embedding, lambda t: t[0, 1:].float().contiguous()),
                  pos_cls=cache.get(('pos_cls',), m.pos_embedding, lambda t: t[0, :1].float().contiguous()),
                  cls=cache.get(('cls',), m.cls_token, lambda t: t.reshape(1, dim).float().contiguous()),
@@ -219,11 +220,16 @@ class GavikoEngine:
             raise GvkError(f'unexpected volume shape {tuple(img.shape)}')
 
         # a1 + a2: patch gather -> GEMM whose epilogue adds bias + positional embedding and writes both token streams
-        patches = ops.patch_gather(img, c['fp'], c['ps'], cdt)
         g = torch.empty((B * T, dim), device=img.device, dtype=torch.float32)
         loc = torch.empty((B * N, dim), device=img.device, dtype=torch.float32)
-        ops.gemm(patches, W['conv_w'], bias=W['conv_b'], pos=W['pos_patch'], rows_per_batch=N, out_batch_rows=T, out_row_offset=P + 1, out=g, out2=loc)
-        del patches
+        fused = False
+        if cdt != torch.float32:
+            # bf16 mode: ONE kernel — TMA patch gather into a tf32 tcgen05 GEMM, bias + positional embedding + both token streams in the epilogue
+            fused = ops.patch_embed(img, c['fp'], c['ps'], W['conv_w32'], W['conv_b'], W['pos_patch'], g, T, P + 1, out2=loc)
+        if not fused:
+            patches = ops.patch_gather(img, c['fp'], c['ps'], cdt)
+            ops.gemm(patches, W['conv_w'], bias=W['conv_b'], pos=W['pos_patch'], rows_per_batch=N, out_batch_rows=T, out_row_offset=P + 1, out=g, out2=loc)
+            del patches
         ops.fill_rows(Tr['prompt_emb'], Tr['prompt_pos'], g, T, 0, B)
         ops.fill_rows(W['cls'], W['pos_cls'], g, T, P, B)
 

@@ -381,6 +381,21 @@ def patch_gather(img, fp, ps, out_dtype):
     return out
 
 
+def patch_embed(img, fp, ps, weight, bias, pos, out, out_batch_rows, out_row_offset, out2=None):
+    """Fused TMA patch gather + tf32 tcgen05 GEMM + bias / positional embedding / token-row scatter (gvk_patch_embed).  Returns False (and does
+    nothing) when the geometry is outside the kernel's range, so that the caller can take the gather + GEMM route."""
+    B, Cc, D, H, W = img.shape
+    if img.dtype != torch.float32 or not img.is_contiguous() or weight.dtype != torch.float32 or not weight.is_contiguous():
+        raise GvkError('patch_embed: expected contiguous fp32 volume and weight')
+    p = S['gvk_patch_embed_params']()
+    _set(p, img=img, B=B, C=Cc, D=D, H=H, W=W, fp=fp, ps=ps, weight=weight, bias=bias, pos=pos, dim=weight.shape[0], out=out, ld_out=_ld(out),
+         out_batch_rows=out_batch_rows, out_row_offset=out_row_offset, out2=out2, ld_out2=_ld(out2) if out2 is not None else 0)
+    if not L.lib().gvk_patch_embed_supported(C.byref(p)):
+        return False
+    L.call('gvk_patch_embed', C.byref(p), L.stream())
+    return True
+
+
 def fill_rows(a, b, out, out_batch_rows, out_row_offset, B):
     R, dim = a.shape
     L.call('gvk_fill_rows', C.c_void_p(L.fptr(a)), C.c_void_p(L.fptr(b)) if b is not None else None, R, dim, C.c_void_p(L.ptr(out, torch.float32)), _ld(out),

@@ -326,6 +326,24 @@ int gvk_rescale_intensity(const gvk_rescale_intensity_params* p, gvk_stream_t st
  * img fp32 contiguous (B, C, D, H, W); patches row-major [B*N, C*fp*ps*ps] in out_dtype. */
 int gvk_patch_gather(const float* img, int B, int C, int D, int H, int W, int fp, int ps, void* patches, int out_dtype, gvk_stream_t stream);
 
+/* Patch embedding in one kernel (a1 + a2 of the hot path; replaces Gaviko.conv_proj = nn.Conv3d(C, dim, kernel = stride = (fp, ps, ps)),
+ * flatten(2).transpose(1, 2) and the patch rows of the token assembly, model/gaviko.py:383-385,532-548): 5-D TMA boxes gather the
+ * non-overlapping patches of the fp32 volume straight into the operand ring of a tcgen05 GEMM (tf32 operands, fp32 accumulation), whose
+ * epilogue writes   x = conv(img)[b, tok, :] + bias + pos[tok, :]   to  out[b*out_batch_rows + out_row_offset + tok, :]  and, when out2 is
+ * set, to out2[b*n_tok + tok, :].  tok = (d*gh + h)*gw + w.  weight is the Conv3d weight as stored: [dim, C*fp*ps*ps] fp32.
+ * gvk_patch_embed_supported() != 0 for ps = 16 and <= 256 tokens per (b, d) plane; other geometries use gvk_patch_gather + gvk_gemm. */
+typedef struct {
+  const float* img; int B, C, D, H, W; int fp, ps;
+  const float* weight;
+  const float* bias;
+  const float* pos;
+  int dim;
+  float* out; int ld_out; int out_batch_rows, out_row_offset;
+  float* out2; int ld_out2;
+} gvk_patch_embed_params;
+int gvk_patch_embed(const gvk_patch_embed_params* p, gvk_stream_t stream);
+int gvk_patch_embed_supported(const gvk_patch_embed_params* p);
+
 /* out[b*out_batch_rows + out_row_offset + r, :] = a[r, :] + b[r, :]   for b < B, r < R   (b may be NULL).
  * Writes the batch-broadcast prompt / cls rows of the token matrix (model/gaviko.py:536-543). */
 int gvk_fill_rows(const float* a, const float* b, int R, int dim, float* out, int ld_out, int out_batch_rows, int out_row_offset, int B, gvk_stream_t stream);

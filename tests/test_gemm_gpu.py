@@ -121,3 +121,28 @@ def test_k_extension_with_split_operands():
     assert rel < 5e-5, rel
     plain = (c.bfloat16().double() @ wu.bfloat16().double().t())          # what a single bf16 product would give
     assert rel < 0.05 * ((plain - want).norm() / want.norm()).item()
+
+
+@pytest.mark.parametrize('B,C,D,H,W,fp,dim,T_extra', [(2, 1, 120, 160, 160, 12, 768, 33), (3, 1, 24, 64, 48, 12, 192, 9), (1, 2, 12, 32, 32, 6, 128, 0), (5, 1, 36, 160, 160, 12, 256, 1)])
+def test_patch_embed_fused_tma_gather(B, C, D, H, W, fp, dim, T_extra):
+    """gvk_patch_embed (TMA patch gather -> tf32 tcgen05 GEMM -> bias + positional embedding -> both token streams) against Conv3d in fp64
+    (model/gaviko.py:383-385,532-548); tolerance = tf32 operand rounding (2^-11 relative per product, K up to 3072)."""
+    from gaviko_b200 import ops
+    torch.manual_seed(B * 7 + dim)
+    ps = 16
+    img = torch.rand(B, C, D, H, W, device='cuda') * 2 - 0.7
+    w = torch.randn(dim, C, fp, ps, ps, device='cuda') * 0.02
+    bias = torch.randn(dim, device='cuda')
+    n_tok = (D // fp) * (H // ps) * (W // ps)
+    pos = torch.randn(n_tok, dim, device='cuda')
+    T = n_tok + T_extra
+    g = torch.full((B * T, dim), 7.0, device='cuda')
+    loc = torch.empty((B * n_tok, dim), device='cuda')
+    assert ops.patch_embed(img, fp, ps, w.reshape(dim, -1).contiguous(), bias, pos, g, T, T_extra, out2=loc)
+    ref = torch.nn.functional.conv3d(img.double(), w.double(), bias.double(), stride=(fp, ps, ps)).flatten(2).transpose(1, 2) + pos.double()
+    got = g.view(B, T, dim)[:, T_extra:].double()
+    err = (got - ref).abs().max().item() / ref.abs().max().item()
+    assert err < 2e-3, err
+    assert torch.equal(loc.view(B, n_tok, dim), g.view(B, T, dim)[:, T_extra:])
+    if T_extra:
+        assert bool((g.view(B, T, dim)[:, :T_extra] == 7.0).all())        # the prompt / cls rows are not touched
