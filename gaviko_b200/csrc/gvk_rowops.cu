@@ -675,7 +675,11 @@ __global__ void __launch_bounds__(kRowThreads, 1) layernorm_bwd_kernel(gvk_layer
       for (int q = 0; q < ROWS; ++q)
 #pragma unroll
         for (int i = 0; i < NITER; ++i) {
-          const float2 d = *reinterpret_cast<const float2*>(p.dy + rowc[q] * p.ld_dy + lane * 2 + 64 * i);
+          float2 d;
+          if (p.dy_dtype == GVK_BF16)
+            d = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(reinterpret_cast<const __nv_bfloat16*>(p.dy) + rowc[q] * p.ld_dy + lane * 2 + 64 * i));
+          else
+            d = *reinterpret_cast<const float2*>(reinterpret_cast<const float*>(p.dy) + rowc[q] * p.ld_dy + lane * 2 + 64 * i);
           if (p.dz) {
             dy[q][i].x += d.x;
             dy[q][i].y += d.y;
@@ -823,6 +827,8 @@ __global__ void __launch_bounds__(kRowThreads, 1) layernorm_bwd_kernel(gvk_layer
 int layernorm_bwd(const gvk_layernorm_bwd_params* p, cudaStream_t stream) {
   GVK_CHECK_ARG(p && p->x && p->gamma && p->mean && p->rstd && p->dx, "gvk_layernorm_bwd: null pointer");
   GVK_CHECK_ARG(p->dy != nullptr || p->dz != nullptr, "gvk_layernorm_bwd: dy and / or dz must be given");
+  GVK_CHECK_ARG(p->dy_dtype == GVK_F32 || p->dy_dtype == GVK_BF16, "gvk_layernorm_bwd: dy_dtype must be GVK_F32 or GVK_BF16");
+  GVK_CHECK_ARG(p->dy_dtype == GVK_F32 || static_cast<const void*>(p->dx) != p->dy, "gvk_layernorm_bwd: dx cannot alias a bf16 dy");
   GVK_CHECK_ARG(!p->ssf_scale || p->beta, "gvk_layernorm_bwd: the SSF form needs beta (to rebuild the LayerNorm output)");
   GVK_CHECK_ARG(!p->dz || (p->w && p->r >= 1 && p->r <= 32), "gvk_layernorm_bwd: rank-r form needs w and 1 <= r <= 32");
   GVK_CHECK_ARG(!p->az || (p->aw && p->ra >= 1 && p->ra <= 32), "gvk_layernorm_bwd: additive rank term needs aw and 1 <= ra <= 32");

@@ -336,8 +336,8 @@ class GavikoEngine:
             a_in = dG_lp if lp else dG
             # ---- MLP dgrad: dH2 = (dG W2) * gelu'(hpre) W1
             dA = ops.gemm(a_in, Lw['w2_t'], act=ops.ACT_MUL_AUX, aux=st['hpre'], out_dtype=cdt)
-            dH2 = ops.gemm(dA, Lw['w1_t'])
-            del dA
+            dH2 = ops.gemm(dA, Lw['w1_t'], out_dtype=cdt)     # bf16 mode: the gradient of the LayerNorm output travels as bf16 (half the bytes of
+            del dA                                            # the GEMM's stores and of the LayerNorm backward's reads; its operands were bf16 anyway)
             # ---- prompt up-projection: d(comb) = dG Wu ; dWu, dbu
             dcomb = ops.rowproj_down(dG, Fu['wu'], transposed=True, prec=pr)['z']
             ops.skinny_wgrad(st['comb'], dG, dw=gF['wu'], dw_layout='dr', dx_colsum=gF['bu'], prec=pr)
@@ -348,7 +348,8 @@ class GavikoEngine:
             ops.skinny_wgrad(dul, st['loc_out'], dw=gF['wd'], dw_layout='rd', da_colsum=gF['bd'], prec=pr)
             # ---- d(g_mid) = dG + LN2'(dH2) + du Wd
             dGm_lp = torch.empty((B * T, dim), device=dev, dtype=cdt) if lp else None
-            dGm = ops.layernorm_bwd(st['g_mid'], Lw['ln2_w'], st['mean2'], st['rstd2'], dy=dH2, dres=dG, dx=dH2, dx_lp=dGm_lp, az=du, aw=Fu['wd'])
+            dGm = ops.layernorm_bwd(st['g_mid'], Lw['ln2_w'], st['mean2'], st['rstd2'], dy=dH2, dres=dG, dx=None if lp else dH2, dx_lp=dGm_lp, az=du, aw=Fu['wd'])
+            del dH2
             # ---- d(loc_out) += dul Wd
             if dLoc is None:
                 dLoc = ops.rowproj_up(dul, Fu['wd'], transposed=True, prec=pr)
@@ -358,10 +359,10 @@ class GavikoEngine:
             dO = ops.gemm(dGm_lp if lp else dGm, Lw['wo_t'], out_dtype=cdt)
             dqkv = self.mhsa_bwd(st['qkv'], st['o'], st['lse'], dO, B, T, H, D, H * D)
             del dO
-            dH1 = ops.gemm(dqkv, Lw['wqkv_t'])
+            dH1 = ops.gemm(dqkv, Lw['wqkv_t'], out_dtype=cdt)
             del dqkv
-            dG = ops.layernorm_bwd(st['g_in'], Lw['ln1_w'], st['mean1'], st['rstd1'], dy=dH1, dres=dGm, dx=dH1, dx_lp=dG_lp)
-            del dGm
+            dG = ops.layernorm_bwd(st['g_in'], Lw['ln1_w'], st['mean1'], st['rstd1'], dy=dH1, dres=dGm, dx=dGm if lp else dH1, dx_lp=dG_lp)
+            del dGm, dH1
             # ---- local branch backward
             dctx = ops.rowproj_down(dLoc, La['wu'], transposed=True, drop_p=ctx['drop_proj'], seed=st['seed_p'], prec=pr)['z']
             ops.skinny_wgrad(st['ctx_l'], dLoc, dw=gL['wu'], dw_layout='dr', dx_colsum=gL['bu'], drop_p=ctx['drop_proj'], seed=st['seed_p'], prec=pr)

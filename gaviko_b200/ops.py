@@ -194,7 +194,7 @@ def layernorm_bwd(x, gamma, mean, rstd, *, dy=None, dz=None, w=None, dres=None, 
     _set(p, x=L.ptr(x, torch.float32), ldx=_ld(x), gamma=L.fptr(gamma), mean=L.fptr(mean), rstd=L.fptr(rstd),
          dx=L.ptr(dx, torch.float32), ld_dx=_ld(dx), dgamma=L.fptr(dgamma), dbeta=L.fptr(dbeta), M=M, dim=dim)
     if dy is not None:
-        _set(p, dy=L.ptr(dy, torch.float32), ld_dy=_ld(dy))
+        _set(p, dy=L.ptr(dy), ld_dy=_ld(dy), dy_dtype=L.dtype_tag(dy.dtype))
     if dz is not None:
         r = dz.shape[1]
         assert tuple(w.shape) == (r, dim) and w.is_contiguous()

@@ -246,8 +246,7 @@ class VitEngine:
         if ctx['emb_drop'][0] > 0:
             x = ops.dropout(x, ctx['emb_drop'][0], ctx['emb_drop'][1])
         vpt = self.kind == 'vpt'
-        if vpt and _p(m.prompt_dropout) > 0:
-            raise NotImplementedError('prompt_dropout > 0 in training mode is not implemented (reference default 0.0)')
+        p_prompt = _p(m.prompt_dropout) if vpt else 0.0      # model/vpt.py:57,129,148,152 (vpt.yaml ships prompt_dropout = 0.1)
         for i in range(c['depth']):
             Lw = W['layers'][i]
             st = dict(T_in=T)
@@ -257,8 +256,12 @@ class VitEngine:
                 P = pr_tok.shape[0]
                 skip = 0 if i == 0 else m.deep_prompt_embeddings.shape[2]
                 x3 = x.view(B, T, dim)
-                x = torch.cat([x3[:, :1], pr_tok.unsqueeze(0).expand(B, P, dim), x3[:, 1 + skip:]], 1).reshape(-1, dim)
-                st.update(vpt=(P, skip, E))
+                pr_b = pr_tok.unsqueeze(0).expand(B, P, dim)
+                seed_pr = self._seed(i, 7)
+                if p_prompt > 0:     # the reference expands to the batch BEFORE the dropout: every volume gets its own mask
+                    pr_b = ops.dropout(pr_b.reshape(B * P, dim).contiguous(), p_prompt, seed_pr).view(B, P, dim)
+                x = torch.cat([x3[:, :1], pr_b, x3[:, 1 + skip:]], 1).reshape(-1, dim)
+                st.update(vpt=(P, skip, E), vpt_drop=(p_prompt, seed_pr))
                 T = x.shape[0] // B
             st['T'] = T
             sa = Lw.get('ssf', {})
@@ -446,7 +449,12 @@ class VitEngine:
                 # undo the token insertion: prompt rows feed prompt_proj / the embeddings, dropped rows get zero gradient
                 P, skip, E = st['vpt']
                 T_in = st['T_in']
-                dPr = ops.batch_rowsum(dX, T, 1, P, B)                                                   # [P, dim] = sum over the batch
+                p_prompt, seed_pr = st['vpt_drop']
+                if p_prompt > 0:      # replay the forward's mask on the prompt rows before they are summed over the batch
+                    dpr_b = ops.dropout(dX.view(B, T, dim)[:, 1:1 + P].reshape(B * P, dim).contiguous(), p_prompt, seed_pr)
+                    dPr = ops.batch_rowsum(dpr_b, P, 0, P, B)
+                else:
+                    dPr = ops.batch_rowsum(dX, T, 1, P, B)                                               # [P, dim] = sum over the batch
                 wp = _f32(m.prompt_proj.weight)
                 pd = wp.shape[1]
                 if g('prompt_proj.weight') is not None:

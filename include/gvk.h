@@ -173,9 +173,9 @@ int gvk_skinny_wgrad(const gvk_skinny_wgrad_params* p, gvk_stream_t stream);
  * az @ aw (optional, az [M, ra], aw(j, c) strided like w) is added OUTSIDE the norm: the dgrad of a rank-ra down-projection that reads
  * the same residual stream as the LayerNorm (Awakening_Prompt.proj_down next to FeedForward's norm, model/gaviko.py:155,304).
  * dgamma / dbeta (optional, [dim]) accumulate with atomics.  dx may alias dres or dy.
- * dx_lp is an optional bf16 copy (the next dgrad GEMM's A operand). */
+ * dx_lp is an optional bf16 copy (the next dgrad GEMM's A operand).  dx may alias dy only when dy is fp32. */
 typedef struct {
-  const float* dy; int ld_dy;
+  const void* dy; int ld_dy; int dy_dtype;   /* GVK_F32 or GVK_BF16 (the dgrad GEMM that produces dy then writes half the bytes) */
   const float* dz; int ld_dz; const float* w; int w_sj, w_sc; int r;
   const float* x; int ldx; const float* gamma; const float* mean; const float* rstd;
   const float* dres; int ld_dres;

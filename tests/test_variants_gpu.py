@@ -74,3 +74,45 @@ def test_variant_bf16_matches_reference(name, tmp_path):
         tol_t = max(0.15, 2 * float(g[f'refbf16_grad_worst_{loss_name}']))
         glob, worst, wname = grad_parity(grads, g, loss_name, tol_global=tol_g, tol_tensor=tol_t, floor=1e-2, floor_slack=2.0)
         print(f'{name} {loss_name}: logits rel {rl:.2e} grads global {glob:.2e} worst {worst:.2e} ({wname})')
+
+
+@pytest.mark.parametrize('name', ['deep_vpt_t16_small', 'shallow_vpt_t16_small'])
+def test_vpt_prompt_dropout_mask_is_replayed_in_backward(name, tmp_path):
+    """prompt_dropout > 0 (the reference's vpt.yaml ships 0.1; model/vpt.py:57,129,148,152): train mode is stochastic across steps, reproducible for
+    a fixed step counter, and the analytic gradient of the prompt embeddings equals a central difference taken under the SAME mask."""
+    method, kw, batch = ALL_CASES[name]
+    cwd = os.getcwd()
+    os.chdir(tmp_path)
+    try:
+        model = build_variant(method, dict(kw, compute_dtype='fp32', prompt_dropout=0.5))
+    finally:
+        os.chdir(cwd)
+    golden_fill(model, seed=0)
+    model = model.cuda()
+    model.train()
+    img = golden_volume(batch, kw['frames'], kw['image_size'], kw['image_size'], channels=kw['channels']).cuda()
+    y = golden_labels(batch, kw['num_classes']).cuda()
+    eng = model._engine
+    crit = CrossEntropyLoss()
+
+    def loss_at(step):
+        eng._step = step
+        return crit(model(img), y)
+
+    l0 = loss_at(10)
+    assert loss_at(10).item() == l0.item()              # same step counter -> same masks
+    assert loss_at(11).item() != l0.item()              # next step -> new masks
+    emb = model.deep_prompt_embeddings if kw['deep_prompt'] else model.prompt_embeddings
+    model.zero_grad()
+    loss_at(10).backward()
+    g = emb.grad.detach().clone()
+    v = torch.randn(emb.shape, generator=torch.Generator().manual_seed(5)).cuda()      # (torch.manual_seed would re-key the engine's dropout masks)
+    eps = 1e-2
+    with torch.no_grad():
+        emb.add_(eps * v)
+        lp = loss_at(10).item()
+        emb.sub_(2 * eps * v)
+        lm = loss_at(10).item()
+        emb.add_(eps * v)
+    fd, an = (lp - lm) / (2 * eps), (g * v).sum().item()
+    assert abs(fd - an) <= 2e-2 * max(abs(an), abs(fd)) + 1e-5, (fd, an)
