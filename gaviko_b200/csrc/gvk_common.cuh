@@ -78,9 +78,11 @@ int patch_embed_supported(const gvk_patch_embed_params* p);
 int mhsa_fwd(const gvk_mhsa_fwd_params* p, cudaStream_t stream);
 int mhsa_bwd(const gvk_mhsa_bwd_params* p, cudaStream_t stream);
 int mhsa_ws_fwd(const gvk_mhsa_fwd_params* p, cudaStream_t stream);
+int mhsa_fwd2(const gvk_mhsa_fwd_params* p, cudaStream_t stream);
 int mhsa_bwd_ws(const gvk_mhsa_bwd_params* p, cudaStream_t stream);
 int mhsa_bwd_pipe(const gvk_mhsa_bwd_params* p, cudaStream_t stream);
 int debug_trace(uint32_t* out, int n_words);
+uint32_t* trace_buffer();   // device buffer [kTraceRoles][kTraceN][2] (allocated on first use), or nullptr
 size_t mhsa_bwd_ws_floats(int B, int T, int H);
 size_t mhsa_bwd_mask_words(int B, int T, int H);
 int prompt_fusion_fwd(const gvk_fusion_fwd_params* p, cudaStream_t stream);
@@ -392,6 +394,16 @@ __device__ __forceinline__ uint32_t mhsa_keep16(const MhsaDrop& d, uint32_t bh, 
   auto keep4 = [&](uint32_t w) { return ((__vcmpltu4(w, d.thr4) & 0x01010101u) * 0x01020408u) >> 24; };
   return (keep4(r.x) & 15u) | ((keep4(r.y) & 15u) << 4) | ((keep4(r.z) & 15u) << 8) | ((keep4(r.w) & 15u) << 12);
 }
+// Timeline trace for tuning the attention kernels: CTA 0 records (tag, clock) pairs per role; read back with gvk_debug_trace (tools/mhsa_trace.py).
+constexpr int kTraceN = 2048, kTraceRoles = 4;
+struct Tracer {
+  uint2* base;
+  int n;
+  __device__ __forceinline__ void init(uint32_t* buf, int role, bool on) { base = (on && buf && blockIdx.x == 0) ? reinterpret_cast<uint2*>(buf) + role * kTraceN : nullptr; n = 0; }
+  __device__ __forceinline__ void operator()(uint32_t tag) {
+    if (base && n < kTraceN) base[n++] = make_uint2(tag, static_cast<uint32_t>(clock()));
+  }
+};
 __device__ __forceinline__ float u32_to_unit(uint32_t x) { return (x >> 8) * (1.0f / 16777216.0f); }  // [0,1)
 #endif  // __CUDACC__
 

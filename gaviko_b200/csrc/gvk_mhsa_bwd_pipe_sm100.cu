@@ -90,21 +90,6 @@ __device__ __forceinline__ void mma_accum(uint32_t d_tmem, uint32_t a_tmem, uint
   }
 }
 
-// Timeline trace for tuning (GVK_PIPE_DBG & 4): CTA 0 records (tag, clock) pairs per role; read back with gvk_debug_trace.
-constexpr int kTraceN = 2048;
-__device__ __align__(8) uint32_t g_trace[4][kTraceN][2];
-struct Tracer {
-  int role, n;
-  bool on;
-  __device__ __forceinline__ void init(int role_, bool on_) { role = role_; n = 0; on = on_ && blockIdx.x == 0; }
-  __device__ __forceinline__ void operator()(uint32_t tag) {
-    if (on && n < kTraceN) {
-      *reinterpret_cast<uint2*>(&g_trace[role][n][0]) = make_uint2(tag, static_cast<uint32_t>(clock()));
-      ++n;
-    }
-  }
-};
-
 struct Args {
   int B, T, H, dim;
   int Tpad;        // T rounded up to 128: row stride of the statistics workspace
@@ -118,6 +103,7 @@ struct Args {
   int num_items;   // B * H * nb
   MhsaDrop drop;   // attention-probability dropout of the forward call (kDrop instantiations)
   uint32_t* mask;  // [B*H][nb (key block)][Tpad (query)][4]: keep bits of the 128 keys of a block, written by the dQ kernel for the dK/dV kernel
+  uint32_t* trace;
   int dbg;         // timing experiments only (GVK_PIPE_DBG): 1 = no exp2, 2 = softmax warps only pass the barriers on (results are wrong); 4 = record the timeline of CTA 0
 };
 
@@ -194,7 +180,7 @@ mhsa_bwd_dq_pipe_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __gri
       // pipe's in-order execution used to order them.
       uint32_t kv_base = 0, work = 0, g0 = 0;   // g = g0 + j numbers the score blocks of this CTA: S buffer g & 1
       const uint32_t idesc_full = make_idesc_bf16(128, kTile, 0, 0), idesc_tail = make_idesc_bf16(128, a.ntail, 0, 0);
-      Tracer tr; tr.init(0, (a.dbg & 4) && lane == 0);
+      Tracer tr; tr.init(a.trace, 0, (a.dbg & 4) && lane == 0);
       for (int item = blockIdx.x; item < a.num_items; item += gridDim.x, ++work, kv_base += nb, g0 += nb) {
         const int ib = work & 1;
         const uint32_t q_lo = desc_lo_k(smem_u32(sQ + ib * kTileBytes)), do_lo = desc_lo_k(smem_u32(sdO + ib * kTileBytes));
@@ -237,7 +223,7 @@ mhsa_bwd_dq_pipe_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __gri
     } else if (warp == 2) {
       // ===================== accumulator issuer: dQ(j) =====================
       uint32_t kv_base = 0, work = 0, g0 = 0;
-      Tracer tr; tr.init(3, (a.dbg & 4) && lane == 0);
+      Tracer tr; tr.init(a.trace, 3, (a.dbg & 4) && lane == 0);
       for (int item = blockIdx.x; item < a.num_items; item += gridDim.x, ++work, kv_base += nb, g0 += nb) {
         const int ib = work & 1;
         for (int j = 0; j < nb; ++j) {
@@ -270,10 +256,15 @@ mhsa_bwd_dq_pipe_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __gri
     const float c2 = a.scale * kLog2e;
     const float2 c2v = make_float2(c2, c2);
     uint32_t g = 0, work = 0;
-    Tracer tr; tr.init(1 + grp, (a.dbg & 4) && (warp & 3) == 0 && lane == 0);
+    Tracer tr; tr.init(a.trace, 1 + grp, (a.dbg & 4) && (warp & 3) == 0 && lane == 0);
     // Per-item set-up (row statistics), software-pipelined one item ahead: the set-up of item n+1 runs in the shadow of item n's last dQ MMAs
     // (the groups would otherwise idle there), so block 0 of the next item starts right behind the epilogue.
     struct ItemCtx { int b, h, bh, row; float lse2, delta; };
+    float lse_pre = 0.f;      // lse of the item AFTER the one being set up: its global load has a whole item to land
+    auto lse_of = [&](int item) {
+      const int bh = item / nb, row = (item - bh * nb) * kTile + r;
+      return (item < a.num_items && row < T) ? a.lse[(size_t)bh * T + row] : 0.f;
+    };
     auto setup = [&](int item, uint32_t wk) {
       ItemCtx c;
       const int bh = item / nb, qt = item - bh * nb;
@@ -282,7 +273,8 @@ mhsa_bwd_dq_pipe_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __gri
       c.bh = bh;
       c.row = qt * kTile + r;
       const int ib = wk & 1;
-      c.lse2 = c.row < T ? a.lse[(size_t)bh * T + c.row] * kLog2e : INFINITY;
+      c.lse2 = c.row < T ? lse_pre * kLog2e : INFINITY;
+      lse_pre = lse_of(item + gridDim.x);
       mbar_wait_warp(&bars[BAR_Q_FULL + ib], (wk >> 1) & 1, lane);
       const uint4* pd = reinterpret_cast<const uint4*>(sdO + ib * kTileBytes + r * 128);
       const uint4* po = reinterpret_cast<const uint4*>(sO + ib * kTileBytes + r * 128);
@@ -308,6 +300,7 @@ mhsa_bwd_dq_pipe_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __gri
       return c;
     };
     ItemCtx cur{};
+    lse_pre = lse_of(blockIdx.x);
     if ((int)blockIdx.x < a.num_items) cur = setup(blockIdx.x, 0);
     for (int item = blockIdx.x; item < a.num_items; item += gridDim.x, ++work) {
       const int b = cur.b, h = cur.h, bh = cur.bh, row = cur.row;
@@ -532,21 +525,26 @@ mhsa_bwd_dkv_pipe_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __gr
     } else if (warp == 2) {
       // ===================== accumulator issuer: dV(i), dK(i) =====================
       uint32_t q_base = 0, work = 0, g0 = 0;
+      Tracer tr; tr.init(a.trace, 3, (a.dbg & 16) && lane == 0);
       for (int item = blockIdx.x; item < a.num_items; item += gridDim.x, ++work, q_base += nb, g0 += nb) {
         const int ib = work & 1;
         for (int i = 0; i < nb; ++i) {
           const uint32_t it = q_base + i, g = g0 + i;
           const int st = it % kStages;
           const int ksteps = (i == nb - 1 ? a.ntail : kTile) / 16;
+          tr(0x100 + i);
           mbar_wait(&bars[BAR_P_FULL + (g & 1)], (g >> 1) & 1);       // implies S^T(i) complete: Q_i landed, and K / V of the item
           tc_fence_after();
+          tr(0x200 + i);
           if (elect_one()) {
             mma_accum(tmem + kColDV, tmem + kColS + (g & 1) * 128, desc_lo_mn(smem_u32(sdO + st * kTileBytes)), ksteps, i > 0);   // dV (+)= P^T dO_i
             umma_commit(&bars[BAR_DV_STEP + (g & 1)]);
           }
           __syncwarp();
+          tr(0x300 + i);
           mbar_wait(&bars[BAR_DS_FULL + (g & 1)], (g >> 1) & 1);
           tc_fence_after();
+          tr(0x400 + i);
           if (elect_one()) {
             mma_accum(tmem + kColDK, tmem + kColDP, desc_lo_mn(smem_u32(sQ + st * kTileBytes)), ksteps, i > 0);                    // dK (+)= dS^T Q_i
             umma_commit(&bars[BAR_DK_STEP]);
@@ -571,10 +569,12 @@ mhsa_bwd_dkv_pipe_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __gr
     const float c2 = a.scale * kLog2e;
     const float2 c2v = make_float2(c2, c2);
     uint32_t g = 0, work = 0, q_base = 0;
+    Tracer tr; tr.init(a.trace, 1 + grp, (a.dbg & 16) && (warp & 3) == 0 && lane == 0);
     for (int item = blockIdx.x; item < a.num_items; item += gridDim.x, ++work, q_base += nb) {
       const int bh = item / nb, kt = item - bh * nb;
       const int h = bh % a.H, b = bh / a.H;
       for (int i = 0; i < nb; ++i, ++g) {
+        tr(0x100 + i);
         const uint32_t it = q_base + i;
         const int st = it % kStages;
         const int ncols = (i == nb - 1 ? a.ntail : kTile) - 64 * grp;
@@ -584,6 +584,7 @@ mhsa_bwd_dkv_pipe_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __gr
         mbar_wait_warp(&bars[BAR_Q_FULL + st], (it / kStages) & 1, lane);       // the statistics of the stage (bulk copies) are visible
         mbar_wait_warp(&bars[BAR_S_FULL + (g & 1)], (g >> 1) & 1, lane);
         tc_fence_after();
+        tr(0x200 + i);
         if (a.dbg & 2) {
           tc_fence_before();
           __syncwarp();
@@ -656,8 +657,10 @@ mhsa_bwd_dkv_pipe_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __gr
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&bars[BAR_P_FULL + (g & 1)]);
+        tr(0x300 + i);
         mbar_wait_warp(&bars[BAR_DP_FULL], g & 1, lane);
         tc_fence_after();
+        tr(0x400 + i);
         if (ncols > 0) {
           float dp0[32], dp1[32];
           tmem_ld_32x32(tdP, dp0);
@@ -673,7 +676,9 @@ mhsa_bwd_dkv_pipe_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __gr
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&bars[BAR_DS_FULL + (g & 1)]);
+        tr(0x500 + i);
       }
+      tr(0x600);
       // ---- epilogue: group 0 stores dK * scale, group 1 dV
       mbar_wait_warp(&bars[BAR_ACC_FULL], work & 1, lane);
       tc_fence_after();
@@ -712,9 +717,18 @@ size_t mhsa_bwd_mask_words(int B, int T, int H) {
   return (size_t)B * H * nb * (nb * pb::kTile) * 4;
 }
 
+static uint32_t* g_trace_dev = nullptr;
+uint32_t* trace_buffer() {
+  if (!g_trace_dev) {
+    if (cudaMalloc(&g_trace_dev, sizeof(uint32_t) * kTraceRoles * kTraceN * 2) != cudaSuccess) return nullptr;
+    cudaMemset(g_trace_dev, 0, sizeof(uint32_t) * kTraceRoles * kTraceN * 2);
+  }
+  return g_trace_dev;
+}
 int debug_trace(uint32_t* out, int n_words) {
-  const size_t bytes = std::min<size_t>(sizeof(pb::g_trace), (size_t)n_words * 4);
-  return cuda_status(cudaMemcpyFromSymbol(out, pb::g_trace, bytes), "debug_trace");
+  if (!g_trace_dev) { set_last_error("gvk_debug_trace: no trace was recorded (GVK_PIPE_DBG)"); return GVK_ERR_INVALID_ARGUMENT; }
+  const size_t bytes = std::min<size_t>(sizeof(uint32_t) * kTraceRoles * kTraceN * 2, (size_t)n_words * 4);
+  return cuda_status(cudaMemcpy(out, g_trace_dev, bytes, cudaMemcpyDeviceToHost), "debug_trace");
 }
 
 int mhsa_bwd_pipe(const gvk_mhsa_bwd_params* p, cudaStream_t stream) {
@@ -751,6 +765,7 @@ int mhsa_bwd_pipe(const gvk_mhsa_bwd_params* p, cudaStream_t stream) {
   a.ld_dqkv = p->ld_dqkv;
   a.num_items = p->B * p->H * a.nb;
   { const char* e = getenv("GVK_PIPE_DBG"); a.dbg = e ? atoi(e) : 0; }
+  a.trace = (a.dbg & (4 | 16)) ? trace_buffer() : nullptr;
   const int grid = std::min(a.num_items, sm_count());
   const bool drop = p->drop_p > 0.f;
   GVK_CHECK_ARG(p->drop_p >= 0.f && p->drop_p < 1.f, "gvk_mhsa_bwd: drop_p must be in [0, 1)");

@@ -635,8 +635,11 @@ int mhsa_fwd(const gvk_mhsa_fwd_params* p, cudaStream_t stream) {
   GVK_CHECK_ARG(p->ld_out % 8 == 0, "gvk_mhsa_fwd: ld_out must be a multiple of 8");
   GVK_CHECK_ARG(p->drop_p >= 0.f && p->drop_p < 1.f, "gvk_mhsa_fwd: drop_p must be in [0, 1)");
   {
-    static int impl = -1;   // GVK_MHSA_IMPL=1 selects the older one-tile-per-CTA kernel (kept for A/B comparison)
+    // GVK_MHSA_IMPL: 2 = 64-key-step warp-specialised kernel (default: 420 us at B = 64), 3 = 128-key-step kernel with the SFU token (440 us; see its
+    // header for what the timeline showed), 1 = one tile per CTA (A/B comparison)
+    static int impl = -1;
     if (impl < 0) { const char* e = getenv("GVK_MHSA_IMPL"); impl = e ? atoi(e) : 2; }
+    if (impl == 3) return mhsa_fwd2(p, stream);
     if (impl == 2) return mhsa_ws_fwd(p, stream);
   }
   GVK_CHECK_ARG(p->drop_p == 0.f, "gvk_mhsa_fwd: attention dropout needs the warp-specialised kernel (GVK_MHSA_IMPL unset)");
