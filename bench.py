@@ -233,7 +233,21 @@ def run_ours(args):
     y_dev = labels_host.to(dev)
     loss_host = torch.zeros((), dtype=torch.float32).pin_memory()
 
+    gstep = None
+    launches_per_replay = 0
+    if args.graph:
+        if not train:
+            raise SystemExit('bench.py --graph: training only')
+        from gaviko_b200.graph import GraphedTrainStep
+        n0 = L.launch_count()
+        gstep = GraphedTrainStep(model, crit, opt, x_dev, y_dev, warmup=2)
+        launches_per_replay = (L.launch_count() - n0) // 3          # 2 warm-up steps + the captured one enqueue the same kernels
+
     def step(x, y):
+        if gstep is not None:
+            loss = gstep(x, y)
+            sched.step()
+            return loss
         if train:
             logits = model(x)
             loss = crit(logits, y)
@@ -268,7 +282,7 @@ def run_ours(args):
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
-    launches = L.launch_count() - launches0
+    launches = L.launch_count() - launches0 + launches_per_replay * args.steps      # kernel nodes of a graph replay are not seen by the library's counter
     ops.GEMM_HOOK = None
     clocks = sampler.stop() if sampler else None
     t = torch.tensor([ms], device=dev)
@@ -324,6 +338,12 @@ def run_ours(args):
         value = world * B * args.steps / (ms / 1e3)
         e2e_value = world * B * args.steps / (ms_e2e / 1e3)
         # roofline of the dominant kernel class: the tcgen05 GEMM (all launches inside the timed region, CUDA events on the launch stream)
+        if gstep is not None:      # no per-kernel events inside a graph replay: time the same GEMM launches over two eager steps after the timed region
+            ops.GEMM_HOOK = gemm_events
+            for _ in range(2):
+                loss = crit(model(x_dev), y_dev); opt.zero_grad(); loss.backward()
+            torch.cuda.synchronize()
+            ops.GEMM_HOOK = None
         gsec = sum(a.elapsed_time(b) for a, b, _ in gemm_events) / 1e3
         gflop = sum(f for _, _, f in gemm_events)
         peak = pk['bf16_tflops_sustained'] if args.dtype == 'bf16' else 80.0
@@ -336,7 +356,7 @@ def run_ours(args):
             pass
         roof = dict(bound='tensor', kernel='gemm_bf16_sm100_kernel' if args.dtype == 'bf16' else 'gemm_f32_kernel', achieved=(gflop / gsec / 1e12) if gsec > 0 else None,
                     peak=peak, unit='TFLOP/s', frac=(gflop / gsec / 1e12 / peak) if gsec > 0 else None, traffic=traffic, peak_source=f'{pk_src} (bf16_tflops_sustained)',
-                    launches=len(gemm_events), share_of_step=gsec * 1e3 / ms if ms > 0 else None,
+                    launches=len(gemm_events), share_of_step=(gsec * 1e3 / (2 if gstep is not None else args.steps)) / (ms / args.steps) if ms > 0 else None,
                     step_tensor_frac=world and (B * args.steps * flops_per_vol / (ms / 1e3) / 1e12 / peak))
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
@@ -363,7 +383,7 @@ def run_ours(args):
                     eager[name] = dict(value=None, unit='volumes/s', sample=f'failed: {type(ex).__name__}: {ex}'[:300])
                 torch.cuda.empty_cache()
         line = dict(metric=metric_name(args), value=value, unit='volumes/s', n_gpus=world, steps=args.steps, warmup=args.warmup, ms_per_step=ms / args.steps,
-                    higher_is_better=True, scaling='weak', vs_baseline=None, dtype=args.dtype, data='synthetic', config=workload(args, B, world), clocks=clocks,
+                    higher_is_better=True, scaling='weak', vs_baseline=None, dtype=args.dtype, data='synthetic', config=dict(workload(args, B, world), launch='one CUDA graph per step' if gstep is not None else 'eager (one launch per kernel)'), clocks=clocks,
                     e2e=dict(value=e2e_value, unit='volumes/s', h2d_bytes_per_step=world * (B * 120 * 160 * 160 * 4 + B * 8), d2h_bytes_per_step=world * 4,
                              ms_per_step=ms_e2e / args.steps),
                     gpu_launches=launches, roofline=roof, cpu_baseline=cpu, gpu_eager_baseline=eager,
@@ -383,6 +403,7 @@ def main():
     ap.add_argument('--backbone', default='vit-b16')
     ap.add_argument('--batch', type=int, default=64, help='volumes per GPU per step (SURVEY 8d: 16 | 32 | 64)')
     ap.add_argument('--dtype', default='bf16', choices=['bf16', 'fp32'])
+    ap.add_argument('--graph', action='store_true', help='train mode, N = 1: replay the whole step as ONE CUDA graph (gaviko_b200.graph.GraphedTrainStep)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-gpu-eager-baseline', action='store_true', help='skip timing the eager-PyTorch port of the reference on this GPU (N=1 only)')
     args = ap.parse_args()

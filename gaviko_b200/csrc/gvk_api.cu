@@ -209,6 +209,10 @@ int gvk_clip_adam(float* param, const float* grad, float* exp_avg, float* exp_av
 }
 int gvk_patch_embed(const gvk_patch_embed_params* p, gvk_stream_t stream) { return gvk::patch_embed(p, S(stream)); }
 int gvk_patch_embed_supported(const gvk_patch_embed_params* p) { return gvk::patch_embed_supported(p); }
+int gvk_clip_adam_dyn(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, size_t n, const float* partials, float max_norm, float grad_scale,
+                      const float* lr_dev, float beta1, float beta2, float eps, float wd, const long long* step_dev, float* norm_out, gvk_stream_t stream) {
+  return gvk::clip_adam_dyn(param, grad, exp_avg, exp_avg_sq, n, partials, max_norm, grad_scale, lr_dev, beta1, beta2, eps, wd, step_dev, norm_out, S(stream));
+}
 int gvk_mhsa_fwd(const gvk_mhsa_fwd_params* p, gvk_stream_t stream) { return gvk::mhsa_fwd(p, S(stream)); }
 int gvk_mhsa_bwd(const gvk_mhsa_bwd_params* p, gvk_stream_t stream) { return gvk::mhsa_bwd(p, S(stream)); }
 size_t gvk_mhsa_bwd_ws_floats(int B, int T, int H) { return gvk::mhsa_bwd_ws_floats(B, T, H); }

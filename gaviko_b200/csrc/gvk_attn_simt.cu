@@ -115,10 +115,10 @@ __device__ __forceinline__ void warp_reduce_scatter64(float (&v)[64], int lane) 
 __device__ __forceinline__ void store_elem(float* p, float v) { *p = v; }
 __device__ __forceinline__ void store_elem(__nv_bfloat16* p, float v) { *p = __float2bfloat16_rn(v); }
 
-__device__ __forceinline__ float prob_drop(const gvk_attn_fwd_params& p, uint64_t elem, float inv_keep) {
+__device__ __forceinline__ float prob_drop(const gvk_attn_fwd_params& p, uint64_t seed, uint64_t elem, float inv_keep) {
   const uint64_t e = p.offset + elem;
   const uint64_t ctr = e >> 2;
-  const uint4 r = philox4x32(make_uint4((uint32_t)ctr, (uint32_t)(ctr >> 32), 0u, 0u), make_uint2((uint32_t)p.seed, (uint32_t)(p.seed >> 32)));
+  const uint4 r = philox4x32(make_uint4((uint32_t)ctr, (uint32_t)(ctr >> 32), 0u, 0u), make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
   const uint32_t sel = (uint32_t)(e & 3);
   const uint32_t v = sel == 0 ? r.x : sel == 1 ? r.y : sel == 2 ? r.z : r.w;
   return u32_to_unit(v) >= p.drop_p ? inv_keep : 0.f;
@@ -127,6 +127,7 @@ __device__ __forceinline__ float prob_drop(const gvk_attn_fwd_params& p, uint64_
 // ------------------------------------------------------------------------------------------------
 template <int D, typename T>
 __global__ void __launch_bounds__(kAttnWarps * 32) attn_fwd_kernel(gvk_attn_fwd_params p) {
+  const uint64_t seed_eff = salted_seed(p.seed, p.seed_salt);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long idx = (long long)blockIdx.x * kAttnWarps + warp;
   if (idx >= (long long)p.B * p.H * p.T) return;
@@ -163,7 +164,7 @@ __global__ void __launch_bounds__(kAttnWarps * 32) attn_fwd_kernel(gvk_attn_fwd_
     }
     float pr = __expf(s - m);
     l += pr;
-    if (p.drop_p > 0.f) pr *= prob_drop(p, ((uint64_t)bh * p.T + i) * p.T + j, inv_keep);
+    if (p.drop_p > 0.f) pr *= prob_drop(p, seed_eff, ((uint64_t)bh * p.T + i) * p.T + j, inv_keep);
     axpy_row<D>(pr, base + (size_t)j * p.ld + p.v_off, acc);
   }
   const float M = warp_max(m);
@@ -190,6 +191,7 @@ __global__ void __launch_bounds__(kAttnWarps * 32) attn_fwd_kernel(gvk_attn_fwd_
 // dQ (+ delta): one warp per query
 template <int D, typename T>
 __global__ void __launch_bounds__(kAttnWarps * 32) attn_bwd_q_kernel(gvk_attn_bwd_params bp) {
+  const uint64_t seed_eff = salted_seed(bp.f.seed, bp.f.seed_salt);
   const gvk_attn_fwd_params& p = bp.f;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long idx = (long long)blockIdx.x * kAttnWarps + warp;
@@ -228,7 +230,7 @@ __global__ void __launch_bounds__(kAttnWarps * 32) attn_bwd_q_kernel(gvk_attn_bw
     const T* kr = base + (size_t)j * p.ld + p.k_off;
     const float pr = __expf(dot_row<D>(kr, q) - lse);
     float dp = dot_row<D>(base + (size_t)j * p.ld + p.v_off, dO);
-    if (p.drop_p > 0.f) dp *= prob_drop(p, ((uint64_t)bh * p.T + i) * p.T + j, inv_keep);
+    if (p.drop_p > 0.f) dp *= prob_drop(p, seed_eff, ((uint64_t)bh * p.T + i) * p.T + j, inv_keep);
     const float ds = pr * (dp - delta);
     axpy_row<D>(ds, kr, dq);
   }
@@ -252,6 +254,7 @@ __global__ void __launch_bounds__(kAttnWarps * 32) attn_bwd_q_kernel(gvk_attn_bw
 // dK, dV: one warp per key
 template <int D, typename T>
 __global__ void __launch_bounds__(kAttnWarps * 32) attn_bwd_kv_kernel(gvk_attn_bwd_params bp) {
+  const uint64_t seed_eff = salted_seed(bp.f.seed, bp.f.seed_salt);
   const gvk_attn_fwd_params& p = bp.f;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long idx = (long long)blockIdx.x * kAttnWarps + warp;
@@ -313,7 +316,7 @@ __global__ void __launch_bounds__(kAttnWarps * 32) attn_bwd_kv_kernel(gvk_attn_b
     const long long qi = (long long)bh * p.T + i;
     const float pr = __expf(s - p.lse[qi]);
     float mult = 1.f;
-    if (p.drop_p > 0.f) mult = prob_drop(p, (uint64_t)qi * p.T + j, inv_keep);
+    if (p.drop_p > 0.f) mult = prob_drop(p, seed_eff, (uint64_t)qi * p.T + j, inv_keep);
     const float ds = pr * (dp * mult - bp.delta[qi]);
     axpy_row<D>(pr * mult, dor, dv);
     axpy_row<D>(ds, qr, dk);

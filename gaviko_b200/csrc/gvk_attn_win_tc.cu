@@ -72,10 +72,10 @@ __device__ __forceinline__ void stage_range(const gvk_attn_fwd_params& p, const 
 
 // dropout multipliers of the aligned 2x2 block (queries 2*ib, 2*ib+1) x (keys 2*jb, 2*jb+1): x (even q, even k) y (even q, odd k)
 // z (odd q, even k) w (odd q, odd k)
-__device__ __forceinline__ float4 block_drop(const gvk_attn_fwd_params& p, int bh, int ib, int jb, float inv_keep) {
+__device__ __forceinline__ float4 block_drop(const gvk_attn_fwd_params& p, uint64_t seed, int bh, int ib, int jb, float inv_keep) {
   const uint64_t t2 = (uint64_t)(p.T + 1) / 2;
   const uint64_t ctr = p.offset + ((uint64_t)bh * t2 + ib) * t2 + jb;
-  const uint4 r = philox4x32(make_uint4((uint32_t)ctr, (uint32_t)(ctr >> 32), 0x77696eu, 0u), make_uint2((uint32_t)p.seed, (uint32_t)(p.seed >> 32)));
+  const uint4 r = philox4x32(make_uint4((uint32_t)ctr, (uint32_t)(ctr >> 32), 0x77696eu, 0u), make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
   return make_float4(u32_to_unit(r.x) >= p.drop_p ? inv_keep : 0.f, u32_to_unit(r.y) >= p.drop_p ? inv_keep : 0.f,
                      u32_to_unit(r.z) >= p.drop_p ? inv_keep : 0.f, u32_to_unit(r.w) >= p.drop_p ? inv_keep : 0.f);
 }
@@ -204,6 +204,7 @@ __device__ __forceinline__ uint32_t tile_allow(const WarpTile& w, const uint32_t
 // and half the shuffles per key).
 template <int D>
 __global__ void __launch_bounds__(kMaxWarps * 32, 2) win_fwd_kernel(gvk_attn_fwd_params p, Geo geo) {
+  const uint64_t seed_eff = salted_seed(p.seed, p.seed_salt);
   constexpr int S = Cfg<D>::S, KS = Cfg<D>::KS;
   extern __shared__ __align__(16) float smem[];
   float* Ks = smem;
@@ -261,7 +262,7 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 2) win_fwd_kernel(gvk_attn_fwd
     if (p.drop_p > 0.f) {
 #pragma unroll
       for (int u = 0; u < 2; ++u) {
-        const float4 d = block_drop(p, bh, (r0 >> 1) + g, ((j0 + 8 * u) >> 1) + t, inv_keep);
+        const float4 d = block_drop(p, seed_eff, bh, (r0 >> 1) + g, ((j0 + 8 * u) >> 1) + t, inv_keep);
         pr[u][0] *= d.x; pr[u][1] *= d.y; pr[u][2] *= d.z; pr[u][3] *= d.w;
       }
     }
@@ -281,6 +282,7 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 2) win_fwd_kernel(gvk_attn_fwd
 // dQ and delta = rowsum(O * dO): same tiling as the forward
 template <int D>
 __global__ void __launch_bounds__(kMaxWarps * 32, 2) win_dq_kernel(gvk_attn_bwd_params bp, Geo geo) {
+  const uint64_t seed_eff = salted_seed(bp.f.seed, bp.f.seed_salt);
   constexpr int S = Cfg<D>::S, KS = Cfg<D>::KS;
   const gvk_attn_fwd_params& p = bp.f;
   extern __shared__ __align__(16) float smem[];
@@ -343,7 +345,7 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 2) win_dq_kernel(gvk_attn_bwd_
 #pragma unroll
     for (int u = 0; u < 2; ++u) {
       if (p.drop_p > 0.f) {
-        const float4 d = block_drop(p, bh, (r0 >> 1) + g, ((j0 + 8 * u) >> 1) + t, inv_keep);
+        const float4 d = block_drop(p, seed_eff, bh, (r0 >> 1) + g, ((j0 + 8 * u) >> 1) + t, inv_keep);
         dp[u][0] *= d.x; dp[u][1] *= d.y; dp[u][2] *= d.z; dp[u][3] *= d.w;
       }
       float ds[4];
@@ -361,6 +363,7 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 2) win_dq_kernel(gvk_attn_bwd_
 // dK, dV: a warp owns 16 keys, the tiles run over the queries that see them (the transposed window is again a box); no atomics
 template <int D>
 __global__ void __launch_bounds__(kMaxWarps * 32, 2) win_dkv_kernel(gvk_attn_bwd_params bp, Geo geo) {
+  const uint64_t seed_eff = salted_seed(bp.f.seed, bp.f.seed_salt);
   constexpr int S = Cfg<D>::S, KS = Cfg<D>::KS;
   const gvk_attn_fwd_params& p = bp.f;
   extern __shared__ __align__(16) float smem[];
@@ -414,7 +417,7 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 2) win_dkv_kernel(gvk_attn_bwd
       float pd[4] = {al[u] & 1u ? fast_ex2(s[u][0] - ls.x) : 0.f, al[u] & 2u ? fast_ex2(s[u][1] - ls.y) : 0.f,
                      al[u] & 4u ? fast_ex2(s[u][2] - ls.x) : 0.f, al[u] & 8u ? fast_ex2(s[u][3] - ls.y) : 0.f};
       float4 d = make_float4(1.f, 1.f, 1.f, 1.f);
-      if (p.drop_p > 0.f) d = block_drop(p, bh, ((i0 + 8 * u) >> 1) + t, (r0 >> 1) + g, inv_keep);
+      if (p.drop_p > 0.f) d = block_drop(p, seed_eff, bh, ((i0 + 8 * u) >> 1) + t, (r0 >> 1) + g, inv_keep);
       // block_drop: x (even q, even k) y (even q, odd k) z (odd q, even k) w (odd q, odd k);  here element 0 = (key 2g, query 2t),
       // 1 = (key 2g, query 2t+1), 2 = (key 2g+1, query 2t), 3 = (key 2g+1, query 2t+1)
       const float mult[4] = {d.x, d.z, d.y, d.w};

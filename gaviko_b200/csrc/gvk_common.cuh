@@ -75,6 +75,8 @@ int clip_adam(float* param, const float* grad, float* m, float* v, size_t n, con
               float beta2, float eps, float wd, int step, float* norm_out, cudaStream_t stream);
 int patch_embed(const gvk_patch_embed_params* p, cudaStream_t stream);
 int patch_embed_supported(const gvk_patch_embed_params* p);
+int clip_adam_dyn(float* param, const float* grad, float* m, float* v, size_t n, const float* partials, float max_norm, float grad_scale, const float* lr_dev,
+                  float beta1, float beta2, float eps, float wd, const long long* step_dev, float* norm_out, cudaStream_t stream);
 int mhsa_fwd(const gvk_mhsa_fwd_params* p, cudaStream_t stream);
 int mhsa_bwd(const gvk_mhsa_bwd_params* p, cudaStream_t stream);
 int mhsa_ws_fwd(const gvk_mhsa_fwd_params* p, cudaStream_t stream);
@@ -358,6 +360,9 @@ __device__ __forceinline__ void mma_tf32(float (&d)[4], uint32_t a0, uint32_t a1
                : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
 }
 
+// Effective dropout seed: the by-value seed plus the device-resident replay counter (gvk.h, seed_salt).
+__device__ __forceinline__ uint64_t salted_seed(uint64_t seed, const uint64_t* salt) { return salt ? seed + *salt * 0x9E3779B97F4A7C15ull : seed; }
+
 // Philox4x32-10 (counter-based RNG for replayable dropout masks).
 __device__ __forceinline__ uint4 philox4x32(uint4 ctr, uint2 key) {
   const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
@@ -377,9 +382,18 @@ struct MhsaDrop {
   uint32_t thr4;     // the 8-bit keep threshold replicated into the four bytes
   uint2 key;
   float inv_keep;    // 256 / threshold
+  const uint64_t* salt;   // optional device-resident replay counter (gvk.h, seed_salt)
+  unsigned long long seed;
 };
-__host__ inline MhsaDrop make_mhsa_drop(float drop_p, unsigned long long seed) {
+__device__ __forceinline__ MhsaDrop mhsa_salted(MhsaDrop d) {      // once per thread, before the first mhsa_keep16
+  const uint64_t s = salted_seed(d.seed, d.salt);
+  d.key = make_uint2(static_cast<uint32_t>(s), static_cast<uint32_t>(s >> 32));
+  return d;
+}
+__host__ inline MhsaDrop make_mhsa_drop(float drop_p, unsigned long long seed, const uint64_t* salt = nullptr) {
   MhsaDrop d;
+  d.salt = salt;
+  d.seed = seed;
   int thr = static_cast<int>(256.0f * (1.0f - drop_p) + 0.5f);
   thr = thr < 1 ? 1 : (thr > 256 ? 256 : thr);
   d.thr4 = thr >= 256 ? 0u : static_cast<uint32_t>(thr) * 0x01010101u;   // 0: keep everything (drop_p rounds to 0)

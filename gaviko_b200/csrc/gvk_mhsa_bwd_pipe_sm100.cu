@@ -256,6 +256,7 @@ mhsa_bwd_dq_pipe_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __gri
     const float c2 = a.scale * kLog2e;
     const float2 c2v = make_float2(c2, c2);
     uint32_t g = 0, work = 0;
+    const MhsaDrop drop = kDrop ? mhsa_salted(a.drop) : a.drop;
     Tracer tr; tr.init(a.trace, 1 + grp, (a.dbg & 4) && (warp & 3) == 0 && lane == 0);
     // Per-item set-up (row statistics), software-pipelined one item ahead: the set-up of item n+1 runs in the shadow of item n's last dQ MMAs
     // (the groups would otherwise idle there), so block 0 of the next item starts right behind the epilogue.
@@ -325,7 +326,7 @@ mhsa_bwd_dq_pipe_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __gri
           uint32_t pk[16];
           uint32_t keep = 0xFFFFFFFFu;
           if (kDrop) {     // replay the forward's dropout decisions of these 32 keys and hand them to the dK/dV kernel
-            keep = mhsa_keep16(a.drop, bh, row, 8 * j + 4 * grp + 2 * c) | (mhsa_keep16(a.drop, bh, row, 8 * j + 4 * grp + 2 * c + 1) << 16);
+            keep = mhsa_keep16(drop, bh, row, 8 * j + 4 * grp + 2 * c) | (mhsa_keep16(drop, bh, row, 8 * j + 4 * grp + 2 * c + 1) << 16);
             a.mask[(((size_t)bh * nb + j) * a.Tpad + row) * 4 + 2 * grp + c] = keep;
           }
           const float2 ik = make_float2(a.drop.inv_keep, a.drop.inv_keep);
@@ -770,7 +771,7 @@ int mhsa_bwd_pipe(const gvk_mhsa_bwd_params* p, cudaStream_t stream) {
   const bool drop = p->drop_p > 0.f;
   GVK_CHECK_ARG(p->drop_p >= 0.f && p->drop_p < 1.f, "gvk_mhsa_bwd: drop_p must be in [0, 1)");
   GVK_CHECK_ARG(!drop || (p->mask_ws && (reinterpret_cast<uintptr_t>(p->mask_ws) & 15) == 0), "gvk_mhsa_bwd: dropout needs a 16-byte aligned mask workspace");
-  a.drop = make_mhsa_drop(p->drop_p, p->seed);
+  a.drop = make_mhsa_drop(p->drop_p, p->seed, p->seed_salt);
   a.mask = p->mask_ws;
   if (drop) {
     dq::mhsa_bwd_dq_pipe_kernel<true><<<grid, kThreads, dq::kSmem, stream>>>(tqkv, tdo, to, a);

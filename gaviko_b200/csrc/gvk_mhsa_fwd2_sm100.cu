@@ -205,6 +205,7 @@ mhsa_fwd2_kernel(const __grid_constant__ CUtensorMap tma_qkv, Args a) {
     const uint32_t tS = tmem + X * kTileCols + lane_off, tP = tS + kColP, tO = tS + kColO;
     const float c2 = a.scale * kLog2e;
     uint32_t g = 0;
+    const MhsaDrop drop = kDrop ? mhsa_salted(a.drop) : a.drop;
     Tracer tr; tr.init(a.trace, 1 + X, (a.dbg & 32) && (warp & 3) == 0 && lane == 0);
     const bool use_token = !(a.dbg & 64);
     if (use_token && X == 1) token_pass(1);      // group A holds the token first (barrier 1 + X = "group X may run its exponentials")
@@ -264,7 +265,7 @@ mhsa_fwd2_kernel(const __grid_constant__ CUtensorMap tma_qkv, Args a) {
           if (32 * c >= ncols) break;
           uint32_t pk[16];
           uint32_t keep = 0xFFFFFFFFu;          // dropout decisions of these 32 keys (the row sum l stays that of the un-dropped softmax)
-          if (kDrop) keep = mhsa_keep16(a.drop, bh, q0 + r, 8 * j + 2 * c) | (mhsa_keep16(a.drop, bh, q0 + r, 8 * j + 2 * c + 1) << 16);
+          if (kDrop) keep = mhsa_keep16(drop, bh, q0 + r, 8 * j + 2 * c) | (mhsa_keep16(drop, bh, q0 + r, 8 * j + 2 * c + 1) << 16);
 #pragma unroll
           for (int i = 0; i < 16; i += 2) {
             float2 pa = ffma2(make_float2(s[32 * c + 2 * i], s[32 * c + 2 * i + 1]), c2v, mcv);
@@ -363,7 +364,7 @@ int mhsa_fwd2(const gvk_mhsa_fwd_params* p, cudaStream_t stream) {
   a.lse = p->lse;
   a.pairs = (a.nb + 1) / 2;
   a.num_items = p->B * p->H * a.pairs;
-  a.drop = make_mhsa_drop(p->drop_p, p->seed);
+  a.drop = make_mhsa_drop(p->drop_p, p->seed, p->seed_salt);
   { const char* e = getenv("GVK_PIPE_DBG"); a.dbg = e ? atoi(e) : 0; }
   a.trace = (a.dbg & 32) ? trace_buffer() : nullptr;
   const int grid = std::min(a.num_items, sm_count());

@@ -201,6 +201,7 @@ mhsa_ws_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_const
     const uint32_t tO = tmem + kOCol + X * 64 + lane_off;   // O (fp32, 64 columns)
     const float c2 = a.scale * kLog2e;
     uint32_t g = 0;                           // score tiles consumed so far by this group
+    const MhsaDrop drop = kDrop ? mhsa_salted(a.drop) : a.drop;
     for (int item = blockIdx.x; item < a.num_items; item += gridDim.x) {
       const int bh = item / a.pairs, qp = item - bh * a.pairs;
       const int h = bh % a.H, b = bh / a.H;
@@ -252,7 +253,7 @@ mhsa_ws_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_const
         for (int c = 0; c < 2; ++c) {           // 32 scores -> 16 packed registers -> P columns 16c .. 16c+15 (over S columns already read)
           uint32_t pk[16];
           uint32_t keep = 0xFFFFFFFFu;          // dropout decisions of these 32 keys (the row sum l stays that of the un-dropped softmax)
-          if (kDrop) keep = mhsa_keep16(a.drop, bh, q0 + r, 4 * j + 2 * c) | (mhsa_keep16(a.drop, bh, q0 + r, 4 * j + 2 * c + 1) << 16);
+          if (kDrop) keep = mhsa_keep16(drop, bh, q0 + r, 4 * j + 2 * c) | (mhsa_keep16(drop, bh, q0 + r, 4 * j + 2 * c + 1) << 16);
 #pragma unroll
           for (int i = 0; i < 16; i += 2) {
             float2 pa = ffma2(make_float2(s[32 * c + 2 * i], s[32 * c + 2 * i + 1]), c2v, mcv);
@@ -356,7 +357,7 @@ int mhsa_ws_fwd(const gvk_mhsa_fwd_params* p, cudaStream_t stream) {
   a.mn_lbo = 8192; a.mn_sbo = 1024; a.mn_kadv = 2048;
   { const char* e = getenv("GVK_WS_DBG"); a.dbg = e ? atoi(e) : 0; }
   const int grid = std::min(a.num_items, sm_count());
-  a.drop = make_mhsa_drop(p->drop_p, p->seed);
+  a.drop = make_mhsa_drop(p->drop_p, p->seed, p->seed_salt);
   if (p->drop_p > 0.f)
     mhsa_ws_fwd_kernel<true><<<grid, kThreads, kFwdSmem, stream>>>(tq, tkv, a);
   else

@@ -169,6 +169,7 @@ static inline int row_block_grid(int M, int rows_per_warp) {
 // ------------------------------------------------------------------------------------------------
 template <int NITER>
 __global__ void __launch_bounds__(kRowThreads, 1) rowproj_down_kernel(gvk_rowproj_down_params p, int rpad) {
+  const uint64_t seed_eff = salted_seed(p.seed, p.seed_salt);
   extern __shared__ float smem[];
   constexpr int dim = NITER * 64;
   constexpr int ROWS = RowBlock<NITER>::ROWS, JCH = RowBlock<NITER>::JCH;
@@ -202,7 +203,7 @@ __global__ void __launch_bounds__(kRowThreads, 1) rowproj_down_kernel(gvk_rowpro
         const uint64_t e0 = p.offset + (uint64_t)min(row0 + q, p.M - 1) * dim + lane * 2;
 #pragma unroll
         for (int i = 0; i < NITER; ++i) {
-          const float2 m = drop_mult2(p.seed, e0 + 64 * i, p.drop_p, inv_keep);
+          const float2 m = drop_mult2(seed_eff, e0 + 64 * i, p.drop_p, inv_keep);
           xv[q][i].x *= m.x;
           xv[q][i].y *= m.y;
         }
@@ -322,6 +323,7 @@ int rowproj_down(const gvk_rowproj_down_params* p, cudaStream_t stream) {
 // ------------------------------------------------------------------------------------------------
 template <int NITER>
 __global__ void __launch_bounds__(kRowThreads, 1) rowproj_up_kernel(gvk_rowproj_up_params p) {
+  const uint64_t seed_eff = salted_seed(p.seed, p.seed_salt);
   extern __shared__ float smem[];
   constexpr int dim = NITER * 64;
   constexpr int ROWS = RowBlock<NITER>::ROWS;
@@ -380,7 +382,7 @@ __global__ void __launch_bounds__(kRowThreads, 1) rowproj_up_kernel(gvk_rowproj_
         const int c = lane * 2 + 64 * i;
         float2 v = acc[q][i];
         if (p.drop_p > 0.f) {
-          const float2 m = drop_mult2(p.seed, p.offset + (uint64_t)row * dim + c, p.drop_p, inv_keep);
+          const float2 m = drop_mult2(seed_eff, p.offset + (uint64_t)row * dim + c, p.drop_p, inv_keep);
           v.x *= m.x;
           v.y *= m.y;
           if (p.res) {
@@ -428,6 +430,7 @@ constexpr int kWgRows = 8;  // rows staged per step
 
 template <int R, int THREADS>
 __global__ void __launch_bounds__(THREADS, 2) skinny_wgrad_kernel(gvk_skinny_wgrad_params p, int rows_per_cta) {
+  const uint64_t seed_eff = salted_seed(p.seed, p.seed_salt);
   __shared__ __align__(16) float sa[kWgRows][R];
   __shared__ float smean[kWgRows], srstd[kWgRows];
   const int tid = threadIdx.x;
@@ -473,7 +476,7 @@ __global__ void __launch_bounds__(THREADS, 2) skinny_wgrad_kernel(gvk_skinny_wgr
       float x[4] = {xr[rr].x, xr[rr].y, xr[rr].z, xr[rr].w};
       if (p.drop_p > 0.f) {
         const uint64_t e = p.offset + (uint64_t)min(m0 + rr, m_end - 1) * p.dim + c0;
-        const float2 ma = drop_mult2(p.seed, e, p.drop_p, inv_keep), mb = drop_mult2(p.seed, e + 2, p.drop_p, inv_keep);
+        const float2 ma = drop_mult2(seed_eff, e, p.drop_p, inv_keep), mb = drop_mult2(seed_eff, e + 2, p.drop_p, inv_keep);
         x[0] *= ma.x; x[1] *= ma.y; x[2] *= mb.x; x[3] *= mb.y;
       }
       if (p.ln_gamma) {
@@ -1089,6 +1092,7 @@ int ssf_bwd(const gvk_ssf_bwd_params* p, cudaStream_t stream) {
 // elementwise dropout (+ residual)
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) dropout_kernel(gvk_dropout_params p) {
+  const uint64_t seed_eff = salted_seed(p.seed, p.seed_salt);
   const int n4 = p.N / 4;
   const size_t total = (size_t)p.M * n4;
   const float inv_keep = 1.0f / (1.0f - p.drop_p);
@@ -1098,7 +1102,7 @@ __global__ void __launch_bounds__(256) dropout_kernel(gvk_dropout_params p) {
 #pragma unroll
     for (int u = 0; u < 4; ++u) v[u] = ld_dyn(p.x, (size_t)m * p.ldx + c + u, p.x_dtype);
     const uint64_t e = p.offset + (uint64_t)m * p.N + c;
-    const float2 ma = drop_mult2(p.seed, e, p.drop_p, inv_keep), mb = drop_mult2(p.seed, e + 2, p.drop_p, inv_keep);
+    const float2 ma = drop_mult2(seed_eff, e, p.drop_p, inv_keep), mb = drop_mult2(seed_eff, e + 2, p.drop_p, inv_keep);
     v[0] *= ma.x; v[1] *= ma.y; v[2] *= mb.x; v[3] *= mb.y;
     if (p.res) {
 #pragma unroll

@@ -109,6 +109,7 @@ static inline int tc_grid(int tiles, int per_sm) { return std::max(1, std::min((
 // =================================================================================================
 template <int NITER, int NT>
 __global__ void __launch_bounds__(kTcThreads, NT <= 4 ? 2 : 1) tc_down_kernel(gvk_rowproj_down_params p) {
+  const uint64_t seed_eff = salted_seed(p.seed, p.seed_salt);
   constexpr int dim = NITER * 64, S = dim + 16, KG = dim / 16, RP = NT * 8;
   constexpr int S2 = 40;  // chained-projection panel row stride (floats): conflict-free float2 fragment loads for RP <= 32
   constexpr int U = (KG % 8 == 0) ? 8 : 4;   // 16-column groups loaded per batch (2 U float4 in flight per lane); KG % U == 0
@@ -170,8 +171,8 @@ __global__ void __launch_bounds__(kTcThreads, NT <= 4 ? 2 : 1) tc_down_kernel(gv
       for (int u = 0; u < U; ++u) {
         const int kk = k0 + u;
         if (p.drop_p > 0.f) {
-          const float4 ma = tc_drop4(p.seed, p.offset + cA * dim + 16 * kk + 4 * t, p.drop_p, inv_keep);
-          const float4 mb = tc_drop4(p.seed, p.offset + cB * dim + 16 * kk + 4 * t, p.drop_p, inv_keep);
+          const float4 ma = tc_drop4(seed_eff, p.offset + cA * dim + 16 * kk + 4 * t, p.drop_p, inv_keep);
+          const float4 mb = tc_drop4(seed_eff, p.offset + cB * dim + 16 * kk + 4 * t, p.drop_p, inv_keep);
           va[u].x *= ma.x; va[u].y *= ma.y; va[u].z *= ma.z; va[u].w *= ma.w;
           vb[u].x *= mb.x; vb[u].y *= mb.y; vb[u].z *= mb.z; vb[u].w *= mb.w;
         }
@@ -305,6 +306,7 @@ int rowproj_down_tc(const gvk_rowproj_down_params* p, cudaStream_t stream) {
 // =================================================================================================
 template <int NITER, int KS>
 __global__ void __launch_bounds__(kTcThreads, KS <= 4 ? 2 : 1) tc_up_kernel(gvk_rowproj_up_params p) {
+  const uint64_t seed_eff = salted_seed(p.seed, p.seed_salt);
   constexpr int dim = NITER * 64, S = dim + 8, KG = dim / 16, RP = KS * 8;
   constexpr int U = 4;
   static_assert(KG % U == 0, "column groups must tile the row");
@@ -354,8 +356,8 @@ __global__ void __launch_bounds__(kTcThreads, KS <= 4 ? 2 : 1) tc_up_kernel(gvk_
         float4 vA = make_float4(d0[0] + bias.x, d0[1] + bias.y, d1[0] + bias.z, d1[1] + bias.w);
         float4 vB = make_float4(d0[2] + bias.x, d0[3] + bias.y, d1[2] + bias.z, d1[3] + bias.w);
         if (p.drop_p > 0.f) {
-          const float4 ma = tc_drop4(p.seed, p.offset + cA * dim + col, p.drop_p, inv_keep);
-          const float4 mb = tc_drop4(p.seed, p.offset + cB * dim + col, p.drop_p, inv_keep);
+          const float4 ma = tc_drop4(seed_eff, p.offset + cA * dim + col, p.drop_p, inv_keep);
+          const float4 mb = tc_drop4(seed_eff, p.offset + cB * dim + col, p.drop_p, inv_keep);
           vA.x *= ma.x; vA.y *= ma.y; vA.z *= ma.z; vA.w *= ma.w;
           vB.x *= mb.x; vB.y *= mb.y; vB.z *= mb.z; vB.w *= mb.w;
         }
@@ -449,6 +451,7 @@ struct WgPipe {
 
 template <int NG>
 __global__ void __launch_bounds__(kTcThreads, 1) tc_wgrad_kernel(gvk_skinny_wgrad_params p, int rows_per_cta, int nwarps) {
+  const uint64_t seed_eff = salted_seed(p.seed, p.seed_salt);
   using L = WgPipe<NG>;
   extern __shared__ __align__(16) float wg_smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
@@ -571,8 +574,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_wgrad_kernel(gvk_skinny_wgra
         float y0[4] = {x0.x, x0.y, x0.z, x0.w}, y1[4] = {x1.x, x1.y, x1.z, x1.w};
         if (p.drop_p > 0.f) {
           const size_t c0 = (size_t)min(mb + l0, m_end - 1), c1 = (size_t)min(mb + l1, m_end - 1);
-          const float4 ma = tc_drop4(p.seed, p.offset + c0 * p.dim + col, p.drop_p, inv_keep);
-          const float4 mb4 = tc_drop4(p.seed, p.offset + c1 * p.dim + col, p.drop_p, inv_keep);
+          const float4 ma = tc_drop4(seed_eff, p.offset + c0 * p.dim + col, p.drop_p, inv_keep);
+          const float4 mb4 = tc_drop4(seed_eff, p.offset + c1 * p.dim + col, p.drop_p, inv_keep);
           y0[0] *= ma.x; y0[1] *= ma.y; y0[2] *= ma.z; y0[3] *= ma.w;
           y1[0] *= mb4.x; y1[1] *= mb4.y; y1[2] *= mb4.z; y1[3] *= mb4.w;
         }

@@ -28,6 +28,11 @@ def _ld(t):
 _Tensor, _Parameter = torch.Tensor, torch.nn.Parameter
 
 
+# Device-resident replay counter mixed into every dropout seed inside the kernels (gvk.h: seed_salt).  None in eager mode; gaviko_b200.graph sets it
+# to a 1-element int64 CUDA tensor so that a captured CUDA graph draws fresh masks on every replay.
+SEED_SALT = None
+
+
 def _set(p, **kw):
     """Fill a parameter struct; tensors become device addresses, None leaves the field zero.  (The class identity test first: isinstance() on
     torch.Tensor goes through a Python-level __instancecheck__ and was 9 of the 13 us this helper cost per call, x 564 calls per step.)"""
@@ -115,7 +120,7 @@ def rowproj_down(x, w, bias=None, *, transposed=False, ln=None, eps=1e-5, act=RO
     pre = torch.empty_like(z) if save_pre else None
     p = S['gvk_rowproj_down_params']()
     _set(p, x=L.ptr(x, torch.float32), ldx=_ld(x), M=M, dim=dim, r=r, w=L.ptr(w, torch.float32), w_sj=sj, w_sc=sc, bias=L.fptr(bias),
-         act=act, pre=pre, z=z, ldz=r, eps=eps, drop_p=drop_p, seed=seed, offset=offset, precision=prec)
+         act=act, pre=pre, z=z, ldz=r, eps=eps, drop_p=drop_p, seed=seed, offset=offset, seed_salt=SEED_SALT, precision=prec)
     mean = rstd = z2 = None
     if ln is not None:
         mean = torch.empty(M, device=x.device, dtype=torch.float32)
@@ -147,7 +152,7 @@ def rowproj_up(c, w, bias=None, *, transposed=False, res=None, out=None, out_lp=
         out = torch.empty((M, dim), device=c.device, dtype=torch.float32)
     p = S['gvk_rowproj_up_params']()
     _set(p, c=L.ptr(c, torch.float32), ldc=_ld(c), M=M, dim=dim, r=r, w=L.ptr(w, torch.float32), w_sj=sj, w_sc=sc, bias=L.fptr(bias),
-         out=L.ptr(out, torch.float32), ld_out=_ld(out), drop_p=drop_p, seed=seed, offset=offset, precision=prec)
+         out=L.ptr(out, torch.float32), ld_out=_ld(out), drop_p=drop_p, seed=seed, offset=offset, seed_salt=SEED_SALT, precision=prec)
     if res is not None:
         _set(p, res=L.ptr(res, torch.float32), ld_res=_ld(res))
     if out_lp is not None:
@@ -164,7 +169,7 @@ def skinny_wgrad(a, x, *, dw=None, dw_layout='rd', da_colsum=None, dx_colsum=Non
         prec = PREC_FP32
     p = S['gvk_skinny_wgrad_params']()
     _set(p, a=L.ptr(a, torch.float32), lda=_ld(a), r=r, x=L.ptr(x, torch.float32), ldx=_ld(x), dim=dim, M=M,
-         da_colsum=L.fptr(da_colsum), dx_colsum=L.fptr(dx_colsum), drop_p=drop_p, seed=seed, offset=offset, precision=prec)
+         da_colsum=L.fptr(da_colsum), dx_colsum=L.fptr(dx_colsum), drop_p=drop_p, seed=seed, offset=offset, seed_salt=SEED_SALT, precision=prec)
     if dw is not None and dw_strides is not None:      # explicit (sj, sc) element strides: a column / row slice of a larger gradient
         _set(p, dw=L.ptr(dw, torch.float32), dw_sj=dw_strides[0], dw_sc=dw_strides[1])
     elif dw is not None:
@@ -275,7 +280,7 @@ def dropout(x, drop_p, seed, *, res=None, out=None, out_dtype=None, offset=0):
     if out is None:
         out = torch.empty((M, N), device=x.device, dtype=out_dtype or x.dtype)
     p = S['gvk_dropout_params']()
-    _set(p, x=x, x_dtype=L.dtype_tag(x.dtype), ldx=_ld(x), out=out, out_dtype=L.dtype_tag(out.dtype), ld_out=_ld(out), M=M, N=N, drop_p=drop_p, seed=seed, offset=offset)
+    _set(p, x=x, x_dtype=L.dtype_tag(x.dtype), ldx=_ld(x), out=out, out_dtype=L.dtype_tag(out.dtype), ld_out=_ld(out), M=M, N=N, drop_p=drop_p, seed=seed, offset=offset, seed_salt=SEED_SALT)
     if res is not None:
         _set(p, res=L.ptr(res, torch.float32), ld_res=_ld(res))
     L.call('gvk_dropout', C.byref(p), L.stream())
@@ -286,7 +291,7 @@ def dropout(x, drop_p, seed, *, res=None, out=None, out_dtype=None, offset=0):
 def _attn_params(qkv, B, T, H, D, q_off, k_off, v_off, scale, window, grid, drop_p, seed, offset, out, lse, prec=PREC_FP32):
     f = S['gvk_attn_fwd_params']()
     _set(f, precision=PREC_FP32 if 'attn' in _TF32_OFF else prec, qkv=qkv, dtype=L.dtype_tag(qkv.dtype), ld=_ld(qkv), q_off=q_off, k_off=k_off, v_off=v_off, B=B, T=T, H=H, D=D, scale=scale,
-         drop_p=drop_p, seed=seed, offset=offset, out=out, ld_out=_ld(out), lse=L.fptr(lse))
+         drop_p=drop_p, seed=seed, offset=offset, seed_salt=SEED_SALT, out=out, ld_out=_ld(out), lse=L.fptr(lse))
     if window is not None:
         _set(f, win_d=window[0], win_h=window[1], win_w=window[2], grid_d=grid[0], grid_h=grid[1], grid_w=grid[2])
     return f
@@ -320,7 +325,7 @@ def mhsa_fwd(qkv, B, T, H, scale, drop_p=0.0, seed=0):
     out = torch.empty((B * T, H * 64), device=qkv.device, dtype=torch.bfloat16)
     lse = torch.empty(B * H * T, device=qkv.device, dtype=torch.float32)
     p = S['gvk_mhsa_fwd_params']()
-    _set(p, qkv=qkv, ld=_ld(qkv), B=B, T=T, H=H, scale=scale, out=out, ld_out=_ld(out), lse=lse, drop_p=float(drop_p), seed=int(seed) & 0xFFFFFFFFFFFFFFFF)
+    _set(p, qkv=qkv, ld=_ld(qkv), B=B, T=T, H=H, scale=scale, out=out, ld_out=_ld(out), lse=lse, drop_p=float(drop_p), seed=int(seed) & 0xFFFFFFFFFFFFFFFF, seed_salt=SEED_SALT)
     L.call('gvk_mhsa_fwd', C.byref(p), L.stream())
     return out, lse
 
@@ -339,7 +344,7 @@ def mhsa_bwd(qkv, out, lse, dout, B, T, H, scale, drop_p=0.0, seed=0):
         fm.restype = C.c_size_t
         mask = torch.empty(int(fm(B, T, H)), device=lse.device, dtype=torch.int32)
     _set(p, qkv=qkv, ld=_ld(qkv), B=B, T=T, H=H, scale=scale, out=out, ld_out=_ld(out), lse=lse, dout=dout, ld_dout=_ld(dout), delta=delta,
-         dqkv=dqkv, ld_dqkv=_ld(dqkv), drop_p=float(drop_p), seed=int(seed) & 0xFFFFFFFFFFFFFFFF, mask_ws=mask)
+         dqkv=dqkv, ld_dqkv=_ld(dqkv), drop_p=float(drop_p), seed=int(seed) & 0xFFFFFFFFFFFFFFFF, seed_salt=SEED_SALT, mask_ws=mask)
     L.call('gvk_mhsa_bwd', C.byref(p), L.stream())
     return dqkv
 

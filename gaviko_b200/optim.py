@@ -53,6 +53,9 @@ class FlatAdam(torch.optim.Optimizer):
             model._engine.grad_sink = {ids[id(p)]: p.grad for p in params if id(p) in ids}
         self.max_grad_norm = max_grad_norm
         self.step_count = 0
+        # CUDA-graph mode (gaviko_b200.graph): the step counter and the learning rate live in device memory so that one captured kernel node
+        # serves every replay.  None in eager mode.
+        self.dyn = None
         self.group = process_group
         self.world = world_size if world_size is not None else (torch.distributed.get_world_size(process_group) if torch.distributed.is_initialized() else 1)
         if self.world > 1:
@@ -113,6 +116,13 @@ class FlatAdam(torch.optim.Optimizer):
         self.step_count += 1
         st = L.stream()
         L.call('gvk_grad_sumsq', C.c_void_p(self.flat_g.data_ptr()), C.c_size_t(self.numel), C.c_float(scale), C.c_void_p(self.partials.data_ptr()), st)
+        if self.dyn is not None:
+            step_dev, lr_dev = self.dyn
+            L.call('gvk_clip_adam_dyn', C.c_void_p(self.flat_p.data_ptr()), C.c_void_p(self.flat_g.data_ptr()), C.c_void_p(self.exp_avg.data_ptr()),
+                   C.c_void_p(self.exp_avg_sq.data_ptr()), C.c_size_t(self.numel), C.c_void_p(self.partials.data_ptr()),
+                   C.c_float(self.max_grad_norm if self.max_grad_norm else 0.0), C.c_float(scale), C.c_void_p(lr_dev.data_ptr()), C.c_float(g['betas'][0]),
+                   C.c_float(g['betas'][1]), C.c_float(g['eps']), C.c_float(g['weight_decay']), C.c_void_p(step_dev.data_ptr()), C.c_void_p(self.grad_norm.data_ptr()), st)
+            return
         L.call('gvk_clip_adam', C.c_void_p(self.flat_p.data_ptr()), C.c_void_p(self.flat_g.data_ptr()), C.c_void_p(self.exp_avg.data_ptr()),
                C.c_void_p(self.exp_avg_sq.data_ptr()), C.c_size_t(self.numel), C.c_void_p(self.partials.data_ptr()),
                C.c_float(self.max_grad_norm if self.max_grad_norm else 0.0), C.c_float(scale), C.c_float(g['lr']), C.c_float(g['betas'][0]),

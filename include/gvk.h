@@ -98,6 +98,9 @@ int gvk_gemm(const gvk_gemm_params* p, gvk_stream_t stream);
  * projections (as far as the [r, dim] fp32 panel fits 227 KB of shared memory), r <= 32 for weight gradients and LayerNorm backward.
  * Strided weights: element (j, c) of a rank-r projection is w[j * w_sj + c * w_sc], so an nn.Linear(dim, r).weight
  * ([r, dim]) is (w_sj = dim, w_sc = 1) and an nn.Linear(r, dim).weight ([dim, r]) used transposed is (w_sj = 1, w_sc = r).
+ * seed_salt (optional, every struct with a seed): device pointer to a 64-bit counter mixed into the seed INSIDE the kernel
+ * (seed + *seed_salt * 0x9E3779B97F4A7C15), so that a CUDA graph that baked `seed` into its kernel nodes still draws fresh masks on every replay
+ * (the graph increments the counter, gaviko_b200/graph.py); forward and backward of one step must see the same counter value.
  * Dropout (replayable): element (m, c) of an [M, dim] tensor is kept iff philox(seed, offset + m * dim + c) >= drop_p and
  * scaled by 1 / (1 - drop_p).  `offset` must be a multiple of 4.
  * ------------------------------------------------------------------------------------------------------------------ */
@@ -132,7 +135,7 @@ typedef struct {
   const float* w; int w_sj, w_sc; const float* bias; int act;
   float* pre; float* z; int ldz;
   const float* w2; int r2; float* z2; int ldz2;
-  float drop_p; uint64_t seed; uint64_t offset;
+  float drop_p; uint64_t seed; uint64_t offset; const uint64_t* seed_salt;
   int precision;
 } gvk_rowproj_down_params;
 int gvk_rowproj_down(const gvk_rowproj_down_params* p, gvk_stream_t stream);
@@ -145,7 +148,7 @@ typedef struct {
   const float* w; int w_sj, w_sc; const float* bias;
   const float* res; int ld_res;
   float* out; int ld_out; void* out_lp; int ld_out_lp;
-  float drop_p; uint64_t seed; uint64_t offset;
+  float drop_p; uint64_t seed; uint64_t offset; const uint64_t* seed_salt;
   int precision;
 } gvk_rowproj_up_params;
 int gvk_rowproj_up(const gvk_rowproj_up_params* p, gvk_stream_t stream);
@@ -161,7 +164,7 @@ typedef struct {
   const float* ln_gamma; const float* ln_beta; const float* mean; const float* rstd;
   float* dw; int dw_sj, dw_sc;
   float* da_colsum; float* dx_colsum;
-  float drop_p; uint64_t seed; uint64_t offset;
+  float drop_p; uint64_t seed; uint64_t offset; const uint64_t* seed_salt;
   float* ws; size_t ws_floats;
   int precision;
 } gvk_skinny_wgrad_params;
@@ -220,7 +223,7 @@ int gvk_ssf_bwd(const gvk_ssf_bwd_params* p, gvk_stream_t stream);
  * (model/vision_transformer.py:33,35,58 and :157) and, applied to gradients with the same seed, for their backward. */
 typedef struct {
   const void* x; int x_dtype; int ldx; const float* res; int ld_res; void* out; int out_dtype; int ld_out;
-  int M, N; float drop_p; uint64_t seed; uint64_t offset;
+  int M, N; float drop_p; uint64_t seed; uint64_t offset; const uint64_t* seed_salt;
 } gvk_dropout_params;
 int gvk_dropout(const gvk_dropout_params* p, gvk_stream_t stream);
 
@@ -246,7 +249,7 @@ typedef struct {
   float scale;
   int win_d, win_h, win_w;      /* window extents; win_d == 0 selects dense attention */
   int grid_d, grid_h, grid_w;   /* token grid (T == grid_d*grid_h*grid_w when windowed) */
-  float drop_p; uint64_t seed; uint64_t offset;
+  float drop_p; uint64_t seed; uint64_t offset; const uint64_t* seed_salt;
   void* out; int ld_out;        /* [B*T, H*D], same dtype as qkv */
   float* lse;                   /* [B*H*T] log-sum-exp of the scaled scores (saved for backward) */
   int precision;                /* GVK_PREC_FP32 (exact, default) or GVK_PREC_TF32 (windowed case only) */
@@ -279,7 +282,7 @@ typedef struct {
   /* Attention-probability dropout (model/vision_transformer.py:50,69; active for --method melo / linear / bitfit in train mode): probability
    * (b, h, i, j) is kept iff byte (j % 16) of philox4x32-10(counter = (i, j / 16, b*H + h, 'mhsa'), key = seed) < round(256 (1 - drop_p)); the
    * kept ones are scaled by 256 / round(256 (1 - drop_p)).  lse stays that of the un-dropped softmax.  drop_p = 0: no dropout. */
-  float drop_p; uint64_t seed;
+  float drop_p; uint64_t seed; const uint64_t* seed_salt;
 } gvk_mhsa_fwd_params;
 int gvk_mhsa_fwd(const gvk_mhsa_fwd_params* p, gvk_stream_t stream);
 
@@ -293,7 +296,7 @@ typedef struct {
   float* delta;                    /* workspace of gvk_mhsa_bwd_ws_floats(B, T, H) floats (16-byte aligned): rowsum(dO*O) and the log2-domain lse handed
                                       from the dQ to the dK/dV kernel, rows padded to the 128-row blocks of the kernels */
   void* dqkv; int ld_dqkv;         /* [B*T, 3*H*64] bf16, fully overwritten */
-  float drop_p; uint64_t seed;     /* the forward call's dropout: the mask is regenerated (dQ kernel) and handed to the dK/dV kernel through mask_ws */
+  float drop_p; uint64_t seed; const uint64_t* seed_salt;     /* the forward call's dropout: the mask is regenerated (dQ kernel) and handed to the dK/dV kernel through mask_ws */
   uint32_t* mask_ws;               /* drop_p > 0: workspace of gvk_mhsa_bwd_mask_words(B, T, H) 32-bit words (16-byte aligned); else unused */
 } gvk_mhsa_bwd_params;
 int gvk_mhsa_bwd(const gvk_mhsa_bwd_params* p, gvk_stream_t stream);
@@ -500,6 +503,10 @@ enum { GVK_SUMSQ_PARTIALS = 128 };
 int gvk_grad_sumsq(const float* grad, size_t n, float grad_scale, float* partials, gvk_stream_t stream);
 int gvk_clip_adam(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, size_t n, const float* partials, float max_norm, float grad_scale,
                   float lr, float beta1, float beta2, float eps, float weight_decay, int step, float* grad_norm_out, gvk_stream_t stream);
+/* gvk_clip_adam with the learning rate (float) and the 1-based step (int64) read from DEVICE memory: the form a captured CUDA graph replays
+ * (gaviko_b200/graph.py), where both change between replays of the same kernel node. */
+int gvk_clip_adam_dyn(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, size_t n, const float* partials, float max_norm, float grad_scale,
+                      const float* lr_dev, float beta1, float beta2, float eps, float wd, const long long* step_dev, float* norm_out, gvk_stream_t stream);
 
 #ifdef __cplusplus
 }
