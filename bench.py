@@ -349,7 +349,7 @@ def run_ours(args):
         peak = pk['bf16_tflops_sustained'] if args.dtype == 'bf16' else 80.0
         traffic = None      # DRAM bytes per GEMM launch from the committed ncu capture of this configuration (profiles/), else null
         try:
-            tj = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'profiles', 'ncu_r01_gemm_traffic.json')))
+            tj = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'profiles', 'ncu_r02_gemm_traffic.json')))
             if (tj['batch'], tj['backbone'], tj['dtype']) == (B, args.backbone, args.dtype) and train:
                 traffic = tj['dram_bytes_per_launch']
         except Exception:  # noqa: BLE001
