@@ -90,7 +90,8 @@ class ClockSampler:
 # ----------------------------------------------------------------------------------------------------------------
 def cpu_reference_step_time(backbone, batch, steps, warmup, mode):
     """Times the reference algorithm (oracle restatement, fp32, torch CPU ops = what the reference itself dispatches to on CPU)
-    for `batch` synthetic volumes: forward + focal loss + backward over the trainable set.  Returns (seconds/step, threads)."""
+    for `batch` synthetic volumes: forward + focal loss + backward over the trainable set + clip_grad_norm_ + Adam (train.py:305-319; dropout off).
+    Returns (seconds/step, threads)."""
     from oracle import gaviko_oracle as O
     from oracle.golden_fill import golden_fill, golden_labels, golden_volume
     from tests_support import sd_for_backbone
@@ -101,14 +102,17 @@ def cpu_reference_step_time(backbone, batch, steps, warmup, mode):
         sd[n].requires_grad_(True)
     img = golden_volume(batch, 120, 160, 160)
     y = golden_labels(batch)
+    params = [sd[n] for n in trainable]
+    opt = torch.optim.Adam(params, lr=1e-4, eps=1e-8) if mode == 'train' else None
     times = []
     for it in range(warmup + steps):
         t0 = time.perf_counter()
         if mode == 'train':
-            for n in trainable:
-                sd[n].grad = None
+            opt.zero_grad(set_to_none=True)
             logits = O.gaviko_forward(sd, img, backbone=backbone, num_prompts=32, frame_patch_size=12, image_patch_size=16, local_k=[6, 6, 6], DHW=[10, 10, 10])
             O.focal_loss(logits, y).backward()
+            torch.nn.utils.clip_grad_norm_(params, 1.0)
+            opt.step()
         else:
             with torch.no_grad():
                 O.gaviko_forward(sd, img, backbone=backbone, num_prompts=32, frame_patch_size=12, image_patch_size=16, local_k=[6, 6, 6], DHW=[10, 10, 10])
@@ -169,7 +173,7 @@ def run_reference(args):
                 ms_per_step=sec * 1e3, higher_is_better=True, scaling='weak', vs_baseline=None, dtype='f32', data='synthetic',
                 config=workload(args, batch, 1, reference=True), gpu_launches=0,
                 cpu_baseline=dict(value=value, unit='volumes/s', cores=threads, kind='port',
-                                  sample=f'{args.steps} steps of batch {batch} (fwd+focal+bwd) of the same {args.backbone} GAViKO workload, fp32, torch CPU'),
+                                  sample=f'{args.steps} steps of batch {batch} (fwd + focal loss + bwd + clip + Adam, dropout off) of the same {args.backbone} GAViKO workload, fp32, torch CPU'),
                 e2e=dict(value=value, unit='volumes/s', h2d_bytes_per_step=0, d2h_bytes_per_step=0))
     print(json.dumps(line))
 
@@ -181,8 +185,8 @@ def metric_name(args):
 def workload(args, batch, world, reference=False):
     if args.mode != 'train':
         what = 'batched inference forward'
-    elif reference:       # the CPU arm times what the reference's loop does per step up to loss.backward() (train.py:305-311), dropout off, no clip / Adam
-        what = 'training step WITHOUT the optimiser (fwd + focal loss + frozen-backbone bwd; dropout off)'
+    elif reference:       # the CPU arm times what the reference's loop does per step (train.py:305-319), dropout off
+        what = 'training step (fwd + focal loss + frozen-backbone bwd + clip + Adam; dropout off)'
     else:
         what = 'training step (fwd + focal loss + frozen-backbone bwd + clip + Adam)'
     return dict(workload=f"GAViKO {args.backbone} {what}, "
