@@ -146,6 +146,7 @@ long long gvk_struct_size(const char* name) {
   GVK_SZ(gvk_fusion_weights) GVK_SZ(gvk_fusion_grads) GVK_SZ(gvk_fusion_saved) GVK_SZ(gvk_fusion_fwd_params)
   GVK_SZ(gvk_fusion_bwd_params) GVK_SZ(gvk_head_fwd_params) GVK_SZ(gvk_head_bwd_params) GVK_SZ(gvk_mhsa_fwd_params) GVK_SZ(gvk_mhsa_bwd_params) GVK_SZ(gvk_rescale_intensity_params)
   GVK_SZ(gvk_latent_xattn_fwd_params) GVK_SZ(gvk_latent_xattn_bwd_params) GVK_SZ(gvk_patch_embed_params)
+  GVK_SZ(gvk_wgrad_params) GVK_SZ(gvk_hfreq_filter_params)
 #undef GVK_SZ
   return -1;
 }
@@ -213,6 +214,8 @@ int gvk_clip_adam_dyn(float* param, const float* grad, float* exp_avg, float* ex
                       const float* lr_dev, float beta1, float beta2, float eps, float wd, const long long* step_dev, float* norm_out, gvk_stream_t stream) {
   return gvk::clip_adam_dyn(param, grad, exp_avg, exp_avg_sq, n, partials, max_norm, grad_scale, lr_dev, beta1, beta2, eps, wd, step_dev, norm_out, S(stream));
 }
+int gvk_wgrad(const gvk_wgrad_params* p, gvk_stream_t stream) { return gvk::wgrad(p, S(stream)); }
+int gvk_hfreq_filter(const gvk_hfreq_filter_params* p, gvk_stream_t stream) { return gvk::hfreq_filter(p, S(stream)); }
 int gvk_mhsa_fwd(const gvk_mhsa_fwd_params* p, gvk_stream_t stream) { return gvk::mhsa_fwd(p, S(stream)); }
 int gvk_mhsa_bwd(const gvk_mhsa_bwd_params* p, gvk_stream_t stream) { return gvk::mhsa_bwd(p, S(stream)); }
 size_t gvk_mhsa_bwd_ws_floats(int B, int T, int H) { return gvk::mhsa_bwd_ws_floats(B, T, H); }

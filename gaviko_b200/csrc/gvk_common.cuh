@@ -97,6 +97,8 @@ int latent_xattn_bwd(const gvk_latent_xattn_bwd_params* p, cudaStream_t stream);
 int gate_scale(const float* x, const float* gate, float* y, size_t n, cudaStream_t stream);
 int gate_grads(const float* x, const float* dy, const float* gate, float* dx, float* dgate, size_t n, cudaStream_t stream);
 int relu_bwd(const float* dy, const float* z, float* y, size_t n, cudaStream_t stream);
+int wgrad(const gvk_wgrad_params* p, cudaStream_t stream);
+int hfreq_filter(const gvk_hfreq_filter_params* p, cudaStream_t stream);
 int head_fwd(const gvk_head_fwd_params* p, cudaStream_t stream);
 int head_bwd(const gvk_head_bwd_params* p, cudaStream_t stream);
 int loss_fwd_bwd(const float* logits, const long long* target, int B, int C, int kind, float gamma, float eps, long long ignore_index, float* loss, float* dlogits,

@@ -401,6 +401,41 @@ def patch_embed(img, fp, ps, weight, bias, pos, out, out_batch_rows, out_row_off
     return True
 
 
+# ---------------------------------------------------------------------------------------------- EVP primitives (csrc/gvk_evp.cu)
+def wgrad(a, b, dw, *, M=None, a_rows=None, b_rows=None, prec=PREC_FP32):
+    """dw[i, j] += sum_m a[row_a(m), i] * b[row_b(m), j]  (gvk_wgrad).  a_rows / b_rows = (rows_per_batch, batch_rows) row maps (None:
+    identity); M = logical row count (default: a.shape[0]).  a, b: fp32 or bf16 row-major; dw: fp32 row-major view (accumulated into)."""
+    if dw.dtype != torch.float32 or tuple(dw.shape) != (a.shape[1], b.shape[1]):
+        raise GvkError(f'wgrad: dw must be fp32 {(a.shape[1], b.shape[1])}, got {dw.dtype} {tuple(dw.shape)}')
+    ar, br = a_rows or (0, 0), b_rows or (0, 0)
+    p = S['gvk_wgrad_params']()
+    _set(p, a=a, a_dtype=L.dtype_tag(a.dtype), lda=_ld(a), na=a.shape[1], a_rows_per_batch=ar[0], a_batch_rows=ar[1],
+         b=b, b_dtype=L.dtype_tag(b.dtype), ldb=_ld(b), nb=b.shape[1], b_rows_per_batch=br[0], b_batch_rows=br[1],
+         M=a.shape[0] if M is None else M, dw=dw, ld_dw=_ld(dw), precision=PREC_FP32 if 'wgrad' in _TF32_OFF else prec)
+    L.call('gvk_wgrad', C.byref(p), L.stream())
+    return dw
+
+
+def hfreq_filter(img, filt, hit):
+    """| filt @ slice | on the depth slices with hit[d] != 0, | slice | elsewhere (gvk_hfreq_filter; reference model/evp.py:124-146)."""
+    B, Cc, D, H, W = img.shape
+    if img.dtype != torch.float32 or not img.is_contiguous():
+        raise GvkError('hfreq_filter: expected a contiguous fp32 (B, C, D, H, W) volume')
+    if tuple(filt.shape) != (H, H) or not filt.is_contiguous() or hit.dtype != torch.uint8 or hit.numel() != D:
+        raise GvkError('hfreq_filter: filt must be a contiguous fp32 [H, H] matrix and hit a uint8 [D] vector')
+    out = torch.empty_like(img)
+    p = S['gvk_hfreq_filter_params']()
+    n = B * Cc * D
+    step = 65535 // D * D      # slices per launch (grid.z limit), a whole number of depth stacks
+    xi, xo = img.view(n, H, W), out.view(n, H, W)
+    for s0 in range(0, n, step):
+        s1 = min(n, s0 + step)
+        _set(p, out=xo[s0:s1], filt=L.fptr(filt), hit=L.ptr(hit), slices=s1 - s0, D=D, H=H, W=W)
+        setattr(p, 'in', L.ptr(xi[s0:s1]))
+        L.call('gvk_hfreq_filter', C.byref(p), L.stream())
+    return out
+
+
 def fill_rows(a, b, out, out_batch_rows, out_row_offset, B):
     R, dim = a.shape
     L.call('gvk_fill_rows', C.c_void_p(L.fptr(a)), C.c_void_p(L.fptr(b)) if b is not None else None, R, dim, C.c_void_p(L.ptr(out, torch.float32)), _ld(out),

@@ -8,6 +8,9 @@ ssf | shallow_vpt | deep_vpt`` of the reference (``src/train.py:111-153``).  All
 * vpt         — prompt tokens inserted after cls, once (shallow) or re-inserted at every layer with the reference's
                 ``1 + prompt_dim`` slice (``src/model/vpt.py:124-161``), so the sequence length changes per layer;
 * linear / bitfit — freeze rules only (``src/train.py:114-137``); bitfit needs the column sums of dY at every bias.
+* evp         — ``x[:, 1:] += shared_mlp(GELU(lightweight_mlp_i(handcrafted + embedding)))`` before every block, where ``embedding`` is a
+                Linear of the raw patch embedding and ``handcrafted`` a second patch embedding of the high-passed volume
+                (``src/model/evp.py:70-95,124-146,208-217``); its rank dim / scale_factor needs general weight-gradient products (``ops.wgrad``).
 
 Backward follows the freeze rule: dX through the frozen GEMMs / attention only as far as a trainable tensor needs it, dW only
 for tensors with ``requires_grad``.  Same two compute modes as ``engine.GavikoEngine`` ('fp32' exact, 'bf16' tensor cores).
@@ -30,7 +33,7 @@ def _p(mod):
 
 
 class VitEngine:
-    """kind: 'vit' (VisionTransformer: linear / bitfit / wrapped by MeLO), 'adaptformer', 'ssf', 'vpt'."""
+    """kind: 'vit' (VisionTransformer: linear / bitfit / wrapped by MeLO), 'adaptformer', 'ssf', 'vpt', 'evp'."""
 
     def __init__(self, module, kind, compute_dtype=None):
         self.__dict__['_module_ref'] = module
@@ -97,6 +100,8 @@ class VitEngine:
         for Lw in W['layers']:
             add(list(Lw['n'].values()))
         ok.update(('prompt_proj.weight', 'prompt_proj.bias', 'deep_prompt_embeddings', 'prompt_embeddings'))
+        if self.kind == 'evp':
+            ok.update(n for n in names if n.startswith('prompt_generator.'))
         bad = [n for n in names if n not in ok]
         if bad:
             raise NotImplementedError('gaviko_b200 implements the frozen-backbone backward of the PEFT methods (linear, bitfit, adaptformer, melo, ssf, '
@@ -129,14 +134,15 @@ class VitEngine:
         def vec(key, src):
             return None if src is None else cache.get((key, 'v'), src, lambda t: t.float().contiguous())
 
-        W = dict(conv_w=mat('conv_w', vt.conv_proj[0].weight), conv_b=vec('conv_b', vt.conv_proj[0].bias),
+        conv = vt.conv_proj.proj if self.kind == 'evp' else vt.conv_proj[0]
+        W = dict(conv_w=mat('conv_w', conv.weight), conv_b=vec('conv_b', conv.bias),
                  pos_patch=cache.get(('pos_patch',), vt.pos_embedding, lambda t: t[0, 1:].float().contiguous()),
                  pos_cls=cache.get(('pos_cls',), vt.pos_embedding, lambda t: t[0, :1].float().contiguous()),
                  cls=cache.get(('cls',), vt.cls_token, lambda t: t.reshape(1, dim).float().contiguous()),
                  norm_w=vec('norm_w', vt.transformer.norm.weight), norm_b=vec('norm_b', vt.transformer.norm.bias),
                  head_w=vec('head_w', vt.mlp_head.weight), head_b=vec('head_b', vt.mlp_head.bias), layers=[], names={})
         nm = W['names']
-        nm['conv_b'] = prefix + 'conv_proj.0.bias'
+        nm['conv_b'] = prefix + ('conv_proj.proj.bias' if self.kind == 'evp' else 'conv_proj.0.bias')
         nm['norm_b'] = prefix + 'transformer.norm.bias'
         nm['head_w'], nm['head_b'] = prefix + 'mlp_head.weight', prefix + 'mlp_head.bias'
         ssf = self.kind == 'ssf'
@@ -240,9 +246,14 @@ class VitEngine:
         sp = W.get('ssf_patch', (None, None))
         ops.gemm(patches, W['conv_w'], bias=W['conv_b'], ssf_scale=sp[0], ssf_shift=sp[1], pos=W['pos_patch'], rows_per_batch=N, out_batch_rows=T,
                  out_row_offset=1, out=x)
+        evp = self.kind == 'evp'
+        if evp:
+            ev = self._evp_setup(img, patches, W, cdt, B, N, T)
         del patches
         ops.fill_rows(W['cls'], W['pos_cls'], x, T, 0, B)
         ctx = dict(B=B, N=N, W=W, cdt=cdt, layers=[], x0=x if save else None, emb_drop=(_p(vt.dropout), self._seed(0, 9)))
+        if evp and save:
+            ctx['evp'] = ev
         if ctx['emb_drop'][0] > 0:
             x = ops.dropout(x, ctx['emb_drop'][0], ctx['emb_drop'][1])
         vpt = self.kind == 'vpt'
@@ -250,6 +261,15 @@ class VitEngine:
         for i in range(c['depth']):
             Lw = W['layers'][i]
             st = dict(T_in=T)
+            if evp:
+                # prompt_i = shared_mlp(GELU(lightweight_mlp_i(f))) added to the patch rows (model/evp.py:85-95,210-214).  All B*T rows go through
+                # the two GEMMs; the cls rows of h are zeroed so that they add nothing (and drop out of the shared_mlp weight gradient)
+                E = ev['E']
+                pre = torch.empty((B * T, E['rp']), device=img.device, dtype=cdt) if save else None
+                h = ops.gemm(ev['f'], E['wi'][i], bias=E['bi'][i], act=ops.ACT_GELU, aux=pre, out_dtype=cdt)
+                h.view(B, T, -1)[:, 0].zero_()            # B rows: plumbing
+                x = ops.gemm(h, E['ws'], pos=E['posb'], rows_per_batch=T, out_batch_rows=T, out_row_offset=0, res1=x)
+                st.update(evp_h=h, evp_pre=pre)
             if vpt and (i == 0 or m.deep_prompt):
                 # [cls ; P prompts ; rest]: at layers >= 1 the reference drops rows 1 .. prompt_dim (NOT 1 .. P), model/vpt.py:151-153
                 pr_tok, E = self._prompts(i)
@@ -472,9 +492,13 @@ class VitEngine:
                 dX = torch.cat([d3[:, :1], torch.zeros((B, min(skip, T_in - 1), dim), device=dev, dtype=torch.float32), d3[:, 1 + P:]], 1).reshape(-1, dim)   # (a depleted sequence has fewer than `skip` rows to drop)
                 assert dX.shape[0] == B * T_in
                 dX_lp = ops.cast_bf16(dX) if lp else None
+            if 'evp' in ctx:
+                self._evp_layer_bwd(i, ctx, st, dX, dX_lp, pr)
             ctx['layers'][i] = None
             if not self._needs_below(i, names, nm):
                 return G
+        if 'evp' in ctx:
+            self._evp_finish_bwd(ctx, G, want, pr)
         # ---- below layer 0: patch-embedding SSF site and the conv bias (bitfit)
         T0 = N + 1
         p_emb, seed_emb = ctx['emb_drop']
@@ -499,9 +523,123 @@ class VitEngine:
         below = [f'{prefix}transformer.layers.{k}.' for k in range(i)]
         for n in names:
             if any(n.startswith(b) for b in below) or n in (nm['conv_b'],) or n in nm.get('ssf_patch', ()) or \
-                    n.startswith('prompt_proj') or n.endswith('prompt_embeddings'):
+                    n.startswith('prompt_proj') or n.endswith('prompt_embeddings') or n.startswith('prompt_generator.'):
                 return True
         return False
+
+    # ------------------------------------------------------------------------------------------ EVP (model/evp.py)
+    def _evp_filter(self, img):
+        """PromptGenerator.fft (reference model/evp.py:124-146) in closed form, for a 5-D (B, C, D, H, W) volume.  ``fft2`` transforms the last
+        two axes; ``fftshift`` / ``ifftshift`` without ``dim`` roll EVERY axis; ``mask[:, :, w//2-line:w//2+line, h//2-line:h//2+line] = 1`` with
+        ``w, h = x.shape[-2:]`` hits axes 2 and 3 of the 5-D mask, i.e. DEPTH and HEIGHT, in shifted coordinates.  Un-shifted: on the depth
+        slices d with (d + D//2) % D inside the first range, the H-frequencies k with (k + H//2) % H inside the second range are removed
+        (every W-frequency is kept); other slices pass.  Removing a band along H, then ``.real``, is the real matrix
+        F = I - (1/H) sum_{k cut} cos(2 pi k (n - m) / H) applied along H; ``abs`` follows.  Returns (F [H, H] fp32, hit [D] uint8) on the device."""
+        import math
+        _, _, D, H, Wd = img.shape
+        rate = float(self.module.prompt_generator.freq_nums)
+        key = ('evp_filter', D, H, Wd, rate, str(img.device))
+        hit_f = getattr(self, '_evp_filter_cache', {}).get(key)
+        if hit_f is None:
+            w, h = H, Wd                                     # the names of evp.py:128
+            line = int((w * h * rate) ** .5 // 2)
+            d_s = torch.zeros(D, dtype=torch.bool)
+            d_s[w // 2 - line:w // 2 + line] = True          # the reference's own slice expressions, python slice semantics per axis
+            k_s = torch.zeros(H, dtype=torch.bool)
+            k_s[h // 2 - line:h // 2 + line] = True
+            d_un = torch.zeros(D, dtype=torch.bool)
+            d_un[(torch.arange(D) - D // 2) % D] = d_s       # fftshift moves index i to (i + n // 2) % n
+            k_un = torch.zeros(H, dtype=torch.bool)
+            k_un[(torch.arange(H) - H // 2) % H] = k_s
+            n = torch.arange(H, dtype=torch.float64)
+            k = n[k_un]
+            Fm = torch.eye(H, dtype=torch.float64) - torch.cos(2 * math.pi * (n[:, None, None] - n[None, :, None]) * k[None, None, :] / H).sum(-1) / H
+            hit_f = (Fm.float().contiguous().to(img.device), d_un.to(torch.uint8).to(img.device))
+            self.__dict__.setdefault('_evp_filter_cache', {})[key] = hit_f
+        return hit_f
+
+    def _evp_weights(self, cdt, T):
+        """The prompt generator's tensors as GEMM operands: zero-padded to a latent width that is a multiple of 64 (the GEMM's K granularity),
+        in compute dtype, plus the transposes the dgrad GEMMs read.  Trainable, so rebuilt every step (a few small casts: plumbing)."""
+        m, c = self.module, self.module._cfg
+        pg = m.prompt_generator
+        r, dim, depth = c['evp_rank'], c['dim'], c['depth']
+        rp = (r + 63) // 64 * 64
+        dev = m.pos_embedding.device
+
+        def padw(w, rows, cols):
+            out = torch.zeros((rows, cols), device=dev, dtype=cdt)
+            out[:w.shape[0], :w.shape[1]] = w.detach()
+            return out
+
+        def padv(v, n):
+            out = torch.zeros(n, device=dev, dtype=torch.float32)
+            out[:v.shape[0]] = v.detach()
+            return out
+
+        conv = pg.prompt_generator.proj
+        lins = [getattr(pg, f'lightweight_mlp_{i}')[0] for i in range(depth)]
+        ws = pg.shared_mlp.weight
+        posb = ws.new_zeros((T, dim), dtype=torch.float32)
+        posb[1:] = pg.shared_mlp.bias.detach().float()         # shared_mlp bias on the patch rows only (row 0 = cls)
+        return dict(r=r, rp=rp, we=padw(pg.embedding_generator.weight, rp, dim), be=padv(pg.embedding_generator.bias, rp),
+                    wc=padw(conv.weight.reshape(r, -1), rp, conv.weight[0].numel()), bc=padv(conv.bias, rp),
+                    ws=padw(ws, dim, rp), ws_t=padw(ws.t(), rp, dim), posb=posb,
+                    wi=[padw(l.weight, rp, rp) for l in lins], wi_t=[padw(l.weight.t(), rp, rp) for l in lins], bi=[padv(l.bias, rp) for l in lins])
+
+    def _evp_setup(self, img, patches, W, cdt, B, N, T):
+        """f = handcrafted + embedding (model/evp.py:70-79,346-351) as a [B*T, rp] matrix whose cls rows are zero."""
+        c = self.module._cfg
+        E = self._evp_weights(cdt, T)
+        xraw = ops.gemm(patches, W['conv_w'], bias=W['conv_b'], out_dtype=cdt)              # conv_proj(img): no cls row, no positional embedding
+        filt, hit = self._evp_filter(img)
+        patches_hp = ops.patch_gather(ops.hfreq_filter(img, filt, hit), c['fp'], c['ps'], cdt)
+        hc = ops.gemm(patches_hp, E['wc'], bias=E['bc'])                                   # second patch embedding (prompt_generator.proj), fp32
+        f = torch.zeros((B * T, E['rp']), device=img.device, dtype=cdt)
+        ops.gemm(xraw, E['we'], bias=E['be'], res1=hc, rows_per_batch=N, out_batch_rows=T, out_row_offset=1, out=f)
+        return dict(E=E, xraw=xraw, patches_hp=patches_hp, f=f)
+
+    def _evp_layer_bwd(self, i, ctx, st, dX, dX_lp, pr):
+        """dX = gradient at the input of block i = gradient of prompt_i on the patch rows: shared_mlp / lightweight_mlp_i weight gradients and the
+        running gradient of f.  Every product runs over all B*T rows: h and f have zero cls rows, bias sums skip the cls rows by row map."""
+        ev = ctx['evp']
+        E, B, N = ev['E'], ctx['B'], ctx['N']
+        T = N + 1
+        dev = dX.device
+        if 'acc' not in ev:
+            rp, dim = E['rp'], dX.shape[1]
+            z = lambda *s: torch.zeros(s, device=dev, dtype=torch.float32)   # noqa: E731
+            ev['acc'] = dict(ws=z(dim, rp), bs=z(dim), wi=[z(rp, rp) for _ in E['wi']], bi=[z(rp) for _ in E['wi']], we=z(rp, dim), bf=z(rp),
+                             wc=z(rp, E['wc'].shape[1]))
+        acc = ev['acc']
+        dP = dX_lp if dX_lp is not None else dX
+        ops.wgrad(dP, st['evp_h'], acc['ws'], prec=pr)
+        ops.ssf_bwd(dX[1:], dshift=acc['bs'], rows_per_batch=N, batch_rows=T, M=B * N)
+        dpre = ops.gemm(dP, E['ws_t'], act=ops.ACT_GELU_BWD, aux=st['evp_pre'], out_dtype=ctx['cdt'])
+        ops.wgrad(dpre, ev['f'], acc['wi'][i], prec=pr)
+        ops.ssf_bwd(dpre[1:], dshift=acc['bi'][i], rows_per_batch=N, batch_rows=T, M=B * N)
+        ev['df'] = ops.gemm(dpre, E['wi_t'][i], res1=ev.get('df'))      # fp32 [B*T, rp], summed over the layers
+
+    def _evp_finish_bwd(self, ctx, G, want, pr):
+        """d f feeds both feature generators (model/evp.py:70-79): embedding_generator (input: the raw patch embedding) and the handcrafted
+        Conv3d (input: the patches of the high-passed volume).  Then the padded accumulators are cut to the parameter shapes."""
+        ev = ctx['evp']
+        E, acc, B, N = ev['E'], ev['acc'], ctx['B'], ctx['N']
+        T, r = N + 1, ev['E']['r']
+        df1 = ev['df'][1:]                                   # logical row m -> physical row (m // N) * T + m % N: the cls rows are skipped
+        ops.ssf_bwd(df1, dshift=acc['bf'], rows_per_batch=N, batch_rows=T, M=B * N)
+        ops.wgrad(df1, ev['xraw'], acc['we'], M=B * N, a_rows=(N, T), prec=pr)
+        ops.wgrad(df1, ev['patches_hp'], acc['wc'], M=B * N, a_rows=(N, T), prec=pr)
+        pg = 'prompt_generator.'
+        out = {pg + 'shared_mlp.weight': acc['ws'][:, :r], pg + 'shared_mlp.bias': acc['bs'],
+               pg + 'embedding_generator.weight': acc['we'][:r], pg + 'embedding_generator.bias': acc['bf'][:r],
+               pg + 'prompt_generator.proj.weight': acc['wc'][:r], pg + 'prompt_generator.proj.bias': acc['bf'][:r]}
+        for i in range(len(acc['wi'])):
+            out[f'{pg}lightweight_mlp_{i}.0.weight'] = acc['wi'][i][:r, :r]
+            out[f'{pg}lightweight_mlp_{i}.0.bias'] = acc['bi'][i][:r]
+        for n, v in out.items():
+            if n in want:
+                G[n].copy_(v.reshape(G[n].shape))              # slice of a padded accumulator -> parameter shape: plumbing
 
     def _adapter_bwd(self, ad, n_, st, dX, dXm, g, pr):
         """x_out = ... + up(ReLU(down(LN_a(x_mid)))): gradients of the six adapter tensors and the contribution to d x_mid

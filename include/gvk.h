@@ -483,6 +483,39 @@ typedef struct {
 int gvk_head_bwd(const gvk_head_bwd_params* p, gvk_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------------------------
+ * --method evp (reference src/model/evp.py): the two primitives beyond the frozen-ViT kernel set.
+ *
+ * gvk_wgrad: general weight gradient   dw[i, j] += sum_{m < M} a[row_a(m), i] * b[row_b(m), j]      (i < na, j < nb; dw fp32, ACCUMULATES)
+ *   row_x(m) = (m / x_rows_per_batch) * x_batch_rows + m % x_rows_per_batch   (x_rows_per_batch == 0: identity) — lets an operand skip the
+ *   cls row of every volume without a copy.  a / b are fp32 or bf16, row-major, na / nb / lda / ldb multiples of 4.
+ *   precision GVK_PREC_TF32: mma.sync tf32 tensor-core tiles;  GVK_PREC_FP32: exact FFMAs.  Rows are split over CTAs and combined with
+ *   fp32 atomics (run-to-run differences at the last bit).  Replaces autograd's weight gradients of PromptGenerator.shared_mlp,
+ *   embedding_generator, lightweight_mlp_i and prompt_generator.proj (model/evp.py:42-52), whose rank dim / scale_factor (192 at ViT-B
+ *   with configs/evp.yaml) is past the r <= 32 limit of gvk_skinny_wgrad.
+ *
+ * gvk_hfreq_filter: PromptGenerator.fft (model/evp.py:124-146) in closed form.  For a (B, C, D, H, W) volume the reference's
+ *   fft2 (last two axes) + all-axes fftshift + mask[:, :, a:b, c:d] = 1 (axes D and H!) + inverse + real + abs equals: on the depth slices
+ *   with hit[d] != 0, out = | filt @ slice |  (filt = I - Re(IDFT diag(cut) DFT), an H x H symmetric real matrix acting along H);
+ *   on the others out = | slice |.  in / out: fp32 [slices = B*C*D, H, W]; filt fp32 [H, H]; hit uint8 [D].  Exact fp32 FMAs.
+ * ------------------------------------------------------------------------------------------------------------------ */
+typedef struct {
+  const void* a; int a_dtype; int lda; int na; int a_rows_per_batch, a_batch_rows;
+  const void* b; int b_dtype; int ldb; int nb; int b_rows_per_batch, b_batch_rows;
+  int M;
+  float* dw; int ld_dw;
+  int precision;
+} gvk_wgrad_params;
+int gvk_wgrad(const gvk_wgrad_params* p, gvk_stream_t stream);
+
+typedef struct {
+  const float* in; float* out;
+  const float* filt;
+  const unsigned char* hit;
+  int slices, D, H, W;
+} gvk_hfreq_filter_params;
+int gvk_hfreq_filter(const gvk_hfreq_filter_params* p, gvk_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
  * Losses on [B, C] fp32 logits, int64 targets.  loss is a device scalar; dlogits (optional) is d loss / d logits.
  * kind 0: the reference's FocalLoss (losses/focal_loss.py:84-111: clamp(logits) -> softmax -> clamp -> softmax, eps 1e-16,
  *         ignore_index, mean over non-ignored);  kind 1: nn.CrossEntropyLoss (mean).

@@ -42,10 +42,15 @@ VARIANT_CASES = {
                                             freeze_vit=True, prompt_dropout=0.0, prompt_dim=6, num_prompts=4, deep_prompt=True), 2),
 }
 
-# SURVEY.md §8 (f) "next" methods: oracle + goldens exist, the CUDA path does not yet (tests/test_oracle_golden.py covers the oracle only)
+# SURVEY.md §8 (f) "next" methods (f3 dvpt, f4 evp)
 NEXT_CASES = {
     'dvpt_t16_small': ('dvpt', dict(SMALL, num_classes=5, channels=1, pool='mean', backbone='vit-t16', dropout=0.0, emb_dropout=0.0,
                                     num_prompts=4, freeze_vit=True), 2),
     'dvpt_cls_t16_small': ('dvpt', dict(SMALL, num_classes=5, channels=1, pool='cls', backbone='vit-t16', dropout=0.0, emb_dropout=0.0,
                                         num_prompts=6, freeze_vit=True), 2),
+    # f4: EVP (model/evp.py).  scale_factor 4 is what configs/evp.yaml ships (latent width dim / 4), 32 is the constructor default
+    'evp_t16_small': ('evp', dict(SMALL, num_classes=5, channels=1, pool='cls', backbone='vit-t16', dropout=0.0, emb_dropout=0.0,
+                                  freeze_vit=True, scale_factor=4, input_type='fft', freq_nums=0.25, handcrafted_tune=True, embedding_tune=True), 2),
+    'evp_mean_t16_small': ('evp', dict(SMALL, num_classes=5, channels=1, pool='mean', backbone='vit-t16', dropout=0.0, emb_dropout=0.0,
+                                       freeze_vit=True, scale_factor=32, input_type='fft', freq_nums=0.25), 3),
 }

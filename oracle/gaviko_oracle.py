@@ -336,3 +336,86 @@ def dvpt_forward(sd, img, *, backbone, frame_patch_size, image_patch_size, num_p
     else:
         y = layer_norm(x[:, :P + 1], sd['transformer.norm.weight'], sd['transformer.norm.bias']).mean(dim=1)
     return y @ sd['mlp_head.weight'].t() + sd['mlp_head.bias']
+
+
+# ----------------------------------------------------------------------------------------------
+# EVP: model/evp.py
+# ----------------------------------------------------------------------------------------------
+
+def evp_filter_plan(shape, rate):
+    """What model/evp.py:124-146 (``PromptGenerator.fft``) does to a 5-D volume (B, C, D, H, W), written out:
+
+    * ``fft2`` transforms the LAST TWO axes (H, W); ``fftshift`` / ``ifftshift`` without ``dim`` roll EVERY axis, batch included;
+    * ``mask[:, :, w//2-line:w//2+line, h//2-line:h//2+line] = 1`` with ``w, h = x.shape[-2:]`` indexes axes 2 and 3 of the 5-D mask,
+      i.e. DEPTH and HEIGHT (all of W), in shifted coordinates; ``line = int((w*h*rate) ** .5 // 2)``.
+
+    In un-shifted coordinates the spectrum of slice d keeps every W frequency and loses the H frequencies kh with
+    (kh + H//2) % H inside [H//2-line, H//2+line) — but only for the depth slices with (d + D//2) % D inside [W//2-line, W//2+line)
+    (clipped to the axis); the other slices pass unchanged.  Returns (depth_hit [D] bool, freq_cut [H] bool)."""
+    _, _, D, H, W = shape
+    w, h = H, W                                   # evp.py:128 names them this way
+    line = int((w * h * rate) ** .5 // 2)
+    d_hit = torch.zeros(D, dtype=torch.bool)
+    d_hit[w // 2 - line:w // 2 + line] = True      # the reference's own slice expressions (python slice semantics on each axis)
+    k_cut = torch.zeros(H, dtype=torch.bool)
+    k_cut[h // 2 - line:h // 2 + line] = True
+    # un-shift: fftshift moves index i to (i + n//2) % n, so shifted position j holds un-shifted index (j - n//2) % n
+    d_un = torch.zeros(D, dtype=torch.bool)
+    d_un[(torch.arange(D) - D // 2) % D] = d_hit
+    k_un = torch.zeros(H, dtype=torch.bool)
+    k_un[(torch.arange(H) - H // 2) % H] = k_cut
+    return d_un, k_un
+
+
+def evp_filter_matrix(H, k_cut):
+    """Real H x H matrix F with  real(ifft_H(fft_H(x) * (1 - cut))) = F @ x  for real x:  F = I - Re(IDFT diag(cut) DFT), in fp64."""
+    n = torch.arange(H, dtype=torch.float64)
+    k = n[k_cut.bool()]
+    ang = 2 * math.pi * (n[:, None, None] - n[None, :, None]) * k[None, None, :] / H
+    return torch.eye(H, dtype=torch.float64) - torch.cos(ang).sum(-1) / H
+
+
+def evp_highpass(img, rate):
+    """model/evp.py:124-146 restated with the same torch.fft calls (the closed form above is checked against this in the tests)."""
+    mask = torch.zeros(img.shape)
+    w, h = img.shape[-2:]
+    line = int((w * h * rate) ** .5 // 2)
+    mask[:, :, w // 2 - line:w // 2 + line, h // 2 - line:h // 2 + line] = 1
+    f = torch.fft.fftshift(torch.fft.fft2(img, norm='forward')) * (1 - mask)
+    return torch.fft.ifft2(torch.fft.ifftshift(f), norm='forward').real.abs()
+
+
+def evp_highpass_closed_form(img, rate):
+    """|F @ x| along H on the hit depth slices, |x| elsewhere (evp_filter_plan / evp_filter_matrix)."""
+    d_un, k_un = evp_filter_plan(img.shape, rate)
+    Fm = evp_filter_matrix(img.shape[3], k_un)
+    y = img.double().clone()
+    y[:, :, d_un] = torch.einsum('hk,bcdkw->bcdhw', Fm, y[:, :, d_un])
+    return y.abs().float()
+
+
+def evp_forward(sd, img, *, backbone, frame_patch_size, image_patch_size, pool='cls', dim_head=64, freq_nums=0.25):
+    """model/evp.py:346-369 (ExplicitVisualPrompting.forward) -> :72-95 (PromptGenerator) -> :208-217 (Transformer).
+    embedding_feature = Linear(conv_proj(img) tokens WITHOUT cls / pos); handcrafted_feature = a second Conv3d patch embedding of the
+    high-passed volume; prompt_i = shared_mlp(GELU(lightweight_mlp_i(handcrafted + embedding))) is added to the patch rows (not cls)
+    before every block; final LayerNorm, pool, plain Linear head."""
+    depth, heads, dim, _ = mapping_vit(backbone)
+    fp, ps = frame_patch_size, image_patch_size
+    pg = 'prompt_generator.'
+    wc, bc = sd['conv_proj.proj.weight'], sd['conv_proj.proj.bias']
+    e = patchify(img, fp, ps) @ wc.reshape(wc.shape[0], -1).t() + bc                     # (B, N, dim)
+    emb = e @ sd[pg + 'embedding_generator.weight'].t() + sd[pg + 'embedding_generator.bias']
+    wh, bh = sd[pg + 'prompt_generator.proj.weight'], sd[pg + 'prompt_generator.proj.bias']
+    hc = patchify(evp_highpass(img, freq_nums), fp, ps) @ wh.reshape(wh.shape[0], -1).t() + bh
+    f = hc + emb
+    B = e.shape[0]
+    x = torch.cat([sd['cls_token'].expand(B, -1, -1), e], dim=1)
+    x = x + sd['pos_embedding'][:, :x.shape[1]]
+    for i in range(depth):
+        lw = f'{pg}lightweight_mlp_{i}.0.'
+        prompt = F.gelu(f @ sd[lw + 'weight'].t() + sd[lw + 'bias']) @ sd[pg + 'shared_mlp.weight'].t() + sd[pg + 'shared_mlp.bias']
+        x = torch.cat([x[:, :1], prompt + x[:, 1:]], dim=1)
+        p = f'transformer.layers.{i}.'
+        x = _vit_block(x, sd, p, heads, dim_head)
+        x = feed_forward(x, sd, p + '1.') + x
+    return _pool_head(x, sd, pool, 'transformer.norm.', 'mlp_head.')

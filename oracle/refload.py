@@ -32,11 +32,14 @@ def load():
     import model.melo as melo
     import model.vpt as vpt
     import model.dvpt as dvpt
-    for m in (g, vt, af, ssf, dvpt):
+    import model.evp as evp
+    evp.device = __import__('torch').device('cpu')       # evp.py:19 picks cuda when present; the goldens are CPU fp32
+    for m in (g, vt, af, ssf, dvpt, evp):
         m.load_pretrain = lambda *a, **k: {}       # names bound by `from ... import` (e.g. gaviko.py:7)
     from losses.focal_loss import FocalLoss
     return types.SimpleNamespace(Gaviko=g.Gaviko, VisionTransformer=vt.VisionTransformer, AdaptFormer=af.AdaptFormer,
                                  ScalingShiftingFeatures=ssf.ScalingShiftingFeatures, MeLO=melo.MeLO,
                                  PromptedVisionTransformer=vpt.PromptedVisionTransformer, DynamicVisualPromptTuning=dvpt.DynamicVisualPromptTuning,
+                                 ExplicitVisualPrompting=evp.ExplicitVisualPrompting,
                                  FocalLoss=FocalLoss,
                                  gaviko=g, vision_transformer=vt)

@@ -325,6 +325,24 @@ def patch_gather(img, fp, ps, out_dtype):
     return x.reshape(B * nd * nh * nw, C * fp * ps * ps).to(out_dtype).contiguous()
 
 
+def _rowmap(M, rows):
+    m = torch.arange(M)
+    return m if not rows or rows[0] <= 0 else (m // rows[0]) * rows[1] + m % rows[0]
+
+
+def wgrad(a, b, dw, *, M=None, a_rows=None, b_rows=None, prec=PREC_FP32):
+    M = a.shape[0] if M is None else M
+    dw.add_(a[_rowmap(M, a_rows)].float().t() @ b[_rowmap(M, b_rows)].float())
+    return dw
+
+
+def hfreq_filter(img, filt, hit):
+    y = img.clone()
+    sel = hit.bool()
+    y[:, :, sel] = torch.einsum('hk,bcdkw->bcdhw', filt, img[:, :, sel])
+    return y.abs()
+
+
 def fill_rows(a, b, out, out_batch_rows, out_row_offset, B):
     R = a.shape[0]
     v = a + (b if b is not None else 0)

@@ -103,6 +103,31 @@ def test_dvpt_seeded_construction_equals_reference_init():
     assert [n for n, p in a.named_parameters() if p.requires_grad] == [n for n, p in b.named_parameters() if p.requires_grad]
 
 
+@pytest.mark.skipif(not refload.available(), reason='live reference only exists in the build container')
+@pytest.mark.parametrize('name', ['evp_t16_small', 'evp_mean_t16_small'])
+def test_evp_seeded_construction_equals_reference_init(name):
+    """EVP: nn defaults, then PromptGenerator.apply(_init_weights) with the reference's private truncated normal (model/evp.py:54-68,
+    165-206) — the drop-in consumes the RNG identically, and keeps the train() quirk (frozen blocks stay in eval, the generator trains)."""
+    from oracle.cases import NEXT_CASES
+    from gaviko_b200.model.evp import ExplicitVisualPrompting
+    ref = refload.load()
+    _, kw, _ = NEXT_CASES[name]
+    torch.manual_seed(3)
+    a = ref.ExplicitVisualPrompting(**kw)
+    torch.manual_seed(3)
+    b = ExplicitVisualPrompting(**kw)
+    sa, sb = a.state_dict(), b.state_dict()
+    assert list(sa.keys()) == list(sb.keys())
+    for k in sa:
+        assert torch.equal(sa[k], sb[k]), k
+    assert [n for n, p in a.named_parameters() if p.requires_grad] == [n for n, p in b.named_parameters() if p.requires_grad]
+    assert a.train() is None and b.train() is None
+    for mod in ('transformer', 'conv_proj', 'dropout', 'mlp_head', 'prompt_generator'):
+        assert getattr(a, mod).training == getattr(b, mod).training, mod
+    a.train(False), b.train(False)
+    assert a.training == b.training and a.prompt_generator.training == b.prompt_generator.training
+
+
 def test_engine_refuses_trainable_backbone_tensors(tmp_path, monkeypatch):
     """--method fft, or AdaptFormer / SSF built with freeze_vit=False (their constructor default), must raise instead of silently
     returning zero gradients for backbone weights the engine has no weight-gradient kernel for; every shipped PEFT trainable set passes."""

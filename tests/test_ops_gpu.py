@@ -464,3 +464,64 @@ def test_dvpt_quickgelu_and_gate_kernels():
     ops.gate_grads(w, dw, gate, acc, dgate)
     close(acc.cpu(), 1 + 0.37 * dw.cpu())
     close(dgate.cpu(), 2.0 + (w.double() * dw.double()).sum().cpu().reshape(1), 1e-5)
+
+
+# ---------------------------------------------------------------------------------------------- EVP primitives (csrc/gvk_evp.cu)
+@pytest.mark.parametrize('M,na,nb', [(1000, 192, 64), (2050, 768, 192), (515, 64, 3072), (33, 4, 8), (4099, 132, 68)])
+@pytest.mark.parametrize('dta,dtb', [(torch.float32, torch.float32), (torch.bfloat16, torch.bfloat16), (torch.float32, torch.bfloat16)])
+def test_evp_wgrad_general(M, na, nb, dta, dtb):
+    """dw += a^T b over the rows (autograd's Linear / Conv3d weight gradients of model/evp.py:42-52) against fp64: exact mode to fp32 rounding,
+    tf32 mode to the tf32 operand rounding; dw accumulates; ragged edges on every side of the 128 x 64 x 32 tiles."""
+    torch.manual_seed(M + na)
+    a = torch.randn(M, na, device=DEV).to(dta)
+    b = torch.randn(M, nb, device=DEV).to(dtb)
+    ref = a.double().t() @ b.double()
+    scale = ref.abs().max().item()
+    base = torch.randn(na, nb, device=DEV)
+    for prec, tol in ((ops.PREC_FP32, 2e-6), (ops.PREC_TF32, 2e-3)):
+        dw = base.clone()
+        ops.wgrad(a, b, dw, prec=prec)
+        err = (dw.double() - base.double() - ref).abs().max().item()
+        assert err <= tol * scale, (prec, err, scale)
+    # accumulate into a column slice of a wider matrix (ld_dw > nb)
+    wide = torch.zeros(na, nb + 8, device=DEV)
+    ops.wgrad(a, b, wide[:, 4:4 + nb], prec=ops.PREC_FP32)
+    assert wide[:, :4].abs().max().item() == 0 and wide[:, 4 + nb:].abs().max().item() == 0
+    assert (wide[:, 4:4 + nb].double() - ref).abs().max().item() <= 2e-6 * scale
+
+
+def test_evp_wgrad_row_maps():
+    """Operands that skip the cls row of every volume (row map (rows_per_batch, batch_rows) on either side) without a copy."""
+    torch.manual_seed(5)
+    B, N, T, na, nb = 3, 64, 65, 64, 192
+    a_full = torch.randn(B * T, na, device=DEV)
+    b_c = torch.randn(B * N, nb, device=DEV).bfloat16()
+    a_tok = a_full.view(B, T, na)[:, 1:].reshape(B * N, na)
+    ref = a_tok.double().t() @ b_c.double()
+    dw = torch.zeros(na, nb, device=DEV)
+    ops.wgrad(a_full[1:], b_c, dw, M=B * N, a_rows=(N, T))
+    assert (dw.double() - ref).abs().max().item() <= 2e-6 * ref.abs().max().item()
+    dw2 = torch.zeros(nb, na, device=DEV)
+    ops.wgrad(b_c, a_full[1:], dw2, M=B * N, b_rows=(N, T))
+    assert (dw2.double() - ref.t()).abs().max().item() <= 2e-6 * ref.abs().max().item()
+
+
+@pytest.mark.parametrize('shape,rate', [((2, 1, 48, 64, 64), 0.25), ((1, 1, 24, 32, 48), 0.1), ((2, 1, 12, 32, 32), 0.9), ((1, 2, 20, 16, 24), 0.5),
+                                        ((2, 1, 120, 160, 160), 0.25), ((1, 1, 6, 200, 330), 0.3)])
+def test_evp_hfreq_filter_matches_reference_fft(shape, rate):
+    """gvk_hfreq_filter with the engine's closed-form filter against PromptGenerator.fft restated with torch.fft (oracle.evp_highpass, pinned
+    to the live reference by the evp goldens): fftshift over every axis, mask on the depth / height axes, real part, abs."""
+    from gaviko_b200.model.evp import ExplicitVisualPrompting
+    from gaviko_b200.vit_engine import VitEngine
+
+    class _Stub:      # the filter builder only reads prompt_generator.freq_nums
+        class prompt_generator:
+            freq_nums = rate
+    eng = VitEngine.__new__(VitEngine)
+    eng.__dict__['_module_ref'] = _Stub
+    img = torch.rand(shape, generator=torch.Generator().manual_seed(7)).to(DEV)
+    filt, hit = eng._evp_filter(img)
+    out = ops.hfreq_filter(img, filt, hit)
+    ref = O.evp_highpass(img.cpu(), rate)
+    assert (out.cpu() - ref).abs().max().item() < 5e-6
+    assert ExplicitVisualPrompting is not None

@@ -80,17 +80,34 @@ def test_variant_oracle_matches_reference(name):
 
 @pytest.mark.parametrize('name', list(NEXT_CASES))
 def test_next_method_oracle_matches_reference(name):
-    """DVPT.  The oracle restatement is pinned against the live reference ahead of the CUDA path (both pool modes; the
-    trainable set recorded from the reference = prompts + every prompt_proj tensor + head)."""
+    """SURVEY.md §8 (f3) DVPT and (f4) EVP: the oracle restatements against the live reference (DVPT in both pool modes, trainable set =
+    prompts + every prompt_proj tensor + head; EVP at scale_factor 4 / 32, trainable set = every prompt_generator tensor + head)."""
     method, kw, batch = NEXT_CASES[name]
     g = load_golden(name)
     sd = sd_from_golden(g)
     names = g['trainable_names'].tolist()
-    assert 'prompt_embeddings' in names and 'prompt_positional_embedding' in names and 'mlp_head.weight' in names
-    assert all(('prompt' in n) or ('head' in n) for n in names) and len(names) == 2 + 5 * 12 + 2
-    fn = lambda sd, img: O.dvpt_forward(sd, img, backbone=kw['backbone'], frame_patch_size=kw['frame_patch_size'], image_patch_size=kw['image_patch_size'],
-                                        num_prompts=kw['num_prompts'], pool=kw['pool'])
+    common = dict(backbone=kw['backbone'], frame_patch_size=kw['frame_patch_size'], image_patch_size=kw['image_patch_size'], pool=kw['pool'])
+    if method == 'dvpt':
+        assert 'prompt_embeddings' in names and 'prompt_positional_embedding' in names and 'mlp_head.weight' in names
+        assert all(('prompt' in n) or ('head' in n) for n in names) and len(names) == 2 + 5 * 12 + 2
+        fn = lambda sd, img: O.dvpt_forward(sd, img, num_prompts=kw['num_prompts'], **common)
+    else:
+        assert all(n.startswith('prompt_generator.') or n.startswith('mlp_head.') for n in names) and len(names) == 2 + 4 + 2 * 12 + 2
+        fn = lambda sd, img: O.evp_forward(sd, img, freq_nums=kw['freq_nums'], **common)
     _check(g, sd, fn, kw, batch)
+
+
+@pytest.mark.parametrize('shape,rate', [((2, 1, 48, 64, 64), 0.25), ((1, 1, 24, 32, 48), 0.1), ((2, 1, 12, 32, 32), 0.9), ((1, 2, 20, 16, 24), 0.5),
+                                        ((1, 1, 120, 160, 160), 0.25)])
+def test_evp_highpass_closed_form(shape, rate):
+    """PromptGenerator.fft (model/evp.py:124-146, restated with the same torch.fft calls) equals its closed form — a real H x H matrix applied
+    along H on a cyclic range of depth slices, |x| elsewhere — which is what gvk_hfreq_filter computes."""
+    img = torch.rand(shape, generator=torch.Generator().manual_seed(3))
+    a, b = O.evp_highpass(img, rate), O.evp_highpass_closed_form(img, rate)
+    assert (a - b).abs().max().item() < 2e-6
+    d_un, k_un = O.evp_filter_plan(shape, rate)
+    if shape[2:] == (120, 160, 160):      # the shipped geometry (configs/evp.yaml): 80 of 120 slices lose the 80 lowest H-frequencies
+        assert int(d_un.sum()) == 80 and int(k_un.sum()) == 80 and bool(k_un[0]) and not bool(d_un[60])
 
 
 def test_focal_known_answers():

@@ -6,7 +6,7 @@ import ops_double
 import test_script_equivalent_gpu as T
 
 
-@pytest.mark.parametrize('method', ['gaviko', 'dvpt', 'deep_vpt', 'melo', 'bitfit'])
+@pytest.mark.parametrize('method', ['gaviko', 'dvpt', 'deep_vpt', 'melo', 'bitfit', 'evp'])
 def test_train_eval_checkpoint_sequence_host_side(method, tmp_path, monkeypatch):
     monkeypatch.setattr(T, 'DEVICE', 'cpu')
     with ops_double.install():

@@ -30,6 +30,7 @@ MODEL = dict(image_size=64, image_patch_size=16, frames=48, frame_patch_size=12,
 
 def _build(method, tmp_path):
     from gaviko_b200.model.dvpt import DynamicVisualPromptTuning
+    from gaviko_b200.model.evp import ExplicitVisualPrompting
     from gaviko_b200.model.gaviko import Gaviko
     from gaviko_b200.model.melo import MeLO
     from gaviko_b200.model.vision_transformer import VisionTransformer
@@ -45,6 +46,8 @@ def _build(method, tmp_path):
                 model = Gaviko(**cfg['model'])
             elif method == 'dvpt':
                 model = DynamicVisualPromptTuning(**cfg['model'])
+            elif method == 'evp':
+                model = ExplicitVisualPrompting(**cfg['model'])
             elif method == 'melo':
                 model = MeLO(vit=VisionTransformer(**cfg['model']), **cfg['model'])
             elif method == 'bitfit':
@@ -58,7 +61,7 @@ def _build(method, tmp_path):
     return model
 
 
-@pytest.mark.parametrize('method', ['gaviko', 'dvpt', 'deep_vpt', 'melo', 'bitfit'])
+@pytest.mark.parametrize('method', ['gaviko', 'dvpt', 'deep_vpt', 'melo', 'bitfit', 'evp'])
 def test_train_eval_checkpoint_sequence(method, tmp_path):
     from gaviko_b200.losses.focal_loss import FocalLoss
     from gaviko_b200.utils.load_pretrained import load_vanilla_pretrain_with_adapters

@@ -86,7 +86,7 @@ def _run(script, *argv):
     return launch.run(os.path.join(REF_SRC, script), list(argv))
 
 
-@pytest.mark.parametrize('method', ['gaviko', 'dvpt', 'deep_vpt', 'melo'])
+@pytest.mark.parametrize('method', ['gaviko', 'dvpt', 'deep_vpt', 'melo', 'evp'])
 def test_unmodified_train_eval_inference(method, tmp_path, monkeypatch):
     monkeypatch.chdir(tmp_path)
     cfg = _dataset(tmp_path)
@@ -139,6 +139,8 @@ def _trainable_names(method, cfg):
             m = ref.DynamicVisualPromptTuning(**kw)
         elif method == 'melo':
             m = ref.MeLO(vit=ref.VisionTransformer(**kw), **kw)
+        elif method == 'evp':
+            m = ref.ExplicitVisualPrompting(**kw)
         else:
             m = ref.PromptedVisionTransformer(**kw)
     for name in [k for k in sys.modules if k.split('.')[0] in ('model', 'losses', 'utils')]:

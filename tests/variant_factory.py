@@ -1,6 +1,7 @@
 """Build a drop-in variant the way reference src/train.py:111-153 does for its --method switch."""
 from gaviko_b200.model.adaptformer import AdaptFormer
 from gaviko_b200.model.dvpt import DynamicVisualPromptTuning
+from gaviko_b200.model.evp import ExplicitVisualPrompting
 from gaviko_b200.model.melo import MeLO
 from gaviko_b200.model.ssf import ScalingShiftingFeatures
 from gaviko_b200.model.vision_transformer import VisionTransformer
@@ -23,4 +24,6 @@ def build_variant(method, kw):
         return PromptedVisionTransformer(**kw)
     if method == 'dvpt':
         return DynamicVisualPromptTuning(**kw)
+    if method == 'evp':
+        return ExplicitVisualPrompting(**kw)
     raise ValueError(method)
