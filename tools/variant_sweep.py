@@ -8,7 +8,7 @@ from gaviko_b200.losses.focal_loss import CrossEntropyLoss
 from gaviko_b200.optim import FlatAdam
 
 ap = argparse.ArgumentParser()
-ap.add_argument('--batch', type=int, default=32); ap.add_argument('--backbone', default='vit-b16'); ap.add_argument('--steps', type=int, default=5)
+ap.add_argument('--batch', type=int, default=32); ap.add_argument('--backbone', default='vit-b16'); ap.add_argument('--steps', type=int, default=5); ap.add_argument('--only', default='')
 a = ap.parse_args()
 FULL = dict(image_size=160, image_patch_size=16, frames=120, frame_patch_size=12, num_classes=5, channels=1, pool='cls', backbone=a.backbone,
             dropout=0.1, emb_dropout=0.1, compute_dtype='bf16')       # the reference configs' dropout: active in train mode for linear / bitfit / melo
@@ -17,7 +17,10 @@ VPT = dict(FZ, prompt_dropout=0.1, prompt_dim=64)
 CASES = [('linear', FULL), ('bitfit', FULL), ('ssf', FZ), ('adaptformer', FZ), ('melo', dict(FULL, r=4, alpha=8)), ('melo', dict(FULL, r=8, alpha=16)),
          ('melo', dict(FULL, r=16, alpha=32)), ('shallow_vpt', dict(VPT, num_prompts=32, deep_prompt=False)), ('deep_vpt', dict(VPT, num_prompts=8, deep_prompt=True)),
          ('deep_vpt', dict(VPT, num_prompts=32, deep_prompt=True)), ('deep_vpt', dict(VPT, num_prompts=64, deep_prompt=True)),
-         ('deep_vpt', dict(VPT, num_prompts=100, deep_prompt=True)), ('dvpt', dict(FZ, num_prompts=32))]
+         ('deep_vpt', dict(VPT, num_prompts=100, deep_prompt=True)), ('dvpt', dict(FZ, num_prompts=32)),
+         ('evp', dict(FZ, scale_factor=4)), ('evp', dict(FZ, scale_factor=32))]      # evp.yaml ships scale_factor 4 (rank 192 at ViT-B); 32 is the constructor default
+if a.only:
+    CASES = [c for c in CASES if c[0] in a.only.split(',')]
 x = torch.rand(a.batch, 1, 120, 160, 160, device='cuda'); y = torch.randint(0, 5, (a.batch,), device='cuda')
 crit = CrossEntropyLoss()
 rows = []
@@ -38,7 +41,7 @@ for method, extra in CASES:
         e1.record(); torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / a.steps
         ntr = sum(p.numel() for p in m.parameters() if p.requires_grad)
-        rows.append(dict(method=method, **{k: v for k, v in extra.items() if k in ('r', 'num_prompts', 'deep_prompt')}, ms_per_step=round(ms, 2), volumes_per_s=round(a.batch / ms * 1e3, 1), trainable=ntr))
+        rows.append(dict(method=method, **{k: v for k, v in extra.items() if k in ('r', 'num_prompts', 'deep_prompt', 'scale_factor')}, ms_per_step=round(ms, 2), volumes_per_s=round(a.batch / ms * 1e3, 1), trainable=ntr))
         print(json.dumps(rows[-1]), flush=True)
     except Exception as e:   # a variant the factory cannot build with these kwargs is reported, not hidden
         print(json.dumps(dict(method=method, **{k: v for k, v in extra.items() if k in ('r', 'num_prompts', 'deep_prompt')}, error=f'{type(e).__name__}: {e}'[:200])), flush=True)
