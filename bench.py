@@ -239,13 +239,18 @@ def run_ours(args):
 
     gstep = None
     launches_per_replay = 0
-    if args.graph:
-        if not train:
-            raise SystemExit('bench.py --graph: training only')
+    launch_mode = 'eager (one launch per kernel)'
+    if train and not args.eager:
+        # default: the whole step (forward + loss + backward + all-reduce + clip + Adam) captured once as ONE CUDA graph and replayed
         from gaviko_b200.graph import GraphedTrainStep
         n0 = L.launch_count()
-        gstep = GraphedTrainStep(model, crit, opt, x_dev, y_dev, warmup=2)
-        launches_per_replay = (L.launch_count() - n0) // 3          # 2 warm-up steps + the captured one enqueue the same kernels
+        try:
+            gstep = GraphedTrainStep(model, crit, opt, x_dev, y_dev, warmup=2)
+            launches_per_replay = (L.launch_count() - n0) // 3          # 2 warm-up steps + the captured one enqueue the same kernels
+            launch_mode = 'one CUDA graph per step'
+        except Exception as ex:  # noqa: BLE001   (reported in config.launch: the same kernels then run launch by launch)
+            gstep = None
+            launch_mode = f'eager (graph capture failed: {type(ex).__name__}: {ex})'[:200]
 
     def step(x, y):
         if gstep is not None:
@@ -387,7 +392,7 @@ def run_ours(args):
                     eager[name] = dict(value=None, unit='volumes/s', sample=f'failed: {type(ex).__name__}: {ex}'[:300])
                 torch.cuda.empty_cache()
         line = dict(metric=metric_name(args), value=value, unit='volumes/s', n_gpus=world, steps=args.steps, warmup=args.warmup, ms_per_step=ms / args.steps,
-                    higher_is_better=True, scaling='weak', vs_baseline=None, dtype=args.dtype, data='synthetic', config=dict(workload(args, B, world), launch='one CUDA graph per step' if gstep is not None else 'eager (one launch per kernel)'), clocks=clocks,
+                    higher_is_better=True, scaling='weak', vs_baseline=None, dtype=args.dtype, data='synthetic', config=dict(workload(args, B, world), launch=launch_mode), clocks=clocks,
                     e2e=dict(value=e2e_value, unit='volumes/s', h2d_bytes_per_step=world * (B * 120 * 160 * 160 * 4 + B * 8), d2h_bytes_per_step=world * 4,
                              ms_per_step=ms_e2e / args.steps),
                     gpu_launches=launches, roofline=roof, cpu_baseline=cpu, gpu_eager_baseline=eager,
@@ -407,7 +412,8 @@ def main():
     ap.add_argument('--backbone', default='vit-b16')
     ap.add_argument('--batch', type=int, default=64, help='volumes per GPU per step (SURVEY 8d: 16 | 32 | 64)')
     ap.add_argument('--dtype', default='bf16', choices=['bf16', 'fp32'])
-    ap.add_argument('--graph', action='store_true', help='train mode, N = 1: replay the whole step as ONE CUDA graph (gaviko_b200.graph.GraphedTrainStep)')
+    ap.add_argument('--graph', action='store_true', help='(default for training) replay the whole step as ONE CUDA graph (gaviko_b200.graph.GraphedTrainStep)')
+    ap.add_argument('--eager', action='store_true', help='training: launch kernel by kernel from Python instead of replaying the captured CUDA graph')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-gpu-eager-baseline', action='store_true', help='skip timing the eager-PyTorch port of the reference on this GPU (N=1 only)')
     args = ap.parse_args()

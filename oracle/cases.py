@@ -54,3 +54,10 @@ NEXT_CASES = {
     'evp_mean_t16_small': ('evp', dict(SMALL, num_classes=5, channels=1, pool='mean', backbone='vit-t16', dropout=0.0, emb_dropout=0.0,
                                        freeze_vit=True, scale_factor=32, input_type='fft', freq_nums=0.25), 3),
 }
+
+# EVP on the reference's own seeded init at the shipped geometry and backbone (configs/evp.yaml: ViT-B, scale_factor 4 -> latent width 192, full
+# 1x120x160x160 volumes): the frequency filter at H = W = 160 inside the model, the un-padded latent width, compact gradient store.
+EVP_INIT_CASES = {
+    'evp_b16_full_init': (dict(FULL, num_classes=5, channels=1, pool='cls', backbone='vit-b16', dropout=0.0, emb_dropout=0.0, freeze_vit=True,
+                               scale_factor=4, input_type='fft', freq_nums=0.25, handcrafted_tune=True, embedding_tune=True), 2, 21, 'subset'),
+}

@@ -13,6 +13,11 @@ CHUNK = 32
 
 
 def stored_in_full(name: str, depth: int) -> bool:
+    if name.startswith('prompt_generator.'):      # EVP: biases and three of the per-layer generators in full, the large matrices as chunk sums
+        m = re.search(r'lightweight_mlp_(\d+)\.', name)
+        if m is not None:
+            return int(m.group(1)) in (0, depth // 2, depth - 1)
+        return name.endswith('.bias')
     m = re.search(r'\.(\d+)\.', name)
     if m is None:
         return True                      # prompts, head

@@ -13,7 +13,7 @@ import numpy as np
 import torch
 
 from . import refload
-from .cases import GAVIKO_CASES, GAVIKO_INIT_CASES, NEXT_CASES, VARIANT_CASES
+from .cases import EVP_INIT_CASES, GAVIKO_CASES, GAVIKO_INIT_CASES, NEXT_CASES, VARIANT_CASES
 from .golden_store import chunk_sums, fingerprint, stored_in_full
 from .golden_fill import golden_eval_volume, golden_fill, golden_labels, golden_volume
 
@@ -96,7 +96,8 @@ def run_case(ref, model, kw, batch, name, bf16_floor=False, fill=True, store='al
         fp = fingerprint(model.state_dict())
         out['fingerprint_names'] = np.array(list(fp.keys()))
         out['fingerprint'] = np.array(list(fp.values()), dtype=np.float64)
-    depth = len(model.transformer.attns) if hasattr(model, 'transformer') and hasattr(model.transformer, 'attns') else 0
+    tr = getattr(model, 'transformer', None)
+    depth = len(tr.attns) if hasattr(tr, 'attns') else (len(tr.layers) if hasattr(tr, 'layers') else 0)
     for loss_name, crit in (('focal', ref.FocalLoss(gamma=1.2)), ('ce', torch.nn.CrossEntropyLoss())):
         model.zero_grad(set_to_none=True)
         logits = model(img)
@@ -195,6 +196,10 @@ def main():
             if want(name):
                 # evp: torch.fft has no bfloat16 kernels, so the reference's own model.to(bfloat16) run does not exist (no bf16 floor recorded)
                 run_case(ref, build_variant(ref, method, kw), kw, batch, name, bf16_floor=(method != 'evp'))
+        for name, (kw, batch, seed, store) in EVP_INIT_CASES.items():
+            if want(name):
+                torch.manual_seed(seed)
+                run_case(ref, ref.ExplicitVisualPrompting(**kw), kw, batch, name, bf16_floor=False, fill=False, store=store)
     finally:
         os.chdir(cwd)
 

@@ -4,7 +4,7 @@ import pytest
 import torch
 
 from oracle import gaviko_oracle as O
-from oracle.cases import GAVIKO_CASES, GAVIKO_INIT_CASES, NEXT_CASES, VARIANT_CASES
+from oracle.cases import EVP_INIT_CASES, GAVIKO_CASES, GAVIKO_INIT_CASES, NEXT_CASES, VARIANT_CASES
 from oracle.golden_fill import golden_labels, golden_volume
 
 from helpers import check_fingerprint, grad_parity, load_golden, rel_l2, sd_from_golden
@@ -94,6 +94,23 @@ def test_next_method_oracle_matches_reference(name):
     else:
         assert all(n.startswith('prompt_generator.') or n.startswith('mlp_head.') for n in names) and len(names) == 2 + 4 + 2 * 12 + 2
         fn = lambda sd, img: O.evp_forward(sd, img, freq_nums=kw['freq_nums'], **common)
+    _check(g, sd, fn, kw, batch)
+
+
+@pytest.mark.parametrize('name', list(EVP_INIT_CASES))
+def test_evp_oracle_matches_reference_on_its_own_init(name):
+    """EVP at the shipped geometry / backbone (ViT-B, scale_factor 4, full volumes) on the reference's own seeded init: the drop-in constructor
+    reproduces the weights (fingerprint recorded from the live reference) and the oracle reproduces logits, losses and gradients on them."""
+    from gaviko_b200.model.evp import ExplicitVisualPrompting
+    kw, batch, seed, _ = EVP_INIT_CASES[name]
+    g = load_golden(name)
+    torch.manual_seed(seed)
+    m = ExplicitVisualPrompting(**kw)
+    check_fingerprint(m, g)
+    tn = set(g['trainable_names'].tolist())
+    sd = {k: v.detach().clone().requires_grad_(k in tn) for k, v in m.state_dict().items()}
+    fn = lambda sd, img: O.evp_forward(sd, img, backbone=kw['backbone'], frame_patch_size=kw['frame_patch_size'], image_patch_size=kw['image_patch_size'],
+                                       pool=kw['pool'], freq_nums=kw['freq_nums'])
     _check(g, sd, fn, kw, batch)
 
 

@@ -117,3 +117,39 @@ def test_vpt_prompt_dropout_mask_is_replayed_in_backward(name, tmp_path):
         emb.add_(eps * v)
     fd, an = (lp - lm) / (2 * eps), (g * v).sum().item()
     assert abs(fd - an) <= 2e-2 * max(abs(an), abs(fd)) + 1e-5, (fd, an)
+
+
+# ---------------------------------------------------------------------------------------------- EVP at the shipped geometry and backbone
+def _build_evp_init(name, compute_dtype):
+    from oracle.cases import EVP_INIT_CASES
+    from gaviko_b200.model.evp import ExplicitVisualPrompting
+    from helpers import check_fingerprint
+    kw, batch, seed, _ = EVP_INIT_CASES[name]
+    torch.manual_seed(seed)
+    model = ExplicitVisualPrompting(**kw, compute_dtype=compute_dtype)
+    g = load_golden(name)
+    check_fingerprint(model, g)          # same weights as the reference built under this seed
+    model = model.cuda()
+    model.eval()
+    img = golden_volume(batch, kw['frames'], kw['image_size'], kw['image_size'], channels=kw['channels']).cuda()
+    y = golden_labels(batch, kw['num_classes']).cuda()
+    return model, img, y, g
+
+
+@pytest.mark.parametrize('mode,tol,tol_t', [('fp32', 1e-4, 1e-3), ('bf16', 2e-2, 6e-2)])
+def test_evp_vitb_full_shape_on_reference_init(mode, tol, tol_t):
+    """EVP as configs/evp.yaml ships it (ViT-B, scale_factor 4: latent width 192 without padding, full 1x120x160x160 volumes: the frequency filter
+    at H = W = 160 inside the model) on the reference's own seeded init: fp32 mode 1e-4, bf16 mode 2e-2 (logits, and gradients as global rel-L2)."""
+    model, img, y, g = _build_evp_init('evp_b16_full_init', mode)
+    for loss_name, crit in (('focal', FocalLoss(gamma=1.2)), ('ce', CrossEntropyLoss())):
+        model.zero_grad(set_to_none=True)
+        logits = model(img)
+        loss = crit(logits, y)
+        loss.backward()
+        rl = rel_l2(logits.detach().cpu(), g['logits'])
+        assert rl < tol, rl
+        assert logits.argmax(1).cpu().tolist() == g['logits'].argmax(1).tolist()
+        assert abs(loss.item() - float(g[f'loss_{loss_name}'])) < (1e-4 if mode == 'fp32' else 2e-2)
+        grads = {n: p.grad for n, p in model.named_parameters() if p.requires_grad}
+        glob, worst, wname = grad_parity(grads, g, loss_name, tol_global=tol, tol_tensor=tol_t, floor=1e-3, floor_slack=2.0)
+        print(f'evp_b16_full_init {mode} {loss_name}: logits rel {rl:.2e} grads global {glob:.2e} worst {worst:.2e} ({wname})')
