@@ -12,13 +12,19 @@ from bench import GAVIKO_KW
 ap = argparse.ArgumentParser()
 ap.add_argument('--backbone', default='vit-b16'); ap.add_argument('--batch', type=int, default=8); ap.add_argument('--dtype', default='bf16')
 ap.add_argument('--steps', type=int, default=2); ap.add_argument('--by-site', action='store_true'); ap.add_argument('--eval', action='store_true')
+ap.add_argument('--method', default='gaviko', help="gaviko (default) or evp (configs/evp.yaml: scale_factor 4)")
 a = ap.parse_args()
 torch.manual_seed(0)
 with contextlib.redirect_stdout(io.StringIO()):
-    model = Gaviko(**GAVIKO_KW, backbone=a.backbone, compute_dtype=a.dtype).cuda()
+    if a.method == 'evp':
+        from gaviko_b200.model.evp import ExplicitVisualPrompting
+        model = ExplicitVisualPrompting(image_size=160, image_patch_size=16, frames=120, frame_patch_size=12, num_classes=5, channels=1, pool='cls', backbone=a.backbone,
+                                        dropout=0.1, emb_dropout=0.1, freeze_vit=True, scale_factor=4, compute_dtype=a.dtype).cuda()
+    else:
+        model = Gaviko(**GAVIKO_KW, backbone=a.backbone, compute_dtype=a.dtype).cuda()
 model.train()
 if a.eval: model.eval()
-opt = FlatAdam(model.parameters(), lr=1e-4, model=model)
+opt = FlatAdam([p for p in model.parameters() if p.requires_grad], lr=1e-4, model=model)
 crit = FocalLoss(gamma=1.2)
 x = torch.rand(a.batch, 1, 120, 160, 160, device='cuda'); y = torch.randint(0, 5, (a.batch,), device='cuda')
 
