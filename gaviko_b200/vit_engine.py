@@ -263,12 +263,15 @@ class VitEngine:
             st = dict(T_in=T)
             if evp:
                 # prompt_i = shared_mlp(GELU(lightweight_mlp_i(f))) added to the patch rows (model/evp.py:85-95,210-214).  All B*T rows go through
-                # the two GEMMs; the cls rows of h are zeroed so that they add nothing (and drop out of the shared_mlp weight gradient)
+                # the two GEMMs.  shared_mlp's bias rides on the GEMM as a K-extension: latent slot r of h holds 1 and column r of the padded weight
+                # holds the bias, so zeroing the cls rows of h (B rows: plumbing) removes weight AND bias from them — and the same slot of the
+                # weight gradient is the bias gradient.  The second GEMM then has the plain bias + fp32-residual epilogue
                 E = ev['E']
                 pre = torch.empty((B * T, E['rp']), device=img.device, dtype=cdt) if save else None
                 h = ops.gemm(ev['f'], E['wi'][i], bias=E['bi'][i], act=ops.ACT_GELU, aux=pre, out_dtype=cdt)
-                h.view(B, T, -1)[:, 0].zero_()            # B rows: plumbing
-                x = ops.gemm(h, E['ws'], pos=E['posb'], rows_per_batch=T, out_batch_rows=T, out_row_offset=0, res1=x)
+                h[:, E['r']].fill_(1.0)
+                h.view(B, T, -1)[:, 0].zero_()
+                x = ops.gemm(h, E['ws'], bias=E['zero_dim'], res1=x)
                 st.update(evp_h=h, evp_pre=pre)
             if vpt and (i == 0 or m.deep_prompt):
                 # [cls ; P prompts ; rest]: at layers >= 1 the reference drops rows 1 .. prompt_dim (NOT 1 .. P), model/vpt.py:151-153
@@ -314,7 +317,12 @@ class VitEngine:
             # ---- MLP (model/vision_transformer.py:26-38) + parallel adapter (model/adaptformer.py:93-99)
             h2, mean2, rstd2 = ops.layernorm_fwd(x_mid, Lw['ln2_w'], Lw['ln2_b'], out_dtype=cdt, ssf_scale=s_f0[0], ssf_shift=s_f0[1], save_stats=save)
             hpre = torch.empty((B * T, c['mlp_dim']), device=img.device, dtype=cdt) if save else None
-            act = ops.gemm(h2, Lw['w1'], bias=Lw['b1'], ssf_scale=s_f1[0], ssf_shift=s_f1[1], act=ops.ACT_GELU, aux=hpre, out_dtype=cdt)
+            # Without an SSF site behind fc1 the backward needs only gelu'(pre): the forward epilogue saves the derivative (it shares the transcendental
+            # with the activation) and the dgrad epilogue is one multiply instead of an erf.  SSF (model/ssf.py:77-80) needs the pre-activation itself.
+            save_grad = save and 'f1' not in sa
+            act = ops.gemm(h2, Lw['w1'], bias=Lw['b1'], ssf_scale=s_f1[0], ssf_shift=s_f1[1], act=ops.ACT_GELU_SAVE_GRAD if save_grad else ops.ACT_GELU,
+                           aux=hpre, out_dtype=cdt)
+            st['gelu_grad_saved'] = save_grad
             del h2
             if p_ff1 > 0:
                 act = ops.dropout(act, p_ff1, seeds[2])
@@ -414,7 +422,7 @@ class VitEngine:
 
             # ---- MLP
             dY2 = site_bwd(dX, st.get('y_f'), 'f2', n_['b2'], p_ff2, seeds[3], dX_lp)
-            dA = ops.gemm(dY2, Lw['w2_t'], act=ops.ACT_GELU_BWD, aux=st['hpre'], out_dtype=cdt)
+            dA = ops.gemm(dY2, Lw['w2_t'], act=ops.ACT_MUL_AUX if st['gelu_grad_saved'] else ops.ACT_GELU_BWD, aux=st['hpre'], out_dtype=cdt)
             if p_ff1 > 0:
                 dA = ops.dropout(dA, p_ff1, seeds[2])
             if 'f1' in sa:
@@ -559,12 +567,13 @@ class VitEngine:
         return hit_f
 
     def _evp_weights(self, cdt, T):
-        """The prompt generator's tensors as GEMM operands: zero-padded to a latent width that is a multiple of 64 (the GEMM's K granularity),
-        in compute dtype, plus the transposes the dgrad GEMMs read.  Trainable, so rebuilt every step (a few small casts: plumbing)."""
+        """The prompt generator's tensors as GEMM operands: zero-padded to a latent width rp that is a multiple of 64 (the GEMM's K granularity)
+        with at least one spare slot (slot r carries shared_mlp's bias, see forward), in compute dtype, plus the transposes the dgrad GEMMs
+        read.  Trainable, so rebuilt every step (a few small casts: plumbing)."""
         m, c = self.module, self.module._cfg
         pg = m.prompt_generator
         r, dim, depth = c['evp_rank'], c['dim'], c['depth']
-        rp = (r + 63) // 64 * 64
+        rp = (r + 1 + 63) // 64 * 64
         dev = m.pos_embedding.device
 
         def padw(w, rows, cols):
@@ -579,12 +588,11 @@ class VitEngine:
 
         conv = pg.prompt_generator.proj
         lins = [getattr(pg, f'lightweight_mlp_{i}')[0] for i in range(depth)]
-        ws = pg.shared_mlp.weight
-        posb = ws.new_zeros((T, dim), dtype=torch.float32)
-        posb[1:] = pg.shared_mlp.bias.detach().float()         # shared_mlp bias on the patch rows only (row 0 = cls)
-        return dict(r=r, rp=rp, we=padw(pg.embedding_generator.weight, rp, dim), be=padv(pg.embedding_generator.bias, rp),
+        ws = padw(pg.shared_mlp.weight, dim, rp)
+        ws[:, r] = pg.shared_mlp.bias.detach()                 # bias as column r (h[:, r] = 1 on the patch rows, 0 on the cls rows)
+        return dict(r=r, rp=rp, zero_dim=torch.zeros(dim, device=dev, dtype=torch.float32), we=padw(pg.embedding_generator.weight, rp, dim), be=padv(pg.embedding_generator.bias, rp),
                     wc=padw(conv.weight.reshape(r, -1), rp, conv.weight[0].numel()), bc=padv(conv.bias, rp),
-                    ws=padw(ws, dim, rp), ws_t=padw(ws.t(), rp, dim), posb=posb,
+                    ws=ws, ws_t=ws.t().contiguous(),
                     wi=[padw(l.weight, rp, rp) for l in lins], wi_t=[padw(l.weight.t(), rp, rp) for l in lins], bi=[padv(l.bias, rp) for l in lins])
 
     def _evp_setup(self, img, patches, W, cdt, B, N, T):
@@ -609,12 +617,11 @@ class VitEngine:
         if 'acc' not in ev:
             rp, dim = E['rp'], dX.shape[1]
             z = lambda *s: torch.zeros(s, device=dev, dtype=torch.float32)   # noqa: E731
-            ev['acc'] = dict(ws=z(dim, rp), bs=z(dim), wi=[z(rp, rp) for _ in E['wi']], bi=[z(rp) for _ in E['wi']], we=z(rp, dim), bf=z(rp),
+            ev['acc'] = dict(ws=z(dim, rp), wi=[z(rp, rp) for _ in E['wi']], bi=[z(rp) for _ in E['wi']], we=z(rp, dim), bf=z(rp),
                              wc=z(rp, E['wc'].shape[1]))
         acc = ev['acc']
         dP = dX_lp if dX_lp is not None else dX
-        ops.wgrad(dP, st['evp_h'], acc['ws'], prec=pr)
-        ops.ssf_bwd(dX[1:], dshift=acc['bs'], rows_per_batch=N, batch_rows=T, M=B * N)
+        ops.wgrad(dP, st['evp_h'], acc['ws'], prec=pr)            # column r (the ones slot of h) accumulates the bias gradient
         dpre = ops.gemm(dP, E['ws_t'], act=ops.ACT_GELU_BWD, aux=st['evp_pre'], out_dtype=ctx['cdt'])
         ops.wgrad(dpre, ev['f'], acc['wi'][i], prec=pr)
         ops.ssf_bwd(dpre[1:], dshift=acc['bi'][i], rows_per_batch=N, batch_rows=T, M=B * N)
@@ -631,7 +638,7 @@ class VitEngine:
         ops.wgrad(df1, ev['xraw'], acc['we'], M=B * N, a_rows=(N, T), prec=pr)
         ops.wgrad(df1, ev['patches_hp'], acc['wc'], M=B * N, a_rows=(N, T), prec=pr)
         pg = 'prompt_generator.'
-        out = {pg + 'shared_mlp.weight': acc['ws'][:, :r], pg + 'shared_mlp.bias': acc['bs'],
+        out = {pg + 'shared_mlp.weight': acc['ws'][:, :r], pg + 'shared_mlp.bias': acc['ws'][:, r],
                pg + 'embedding_generator.weight': acc['we'][:r], pg + 'embedding_generator.bias': acc['bf'][:r],
                pg + 'prompt_generator.proj.weight': acc['wc'][:r], pg + 'prompt_generator.proj.bias': acc['bf'][:r]}
         for i in range(len(acc['wi'])):
