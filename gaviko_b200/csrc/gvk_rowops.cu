@@ -1091,34 +1091,162 @@ int ssf_bwd(const gvk_ssf_bwd_params* p, cudaStream_t stream) {
 // ------------------------------------------------------------------------------------------------
 // elementwise dropout (+ residual)
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) dropout_kernel(gvk_dropout_params p) {
-  const uint64_t seed_eff = salted_seed(p.seed, p.seed_salt);
-  const int n4 = p.N / 4;
-  const size_t total = (size_t)p.M * n4;
-  const float inv_keep = 1.0f / (1.0f - p.drop_p);
-  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-    const int m = (int)(i / n4), c = (int)(i - (size_t)m * n4) * 4;
-    float v[4];
-#pragma unroll
-    for (int u = 0; u < 4; ++u) v[u] = ld_dyn(p.x, (size_t)m * p.ldx + c + u, p.x_dtype);
-    const uint64_t e = p.offset + (uint64_t)m * p.N + c;
-    const float2 ma = drop_mult2(seed_eff, e, p.drop_p, inv_keep), mb = drop_mult2(seed_eff, e + 2, p.drop_p, inv_keep);
-    v[0] *= ma.x; v[1] *= ma.y; v[2] *= mb.x; v[3] *= mb.y;
-    if (p.res) {
-#pragma unroll
-      for (int u = 0; u < 4; ++u) v[u] += p.res[(size_t)m * p.ld_res + c + u];
+// Mask rule (include/gvk.h, gvk_dropout_params): element e = offset + m * N + n is kept iff byte (e % 16) of
+// philox4x32-10(counter = (e / 16 low, e / 16 high, 0, 'drop'), key = seed) is < thr = round(256 (1 - drop_p)); kept values are scaled by 256 / thr
+// (the rule of the attention-probability dropout, gvk_mhsa_fwd_params).  One Philox call decides 16 elements, so a pass over an [M, 3072] bf16
+// activation is bound by HBM, not by the integer pipe (the 4-elements-per-call rule of the rank-r kernels cost ~20 instructions per element).
+constexpr uint32_t kDropTag = 0x64726f70u;   // 'drop'
+
+template <typename T>
+__device__ __forceinline__ void drop_ld4(const T* p, bool vec, float (&v)[4]) {
+  if (vec) {
+    if constexpr (sizeof(T) == 4) {
+      const float4 q = *reinterpret_cast<const float4*>(p);
+      v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
+    } else {
+      const uint2 q = *reinterpret_cast<const uint2*>(p);
+      const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&q.x)), b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&q.y));
+      v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
     }
+  } else {
 #pragma unroll
-    for (int u = 0; u < 4; ++u) st_dyn(p.out, (size_t)m * p.ld_out + c + u, p.out_dtype, v[u]);
+    for (int u = 0; u < 4; ++u) v[u] = ld_as_float<T>(p + u);
   }
+}
+template <typename T>
+__device__ __forceinline__ void drop_st4(T* p, bool vec, const float (&v)[4]) {
+  if (vec) {
+    if constexpr (sizeof(T) == 4) {
+      *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+    } else {
+      __nv_bfloat162 lo = __floats2bfloat162_rn(v[0], v[1]), hi = __floats2bfloat162_rn(v[2], v[3]);
+      *reinterpret_cast<uint2*>(p) = make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
+    }
+  } else {
+#pragma unroll
+    for (int u = 0; u < 4; ++u) st_from_float<T>(p + u, v[u]);
+  }
+}
+
+// 4 consecutive elements starting at column c of row m, decided by the 4 bytes of `word`
+template <typename TX, typename TO>
+__device__ __forceinline__ void dropout_quad(const gvk_dropout_params& p, uint32_t word, uint32_t thr, float scale, int m, int c, bool vec) {
+  float v[4];
+  drop_ld4<TX>(reinterpret_cast<const TX*>(p.x) + (size_t)m * p.ldx + c, vec, v);
+#pragma unroll
+  for (int u = 0; u < 4; ++u) v[u] = ((word >> (8 * u)) & 0xFFu) < thr ? v[u] * scale : 0.f;
+  if (p.res) {
+    float r[4];
+    drop_ld4<float>(p.res + (size_t)m * p.ld_res + c, vec, r);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) v[u] += r[u];
+  }
+  drop_st4<TO>(reinterpret_cast<TO*>(p.out) + (size_t)m * p.ld_out + c, vec, v);
+}
+
+template <typename TX, typename TO, bool WIDE>
+__global__ void __launch_bounds__(256) dropout_kernel(gvk_dropout_params p, int vec, uint32_t thr) {
+  const uint64_t seed_eff = salted_seed(p.seed, p.seed_salt);
+  const uint2 key = make_uint2((uint32_t)seed_eff, (uint32_t)(seed_eff >> 32));
+  const float scale = 256.0f / (float)thr;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  if constexpr (WIDE) {      // N % 16 == 0 and offset % 16 == 0: a thread owns a whole 16-element group: one Philox call, 16-byte accesses
+                             // (every lane running its own call is what makes the call cheap per element: a divergent "one lane in four"
+                             // issues the same instructions for a quarter of the work)
+    const uint32_t n16 = p.N / 16;
+    const size_t total = (size_t)p.M * n16;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += stride) {
+      const uint32_t m = (uint32_t)(i / n16), c = (uint32_t)(i - (size_t)m * n16) * 16;
+      const uint64_t ctr = (p.offset + (uint64_t)m * p.N + c) >> 4;
+      const uint4 r = philox4x32(make_uint4((uint32_t)ctr, (uint32_t)(ctr >> 32), 0u, kDropTag), key);
+      const uint32_t words[4] = {r.x, r.y, r.z, r.w};
+      if (vec == 2) {        // 16-byte aligned rows: bf16 travels as two 8-element accesses, fp32 as four 4-element ones
+        float v[16];
+        const TX* x = reinterpret_cast<const TX*>(p.x) + (size_t)m * p.ldx + c;
+        if constexpr (sizeof(TX) == 4) {
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const float4 q = reinterpret_cast<const float4*>(x)[u];
+            v[4 * u] = q.x; v[4 * u + 1] = q.y; v[4 * u + 2] = q.z; v[4 * u + 3] = q.w;
+          }
+        } else {
+#pragma unroll
+          for (int u = 0; u < 2; ++u) {
+            const uint4 q = reinterpret_cast<const uint4*>(x)[u];
+            const uint32_t qq[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&qq[k]));
+              v[8 * u + 2 * k] = f.x; v[8 * u + 2 * k + 1] = f.y;
+            }
+          }
+        }
+#pragma unroll
+        for (int e = 0; e < 16; ++e) v[e] = ((words[e >> 2] >> (8 * (e & 3))) & 0xFFu) < thr ? v[e] * scale : 0.f;
+        if (p.res) {
+          const float4* rs = reinterpret_cast<const float4*>(p.res + (size_t)m * p.ld_res + c);
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const float4 q = rs[u];
+            v[4 * u] += q.x; v[4 * u + 1] += q.y; v[4 * u + 2] += q.z; v[4 * u + 3] += q.w;
+          }
+        }
+        TO* o = reinterpret_cast<TO*>(p.out) + (size_t)m * p.ld_out + c;
+        if constexpr (sizeof(TO) == 4) {
+#pragma unroll
+          for (int u = 0; u < 4; ++u) reinterpret_cast<float4*>(o)[u] = make_float4(v[4 * u], v[4 * u + 1], v[4 * u + 2], v[4 * u + 3]);
+        } else {
+#pragma unroll
+          for (int u = 0; u < 2; ++u) {
+            uint32_t qq[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              __nv_bfloat162 h = __floats2bfloat162_rn(v[8 * u + 2 * k], v[8 * u + 2 * k + 1]);
+              qq[k] = *reinterpret_cast<uint32_t*>(&h);
+            }
+            reinterpret_cast<uint4*>(o)[u] = make_uint4(qq[0], qq[1], qq[2], qq[3]);
+          }
+        }
+      } else {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) dropout_quad<TX, TO>(p, words[u], thr, scale, (int)m, (int)c + 4 * u, vec != 0);
+      }
+    }
+  } else {                   // any N % 4 == 0, offset % 4 == 0: a thread owns 4 elements and takes its word of the group's call
+    const uint32_t n4 = p.N / 4;
+    const size_t total = (size_t)p.M * n4;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += stride) {
+      const uint32_t m = (uint32_t)(i / n4), c = (uint32_t)(i - (size_t)m * n4) * 4;
+      const uint64_t e = p.offset + (uint64_t)m * p.N + c, ctr = e >> 4;
+      const uint4 r = philox4x32(make_uint4((uint32_t)ctr, (uint32_t)(ctr >> 32), 0u, kDropTag), key);
+      const uint32_t q = (uint32_t)(e >> 2) & 3u;
+      dropout_quad<TX, TO>(p, q == 0 ? r.x : q == 1 ? r.y : q == 2 ? r.z : r.w, thr, scale, (int)m, (int)c, vec != 0);
+    }
+  }
+}
+
+template <typename TX, typename TO>
+static void dropout_launch(const gvk_dropout_params* p, int vec, uint32_t thr, cudaStream_t stream) {
+  const bool wide = p->N % 16 == 0 && (p->offset & 15) == 0;
+  const size_t total = (size_t)p->M * (p->N / (wide ? 16 : 4));
+  const int grid = (int)std::max<size_t>(1, std::min<size_t>((total + 255) / 256, (size_t)sm_count() * 16));
+  if (wide) dropout_kernel<TX, TO, true><<<grid, 256, 0, stream>>>(*p, vec, thr);
+  else dropout_kernel<TX, TO, false><<<grid, 256, 0, stream>>>(*p, vec, thr);
 }
 
 int dropout(const gvk_dropout_params* p, cudaStream_t stream) {
   GVK_CHECK_ARG(p && p->x && p->out && p->M > 0 && p->N > 0 && p->N % 4 == 0, "gvk_dropout: bad argument (N %% 4 == 0)");
   GVK_CHECK_ARG(p->drop_p >= 0.f && p->drop_p < 1.f && (p->offset & 3) == 0, "gvk_dropout: drop_p in [0,1), offset %% 4 == 0");
-  const size_t total = (size_t)p->M * (p->N / 4);
-  const int grid = (int)std::min<size_t>((total + 255) / 256, (size_t)sm_count() * 16);
-  dropout_kernel<<<grid, 256, 0, stream>>>(*p);
+  GVK_CHECK_ARG((p->x_dtype == GVK_F32 || p->x_dtype == GVK_BF16) && (p->out_dtype == GVK_F32 || p->out_dtype == GVK_BF16), "gvk_dropout: dtypes must be GVK_F32 / GVK_BF16");
+  const uint32_t thr = (uint32_t)std::min(256, std::max(1, (int)(256.0f * (1.0f - p->drop_p) + 0.5f)));
+  auto al = [](const void* q, int dtype, int ld) { return (reinterpret_cast<uintptr_t>(q) & (dtype == GVK_F32 ? 15 : 7)) == 0 && ld % 4 == 0; };
+  int vec = al(p->x, p->x_dtype, p->ldx) && al(p->out, p->out_dtype, p->ld_out) && (!p->res || al(p->res, GVK_F32, p->ld_res));
+  auto al16 = [](const void* q, int dtype, int ld) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0 && ld % (dtype == GVK_F32 ? 4 : 8) == 0; };
+  if (vec && al16(p->x, p->x_dtype, p->ldx) && al16(p->out, p->out_dtype, p->ld_out)) vec = 2;      // 16-byte rows on both sides (res: fp32, already 16-byte)
+  if (p->x_dtype == GVK_F32 && p->out_dtype == GVK_F32) dropout_launch<float, float>(p, vec, thr, stream);
+  else if (p->x_dtype == GVK_F32) dropout_launch<float, __nv_bfloat16>(p, vec, thr, stream);
+  else if (p->out_dtype == GVK_F32) dropout_launch<__nv_bfloat16, float>(p, vec, thr, stream);
+  else dropout_launch<__nv_bfloat16, __nv_bfloat16>(p, vec, thr, stream);
   GVK_CHECK_LAUNCH("dropout");
   return GVK_OK;
 }

@@ -218,7 +218,10 @@ typedef struct {
 int gvk_ssf_bwd(const gvk_ssf_bwd_params* p, gvk_stream_t stream);
 
 /* out = res + dropout(x) elementwise over an [M, N] matrix (x / out in `dtype`, res optional fp32 [M, N] with out then fp32... see below).
- * Replayable mask: element (m, n) kept iff philox(seed, offset + m * N + n) >= drop_p, scaled by 1 / (1 - drop_p).  N % 4 == 0.
+ * Replayable mask: element e = offset + m * N + n is kept iff byte (e % 16) of philox4x32-10(counter = (e / 16 low, e / 16 high, 0, 'drop'),
+ * key = seed [+ seed_salt]) is < thr = round(256 (1 - drop_p)); kept values are scaled by 256 / thr (unbiased for the drop probability
+ * actually applied, 1 - thr / 256 — the rule of the attention-probability dropout).  One Philox call decides 16 elements, which keeps the
+ * pass HBM-bound.  N % 4 == 0, offset % 4 == 0.  (The rank-r kernels keep their own rule: one 32-bit word per element.)
  * x_dtype / out_dtype in {GVK_F32, GVK_BF16}; res (optional) is fp32.  Used for the nn.Dropout sites of the un-frozen train mode
  * (model/vision_transformer.py:33,35,58 and :157) and, applied to gradients with the same seed, for their backward. */
 typedef struct {

@@ -115,3 +115,27 @@ def mhsa_keep_mask(B, H, T, drop_p, seed):
     bytes_ = np.stack([(words >> np.uint64(8 * b)) & np.uint64(0xFF) for b in range(4)], -1)   # [..., word, byte]
     keep = (bytes_.reshape(B * H, T, n16 * 16) < thr)[:, :, :T]
     return torch.from_numpy(keep.reshape(B, H, T, T)), 256.0 / thr
+
+
+def elementwise_keep_mask(M, N, drop_p, seed, offset=0):
+    """Host restatement of the replayable mask of gvk_dropout (include/gvk.h, gvk_dropout_params): element (m, n) with linear index
+    e = offset + m * N + n is kept iff byte (e % 16) of philox4x32-10(counter = (e // 16 low, e // 16 high, 0, 'drop'), key = seed) is
+    < thr = round(256 (1 - drop_p)); kept values are scaled by 256 / thr.  Returns (keep bool [M, N], scale)."""
+    thr = min(256, max(1, int(256.0 * (1.0 - drop_p) + 0.5)))
+    e = np.uint64(offset) + np.arange(M * N, dtype=np.uint64)
+    ctr = e >> np.uint64(4)
+    MASK = np.uint64(0xFFFFFFFF)
+    x, y = ctr & MASK, ctr >> np.uint64(32)
+    z, w = np.zeros_like(x), np.full_like(x, 0x64726f70)
+    k0, k1 = np.uint64(seed & 0xFFFFFFFF), np.uint64((seed >> 32) & 0xFFFFFFFF)
+    M0, M1, W0, W1 = np.uint64(0xD2511F53), np.uint64(0xCD9E8D57), np.uint64(0x9E3779B9), np.uint64(0xBB67AE85)
+    for _ in range(10):
+        p0, p1 = M0 * x, M1 * z
+        hi0, lo0, hi1, lo1 = p0 >> np.uint64(32), p0 & MASK, p1 >> np.uint64(32), p1 & MASK
+        x, y, z, w = hi1 ^ y ^ k0, lo1, hi0 ^ w ^ k1, lo0
+        k0, k1 = (k0 + W0) & MASK, (k1 + W1) & MASK
+    words = np.stack([x, y, z, w], -1)
+    idx = (e & np.uint64(15)).astype(np.int64)
+    word = words[np.arange(M * N), idx // 4]
+    byte = (word >> (np.uint64(8) * (idx % 4).astype(np.uint64))) & np.uint64(0xFF)
+    return torch.from_numpy((byte < thr).reshape(M, N)), 256.0 / thr

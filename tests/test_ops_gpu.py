@@ -525,3 +525,34 @@ def test_evp_hfreq_filter_matches_reference_fft(shape, rate):
     ref = O.evp_highpass(img.cpu(), rate)
     assert (out.cpu() - ref).abs().max().item() < 5e-6
     assert ExplicitVisualPrompting is not None
+
+
+@pytest.mark.parametrize('dt_in,dt_out,with_res', [(torch.float32, torch.float32, False), (torch.bfloat16, torch.bfloat16, False), (torch.float32, torch.float32, True),
+                                                   (torch.bfloat16, torch.float32, True)])
+def test_elementwise_dropout_mask_rule_and_views(dt_in, dt_out, with_res):
+    """gvk_dropout (the nn.Dropout sites of model/vision_transformer.py:33,35,58,157 in the un-frozen train mode): out = res + x * mask with the mask
+    rule of include/gvk.h restated on the host (helpers.elementwise_keep_mask): 16-element groups (one Philox call each), the 4-element path
+    (N or offset not a multiple of 16: same rule, same mask), contiguous tensors (vector accesses) and odd-offset column views (scalar accesses)."""
+    from helpers import elementwise_keep_mask
+    torch.manual_seed(11)
+    p, seed = 0.3, 0x1234567890ABCDEF & ((1 << 63) - 1)
+    for M, N, off in ((203, 192, 16), (203, 192, 8), (57, 72, 4), (64, 3072, 0)):
+        x = torch.randn(M, N, device=DEV).to(dt_in)
+        res = torch.randn(M, N, device=DEV) if with_res else None
+        keep, scale = elementwise_keep_mask(M, N, p, seed, off)
+        keep = keep.to(DEV)
+        tol = 1e-6 if dt_out == torch.float32 else 1e-2
+        ref = x.float() * keep * scale + (res if with_res else 0)
+        out = ops.dropout(x, p, seed, res=res, out_dtype=dt_out, offset=off)
+        assert out.dtype == dt_out
+        close(out, ref.to(dt_out), tol)
+        assert abs(keep.float().mean().item() - (1 - p)) < 0.03
+        # unaligned views: columns 1 .. of a wider input, columns 3 .. of a wider output (pointers off the 16-byte grid, odd leading dimensions)
+        wide = torch.randn(M, N + 5, device=DEV).to(dt_in)
+        xv = wide[:, 1:1 + N]
+        out2 = torch.empty(M, N + 3, device=DEV, dtype=dt_out)[:, 3:3 + N]
+        ops.dropout(xv, p, seed, res=res, out=out2, offset=off)
+        close(out2, (xv.float() * keep * scale + (res if with_res else 0)).to(dt_out), tol)
+    # replay: the same (seed, offset) gives the same mask, another seed another one
+    a = ops.dropout(torch.ones(64, 768, device=DEV), p, seed)
+    assert torch.equal(a, ops.dropout(torch.ones(64, 768, device=DEV), p, seed)) and not torch.equal(a, ops.dropout(torch.ones(64, 768, device=DEV), p, seed + 1))
