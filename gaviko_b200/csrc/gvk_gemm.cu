@@ -83,7 +83,10 @@ __device__ __forceinline__ void epi_elem(const EpiArgs& e, int m, int n, float v
 // global access is a contiguous 128 B (fp32) / 64 B (bf16) row segment.  Loads the epilogue depends on (residual, saved GELU
 // pre-activation) are issued before the TMEM wait so their latency overlaps it.
 // -------------------------------------------------------------------------------------------------
-enum { EPI_GENERIC = 0, EPI_STORE_BF16 = 1, EPI_BIAS_GELU_BF16 = 2, EPI_BIAS_RES_F32 = 3, EPI_GELU_BWD_BF16 = 4, EPI_STORE_F32 = 5, EPI_BIAS_GELU_SAVEGRAD_BF16 = 6, EPI_MUL_AUX_BF16 = 7 };
+enum { EPI_GENERIC = 0, EPI_STORE_BF16 = 1, EPI_BIAS_GELU_BF16 = 2, EPI_BIAS_RES_F32 = 3, EPI_GELU_BWD_BF16 = 4, EPI_STORE_F32 = 5, EPI_BIAS_GELU_SAVEGRAD_BF16 = 6, EPI_MUL_AUX_BF16 = 7,
+       EPI_BIAS_BF16 = 8, EPI_BIAS_F32 = 9 };   // 8 / 9: bias only (SSF sites folded into the weights, Linear outputs that feed a separate dropout)
+template <int EPI>
+constexpr bool kEpiBias = (EPI == EPI_BIAS_GELU_BF16 || EPI == EPI_BIAS_RES_F32 || EPI == EPI_BIAS_GELU_SAVEGRAD_BF16 || EPI == EPI_BIAS_BF16 || EPI == EPI_BIAS_F32);
 
 // Standard-normal CDF Phi(x) = 0.5 (1 + erf(x / sqrt 2)) with |abs err| < 2e-7 (Abramowitz-Stegun 7.1.26), branch-free:
 // rcp.approx + ex2.approx + 7 fma/mul + select.  Also returns e = exp(-x^2 / 2) for the GELU derivative.  Used only on the bf16
@@ -221,7 +224,7 @@ __device__ __forceinline__ void epilogue_patch_fast(const EpiArgs& e, uint32_t t
   const int sr = lane >> 3, cv = lane & 7;  // sub-row 0..3, 4-column vector 0..7
   const int col = col0 + cv * 4;
   float4 bias = make_float4(0.f, 0.f, 0.f, 0.f);
-  if constexpr (EPI == EPI_BIAS_GELU_BF16 || EPI == EPI_BIAS_RES_F32 || EPI == EPI_BIAS_GELU_SAVEGRAD_BF16) bias = *reinterpret_cast<const float4*>(e.bias + col);
+  if constexpr (kEpiBias<EPI>) bias = *reinterpret_cast<const float4*>(e.bias + col);
   // ---- TMEM -> registers (thread = row) -> swizzled smem  (loading the next patch's accumulator during this one's math was tried: no gain)
   float v[32];
   tmem_ld_32x32(taddr, v);
@@ -240,7 +243,7 @@ __device__ __forceinline__ void epilogue_patch_fast(const EpiArgs& e, uint32_t t
     float4 x = reinterpret_cast<const float4*>(patch)[r * 8 + (cv ^ (r & 7))];
     const bool live = m < M;   // rows past M are computed like any other and only their stores are predicated: a `continue` here put a
                                // branch between the eight unrolled iterations and kept the scheduler from interleaving their math
-    if constexpr (EPI == EPI_BIAS_GELU_BF16 || EPI == EPI_BIAS_RES_F32 || EPI == EPI_BIAS_GELU_SAVEGRAD_BF16) {
+    if constexpr (kEpiBias<EPI>) {
       x.x += bias.x; x.y += bias.y; x.z += bias.z; x.w += bias.w;
     }
     if constexpr (EPI == EPI_BIAS_GELU_SAVEGRAD_BF16) {
@@ -268,7 +271,7 @@ __device__ __forceinline__ void epilogue_patch_fast(const EpiArgs& e, uint32_t t
       x.x += res[it].x; x.y += res[it].y; x.z += res[it].z; x.w += res[it].w;
     }
     if (live) {
-      if constexpr (EPI == EPI_BIAS_RES_F32 || EPI == EPI_STORE_F32) {
+      if constexpr (EPI == EPI_BIAS_RES_F32 || EPI == EPI_STORE_F32 || EPI == EPI_BIAS_F32) {
         *reinterpret_cast<float4*>(reinterpret_cast<float*>(e.out) + (size_t)m * e.ld_out + col) = x;
       } else {
         *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(e.out) + (size_t)m * e.ld_out + col) = float4_to_bf16x4(x);
@@ -569,6 +572,7 @@ int gemm_dispatch(const gvk_gemm_params* p, cudaStream_t stream) {
       else if (!p->bias && p->act == GVK_ACT_GELU_BWD && !p->res1 && p->out_dtype == GVK_BF16 && p->aux && aux_ok) epi = EPI_GELU_BWD_BF16;
       else if (bias_ok && p->act == GVK_ACT_GELU_SAVE_GRAD && !p->res1 && p->out_dtype == GVK_BF16 && aux_ok) epi = EPI_BIAS_GELU_SAVEGRAD_BF16;
       else if (!p->bias && p->act == GVK_ACT_MUL_AUX && !p->res1 && p->out_dtype == GVK_BF16 && p->aux && aux_ok) epi = EPI_MUL_AUX_BF16;
+      else if (bias_ok && p->act == GVK_ACT_NONE && !p->res1 && !p->aux) epi = p->out_dtype == GVK_BF16 ? EPI_BIAS_BF16 : EPI_BIAS_F32;
     }
 #define GVK_GEMM_CASE(E)                                               \
   case E:                                                              \
@@ -582,6 +586,8 @@ int gemm_dispatch(const gvk_gemm_params* p, cudaStream_t stream) {
       GVK_GEMM_CASE(EPI_STORE_F32)
       GVK_GEMM_CASE(EPI_BIAS_GELU_SAVEGRAD_BF16)
       GVK_GEMM_CASE(EPI_MUL_AUX_BF16)
+      GVK_GEMM_CASE(EPI_BIAS_BF16)
+      GVK_GEMM_CASE(EPI_BIAS_F32)
       default:
         GVK_GEMM_CASE(EPI_GENERIC)
     }

@@ -109,6 +109,13 @@ class FlatAdam(torch.optim.Optimizer):
         self._realias(gather=True)
         with torch.cuda.device(self.flat_p.device):
             self._step()
+        # The update kernel writes the flat buffer behind autograd's back: bump the version counters of the parameters, so that whatever an engine
+        # caches on (data_ptr, _version) of a TRAINABLE tensor (stacked LoRA factors, SSF scales folded into GEMM operands) is rebuilt next forward
+        try:
+            torch._C._increment_version(self._params)
+        except (AttributeError, TypeError):      # private entry point moved: an in-place no-op bumps the counter as well
+            for q in self._params:
+                q.add_(0)
 
     def _step(self):
         scale = exchange_flat_gradient(self.flat_g, self.group) if self.world > 1 else 1.0   # SUM; the 1/world mean is folded into grad_scale

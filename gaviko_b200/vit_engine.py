@@ -172,6 +172,19 @@ class VitEngine:
                                  a2=(vec(('sa2s', i), a.ssf_scale_2), vec(('sa2h', i), a.ssf_shift_2)), f0=(vec(('sf0s', i), f.ssf_scale_0), vec(('sf0h', i), f.ssf_shift_0)),
                                  f1=(vec(('sf1s', i), f.ssf_scale_1), vec(('sf1h', i), f.ssf_shift_1)), f2=(vec(('sf2s', i), f.ssf_scale_2), vec(('sf2h', i), f.ssf_shift_2)))
                 Lw['n'].update({k: (p_ + f'ssf_scale_{k[1]}', p_ + f'ssf_shift_{k[1]}') for k, p_ in (('a0', pa), ('a1', pa), ('a2', pa), ('f0', pf), ('f1', pf), ('f2', pf))})
+                if cdt != torch.float32:
+                    # bf16 mode: the SSF site behind a Linear folds into its operands, (x W^T + b) s + t = x (diag(s) W)^T + (b s + t), so the GEMM keeps
+                    # a compile-time epilogue (bias [+ GELU]) instead of the generic one (4.5x slower on fc1).  The scales train: rebuilt when
+                    # their version changes (torch's optimisers bump it; FlatAdam.step does so explicitly).  Backward is unchanged: it recovers
+                    # the site's input from its saved output (ops.ssf_bwd) and runs the dgrad GEMM on the unscaled transposed weight.
+                    def fold(key, wsrc, bsrc, site):
+                        sc, sh = getattr(site[0], f'ssf_scale_{site[1]}'), getattr(site[0], f'ssf_shift_{site[1]}')
+                        tag = (sc.data_ptr(), sc._version, sh.data_ptr(), sh._version, None if bsrc is None else (bsrc.data_ptr(), bsrc._version))
+                        wf = cache.get((key, 'ssf_w', i, cdt), wsrc, lambda t: (t.float() * sc.detach().float()[:, None]).to(cdt).contiguous(), extra=tag)
+                        bf = cache.get((key, 'ssf_b', i), wsrc, lambda t: ((0 if bsrc is None else bsrc.detach().float() * sc.detach().float()) + sh.detach().float()).contiguous(), extra=tag)
+                        return wf, bf
+                    Lw['fold'] = dict(a1=fold('wqkv', qkv_lin.weight, None, (a, 1)), a2=fold('wo', a.to_out[0].weight, a.to_out[0].bias, (a, 2)),
+                                      f1=fold('w1', f.net[1].weight, f.net[1].bias, (f, 1)), f2=fold('w2', f.net[4].weight, f.net[4].bias, (f, 2)))
             if lora:
                 r, s = qkv_mod.r, float(qkv_mod.alpha // qkv_mod.r)
                 Aq, Av, Bq, Bv = qkv_mod.linear_a_q.weight, qkv_mod.linear_a_v.weight, qkv_mod.linear_b_q.weight, qkv_mod.linear_b_v.weight
@@ -305,11 +318,16 @@ class VitEngine:
                 st['lora_z'] = z
                 del qkv32
             else:
-                qkv = ops.gemm(h1, Lw['wqkv'], ssf_scale=s_a1[0], ssf_shift=s_a1[1], out_dtype=cdt)
+                fo = Lw.get('fold')
+                if fo is not None:
+                    qkv = ops.gemm(h1, fo['a1'][0], bias=fo['a1'][1], out_dtype=cdt)
+                else:
+                    qkv = ops.gemm(h1, Lw['wqkv'], ssf_scale=s_a1[0], ssf_shift=s_a1[1], out_dtype=cdt)
             del h1
             o, lse = self._attention(qkv, B, T, H, D, H * D, p_attn, seeds[0])
             if ssf or p_out > 0:
-                y_a = ops.gemm(o, Lw['wo'], bias=Lw['bo'], ssf_scale=s_a2[0], ssf_shift=s_a2[1])
+                fo = Lw.get('fold')
+                y_a = ops.gemm(o, fo['a2'][0], bias=fo['a2'][1]) if fo is not None else ops.gemm(o, Lw['wo'], bias=Lw['bo'], ssf_scale=s_a2[0], ssf_shift=s_a2[1])
                 x_mid = ops.dropout(y_a, p_out, seeds[1], res=x, out_dtype=torch.float32)
                 st['y_a'] = y_a if ssf else None
             else:
@@ -320,14 +338,18 @@ class VitEngine:
             # Without an SSF site behind fc1 the backward needs only gelu'(pre): the forward epilogue saves the derivative (it shares the transcendental
             # with the activation) and the dgrad epilogue is one multiply instead of an erf.  SSF (model/ssf.py:77-80) needs the pre-activation itself.
             save_grad = save and 'f1' not in sa
-            act = ops.gemm(h2, Lw['w1'], bias=Lw['b1'], ssf_scale=s_f1[0], ssf_shift=s_f1[1], act=ops.ACT_GELU_SAVE_GRAD if save_grad else ops.ACT_GELU,
-                           aux=hpre, out_dtype=cdt)
+            fo = Lw.get('fold')
+            if fo is not None:
+                act = ops.gemm(h2, fo['f1'][0], bias=fo['f1'][1], act=ops.ACT_GELU, aux=hpre, out_dtype=cdt)
+            else:
+                act = ops.gemm(h2, Lw['w1'], bias=Lw['b1'], ssf_scale=s_f1[0], ssf_shift=s_f1[1], act=ops.ACT_GELU_SAVE_GRAD if save_grad else ops.ACT_GELU,
+                               aux=hpre, out_dtype=cdt)
             st['gelu_grad_saved'] = save_grad
             del h2
             if p_ff1 > 0:
                 act = ops.dropout(act, p_ff1, seeds[2])
             if ssf or p_ff2 > 0:
-                y_f = ops.gemm(act, Lw['w2'], bias=Lw['b2'], ssf_scale=s_f2[0], ssf_shift=s_f2[1])
+                y_f = ops.gemm(act, fo['f2'][0], bias=fo['f2'][1]) if fo is not None else ops.gemm(act, Lw['w2'], bias=Lw['b2'], ssf_scale=s_f2[0], ssf_shift=s_f2[1])
                 x_out = ops.dropout(y_f, p_ff2, seeds[3], res=x_mid, out_dtype=torch.float32)
                 st['y_f'] = y_f if ssf else None
             else:

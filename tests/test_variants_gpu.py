@@ -153,3 +153,35 @@ def test_evp_vitb_full_shape_on_reference_init(mode, tol, tol_t):
         grads = {n: p.grad for n, p in model.named_parameters() if p.requires_grad}
         glob, worst, wname = grad_parity(grads, g, loss_name, tol_global=tol, tol_tensor=tol_t, floor=1e-3, floor_slack=2.0)
         print(f'evp_b16_full_init {mode} {loss_name}: logits rel {rl:.2e} grads global {glob:.2e} worst {worst:.2e} ({wname})')
+
+
+@pytest.mark.parametrize('name', ['melo_t16_small', 'ssf_t16_small'])
+def test_flat_adam_steps_refresh_operands_cached_on_trainable_tensors(name, tmp_path):
+    """FlatAdam updates the parameters with its own kernel, behind autograd's version counters; the engines cache operands derived from TRAINABLE
+    tensors on (data_ptr, _version) — the stacked, scaled LoRA factors of MeLO, the SSF scales folded into the bf16 GEMM operands.  After optimiser
+    steps those operands must follow the parameters (a stale cache would keep training on step-0 values)."""
+    from gaviko_b200.optim import FlatAdam
+    model, img, y = _build(name, 'bf16', tmp_path)
+    model.train()
+    opt = FlatAdam([p for p in model.parameters() if p.requires_grad], lr=1e-2, model=model)
+    crit = CrossEntropyLoss()
+    for _ in range(3):
+        loss = crit(model(img), y)
+        opt.zero_grad()
+        loss.backward()
+        opt.step()
+    eng = model._engine
+    W = eng._weights(eng.compute_dtype())
+    if name.startswith('melo'):
+        q = eng.vt.transformer.layers[0][0].to_qkv
+        s = float(q.alpha // q.r)
+        want = s * torch.cat([q.linear_a_q.weight.detach().float(), q.linear_a_v.weight.detach().float()], 0)
+        got = W['layers'][0]['lora']['sa_stack']
+    else:
+        a = eng.vt.transformer.layers[0][0]
+        want = (a.to_qkv.weight.detach().float() * a.ssf_scale_1.detach().float()[:, None]).bfloat16().float()
+        got = W['layers'][0]['fold']['a1'][0].float()
+    assert torch.equal(got, want), (got - want).abs().max().item()
+    # and the parameters did move
+    moved = [n for n, p in model.named_parameters() if p.requires_grad and p.grad is not None]
+    assert moved
