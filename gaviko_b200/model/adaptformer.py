@@ -41,19 +41,23 @@ class Adapter(_Container):
 class Transformer(_Container):
     """layers.{i} = [Attention, Adapter, FeedForward] (reference adaptformer.py:81-99)."""
 
-    def __init__(self, dim, depth, heads, dim_head, mlp_dim, dropout=0.):
+    def __init__(self, dim, depth, heads, dim_head, mlp_dim, dropout=0., adapter_dim=64):
         super().__init__()
         self.norm = nn.LayerNorm(dim)
         self.layers = nn.ModuleList([])
         for _ in range(depth):
-            self.layers.append(nn.ModuleList([Attention(dim, heads=heads, dim_head=dim_head, dropout=dropout), Adapter(dim),
+            self.layers.append(nn.ModuleList([Attention(dim, heads=heads, dim_head=dim_head, dropout=dropout), Adapter(dim, down_dim=adapter_dim),
                                               FeedForward(dim, mlp_dim, dropout=dropout)]))
 
 
 class AdaptFormer(nn.Module):
     def __init__(self, *, image_size, image_patch_size, frames, frame_patch_size, num_classes, pool='cls', channels=3, dim_head=64,
-                 dropout=0., emb_dropout=0., backbone=None, freeze_vit=False, compute_dtype=None, **kwargs):
+                 dropout=0., emb_dropout=0., backbone=None, freeze_vit=False, compute_dtype=None, adapter_dim=64, **kwargs):
+        """adapter_dim: bottleneck width (the reference hard-wires 64, adaptformer.py:89; an optional kwarg here for the adapter-rank sweep of
+        BASELINE.json's config 4 — the default reproduces the reference, which ignores unknown kwargs).  Multiples of 4 up to 64."""
         super().__init__()
+        if adapter_dim % 4 != 0 or not 4 <= adapter_dim <= 64:
+            raise ValueError('adapter_dim must be a multiple of 4 in [4, 64]')
         depth, heads, dim, mlp_dim = mapping_vit(backbone)
         image_height, image_width = pair(image_size)
         patch_height, patch_width = pair(image_patch_size)
@@ -71,7 +75,7 @@ class AdaptFormer(nn.Module):
         self.pos_embedding = nn.Parameter(torch.randn(1, num_patches + 1, dim))
         self.cls_token = nn.Parameter(torch.randn(1, 1, dim))
         self.dropout = nn.Dropout(emb_dropout)
-        self.transformer = Transformer(dim, depth, heads, dim_head, mlp_dim, dropout)
+        self.transformer = Transformer(dim, depth, heads, dim_head, mlp_dim, dropout, adapter_dim=adapter_dim)
         self.pool = pool
         self.to_latent = nn.Identity()
         self.mlp_head = nn.Linear(dim, num_classes)

@@ -197,6 +197,14 @@ class VitEngine:
                                   bq=_f32(Bq), bv=_f32(Bv),
                                   sbq=cache.get(('lorasBq', i), Bq, lambda t: (s * t.float()).contiguous()),
                                   sbv=cache.get(('lorasBv', i), Bv, lambda t: (s * t.float()).contiguous()))
+                if cdt == torch.bfloat16 and 6 * r <= 128:
+                    # bf16 mode: the LoRA update rides on the qkv GEMM as a K-extension (the scheme of GAViKO's prompt up-projection, engine.py): operand
+                    # [LN1(x) | z] with z = s A LN1(x) in three 2r-wide hi / lo bf16 slots, weight [W_qkv | B] with B_q on the q rows, B_v on the v
+                    # rows (hi*hi + lo*hi + hi*lo keeps ~16 mantissa bits).  The frozen part is cached; the forward rewrites the B columns every call
+                    kext = 64 if 6 * r <= 64 else 128
+                    Lw['lora']['kext'] = kext
+                    Lw['lora']['wqkv_x'] = cache.get((('wqkvx', i, kext), cdt), qkv_lin.weight,
+                                                     lambda t: torch.cat([t.to(cdt), torch.zeros(t.shape[0], kext, device=t.device, dtype=cdt)], 1).contiguous())
                 pq = pa + 'to_qkv.'
                 Lw['n'].update(aq=pq + 'linear_a_q.weight', av=pq + 'linear_a_v.weight', bq=pq + 'linear_b_q.weight', bv=pq + 'linear_b_v.weight')
             if ad is not None:
@@ -306,24 +314,39 @@ class VitEngine:
             p_attn, p_out, p_ff1, p_ff2 = _p(Lw['drop_attn']), _p(Lw['drop_out']), _p(Lw['drop_ff1']), _p(Lw['drop_ff2'])
             seeds = [self._seed(i, k) for k in range(4)]
             # ---- attention (model/vision_transformer.py:60-72)
-            h1, mean1, rstd1 = ops.layernorm_fwd(x, Lw['ln1_w'], Lw['ln1_b'], out_dtype=cdt, ssf_scale=s_a0[0], ssf_shift=s_a0[1], save_stats=save)
             lo = Lw.get('lora')
-            if lo is not None:
-                qkv32 = ops.gemm(h1, Lw['wqkv'])
+            if lo is not None and 'wqkv_x' in lo:
+                # MeLO, bf16 mode: q / v updates B (s A LN1(x)) as a K-extension of the qkv GEMM (see _weights)
+                r, kext = lo['r'], lo['kext']
+                h1x = torch.empty((B * T, dim + kext), device=img.device, dtype=cdt)
+                _, mean1, rstd1 = ops.layernorm_fwd(x, Lw['ln1_w'], Lw['ln1_b'], out=h1x[:, :dim], save_stats=save)
                 z = ops.rowproj_down(x, lo['sa_stack'], ln=(Lw['ln1_w'], Lw['ln1_b']), prec=pr)['z']          # [M, 2r] = s * A LN1(x)
-                r = lo['r']
-                ops.rowproj_up(z[:, :r], lo['bq'], res=qkv32[:, :dim], out=qkv32[:, :dim], prec=pr)           # q += B_q (s A_q x)
-                ops.rowproj_up(z[:, r:], lo['bv'], res=qkv32[:, 2 * dim:], out=qkv32[:, 2 * dim:], prec=pr)  # v += B_v (s A_v x)
-                qkv = ops.cast_bf16(qkv32) if lp else qkv32
+                bfull = torch.zeros((3 * dim, 2 * r), device=img.device, dtype=torch.float32)                # placement of the two up factors: plumbing
+                bfull[:dim, :r] = lo['bq']
+                bfull[2 * dim:, r:] = lo['bv']
+                ops.split_pack_bf16(z, h1x[:, dim:], 0b010)                  # (hi, lo, hi)
+                ops.split_pack_bf16(bfull, lo['wqkv_x'][:, dim:], 0b100)     # (hi, hi, lo)
+                qkv = ops.gemm(h1x, lo['wqkv_x'], out_dtype=cdt)
                 st['lora_z'] = z
-                del qkv32
+                del h1x
             else:
-                fo = Lw.get('fold')
-                if fo is not None:
-                    qkv = ops.gemm(h1, fo['a1'][0], bias=fo['a1'][1], out_dtype=cdt)
+                h1, mean1, rstd1 = ops.layernorm_fwd(x, Lw['ln1_w'], Lw['ln1_b'], out_dtype=cdt, ssf_scale=s_a0[0], ssf_shift=s_a0[1], save_stats=save)
+                if lo is not None:
+                    qkv32 = ops.gemm(h1, Lw['wqkv'])
+                    z = ops.rowproj_down(x, lo['sa_stack'], ln=(Lw['ln1_w'], Lw['ln1_b']), prec=pr)['z']          # [M, 2r] = s * A LN1(x)
+                    r = lo['r']
+                    ops.rowproj_up(z[:, :r], lo['bq'], res=qkv32[:, :dim], out=qkv32[:, :dim], prec=pr)           # q += B_q (s A_q x)
+                    ops.rowproj_up(z[:, r:], lo['bv'], res=qkv32[:, 2 * dim:], out=qkv32[:, 2 * dim:], prec=pr)  # v += B_v (s A_v x)
+                    qkv = ops.cast_bf16(qkv32) if lp else qkv32
+                    st['lora_z'] = z
+                    del qkv32
                 else:
-                    qkv = ops.gemm(h1, Lw['wqkv'], ssf_scale=s_a1[0], ssf_shift=s_a1[1], out_dtype=cdt)
-            del h1
+                    fo = Lw.get('fold')
+                    if fo is not None:
+                        qkv = ops.gemm(h1, fo['a1'][0], bias=fo['a1'][1], out_dtype=cdt)
+                    else:
+                        qkv = ops.gemm(h1, Lw['wqkv'], ssf_scale=s_a1[0], ssf_shift=s_a1[1], out_dtype=cdt)
+                del h1
             o, lse = self._attention(qkv, B, T, H, D, H * D, p_attn, seeds[0])
             if ssf or p_out > 0:
                 fo = Lw.get('fold')
@@ -473,8 +496,10 @@ class VitEngine:
             dz = None
             if lo is not None:
                 r = lo['r']
-                d32 = ops.cast_f32(dqkv) if lp else dqkv
-                dq, dv, z = d32[:, :dim], d32[:, 2 * dim:], st['lora_z']
+                # only the q and v column blocks feed the LoRA factors (model/melo.py:41-47): the rank-r kernels read fp32, so those two blocks are cast
+                dq = ops.cast_f32(dqkv[:, :dim]) if lp else dqkv[:, :dim]
+                dv = ops.cast_f32(dqkv[:, 2 * dim:]) if lp else dqkv[:, 2 * dim:]
+                z = st['lora_z']
                 if g(n_['bq']) is not None:
                     ops.skinny_wgrad(z[:, :r], dq, dw=g(n_['bq']), dw_layout='dr', prec=pr)
                 if g(n_['bv']) is not None:
@@ -486,7 +511,7 @@ class VitEngine:
                     ops.skinny_wgrad(dz[:, :r], st['x_in'], dw=g(n_['aq']), dw_layout='rd', ln=ln, prec=pr)
                 if g(n_['av']) is not None:
                     ops.skinny_wgrad(dz[:, r:], st['x_in'], dw=g(n_['av']), dw_layout='rd', ln=ln, prec=pr)
-                del d32
+                del dq, dv
             dH1 = ops.gemm(dqkv, Lw['wqkv_t'])
             del dqkv
             a0 = sa.get('a0')

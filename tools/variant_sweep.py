@@ -14,7 +14,8 @@ FULL = dict(image_size=160, image_patch_size=16, frames=120, frame_patch_size=12
             dropout=0.1, emb_dropout=0.1, compute_dtype='bf16')       # the reference configs' dropout: active in train mode for linear / bitfit / melo
 FZ = dict(FULL, freeze_vit=True)
 VPT = dict(FZ, prompt_dropout=0.1, prompt_dim=64)
-CASES = [('linear', FULL), ('bitfit', FULL), ('ssf', FZ), ('adaptformer', FZ), ('melo', dict(FULL, r=4, alpha=8)), ('melo', dict(FULL, r=8, alpha=16)),
+CASES = [('linear', FULL), ('bitfit', FULL), ('ssf', FZ), ('adaptformer', dict(FZ, adapter_dim=8)), ('adaptformer', dict(FZ, adapter_dim=16)), ('adaptformer', dict(FZ, adapter_dim=32)),
+         ('adaptformer', dict(FZ, adapter_dim=64)), ('melo', dict(FULL, r=4, alpha=8)), ('melo', dict(FULL, r=8, alpha=16)),
          ('melo', dict(FULL, r=16, alpha=32)), ('shallow_vpt', dict(VPT, num_prompts=32, deep_prompt=False)), ('deep_vpt', dict(VPT, num_prompts=8, deep_prompt=True)),
          ('deep_vpt', dict(VPT, num_prompts=32, deep_prompt=True)), ('deep_vpt', dict(VPT, num_prompts=64, deep_prompt=True)),
          ('deep_vpt', dict(VPT, num_prompts=100, deep_prompt=True)), ('dvpt', dict(FZ, num_prompts=32)),
@@ -41,7 +42,7 @@ for method, extra in CASES:
         e1.record(); torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / a.steps
         ntr = sum(p.numel() for p in m.parameters() if p.requires_grad)
-        rows.append(dict(method=method, **{k: v for k, v in extra.items() if k in ('r', 'num_prompts', 'deep_prompt', 'scale_factor')}, ms_per_step=round(ms, 2), volumes_per_s=round(a.batch / ms * 1e3, 1), trainable=ntr))
+        rows.append(dict(method=method, **{k: v for k, v in extra.items() if k in ('r', 'num_prompts', 'deep_prompt', 'scale_factor', 'adapter_dim')}, ms_per_step=round(ms, 2), volumes_per_s=round(a.batch / ms * 1e3, 1), trainable=ntr))
         print(json.dumps(rows[-1]), flush=True)
     except Exception as e:   # a variant the factory cannot build with these kwargs is reported, not hidden
         print(json.dumps(dict(method=method, **{k: v for k, v in extra.items() if k in ('r', 'num_prompts', 'deep_prompt')}, error=f'{type(e).__name__}: {e}'[:200])), flush=True)
