@@ -82,3 +82,38 @@ class GraphedTrainStep:
         self.graph.replay()
         self.optimizer.step_count += 1          # mirrors the device-side counter the graph just incremented (state_dict / resume)
         return self.loss
+
+
+class GraphedForward:
+    """``model(inputs)`` under ``torch.no_grad()`` as ONE CUDA graph (the loop of reference ``src/inference.py:105-113`` / ``eval.py:106-114`` with a fixed
+    batch shape): ~280 kernel launches per forward become one graph launch.  The model must already be in eval mode; the returned logits tensor
+    is the graph's static output (copy it before the next call if it has to survive).
+
+        fwd = GraphedForward(model, example_inputs)
+        for inputs in loader:
+            preds = fwd(inputs).argmax(1)
+    """
+
+    def __init__(self, model, example_inputs, warmup=2):
+        dev = example_inputs.device
+        if dev.type != 'cuda':
+            raise GvkError('GraphedForward needs CUDA inputs')
+        self.model = model
+        self.x = example_inputs.detach().clone()
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side), torch.no_grad():
+            for _ in range(max(1, warmup)):      # lazy one-time work (weight caches, tensor maps, function attributes) must not be captured
+                model(self.x)
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph, capture_error_mode='thread_local'), torch.no_grad():
+            self.out = model(self.x)
+
+    def __call__(self, inputs):
+        if inputs.shape != self.x.shape:
+            raise GvkError(f'GraphedForward was captured for inputs of shape {tuple(self.x.shape)}, got {tuple(inputs.shape)}')
+        self.x.copy_(inputs, non_blocking=True)
+        self.graph.replay()
+        return self.out

@@ -74,3 +74,23 @@ def test_graphed_step_draws_fresh_dropout_masks():
     opt.param_groups[0]['lr'] = 3e-3
     losses = [step(x, y).item() for _ in range(30)]
     assert sum(losses[-5:]) / 5 < sum(losses[:5]) / 5
+
+
+@pytest.mark.parametrize('mode', ['fp32', 'bf16'])
+def test_graphed_forward_equals_eager_forward(mode):
+    """Inference (reference src/inference.py:105-113) as one CUDA graph: bit-identical logits to the eager forward for fresh inputs copied into the
+    static buffer, and a shape the graph was not captured for is refused."""
+    from gaviko_b200._lib import GvkError
+    from gaviko_b200.graph import GraphedForward
+    kw, batch, seed, _ = GAVIKO_INIT_CASES['gaviko_t16_small_init']
+    m = _make(kw, mode, seed)
+    m.eval()
+    g = torch.Generator().manual_seed(5)
+    xs = [torch.rand(batch, kw['channels'], kw['frames'], kw['image_size'], kw['image_size'], generator=g).cuda() for _ in range(3)]
+    fwd = GraphedForward(m, xs[0])
+    for x in xs[::-1]:
+        with torch.no_grad():
+            ref = m(x).clone()
+        assert torch.equal(fwd(x), ref)
+    with pytest.raises(GvkError):
+        fwd(xs[0][:1])

@@ -12,6 +12,7 @@ from bench import GAVIKO_KW
 ap = argparse.ArgumentParser()
 ap.add_argument('--backbone', default='vit-b16'); ap.add_argument('--batch', type=int, default=8); ap.add_argument('--dtype', default='bf16')
 ap.add_argument('--steps', type=int, default=2); ap.add_argument('--by-site', action='store_true'); ap.add_argument('--eval', action='store_true')
+ap.add_argument('--infer', action='store_true', help='forward only under torch.no_grad() (model.eval())')
 ap.add_argument('--method', default='gaviko', help="gaviko (default) or evp (configs/evp.yaml: scale_factor 4)")
 a = ap.parse_args()
 torch.manual_seed(0)
@@ -36,7 +37,13 @@ crit = FocalLoss(gamma=1.2)
 x = torch.rand(a.batch, 1, 120, 160, 160, device='cuda'); y = torch.randint(0, 5, (a.batch,), device='cuda')
 
 def step():
+    if a.infer:
+        with torch.no_grad():
+            return model(x)
     loss = crit(model(x), y); opt.zero_grad(); loss.backward(); opt.step(); return loss
+
+if a.infer:
+    model.eval()
 
 for _ in range(2): step()
 torch.cuda.synchronize()
