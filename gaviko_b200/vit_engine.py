@@ -244,7 +244,11 @@ class VitEngine:
         """(P, dim) projected prompt tokens of layer i (model/vpt.py:127-131,146-153) and the embedding they came from."""
         m = self.module
         E = _f32(m.deep_prompt_embeddings[i] if m.deep_prompt else m.prompt_embeddings[0])
-        return ops.rowproj_up(E, _f32(m.prompt_proj.weight), _f32(m.prompt_proj.bias)), E
+        wp, bp = _f32(m.prompt_proj.weight), _f32(m.prompt_proj.bias)
+        if E.shape[1] % 4 == 0:
+            # P rows only: the exact-fp32 GEMM (tiles over dim) instead of a rank-r row kernel, whose per-CTA panel staging (~0.1 ms) dwarfs the work
+            return ops.gemm(E, wp, bias=bp), E
+        return ops.rowproj_up(E, wp, bp), E
 
     def forward(self, img, save):
         m, vt, c = self.module, self.vt, self.module._cfg
@@ -532,14 +536,18 @@ class VitEngine:
                     dPr = ops.batch_rowsum(dX, T, 1, P, B)                                               # [P, dim] = sum over the batch
                 wp = _f32(m.prompt_proj.weight)
                 pd = wp.shape[1]
-                if g('prompt_proj.weight') is not None:
+                if g('prompt_proj.weight') is not None and pd % 4 == 0:
+                    ops.wgrad(dPr, E, G['prompt_proj.weight'])                                           # [dim, prompt_dim] += dPr^T E (P rows, exact fp32)
+                    if g('prompt_proj.bias') is not None:
+                        ops.ssf_bwd(dPr, dshift=G['prompt_proj.bias'])
+                elif g('prompt_proj.weight') is not None:
                     for j0 in range(0, pd, 32):
                         j1 = min(pd, j0 + 32)
                         ops.skinny_wgrad(E[:, j0:j1], dPr, dw=G['prompt_proj.weight'][:, j0:j1], dw_strides=(1, pd),
                                          dx_colsum=g('prompt_proj.bias') if j0 == 0 else None)
                 elif g('prompt_proj.bias') is not None:
                     ops.ssf_bwd(dPr, dshift=G['prompt_proj.bias'])
-                dE = ops.rowproj_down(dPr, wp, transposed=True)['z']                                     # [P, prompt_dim]
+                dE = ops.gemm(dPr, wp.t().contiguous()) if pd % 4 == 0 else ops.rowproj_down(dPr, wp, transposed=True)['z']   # [P, prompt_dim]
                 ename = 'deep_prompt_embeddings' if m.deep_prompt else 'prompt_embeddings'
                 if g(ename) is not None:
                     G[ename][i if m.deep_prompt else 0] += dE      # torch add of a [P, prompt_dim] tile: accumulation plumbing
