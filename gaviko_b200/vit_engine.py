@@ -216,6 +216,13 @@ class VitEngine:
                                 wu=_f32(ad.up_adapter_proj.weight), bu=_f32(ad.up_adapter_proj.bias), drop=float(ad.dropout))
                 if ad.dropout != 0.0:
                     raise NotImplementedError('Adapter dropout > 0 is not implemented (reference default 0.0)')
+                if cdt == torch.bfloat16:
+                    # bf16 mode: the adapter's up-projection rides on the fc2 GEMM as a K-extension (hi / lo bf16 slots, as GAViKO's prompt path does):
+                    # the frozen fc2 weight with kext zero columns is cached, the forward rewrites those columns from the up weight every call
+                    kext = (3 * ad.down_dim + 63) // 64 * 64
+                    Lw['ad']['kext'] = kext
+                    Lw['ad']['w2x'] = cache.get((('ad_w2x', i, kext), cdt), f.net[4].weight,
+                                                lambda t: torch.cat([t.to(cdt), torch.zeros(t.shape[0], kext, device=t.device, dtype=cdt)], 1).contiguous())
                 Lw['n'].update(ad_ln_w=pd_ + 'adapter_layer_norm_before.weight', ad_ln_b=pd_ + 'adapter_layer_norm_before.bias',
                                ad_wd=pd_ + 'down_adapter_proj.weight', ad_bd=pd_ + 'down_adapter_proj.bias',
                                ad_wu=pd_ + 'up_adapter_proj.weight', ad_bu=pd_ + 'up_adapter_proj.bias')
@@ -366,24 +373,37 @@ class VitEngine:
             # with the activation) and the dgrad epilogue is one multiply instead of an erf.  SSF (model/ssf.py:77-80) needs the pre-activation itself.
             save_grad = save and 'f1' not in sa
             fo = Lw.get('fold')
+            ad = Lw.get('ad')
+            ad_fused = ad is not None and 'w2x' in ad and p_ff1 == 0 and p_ff2 == 0
+            act_x = None
+            if ad_fused:      # the activation goes straight into the left block of the K-extended fc2 operand (below)
+                mlp, kext = c['mlp_dim'], ad['kext']
+                act_x = torch.empty((B * T, mlp + kext), device=img.device, dtype=cdt)
             if fo is not None:
                 act = ops.gemm(h2, fo['f1'][0], bias=fo['f1'][1], act=ops.ACT_GELU, aux=hpre, out_dtype=cdt)
             else:
                 act = ops.gemm(h2, Lw['w1'], bias=Lw['b1'], ssf_scale=s_f1[0], ssf_shift=s_f1[1], act=ops.ACT_GELU_SAVE_GRAD if save_grad else ops.ACT_GELU,
-                               aux=hpre, out_dtype=cdt)
+                               aux=hpre, out_dtype=cdt, out=None if act_x is None else act_x[:, :mlp])
             st['gelu_grad_saved'] = save_grad
             del h2
             if p_ff1 > 0:
                 act = ops.dropout(act, p_ff1, seeds[2])
-            if ssf or p_ff2 > 0:
+            if ad_fused:
+                # x_out = x_mid + [act | z] [W2 | Wu]^T + (b2 + bu): fc2 and the adapter's up-projection in ONE GEMM (K = mlp + kext)
+                d = ops.rowproj_down(x_mid, ad['wd'], ad['bd'], ln=(ad['ln_w'], ad['ln_b']), act=ops.ROWACT_RELU, prec=pr)
+                ops.split_pack_bf16(d['z'], act_x[:, mlp:], 0b010)           # (hi, lo, hi)
+                ops.split_pack_bf16(ad['wu'], ad['w2x'][:, mlp:], 0b100)     # (hi, hi, lo)
+                x_out = ops.gemm(act_x, ad['w2x'], bias=Lw['b2'] + ad['bu'], res1=x_mid)
+                st.update(ad_z=d['z'], ad_mean=d['mean'], ad_rstd=d['rstd'])
+                del act_x
+            elif ssf or p_ff2 > 0:
                 y_f = ops.gemm(act, fo['f2'][0], bias=fo['f2'][1]) if fo is not None else ops.gemm(act, Lw['w2'], bias=Lw['b2'], ssf_scale=s_f2[0], ssf_shift=s_f2[1])
                 x_out = ops.dropout(y_f, p_ff2, seeds[3], res=x_mid, out_dtype=torch.float32)
                 st['y_f'] = y_f if ssf else None
             else:
                 x_out = ops.gemm(act, Lw['w2'], bias=Lw['b2'], res1=x_mid)
             del act
-            ad = Lw.get('ad')
-            if ad is not None:
+            if ad is not None and not ad_fused:
                 d = ops.rowproj_down(x_mid, ad['wd'], ad['bd'], ln=(ad['ln_w'], ad['ln_b']), act=ops.ROWACT_RELU, prec=pr)
                 self._up_chunked(d['z'], ad['wu'], ad['bu'], x_out, pr)
                 st.update(ad_z=d['z'], ad_mean=d['mean'], ad_rstd=d['rstd'])
@@ -479,15 +499,15 @@ class VitEngine:
                 ops.ssf_bwd(dA, y=st['hpre'], scale=sa['f1'][0], shift=sa['f1'][1], dx=dA, dscale=ds_, dshift=dh_)
             if g(n_['b1']) is not None:
                 ops.ssf_bwd(dA, dshift=g(n_['b1']))
-            dH2 = ops.gemm(dA, Lw['w1_t'])
-            del dA
+            dH2 = ops.gemm(dA, Lw['w1_t'], out_dtype=cdt)     # bf16 mode: the gradient of a LayerNorm output travels as bf16 (half the bytes of the GEMM's
+            del dA                                            # stores and of the LayerNorm backward's reads; its operands were bf16 anyway)
             f0 = sa.get('f0')
-            dXm = ops.layernorm_bwd(st['x_mid'], Lw['ln2_w'], st['mean2'], st['rstd2'], dy=dH2, dres=dX, dx=dH2, dbeta=g(n_['ln2_b']),
+            dXm = ops.layernorm_bwd(st['x_mid'], Lw['ln2_w'], st['mean2'], st['rstd2'], dy=dH2, dres=dX, dx=None if lp else dH2, dbeta=g(n_['ln2_b']),
                                     beta=Lw['ln2_b'] if f0 else None, ssf_scale=f0[0] if f0 else None,
                                     dssf_scale=g2(n_['f0'])[0] if f0 else None, dssf_shift=g2(n_['f0'])[1] if f0 else None)
             ad = Lw.get('ad')
             if ad is not None:
-                self._adapter_bwd(ad, n_, st, dX, dXm, g, pr)
+                self._adapter_bwd(ad, n_, st, dX, dXm, g, pr, dX_lp if lp else None)
             # ---- attention
             dYa = site_bwd(dXm, st.get('y_a'), 'a2', n_['bo'], p_out, seeds[1], None)
             dO = ops.gemm(dYa, Lw['wo_t'], out_dtype=cdt)
@@ -516,12 +536,12 @@ class VitEngine:
                 if g(n_['av']) is not None:
                     ops.skinny_wgrad(dz[:, r:], st['x_in'], dw=g(n_['av']), dw_layout='rd', ln=ln, prec=pr)
                 del dq, dv
-            dH1 = ops.gemm(dqkv, Lw['wqkv_t'])
+            dH1 = ops.gemm(dqkv, Lw['wqkv_t'], out_dtype=cdt)
             del dqkv
             a0 = sa.get('a0')
             dX_lp = torch.empty((B * T, dim), device=dev, dtype=cdt) if lp else None
             dX = ops.layernorm_bwd(st['x_in'], Lw['ln1_w'], st['mean1'], st['rstd1'], dy=dH1, dz=dz, w=lo['a_stack'] if lo is not None else None,
-                                   dres=dXm, dx=dH1, dx_lp=dX_lp, dbeta=g(n_['ln1_b']), beta=Lw['ln1_b'] if a0 else None,
+                                   dres=dXm, dx=None if lp else dH1, dx_lp=dX_lp, dbeta=g(n_['ln1_b']), beta=Lw['ln1_b'] if a0 else None,
                                    ssf_scale=a0[0] if a0 else None, dssf_scale=g2(n_['a0'])[0] if a0 else None, dssf_shift=g2(n_['a0'])[1] if a0 else None)
             del dXm
             if 'vpt' in st:
@@ -703,18 +723,25 @@ class VitEngine:
             if n in want:
                 G[n].copy_(v.reshape(G[n].shape))              # slice of a padded accumulator -> parameter shape: plumbing
 
-    def _adapter_bwd(self, ad, n_, st, dX, dXm, g, pr):
+    def _adapter_bwd(self, ad, n_, st, dX, dXm, g, pr, dX_lp=None):
         """x_out = ... + up(ReLU(down(LN_a(x_mid)))): gradients of the six adapter tensors and the contribution to d x_mid
         (model/adaptformer.py:58-78).  Rank 64 is processed in 32-wide slices (kernel limit of the rank-r gradient kernels)."""
         z = st['ad_z']
         r, dim = z.shape[1], dX.shape[1]
         ln = (ad['ln_w'], ad['ln_b'], st['ad_mean'], st['ad_rstd'])
+        # bf16 mode, bottleneck a multiple of 64 (the reference's 64): the two [M, dim] x [dim, r] / [M, r] x [r, dim] products of the dgrad run on the
+        # tcgen05 GEMM (one pass each over the gradient stream) instead of 32-wide slices through the rank-r row kernels (two passes each)
+        tc = dX_lp is not None and r % 64 == 0
+        cdt = dX_lp.dtype if tc else None
         dz = torch.empty_like(z)
         for j0 in range(0, r, 32):
             j1 = min(r, j0 + 32)
             if g(n_['ad_wu']) is not None:
                 ops.skinny_wgrad(z[:, j0:j1], dX, dw=g(n_['ad_wu'])[:, j0:j1], dw_strides=(1, r), dx_colsum=g(n_['ad_bu']) if j0 == 0 else None, prec=pr)
-            dz[:, j0:j1] = ops.rowproj_down(dX, ad['wu'][:, j0:j1].contiguous(), transposed=True, prec=pr)['z']   # column-block copy: plumbing
+            if not tc:
+                dz[:, j0:j1] = ops.rowproj_down(dX, ad['wu'][:, j0:j1].contiguous(), transposed=True, prec=pr)['z']   # column-block copy: plumbing
+        if tc:
+            ops.gemm(dX_lp, ad['wu'].t().contiguous().to(cdt), out=dz)                  # dz = dX Wu  ([M, dim] x [dim, r])
         ops.relu_bwd(dz, z, out=dz)
         for j0 in range(0, r, 32):
             j1 = min(r, j0 + 32)
@@ -722,8 +749,12 @@ class VitEngine:
             if g(n_['ad_wd']) is not None:
                 ops.skinny_wgrad(dzc, st['x_mid'], dw=g(n_['ad_wd'])[j0:j1], dw_layout='rd', da_colsum=g(n_['ad_bd'])[j0:j1] if g(n_['ad_bd']) is not None else None,
                                  ln=ln, prec=pr)
-            ops.layernorm_bwd(st['x_mid'], ad['ln_w'], st['ad_mean'], st['ad_rstd'], dz=dzc, w=ad['wd'][j0:j1].contiguous(), dres=dXm, dx=dXm,
-                              dgamma=g(n_['ad_ln_w']), dbeta=g(n_['ad_ln_b']))
+            if not tc:
+                ops.layernorm_bwd(st['x_mid'], ad['ln_w'], st['ad_mean'], st['ad_rstd'], dz=dzc, w=ad['wd'][j0:j1].contiguous(), dres=dXm, dx=dXm,
+                                  dgamma=g(n_['ad_ln_w']), dbeta=g(n_['ad_ln_b']))
+        if tc:
+            dy = ops.gemm(ops.cast_bf16(dz), ad['wd'].t().contiguous().to(cdt), out_dtype=cdt)   # gradient of the adapter's LayerNorm output, [M, dim]
+            ops.layernorm_bwd(st['x_mid'], ad['ln_w'], st['ad_mean'], st['ad_rstd'], dy=dy, dres=dXm, dx=dXm, dgamma=g(n_['ad_ln_w']), dbeta=g(n_['ad_ln_b']))
 
 
 class _VitFn(torch.autograd.Function):
