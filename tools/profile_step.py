@@ -26,7 +26,8 @@ with contextlib.redirect_stdout(io.StringIO()):
         from variant_factory import build_variant
         kw = dict(image_size=160, image_patch_size=16, frames=120, frame_patch_size=12, num_classes=5, channels=1, pool='cls', backbone=a.backbone, dropout=0.1,
                   emb_dropout=0.1, compute_dtype=a.dtype)
-        extra = dict(melo=dict(r=4, alpha=8), adaptformer=dict(freeze_vit=True), ssf=dict(freeze_vit=True), deep_vpt=dict(freeze_vit=True, prompt_dropout=0.1, prompt_dim=64, num_prompts=32, deep_prompt=True))
+        extra = dict(melo=dict(r=4, alpha=8), adaptformer=dict(freeze_vit=True), ssf=dict(freeze_vit=True), deep_vpt=dict(freeze_vit=True, prompt_dropout=0.1, prompt_dim=64, num_prompts=32, deep_prompt=True), dvpt=dict(freeze_vit=True, num_prompts=32),
+                     bitfit=dict(), linear=dict())
         model = build_variant(a.method, dict(kw, **extra.get(a.method, {}))).cuda()
     else:
         model = Gaviko(**GAVIKO_KW, backbone=a.backbone, compute_dtype=a.dtype).cuda()
