@@ -507,7 +507,7 @@ def test_evp_wgrad_row_maps():
 
 
 @pytest.mark.parametrize('shape,rate', [((2, 1, 48, 64, 64), 0.25), ((1, 1, 24, 32, 48), 0.1), ((2, 1, 12, 32, 32), 0.9), ((1, 2, 20, 16, 24), 0.5),
-                                        ((2, 1, 120, 160, 160), 0.25), ((1, 1, 6, 200, 330), 0.3)])
+                                        ((2, 1, 120, 160, 160), 0.25), ((1, 1, 6, 200, 330), 0.3), ((1100, 1, 60, 8, 12), 0.25)])
 def test_evp_hfreq_filter_matches_reference_fft(shape, rate):
     """gvk_hfreq_filter with the engine's closed-form filter against PromptGenerator.fft restated with torch.fft (oracle.evp_highpass, pinned
     to the live reference by the evp goldens): fftshift over every axis, mask on the depth / height axes, real part, abs."""
