@@ -9,6 +9,7 @@
 // Used by the bf16 compute mode for LocalSelfAttention / Awakening_Prompt projections and their weight gradients
 // (reference model/gaviko.py:149-187, 229-244 and the autograd of those lines).
 #include <algorithm>
+#include <cstdlib>
 
 #include "gvk_common.cuh"
 
@@ -680,6 +681,307 @@ bool skinny_wgrad_tc_supported(const gvk_skinny_wgrad_params* p) {
   const bool dim_ok = (p->dim % 96 == 0 && p->dim / 96 <= kTcWarps) || (p->dim % 128 == 0 && p->dim / 128 <= kTcWarps);
   return dim_ok && p->r <= 32 && p->r % 4 == 0 && p->ldx % 4 == 0 && p->lda % 4 == 0 && (reinterpret_cast<uintptr_t>(p->x) & 15) == 0 &&
          (reinterpret_cast<uintptr_t>(p->a) & 15) == 0;
+}
+
+
+// =================================================================================================
+// LayerNorm backward with a rank-r term, the rank-r product on the tensor cores:
+//   MODE 0:  dx = dres + LN'(dy) + az @ aw        dy dense bf16 (the d(g_mid) pass: model/gaviko.py:155 next to :304's LayerNorm)
+//   MODE 1:  dx = dres + LN'(dz @ w)              + dgamma / dbeta (LocalSelfAttention.norm -> proj_down, model/gaviko.py:229-231)
+// The exact-fp32 kernel (gvk_rowops.cu) re-reads the [r, dim] panel from shared memory for every pair of rows (61 KB per pair at r = 20,
+// dim = 768: 232 us against 155 us without the term at M = 66 k).  Here a CTA owns 16 rows per step and warp w owns columns
+// [w dim/8, (w+1) dim/8) of all 16 in the C-fragment layout of tc_up (lane (g, t): rows g / g+8, four consecutive columns 16 kk + 4 t), so
+// the panel is read once per 16 rows as MMA B fragments and the row statistics need one shared-memory exchange between the 8 warps
+// (double-buffered: one __syncthreads per step).
+// One CTA per SM.  The three row streams (x, dy, dres) of the NEXT step travel by cp.async into thread-private shared-memory slots while
+// the current step is computed: a thread re-fills a slot right after it has read it, so ~120 KB per SM are in flight all the time and no
+// warp waits on a load it has just issued.  (Measured at M = 66 112, dim 768, r 20: exact kernel 238 us; this layout with two CTAs per SM
+// and plain loads 227 us; one CTA with the next step's x / dy prefetched into registers 182 us; profiles/lnbwd_tc_r02*.jsonl.)
+// =================================================================================================
+__device__ __forceinline__ float4 bf16x4_to_float4(uint2 v) {
+  const float2 lo = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&v.x));
+  const float2 hi = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&v.y));
+  return make_float4(lo.x, lo.y, hi.x, hi.y);
+}
+__device__ __forceinline__ void cp_async8(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+
+template <int NITER, int KS, int MODE>
+struct LnbTc {
+  static constexpr int dim = NITER * 64, S = dim + 8, GW = NITER / 2, RP = KS * 8;
+  static constexpr int kSlots = GW * 2 * kTcThreads;       // one 16-byte (x, dres) or 8-byte (dy) slot per (column group, row, thread)
+  static constexpr size_t kSmem = ((size_t)RP * S + dim) * sizeof(float) + 2 * 16 * kTcWarps * sizeof(float2) + 2 * (size_t)kSlots * sizeof(float4) +
+                                  (MODE == 0 ? (size_t)kSlots * sizeof(uint2) : 0);
+};
+
+template <int NITER, int KS, int MODE, bool PGRAD>
+__global__ void __launch_bounds__(kTcThreads, 1) ln_bwd_tc_kernel(gvk_layernorm_bwd_params p) {
+  using L = LnbTc<NITER, KS, MODE>;
+  constexpr int dim = L::dim, S = L::S, GW = L::GW, RP = L::RP;
+  static_assert(NITER % 2 == 0, "dim must be a multiple of 128");
+  extern __shared__ __align__(16) float smem[];
+  float* sW = smem;                                       // [RP][S] tf32 panel, two low column bits of every 16-column group swapped
+  float* s_gamma = sW + RP * S;                           // [dim]
+  float2* red = reinterpret_cast<float2*>(s_gamma + dim); // [2][16][kTcWarps]
+  float4* s_x = reinterpret_cast<float4*>(red + 2 * 16 * kTcWarps);   // [GW][2][kTcThreads]
+  float4* s_r = s_x + L::kSlots;
+  uint2* s_y = reinterpret_cast<uint2*>(s_r + L::kSlots);  // MODE 0: raw bf16 x 4
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+  const float* rsrc = MODE == 0 ? p.az : p.dz;            // [M, r] latent operand of the rank-r product
+  const int rld = MODE == 0 ? p.ld_az : p.ld_dz, rr = MODE == 0 ? p.ra : p.r;
+  const int ntiles = (p.M + 15) / 16;
+  const float inv_dim = 1.0f / dim;
+  const int cw = warp * 16 * GW + 4 * t;                  // this lane's first column
+  const __nv_bfloat16* dyp = reinterpret_cast<const __nv_bfloat16*>(p.dy);
+  auto slot = [&](int kk, int row) { return (kk * 2 + row) * kTcThreads + tid; };
+  auto row_a = [&](int tile) { return (size_t)min(tile * 16 + g, p.M - 1); };
+  auto row_b = [&](int tile) { return (size_t)min(tile * 16 + g + 8, p.M - 1); };
+  auto fetch_xy = [&](int tile, int kk) {
+    const size_t cA = row_a(tile), cB = row_b(tile);
+    cp_async16(s_x + slot(kk, 0), p.x + cA * p.ldx + cw + 16 * kk);
+    cp_async16(s_x + slot(kk, 1), p.x + cB * p.ldx + cw + 16 * kk);
+    if (MODE == 0) {
+      cp_async8(s_y + slot(kk, 0), dyp + cA * p.ld_dy + cw + 16 * kk);
+      cp_async8(s_y + slot(kk, 1), dyp + cB * p.ld_dy + cw + 16 * kk);
+    }
+  };
+  auto fetch_r = [&](int tile, int kk) {
+    cp_async16(s_r + slot(kk, 0), p.dres + row_a(tile) * p.ld_dres + cw + 16 * kk);
+    cp_async16(s_r + slot(kk, 1), p.dres + row_b(tile) * p.ld_dres + cw + 16 * kk);
+  };
+  struct Lat { float v[KS][4]; float meanA, rstdA, meanB, rstdB; };
+  auto load_lat = [&](int tile, Lat& T) {
+    const size_t cA = row_a(tile), cB = row_b(tile);
+#pragma unroll
+    for (int s = 0; s < KS; ++s) {
+      const int k0 = 8 * s + t, k1 = k0 + 4;
+      T.v[s][0] = k0 < rr ? rsrc[cA * rld + k0] : 0.f;
+      T.v[s][1] = k0 < rr ? rsrc[cB * rld + k0] : 0.f;
+      T.v[s][2] = k1 < rr ? rsrc[cA * rld + k1] : 0.f;
+      T.v[s][3] = k1 < rr ? rsrc[cB * rld + k1] : 0.f;
+    }
+    T.meanA = p.mean[cA]; T.rstdA = p.rstd[cA]; T.meanB = p.mean[cB]; T.rstdB = p.rstd[cB];
+  };
+  // ---- prologue: the first step's streams start before the panel is staged
+  Lat cur;
+  if ((int)blockIdx.x < ntiles) {
+#pragma unroll
+    for (int kk = 0; kk < GW; ++kk) fetch_xy(blockIdx.x, kk);
+  }
+  cp_async_commit();
+  if ((int)blockIdx.x < ntiles && p.dres) {
+#pragma unroll
+    for (int kk = 0; kk < GW; ++kk) fetch_r(blockIdx.x, kk);
+  }
+  cp_async_commit();
+  if ((int)blockIdx.x < ntiles) load_lat(blockIdx.x, cur);
+  if (MODE == 0) tc_stage_panel<RP, S, true>(sW, p.aw, p.ra, dim, p.aw_sj, p.aw_sc, nullptr);
+  else tc_stage_panel<RP, S, true>(sW, p.w, p.r, dim, p.w_sj, p.w_sc, nullptr);
+  for (int c = tid; c < dim; c += kTcThreads) s_gamma[c] = p.gamma[c];
+  __syncthreads();
+  float4 dgm[PGRAD ? GW : 1], dbt[PGRAD ? GW : 1];
+#pragma unroll
+  for (int kk = 0; kk < (PGRAD ? GW : 1); ++kk) dgm[kk] = dbt[kk] = make_float4(0.f, 0.f, 0.f, 0.f);
+  int buf = 0;
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, buf ^= 1) {
+    const int rA = tile * 16 + g, rB = rA + 8;
+    const int next = tile + gridDim.x;
+    const bool has_next = next < ntiles;                  // uniform over the CTA
+    Lat nxt;
+    if (has_next) load_lat(next, nxt);
+    const float meanA = cur.meanA, rstdA = cur.rstdA, meanB = cur.meanB, rstdB = cur.rstdB;
+    uint32_t a[KS][4];
+#pragma unroll
+    for (int s = 0; s < KS; ++s)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) a[s][e] = f2tf32(cur.v[s][e]);
+    const float liveA = rA < p.M ? 1.f : 0.f, liveB = rB < p.M ? 1.f : 0.f;
+    // rank-r product of one 16-column group on top of (accA, accB): lane's four consecutive columns of rows g and g+8
+    auto rank_mma = [&](int kk, float4& accA, float4& accB) {
+      float d0[4] = {accA.x, accA.y, accB.x, accB.y}, d1[4] = {accA.z, accA.w, accB.z, accB.w};
+#pragma unroll
+      for (int s = 0; s < KS; ++s) {
+        const float2 b0 = *reinterpret_cast<const float2*>(sW + (8 * s + t) * S + 16 * (warp * GW + kk) + 2 * g);
+        const float2 b1 = *reinterpret_cast<const float2*>(sW + (8 * s + t + 4) * S + 16 * (warp * GW + kk) + 2 * g);
+        mma_tf32(d0, a[s][0], a[s][1], a[s][2], a[s][3], __float_as_uint(b0.x), __float_as_uint(b1.x));
+        mma_tf32(d1, a[s][0], a[s][1], a[s][2], a[s][3], __float_as_uint(b0.y), __float_as_uint(b1.y));
+      }
+      accA = make_float4(d0[0], d0[1], d1[0], d1[1]);
+      accB = make_float4(d0[2], d0[3], d1[2], d1[3]);
+    };
+    // ---- row statistics: m1 = mean(dy gamma), m2 = mean(dy gamma xhat).  Pending copy groups here: x / dy of this step, dres of this step.
+    cp_async_wait<1>();
+    float4 xa[GW], xb[GW];
+    uint2 ya[MODE == 0 ? GW : 1], yb[MODE == 0 ? GW : 1];
+    float s1A = 0.f, s2A = 0.f, s1B = 0.f, s2B = 0.f;
+#pragma unroll
+    for (int kk = 0; kk < GW; ++kk) {
+      xa[kk] = s_x[slot(kk, 0)];
+      xb[kk] = s_x[slot(kk, 1)];
+      if (MODE == 0) {
+        ya[kk] = s_y[slot(kk, 0)];
+        yb[kk] = s_y[slot(kk, 1)];
+      }
+      if (has_next) fetch_xy(next, kk);                   // the slots just read are free again
+      const float4 gam = *reinterpret_cast<const float4*>(s_gamma + cw + 16 * kk);
+      xa[kk] = make_float4((xa[kk].x - meanA) * rstdA, (xa[kk].y - meanA) * rstdA, (xa[kk].z - meanA) * rstdA, (xa[kk].w - meanA) * rstdA);
+      xb[kk] = make_float4((xb[kk].x - meanB) * rstdB, (xb[kk].y - meanB) * rstdB, (xb[kk].z - meanB) * rstdB, (xb[kk].w - meanB) * rstdB);
+      float4 dA, dB;
+      if (MODE == 0) {
+        dA = bf16x4_to_float4(ya[kk]);
+        dB = bf16x4_to_float4(yb[kk]);
+      } else {
+        dA = dB = make_float4(0.f, 0.f, 0.f, 0.f);
+        rank_mma(kk, dA, dB);
+      }
+      if (PGRAD) {
+        dgm[kk].x += liveA * dA.x * xa[kk].x + liveB * dB.x * xb[kk].x;
+        dgm[kk].y += liveA * dA.y * xa[kk].y + liveB * dB.y * xb[kk].y;
+        dgm[kk].z += liveA * dA.z * xa[kk].z + liveB * dB.z * xb[kk].z;
+        dgm[kk].w += liveA * dA.w * xa[kk].w + liveB * dB.w * xb[kk].w;
+        dbt[kk].x += liveA * dA.x + liveB * dB.x;
+        dbt[kk].y += liveA * dA.y + liveB * dB.y;
+        dbt[kk].z += liveA * dA.z + liveB * dB.z;
+        dbt[kk].w += liveA * dA.w + liveB * dB.w;
+      }
+      dA.x *= gam.x; dA.y *= gam.y; dA.z *= gam.z; dA.w *= gam.w;
+      dB.x *= gam.x; dB.y *= gam.y; dB.z *= gam.z; dB.w *= gam.w;
+      s1A += (dA.x + dA.y) + (dA.z + dA.w);
+      s2A = fmaf(dA.x, xa[kk].x, fmaf(dA.y, xa[kk].y, fmaf(dA.z, xa[kk].z, fmaf(dA.w, xa[kk].w, s2A))));
+      s1B += (dB.x + dB.y) + (dB.z + dB.w);
+      s2B = fmaf(dB.x, xb[kk].x, fmaf(dB.y, xb[kk].y, fmaf(dB.z, xb[kk].z, fmaf(dB.w, xb[kk].w, s2B))));
+    }
+    cp_async_commit();                                    // x / dy of the next step
+    s1A += __shfl_xor_sync(0xffffffffu, s1A, 1); s1A += __shfl_xor_sync(0xffffffffu, s1A, 2);
+    s2A += __shfl_xor_sync(0xffffffffu, s2A, 1); s2A += __shfl_xor_sync(0xffffffffu, s2A, 2);
+    s1B += __shfl_xor_sync(0xffffffffu, s1B, 1); s1B += __shfl_xor_sync(0xffffffffu, s1B, 2);
+    s2B += __shfl_xor_sync(0xffffffffu, s2B, 1); s2B += __shfl_xor_sync(0xffffffffu, s2B, 2);
+    float2* rbuf = red + buf * 16 * kTcWarps;
+    if (t == 0) {
+      rbuf[g * kTcWarps + warp] = make_float2(s1A, s2A);
+      rbuf[(g + 8) * kTcWarps + warp] = make_float2(s1B, s2B);
+    }
+    __syncthreads();
+    float m1A = 0.f, m2A = 0.f, m1B = 0.f, m2B = 0.f;
+#pragma unroll
+    for (int w = 0; w < kTcWarps; w += 2) {
+      const float4 va = *reinterpret_cast<const float4*>(rbuf + g * kTcWarps + w);
+      const float4 vb = *reinterpret_cast<const float4*>(rbuf + (g + 8) * kTcWarps + w);
+      m1A += va.x + va.z; m2A += va.y + va.w;
+      m1B += vb.x + vb.z; m2B += vb.y + vb.w;
+    }
+    m1A *= inv_dim; m2A *= inv_dim; m1B *= inv_dim; m2B *= inv_dim;
+    // ---- dx = rstd (dy gamma - m1 - xhat m2) (+ az @ aw) (+ dres).  Pending copy groups: dres of this step, x / dy of the next.
+    cp_async_wait<1>();
+#pragma unroll
+    for (int kk = 0; kk < GW; ++kk) {
+      const int col = cw + 16 * kk;
+      float4 rcA = make_float4(0.f, 0.f, 0.f, 0.f), rcB = rcA;
+      if (p.dres) {
+        rcA = s_r[slot(kk, 0)];
+        rcB = s_r[slot(kk, 1)];
+        if (has_next) fetch_r(next, kk);
+      }
+      const float4 gam = *reinterpret_cast<const float4*>(s_gamma + col);
+      float4 dA, dB;
+      if (MODE == 0) {
+        dA = bf16x4_to_float4(ya[kk]);
+        dB = bf16x4_to_float4(yb[kk]);
+      } else {
+        dA = dB = make_float4(0.f, 0.f, 0.f, 0.f);
+        rank_mma(kk, dA, dB);
+      }
+      float4 vA = make_float4(rstdA * (dA.x * gam.x - m1A - xa[kk].x * m2A), rstdA * (dA.y * gam.y - m1A - xa[kk].y * m2A),
+                              rstdA * (dA.z * gam.z - m1A - xa[kk].z * m2A), rstdA * (dA.w * gam.w - m1A - xa[kk].w * m2A));
+      float4 vB = make_float4(rstdB * (dB.x * gam.x - m1B - xb[kk].x * m2B), rstdB * (dB.y * gam.y - m1B - xb[kk].y * m2B),
+                              rstdB * (dB.z * gam.z - m1B - xb[kk].z * m2B), rstdB * (dB.w * gam.w - m1B - xb[kk].w * m2B));
+      if (MODE == 0) rank_mma(kk, vA, vB);
+      vA.x += rcA.x; vA.y += rcA.y; vA.z += rcA.z; vA.w += rcA.w;
+      vB.x += rcB.x; vB.y += rcB.y; vB.z += rcB.z; vB.w += rcB.w;
+      if (rA < p.M) {
+        *reinterpret_cast<float4*>(p.dx + (size_t)rA * p.ld_dx + col) = vA;
+        if (p.dx_lp) {
+          __nv_bfloat162 lo = __floats2bfloat162_rn(vA.x, vA.y), hi = __floats2bfloat162_rn(vA.z, vA.w);
+          *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.dx_lp) + (size_t)rA * p.ld_dx_lp + col) =
+              make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
+        }
+      }
+      if (rB < p.M) {
+        *reinterpret_cast<float4*>(p.dx + (size_t)rB * p.ld_dx + col) = vB;
+        if (p.dx_lp) {
+          __nv_bfloat162 lo = __floats2bfloat162_rn(vB.x, vB.y), hi = __floats2bfloat162_rn(vB.z, vB.w);
+          *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.dx_lp) + (size_t)rB * p.ld_dx_lp + col) =
+              make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
+        }
+      }
+    }
+    cp_async_commit();                                    // dres of the next step
+    if (has_next) cur = nxt;
+  }
+  cp_async_wait<0>();
+  if (PGRAD) {
+    // lanes that share t hold the same columns for different rows: sum over g, then one atomic per column from the g == 0 lanes
+#pragma unroll
+    for (int kk = 0; kk < GW; ++kk) {
+      float v[8] = {dgm[kk].x, dgm[kk].y, dgm[kk].z, dgm[kk].w, dbt[kk].x, dbt[kk].y, dbt[kk].z, dbt[kk].w};
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        v[e] += __shfl_xor_sync(0xffffffffu, v[e], 4);
+        v[e] += __shfl_xor_sync(0xffffffffu, v[e], 8);
+        v[e] += __shfl_xor_sync(0xffffffffu, v[e], 16);
+      }
+      if (g == 0) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          if (p.dgamma) atomicAdd(p.dgamma + cw + 16 * kk + e, v[e]);
+          if (p.dbeta) atomicAdd(p.dbeta + cw + 16 * kk + e, v[4 + e]);
+        }
+      }
+    }
+  }
+}
+
+template <int NITER, int KS, int MODE, bool PGRAD>
+static int ln_bwd_tc_launch(const gvk_layernorm_bwd_params* p, cudaStream_t stream) {
+  constexpr size_t smem = LnbTc<NITER, KS, MODE>::kSmem;
+  static_assert(smem <= 227 * 1024, "layernorm_bwd_tc: shared memory");
+  static const int attr = cudaFuncSetAttribute(ln_bwd_tc_kernel<NITER, KS, MODE, PGRAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (attr != cudaSuccess) return cuda_status((cudaError_t)attr, "layernorm_bwd_tc (smem attribute)");
+  const int ntiles = (p->M + 15) / 16;
+  ln_bwd_tc_kernel<NITER, KS, MODE, PGRAD><<<std::max(1, std::min(ntiles, sm_count())), kTcThreads, smem, stream>>>(*p);
+  GVK_CHECK_LAUNCH("layernorm_bwd_tc");
+  return GVK_OK;
+}
+
+// Forms the tensor-core kernel takes (everything else stays on the fp32 kernel): dense bf16 dy + additive rank term without parameter
+// gradients (MODE 0), or rank-r dy alone with both parameter gradients (MODE 1); dim a multiple of 128; 16-byte aligned fp32 streams.
+bool layernorm_bwd_tc_supported(const gvk_layernorm_bwd_params* p) {
+  auto al = [](const void* q, uintptr_t m) { return (reinterpret_cast<uintptr_t>(q) & m) == 0; };
+  if (p->dim != 384 && p->dim != 768) return false;      // dim 1024 (16 column groups per warp pair) does not fit the register file without spills
+  if (p->ssf_scale) return false;
+  if (!al(p->x, 15) || p->ldx % 4 != 0 || !al(p->dx, 15) || p->ld_dx % 4 != 0) return false;
+  if (p->dres && (!al(p->dres, 15) || p->ld_dres % 4 != 0)) return false;
+  if (p->dx_lp && (!al(p->dx_lp, 7) || p->ld_dx_lp % 4 != 0)) return false;
+  const bool mode0 = p->dy && p->dy_dtype == GVK_BF16 && p->az && !p->dz && !p->dgamma && !p->dbeta && p->ra <= 32 && al(p->dy, 7) && p->ld_dy % 4 == 0;
+  const bool mode1 = !p->dy && p->dz && !p->az && p->dgamma && p->dbeta && p->r <= 32;
+  return mode0 || mode1;
+}
+
+int layernorm_bwd_tc(const gvk_layernorm_bwd_params* p, cudaStream_t stream) {
+  const bool mode0 = p->dy != nullptr;
+  const int r = mode0 ? p->ra : p->r;
+#define GVK_LNB_TC(NITER)                                                                                                              \
+  if (mode0) return r <= 24 ? ln_bwd_tc_launch<NITER, 3, 0, false>(p, stream) : ln_bwd_tc_launch<NITER, 4, 0, false>(p, stream);       \
+  return r <= 24 ? ln_bwd_tc_launch<NITER, 3, 1, true>(p, stream) : ln_bwd_tc_launch<NITER, 4, 1, true>(p, stream);
+  switch (p->dim / 64) {
+    case 6: GVK_LNB_TC(6)
+    case 12: GVK_LNB_TC(12)
+    default:
+      set_last_error("gvk_layernorm_bwd(tf32): dim %d", p->dim);
+      return GVK_ERR_UNSUPPORTED;
+  }
+#undef GVK_LNB_TC
 }
 
 }  // namespace gvk

@@ -348,7 +348,7 @@ class GavikoEngine:
             ops.skinny_wgrad(dul, st['loc_out'], dw=gF['wd'], dw_layout='rd', da_colsum=gF['bd'], prec=pr)
             # ---- d(g_mid) = dG + LN2'(dH2) + du Wd
             dGm_lp = torch.empty((B * T, dim), device=dev, dtype=cdt) if lp else None
-            dGm = ops.layernorm_bwd(st['g_mid'], Lw['ln2_w'], st['mean2'], st['rstd2'], dy=dH2, dres=dG, dx=None if lp else dH2, dx_lp=dGm_lp, az=du, aw=Fu['wd'])
+            dGm = ops.layernorm_bwd(st['g_mid'], Lw['ln2_w'], st['mean2'], st['rstd2'], dy=dH2, dres=dG, dx=None if lp else dH2, dx_lp=dGm_lp, az=du, aw=Fu['wd'], prec=pr)
             del dH2
             # ---- d(loc_out) += dul Wd
             if dLoc is None:
@@ -372,7 +372,7 @@ class GavikoEngine:
             dz = ops.small_matmul(dqkv_l, La['wqkv'])
             ops.skinny_wgrad(dz, st['loc_in'], dw=gL['wd'], dw_layout='rd', da_colsum=gL['bd'], ln=(La['ln_w'], La['ln_b'], st['mean_l'], st['rstd_l']), prec=pr)
             dLoc = ops.layernorm_bwd(st['loc_in'], La['ln_w'], st['mean_l'], st['rstd_l'], dz=dz, w=La['wd'], dres=dLoc, dx=dLoc,
-                                     dgamma=gL['ln_w'], dbeta=gL['ln_b'])
+                                     dgamma=gL['ln_w'], dbeta=gL['ln_b'], prec=pr)
             ctx['layers'][i] = None     # release this layer's activations
         # prompt rows of the layer-0 input (model/gaviko.py:540-543): both prompt tensors receive the same gradient
         ops.batch_rowsum(dG, T, 0, P, B, out=G['prompt_emb'].view(P, dim), accumulate=True)

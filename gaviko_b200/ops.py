@@ -190,14 +190,15 @@ def skinny_wgrad(a, x, *, dw=None, dw_layout='rd', da_colsum=None, dx_colsum=Non
 
 
 def layernorm_bwd(x, gamma, mean, rstd, *, dy=None, dz=None, w=None, dres=None, dx=None, dx_lp=None, dgamma=None, dbeta=None, az=None, aw=None,
-                  beta=None, ssf_scale=None, dssf_scale=None, dssf_shift=None):
-    """dx = dres + LN'(dy) + az @ aw;  dy dense [M, dim] or rank-r (dz [M, r], w [r, dim]);  az [M, ra], aw [ra, dim]."""
+                  beta=None, ssf_scale=None, dssf_scale=None, dssf_shift=None, prec=PREC_FP32):
+    """dx = dres + LN'(dy) + az @ aw;  dy dense [M, dim] or rank-r (dz [M, r], w [r, dim]);  az [M, ra], aw [ra, dim].  prec = PREC_TF32: the
+    rank-r product of the two forms gvk.h names runs on the tensor cores (tf32 operands) inside the pass."""
     M, dim = x.shape
     if dx is None:
         dx = torch.empty((M, dim), device=x.device, dtype=torch.float32)
     p = S['gvk_layernorm_bwd_params']()
     _set(p, x=L.ptr(x, torch.float32), ldx=_ld(x), gamma=L.fptr(gamma), mean=L.fptr(mean), rstd=L.fptr(rstd),
-         dx=L.ptr(dx, torch.float32), ld_dx=_ld(dx), dgamma=L.fptr(dgamma), dbeta=L.fptr(dbeta), M=M, dim=dim)
+         dx=L.ptr(dx, torch.float32), ld_dx=_ld(dx), dgamma=L.fptr(dgamma), dbeta=L.fptr(dbeta), M=M, dim=dim, precision=prec)
     if dy is not None:
         _set(p, dy=L.ptr(dy), ld_dy=_ld(dy), dy_dtype=L.dtype_tag(dy.dtype))
     if dz is not None:

@@ -176,7 +176,10 @@ int gvk_skinny_wgrad(const gvk_skinny_wgrad_params* p, gvk_stream_t stream);
  * az @ aw (optional, az [M, ra], aw(j, c) strided like w) is added OUTSIDE the norm: the dgrad of a rank-ra down-projection that reads
  * the same residual stream as the LayerNorm (Awakening_Prompt.proj_down next to FeedForward's norm, model/gaviko.py:155,304).
  * dgamma / dbeta (optional, [dim]) accumulate with atomics.  dx may alias dres or dy.
- * dx_lp is an optional bf16 copy (the next dgrad GEMM's A operand).  dx may alias dy only when dy is fp32. */
+ * dx_lp is an optional bf16 copy (the next dgrad GEMM's A operand).  dx may alias dy only when dy is fp32.
+ * precision = GVK_PREC_TF32 (bf16 compute mode) runs the rank-r product (az @ aw next to a dense bf16 dy, or dz @ w with dgamma / dbeta)
+ * as mma.sync m16n8k8 with tf32 operands inside the same pass; the LayerNorm arithmetic itself stays fp32.  Forms outside those two run
+ * the exact kernel whatever the field says. */
 typedef struct {
   const void* dy; int ld_dy; int dy_dtype;   /* GVK_F32 or GVK_BF16 (the dgrad GEMM that produces dy then writes half the bytes) */
   const float* dz; int ld_dz; const float* w; int w_sj, w_sc; int r;
@@ -187,6 +190,7 @@ typedef struct {
   int M, dim;
   const float* az; int ld_az; const float* aw; int aw_sj, aw_sc; int ra;
   const float* beta; const float* ssf_scale; float* dssf_scale; float* dssf_shift;
+  int precision;                /* GVK_PREC_FP32 (exact, default) or GVK_PREC_TF32 */
 } gvk_layernorm_bwd_params;
 int gvk_layernorm_bwd(const gvk_layernorm_bwd_params* p, gvk_stream_t stream);
 

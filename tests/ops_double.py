@@ -155,7 +155,7 @@ def skinny_wgrad(a, x, *, dw=None, dw_layout='rd', da_colsum=None, dx_colsum=Non
 
 
 def layernorm_bwd(x, gamma, mean, rstd, *, dy=None, dz=None, w=None, dres=None, dx=None, dx_lp=None, dgamma=None, dbeta=None, az=None, aw=None,
-                  beta=None, ssf_scale=None, dssf_scale=None, dssf_shift=None):
+                  beta=None, ssf_scale=None, dssf_scale=None, dssf_shift=None, prec=0):
     xh = (x - mean[:, None]) * rstd[:, None]
     g = torch.zeros_like(x)
     if dy is not None:

@@ -114,6 +114,51 @@ def test_rowproj_down_up_wgrad(dim, r, prec):
     close(got, want, 1e-4)
 
 
+@pytest.mark.parametrize('M,dim,r', [(1033, 768, 20), (16 * 300 + 5, 768, 20), (517, 384, 20), (2066, 768, 32), (9, 768, 8), (16 * 148 * 3, 768, 20)])
+def test_layernorm_bwd_tensor_core_forms(M, dim, r):
+    """prec = TF32: the two rank-r forms of the GAViKO backward (gvk.h) with the rank-r product as tf32 MMAs inside the LayerNorm pass.
+    Ragged row counts, more steps per CTA than the cp.async slots hold, in-place residual, parameter gradients."""
+    torch.manual_seed(M + dim + r)
+    x = torch.randn(M, dim, device=DEV) * 2 + 0.3
+    g = torch.randn(dim, device=DEV) * 0.1 + 1
+    be = torch.randn(dim, device=DEV) * 0.1
+    _, mean, rstd = ops.layernorm_fwd(x, g, be)
+    w = torch.randn(r, dim, device=DEV) / dim ** 0.5
+    dz = torch.randn(M, r, device=DEV)
+    dres = torch.randn(M, dim, device=DEV)
+    # form 0: dense bf16 dy + additive rank-r term + residual, bf16 copy
+    dy = torch.randn(M, dim, device=DEV).bfloat16()
+    xr = x.double().requires_grad_(True)
+    F.layer_norm(xr, (dim,), g.double(), be.double(), 1e-5).backward(dy.double())
+    want = xr.grad + dres.double() + dz.double() @ w.double()
+    dx_lp = torch.empty(M, dim, device=DEV, dtype=torch.bfloat16)
+    n0 = ops.L.launch_count()
+    got = ops.layernorm_bwd(x, g, mean, rstd, dy=dy, dres=dres, dx_lp=dx_lp, az=dz, aw=w, prec=ops.PREC_TF32)
+    assert ops.L.launch_count() == n0 + 1
+    close(got, want, 3e-3)
+    close(dx_lp, want, 1e-2)
+    exact = ops.layernorm_bwd(x, g, mean, rstd, dy=dy, dres=dres, az=dz, aw=w)
+    close(exact, want, 1e-4)
+    assert not torch.equal(exact, got)                      # the tf32 form really ran
+    got2 = ops.layernorm_bwd(x, g, mean, rstd, dy=dy, az=dz, aw=w, prec=ops.PREC_TF32)      # no residual
+    close(got2, want - dres.double(), 3e-3)
+    # form 1: rank-r dy, residual in place, parameter gradients
+    xr = x.double().requires_grad_(True)
+    gr, br = g.double().requires_grad_(True), be.double().requires_grad_(True)
+    (F.layer_norm(xr, (dim,), gr, br, 1e-5) @ w.double().t()).backward(dz.double())
+    dgam, dbet = torch.zeros(dim, device=DEV), torch.zeros(dim, device=DEV)
+    buf = dres.clone()
+    out = ops.layernorm_bwd(x, g, mean, rstd, dz=dz, w=w, dres=buf, dx=buf, dgamma=dgam, dbeta=dbet, prec=ops.PREC_TF32)
+    assert out.data_ptr() == buf.data_ptr()
+    close(out, xr.grad + dres.double(), 3e-3)
+    close(dgam, gr.grad, 3e-3)
+    close(dbet, br.grad, 3e-3)
+    dgam2, dbet2 = torch.zeros(dim, device=DEV), torch.zeros(dim, device=DEV)
+    exact = ops.layernorm_bwd(x, g, mean, rstd, dz=dz, w=w, dres=dres, dgamma=dgam2, dbeta=dbet2)
+    close(exact, xr.grad + dres.double(), 1e-4)
+    close(dgam2, gr.grad, 1e-4)
+
+
 @pytest.mark.parametrize('prec', [ops.PREC_FP32, ops.PREC_TF32])
 def test_rowproj_dropout_replay(prec):
     """The forward mask of rowproj_up is replayed by rowproj_down / skinny_wgrad in backward (same mask in both precisions)."""

@@ -1,0 +1,61 @@
+"""Time the LayerNorm-backward forms of the GAViKO step that carry a rank-20 product (d(g_mid) pass: dense bf16 dy + az @ aw; local-branch
+pass: dy = dz @ w with dgamma / dbeta) — exact-fp32 kernel vs the tensor-core kernels — against the HBM roofline.
+python tools/run_lnbwd.py [--batch 64]"""
+import argparse
+import json
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+from gaviko_b200 import ops  # noqa: E402
+from run_rowops import timeit  # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--batch', type=int, default=64)
+    ap.add_argument('--iters', type=int, default=10)
+    ap.add_argument('--flush', default='dirty', choices=['dirty', 'clean', 'none'])
+    a = ap.parse_args()
+    dim, r, peak = 768, 20, 6550.0
+    try:
+        peak = float(json.load(open(os.path.join(os.path.dirname(__file__), '..', 'MEASURED_PEAKS.json')))['hbm_gbs'])
+    except Exception:  # noqa: BLE001
+        pass
+    dev = 'cuda'
+    torch.manual_seed(0)
+    flush = torch.zeros(64 * 1024 * 1024, device=dev)
+    gamma = torch.rand(dim, device=dev) + 0.5
+    w = torch.randn(r, dim, device=dev) / dim ** 0.5
+    rows = []
+    for name, M in (('g_mid pass (bf16 dy + dres + az @ aw -> dx fp32 + bf16)', a.batch * 1033), ('local pass (dz @ w + dres in place + dgamma / dbeta)', a.batch * 1000)):
+        x = torch.randn(M, dim, device=dev)
+        mean, rstd = x.mean(1), 1.0 / x.var(1, unbiased=False).add(1e-5).sqrt()
+        dz = torch.randn(M, r, device=dev)
+        dres = torch.randn(M, dim, device=dev)
+        if name.startswith('g_mid'):
+            dy = torch.randn(M, dim, device=dev).bfloat16()
+            dx = torch.empty(M, dim, device=dev)
+            dx_lp = torch.empty(M, dim, device=dev, dtype=torch.bfloat16)
+            nbytes = M * dim * (4 + 2 + 4 + 4 + 2)
+            forms = {'exact fp32': ops.PREC_FP32, 'tensor-core (tf32 mma.sync, cp.async-staged streams)': ops.PREC_TF32}
+            def run(prec):
+                ops.layernorm_bwd(x, gamma, mean, rstd, dy=dy, dres=dres, dx=dx, dx_lp=dx_lp, az=dz, aw=w, prec=prec)
+        else:
+            dgam, dbet = torch.zeros(dim, device=dev), torch.zeros(dim, device=dev)
+            nbytes = M * dim * (4 + 4 + 4)
+            forms = {'exact fp32': ops.PREC_FP32, 'tensor-core (tf32 mma.sync, cp.async-staged streams)': ops.PREC_TF32}
+            def run(prec):
+                ops.layernorm_bwd(x, gamma, mean, rstd, dz=dz, w=w, dres=dres, dx=dres, dgamma=dgam, dbeta=dbet, prec=prec)
+        for form, prec in forms.items():
+            us = timeit(lambda: run(prec), a.iters, flush, a.flush)
+            rows.append(dict(kernel=name, form=form, M=M, us=round(us, 1), gbps=round(nbytes / us / 1e3, 1), frac_of_copy_peak=round(nbytes / us / 1e3 / peak, 3),
+                             roofline_us=round(nbytes / peak / 1e3, 1)))
+            print(json.dumps(rows[-1]), flush=True)
+
+
+if __name__ == '__main__':
+    main()
