@@ -146,7 +146,7 @@ long long gvk_struct_size(const char* name) {
   GVK_SZ(gvk_fusion_weights) GVK_SZ(gvk_fusion_grads) GVK_SZ(gvk_fusion_saved) GVK_SZ(gvk_fusion_fwd_params)
   GVK_SZ(gvk_fusion_bwd_params) GVK_SZ(gvk_head_fwd_params) GVK_SZ(gvk_head_bwd_params) GVK_SZ(gvk_mhsa_fwd_params) GVK_SZ(gvk_mhsa_bwd_params) GVK_SZ(gvk_rescale_intensity_params)
   GVK_SZ(gvk_latent_xattn_fwd_params) GVK_SZ(gvk_latent_xattn_bwd_params) GVK_SZ(gvk_patch_embed_params)
-  GVK_SZ(gvk_wgrad_params) GVK_SZ(gvk_hfreq_filter_params)
+  GVK_SZ(gvk_wgrad_params) GVK_SZ(gvk_hfreq_filter_params) GVK_SZ(gvk_layernorm_fwd_down_params)
 #undef GVK_SZ
   return -1;
 }
@@ -155,6 +155,7 @@ long long gvk_struct_size(const char* name) {
 int gvk_gemm(const gvk_gemm_params* p, gvk_stream_t stream) { return gvk::gemm_dispatch(p, S(stream)); }
 int gvk_layernorm_fwd(const gvk_layernorm_fwd_params* p, gvk_stream_t stream) { return gvk::layernorm_fwd(p, S(stream)); }
 int gvk_layernorm_bwd(const gvk_layernorm_bwd_params* p, gvk_stream_t stream) { return gvk::layernorm_bwd(p, S(stream)); }
+int gvk_layernorm_fwd_down(const gvk_layernorm_fwd_down_params* p, gvk_stream_t stream) { return gvk::layernorm_fwd_down(p, S(stream)); }
 int gvk_rowproj_down(const gvk_rowproj_down_params* p, gvk_stream_t stream) { return gvk::rowproj_down(p, S(stream)); }
 int gvk_rowproj_up(const gvk_rowproj_up_params* p, gvk_stream_t stream) { return gvk::rowproj_up(p, S(stream)); }
 int gvk_skinny_wgrad(const gvk_skinny_wgrad_params* p, gvk_stream_t stream) { return gvk::skinny_wgrad(p, S(stream)); }

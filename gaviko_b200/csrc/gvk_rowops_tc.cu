@@ -696,7 +696,8 @@ bool skinny_wgrad_tc_supported(const gvk_skinny_wgrad_params* p) {
 // One CTA per SM.  The three row streams (x, dy, dres) of the NEXT step travel by cp.async into thread-private shared-memory slots while
 // the current step is computed: a thread re-fills a slot right after it has read it, so ~120 KB per SM are in flight all the time and no
 // warp waits on a load it has just issued.  (Measured at M = 66 112, dim 768, r 20: exact kernel 238 us; this layout with two CTAs per SM
-// and plain loads 227 us; one CTA with the next step's x / dy prefetched into registers 182 us; profiles/lnbwd_tc_r02*.jsonl.)
+// and plain loads 227 us; one CTA with the next step's x / dy prefetched into registers 182 us; this form 156 us; the same with 16 warps of
+// three column groups each 186 us — narrower per-warp row segments cost more than the extra warps hide; profiles/lnbwd_tc_r02*.jsonl.)
 // =================================================================================================
 __device__ __forceinline__ float4 bf16x4_to_float4(uint2 v) {
   const float2 lo = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&v.x));
@@ -982,6 +983,181 @@ int layernorm_bwd_tc(const gvk_layernorm_bwd_params* p, cudaStream_t stream) {
       return GVK_ERR_UNSUPPORTED;
   }
 #undef GVK_LNB_TC
+}
+
+
+// =================================================================================================
+// LayerNorm forward + rank-r down-projection of the SAME rows in one pass over x:
+//   y = LN(x) gamma + beta (bf16),  mean / rstd saved;     z = act(x W^T + bias), pre = the pre-activation.
+// In the GAViKO layer both FeedForward's LayerNorm (model/vision_transformer.py:30) and Awakening_Prompt.proj_down (model/gaviko.py:155-156)
+// read the residual stream g_mid; as two kernels (layernorm_fwd 59 us + tc_down 54 us at M = 66 k) the 203 MB stream is read twice.
+// Same CTA layout as ln_bwd_tc_kernel: a CTA owns 16 rows per step, warp w the columns [w dim/8, (w+1) dim/8); x of the next step
+// travels by cp.async into thread-private slots.  The lane's x registers are tc_down's A fragments (k slot t <-> column 4t, t+4 <-> 4t+1,
+// second MMA 4t+2 / 4t+3), so each warp accumulates a [16, r] partial over its columns; partial products and row sums (sum x, sum x^2)
+// are exchanged through shared memory with one __syncthreads per step (double-buffered).
+// =================================================================================================
+template <int NITER, int NT>
+struct LnFwdDown {
+  static constexpr int dim = NITER * 64, S = dim + 16, GW = NITER / 2, RP = NT * 8;
+  static constexpr int kSlots = GW * 2 * kTcThreads;
+  static constexpr int kZ = kTcWarps * 16 * RP;            // floats of one partial-product exchange buffer
+  static constexpr size_t kSmem = ((size_t)RP * S + 2 * dim + RP) * sizeof(float) + 2 * 16 * kTcWarps * sizeof(float2) + 2 * (size_t)kZ * sizeof(float) +
+                                  (size_t)kSlots * sizeof(float4);
+};
+
+template <int NITER, int NT>
+__global__ void __launch_bounds__(kTcThreads, 1) ln_fwd_down_tc_kernel(gvk_layernorm_fwd_down_params p) {
+  using L = LnFwdDown<NITER, NT>;
+  constexpr int dim = L::dim, S = L::S, GW = L::GW, RP = L::RP;
+  extern __shared__ __align__(16) float smem[];
+  float* sW = smem;                                       // [RP][S] tf32 panel
+  float* s_gamma = sW + RP * S;                           // [dim]
+  float* s_beta = s_gamma + dim;                          // [dim]
+  float* s_bias = s_beta + dim;                           // [RP]
+  float2* red = reinterpret_cast<float2*>(s_bias + RP);   // [2][16][kTcWarps]  (sum x, sum x^2)
+  float* zbuf = reinterpret_cast<float*>(red + 2 * 16 * kTcWarps);   // [2][kTcWarps][16][RP]
+  float4* s_x = reinterpret_cast<float4*>(zbuf + 2 * L::kZ);          // [GW][2][kTcThreads]
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+  const int ntiles = (p.M + 15) / 16;
+  const float inv_dim = 1.0f / dim;
+  const int cw = warp * 16 * GW + 4 * t;
+  auto slot = [&](int kk, int row) { return (kk * 2 + row) * kTcThreads + tid; };
+  auto fetch_x = [&](int tile, int kk) {
+    const size_t cA = (size_t)min(tile * 16 + g, p.M - 1), cB = (size_t)min(tile * 16 + g + 8, p.M - 1);
+    cp_async16(s_x + slot(kk, 0), p.x + cA * p.ldx + cw + 16 * kk);
+    cp_async16(s_x + slot(kk, 1), p.x + cB * p.ldx + cw + 16 * kk);
+  };
+  if ((int)blockIdx.x < ntiles) {
+#pragma unroll
+    for (int kk = 0; kk < GW; ++kk) fetch_x(blockIdx.x, kk);
+  }
+  cp_async_commit();
+  tc_stage_panel<RP, S, false>(sW, p.w, p.r, dim, p.w_sj, p.w_sc, nullptr);
+  for (int c = tid; c < dim; c += kTcThreads) {
+    s_gamma[c] = p.gamma[c];
+    s_beta[c] = p.beta[c];
+  }
+  if (tid < RP) s_bias[tid] = (p.bias && tid < p.r) ? p.bias[tid] : 0.f;
+  __syncthreads();
+  __nv_bfloat16* yp = reinterpret_cast<__nv_bfloat16*>(p.y);
+  int buf = 0;
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, buf ^= 1) {
+    const int rA = tile * 16 + g, rB = rA + 8;
+    const int next = tile + gridDim.x;
+    const bool has_next = next < ntiles;
+    cp_async_wait<0>();
+    float4 xa[GW], xb[GW];
+    float acc[NT][4];
+#pragma unroll
+    for (int j = 0; j < NT; ++j) acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f;
+    float sA = 0.f, qA = 0.f, sB = 0.f, qB = 0.f;
+#pragma unroll
+    for (int kk = 0; kk < GW; ++kk) {
+      xa[kk] = s_x[slot(kk, 0)];
+      xb[kk] = s_x[slot(kk, 1)];
+      if (has_next) fetch_x(next, kk);                    // the slots just read are free again
+      sA += (xa[kk].x + xa[kk].y) + (xa[kk].z + xa[kk].w);
+      qA = fmaf(xa[kk].x, xa[kk].x, fmaf(xa[kk].y, xa[kk].y, fmaf(xa[kk].z, xa[kk].z, fmaf(xa[kk].w, xa[kk].w, qA))));
+      sB += (xb[kk].x + xb[kk].y) + (xb[kk].z + xb[kk].w);
+      qB = fmaf(xb[kk].x, xb[kk].x, fmaf(xb[kk].y, xb[kk].y, fmaf(xb[kk].z, xb[kk].z, fmaf(xb[kk].w, xb[kk].w, qB))));
+      const uint32_t ax = f2tf32(xa[kk].x), ay = f2tf32(xa[kk].y), az = f2tf32(xa[kk].z), aw = f2tf32(xa[kk].w);
+      const uint32_t bx = f2tf32(xb[kk].x), by = f2tf32(xb[kk].y), bz = f2tf32(xb[kk].z), bw = f2tf32(xb[kk].w);
+#pragma unroll
+      for (int j = 0; j < NT; ++j) {
+        const float4 w = *reinterpret_cast<const float4*>(sW + (8 * j + g) * S + cw + 16 * kk);
+        mma_tf32(acc[j], ax, bx, ay, by, __float_as_uint(w.x), __float_as_uint(w.y));
+        mma_tf32(acc[j], az, bz, aw, bw, __float_as_uint(w.z), __float_as_uint(w.w));
+      }
+    }
+    cp_async_commit();
+    sA += __shfl_xor_sync(0xffffffffu, sA, 1); sA += __shfl_xor_sync(0xffffffffu, sA, 2);
+    qA += __shfl_xor_sync(0xffffffffu, qA, 1); qA += __shfl_xor_sync(0xffffffffu, qA, 2);
+    sB += __shfl_xor_sync(0xffffffffu, sB, 1); sB += __shfl_xor_sync(0xffffffffu, sB, 2);
+    qB += __shfl_xor_sync(0xffffffffu, qB, 1); qB += __shfl_xor_sync(0xffffffffu, qB, 2);
+    float2* rbuf = red + buf * 16 * kTcWarps;
+    float* zb = zbuf + buf * L::kZ;
+    if (t == 0) {
+      rbuf[g * kTcWarps + warp] = make_float2(sA, qA);
+      rbuf[(g + 8) * kTcWarps + warp] = make_float2(sB, qB);
+    }
+#pragma unroll
+    for (int j = 0; j < NT; ++j) {
+      *reinterpret_cast<float2*>(zb + (warp * 16 + g) * RP + 8 * j + 2 * t) = make_float2(acc[j][0], acc[j][1]);
+      *reinterpret_cast<float2*>(zb + (warp * 16 + g + 8) * RP + 8 * j + 2 * t) = make_float2(acc[j][2], acc[j][3]);
+    }
+    __syncthreads();
+    float mA = 0.f, vA = 0.f, mB = 0.f, vB = 0.f;
+#pragma unroll
+    for (int w = 0; w < kTcWarps; w += 2) {
+      const float4 a4 = *reinterpret_cast<const float4*>(rbuf + g * kTcWarps + w);
+      const float4 b4 = *reinterpret_cast<const float4*>(rbuf + (g + 8) * kTcWarps + w);
+      mA += a4.x + a4.z; vA += a4.y + a4.w;
+      mB += b4.x + b4.z; vB += b4.y + b4.w;
+    }
+    mA *= inv_dim; mB *= inv_dim;
+    const float rsA = rsqrtf(fmaxf(vA * inv_dim - mA * mA, 0.f) + p.eps), rsB = rsqrtf(fmaxf(vB * inv_dim - mB * mB, 0.f) + p.eps);
+    if (warp == 0 && t == 0) {
+      if (rA < p.M) { if (p.mean) p.mean[rA] = mA; if (p.rstd) p.rstd[rA] = rsA; }
+      if (rB < p.M) { if (p.mean) p.mean[rB] = mB; if (p.rstd) p.rstd[rB] = rsB; }
+    }
+    // ---- the rank-r output of the step: 16 x RP sums over the 8 warps' partials
+    for (int idx = tid; idx < 16 * RP; idx += kTcThreads) {
+      const int row = idx / RP, n = idx - row * RP;
+      float z = 0.f;
+#pragma unroll
+      for (int w = 0; w < kTcWarps; ++w) z += zb[w * 16 * RP + idx];
+      const int m = tile * 16 + row;
+      if (n < p.r && m < p.M) {
+        z += s_bias[n];
+        if (p.pre) p.pre[(size_t)m * p.ldz + n] = z;
+        if (p.act == GVK_ROWACT_QUICKGELU) z = quick_gelu(z);
+        else if (p.act == GVK_ROWACT_RELU) z = fmaxf(z, 0.f);
+        p.z[(size_t)m * p.ldz + n] = z;
+      }
+    }
+    // ---- y = (x - mean) rstd gamma + beta
+#pragma unroll
+    for (int kk = 0; kk < GW; ++kk) {
+      const int col = cw + 16 * kk;
+      const float4 gam = *reinterpret_cast<const float4*>(s_gamma + col);
+      const float4 bet = *reinterpret_cast<const float4*>(s_beta + col);
+      if (rA < p.M) {
+        __nv_bfloat162 lo = __floats2bfloat162_rn(fmaf((xa[kk].x - mA) * rsA, gam.x, bet.x), fmaf((xa[kk].y - mA) * rsA, gam.y, bet.y));
+        __nv_bfloat162 hi = __floats2bfloat162_rn(fmaf((xa[kk].z - mA) * rsA, gam.z, bet.z), fmaf((xa[kk].w - mA) * rsA, gam.w, bet.w));
+        *reinterpret_cast<uint2*>(yp + (size_t)rA * p.ldy + col) = make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
+      }
+      if (rB < p.M) {
+        __nv_bfloat162 lo = __floats2bfloat162_rn(fmaf((xb[kk].x - mB) * rsB, gam.x, bet.x), fmaf((xb[kk].y - mB) * rsB, gam.y, bet.y));
+        __nv_bfloat162 hi = __floats2bfloat162_rn(fmaf((xb[kk].z - mB) * rsB, gam.z, bet.z), fmaf((xb[kk].w - mB) * rsB, gam.w, bet.w));
+        *reinterpret_cast<uint2*>(yp + (size_t)rB * p.ldy + col) = make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
+      }
+    }
+  }
+  cp_async_wait<0>();
+}
+
+template <int NITER, int NT>
+static int ln_fwd_down_launch(const gvk_layernorm_fwd_down_params* p, cudaStream_t stream) {
+  constexpr size_t smem = LnFwdDown<NITER, NT>::kSmem;
+  static_assert(smem <= 227 * 1024, "layernorm_fwd_down: shared memory");
+  static const int attr = cudaFuncSetAttribute(ln_fwd_down_tc_kernel<NITER, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (attr != cudaSuccess) return cuda_status((cudaError_t)attr, "layernorm_fwd_down (smem attribute)");
+  const int ntiles = (p->M + 15) / 16;
+  ln_fwd_down_tc_kernel<NITER, NT><<<std::max(1, std::min(ntiles, sm_count())), kTcThreads, smem, stream>>>(*p);
+  GVK_CHECK_LAUNCH("layernorm_fwd_down");
+  return GVK_OK;
+}
+
+int layernorm_fwd_down(const gvk_layernorm_fwd_down_params* p, cudaStream_t stream) {
+  GVK_CHECK_ARG(p && p->x && p->gamma && p->beta && p->y && p->w && p->z && p->M > 0, "gvk_layernorm_fwd_down: null pointer");
+  GVK_CHECK_ARG(p->dim == 384 || p->dim == 768, "gvk_layernorm_fwd_down: dim %d (384 or 768)", p->dim);
+  GVK_CHECK_ARG(p->r >= 1 && p->r <= 32, "gvk_layernorm_fwd_down: r=%d (1..32)", p->r);
+  GVK_CHECK_ARG((reinterpret_cast<uintptr_t>(p->x) & 15) == 0 && p->ldx % 4 == 0 && (reinterpret_cast<uintptr_t>(p->y) & 7) == 0 && p->ldy % 4 == 0,
+                "gvk_layernorm_fwd_down: x must be 16-byte and y 8-byte aligned, leading dimensions multiples of 4");
+#define GVK_LFD(NITER) return p->r <= 24 ? ln_fwd_down_launch<NITER, 3>(p, stream) : ln_fwd_down_launch<NITER, 4>(p, stream);
+  if (p->dim == 384) { GVK_LFD(6) }
+  GVK_LFD(12)
+#undef GVK_LFD
 }
 
 }  // namespace gvk

@@ -255,12 +255,18 @@ class GavikoEngine:
             o, lse = self.mhsa_fwd(qkv, B, T, H, D, H * D)
             g_mid = ops.gemm(o, Lw['wo'], bias=Lw['bo'], res1=g)
             # ---- Awakening_Prompt (model/gaviko.py:149-187)
-            dg = ops.rowproj_down(g_mid, Fu['wd'], Fu['bd'], act=ops.ROWACT_QUICKGELU, save_pre=save, prec=pr)
+            fuse_ln2 = cdt == torch.bfloat16 and ops.layernorm_fwd_down_supported(g_mid, Fu['wd'].shape[0])
+            if fuse_ln2:     # one pass over g_mid for its two readers: FeedForward's LayerNorm (below) and proj_down
+                h2, mean2, rstd2, dg = ops.layernorm_fwd_down(g_mid, Lw['ln2_w'], Lw['ln2_b'], Fu['wd'], Fu['bd'], act=ops.ROWACT_QUICKGELU, save_pre=save,
+                                                              save_stats=save)
+            else:
+                dg = ops.rowproj_down(g_mid, Fu['wd'], Fu['bd'], act=ops.ROWACT_QUICKGELU, save_pre=save, prec=pr)
             dl = ops.rowproj_down(loc_new, Fu['wd'], Fu['bd'], act=ops.ROWACT_QUICKGELU, save_pre=save, prec=pr)
             comb, ll = dg['z'], dl['z']
             fsaved = ops.prompt_fusion_fwd(comb, ll, Fu['k'], B, T, N, P)      # comb: xl -> combined latent, in place
             # ---- frozen MLP (model/vision_transformer.py:26-38, residual + prompt gaviko.py:304)
-            h2, mean2, rstd2 = ops.layernorm_fwd(g_mid, Lw['ln2_w'], Lw['ln2_b'], out_dtype=cdt, save_stats=save)
+            if not fuse_ln2:
+                h2, mean2, rstd2 = ops.layernorm_fwd(g_mid, Lw['ln2_w'], Lw['ln2_b'], out_dtype=cdt, save_stats=save)
             hpre = torch.empty((B * T, c['mlp_dim']), device=img.device, dtype=cdt) if save else None
             mlp = c['mlp_dim']
             if 'w2x' in Lw and 3 * r_p <= _KEXT:

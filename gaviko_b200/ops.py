@@ -97,6 +97,28 @@ def layernorm_fwd(x, gamma, beta, *, out=None, out_dtype=torch.float32, eps=1e-5
     return out, mean, rstd
 
 
+def layernorm_fwd_down(x, gamma, beta, w, bias=None, *, act=ROWACT_NONE, save_pre=False, eps=1e-5, save_stats=True):
+    """One pass over x (bf16 compute mode): y = LN(x) gamma + beta as bf16 (+ mean, rstd) and z = act(x @ w^T + bias) on the RAW rows
+    (gvk_layernorm_fwd_down; w [r, dim]).  Returns (y, mean, rstd, dict(z, pre))."""
+    M, dim = x.shape
+    r = w.shape[0]
+    sj, sc = _wstrides(w, r, dim, False)
+    y = torch.empty((M, dim), device=x.device, dtype=torch.bfloat16)
+    mean = torch.empty(M, device=x.device, dtype=torch.float32) if save_stats else None
+    rstd = torch.empty(M, device=x.device, dtype=torch.float32) if save_stats else None
+    z = torch.empty((M, r), device=x.device, dtype=torch.float32)
+    pre = torch.empty_like(z) if save_pre else None
+    p = S['gvk_layernorm_fwd_down_params']()
+    _set(p, x=L.ptr(x, torch.float32), ldx=_ld(x), M=M, dim=dim, gamma=L.fptr(gamma), beta=L.fptr(beta), eps=eps, y=y, ldy=dim, mean=mean, rstd=rstd,
+         w=L.ptr(w, torch.float32), w_sj=sj, w_sc=sc, bias=L.fptr(bias), r=r, act=act, pre=pre, z=z, ldz=r)
+    L.call('gvk_layernorm_fwd_down', C.byref(p), L.stream())
+    return y, mean, rstd, dict(z=z, pre=pre)
+
+
+def layernorm_fwd_down_supported(x, r):
+    return x.shape[1] in (384, 768) and r <= 32 and 'down' not in _TF32_OFF
+
+
 def _wstrides(w, r, dim, transposed):
     """(w_sj, w_sc) of element (j, c) for an nn.Linear weight: [r, dim] (transposed=False) or [dim, r] (True)."""
     if not w.is_contiguous():

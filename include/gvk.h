@@ -140,6 +140,21 @@ typedef struct {
 } gvk_rowproj_down_params;
 int gvk_rowproj_down(const gvk_rowproj_down_params* p, gvk_stream_t stream);
 
+/* LayerNorm forward and a rank-r down-projection of the RAW rows in one pass over x (bf16 compute mode):
+ *   y = LayerNorm(x) * gamma + beta  (bf16; mean / rstd optional),   z = act(x W^T + bias),  pre (optional) = the pre-activation.
+ * The two readers of the residual stream after attention in a GAViKO layer: FeedForward's norm (model/vision_transformer.py:30, called at
+ * model/gaviko.py:304) and Awakening_Prompt.proj_down (model/gaviko.py:155-156).  The rank-r product runs as tf32 mma.sync (GVK_PREC_TF32
+ * arithmetic); dim 384 or 768, r <= 32, w(j, c) strided like gvk_rowproj_down's. */
+typedef struct {
+  const float* x; int ldx; int M, dim;
+  const float* gamma; const float* beta; float eps;
+  void* y; int ldy;
+  float* mean; float* rstd;
+  const float* w; int w_sj, w_sc; const float* bias; int r; int act;
+  float* pre; float* z; int ldz;
+} gvk_layernorm_fwd_down_params;
+int gvk_layernorm_fwd_down(const gvk_layernorm_fwd_down_params* p, gvk_stream_t stream);
+
 /* out[m, c] = res[m, c] + dropout( sum_j c[m, j] * w(j, c) + bias[c] );  out_lp is an optional bf16 copy of out.
  * Replaces LocalSelfAttention.proj_up + proj_drop + residual (model/gaviko.py:242-243, 301), Awakening_Prompt.proj_up
  * (model/gaviko.py:187) and, with transposed strides, the dgrad of every rank-r down-projection. */

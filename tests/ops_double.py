@@ -97,6 +97,16 @@ def layernorm_fwd(x, gamma, beta, *, out=None, out_dtype=torch.float32, eps=1e-5
     return out, (mean if save_stats else None), (rstd if save_stats else None)
 
 
+def layernorm_fwd_down(x, gamma, beta, w, bias=None, *, act=ROWACT_NONE, save_pre=False, eps=1e-5, save_stats=True):
+    y, mean, rstd = layernorm_fwd(x, gamma, beta, out_dtype=torch.bfloat16, eps=eps, save_stats=save_stats)
+    d = rowproj_down(x, w, bias, act=act, save_pre=save_pre)
+    return y, mean, rstd, dict(z=d['z'], pre=d['pre'])
+
+
+def layernorm_fwd_down_supported(x, r):
+    return x.shape[1] in (384, 768) and r <= 32
+
+
 def rowproj_down(x, w, bias=None, *, transposed=False, ln=None, eps=1e-5, act=ROWACT_NONE, save_pre=False, w2=None, drop_p=0.0, seed=0, offset=0, prec=PREC_FP32):
     mean = rstd = z2 = None
     k = _keep(x.shape, drop_p, seed, offset)

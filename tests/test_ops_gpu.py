@@ -159,6 +159,37 @@ def test_layernorm_bwd_tensor_core_forms(M, dim, r):
     close(dgam2, gr.grad, 1e-4)
 
 
+@pytest.mark.parametrize('save', [True, False])
+@pytest.mark.parametrize('M,dim,r', [(1033, 768, 20), (16 * 148 * 2 + 7, 768, 20), (517, 384, 20), (2066, 768, 32), (9, 768, 8)])
+def test_layernorm_fwd_down_one_pass(M, dim, r, save):
+    """gvk_layernorm_fwd_down: the LayerNorm output (bf16, + statistics) and the QuickGELU down-projection of the raw rows from one read of x."""
+    torch.manual_seed(M + dim + r)
+    x = torch.randn(M, dim, device=DEV) * 2 + 0.3
+    g = torch.randn(dim, device=DEV) * 0.1 + 1
+    be = torch.randn(dim, device=DEV) * 0.1
+    w = torch.randn(r, dim, device=DEV) / dim ** 0.5
+    b = torch.randn(r, device=DEV) * 0.1
+    n0 = ops.L.launch_count()
+    y, mean, rstd, d = ops.layernorm_fwd_down(x, g, be, w, b, act=ops.ROWACT_QUICKGELU, save_pre=save, save_stats=save)
+    assert ops.L.launch_count() == n0 + 1
+    yr = F.layer_norm(x.double(), (dim,), g.double(), be.double(), 1e-5)
+    assert y.dtype == torch.bfloat16
+    close(y, yr, 1e-2)
+    y2, mean2, rstd2 = ops.layernorm_fwd(x, g, be, out_dtype=torch.bfloat16)
+    assert (y.float() - y2.float()).abs().max().item() <= 2 ** -6 * yr.abs().max().item()      # at most a bf16 rounding step apart from the two-kernel path
+    pre = x.double() @ w.double().t() + b.double()
+    close(d['z'], pre * torch.sigmoid(1.702 * pre), 3e-3)
+    if save:
+        close(d['pre'], pre, 3e-3)
+        close(mean, x.double().mean(1), 1e-5)
+        close(rstd, 1.0 / (x.double().var(1, unbiased=False) + 1e-5).sqrt(), 1e-5)
+    else:
+        assert d['pre'] is None and mean is None and rstd is None
+    # no bias, no activation
+    _, _, _, d2 = ops.layernorm_fwd_down(x, g, be, w)
+    close(d2['z'], x.double() @ w.double().t(), 3e-3)
+
+
 @pytest.mark.parametrize('prec', [ops.PREC_FP32, ops.PREC_TF32])
 def test_rowproj_dropout_replay(prec):
     """The forward mask of rowproj_up is replayed by rowproj_down / skinny_wgrad in backward (same mask in both precisions)."""

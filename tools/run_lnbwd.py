@@ -55,6 +55,27 @@ def main():
             rows.append(dict(kernel=name, form=form, M=M, us=round(us, 1), gbps=round(nbytes / us / 1e3, 1), frac_of_copy_peak=round(nbytes / us / 1e3 / peak, 3),
                              roofline_us=round(nbytes / peak / 1e3, 1)))
             print(json.dumps(rows[-1]), flush=True)
+    forward_pair(a, peak)
+
+
+def forward_pair(a, peak):
+    """FeedForward's LayerNorm + Awakening_Prompt.proj_down on g_mid: two kernels vs gvk_layernorm_fwd_down."""
+    dev, dim, r = 'cuda', 768, 20
+    M = a.batch * 1033
+    flush = torch.zeros(64 * 1024 * 1024, device=dev)
+    x = torch.randn(M, dim, device=dev)
+    gamma, beta = torch.rand(dim, device=dev) + 0.5, torch.randn(dim, device=dev) * 0.1
+    w, b = torch.randn(r, dim, device=dev) / dim ** 0.5, torch.randn(r, device=dev) * 0.1
+    y = torch.empty(M, dim, device=dev, dtype=torch.bfloat16)
+    forms = {
+        'layernorm_fwd (bf16 out)': (lambda: ops.layernorm_fwd(x, gamma, beta, out=y), M * dim * 6),
+        'rowproj_down (tf32, QuickGELU, pre saved)': (lambda: ops.rowproj_down(x, w, b, act=ops.ROWACT_QUICKGELU, save_pre=True, prec=ops.PREC_TF32), M * dim * 4),
+        'layernorm_fwd_down (one pass)': (lambda: ops.layernorm_fwd_down(x, gamma, beta, w, b, act=ops.ROWACT_QUICKGELU, save_pre=True), M * dim * 6),
+    }
+    for form, (fn, nbytes) in forms.items():
+        us = timeit(fn, a.iters, flush, a.flush)
+        print(json.dumps(dict(kernel='g_mid forward readers', form=form, M=M, us=round(us, 1), gbps=round(nbytes / us / 1e3, 1),
+                              frac_of_copy_peak=round(nbytes / us / 1e3 / peak, 3), roofline_us=round(nbytes / peak / 1e3, 1))), flush=True)
 
 
 if __name__ == '__main__':
