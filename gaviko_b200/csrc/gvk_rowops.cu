@@ -835,7 +835,12 @@ int layernorm_bwd(const gvk_layernorm_bwd_params* p, cudaStream_t stream) {
   GVK_CHECK_ARG(!p->ssf_scale || p->beta, "gvk_layernorm_bwd: the SSF form needs beta (to rebuild the LayerNorm output)");
   GVK_CHECK_ARG(!p->dz || (p->w && p->r >= 1 && p->r <= 32), "gvk_layernorm_bwd: rank-r form needs w and 1 <= r <= 32");
   GVK_CHECK_ARG(!p->az || (p->aw && p->ra >= 1 && p->ra <= 32), "gvk_layernorm_bwd: additive rank term needs aw and 1 <= ra <= 32");
+  GVK_CHECK_ARG(!p->ow || (p->oz && p->orank >= 1 && p->orank <= 32), "gvk_layernorm_bwd: output projection needs oz and 1 <= orank <= 32");
   if (p->precision == GVK_PREC_TF32 && layernorm_bwd_tc_supported(p)) return layernorm_bwd_tc(p, stream);
+  if (p->ow) {
+    set_last_error("gvk_layernorm_bwd: the output projection exists in the tensor-core form only (precision TF32, dense bf16 dy, no az / dz / dgamma / dbeta, dim 384 or 768)");
+    return GVK_ERR_UNSUPPORTED;
+  }
   const bool red = p->dgamma || p->dbeta || p->ssf_scale;
   const size_t smem = ((p->dz ? (size_t)p->r * p->dim : 0) + (p->az ? (size_t)p->ra * p->dim : 0) + (red ? (size_t)kRowWarps * 2 * p->dim : 0)) * sizeof(float);
   if (smem > 227 * 1024) {

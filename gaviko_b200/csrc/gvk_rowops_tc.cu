@@ -708,29 +708,38 @@ __device__ __forceinline__ void cp_async8(void* smem_dst, const void* gsrc) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
 }
 
-template <int NITER, int KS, int MODE>
+template <int NITER, int KS, int MODE, bool DOWN>
 struct LnbTc {
   static constexpr int dim = NITER * 64, S = dim + 8, GW = NITER / 2, RP = KS * 8;
+  static constexpr int S2 = dim + 16;                      // DOWN: the output projection's panel in tc_down's layout
   static constexpr int kSlots = GW * 2 * kTcThreads;       // one 16-byte (x, dres) or 8-byte (dy) slot per (column group, row, thread)
-  static constexpr size_t kSmem = ((size_t)RP * S + dim) * sizeof(float) + 2 * 16 * kTcWarps * sizeof(float2) + 2 * (size_t)kSlots * sizeof(float4) +
-                                  (MODE == 0 ? (size_t)kSlots * sizeof(uint2) : 0);
+  static constexpr int kZ = kTcWarps * 16 * RP;            // DOWN: floats of one partial-product exchange buffer
+  static constexpr size_t kSmem = ((size_t)RP * (DOWN ? S2 : S) + dim) * sizeof(float) + 2 * 16 * kTcWarps * sizeof(float2) + 2 * (size_t)kSlots * sizeof(float4) +
+                                  (MODE == 0 ? (size_t)kSlots * sizeof(uint2) : 0) + (DOWN ? 2 * (size_t)kZ * sizeof(float) : 0);
 };
 
-template <int NITER, int KS, int MODE, bool PGRAD>
+// DOWN (MODE 0 without the additive term): the kernel also projects its OUTPUT rows, oz = dx @ ow^T (rank <= 8 KS) — the next consumer of
+// the residual gradient in the GAViKO backward is the dgrad of Awakening_Prompt.proj_up (d(comb) = dG Wu, model/gaviko.py:187), which
+// otherwise re-reads the 203 MB stream this kernel has just written.  The output registers are tc_down's A fragments; the per-warp
+// partial products of a step are summed by the whole CTA after the NEXT step's barrier (no second barrier per step).
+template <int NITER, int KS, int MODE, bool PGRAD, bool DOWN>
 __global__ void __launch_bounds__(kTcThreads, 1) ln_bwd_tc_kernel(gvk_layernorm_bwd_params p) {
-  using L = LnbTc<NITER, KS, MODE>;
-  constexpr int dim = L::dim, S = L::S, GW = L::GW, RP = L::RP;
+  using L = LnbTc<NITER, KS, MODE, DOWN>;
+  constexpr int dim = L::dim, S = L::S, GW = L::GW, RP = L::RP, S2 = L::S2;
+  constexpr bool RANK = !DOWN;                            // the rank-r product of MODE 0 / MODE 1
   static_assert(NITER % 2 == 0, "dim must be a multiple of 128");
+  static_assert(!DOWN || (MODE == 0 && !PGRAD), "output projection: dense-dy form only");
   extern __shared__ __align__(16) float smem[];
   float* sW = smem;                                       // [RP][S] tf32 panel, two low column bits of every 16-column group swapped
-  float* s_gamma = sW + RP * S;                           // [dim]
+  float* s_gamma = sW + RP * (DOWN ? S2 : S);             // [dim]
   float2* red = reinterpret_cast<float2*>(s_gamma + dim); // [2][16][kTcWarps]
   float4* s_x = reinterpret_cast<float4*>(red + 2 * 16 * kTcWarps);   // [GW][2][kTcThreads]
   float4* s_r = s_x + L::kSlots;
   uint2* s_y = reinterpret_cast<uint2*>(s_r + L::kSlots);  // MODE 0: raw bf16 x 4
+  float* zbuf = reinterpret_cast<float*>(s_y + (MODE == 0 ? L::kSlots : 0));   // DOWN: [2][kTcWarps][16][RP]
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
   const float* rsrc = MODE == 0 ? p.az : p.dz;            // [M, r] latent operand of the rank-r product
-  const int rld = MODE == 0 ? p.ld_az : p.ld_dz, rr = MODE == 0 ? p.ra : p.r;
+  const int rld = MODE == 0 ? p.ld_az : p.ld_dz, rr = RANK ? (MODE == 0 ? p.ra : p.r) : 0;
   const int ntiles = (p.M + 15) / 16;
   const float inv_dim = 1.0f / dim;
   const int cw = warp * 16 * GW + 4 * t;                  // this lane's first column
@@ -755,7 +764,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) ln_bwd_tc_kernel(gvk_layernorm_
   auto load_lat = [&](int tile, Lat& T) {
     const size_t cA = row_a(tile), cB = row_b(tile);
 #pragma unroll
-    for (int s = 0; s < KS; ++s) {
+    for (int s = 0; s < (RANK ? KS : 0); ++s) {
       const int k0 = 8 * s + t, k1 = k0 + 4;
       T.v[s][0] = k0 < rr ? rsrc[cA * rld + k0] : 0.f;
       T.v[s][1] = k0 < rr ? rsrc[cB * rld + k0] : 0.f;
@@ -777,13 +786,24 @@ __global__ void __launch_bounds__(kTcThreads, 1) ln_bwd_tc_kernel(gvk_layernorm_
   }
   cp_async_commit();
   if ((int)blockIdx.x < ntiles) load_lat(blockIdx.x, cur);
-  if (MODE == 0) tc_stage_panel<RP, S, true>(sW, p.aw, p.ra, dim, p.aw_sj, p.aw_sc, nullptr);
+  if (DOWN) tc_stage_panel<RP, S2, false>(sW, p.ow, p.orank, dim, p.ow_sj, p.ow_sc, nullptr);
+  else if (MODE == 0) tc_stage_panel<RP, S, true>(sW, p.aw, p.ra, dim, p.aw_sj, p.aw_sc, nullptr);
   else tc_stage_panel<RP, S, true>(sW, p.w, p.r, dim, p.w_sj, p.w_sc, nullptr);
   for (int c = tid; c < dim; c += kTcThreads) s_gamma[c] = p.gamma[c];
   __syncthreads();
   float4 dgm[PGRAD ? GW : 1], dbt[PGRAD ? GW : 1];
 #pragma unroll
   for (int kk = 0; kk < (PGRAD ? GW : 1); ++kk) dgm[kk] = dbt[kk] = make_float4(0.f, 0.f, 0.f, 0.f);
+  // DOWN: oz rows of one finished step = sum of the 8 warps' partial products
+  auto flush_oz = [&](int tile, const float* zb) {
+    for (int idx = tid; idx < 16 * RP; idx += kTcThreads) {
+      const int row = idx / RP, n = idx - row * RP, m = tile * 16 + row;
+      float z = 0.f;
+#pragma unroll
+      for (int w = 0; w < kTcWarps; ++w) z += zb[w * 16 * RP + idx];
+      if (n < p.orank && m < p.M) p.oz[(size_t)m * p.ld_oz + n] = z;
+    }
+  };
   int buf = 0;
   for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, buf ^= 1) {
     const int rA = tile * 16 + g, rB = rA + 8;
@@ -794,7 +814,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) ln_bwd_tc_kernel(gvk_layernorm_
     const float meanA = cur.meanA, rstdA = cur.rstdA, meanB = cur.meanB, rstdB = cur.rstdB;
     uint32_t a[KS][4];
 #pragma unroll
-    for (int s = 0; s < KS; ++s)
+    for (int s = 0; s < (RANK ? KS : 0); ++s)
 #pragma unroll
       for (int e = 0; e < 4; ++e) a[s][e] = f2tf32(cur.v[s][e]);
     const float liveA = rA < p.M ? 1.f : 0.f, liveB = rB < p.M ? 1.f : 0.f;
@@ -864,6 +884,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) ln_bwd_tc_kernel(gvk_layernorm_
       rbuf[(g + 8) * kTcWarps + warp] = make_float2(s1B, s2B);
     }
     __syncthreads();
+    if (DOWN && tile != (int)blockIdx.x) flush_oz(tile - gridDim.x, zbuf + (buf ^ 1) * L::kZ);
     float m1A = 0.f, m2A = 0.f, m1B = 0.f, m2B = 0.f;
 #pragma unroll
     for (int w = 0; w < kTcWarps; w += 2) {
@@ -875,6 +896,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) ln_bwd_tc_kernel(gvk_layernorm_
     m1A *= inv_dim; m2A *= inv_dim; m1B *= inv_dim; m2B *= inv_dim;
     // ---- dx = rstd (dy gamma - m1 - xhat m2) (+ az @ aw) (+ dres).  Pending copy groups: dres of this step, x / dy of the next.
     cp_async_wait<1>();
+    float oacc[DOWN ? KS : 1][4];
+#pragma unroll
+    for (int j = 0; j < (DOWN ? KS : 1); ++j) oacc[j][0] = oacc[j][1] = oacc[j][2] = oacc[j][3] = 0.f;
 #pragma unroll
     for (int kk = 0; kk < GW; ++kk) {
       const int col = cw + 16 * kk;
@@ -897,9 +921,19 @@ __global__ void __launch_bounds__(kTcThreads, 1) ln_bwd_tc_kernel(gvk_layernorm_
                               rstdA * (dA.z * gam.z - m1A - xa[kk].z * m2A), rstdA * (dA.w * gam.w - m1A - xa[kk].w * m2A));
       float4 vB = make_float4(rstdB * (dB.x * gam.x - m1B - xb[kk].x * m2B), rstdB * (dB.y * gam.y - m1B - xb[kk].y * m2B),
                               rstdB * (dB.z * gam.z - m1B - xb[kk].z * m2B), rstdB * (dB.w * gam.w - m1B - xb[kk].w * m2B));
-      if (MODE == 0) rank_mma(kk, vA, vB);
+      if (MODE == 0 && RANK) rank_mma(kk, vA, vB);
       vA.x += rcA.x; vA.y += rcA.y; vA.z += rcA.z; vA.w += rcA.w;
       vB.x += rcB.x; vB.y += rcB.y; vB.z += rcB.z; vB.w += rcB.w;
+      if (DOWN) {   // the finished output rows are tc_down's A fragments (k slot t <-> column 4t, t+4 <-> 4t+1; second MMA 4t+2 / 4t+3)
+        const uint32_t ax = f2tf32(vA.x), ay = f2tf32(vA.y), az = f2tf32(vA.z), aw = f2tf32(vA.w);
+        const uint32_t bx = f2tf32(vB.x), by = f2tf32(vB.y), bz = f2tf32(vB.z), bw = f2tf32(vB.w);
+#pragma unroll
+        for (int j = 0; j < KS; ++j) {
+          const float4 w = *reinterpret_cast<const float4*>(sW + (8 * j + g) * S2 + col);
+          mma_tf32(oacc[j], ax, bx, ay, by, __float_as_uint(w.x), __float_as_uint(w.y));
+          mma_tf32(oacc[j], az, bz, aw, bw, __float_as_uint(w.z), __float_as_uint(w.w));
+        }
+      }
       if (rA < p.M) {
         *reinterpret_cast<float4*>(p.dx + (size_t)rA * p.ld_dx + col) = vA;
         if (p.dx_lp) {
@@ -918,7 +952,19 @@ __global__ void __launch_bounds__(kTcThreads, 1) ln_bwd_tc_kernel(gvk_layernorm_
       }
     }
     cp_async_commit();                                    // dres of the next step
+    if (DOWN) {
+      float* zb = zbuf + buf * L::kZ;
+#pragma unroll
+      for (int j = 0; j < KS; ++j) {
+        *reinterpret_cast<float2*>(zb + (warp * 16 + g) * RP + 8 * j + 2 * t) = make_float2(oacc[j][0], oacc[j][1]);
+        *reinterpret_cast<float2*>(zb + (warp * 16 + g + 8) * RP + 8 * j + 2 * t) = make_float2(oacc[j][2], oacc[j][3]);
+      }
+    }
     if (has_next) cur = nxt;
+    if (DOWN && !has_next) {                              // last step of this CTA
+      __syncthreads();
+      flush_oz(tile, zbuf + buf * L::kZ);
+    }
   }
   cp_async_wait<0>();
   if (PGRAD) {
@@ -943,20 +989,21 @@ __global__ void __launch_bounds__(kTcThreads, 1) ln_bwd_tc_kernel(gvk_layernorm_
   }
 }
 
-template <int NITER, int KS, int MODE, bool PGRAD>
+template <int NITER, int KS, int MODE, bool PGRAD, bool DOWN = false>
 static int ln_bwd_tc_launch(const gvk_layernorm_bwd_params* p, cudaStream_t stream) {
-  constexpr size_t smem = LnbTc<NITER, KS, MODE>::kSmem;
+  constexpr size_t smem = LnbTc<NITER, KS, MODE, DOWN>::kSmem;
   static_assert(smem <= 227 * 1024, "layernorm_bwd_tc: shared memory");
-  static const int attr = cudaFuncSetAttribute(ln_bwd_tc_kernel<NITER, KS, MODE, PGRAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  static const int attr = cudaFuncSetAttribute(ln_bwd_tc_kernel<NITER, KS, MODE, PGRAD, DOWN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (attr != cudaSuccess) return cuda_status((cudaError_t)attr, "layernorm_bwd_tc (smem attribute)");
   const int ntiles = (p->M + 15) / 16;
-  ln_bwd_tc_kernel<NITER, KS, MODE, PGRAD><<<std::max(1, std::min(ntiles, sm_count())), kTcThreads, smem, stream>>>(*p);
+  ln_bwd_tc_kernel<NITER, KS, MODE, PGRAD, DOWN><<<std::max(1, std::min(ntiles, sm_count())), kTcThreads, smem, stream>>>(*p);
   GVK_CHECK_LAUNCH("layernorm_bwd_tc");
   return GVK_OK;
 }
 
 // Forms the tensor-core kernel takes (everything else stays on the fp32 kernel): dense bf16 dy + additive rank term without parameter
-// gradients (MODE 0), or rank-r dy alone with both parameter gradients (MODE 1); dim a multiple of 128; 16-byte aligned fp32 streams.
+// gradients (MODE 0), dense bf16 dy + a projection of the output rows (DOWN), or rank-r dy alone with both parameter gradients (MODE 1);
+// dim 384 / 768; 16-byte aligned fp32 streams.
 bool layernorm_bwd_tc_supported(const gvk_layernorm_bwd_params* p) {
   auto al = [](const void* q, uintptr_t m) { return (reinterpret_cast<uintptr_t>(q) & m) == 0; };
   if (p->dim != 384 && p->dim != 768) return false;      // dim 1024 (16 column groups per warp pair) does not fit the register file without spills
@@ -964,15 +1011,18 @@ bool layernorm_bwd_tc_supported(const gvk_layernorm_bwd_params* p) {
   if (!al(p->x, 15) || p->ldx % 4 != 0 || !al(p->dx, 15) || p->ld_dx % 4 != 0) return false;
   if (p->dres && (!al(p->dres, 15) || p->ld_dres % 4 != 0)) return false;
   if (p->dx_lp && (!al(p->dx_lp, 7) || p->ld_dx_lp % 4 != 0)) return false;
-  const bool mode0 = p->dy && p->dy_dtype == GVK_BF16 && p->az && !p->dz && !p->dgamma && !p->dbeta && p->ra <= 32 && al(p->dy, 7) && p->ld_dy % 4 == 0;
-  const bool mode1 = !p->dy && p->dz && !p->az && p->dgamma && p->dbeta && p->r <= 32;
-  return mode0 || mode1;
+  const bool dense = p->dy && p->dy_dtype == GVK_BF16 && !p->dz && !p->dgamma && !p->dbeta && al(p->dy, 7) && p->ld_dy % 4 == 0;
+  const bool mode0 = dense && p->az && !p->ow && p->ra <= 32;
+  const bool down = dense && !p->az && p->ow && p->orank <= 24;   // a 32-row panel and its exchange buffers do not fit next to the stream slots
+  const bool mode1 = !p->dy && p->dz && !p->az && !p->ow && p->dgamma && p->dbeta && p->r <= 32;
+  return mode0 || mode1 || down;
 }
 
 int layernorm_bwd_tc(const gvk_layernorm_bwd_params* p, cudaStream_t stream) {
-  const bool mode0 = p->dy != nullptr;
-  const int r = mode0 ? p->ra : p->r;
+  const bool mode0 = p->dy != nullptr, down = p->ow != nullptr;
+  const int r = down ? p->orank : (mode0 ? p->ra : p->r);
 #define GVK_LNB_TC(NITER)                                                                                                              \
+  if (down) return ln_bwd_tc_launch<NITER, 3, 0, false, true>(p, stream);                                                              \
   if (mode0) return r <= 24 ? ln_bwd_tc_launch<NITER, 3, 0, false>(p, stream) : ln_bwd_tc_launch<NITER, 4, 0, false>(p, stream);       \
   return r <= 24 ? ln_bwd_tc_launch<NITER, 3, 1, true>(p, stream) : ln_bwd_tc_launch<NITER, 4, 1, true>(p, stream);
   switch (p->dim / 64) {
@@ -984,7 +1034,6 @@ int layernorm_bwd_tc(const gvk_layernorm_bwd_params* p, cudaStream_t stream) {
   }
 #undef GVK_LNB_TC
 }
-
 
 // =================================================================================================
 // LayerNorm forward + rank-r down-projection of the SAME rows in one pass over x:

@@ -335,6 +335,7 @@ class GavikoEngine:
         ops.head_bwd(ctx['g_final'], B, T, 0, P + 1, W['norm_w'], W['norm_b'], Tr['head_w'], Tr['head_b'], ctx['pooled'], dlogits, dx=dG, dx_lp=dG_lp,
                      dwh=G['head_w'], dbh=G['head_b'])
         dLoc = None
+        dcomb_next = None
         for i in reversed(range(c['depth'])):
             s = i // c['share_factor']
             Lw, La, Fu, st = W['layers'][i], Tr['local'][s], Tr['fusion'][s], ctx['layers'][i]
@@ -345,7 +346,10 @@ class GavikoEngine:
             dH2 = ops.gemm(dA, Lw['w1_t'], out_dtype=cdt)     # bf16 mode: the gradient of the LayerNorm output travels as bf16 (half the bytes of
             del dA                                            # the GEMM's stores and of the LayerNorm backward's reads; its operands were bf16 anyway)
             # ---- prompt up-projection: d(comb) = dG Wu ; dWu, dbu
-            dcomb = ops.rowproj_down(dG, Fu['wu'], transposed=True, prec=pr)['z']
+            if dcomb_next is None:
+                dcomb = ops.rowproj_down(dG, Fu['wu'], transposed=True, prec=pr)['z']
+            else:
+                dcomb = dcomb_next       # projected from the output rows of the previous iteration's LayerNorm-backward pass
             ops.skinny_wgrad(st['comb'], dG, dw=gF['wu'], dw_layout='dr', dx_colsum=gF['bu'], prec=pr)
             dll = ops.prompt_fusion_bwd(st['comb'], st['ll'], dcomb, Fu['k'], st['fsaved'], gF['k'], B, T, N, P)
             du = ops.quickgelu_bwd(dcomb, st['pre_g'], out=dcomb)
@@ -367,7 +371,13 @@ class GavikoEngine:
             del dO
             dH1 = ops.gemm(dqkv, Lw['wqkv_t'], out_dtype=cdt)
             del dqkv
-            dG = ops.layernorm_bwd(st['g_in'], Lw['ln1_w'], st['mean1'], st['rstd1'], dy=dH1, dres=dGm, dx=dGm if lp else dH1, dx_lp=dG_lp)
+            dcomb_next = None
+            if i > 0 and lp and ops.layernorm_bwd_down_supported(st['g_in'], Tr['fusion'][(i - 1) // c['share_factor']]['wu'].shape[1], pr):
+                # the next iteration's d(comb) = dG Wu rides on this pass (its input rows are this pass's output rows)
+                dG, dcomb_next = ops.layernorm_bwd(st['g_in'], Lw['ln1_w'], st['mean1'], st['rstd1'], dy=dH1, dres=dGm, dx=dGm, dx_lp=dG_lp, prec=pr,
+                                                   ow=Tr['fusion'][(i - 1) // c['share_factor']]['wu'], ow_transposed=True)
+            else:
+                dG = ops.layernorm_bwd(st['g_in'], Lw['ln1_w'], st['mean1'], st['rstd1'], dy=dH1, dres=dGm, dx=dGm if lp else dH1, dx_lp=dG_lp)
             del dGm, dH1
             # ---- local branch backward
             dctx = ops.rowproj_down(dLoc, La['wu'], transposed=True, drop_p=ctx['drop_proj'], seed=st['seed_p'], prec=pr)['z']

@@ -212,9 +212,10 @@ def skinny_wgrad(a, x, *, dw=None, dw_layout='rd', da_colsum=None, dx_colsum=Non
 
 
 def layernorm_bwd(x, gamma, mean, rstd, *, dy=None, dz=None, w=None, dres=None, dx=None, dx_lp=None, dgamma=None, dbeta=None, az=None, aw=None,
-                  beta=None, ssf_scale=None, dssf_scale=None, dssf_shift=None, prec=PREC_FP32):
+                  beta=None, ssf_scale=None, dssf_scale=None, dssf_shift=None, prec=PREC_FP32, ow=None, ow_transposed=False):
     """dx = dres + LN'(dy) + az @ aw;  dy dense [M, dim] or rank-r (dz [M, r], w [r, dim]);  az [M, ra], aw [ra, dim].  prec = PREC_TF32: the
-    rank-r product of the two forms gvk.h names runs on the tensor cores (tf32 operands) inside the pass."""
+    rank-r product of the two forms gvk.h names runs on the tensor cores (tf32 operands) inside the pass.  ow ([r, dim], or [dim, r] with
+    ow_transposed): also returns oz = dx @ W^T computed from the output rows in the same pass (tensor-core form only) -> (dx, oz)."""
     M, dim = x.shape
     if dx is None:
         dx = torch.empty((M, dim), device=x.device, dtype=torch.float32)
@@ -237,8 +238,18 @@ def layernorm_bwd(x, gamma, mean, rstd, *, dy=None, dz=None, w=None, dres=None, 
         ra = az.shape[1]
         assert tuple(aw.shape) == (ra, dim) and aw.is_contiguous()
         _set(p, az=L.ptr(az, torch.float32), ld_az=_ld(az), aw=L.ptr(aw, torch.float32), aw_sj=dim, aw_sc=1, ra=ra)
+    oz = None
+    if ow is not None:
+        orank = ow.shape[1] if ow_transposed else ow.shape[0]
+        sj, sc = _wstrides(ow, orank, dim, ow_transposed)
+        oz = torch.empty((M, orank), device=x.device, dtype=torch.float32)
+        _set(p, ow=L.ptr(ow, torch.float32), ow_sj=sj, ow_sc=sc, orank=orank, oz=oz, ld_oz=orank)
     L.call('gvk_layernorm_bwd', C.byref(p), L.stream())
-    return dx
+    return dx if ow is None else (dx, oz)
+
+
+def layernorm_bwd_down_supported(x, orank, prec):
+    return prec == PREC_TF32 and x.shape[1] in (384, 768) and orank <= 24 and 'down' not in _TF32_OFF
 
 
 def small_wgrad(a, b, dw):

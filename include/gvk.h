@@ -206,6 +206,10 @@ typedef struct {
   const float* az; int ld_az; const float* aw; int aw_sj, aw_sc; int ra;
   const float* beta; const float* ssf_scale; float* dssf_scale; float* dssf_shift;
   int precision;                /* GVK_PREC_FP32 (exact, default) or GVK_PREC_TF32 */
+  /* optional projection of the OUTPUT rows, oz[m, j] = sum_c dx[m, c] * ow(j, c)  (ow strided like w; orank <= 24): the dgrad of the rank-r
+   * up-projection that reads the residual gradient next (Awakening_Prompt.proj_up, model/gaviko.py:187).  GVK_PREC_TF32 with a dense bf16
+   * dy and no other rank term only; any other request with ow set is refused. */
+  const float* ow; int ow_sj, ow_sc; int orank; float* oz; int ld_oz;
 } gvk_layernorm_bwd_params;
 int gvk_layernorm_bwd(const gvk_layernorm_bwd_params* p, gvk_stream_t stream);
 

@@ -165,7 +165,7 @@ def skinny_wgrad(a, x, *, dw=None, dw_layout='rd', da_colsum=None, dx_colsum=Non
 
 
 def layernorm_bwd(x, gamma, mean, rstd, *, dy=None, dz=None, w=None, dres=None, dx=None, dx_lp=None, dgamma=None, dbeta=None, az=None, aw=None,
-                  beta=None, ssf_scale=None, dssf_scale=None, dssf_shift=None, prec=0):
+                  beta=None, ssf_scale=None, dssf_scale=None, dssf_shift=None, prec=0, ow=None, ow_transposed=False):
     xh = (x - mean[:, None]) * rstd[:, None]
     g = torch.zeros_like(x)
     if dy is not None:
@@ -194,7 +194,13 @@ def layernorm_bwd(x, gamma, mean, rstd, *, dy=None, dz=None, w=None, dres=None, 
     dx.copy_(v)
     if dx_lp is not None:
         dx_lp.copy_(v)
+    if ow is not None:
+        return dx, (v @ (ow if ow_transposed else ow.t())).contiguous()
     return dx
+
+
+def layernorm_bwd_down_supported(x, orank, prec):
+    return prec == PREC_TF32 and x.shape[1] in (384, 768) and orank <= 24
 
 
 def small_wgrad(a, b, dw):

@@ -159,6 +159,37 @@ def test_layernorm_bwd_tensor_core_forms(M, dim, r):
     close(dgam2, gr.grad, 1e-4)
 
 
+@pytest.mark.parametrize('M,dim,r', [(1033, 768, 20), (16 * 148 * 3 + 5, 768, 20), (517, 384, 20), (9, 768, 8), (16 * 148, 768, 24)])
+def test_layernorm_bwd_with_output_projection(M, dim, r):
+    """gvk_layernorm_bwd ow / oz: d(comb) = dG Wu computed from the output rows of the LayerNorm-backward pass that produces dG (in place over
+    the residual gradient, bf16 copy written)."""
+    torch.manual_seed(M + dim + r)
+    x = torch.randn(M, dim, device=DEV) * 2 + 0.3
+    g = torch.randn(dim, device=DEV) * 0.1 + 1
+    be = torch.randn(dim, device=DEV) * 0.1
+    _, mean, rstd = ops.layernorm_fwd(x, g, be)
+    wu = torch.randn(dim, r, device=DEV) / dim ** 0.5          # nn.Linear(r, dim).weight
+    dres = torch.randn(M, dim, device=DEV)
+    dy = torch.randn(M, dim, device=DEV).bfloat16()
+    xr = x.double().requires_grad_(True)
+    F.layer_norm(xr, (dim,), g.double(), be.double(), 1e-5).backward(dy.double())
+    want = xr.grad + dres.double()
+    buf = dres.clone()
+    dx_lp = torch.empty(M, dim, device=DEV, dtype=torch.bfloat16)
+    n0 = ops.L.launch_count()
+    dx, oz = ops.layernorm_bwd(x, g, mean, rstd, dy=dy, dres=buf, dx=buf, dx_lp=dx_lp, prec=ops.PREC_TF32, ow=wu, ow_transposed=True)
+    assert ops.L.launch_count() == n0 + 1 and dx.data_ptr() == buf.data_ptr()
+    close(dx, want, 1e-5)                                       # no rank term inside: the LayerNorm arithmetic is fp32
+    close(dx_lp, want, 1e-2)
+    close(oz, want @ wu.double(), 3e-3)
+    close(oz, ops.rowproj_down(dx, wu, transposed=True, prec=ops.PREC_TF32)['z'], 3e-3)
+    w2 = torch.randn(r, dim, device=DEV) / dim ** 0.5
+    _, oz2 = ops.layernorm_bwd(x, g, mean, rstd, dy=dy, dres=dres, prec=ops.PREC_TF32, ow=w2)
+    close(oz2, want @ w2.double().t(), 3e-3)
+    with pytest.raises(Exception):                              # no exact-fp32 form of the fused projection
+        ops.layernorm_bwd(x, g, mean, rstd, dy=dy, dres=dres, ow=w2)
+
+
 @pytest.mark.parametrize('save', [True, False])
 @pytest.mark.parametrize('M,dim,r', [(1033, 768, 20), (16 * 148 * 2 + 7, 768, 20), (517, 384, 20), (2066, 768, 32), (9, 768, 8)])
 def test_layernorm_fwd_down_one_pass(M, dim, r, save):

@@ -56,6 +56,32 @@ def main():
                              roofline_us=round(nbytes / peak / 1e3, 1)))
             print(json.dumps(rows[-1]), flush=True)
     forward_pair(a, peak)
+    backward_pair(a, peak)
+
+
+def backward_pair(a, peak):
+    """LayerNorm1 backward producing dG (in place over d(g_mid), + bf16 copy) and d(comb) = dG Wu of the next iteration: two kernels vs one."""
+    dev, dim, r = 'cuda', 768, 20
+    M = a.batch * 1033
+    flush = torch.zeros(64 * 1024 * 1024, device=dev)
+    x = torch.randn(M, dim, device=dev)
+    gamma = torch.rand(dim, device=dev) + 0.5
+    mean, rstd = x.mean(1), 1.0 / x.var(1, unbiased=False).add(1e-5).sqrt()
+    dy = torch.randn(M, dim, device=dev).bfloat16()
+    dres = torch.randn(M, dim, device=dev)
+    dx_lp = torch.empty(M, dim, device=dev, dtype=torch.bfloat16)
+    wu = torch.randn(dim, r, device=dev) / dim ** 0.5
+    nb = M * dim * (4 + 2 + 4 + 4 + 2)
+    forms = {
+        'layernorm_bwd exact (dy bf16 + dres in place + bf16 copy)': (lambda: ops.layernorm_bwd(x, gamma, mean, rstd, dy=dy, dres=dres, dx=dres, dx_lp=dx_lp), nb),
+        'rowproj_down (tf32, transposed weight)': (lambda: ops.rowproj_down(dres, wu, transposed=True, prec=ops.PREC_TF32), M * dim * 4),
+        'layernorm_bwd with the output projection (one pass)': (lambda: ops.layernorm_bwd(x, gamma, mean, rstd, dy=dy, dres=dres, dx=dres, dx_lp=dx_lp, prec=ops.PREC_TF32,
+                                                                                       ow=wu, ow_transposed=True), nb),
+    }
+    for form, (fn, nbytes) in forms.items():
+        us = timeit(fn, a.iters, flush, a.flush)
+        print(json.dumps(dict(kernel='dG pass + next d(comb)', form=form, M=M, us=round(us, 1), gbps=round(nbytes / us / 1e3, 1),
+                              frac_of_copy_peak=round(nbytes / us / 1e3 / peak, 3), roofline_us=round(nbytes / peak / 1e3, 1))), flush=True)
 
 
 def forward_pair(a, peak):
