@@ -930,9 +930,92 @@ __global__ void __launch_bounds__(256) small_wgrad_kernel(const float* __restric
     if (i < nmine) atomicAdd(dw + tid + 256 * i, acc[i]);
 }
 
+// Tensor-core form for ra <= 64, rb <= 24 (LocalSelfAttention.qkv: 60 x 20): D[j, k] += A^T[j, m] B[m, k] with the row index as the MMA k
+// dimension, mma.sync m16n8k8 tf32 with both operands split into hi + lo (hi hi + lo hi + hi lo: ~2^-21 relative, inside the 1e-4 parity mode).
+// The staged FMA form above reads two shared-memory words per FMA: 45 us for 64 k rows against 3 us of operand traffic.  Here a warp walks
+// 8-row steps with its fragments loaded straight from global memory (the operands are a few MB and L2-resident), the 8 warps of a CTA meet in
+// shared memory and the CTA issues one atomic per output.
+constexpr int kSwtWarps = 8;
+__global__ void __launch_bounds__(kSwtWarps * 32) small_wgrad_tc_kernel(const float* __restrict__ a, int lda, int ra, const float* __restrict__ b, int ldb, int rb, int M,
+                                                                         float* __restrict__ dw) {
+  constexpr int MT = 4, NT = 3;
+  __shared__ float sacc[MT * 16 * NT * 8];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+  for (int i = tid; i < MT * 16 * NT * 8; i += blockDim.x) sacc[i] = 0.f;
+  __syncthreads();
+  float acc[MT][NT][4];
+#pragma unroll
+  for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) acc[mt][nt][0] = acc[mt][nt][1] = acc[mt][nt][2] = acc[mt][nt][3] = 0.f;
+  const int nwarps = gridDim.x * kSwtWarps;
+  for (int m0 = (blockIdx.x * kSwtWarps + warp) * 8; m0 < M; m0 += nwarps * 8) {
+    const int r0 = m0 + t, r1 = m0 + t + 4;
+    const bool v0 = r0 < M, v1 = r1 < M;
+    float av[MT][4], bv[NT][2];
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt) {
+      const int j0 = 16 * mt + g, j1 = j0 + 8;
+      av[mt][0] = (v0 && j0 < ra) ? a[(size_t)r0 * lda + j0] : 0.f;
+      av[mt][1] = (v0 && j1 < ra) ? a[(size_t)r0 * lda + j1] : 0.f;
+      av[mt][2] = (v1 && j0 < ra) ? a[(size_t)r1 * lda + j0] : 0.f;
+      av[mt][3] = (v1 && j1 < ra) ? a[(size_t)r1 * lda + j1] : 0.f;
+    }
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) {
+      const int k = 8 * nt + g;
+      bv[nt][0] = (v0 && k < rb) ? b[(size_t)r0 * ldb + k] : 0.f;
+      bv[nt][1] = (v1 && k < rb) ? b[(size_t)r1 * ldb + k] : 0.f;
+    }
+    uint32_t ah[MT][4], al[MT][4], bh[NT][2], bl[NT][2];
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        ah[mt][e] = f2tf32(av[mt][e]);
+        al[mt][e] = f2tf32(av[mt][e] - __uint_as_float(ah[mt][e]));
+      }
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        bh[nt][e] = f2tf32(bv[nt][e]);
+        bl[nt][e] = f2tf32(bv[nt][e] - __uint_as_float(bh[nt][e]));
+      }
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt) {
+        mma_tf32(acc[mt][nt], al[mt][0], al[mt][1], al[mt][2], al[mt][3], bh[nt][0], bh[nt][1]);
+        mma_tf32(acc[mt][nt], ah[mt][0], ah[mt][1], ah[mt][2], ah[mt][3], bl[nt][0], bl[nt][1]);
+        mma_tf32(acc[mt][nt], ah[mt][0], ah[mt][1], ah[mt][2], ah[mt][3], bh[nt][0], bh[nt][1]);
+      }
+  }
+#pragma unroll
+  for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) {
+      atomicAdd(&sacc[(16 * mt + g) * (NT * 8) + 8 * nt + 2 * t], acc[mt][nt][0]);
+      atomicAdd(&sacc[(16 * mt + g) * (NT * 8) + 8 * nt + 2 * t + 1], acc[mt][nt][1]);
+      atomicAdd(&sacc[(16 * mt + g + 8) * (NT * 8) + 8 * nt + 2 * t], acc[mt][nt][2]);
+      atomicAdd(&sacc[(16 * mt + g + 8) * (NT * 8) + 8 * nt + 2 * t + 1], acc[mt][nt][3]);
+    }
+  __syncthreads();
+  for (int i = tid; i < ra * rb; i += blockDim.x) {
+    const int j = i / rb, k = i - j * rb;
+    atomicAdd(dw + i, sacc[j * (NT * 8) + k]);
+  }
+}
+
 int small_wgrad(const float* a, int lda, int ra, const float* b, int ldb, int rb, int M, float* dw, cudaStream_t stream) {
   GVK_CHECK_ARG(a && b && dw && M > 0, "gvk_small_wgrad: null pointer");
   GVK_CHECK_ARG(ra >= 1 && ra <= 96 && rb >= 1 && rb <= 96 && ra * rb <= 4096, "gvk_small_wgrad: ra=%d rb=%d must be in [1,96], ra*rb <= 4096", ra, rb);
+  if (ra <= 64 && rb <= 24) {
+    const int grid = std::max(1, std::min(sm_count() * 2, (M + kSwtWarps * 8 - 1) / (kSwtWarps * 8)));
+    small_wgrad_tc_kernel<<<grid, kSwtWarps * 32, 0, stream>>>(a, lda, ra, b, ldb, rb, M, dw);
+    GVK_CHECK_LAUNCH("small_wgrad_tc");
+    return GVK_OK;
+  }
   const int ctas = std::max(1, std::min(sm_count() * 2, (M + 127) / 128));
   int rows_per_cta = ((M + ctas - 1) / ctas + kSwRows - 1) / kSwRows * kSwRows;
   const int grid = (M + rows_per_cta - 1) / rows_per_cta;
@@ -1018,9 +1101,39 @@ __global__ void __launch_bounds__(256) split_pack_bf16_kernel(const float* __res
   }
   dst[(size_t)row * ld_dst + c] = __float2bfloat16_rn(out);
 }
+// Same rule, a thread per 8 output columns and one 16-byte store (width % 8 == 0, 16-byte aligned rows): the element-per-thread form spends
+// 23 us on the [66 k, 20] -> [66 k, 64] pack of a GAViKO layer (two integer divisions and a 2-byte store per element) for 13 MB of traffic.
+__global__ void __launch_bounds__(256) split_pack_bf16_vec_kernel(const float* __restrict__ src, int ld_src, int rows, int r, __nv_bfloat16* __restrict__ dst, int ld_dst,
+                                                                  int width, int pattern) {
+  const int per_row = width / 8;
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= rows * per_row) return;
+  const int row = idx / per_row, c0 = (idx - row * per_row) * 8;
+  const float* sr = src + (size_t)row * ld_src;
+  __align__(16) __nv_bfloat16 o[8];
+  int slot = c0 / r, j = c0 - slot * r;
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    float out = 0.f;
+    if (slot < 3) {
+      const float x = sr[j];
+      const float hi = __bfloat162float(__float2bfloat16_rn(x));
+      out = (pattern >> slot) & 1 ? x - hi : hi;
+    }
+    o[e] = __float2bfloat16_rn(out);
+    if (++j == r) { j = 0; ++slot; }
+  }
+  *reinterpret_cast<uint4*>(dst + (size_t)row * ld_dst + c0) = *reinterpret_cast<const uint4*>(o);
+}
 
 int split_pack_bf16(const float* src, int ld_src, int rows, int r, void* dst, int ld_dst, int width, int pattern, cudaStream_t stream) {
   GVK_CHECK_ARG(src && dst && rows > 0 && r > 0 && width >= 3 * r, "gvk_split_pack_bf16: bad argument (rows=%d r=%d width=%d)", rows, r, width);
+  if (width % 8 == 0 && ld_dst % 8 == 0 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+    const long long total = (long long)rows * (width / 8);
+    split_pack_bf16_vec_kernel<<<(int)((total + 255) / 256), 256, 0, stream>>>(src, ld_src, rows, r, reinterpret_cast<__nv_bfloat16*>(dst), ld_dst, width, pattern);
+    GVK_CHECK_LAUNCH("split_pack_bf16");
+    return GVK_OK;
+  }
   const long long total = (long long)rows * width;
   split_pack_bf16_kernel<<<(int)((total + 255) / 256), 256, 0, stream>>>(src, ld_src, rows, r, reinterpret_cast<__nv_bfloat16*>(dst), ld_dst, width, pattern);
   GVK_CHECK_LAUNCH("split_pack_bf16");

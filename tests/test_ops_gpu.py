@@ -273,6 +273,35 @@ def test_small_ops():
     out = torch.zeros(60, device=DEV)
     ops.colsum(a, out)
     close(out, a.double().sum(0), 1e-4)
+    # the hot-path shape: 64 000 rows, accumulation on top of an existing gradient (hi / lo split tf32 MMAs stay inside the fp32 tolerance)
+    M4 = 64000
+    a4, b4 = torch.randn(M4, 60, device=DEV), torch.randn(M4, 20, device=DEV)
+    dw4 = torch.ones(60, 20, device=DEV)
+    ops.small_wgrad(a4, b4, dw4)
+    want4 = a4.double().t() @ b4.double() + 1.0
+    assert (dw4.double() - want4).abs().max().item() <= 1e-5 * want4.abs().max().item()
+    views = torch.randn(M, 100, device=DEV)                                           # strided operands
+    dw5 = torch.zeros(60, 20, device=DEV)
+    ops.small_wgrad(views[:, :60], views[:, 80:], dw5)
+    close(dw5, views[:, :60].double().t() @ views[:, 80:].double(), 1e-4)
+
+
+@pytest.mark.parametrize('width', [64, 60, 72])
+def test_split_pack_bf16_rule(width):
+    """hi / lo bf16 slots of the K-extension operands: the 16-byte-store form (width % 8 == 0) and the element form write the same thing."""
+    torch.manual_seed(width)
+    rows, r = 1037, 20
+    src = torch.randn(rows, r, device=DEV)
+    big = torch.full((rows, 128 + width), 7.0, device=DEV, dtype=torch.bfloat16)
+    for pattern in (0b010, 0b100):
+        ops.split_pack_bf16(src, big[:, 128:], pattern)
+        hi = src.bfloat16()
+        lo = (src - hi.float()).bfloat16()
+        want = torch.zeros(rows, width, device=DEV, dtype=torch.bfloat16)
+        for slot in range(3):
+            want[:, slot * r:(slot + 1) * r] = lo if (pattern >> slot) & 1 else hi
+        assert torch.equal(big[:, 128:], want)
+        assert (big[:, :128] == 7.0).all()
     x = torch.randn(77, 192, device=DEV)
     assert torch.equal(ops.cast_bf16(x), x.bfloat16())
     dy, pre = torch.randn(M, 20, device=DEV), torch.randn(M, 20, device=DEV)
