@@ -146,7 +146,7 @@ long long gvk_struct_size(const char* name) {
   GVK_SZ(gvk_fusion_weights) GVK_SZ(gvk_fusion_grads) GVK_SZ(gvk_fusion_saved) GVK_SZ(gvk_fusion_fwd_params)
   GVK_SZ(gvk_fusion_bwd_params) GVK_SZ(gvk_head_fwd_params) GVK_SZ(gvk_head_bwd_params) GVK_SZ(gvk_mhsa_fwd_params) GVK_SZ(gvk_mhsa_bwd_params) GVK_SZ(gvk_rescale_intensity_params)
   GVK_SZ(gvk_latent_xattn_fwd_params) GVK_SZ(gvk_latent_xattn_bwd_params) GVK_SZ(gvk_patch_embed_params)
-  GVK_SZ(gvk_wgrad_params) GVK_SZ(gvk_hfreq_filter_params) GVK_SZ(gvk_layernorm_fwd_down_params)
+  GVK_SZ(gvk_wgrad_params) GVK_SZ(gvk_hfreq_filter_params) GVK_SZ(gvk_layernorm_fwd_down_params) GVK_SZ(gvk_rowproj_up_down_params)
 #undef GVK_SZ
   return -1;
 }
@@ -158,6 +158,7 @@ int gvk_layernorm_bwd(const gvk_layernorm_bwd_params* p, gvk_stream_t stream) { 
 int gvk_layernorm_fwd_down(const gvk_layernorm_fwd_down_params* p, gvk_stream_t stream) { return gvk::layernorm_fwd_down(p, S(stream)); }
 int gvk_rowproj_down(const gvk_rowproj_down_params* p, gvk_stream_t stream) { return gvk::rowproj_down(p, S(stream)); }
 int gvk_rowproj_up(const gvk_rowproj_up_params* p, gvk_stream_t stream) { return gvk::rowproj_up(p, S(stream)); }
+int gvk_rowproj_up_down(const gvk_rowproj_up_down_params* p, gvk_stream_t stream) { return gvk::rowproj_up_down(p, S(stream)); }
 int gvk_skinny_wgrad(const gvk_skinny_wgrad_params* p, gvk_stream_t stream) { return gvk::skinny_wgrad(p, S(stream)); }
 size_t gvk_skinny_wgrad_ws_floats(int r, int dim, int M) { return gvk::skinny_wgrad_ws_floats(r, dim, M); }
 int gvk_cast_bf16_f32(const void* x, int ldx, float* y, int ldy, int M, int dim, gvk_stream_t stream) { return gvk::cast_bf16_f32(x, ldx, y, ldy, M, dim, S(stream)); }

@@ -56,6 +56,7 @@ bool skinny_wgrad_tc_supported(const gvk_skinny_wgrad_params* p);
 int layernorm_bwd_tc(const gvk_layernorm_bwd_params* p, cudaStream_t stream);
 bool layernorm_bwd_tc_supported(const gvk_layernorm_bwd_params* p);
 int layernorm_fwd_down(const gvk_layernorm_fwd_down_params* p, cudaStream_t stream);
+int rowproj_up_down(const gvk_rowproj_up_down_params* p, cudaStream_t stream);
 int small_wgrad(const float* a, int lda, int ra, const float* b, int ldb, int rb, int M, float* dw, cudaStream_t stream);
 int small_matmul(const float* a, int lda, int ra, const float* w, int rb, int M, float* out, int ldo, cudaStream_t stream);
 int colsum(const float* x, int ldx, int M, int dim, float* out, cudaStream_t stream);

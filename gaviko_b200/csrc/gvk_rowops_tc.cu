@@ -1209,4 +1209,182 @@ int layernorm_fwd_down(const gvk_layernorm_fwd_down_params* p, cudaStream_t stre
 #undef GVK_LFD
 }
 
+
+// =================================================================================================
+// Rank-r up-projection followed by a rank-r down-projection of its OUTPUT rows, one pass over the [M, dim] stream:
+//   out = res + drop_up(c W + b)                                   (gvk_rowproj_up)
+//   z   = act(drop_dn(out) W2^T + b2),  pre = the pre-activation   (gvk_rowproj_down on the rows just written)
+// GAViKO forward: LocalSelfAttention.proj_up + proj_drop + residual (model/gaviko.py:242-243, 301) followed by Awakening_Prompt.proj_down of
+// the new local stream (model/gaviko.py:155-156 on ll); backward: d(loc) += d(ul) Wd followed by the dgrad of proj_up with the replayed
+// proj_drop mask.  As two kernels the 197 MB stream is written and read again.  CTA layout of ln_bwd_tc_kernel: 16 rows per step, warp w
+// owns columns [w dim/8, (w+1) dim/8); res of the next step travels by cp.async into thread-private slots; the output registers of the
+// up-projection (tc_up's C fragments) are tc_down's A fragments; per-warp partial products meet in shared memory (one barrier per step).
+// =================================================================================================
+template <int NITER>
+struct UpDown {
+  static constexpr int dim = NITER * 64, SU = dim + 8, SD = dim + 16, GW = NITER / 2, RP = 24, KS = 3;
+  static constexpr int kSlots = GW * 2 * kTcThreads;
+  static constexpr int kZ = kTcWarps * 16 * RP;
+  static constexpr size_t kSmem = ((size_t)RP * SU + (size_t)RP * SD + dim + RP) * sizeof(float) + 2 * (size_t)kZ * sizeof(float) + (size_t)kSlots * sizeof(float4);
+};
+
+template <int NITER>
+__global__ void __launch_bounds__(kTcThreads, 1) up_down_tc_kernel(gvk_rowproj_up_down_params p) {
+  using L = UpDown<NITER>;
+  constexpr int dim = L::dim, SU = L::SU, SD = L::SD, GW = L::GW, RP = L::RP, KS = L::KS;
+  extern __shared__ __align__(16) float smem[];
+  float* sWu = smem;                                      // [RP][SU] up panel, two low column bits of every 16-column group swapped
+  float* sWd = sWu + RP * SU;                             // [RP][SD] down panel (tc_down's layout)
+  float* s_bu = sWd + RP * SD;                            // [dim]
+  float* s_bd = s_bu + dim;                               // [RP]
+  float* zbuf = s_bd + RP;                                // [2][kTcWarps][16][RP]
+  float4* s_r = reinterpret_cast<float4*>(zbuf + 2 * L::kZ);   // [GW][2][kTcThreads]
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+  const uint64_t seed_up = salted_seed(p.up_seed, p.seed_salt), seed_dn = salted_seed(p.dn_seed, p.seed_salt);
+  const float keep_up = p.up_drop_p > 0.f ? 1.0f / (1.0f - p.up_drop_p) : 1.f, keep_dn = p.dn_drop_p > 0.f ? 1.0f / (1.0f - p.dn_drop_p) : 1.f;
+  const int ntiles = (p.M + 15) / 16;
+  const int cw = warp * 16 * GW + 4 * t;
+  auto slot = [&](int kk, int row) { return (kk * 2 + row) * kTcThreads + tid; };
+  auto fetch_r = [&](int tile, int kk) {
+    const size_t cA = (size_t)min(tile * 16 + g, p.M - 1), cB = (size_t)min(tile * 16 + g + 8, p.M - 1);
+    cp_async16(s_r + slot(kk, 0), p.res + cA * p.ld_res + cw + 16 * kk);
+    cp_async16(s_r + slot(kk, 1), p.res + cB * p.ld_res + cw + 16 * kk);
+  };
+  struct Lat { float v[KS][4]; };
+  auto load_lat = [&](int tile, Lat& T) {
+    const size_t cA = (size_t)min(tile * 16 + g, p.M - 1), cB = (size_t)min(tile * 16 + g + 8, p.M - 1);
+#pragma unroll
+    for (int s = 0; s < KS; ++s) {
+      const int k0 = 8 * s + t, k1 = k0 + 4;
+      T.v[s][0] = k0 < p.r ? p.c[cA * p.ldc + k0] : 0.f;
+      T.v[s][1] = k0 < p.r ? p.c[cB * p.ldc + k0] : 0.f;
+      T.v[s][2] = k1 < p.r ? p.c[cA * p.ldc + k1] : 0.f;
+      T.v[s][3] = k1 < p.r ? p.c[cB * p.ldc + k1] : 0.f;
+    }
+  };
+  Lat cur;
+  if ((int)blockIdx.x < ntiles) {
+    if (p.res) {
+#pragma unroll
+      for (int kk = 0; kk < GW; ++kk) fetch_r(blockIdx.x, kk);
+    }
+    load_lat(blockIdx.x, cur);
+  }
+  cp_async_commit();
+  tc_stage_panel<RP, SU, true>(sWu, p.w, p.r, dim, p.w_sj, p.w_sc, nullptr);
+  tc_stage_panel<RP, SD, false>(sWd, p.w2, p.r2, dim, p.w2_sj, p.w2_sc, nullptr);
+  for (int c = tid; c < dim; c += kTcThreads) s_bu[c] = p.bias ? p.bias[c] : 0.f;
+  if (tid < RP) s_bd[tid] = (p.bias2 && tid < p.r2) ? p.bias2[tid] : 0.f;
+  __syncthreads();
+  int buf = 0;
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, buf ^= 1) {
+    const int rA = tile * 16 + g, rB = rA + 8;
+    const size_t cA = (size_t)min(rA, p.M - 1), cB = (size_t)min(rB, p.M - 1);
+    const int next = tile + gridDim.x;
+    const bool has_next = next < ntiles;
+    Lat nxt;
+    if (has_next) load_lat(next, nxt);
+    uint32_t a[KS][4];
+#pragma unroll
+    for (int s = 0; s < KS; ++s)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) a[s][e] = f2tf32(cur.v[s][e]);
+    float oacc[KS][4];
+#pragma unroll
+    for (int j = 0; j < KS; ++j) oacc[j][0] = oacc[j][1] = oacc[j][2] = oacc[j][3] = 0.f;
+    cp_async_wait<0>();
+#pragma unroll
+    for (int kk = 0; kk < GW; ++kk) {
+      const int col = cw + 16 * kk;
+      float4 rcA = make_float4(0.f, 0.f, 0.f, 0.f), rcB = rcA;
+      if (p.res) {
+        rcA = s_r[slot(kk, 0)];
+        rcB = s_r[slot(kk, 1)];
+        if (has_next) fetch_r(next, kk);                  // the slots just read are free again
+      }
+      float d0[4] = {0.f, 0.f, 0.f, 0.f}, d1[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int s = 0; s < KS; ++s) {
+        const float2 b0 = *reinterpret_cast<const float2*>(sWu + (8 * s + t) * SU + 16 * (warp * GW + kk) + 2 * g);
+        const float2 b1 = *reinterpret_cast<const float2*>(sWu + (8 * s + t + 4) * SU + 16 * (warp * GW + kk) + 2 * g);
+        mma_tf32(d0, a[s][0], a[s][1], a[s][2], a[s][3], __float_as_uint(b0.x), __float_as_uint(b1.x));
+        mma_tf32(d1, a[s][0], a[s][1], a[s][2], a[s][3], __float_as_uint(b0.y), __float_as_uint(b1.y));
+      }
+      const float4 bias = *reinterpret_cast<const float4*>(s_bu + col);
+      float4 vA = make_float4(d0[0] + bias.x, d0[1] + bias.y, d1[0] + bias.z, d1[1] + bias.w);
+      float4 vB = make_float4(d0[2] + bias.x, d0[3] + bias.y, d1[2] + bias.z, d1[3] + bias.w);
+      if (p.up_drop_p > 0.f) {
+        const float4 ma = tc_drop4(seed_up, p.up_offset + cA * dim + col, p.up_drop_p, keep_up);
+        const float4 mb = tc_drop4(seed_up, p.up_offset + cB * dim + col, p.up_drop_p, keep_up);
+        vA.x *= ma.x; vA.y *= ma.y; vA.z *= ma.z; vA.w *= ma.w;
+        vB.x *= mb.x; vB.y *= mb.y; vB.z *= mb.z; vB.w *= mb.w;
+      }
+      vA.x += rcA.x; vA.y += rcA.y; vA.z += rcA.z; vA.w += rcA.w;
+      vB.x += rcB.x; vB.y += rcB.y; vB.z += rcB.z; vB.w += rcB.w;
+      if (rA < p.M) *reinterpret_cast<float4*>(p.out + (size_t)rA * p.ld_out + col) = vA;
+      if (rB < p.M) *reinterpret_cast<float4*>(p.out + (size_t)rB * p.ld_out + col) = vB;
+      if (p.dn_drop_p > 0.f) {
+        const float4 ma = tc_drop4(seed_dn, p.dn_offset + cA * dim + col, p.dn_drop_p, keep_dn);
+        const float4 mb = tc_drop4(seed_dn, p.dn_offset + cB * dim + col, p.dn_drop_p, keep_dn);
+        vA.x *= ma.x; vA.y *= ma.y; vA.z *= ma.z; vA.w *= ma.w;
+        vB.x *= mb.x; vB.y *= mb.y; vB.z *= mb.z; vB.w *= mb.w;
+      }
+      // the output rows are tc_down's A fragments (k slot t <-> column 4t, t+4 <-> 4t+1; second MMA 4t+2 / 4t+3)
+      const uint32_t ax = f2tf32(vA.x), ay = f2tf32(vA.y), az = f2tf32(vA.z), aw = f2tf32(vA.w);
+      const uint32_t bx = f2tf32(vB.x), by = f2tf32(vB.y), bz = f2tf32(vB.z), bw = f2tf32(vB.w);
+#pragma unroll
+      for (int j = 0; j < KS; ++j) {
+        const float4 w = *reinterpret_cast<const float4*>(sWd + (8 * j + g) * SD + col);
+        mma_tf32(oacc[j], ax, bx, ay, by, __float_as_uint(w.x), __float_as_uint(w.y));
+        mma_tf32(oacc[j], az, bz, aw, bw, __float_as_uint(w.z), __float_as_uint(w.w));
+      }
+    }
+    cp_async_commit();
+    float* zb = zbuf + buf * L::kZ;
+#pragma unroll
+    for (int j = 0; j < KS; ++j) {
+      *reinterpret_cast<float2*>(zb + (warp * 16 + g) * RP + 8 * j + 2 * t) = make_float2(oacc[j][0], oacc[j][1]);
+      *reinterpret_cast<float2*>(zb + (warp * 16 + g + 8) * RP + 8 * j + 2 * t) = make_float2(oacc[j][2], oacc[j][3]);
+    }
+    __syncthreads();
+    for (int idx = tid; idx < 16 * RP; idx += kTcThreads) {
+      const int row = idx / RP, n = idx - row * RP, m = tile * 16 + row;
+      float z = 0.f;
+#pragma unroll
+      for (int w = 0; w < kTcWarps; ++w) z += zb[w * 16 * RP + idx];
+      if (n < p.r2 && m < p.M) {
+        z += s_bd[n];
+        if (p.pre) p.pre[(size_t)m * p.ldz + n] = z;
+        if (p.act == GVK_ROWACT_QUICKGELU) z = quick_gelu(z);
+        else if (p.act == GVK_ROWACT_RELU) z = fmaxf(z, 0.f);
+        p.z[(size_t)m * p.ldz + n] = z;
+      }
+    }
+    if (has_next) cur = nxt;
+  }
+  cp_async_wait<0>();
+}
+
+template <int NITER>
+static int up_down_launch(const gvk_rowproj_up_down_params* p, cudaStream_t stream) {
+  constexpr size_t smem = UpDown<NITER>::kSmem;
+  static_assert(smem <= 227 * 1024, "rowproj_up_down: shared memory");
+  static const int attr = cudaFuncSetAttribute(up_down_tc_kernel<NITER>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (attr != cudaSuccess) return cuda_status((cudaError_t)attr, "rowproj_up_down (smem attribute)");
+  const int ntiles = (p->M + 15) / 16;
+  up_down_tc_kernel<NITER><<<std::max(1, std::min(ntiles, sm_count())), kTcThreads, smem, stream>>>(*p);
+  GVK_CHECK_LAUNCH("rowproj_up_down");
+  return GVK_OK;
+}
+
+int rowproj_up_down(const gvk_rowproj_up_down_params* p, cudaStream_t stream) {
+  GVK_CHECK_ARG(p && p->c && p->w && p->out && p->w2 && p->z && p->M > 0, "gvk_rowproj_up_down: null pointer");
+  GVK_CHECK_ARG(p->dim == 384 || p->dim == 768, "gvk_rowproj_up_down: dim %d (384 or 768)", p->dim);
+  GVK_CHECK_ARG(p->r >= 1 && p->r <= 24 && p->r2 >= 1 && p->r2 <= 24, "gvk_rowproj_up_down: r=%d r2=%d (1..24)", p->r, p->r2);
+  GVK_CHECK_ARG((reinterpret_cast<uintptr_t>(p->out) & 15) == 0 && p->ld_out % 4 == 0 && (!p->res || ((reinterpret_cast<uintptr_t>(p->res) & 15) == 0 && p->ld_res % 4 == 0)),
+                "gvk_rowproj_up_down: out / res must be 16-byte aligned with leading dimensions multiples of 4");
+  GVK_CHECK_ARG(p->up_offset % 4 == 0 && p->dn_offset % 4 == 0, "gvk_rowproj_up_down: dropout offsets must be multiples of 4");
+  return p->dim == 384 ? up_down_launch<6>(p, stream) : up_down_launch<12>(p, stream);
+}
+
 }  // namespace gvk

@@ -247,7 +247,12 @@ class GavikoEngine:
             seed_a, seed_p = self._seed(i, 1), self._seed(i, 2)
             ctx_l, lse_l = ops.attn_simt_fwd(d['z2'], B, N, 1, r_l, q_off=0, k_off=r_l, v_off=2 * r_l, scale=dim ** -0.5,
                                              window=c['local_k'], grid=c['DHW'], drop_p=drop_attn, seed=seed_a, prec=pr)
-            loc_new = ops.rowproj_up(ctx_l, La['wu'], La['bu'], res=loc, drop_p=drop_proj, seed=seed_p, prec=pr)
+            fuse_ud = ops.rowproj_up_down_supported(dim, r_l, Fu['wd'].shape[0], pr)
+            if fuse_ud:      # proj_up + proj_drop + residual and Awakening_Prompt.proj_down of the new local stream: one pass over the stream
+                loc_new, dl = ops.rowproj_up_down(ctx_l, La['wu'], La['bu'], res=loc, up_drop_p=drop_proj, up_seed=seed_p, w2=Fu['wd'], bias2=Fu['bd'],
+                                                  act=ops.ROWACT_QUICKGELU, save_pre=save)
+            else:
+                loc_new = ops.rowproj_up(ctx_l, La['wu'], La['bu'], res=loc, drop_p=drop_proj, seed=seed_p, prec=pr)
             # ---- frozen MHSA (model/vision_transformer.py:60-72, residual gaviko.py:302)
             h1, mean1, rstd1 = ops.layernorm_fwd(g, Lw['ln1_w'], Lw['ln1_b'], out_dtype=cdt, save_stats=save)
             qkv = ops.gemm(h1, Lw['wqkv'], out_dtype=cdt)
@@ -261,7 +266,8 @@ class GavikoEngine:
                                                               save_stats=save)
             else:
                 dg = ops.rowproj_down(g_mid, Fu['wd'], Fu['bd'], act=ops.ROWACT_QUICKGELU, save_pre=save, prec=pr)
-            dl = ops.rowproj_down(loc_new, Fu['wd'], Fu['bd'], act=ops.ROWACT_QUICKGELU, save_pre=save, prec=pr)
+            if not fuse_ud:
+                dl = ops.rowproj_down(loc_new, Fu['wd'], Fu['bd'], act=ops.ROWACT_QUICKGELU, save_pre=save, prec=pr)
             comb, ll = dg['z'], dl['z']
             fsaved = ops.prompt_fusion_fwd(comb, ll, Fu['k'], B, T, N, P)      # comb: xl -> combined latent, in place
             # ---- frozen MLP (model/vision_transformer.py:26-38, residual + prompt gaviko.py:304)
@@ -361,7 +367,13 @@ class GavikoEngine:
             dGm = ops.layernorm_bwd(st['g_mid'], Lw['ln2_w'], st['mean2'], st['rstd2'], dy=dH2, dres=dG, dx=None if lp else dH2, dx_lp=dGm_lp, az=du, aw=Fu['wd'], prec=pr)
             del dH2
             # ---- d(loc_out) += dul Wd
-            if dLoc is None:
+            dctx = None
+            if ops.rowproj_up_down_supported(dim, dul.shape[1], r_l, pr):
+                # ... and the dgrad of LocalSelfAttention.proj_up (replayed proj_drop mask) from the rows just updated: one pass over d(loc)
+                dLoc, dd = ops.rowproj_up_down(dul, Fu['wd'], transposed=True, res=dLoc, out=dLoc, w2=La['wu'], transposed2=True,
+                                               dn_drop_p=ctx['drop_proj'], dn_seed=st['seed_p'])
+                dctx = dd['z']
+            elif dLoc is None:
                 dLoc = ops.rowproj_up(dul, Fu['wd'], transposed=True, prec=pr)
             else:
                 ops.rowproj_up(dul, Fu['wd'], transposed=True, res=dLoc, out=dLoc, prec=pr)
@@ -380,7 +392,8 @@ class GavikoEngine:
                 dG = ops.layernorm_bwd(st['g_in'], Lw['ln1_w'], st['mean1'], st['rstd1'], dy=dH1, dres=dGm, dx=dGm if lp else dH1, dx_lp=dG_lp)
             del dGm, dH1
             # ---- local branch backward
-            dctx = ops.rowproj_down(dLoc, La['wu'], transposed=True, drop_p=ctx['drop_proj'], seed=st['seed_p'], prec=pr)['z']
+            if dctx is None:
+                dctx = ops.rowproj_down(dLoc, La['wu'], transposed=True, drop_p=ctx['drop_proj'], seed=st['seed_p'], prec=pr)['z']
             ops.skinny_wgrad(st['ctx_l'], dLoc, dw=gL['wu'], dw_layout='dr', dx_colsum=gL['bu'], drop_p=ctx['drop_proj'], seed=st['seed_p'], prec=pr)
             dqkv_l = ops.attn_simt_bwd(st['qkv_l'], st['ctx_l'], st['lse_l'], dctx, B, N, 1, r_l, q_off=0, k_off=r_l, v_off=2 * r_l, scale=dim ** -0.5,
                                        window=c['local_k'], grid=c['DHW'], drop_p=ctx['drop_attn'], seed=st['seed_a'], prec=pr)

@@ -183,6 +183,39 @@ def rowproj_up(c, w, bias=None, *, transposed=False, res=None, out=None, out_lp=
     return out
 
 
+def rowproj_up_down(c, w, bias=None, *, transposed=False, res=None, out=None, up_drop_p=0.0, up_seed=0, up_offset=0, w2=None, bias2=None, transposed2=False,
+                    act=ROWACT_NONE, save_pre=False, dn_drop_p=0.0, dn_seed=0, dn_offset=0):
+    """rowproj_up then rowproj_down of its output rows in one pass (gvk_rowproj_up_down; bf16 compute mode only): returns (out, dict(z, pre)).
+    `w` / `transposed` as in rowproj_up, `w2` / `transposed2` as in rowproj_down."""
+    M, r = c.shape
+    dim = w.shape[1] if transposed else w.shape[0]
+    if transposed:
+        assert tuple(w.shape) == (r, dim) and w.is_contiguous()
+        sj, sc = dim, 1
+    else:
+        assert tuple(w.shape) == (dim, r) and w.is_contiguous()
+        sj, sc = 1, r
+    r2 = w2.shape[1] if transposed2 else w2.shape[0]
+    sj2, sc2 = _wstrides(w2, r2, dim, transposed2)
+    if out is None:
+        out = torch.empty((M, dim), device=c.device, dtype=torch.float32)
+    z = torch.empty((M, r2), device=c.device, dtype=torch.float32)
+    pre = torch.empty_like(z) if save_pre else None
+    p = S['gvk_rowproj_up_down_params']()
+    _set(p, c=L.ptr(c, torch.float32), ldc=_ld(c), M=M, dim=dim, r=r, w=L.ptr(w, torch.float32), w_sj=sj, w_sc=sc, bias=L.fptr(bias),
+         out=L.ptr(out, torch.float32), ld_out=_ld(out), up_drop_p=up_drop_p, up_seed=up_seed, up_offset=up_offset,
+         w2=L.ptr(w2, torch.float32), w2_sj=sj2, w2_sc=sc2, bias2=L.fptr(bias2), r2=r2, act=act, pre=pre, z=z, ldz=r2,
+         dn_drop_p=dn_drop_p, dn_seed=dn_seed, dn_offset=dn_offset, seed_salt=SEED_SALT)
+    if res is not None:
+        _set(p, res=L.ptr(res, torch.float32), ld_res=_ld(res))
+    L.call('gvk_rowproj_up_down', C.byref(p), L.stream())
+    return out, dict(z=z, pre=pre)
+
+
+def rowproj_up_down_supported(dim, r, r2, prec):
+    return prec == PREC_TF32 and dim in (384, 768) and r <= 24 and r2 <= 24 and not ({'up', 'down'} & _TF32_OFF)
+
+
 def skinny_wgrad(a, x, *, dw=None, dw_layout='rd', da_colsum=None, dx_colsum=None, ln=None, drop_p=0.0, seed=0, offset=0, prec=PREC_FP32, dw_strides=None):
     """dw(j,c) += sum_m a[m,j] f(x[m,c]).  dw_layout 'rd': dw is [r, dim]; 'dr': dw is [dim, r].  Accumulates (zero first)."""
     M, r = a.shape

@@ -168,6 +168,26 @@ typedef struct {
 } gvk_rowproj_up_params;
 int gvk_rowproj_up(const gvk_rowproj_up_params* p, gvk_stream_t stream);
 
+/* gvk_rowproj_up followed by gvk_rowproj_down on the rows it has just produced, in one pass over the [M, dim] stream (bf16 compute mode,
+ * tf32 tensor-core arithmetic for both rank-r products; dim 384 or 768, r and r2 <= 24):
+ *   out[m, c] = res[m, c] + drop_up( sum_j c[m, j] * w(j, c) + bias[c] )
+ *   z[m, k]   = act( sum_c drop_dn(out[m, c]) * w2(k, c) + bias2[k] ),   pre (optional) = the pre-activation.
+ * Forward of a GAViKO layer: LocalSelfAttention.proj_up + proj_drop + residual (model/gaviko.py:242-243, 301), then Awakening_Prompt.proj_down
+ * of the new local stream (model/gaviko.py:155-156).  Backward: d(loc) += d(ul) Wd, then the dgrad of proj_up with the replayed proj_drop
+ * mask.  Both dropout masks follow gvk_rowproj_up's rule (element index = offset + m * dim + c; offsets multiples of 4).  out may alias res. */
+typedef struct {
+  const float* c; int ldc; int M, dim, r;
+  const float* w; int w_sj, w_sc; const float* bias;
+  const float* res; int ld_res;
+  float* out; int ld_out;
+  float up_drop_p; uint64_t up_seed; uint64_t up_offset;
+  const float* w2; int w2_sj, w2_sc; const float* bias2; int r2; int act;
+  float* pre; float* z; int ldz;
+  float dn_drop_p; uint64_t dn_seed; uint64_t dn_offset;
+  const uint64_t* seed_salt;
+} gvk_rowproj_up_down_params;
+int gvk_rowproj_up_down(const gvk_rowproj_up_down_params* p, gvk_stream_t stream);
+
 /* Rank-r weight gradient:  dw(j, c) += sum_m a[m, j] * f(x[m, c]);  da_colsum[j] += sum_m a[m, j];  dx_colsum[c] += sum_m f(x[m, c]).
  * f = optional dropout mask, then optional LayerNorm recomputed from saved mean / rstd.  Outputs ACCUMULATE (zero them first).
  * Deterministic two-stage reduction (per-CTA partials in `ws`, then one reduce launch): `ws` must hold at least

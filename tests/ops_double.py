@@ -144,6 +144,17 @@ def rowproj_up(c, w, bias=None, *, transposed=False, res=None, out=None, out_lp=
     return out
 
 
+def rowproj_up_down(c, w, bias=None, *, transposed=False, res=None, out=None, up_drop_p=0.0, up_seed=0, up_offset=0, w2=None, bias2=None, transposed2=False,
+                    act=ROWACT_NONE, save_pre=False, dn_drop_p=0.0, dn_seed=0, dn_offset=0):
+    out = rowproj_up(c, w, bias, transposed=transposed, res=res, out=out, drop_p=up_drop_p, seed=up_seed, offset=up_offset)
+    d = rowproj_down(out, w2, bias2, transposed=transposed2, act=act, save_pre=save_pre, drop_p=dn_drop_p, seed=dn_seed, offset=dn_offset)
+    return out, dict(z=d['z'], pre=d['pre'])
+
+
+def rowproj_up_down_supported(dim, r, r2, prec):
+    return prec == PREC_TF32 and dim in (384, 768) and r <= 24 and r2 <= 24
+
+
 def skinny_wgrad(a, x, *, dw=None, dw_layout='rd', da_colsum=None, dx_colsum=None, ln=None, drop_p=0.0, seed=0, offset=0, prec=PREC_FP32, dw_strides=None):
     k = _keep(x.shape, drop_p, seed, offset)
     fx = x if k is None else x * k

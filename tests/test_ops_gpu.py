@@ -221,6 +221,51 @@ def test_layernorm_fwd_down_one_pass(M, dim, r, save):
     close(d2['z'], x.double() @ w.double().t(), 3e-3)
 
 
+@pytest.mark.parametrize('M,dim', [(1000, 768), (16 * 148 * 2 + 3, 768), (517, 384), (9, 768)])
+def test_rowproj_up_down_one_pass(M, dim):
+    """gvk_rowproj_up_down against the two kernels it replaces (same tf32 arithmetic, same dropout masks): forward form (bias, proj_drop,
+    residual, QuickGELU down-projection) and backward form (in place over the residual, replayed mask in front of the down-projection)."""
+    torch.manual_seed(M + dim)
+    r, p = 20, 0.2
+    c = torch.randn(M, r, device=DEV)
+    wu = torch.randn(dim, r, device=DEV) / r ** 0.5          # nn.Linear(r, dim).weight
+    bu = torch.randn(dim, device=DEV) * 0.1
+    wd = torch.randn(r, dim, device=DEV) / dim ** 0.5        # nn.Linear(dim, r).weight
+    bd = torch.randn(r, device=DEV) * 0.1
+    res = torch.randn(M, dim, device=DEV)
+    for drop in (0.0, p):
+        n0 = ops.L.launch_count()
+        out, d = ops.rowproj_up_down(c, wu, bu, res=res, up_drop_p=drop, up_seed=11, w2=wd, bias2=bd, act=ops.ROWACT_QUICKGELU, save_pre=True)
+        assert ops.L.launch_count() == n0 + 1
+        ref = ops.rowproj_up(c, wu, bu, res=res, drop_p=drop, seed=11, prec=ops.PREC_TF32)
+        close(out, ref, 1e-6)                                  # same MMAs, same mask (an FMA contraction apart at most)
+        assert torch.equal(out == res, ref == res)             # the same elements dropped
+        rd = ops.rowproj_down(ref, wd, bd, act=ops.ROWACT_QUICKGELU, save_pre=True, prec=ops.PREC_TF32)
+        close(d['pre'], rd['pre'], 1e-4)                       # same tf32 products, different summation order over the columns
+        close(d['z'], rd['z'], 1e-4)
+        if drop == 0.0:
+            want = res.double() + c.double() @ wu.double().t() + bu.double()
+            close(out, want, 3e-3)
+            pre = want @ wd.double().t() + bd.double()
+            close(d['pre'], pre, 3e-3)
+            close(d['z'], pre * torch.sigmoid(1.702 * pre), 3e-3)
+    # backward form: d(loc) += dul Wd in place, then dctx = mask(d(loc)) Wu with the forward's mask (seed 11)
+    dul = torch.randn(M, r, device=DEV)
+    dloc = torch.randn(M, dim, device=DEV)
+    ref = ops.rowproj_up(dul, wd, transposed=True, res=dloc, prec=ops.PREC_TF32)
+    rd = ops.rowproj_down(ref, wu, transposed=True, drop_p=p, seed=11, prec=ops.PREC_TF32)
+    buf = dloc.clone()
+    out, d = ops.rowproj_up_down(dul, wd, transposed=True, res=buf, out=buf, w2=wu, transposed2=True, dn_drop_p=p, dn_seed=11)
+    assert out.data_ptr() == buf.data_ptr() and d['pre'] is None
+    close(out, ref, 1e-6)
+    close(d['z'], rd['z'], 1e-4)
+    # no residual (first iteration of the backward loop)
+    out0, d0 = ops.rowproj_up_down(dul, wd, transposed=True, w2=wu, transposed2=True)
+    ref0 = ops.rowproj_up(dul, wd, transposed=True, prec=ops.PREC_TF32)
+    close(out0, ref0, 1e-6)
+    close(d0['z'], ops.rowproj_down(ref0, wu, transposed=True, prec=ops.PREC_TF32)['z'], 1e-4)
+
+
 @pytest.mark.parametrize('prec', [ops.PREC_FP32, ops.PREC_TF32])
 def test_rowproj_dropout_replay(prec):
     """The forward mask of rowproj_up is replayed by rowproj_down / skinny_wgrad in backward (same mask in both precisions)."""
@@ -284,6 +329,12 @@ def test_small_ops():
     dw5 = torch.zeros(60, 20, device=DEV)
     ops.small_wgrad(views[:, :60], views[:, 80:], dw5)
     close(dw5, views[:, :60].double().t() @ views[:, 80:].double(), 1e-4)
+    x = torch.randn(77, 192, device=DEV)
+    assert torch.equal(ops.cast_bf16(x), x.bfloat16())
+    dy, pre = torch.randn(M, 20, device=DEV), torch.randn(M, 20, device=DEV)
+    pr = pre.double().requires_grad_(True)
+    (pr * torch.sigmoid(1.702 * pr)).backward(dy.double())
+    close(ops.quickgelu_bwd(dy, pre), pr.grad)
 
 
 @pytest.mark.parametrize('width', [64, 60, 72])
@@ -302,12 +353,6 @@ def test_split_pack_bf16_rule(width):
             want[:, slot * r:(slot + 1) * r] = lo if (pattern >> slot) & 1 else hi
         assert torch.equal(big[:, 128:], want)
         assert (big[:, :128] == 7.0).all()
-    x = torch.randn(77, 192, device=DEV)
-    assert torch.equal(ops.cast_bf16(x), x.bfloat16())
-    dy, pre = torch.randn(M, 20, device=DEV), torch.randn(M, 20, device=DEV)
-    pr = pre.double().requires_grad_(True)
-    (pr * torch.sigmoid(1.702 * pr)).backward(dy.double())
-    close(ops.quickgelu_bwd(dy, pre), pr.grad)
 
 
 def _dense_attn_ref(qkv, B, T, H, D, scale, allow=None):
