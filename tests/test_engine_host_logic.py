@@ -51,6 +51,45 @@ def test_variant_engine_host_logic(name, tmp_path, monkeypatch):
     _check(model, kw, batch, load_golden(name))
 
 
+def test_gaviko_bf16_mode_fused_side_passes_host_logic(monkeypatch):
+    """bf16 compute mode at dim 768 takes the one-pass forms (gvk_layernorm_fwd_down, gvk_rowproj_up_down, gvk_layernorm_bwd with an output
+    projection).  On the double each of them is the composition of the kernels it replaces, so the step with and without them must agree to
+    rounding: a wrong layer's weights, a stale d(comb) or a missed in-place update in the engine shows up here without a GPU."""
+    kw, batch = GAVIKO_CASES['gaviko_t16_small']
+    kw = dict(kw, backbone='vit-b16')                      # dim 768, 12 layers, share_factor 2; 64 + 9 tokens
+    img = golden_volume(batch, kw['frames'], kw['image_size'], kw['image_size'], channels=kw['channels'])
+    y = golden_labels(batch, kw['num_classes'])
+
+    def run(fused):
+        with contextlib.redirect_stdout(io.StringIO()):
+            from gaviko_b200.model.gaviko import Gaviko
+            model = Gaviko(**kw, compute_dtype='bf16')
+        golden_fill(model, seed=0)
+        model.eval()
+        calls = []
+        with monkeypatch.context() as mp:
+            for n in ('layernorm_fwd_down', 'rowproj_up_down', 'layernorm_bwd'):
+                f = getattr(ops_double, n)
+                mp.setattr(ops_double, n, (lambda f, n: lambda *a, **k: (calls.append((n, 'ow' in k and k['ow'] is not None)), f(*a, **k))[1])(f, n))
+            if not fused:
+                for n in ('layernorm_fwd_down_supported', 'layernorm_bwd_down_supported', 'rowproj_up_down_supported'):
+                    mp.setattr(ops_double, n, lambda *a, **k: False)
+            with ops_double.install():
+                logits = model(img)
+                CrossEntropyLoss()(logits, y).backward()
+        return logits.detach(), {n: p.grad.clone() for n, p in model.named_parameters() if p.requires_grad}, calls
+
+    l1, g1, c1 = run(True)
+    l0, g0, c0 = run(False)
+    depth = 12
+    assert c1.count(('layernorm_fwd_down', False)) == depth and c1.count(('rowproj_up_down', False)) == 2 * depth
+    assert c1.count(('layernorm_bwd', True)) == depth - 1          # every LayerNorm1 backward but layer 0's projects its output for the next iteration
+    assert not any(n in ('layernorm_fwd_down', 'rowproj_up_down') or ow for n, ow in c0)
+    assert rel_l2(l1, l0) < 1e-6
+    for n in g1:
+        assert rel_l2(g1[n], g0[n]) < 1e-5, n
+
+
 def test_double_is_not_reachable_without_install():
     """The double only exists inside `install()`: outside it a CPU tensor still raises (no CPU fallback)."""
     from gaviko_b200._lib import GvkError
