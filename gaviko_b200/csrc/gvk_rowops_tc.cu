@@ -1219,19 +1219,33 @@ int layernorm_fwd_down(const gvk_layernorm_fwd_down_params* p, cudaStream_t stre
 // proj_drop mask.  As two kernels the 197 MB stream is written and read again.  CTA layout of ln_bwd_tc_kernel: 16 rows per step, warp w
 // owns columns [w dim/8, (w+1) dim/8); res of the next step travels by cp.async into thread-private slots; the output registers of the
 // up-projection (tc_up's C fragments) are tc_down's A fragments; per-warp partial products meet in shared memory (one barrier per step).
+// 8 streaming warps + 8 helper warps (masks of the next step, output sums of the finished one), see the kernel.
 // =================================================================================================
 template <int NITER>
 struct UpDown {
   static constexpr int dim = NITER * 64, SU = dim + 8, SD = dim + 16, GW = NITER / 2, RP = 24, KS = 3;
   static constexpr int kSlots = GW * 2 * kTcThreads;
   static constexpr int kZ = kTcWarps * 16 * RP;
-  static constexpr size_t kSmem = ((size_t)RP * SU + (size_t)RP * SD + dim + RP) * sizeof(float) + 2 * (size_t)kZ * sizeof(float) + (size_t)kSlots * sizeof(float4);
+  static constexpr int kMaskHalves = (GW + 1) / 2;          // 16-bit words of one thread's mask nibbles (rows g / g+8 of GW column groups)
+  static constexpr size_t kSmem = ((size_t)RP * SU + (size_t)RP * SD + dim + RP) * sizeof(float) + 2 * (size_t)kZ * sizeof(float) + (size_t)kSlots * sizeof(float4) +
+                                  2 * (size_t)kMaskHalves * kTcThreads * sizeof(uint16_t);
 };
 
+// keep bits of the 4 consecutive elements starting at e (e % 4 == 0) under gvk_rowproj_up's mask rule: bit i = 1 iff element e + i is kept.
+// u32_to_unit(r) >= p  <=>  (r >> 8) >= ceil(p 2^24)  (both sides are exact in fp32), i.e. r >= thr with thr = ceil(p 2^24) << 8.
+__device__ __forceinline__ uint32_t tc_keep4(uint64_t seed, uint64_t e, uint32_t thr) {
+  const uint64_t ctr = e >> 2;
+  const uint4 r = philox4x32(make_uint4((uint32_t)ctr, (uint32_t)(ctr >> 32), 0u, 0u), make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+  return (r.x >= thr ? 1u : 0u) | (r.y >= thr ? 2u : 0u) | (r.z >= thr ? 4u : 0u) | (r.w >= thr ? 8u : 0u);
+}
+
+// 16 warps: warps 0-7 stream and multiply as described above; warps 8-15 produce the dropout mask of the NEXT step (one Philox call per four
+// elements — ~100 instructions that the 8 streaming warps could not hide at two warps per scheduler: 155 us per launch with the calls in line)
+// as nibbles in shared memory, and sum the partial products of the finished step after the step's barrier.
 template <int NITER>
-__global__ void __launch_bounds__(kTcThreads, 1) up_down_tc_kernel(gvk_rowproj_up_down_params p) {
+__global__ void __launch_bounds__(2 * kTcThreads, 1) up_down_tc_kernel(gvk_rowproj_up_down_params p) {
   using L = UpDown<NITER>;
-  constexpr int dim = L::dim, SU = L::SU, SD = L::SD, GW = L::GW, RP = L::RP, KS = L::KS;
+  constexpr int dim = L::dim, SU = L::SU, SD = L::SD, GW = L::GW, RP = L::RP, KS = L::KS, MH = L::kMaskHalves;
   extern __shared__ __align__(16) float smem[];
   float* sWu = smem;                                      // [RP][SU] up panel, two low column bits of every 16-column group swapped
   float* sWd = sWu + RP * SU;                             // [RP][SD] down panel (tc_down's layout)
@@ -1239,9 +1253,16 @@ __global__ void __launch_bounds__(kTcThreads, 1) up_down_tc_kernel(gvk_rowproj_u
   float* s_bd = s_bu + dim;                               // [RP]
   float* zbuf = s_bd + RP;                                // [2][kTcWarps][16][RP]
   float4* s_r = reinterpret_cast<float4*>(zbuf + 2 * L::kZ);   // [GW][2][kTcThreads]
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
-  const uint64_t seed_up = salted_seed(p.up_seed, p.seed_salt), seed_dn = salted_seed(p.dn_seed, p.seed_salt);
-  const float keep_up = p.up_drop_p > 0.f ? 1.0f / (1.0f - p.up_drop_p) : 1.f, keep_dn = p.dn_drop_p > 0.f ? 1.0f / (1.0f - p.dn_drop_p) : 1.f;
+  uint16_t* s_mk = reinterpret_cast<uint16_t*>(s_r + L::kSlots);   // [2][MH][kTcThreads] mask nibbles (byte kk: low = row g, high = row g + 8)
+  const bool producer = threadIdx.x >= kTcThreads;
+  const int tid = threadIdx.x & (kTcThreads - 1), warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;   // producer thread i mirrors streaming thread i
+  // one mask comes from the producer warps: the up mask if there is one, else the down mask; a launch with both computes the second in line
+  const bool mk_up = p.up_drop_p > 0.f, mk_dn = !mk_up && p.dn_drop_p > 0.f, dn_inline = mk_up && p.dn_drop_p > 0.f;
+  const float mk_p = mk_up ? p.up_drop_p : p.dn_drop_p;
+  const uint64_t mk_seed = salted_seed(mk_up ? p.up_seed : p.dn_seed, p.seed_salt), mk_off = mk_up ? p.up_offset : p.dn_offset;
+  const uint32_t mk_thr = (uint32_t)ceilf(mk_p * 16777216.0f) << 8;
+  const float keep_up = mk_up ? 1.0f / (1.0f - p.up_drop_p) : 1.f, keep_dn = p.dn_drop_p > 0.f ? 1.0f / (1.0f - p.dn_drop_p) : 1.f;
+  const uint64_t seed_dn = salted_seed(p.dn_seed, p.seed_salt);
   const int ntiles = (p.M + 15) / 16;
   const int cw = warp * 16 * GW + 4 * t;
   auto slot = [&](int kk, int row) { return (kk * 2 + row) * kTcThreads + tid; };
@@ -1249,6 +1270,17 @@ __global__ void __launch_bounds__(kTcThreads, 1) up_down_tc_kernel(gvk_rowproj_u
     const size_t cA = (size_t)min(tile * 16 + g, p.M - 1), cB = (size_t)min(tile * 16 + g + 8, p.M - 1);
     cp_async16(s_r + slot(kk, 0), p.res + cA * p.ld_res + cw + 16 * kk);
     cp_async16(s_r + slot(kk, 1), p.res + cB * p.ld_res + cw + 16 * kk);
+  };
+  auto make_masks = [&](int tile, int b) {
+    const size_t cA = (size_t)min(tile * 16 + g, p.M - 1), cB = (size_t)min(tile * 16 + g + 8, p.M - 1);
+    uint32_t by[2 * MH];
+#pragma unroll
+    for (int kk = 0; kk < 2 * MH; ++kk) {
+      by[kk] = 0u;
+      if (kk < GW) by[kk] = tc_keep4(mk_seed, mk_off + cA * dim + cw + 16 * kk, mk_thr) | (tc_keep4(mk_seed, mk_off + cB * dim + cw + 16 * kk, mk_thr) << 4);
+    }
+#pragma unroll
+    for (int h = 0; h < MH; ++h) s_mk[(b * MH + h) * kTcThreads + tid] = (uint16_t)(by[2 * h] | (by[2 * h + 1] << 8));
   };
   struct Lat { float v[KS][4]; };
   auto load_lat = [&](int tile, Lat& T) {
@@ -1263,25 +1295,49 @@ __global__ void __launch_bounds__(kTcThreads, 1) up_down_tc_kernel(gvk_rowproj_u
     }
   };
   Lat cur;
-  if ((int)blockIdx.x < ntiles) {
-    if (p.res) {
+  if (!producer) {
+    if ((int)blockIdx.x < ntiles) {
+      if (p.res) {
 #pragma unroll
-      for (int kk = 0; kk < GW; ++kk) fetch_r(blockIdx.x, kk);
+        for (int kk = 0; kk < GW; ++kk) fetch_r(blockIdx.x, kk);
+      }
+      load_lat(blockIdx.x, cur);
     }
-    load_lat(blockIdx.x, cur);
+    cp_async_commit();
+    tc_stage_panel<RP, SU, true>(sWu, p.w, p.r, dim, p.w_sj, p.w_sc, nullptr);
+    tc_stage_panel<RP, SD, false>(sWd, p.w2, p.r2, dim, p.w2_sj, p.w2_sc, nullptr);
+    for (int c = tid; c < dim; c += kTcThreads) s_bu[c] = p.bias ? p.bias[c] : 0.f;
+    if (tid < RP) s_bd[tid] = (p.bias2 && tid < p.r2) ? p.bias2[tid] : 0.f;
+  } else if ((mk_up || mk_dn) && (int)blockIdx.x < ntiles) {
+    make_masks(blockIdx.x, 0);
   }
-  cp_async_commit();
-  tc_stage_panel<RP, SU, true>(sWu, p.w, p.r, dim, p.w_sj, p.w_sc, nullptr);
-  tc_stage_panel<RP, SD, false>(sWd, p.w2, p.r2, dim, p.w2_sj, p.w2_sc, nullptr);
-  for (int c = tid; c < dim; c += kTcThreads) s_bu[c] = p.bias ? p.bias[c] : 0.f;
-  if (tid < RP) s_bd[tid] = (p.bias2 && tid < p.r2) ? p.bias2[tid] : 0.f;
   __syncthreads();
   int buf = 0;
   for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, buf ^= 1) {
-    const int rA = tile * 16 + g, rB = rA + 8;
-    const size_t cA = (size_t)min(rA, p.M - 1), cB = (size_t)min(rB, p.M - 1);
     const int next = tile + gridDim.x;
     const bool has_next = next < ntiles;
+    float* zb = zbuf + buf * L::kZ;
+    if (producer) {
+      if ((mk_up || mk_dn) && has_next) make_masks(next, buf ^ 1);
+      __syncthreads();
+      // ---- z rows of the finished step: sum of the 8 streaming warps' partial products
+      for (int idx = tid; idx < 16 * RP; idx += kTcThreads) {
+        const int row = idx / RP, n = idx - row * RP, m = tile * 16 + row;
+        float z = 0.f;
+#pragma unroll
+        for (int w = 0; w < kTcWarps; ++w) z += zb[w * 16 * RP + idx];
+        if (n < p.r2 && m < p.M) {
+          z += s_bd[n];
+          if (p.pre) p.pre[(size_t)m * p.ldz + n] = z;
+          if (p.act == GVK_ROWACT_QUICKGELU) z = quick_gelu(z);
+          else if (p.act == GVK_ROWACT_RELU) z = fmaxf(z, 0.f);
+          p.z[(size_t)m * p.ldz + n] = z;
+        }
+      }
+      continue;
+    }
+    const int rA = tile * 16 + g, rB = rA + 8;
+    const size_t cA = (size_t)min(rA, p.M - 1), cB = (size_t)min(rB, p.M - 1);
     Lat nxt;
     if (has_next) load_lat(next, nxt);
     uint32_t a[KS][4];
@@ -1292,10 +1348,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) up_down_tc_kernel(gvk_rowproj_u
     float oacc[KS][4];
 #pragma unroll
     for (int j = 0; j < KS; ++j) oacc[j][0] = oacc[j][1] = oacc[j][2] = oacc[j][3] = 0.f;
+    uint32_t mk[MH];
+#pragma unroll
+    for (int h = 0; h < MH; ++h) mk[h] = (mk_up || mk_dn) ? s_mk[(buf * MH + h) * kTcThreads + tid] : 0xFFFFu;
     cp_async_wait<0>();
 #pragma unroll
     for (int kk = 0; kk < GW; ++kk) {
       const int col = cw + 16 * kk;
+      const uint32_t nib = mk[kk >> 1] >> (8 * (kk & 1));   // bits 0-3: row g, bits 4-7: row g + 8
       float4 rcA = make_float4(0.f, 0.f, 0.f, 0.f), rcB = rcA;
       if (p.res) {
         rcA = s_r[slot(kk, 0)];
@@ -1313,17 +1373,18 @@ __global__ void __launch_bounds__(kTcThreads, 1) up_down_tc_kernel(gvk_rowproj_u
       const float4 bias = *reinterpret_cast<const float4*>(s_bu + col);
       float4 vA = make_float4(d0[0] + bias.x, d0[1] + bias.y, d1[0] + bias.z, d1[1] + bias.w);
       float4 vB = make_float4(d0[2] + bias.x, d0[3] + bias.y, d1[2] + bias.z, d1[3] + bias.w);
-      if (p.up_drop_p > 0.f) {
-        const float4 ma = tc_drop4(seed_up, p.up_offset + cA * dim + col, p.up_drop_p, keep_up);
-        const float4 mb = tc_drop4(seed_up, p.up_offset + cB * dim + col, p.up_drop_p, keep_up);
-        vA.x *= ma.x; vA.y *= ma.y; vA.z *= ma.z; vA.w *= ma.w;
-        vB.x *= mb.x; vB.y *= mb.y; vB.z *= mb.z; vB.w *= mb.w;
+      if (mk_up) {
+        vA.x *= (nib & 1u) ? keep_up : 0.f; vA.y *= (nib & 2u) ? keep_up : 0.f; vA.z *= (nib & 4u) ? keep_up : 0.f; vA.w *= (nib & 8u) ? keep_up : 0.f;
+        vB.x *= (nib & 16u) ? keep_up : 0.f; vB.y *= (nib & 32u) ? keep_up : 0.f; vB.z *= (nib & 64u) ? keep_up : 0.f; vB.w *= (nib & 128u) ? keep_up : 0.f;
       }
       vA.x += rcA.x; vA.y += rcA.y; vA.z += rcA.z; vA.w += rcA.w;
       vB.x += rcB.x; vB.y += rcB.y; vB.z += rcB.z; vB.w += rcB.w;
       if (rA < p.M) *reinterpret_cast<float4*>(p.out + (size_t)rA * p.ld_out + col) = vA;
       if (rB < p.M) *reinterpret_cast<float4*>(p.out + (size_t)rB * p.ld_out + col) = vB;
-      if (p.dn_drop_p > 0.f) {
+      if (mk_dn) {
+        vA.x *= (nib & 1u) ? keep_dn : 0.f; vA.y *= (nib & 2u) ? keep_dn : 0.f; vA.z *= (nib & 4u) ? keep_dn : 0.f; vA.w *= (nib & 8u) ? keep_dn : 0.f;
+        vB.x *= (nib & 16u) ? keep_dn : 0.f; vB.y *= (nib & 32u) ? keep_dn : 0.f; vB.z *= (nib & 64u) ? keep_dn : 0.f; vB.w *= (nib & 128u) ? keep_dn : 0.f;
+      } else if (dn_inline) {
         const float4 ma = tc_drop4(seed_dn, p.dn_offset + cA * dim + col, p.dn_drop_p, keep_dn);
         const float4 mb = tc_drop4(seed_dn, p.dn_offset + cB * dim + col, p.dn_drop_p, keep_dn);
         vA.x *= ma.x; vA.y *= ma.y; vA.z *= ma.z; vA.w *= ma.w;
@@ -1340,29 +1401,15 @@ __global__ void __launch_bounds__(kTcThreads, 1) up_down_tc_kernel(gvk_rowproj_u
       }
     }
     cp_async_commit();
-    float* zb = zbuf + buf * L::kZ;
 #pragma unroll
     for (int j = 0; j < KS; ++j) {
       *reinterpret_cast<float2*>(zb + (warp * 16 + g) * RP + 8 * j + 2 * t) = make_float2(oacc[j][0], oacc[j][1]);
       *reinterpret_cast<float2*>(zb + (warp * 16 + g + 8) * RP + 8 * j + 2 * t) = make_float2(oacc[j][2], oacc[j][3]);
     }
     __syncthreads();
-    for (int idx = tid; idx < 16 * RP; idx += kTcThreads) {
-      const int row = idx / RP, n = idx - row * RP, m = tile * 16 + row;
-      float z = 0.f;
-#pragma unroll
-      for (int w = 0; w < kTcWarps; ++w) z += zb[w * 16 * RP + idx];
-      if (n < p.r2 && m < p.M) {
-        z += s_bd[n];
-        if (p.pre) p.pre[(size_t)m * p.ldz + n] = z;
-        if (p.act == GVK_ROWACT_QUICKGELU) z = quick_gelu(z);
-        else if (p.act == GVK_ROWACT_RELU) z = fmaxf(z, 0.f);
-        p.z[(size_t)m * p.ldz + n] = z;
-      }
-    }
     if (has_next) cur = nxt;
   }
-  cp_async_wait<0>();
+  if (!producer) cp_async_wait<0>();
 }
 
 template <int NITER>
@@ -1372,7 +1419,7 @@ static int up_down_launch(const gvk_rowproj_up_down_params* p, cudaStream_t stre
   static const int attr = cudaFuncSetAttribute(up_down_tc_kernel<NITER>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (attr != cudaSuccess) return cuda_status((cudaError_t)attr, "rowproj_up_down (smem attribute)");
   const int ntiles = (p->M + 15) / 16;
-  up_down_tc_kernel<NITER><<<std::max(1, std::min(ntiles, sm_count())), kTcThreads, smem, stream>>>(*p);
+  up_down_tc_kernel<NITER><<<std::max(1, std::min(ntiles, sm_count())), 2 * kTcThreads, smem, stream>>>(*p);
   GVK_CHECK_LAUNCH("rowproj_up_down");
   return GVK_OK;
 }
