@@ -697,7 +697,7 @@ bool skinny_wgrad_tc_supported(const gvk_skinny_wgrad_params* p) {
 // the current step is computed: a thread re-fills a slot right after it has read it, so ~120 KB per SM are in flight all the time and no
 // warp waits on a load it has just issued.  (Measured at M = 66 112, dim 768, r 20: exact kernel 238 us; this layout with two CTAs per SM
 // and plain loads 227 us; one CTA with the next step's x / dy prefetched into registers 182 us; this form 156 us; the same with 16 warps of
-// three column groups each 186 us — narrower per-warp row segments cost more than the extra warps hide; profiles/lnbwd_tc_r02*.jsonl.)
+// three column groups each 186 us (cause not isolated: DESIGN.md section 8); profiles/lnbwd_tc_r02*.jsonl.)
 // =================================================================================================
 __device__ __forceinline__ float4 bf16x4_to_float4(uint2 v) {
   const float2 lo = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&v.x));
