@@ -3,8 +3,10 @@
 Purpose: exercise the HOST logic of the engines (``engine.py``, ``vit_engine.py``, ``dvpt_engine.py``: call order, in-place conventions, token /
 row bookkeeping, which gradients go where) in the ``-m "not gpu"`` suite, against the same golden vectors the GPU tests use.  It is test
 infrastructure only: it is installed by monkeypatching the engines' ``ops`` reference (``install()`` below) and never ships — the product path has no
-CPU fallback (``tests/test_dropin_surface.py::test_no_cpu_fallback``).  fp32 mode only; dropout masks are replayable functions of the seed (not the
-kernels' Philox values).
+CPU fallback (``tests/test_dropin_surface.py::test_no_cpu_fallback``).  The arithmetic inside every wrapper is torch fp32 whatever the engine's
+compute mode (bf16 mode: bf16 storage of operands / activations, the hi / lo slot packing and the one-pass forms as compositions of the kernels
+they replace); the one-kernel patch embedding reports 'not taken'.  Dropout masks are replayable functions of the seed (not the kernels' Philox
+values); attention-probability dropout is not emulated.
 """
 import contextlib
 import math
@@ -328,12 +330,15 @@ def attn_simt_bwd(qkv, out, lse, dout, B, T, H, D, *, q_off, k_off, v_off, scale
     return dqkv
 
 
-def mhsa_fwd(qkv, B, T, H, scale):
-    return attn_simt_fwd(qkv, B, T, H, 64, q_off=0, k_off=H * 64, v_off=2 * H * 64, scale=scale)
+def mhsa_fwd(qkv, B, T, H, scale, drop_p=0.0, seed=0):
+    assert drop_p == 0.0, 'ops double: attention dropout is not emulated (the parity cases run with dropout off)'
+    out, lse = attn_simt_fwd(qkv.float(), B, T, H, 64, q_off=0, k_off=H * 64, v_off=2 * H * 64, scale=scale)
+    return out.to(qkv.dtype), lse
 
 
-def mhsa_bwd(qkv, out, lse, dout, B, T, H, scale):
-    return attn_simt_bwd(qkv, out, lse, dout, B, T, H, 64, q_off=0, k_off=H * 64, v_off=2 * H * 64, scale=scale)
+def mhsa_bwd(qkv, out, lse, dout, B, T, H, scale, drop_p=0.0, seed=0):
+    assert drop_p == 0.0, 'ops double: attention dropout is not emulated (the parity cases run with dropout off)'
+    return attn_simt_bwd(qkv.float(), out.float(), lse, dout.float(), B, T, H, 64, q_off=0, k_off=H * 64, v_off=2 * H * 64, scale=scale).to(qkv.dtype)
 
 
 # ---------------------------------------------------------------------------------------------- token assembly

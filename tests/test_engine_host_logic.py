@@ -51,6 +51,40 @@ def test_variant_engine_host_logic(name, tmp_path, monkeypatch):
     _check(model, kw, batch, load_golden(name))
 
 
+@pytest.mark.parametrize('name', ['gaviko_t16_small'] + list(VARIANT_CASES) + list(NEXT_CASES))
+def test_engine_host_logic_bf16_mode(name, tmp_path, monkeypatch):
+    """The bf16-mode branches of the engines (bf16 operands and activations, K-extension operands packed as hi / lo slots, bf16 LayerNorm-output
+    gradients, folded SSF operands) through the double: same bars as the GPU bf16 parity tests (logits 2e-2, identical argmax, gradients 2e-2
+    globally or the reference's own bf16 deviation where that is larger).  The arithmetic inside each wrapper is the double's fp32, so this checks
+    the engines' bookkeeping in that mode, not the kernels."""
+    monkeypatch.chdir(tmp_path)
+    if name in GAVIKO_CASES:
+        kw, batch = GAVIKO_CASES[name]
+        with contextlib.redirect_stdout(io.StringIO()):
+            from gaviko_b200.model.gaviko import Gaviko
+            model = Gaviko(**kw, compute_dtype='bf16')
+    else:
+        method, kw, batch = dict(VARIANT_CASES, **NEXT_CASES)[name]
+        model = build_variant(method, dict(kw, compute_dtype='bf16'))
+    golden_fill(model, seed=0)
+    model.eval()
+    g = load_golden(name)
+    img = golden_volume(batch, kw['frames'], kw['image_size'], kw['image_size'], channels=kw['channels'])
+    y = golden_labels(batch, kw['num_classes'])
+    with ops_double.install():
+        for loss_name, crit in (('focal', FocalLoss(gamma=1.2)), ('ce', CrossEntropyLoss())):
+            model.zero_grad(set_to_none=True)
+            logits = model(img)
+            crit(logits, y).backward()
+            assert rel_l2(logits.detach().float(), g['logits']) < 2e-2
+            assert logits.argmax(1).tolist() == g['logits'].argmax(1).tolist()
+            grads = {n: p.grad for n, p in model.named_parameters() if p.requires_grad}
+            ref_dev = lambda k: float(g[k]) if k in g else 0.0      # noqa: E731
+            tol_g = max(2e-2, 2 * ref_dev(f'refbf16_grad_global_{loss_name}'))
+            tol_t = max(0.15, 2 * ref_dev(f'refbf16_grad_worst_{loss_name}'))
+            grad_parity(grads, g, loss_name, tol_global=tol_g, tol_tensor=tol_t, floor=1e-2, floor_slack=2.0)
+
+
 def test_gaviko_bf16_mode_fused_side_passes_host_logic(monkeypatch):
     """bf16 compute mode at dim 768 takes the one-pass forms (gvk_layernorm_fwd_down, gvk_rowproj_up_down, gvk_layernorm_bwd with an output
     projection).  On the double each of them is the composition of the kernels it replaces, so the step with and without them must agree to
