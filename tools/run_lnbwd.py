@@ -19,6 +19,7 @@ def main():
     ap.add_argument('--batch', type=int, default=64)
     ap.add_argument('--iters', type=int, default=10)
     ap.add_argument('--flush', default='dirty', choices=['dirty', 'clean', 'none'])
+    ap.add_argument('--only', default='', help="'updown': only the up + down pair")
     a = ap.parse_args()
     dim, r, peak = 768, 20, 6550.0
     try:
@@ -27,6 +28,8 @@ def main():
         pass
     dev = 'cuda'
     torch.manual_seed(0)
+    if a.only == 'updown':
+        return updown_pair(a, peak)
     flush = torch.zeros(64 * 1024 * 1024, device=dev)
     gamma = torch.rand(dim, device=dev) + 0.5
     w = torch.randn(r, dim, device=dev) / dim ** 0.5
@@ -57,6 +60,7 @@ def main():
             print(json.dumps(rows[-1]), flush=True)
     forward_pair(a, peak)
     backward_pair(a, peak)
+    updown_pair(a, peak)
 
 
 def backward_pair(a, peak):
@@ -81,6 +85,33 @@ def backward_pair(a, peak):
     for form, (fn, nbytes) in forms.items():
         us = timeit(fn, a.iters, flush, a.flush)
         print(json.dumps(dict(kernel='dG pass + next d(comb)', form=form, M=M, us=round(us, 1), gbps=round(nbytes / us / 1e3, 1),
+                              frac_of_copy_peak=round(nbytes / us / 1e3 / peak, 3), roofline_us=round(nbytes / peak / 1e3, 1))), flush=True)
+
+
+def updown_pair(a, peak):
+    """Local branch: proj_up + proj_drop + residual then Awakening_Prompt.proj_down (forward), d(loc) += d(ul) Wd then the dgrad of proj_up with the
+    replayed mask (backward): two kernels vs gvk_rowproj_up_down."""
+    dev, dim, r, p = 'cuda', 768, 20, 0.2
+    M = a.batch * 1000
+    flush = torch.zeros(64 * 1024 * 1024, device=dev)
+    c = torch.randn(M, r, device=dev)
+    wu, bu = torch.randn(dim, r, device=dev) / r ** 0.5, torch.randn(dim, device=dev) * 0.1
+    wd, bd = torch.randn(r, dim, device=dev) / dim ** 0.5, torch.randn(r, device=dev) * 0.1
+    res, out = torch.randn(M, dim, device=dev), torch.empty(M, dim, device=dev)
+    nb = M * dim * 8
+    forms = {
+        'fwd: rowproj_up (dropout 0.2)': (lambda: ops.rowproj_up(c, wu, bu, res=res, out=out, drop_p=p, seed=3, prec=ops.PREC_TF32), nb),
+        'fwd: rowproj_down (QuickGELU, pre saved)': (lambda: ops.rowproj_down(out, wd, bd, act=ops.ROWACT_QUICKGELU, save_pre=True, prec=ops.PREC_TF32), nb // 2),
+        'fwd: rowproj_up_down (dropout 0.2)': (lambda: ops.rowproj_up_down(c, wu, bu, res=res, out=out, up_drop_p=p, up_seed=3, w2=wd, bias2=bd, act=ops.ROWACT_QUICKGELU,
+                                                                          save_pre=True), nb),
+        'fwd: rowproj_up_down (no dropout: inference)': (lambda: ops.rowproj_up_down(c, wu, bu, res=res, out=out, w2=wd, bias2=bd, act=ops.ROWACT_QUICKGELU), nb),
+        'bwd: rowproj_up (in place)': (lambda: ops.rowproj_up(c, wd, transposed=True, res=res, out=res, prec=ops.PREC_TF32), nb),
+        'bwd: rowproj_down (replayed mask)': (lambda: ops.rowproj_down(res, wu, transposed=True, drop_p=p, seed=3, prec=ops.PREC_TF32), nb // 2),
+        'bwd: rowproj_up_down (in place, replayed mask)': (lambda: ops.rowproj_up_down(c, wd, transposed=True, res=res, out=res, w2=wu, transposed2=True, dn_drop_p=p, dn_seed=3), nb),
+    }
+    for form, (fn, nbytes) in forms.items():
+        us = timeit(fn, a.iters, flush, a.flush)
+        print(json.dumps(dict(kernel='local stream up + down', form=form, M=M, us=round(us, 1), gbps=round(nbytes / us / 1e3, 1),
                               frac_of_copy_peak=round(nbytes / us / 1e3 / peak, 3), roofline_us=round(nbytes / peak / 1e3, 1))), flush=True)
 
 
