@@ -189,6 +189,8 @@ def rowproj_up_down(c, w, bias=None, *, transposed=False, res=None, out=None, up
     `w` / `transposed` as in rowproj_up, `w2` / `transposed2` as in rowproj_down."""
     M, r = c.shape
     dim = w.shape[1] if transposed else w.shape[0]
+    if not (0.0 <= up_drop_p < 1.0 and 0.0 <= dn_drop_p < 1.0):
+        raise GvkError(f'rowproj_up_down: dropout probabilities must be in [0, 1), got {up_drop_p}, {dn_drop_p}')
     if transposed:
         assert tuple(w.shape) == (r, dim) and w.is_contiguous()
         sj, sc = dim, 1
